@@ -1,0 +1,342 @@
+"""ctypes binding of libfvmgpu.so (include/fvmgpu.h) -- the thin layer every Python caller uses.
+
+There is no CPU fallback: if the CUDA library is missing or no device is present the calls
+raise `FvmGpuError` (the analogue of the reference's CException -> RuntimeError, F/baseExt.i:49-59).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfvmgpu.so")
+
+
+class FvmGpuError(RuntimeError):
+    pass
+
+
+# enums of fvmgpu.h
+GROUP_INTERIOR, GROUP_BOUNDARY, GROUP_INTERFACE, GROUP_SYMMETRY = 0, 1, 2, 3
+(BC_DIRICHLET, BC_NEUMANN, BC_EXTRAPOLATION, BC_CONVECTIVE, BC_RADIATIVE, BC_MIXED, BC_INTERFACE,
+ BC_DIRICHLET_OR_OUTFLOW) = range(8)
+(FIELD_X, FIELD_DIFFUSIVITY, FIELD_SOURCE, FIELD_FACE_FLUX, FIELD_X_N1, FIELD_X_N2, FIELD_DENSITY,
+ FIELD_CONT_RESID, FIELD_GRADIENT, FIELD_BFLUX, FIELD_DELTA, FIELD_B) = range(12)
+CYCLE_V, CYCLE_W, CYCLE_F = 0, 1, 2
+SMOOTHER_GAUSS_SEIDEL, SMOOTHER_JACOBI = 0, 1
+
+
+class AssembleOpts(C.Structure):
+    _fields_ = [("diffusion", C.c_int), ("convection", C.c_int), ("source", C.c_int),
+                ("time_order", C.c_int), ("dt", C.c_double), ("underrelax", C.c_double),
+                ("apply_bcs", C.c_int), ("eliminate_boundary", C.c_int)]
+
+
+class AmgOpts(C.Structure):
+    _fields_ = [("nMaxIterations", C.c_int), ("verbosity", C.c_int),
+                ("relativeTolerance", C.c_double), ("absoluteTolerance", C.c_double),
+                ("maxCoarseLevels", C.c_int), ("nPreSweeps", C.c_int), ("nPostSweeps", C.c_int),
+                ("coarseGroupSize", C.c_int), ("weightRatioThreshold", C.c_double),
+                ("cycleType", C.c_int), ("smootherType", C.c_int)]
+
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+_dpn = C.c_void_p  # nullable double*
+_ipn = C.c_void_p  # nullable int*
+
+# name -> (restype, argtypes); every symbol include/fvmgpu.h declares
+SIGNATURES = {
+    "fvmgpu_amg_default_opts": (None, [C.POINTER(AmgOpts)]),
+    "fvmgpu_init": (C.c_int, [C.c_int]),
+    "fvmgpu_shutdown": (C.c_int, []),
+    "fvmgpu_last_error": (C.c_char_p, []),
+    "fvmgpu_version": (C.c_int, []),
+    "fvmgpu_device_info": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "fvmgpu_synchronize": (C.c_int, []),
+    "fvmgpu_timer_start": (C.c_int, [C.c_int]),
+    "fvmgpu_timer_stop": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
+    "fvmgpu_counters": (C.c_int, [C.POINTER(C.c_longlong)] * 3),
+    "fvmgpu_flush_l2": (C.c_int, []),
+    "fvmgpu_mesh_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip,
+                                     C.c_int, _ip, _ip, _ip, _ip]),
+    "fvmgpu_mesh_set_geometry": (C.c_int, [_vp, _dp, _dp, _dpn, _dp, _dp, _ipn]),
+    "fvmgpu_mesh_set_halo": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _ip, _ip]),
+    "fvmgpu_mesh_destroy": (C.c_int, [_vp]),
+    "fvmgpu_mesh_download_pair_to_col": (C.c_int, [_vp, _ip]),
+    "fvmgpu_mesh_download_gradient_weights": (C.c_int, [_vp, _dp]),
+    "fvmgpu_system_create": (C.c_int, [C.POINTER(_vp), _vp]),
+    "fvmgpu_system_create_raw": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]),
+    "fvmgpu_system_destroy": (C.c_int, [_vp]),
+    "fvmgpu_system_set_field": (C.c_int, [_vp, C.c_int, _dp, C.c_longlong]),
+    "fvmgpu_system_fill_field": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "fvmgpu_system_get_field": (C.c_int, [_vp, C.c_int, _dp, C.c_longlong]),
+    "fvmgpu_system_set_bc": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, _dpn]),
+    "fvmgpu_compute_gradient": (C.c_int, [_vp]),
+    "fvmgpu_assemble": (C.c_int, [_vp, C.POINTER(AssembleOpts)]),
+    "fvmgpu_download_system": (C.c_int, [_vp, _dp, _dp, _dp, _ipn]),
+    "fvmgpu_amg_create": (C.c_int, [C.POINTER(_vp), C.POINTER(AmgOpts)]),
+    "fvmgpu_amg_set_opts": (C.c_int, [_vp, C.POINTER(AmgOpts)]),
+    "fvmgpu_amg_solve": (C.c_int, [_vp, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "fvmgpu_amg_smooth": (C.c_int, [_vp, _vp]),
+    "fvmgpu_amg_cleanup": (C.c_int, [_vp]),
+    "fvmgpu_amg_destroy": (C.c_int, [_vp]),
+    "fvmgpu_amg_levels": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int),
+                                    np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"),
+                                    np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), _ip]),
+    "fvmgpu_solver_history": (C.c_int, [_vp, C.c_int, _dp, C.POINTER(C.c_int)]),
+    "fvmgpu_bcgstab_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "fvmgpu_post_solve_update": (C.c_int, [_vp]),
+    "fvmgpu_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "fvmgpu_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p]),
+    "fvmgpu_comm_destroy": (C.c_int, []),
+}
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _nullable(a, dtype):
+    if a is None:
+        return None, None
+    arr = np.ascontiguousarray(a, dtype=dtype)
+    return arr, arr.ctypes.data_as(C.c_void_p)
+
+
+class Lib:
+    """A loaded libfvmgpu.so with typed entry points; `call()` raises FvmGpuError on failure."""
+
+    def __init__(self, path=None):
+        path = path or LIB_PATH
+        if not os.path.exists(path):
+            raise FvmGpuError(
+                "libfvmgpu.so not built (%s). Build it with `python -m fvm_b200.build`; "
+                "there is no CPU fallback." % path)
+        self.path = path
+        self.dll = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(self.dll, name)
+            fn.restype = res
+            fn.argtypes = args
+        self._initialised = False
+
+    def call(self, name, *args):
+        rc = getattr(self.dll, name)(*args)
+        if rc != 0:
+            raise FvmGpuError(self.dll.fvmgpu_last_error().decode())
+
+    def init(self, device=0):
+        self.call("fvmgpu_init", device)
+        self._initialised = True
+
+    def device_info(self):
+        name = C.create_string_buffer(256)
+        sm = C.c_int(0)
+        mem = C.c_double(0)
+        self.call("fvmgpu_device_info", name, 256, C.byref(sm), C.byref(mem))
+        return name.value.decode(), sm.value, mem.value
+
+    def counters(self):
+        a, b, c = C.c_longlong(0), C.c_longlong(0), C.c_longlong(0)
+        self.dll.fvmgpu_counters(C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def timer_start(self, slot=0):
+        self.call("fvmgpu_timer_start", slot)
+
+    def timer_stop(self, slot=0):
+        ms = C.c_double(0)
+        self.call("fvmgpu_timer_stop", slot, C.byref(ms))
+        return ms.value
+
+    def synchronize(self):
+        self.call("fvmgpu_synchronize")
+
+    def flush_l2(self):
+        self.call("fvmgpu_flush_l2")
+
+    def default_amg_opts(self):
+        o = AmgOpts()
+        self.dll.fvmgpu_amg_default_opts(C.byref(o))
+        return o
+
+
+_default = None
+
+
+def default_lib():
+    """The product library (fvm_b200/libfvmgpu.so), initialised on device LOCAL_RANK (or 0)."""
+    global _default
+    if _default is None:
+        lib = Lib()
+        lib.init(int(os.environ.get("LOCAL_RANK", "0")))
+        _default = lib
+    return _default
+
+
+class DeviceMesh:
+    """Device mirror of Mesh + StorageSite + CRConnectivity + GeomFields for one mesh."""
+
+    def __init__(self, lib, dim, n_self, n_total, face_cells, cc_row, cc_col, group_offset, group_count,
+                 group_id, group_kind):
+        self.lib = lib
+        self.dim, self.n_self, self.n_total = int(dim), int(n_self), int(n_total)
+        fc = _i32(face_cells).reshape(-1)
+        self.n_faces = len(fc) // 2
+        self.nnz = int(cc_row[-1])
+        self.group_offset = _i32(group_offset)
+        self.group_count = _i32(group_count)
+        self.group_id = _i32(group_id)
+        self.group_kind = _i32(group_kind)
+        self.h = _vp()
+        lib.call("fvmgpu_mesh_create", C.byref(self.h), self.dim, self.n_self, self.n_total, self.n_faces,
+                 fc, _i32(cc_row), _i32(cc_col), len(self.group_offset), self.group_offset,
+                 self.group_count, self.group_id, self.group_kind)
+
+    def set_geometry(self, face_area, face_area_mag, cell_centroid, cell_volume, face_centroid=None,
+                     ib_type=None):
+        _a, fcp = _nullable(face_centroid, np.float64)
+        _b, ibp = _nullable(ib_type, np.int32)
+        self.lib.call("fvmgpu_mesh_set_geometry", self.h, _f64(face_area).reshape(-1), _f64(face_area_mag),
+                      fcp, _f64(cell_centroid).reshape(-1), _f64(cell_volume), ibp)
+
+    def pair_to_col(self):
+        out = np.zeros(2 * self.n_faces, np.int32)
+        self.lib.call("fvmgpu_mesh_download_pair_to_col", self.h, out)
+        return out.reshape(-1, 2)
+
+    def gradient_weights(self):
+        out = np.zeros(3 * self.nnz)
+        self.lib.call("fvmgpu_mesh_download_gradient_weights", self.h, out)
+        return out.reshape(-1, 3)
+
+    def close(self):
+        if self.h:
+            self.lib.call("fvmgpu_mesh_destroy", self.h)
+            self.h = None
+
+
+class DeviceSystem:
+    """Device mirror of LinearSystem + CRMatrix<T,T,T> (+ boundary flux rows) on a DeviceMesh."""
+
+    def __init__(self, lib, mesh=None, raw=None):
+        self.lib = lib
+        self.mesh = mesh
+        self.h = _vp()
+        if mesh is not None:
+            lib.call("fvmgpu_system_create", C.byref(self.h), mesh.h)
+            self.n_self, self.n_total, self.nnz = mesh.n_self, mesh.n_total, mesh.nnz
+        else:
+            n_self, n_ghost, row, col, diag, off, b = raw
+            self.n_self, self.n_total = int(n_self), int(n_self + n_ghost)
+            self.nnz = int(row[-1])
+            lib.call("fvmgpu_system_create_raw", C.byref(self.h), int(n_self), int(n_ghost), _i32(row),
+                     _i32(col) if self.nnz else np.zeros(1, np.int32), _f64(diag),
+                     _f64(off) if self.nnz else np.zeros(1), _f64(b))
+
+    def set_field(self, field, values):
+        v = _f64(values).reshape(-1)
+        self.lib.call("fvmgpu_system_set_field", self.h, field, v, v.size)
+
+    def fill_field(self, field, value):
+        self.lib.call("fvmgpu_system_fill_field", self.h, field, float(value))
+
+    def get_field(self, field):
+        if field == FIELD_GRADIENT:
+            n = 3 * self.n_total
+        elif field in (FIELD_FACE_FLUX, FIELD_BFLUX):
+            n = self.mesh.n_faces
+        else:
+            n = self.n_total
+        out = np.zeros(n)
+        self.lib.call("fvmgpu_system_get_field", self.h, field, out, n)
+        return out.reshape(-1, 3) if field == FIELD_GRADIENT else out
+
+    def set_bc(self, group_id, kind, params=(), per_face=None):
+        p = _f64(list(params) + [0.0] * (4 - len(params)))
+        _a, pf = _nullable(per_face, np.float64)
+        self.lib.call("fvmgpu_system_set_bc", self.h, int(group_id), int(kind), p, 4, pf)
+
+    def compute_gradient(self):
+        self.lib.call("fvmgpu_compute_gradient", self.h)
+
+    def assemble(self, diffusion=1, convection=0, source=1, time_order=0, dt=0.0, underrelax=0.0,
+                 apply_bcs=1, eliminate_boundary=1):
+        o = AssembleOpts(diffusion, convection, source, time_order, dt, underrelax, apply_bcs,
+                         eliminate_boundary)
+        self.lib.call("fvmgpu_assemble", self.h, C.byref(o))
+
+    def download(self):
+        diag = np.zeros(self.n_total)
+        off = np.zeros(max(self.nnz, 1))
+        b = np.zeros(self.n_total)
+        isb = np.zeros(self.n_total, np.int32)
+        self.lib.call("fvmgpu_download_system", self.h, diag, off, b, isb.ctypes.data_as(C.c_void_p))
+        return dict(diag=diag, offdiag=off[:self.nnz], b=b, is_boundary=isb)
+
+    def post_solve_update(self):
+        self.lib.call("fvmgpu_post_solve_update", self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.call("fvmgpu_system_destroy", self.h)
+            self.h = None
+
+
+class DeviceAMG:
+    """Device AMG hierarchy + cycle driver; also the preconditioner of BCGStab."""
+
+    def __init__(self, lib, opts=None):
+        self.lib = lib
+        self.opts = opts or lib.default_amg_opts()
+        self.h = _vp()
+        lib.call("fvmgpu_amg_create", C.byref(self.h), C.byref(self.opts))
+
+    def set_opts(self, opts):
+        self.opts = opts
+        self.lib.call("fvmgpu_amg_set_opts", self.h, C.byref(opts))
+
+    def solve(self, system):
+        r0, r, it = C.c_double(0), C.c_double(0), C.c_int(0)
+        self.lib.call("fvmgpu_amg_solve", self.h, system.h, C.byref(r0), C.byref(r), C.byref(it))
+        return r0.value, r.value, it.value
+
+    def smooth(self, system):
+        self.lib.call("fvmgpu_amg_smooth", self.h, system.h)
+
+    def bcgstab(self, system, n_max_iterations, relative_tolerance, absolute_tolerance):
+        r0, r, it = C.c_double(0), C.c_double(0), C.c_int(0)
+        self.lib.call("fvmgpu_bcgstab_solve", self.h, system.h, int(n_max_iterations),
+                      float(relative_tolerance), float(absolute_tolerance), C.byref(r0), C.byref(r),
+                      C.byref(it))
+        return r0.value, r.value, it.value
+
+    def levels(self):
+        n = C.c_int(0)
+        sizes = np.zeros(64, np.int64)
+        nnzs = np.zeros(64, np.int64)
+        cols = np.zeros(64, np.int32)
+        self.lib.call("fvmgpu_amg_levels", self.h, 64, C.byref(n), sizes, nnzs, cols)
+        k = n.value
+        return dict(sizes=sizes[:k].tolist(), nnz=nnzs[:k].tolist(), colours=cols[:k].tolist())
+
+    def history(self):
+        n = C.c_int(0)
+        out = np.zeros(1 << 14)
+        self.lib.call("fvmgpu_solver_history", self.h, len(out), out, C.byref(n))
+        return out[:min(n.value, len(out))].copy()
+
+    def cleanup(self):
+        self.lib.call("fvmgpu_amg_cleanup", self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.call("fvmgpu_amg_destroy", self.h)
+            self.h = None

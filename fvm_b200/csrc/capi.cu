@@ -1,0 +1,427 @@
+// fvm_b200 / libfvmgpu -- the extern "C" boundary declared in include/fvmgpu.h.
+// Every entry point catches C++ exceptions and turns them into (non-zero return, message):
+// the C-ABI equivalent of the reference's CException -> RuntimeError translation
+// (F/CException.h:16-21, F/baseExt.i:49-59).
+#include "solver.cuh"
+
+#ifndef FVMGPU_HOSTSIM
+#include <dlfcn.h>
+#endif
+
+using namespace fvmgpu;
+
+static thread_local std::string g_lastError;
+
+#define API_BEGIN try {
+#define API_END                                  \
+  return 0;                                      \
+  }                                              \
+  catch (const std::exception& e) {              \
+    g_lastError = e.what();                      \
+    return 1;                                    \
+  }                                              \
+  catch (...) {                                  \
+    g_lastError = "unknown error";               \
+    return 1;                                    \
+  }
+
+// the opaque handle types of fvmgpu.h are never defined: handles are the C++ objects' addresses
+static Mesh* M(fvmgpu_mesh_t h) { if (!h) fail("null mesh handle"); return reinterpret_cast<Mesh*>(h); }
+static System* S(fvmgpu_system_t h) { if (!h) fail("null system handle"); return reinterpret_cast<System*>(h); }
+static Amg* A(fvmgpu_solver_t h) { if (!h) fail("null solver handle"); return reinterpret_cast<Amg*>(h); }
+
+extern "C" {
+
+const char* fvmgpu_last_error(void) { return g_lastError.c_str(); }
+int fvmgpu_version(void) { return FVMGPU_VERSION; }
+
+void fvmgpu_amg_default_opts(fvmgpu_amg_opts* o) {
+  // F/AMG.cpp:14-22 and F/LinearSolver.h:15-20
+  o->nMaxIterations = 100;
+  o->verbosity = 2;
+  o->relativeTolerance = 1e-8;
+  o->absoluteTolerance = 1e-50;
+  o->maxCoarseLevels = 30;
+  o->nPreSweeps = 0;
+  o->nPostSweeps = 1;
+  o->coarseGroupSize = 2;
+  o->weightRatioThreshold = 0.65;
+  o->cycleType = FVMGPU_CYCLE_V;
+  o->smootherType = FVMGPU_SMOOTHER_GAUSS_SEIDEL;
+}
+
+int fvmgpu_init(int device) {
+  API_BEGIN
+  Context& c = ctx();
+  if (c.ready) {
+    if (c.device != device) fail("libfvmgpu already initialised on device %d", c.device);
+    return 0;
+  }
+#ifndef FVMGPU_HOSTSIM
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    fail("libfvmgpu needs a CUDA device (sm_100a build, no CPU fallback): %s",
+         e != cudaSuccess ? cudaGetErrorString(e) : "no device found");
+  if (device < 0 || device >= count) fail("device %d out of range (have %d)", device, count);
+  CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  c.smCount = prop.multiProcessorCount;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 16; i++) {
+    CUDA_CHECK(cudaEventCreate(&c.timerStart[i]));
+    CUDA_CHECK(cudaEventCreate(&c.timerStop[i]));
+  }
+  c.reduceScratch = (double*)devAlloc(sizeof(double) * 4 * kMaxReduceBlocks);
+#else
+  c.reduceScratch = (double*)devAlloc(sizeof(double) * 4 * kMaxReduceBlocks);
+#endif
+  c.device = device;
+  c.ready = true;
+  API_END
+}
+
+int fvmgpu_shutdown(void) {
+  API_BEGIN
+  Context& c = ctx();
+  if (!c.ready) return 0;
+#ifndef FVMGPU_HOSTSIM
+  cudaStreamSynchronize(c.stream);
+  for (int i = 0; i < 16; i++) { cudaEventDestroy(c.timerStart[i]); cudaEventDestroy(c.timerStop[i]); }
+  cudaStreamDestroy(c.stream);
+  c.stream = nullptr;
+#endif
+  if (c.reduceScratch) devFree(c.reduceScratch);
+  if (c.l2scratch) devFree(c.l2scratch);
+  c.reduceScratch = nullptr;
+  c.l2scratch = nullptr;
+  c.ready = false;
+  API_END
+}
+
+int fvmgpu_device_info(char* name, int cap, int* sm_count, double* mem_gb) {
+  API_BEGIN
+  requireReady();
+#ifndef FVMGPU_HOSTSIM
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, ctx().device));
+  if (name && cap > 0) { std::strncpy(name, prop.name, cap - 1); name[cap - 1] = 0; }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (mem_gb) *mem_gb = (double)prop.totalGlobalMem / 1e9;
+#else
+  if (name && cap > 0) { std::strncpy(name, "hostsim", cap - 1); name[cap - 1] = 0; }
+  if (sm_count) *sm_count = 0;
+  if (mem_gb) *mem_gb = 0;
+#endif
+  API_END
+}
+
+int fvmgpu_synchronize(void) {
+  API_BEGIN
+  requireReady();
+  streamSync();
+  API_END
+}
+
+int fvmgpu_timer_start(int slot) {
+  API_BEGIN
+  requireReady();
+  if (slot < 0 || slot >= 16) fail("timer slot out of range");
+#ifndef FVMGPU_HOSTSIM
+  CUDA_CHECK(cudaEventRecord(ctx().timerStart[slot], ctx().stream));
+#endif
+  API_END
+}
+int fvmgpu_timer_stop(int slot, double* ms) {
+  API_BEGIN
+  requireReady();
+  if (slot < 0 || slot >= 16) fail("timer slot out of range");
+#ifndef FVMGPU_HOSTSIM
+  CUDA_CHECK(cudaEventRecord(ctx().timerStop[slot], ctx().stream));
+  CUDA_CHECK(cudaEventSynchronize(ctx().timerStop[slot]));
+  float t = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&t, ctx().timerStart[slot], ctx().timerStop[slot]));
+  if (ms) *ms = t;
+#else
+  if (ms) *ms = 0;
+#endif
+  API_END
+}
+int fvmgpu_counters(long long* kernel_launches, long long* h2d_bytes, long long* d2h_bytes) {
+  if (kernel_launches) *kernel_launches = ctx().launches;
+  if (h2d_bytes) *h2d_bytes = ctx().h2d;
+  if (d2h_bytes) *d2h_bytes = ctx().d2h;
+  return 0;
+}
+int fvmgpu_flush_l2(void) {
+  API_BEGIN
+  requireReady();
+  const size_t bytes = 256u << 20;
+  if (!ctx().l2scratch) ctx().l2scratch = devAlloc(bytes);
+  devMemset(ctx().l2scratch, 1, bytes);
+  API_END
+}
+
+// ---------------------------------------------------------------- mesh
+int fvmgpu_mesh_create(fvmgpu_mesh_t* out, int dim, int nCellsSelf, int nCellsTotal, int nFaces,
+                       const int* faceCells, const int* cellCellsRow, const int* cellCellsCol, int nGroups,
+                       const int* groupOffset, const int* groupCount, const int* groupId, const int* groupKind) {
+  API_BEGIN
+  if (!out) fail("null output handle");
+  *out = reinterpret_cast<fvmgpu_mesh_t>(meshCreate(dim, nCellsSelf, nCellsTotal, nFaces, faceCells, cellCellsRow,
+                                                    cellCellsCol, nGroups, groupOffset, groupCount, groupId, groupKind));
+  API_END
+}
+int fvmgpu_mesh_set_geometry(fvmgpu_mesh_t mesh, const double* faceArea, const double* faceAreaMag,
+                             const double* faceCentroid, const double* cellCentroid, const double* cellVolume,
+                             const int* ibType) {
+  API_BEGIN
+  if (!faceArea || !faceAreaMag || !cellCentroid || !cellVolume) fail("set_geometry: null array");
+  meshSetGeometry(M(mesh), faceArea, faceAreaMag, faceCentroid, cellCentroid, cellVolume, ibType);
+  API_END
+}
+int fvmgpu_mesh_set_halo(fvmgpu_mesh_t mesh, int nNeigh, const int* peerRank, const int* scatterOff,
+                         const int* scatterIdx, const int* gatherOff, const int* gatherIdx) {
+  API_BEGIN
+  meshSetHalo(M(mesh), nNeigh, peerRank, scatterOff, scatterIdx, gatherOff, gatherIdx);
+  API_END
+}
+int fvmgpu_mesh_destroy(fvmgpu_mesh_t mesh) {
+  API_BEGIN
+  if (mesh) { streamSync(); delete M(mesh); }
+  API_END
+}
+int fvmgpu_mesh_download_pair_to_col(fvmgpu_mesh_t mesh, int* pairToCol) {
+  API_BEGIN
+  Mesh* m = M(mesh);
+  m->pairToCol.download(pairToCol, 2 * (size_t)m->nFaces);
+  API_END
+}
+int fvmgpu_mesh_download_gradient_weights(fvmgpu_mesh_t mesh, double* coeffs) {
+  API_BEGIN
+  Mesh* m = M(mesh);
+  if (!m->hasGeometry) fail("gradient weights: geometry not set");
+  std::vector<double> w = m->gradW.toHost();
+  const size_t nnz = (size_t)m->nnz;
+  for (size_t k = 0; k < nnz; k++) {
+    coeffs[3 * k] = w[k];
+    coeffs[3 * k + 1] = w[nnz + k];
+    coeffs[3 * k + 2] = w[2 * nnz + k];
+  }
+  API_END
+}
+
+// ---------------------------------------------------------------- system
+int fvmgpu_system_create(fvmgpu_system_t* out, fvmgpu_mesh_t mesh) {
+  API_BEGIN
+  if (!out) fail("null output handle");
+  *out = reinterpret_cast<fvmgpu_system_t>(systemCreate(M(mesh)));
+  API_END
+}
+int fvmgpu_system_create_raw(fvmgpu_system_t* out, int nSelf, int nGhost, const int* row, const int* col,
+                             const double* diag, const double* offdiag, const double* b) {
+  API_BEGIN
+  if (!out) fail("null output handle");
+  if (nSelf <= 0 || nGhost < 0 || !row || !diag || !b) fail("system_create_raw: bad arguments");
+  *out = reinterpret_cast<fvmgpu_system_t>(systemCreateRaw(nSelf, nGhost, row, col, diag, offdiag, b));
+  API_END
+}
+int fvmgpu_system_destroy(fvmgpu_system_t sys) {
+  API_BEGIN
+  if (sys) { streamSync(); delete S(sys); }
+  API_END
+}
+int fvmgpu_system_set_field(fvmgpu_system_t sys, int field, const double* host, long long n) {
+  API_BEGIN
+  if (!host) fail("set_field: null array");
+  systemSetField(S(sys), field, host, n, false, 0.0);
+  API_END
+}
+int fvmgpu_system_fill_field(fvmgpu_system_t sys, int field, double value) {
+  API_BEGIN
+  systemSetField(S(sys), field, nullptr, 0, true, value);
+  API_END
+}
+int fvmgpu_system_get_field(fvmgpu_system_t sys, int field, double* host, long long n) {
+  API_BEGIN
+  if (!host) fail("get_field: null array");
+  systemGetField(S(sys), field, host, n);
+  API_END
+}
+int fvmgpu_system_set_bc(fvmgpu_system_t sys, int groupId, int bcKind, const double* p, int np,
+                         const double* perFace) {
+  API_BEGIN
+  if (bcKind < 0 || bcKind > FVMGPU_BC_DIRICHLET_OR_OUTFLOW) fail("set_bc: unknown BC kind %d", bcKind);
+  systemSetBc(S(sys), groupId, bcKind, p, np, perFace);
+  API_END
+}
+int fvmgpu_compute_gradient(fvmgpu_system_t sys) {
+  API_BEGIN
+  computeGradient(S(sys));
+  API_END
+}
+int fvmgpu_assemble(fvmgpu_system_t sys, const fvmgpu_assemble_opts* opts) {
+  API_BEGIN
+  if (!opts) fail("assemble: null options");
+  assemble(S(sys), *opts);
+  API_END
+}
+int fvmgpu_download_system(fvmgpu_system_t sys, double* diag, double* offdiag, double* b, int* isBoundary) {
+  API_BEGIN
+  System* s = S(sys);
+  if (diag) s->diag.download(diag, s->nTotal);
+  if (offdiag) s->off.download(offdiag, (size_t)s->nnz);
+  if (b) s->b.download(b, s->nTotal);
+  if (isBoundary) s->isBoundary.download(isBoundary, s->nTotal);
+  API_END
+}
+
+// ---------------------------------------------------------------- solvers
+int fvmgpu_amg_create(fvmgpu_solver_t* out, const fvmgpu_amg_opts* opts) {
+  API_BEGIN
+  if (!out) fail("null output handle");
+  Amg* a = new Amg;
+  if (opts) a->opts = *opts;
+  else fvmgpu_amg_default_opts(&a->opts);
+  *out = reinterpret_cast<fvmgpu_solver_t>(a);
+  API_END
+}
+int fvmgpu_amg_set_opts(fvmgpu_solver_t s, const fvmgpu_amg_opts* opts) {
+  API_BEGIN
+  if (!opts) fail("null options");
+  Amg* a = A(s);
+  const bool structural = a->opts.coarseGroupSize != opts->coarseGroupSize ||
+                          a->opts.weightRatioThreshold != opts->weightRatioThreshold ||
+                          a->opts.maxCoarseLevels != opts->maxCoarseLevels;
+  a->opts = *opts;
+  if (structural) a->cleanup();
+  API_END
+}
+int fvmgpu_amg_solve(fvmgpu_solver_t s, fvmgpu_system_t sys, double* rnorm0, double* rnorm, int* iters) {
+  API_BEGIN
+  A(s)->solve(S(sys), rnorm0, rnorm, iters);
+  API_END
+}
+int fvmgpu_amg_smooth(fvmgpu_solver_t s, fvmgpu_system_t sys) {
+  API_BEGIN
+  A(s)->smooth(S(sys));
+  API_END
+}
+int fvmgpu_amg_cleanup(fvmgpu_solver_t s) {
+  API_BEGIN
+  streamSync();
+  A(s)->cleanup();
+  API_END
+}
+int fvmgpu_amg_destroy(fvmgpu_solver_t s) {
+  API_BEGIN
+  if (s) { streamSync(); delete A(s); }
+  API_END
+}
+int fvmgpu_amg_levels(fvmgpu_solver_t s, int cap, int* nLevels, long long* sizes, long long* nnzs, int* colours) {
+  API_BEGIN
+  Amg* a = A(s);
+  const int nl = (int)a->levels.size();
+  if (nLevels) *nLevels = nl;
+  for (int l = 0; l < nl && l < cap; l++) {
+    if (sizes) sizes[l] = a->levels[l]->n;
+    if (nnzs) nnzs[l] = a->levels[l]->nnzTrue;
+    if (colours) colours[l] = a->levels[l]->nColours;
+  }
+  API_END
+}
+int fvmgpu_solver_history(fvmgpu_solver_t s, int cap, double* out, int* n) {
+  API_BEGIN
+  Amg* a = A(s);
+  const int cnt = (int)a->history.size();
+  if (n) *n = cnt;
+  for (int i = 0; i < cnt && i < cap; i++) out[i] = a->history[i];
+  API_END
+}
+int fvmgpu_bcgstab_solve(fvmgpu_solver_t precond, fvmgpu_system_t sys, int nMaxIterations, double relativeTolerance,
+                         double absoluteTolerance, double* rnorm0, double* rnorm, int* iters) {
+  API_BEGIN
+  A(precond)->bcgstab(S(sys), nMaxIterations, relativeTolerance, absoluteTolerance, rnorm0, rnorm, iters);
+  API_END
+}
+int fvmgpu_post_solve_update(fvmgpu_system_t sys) {
+  API_BEGIN
+  postSolveUpdate(S(sys));
+  API_END
+}
+
+// ---------------------------------------------------------------- multi-GPU plumbing
+// NCCL is resolved at run time (dlopen) so that libfvmgpu.so carries no link-time dependency;
+// in a torchrun-launched process torch has already loaded its bundled libnccl.so.2.
+#ifndef FVMGPU_HOSTSIM
+struct Id128 { char b[128]; };  // ncclUniqueId is passed BY VALUE (128 bytes)
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+static NcclApi& nccl() {
+  static NcclApi api;
+  if (!api.lib) {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (!api.lib) fail("multi-GPU: cannot dlopen libnccl.so.2 (%s)", dlerror());
+    api.GetUniqueId = (int (*)(void*))dlsym(api.lib, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(api.lib, "ncclCommInitRank");
+    api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
+    api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy) fail("multi-GPU: libnccl lacks required symbols");
+  }
+  return api;
+}
+#endif
+
+int fvmgpu_comm_unique_id(void* out128) {
+  API_BEGIN
+#ifndef FVMGPU_HOSTSIM
+  int rc = nccl().GetUniqueId(out128);
+  if (rc) fail("ncclGetUniqueId failed: %d", rc);
+#else
+  std::memset(out128, 0, 128);
+#endif
+  API_END
+}
+int fvmgpu_comm_init(int nranks, int rank, const void* uniqueId128) {
+  API_BEGIN
+  requireReady();
+  if (nranks < 1 || rank < 0 || rank >= nranks) fail("comm_init: bad rank %d of %d", rank, nranks);
+  ctx().nranks = nranks;
+  ctx().rank = rank;
+#ifndef FVMGPU_HOSTSIM
+  if (nranks > 1) {
+    Id128 id;
+    std::memcpy(id.b, uniqueId128, 128);
+    void* comm = nullptr;
+    int rc = nccl().CommInitRank(&comm, nranks, id, rank);
+    if (rc) fail("ncclCommInitRank failed: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
+    ctx().ncclComm = comm;
+  }
+#else
+  (void)uniqueId128;
+#endif
+  API_END
+}
+int fvmgpu_comm_destroy(void) {
+  API_BEGIN
+#ifndef FVMGPU_HOSTSIM
+  if (ctx().ncclComm) { nccl().CommDestroy(ctx().ncclComm); ctx().ncclComm = nullptr; }
+#endif
+  ctx().nranks = 1;
+  ctx().rank = 0;
+  API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// fvm_b200 / libfvmgpu -- context, raw memory, scan / sort primitives.
+// Device build: CUDA runtime + CUB (device-wide scan / radix sort used by the SETUP phases only).
+// FVMGPU_HOSTSIM build (tests only, see common.cuh): malloc / std algorithms.
+#include "common.cuh"
+
+#ifndef FVMGPU_HOSTSIM
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#else
+#include <algorithm>
+#include <numeric>
+#endif
+
+namespace fvmgpu {
+
+Context& ctx() {
+  static Context c;
+  return c;
+}
+
+void requireReady() {
+  if (!ctx().ready) fail("libfvmgpu: not initialised (call fvmgpu_init; a CUDA device is required, there is no CPU path)");
+}
+
+#ifndef FVMGPU_HOSTSIM
+void* devAlloc(size_t bytes) {
+  void* p = nullptr;
+  CUDA_CHECK(cudaMalloc(&p, bytes));
+  return p;
+}
+void devFree(void* p) { cudaFree(p); }
+void devMemset(void* p, int byte, size_t bytes) { CUDA_CHECK(cudaMemsetAsync(p, byte, bytes, ctx().stream)); }
+void copyH2D(void* d, const void* h, size_t bytes) {
+  CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx().stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx().stream));  // pageable host source may be reused by the caller
+  ctx().h2d += (long long)bytes;
+}
+void copyD2H(void* h, const void* d, size_t bytes) {
+  CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx().stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
+  ctx().d2h += (long long)bytes;
+}
+void copyD2D(void* d, const void* s, size_t bytes) {
+  CUDA_CHECK(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, ctx().stream));
+}
+void streamSync() { CUDA_CHECK(cudaStreamSynchronize(ctx().stream)); }
+
+static DBuf<char>& cubTemp() {
+  static DBuf<char> t;
+  return t;
+}
+
+void exclusiveScan(const int* in_d, int* out_d, long long n) {
+  // out has n+1 entries: out[n] = total. Scan n+1 items where the extra input is ignored:
+  // ExclusiveSum over n+1 outputs needs n+1 inputs; use a temp copy when in aliases out.
+  if (n < 0) return;
+  DBuf<int> tmp((size_t)n + 1);
+  copyD2D(tmp.p, in_d, (size_t)n * sizeof(int));
+  devMemset(tmp.p + n, 0, sizeof(int));
+  size_t bytes = 0;
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, tmp.p, out_d, (int)(n + 1), ctx().stream));
+  cubTemp().ensure(bytes);
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(cubTemp().p, bytes, tmp.p, out_d, (int)(n + 1), ctx().stream));
+  ctx().launches += 2;
+  streamSync();  // tmp freed on return
+}
+
+void sortPairs(int* keys_d, int* vals_d, long long n, int bits) {
+  if (n <= 0) return;
+  DBuf<int> k2((size_t)n), v2((size_t)n);
+  size_t bytes = 0;
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_d, k2.p, vals_d, v2.p, (int)n, 0, bits, ctx().stream));
+  cubTemp().ensure(bytes);
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cubTemp().p, bytes, keys_d, k2.p, vals_d, v2.p, (int)n, 0, bits,
+                                             ctx().stream));
+  copyD2D(keys_d, k2.p, (size_t)n * sizeof(int));
+  copyD2D(vals_d, v2.p, (size_t)n * sizeof(int));
+  ctx().launches += 4;
+  streamSync();
+}
+#else
+void* devAlloc(size_t bytes) { return std::malloc(bytes ? bytes : 1); }
+void devFree(void* p) { std::free(p); }
+void devMemset(void* p, int byte, size_t bytes) { std::memset(p, byte, bytes); }
+void copyH2D(void* d, const void* h, size_t bytes) { std::memcpy(d, h, bytes); ctx().h2d += (long long)bytes; }
+void copyD2H(void* h, const void* d, size_t bytes) { std::memcpy(h, d, bytes); ctx().d2h += (long long)bytes; }
+void copyD2D(void* d, const void* s, size_t bytes) { std::memmove(d, s, bytes); }
+void streamSync() {}
+void exclusiveScan(const int* in_d, int* out_d, long long n) {
+  int acc = 0;
+  for (long long i = 0; i < n; i++) { int v = in_d[i]; out_d[i] = acc; acc += v; }
+  out_d[n] = acc;
+}
+void sortPairs(int* keys_d, int* vals_d, long long n, int) {
+  std::vector<std::pair<int, int>> v((size_t)n);
+  for (long long i = 0; i < n; i++) v[(size_t)i] = {keys_d[i], vals_d[i]};
+  std::stable_sort(v.begin(), v.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+  for (long long i = 0; i < n; i++) { keys_d[i] = v[(size_t)i].first; vals_d[i] = v[(size_t)i].second; }
+}
+#endif
+
+}  // namespace fvmgpu

@@ -1,0 +1,787 @@
+// fvm_b200 / libfvmgpu -- additive-correction algebraic multigrid + BiCGStab on the device.
+//
+// What the reference does (sequentially, one rank)          what this file does (B200)
+//   CRMatrix::createCoarsening   F/CRMatrix.h:468-586      parallel handshake pairing with the
+//     greedy pairwise agglomeration by                     same weight |a_ij|/max(|a_ii|,|a_jj|)
+//     weight, threshold 0.65                                and weightRatioThreshold
+//   createCoarseConnectivity     :597-691                  one thread per coarse row: merge the
+//   createCoarseMatrix           :699-758                  members' rows through coarseIndex,
+//     (Galerkin by summation)                               intra-aggregate entries fold into diag
+//   forwardGS / reverseGS        :303-346                  multicolour Gauss-Seidel: colours
+//                                                           ascending = forward, descending = reverse
+//   Jacobi                       :353-374                  same
+//   computeResidual  r = b + A x :407-426                  same, fused with the 1-norm
+//   Array::inject / correct      F/Array.h:427-467         gather-form restriction (deterministic),
+//                                                           pointwise prolongation
+//   AMG::cycle / solve / smooth  F/AMG.cpp:70-298          same recursion (V/W/F), same
+//                                                           convergence test on the L1 norm
+//   BCGStab::solve               F/BCGStab.cpp:26-170      same recurrence, dots batched
+//
+// Storage: every level keeps its matrix in SELL-32 (sliced ELLPACK, slice = 32 rows = one warp,
+// column-major inside the slice) with rows renumbered colour by colour, so one thread per row
+// reads val/col fully coalesced and a colour is a contiguous row range. x, b, r, diag are plain
+// FP64 arrays in the same numbering and stay resident in HBM for the whole solve.
+#include "solver.cuh"
+
+namespace fvmgpu {
+
+// ================================================================= small kernels
+FVM_DEV unsigned hash32(unsigned a) {
+  a ^= a >> 16; a *= 0x7feb352dU; a ^= a >> 15; a *= 0x846ca68bU; a ^= a >> 16;
+  return a;
+}
+FVM_DEV unsigned edgeHash(int i, int j) {
+  const unsigned lo = (unsigned)(i < j ? i : j), hi = (unsigned)(i < j ? j : i);
+  return hash32(lo * 0x9e3779b9U + hash32(hi));
+}
+
+struct IotaKernel { int* p; FVM_DEV void operator()(long long i) const { p[i] = (int)i; } };
+struct FillIntKernel { int* p; int v; FVM_DEV void operator()(long long i) const { p[i] = v; } };
+struct FillDblKernel { double* p; double v; FVM_DEV void operator()(long long i) const { p[i] = v; } };
+
+// ---- colouring (Jones-Plassmann with hashed priorities) on a CSR pattern
+struct ColourRoundKernel {
+  int n; const int* row; const int* col; int* colour; int* remaining; int* overflow;
+  FVM_DEV bool higher(int a, int b) const {  // priority(a) > priority(b)
+    const unsigned ha = hash32((unsigned)a), hb = hash32((unsigned)b);
+    return ha != hb ? ha > hb : a > b;
+  }
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    if (colour[i] >= 0) return;
+    unsigned long long used = 0ULL;
+    for (int k = row[i]; k < row[i + 1]; k++) {
+      const int j = col[k];
+      if (j >= n || j == i) continue;
+      const int cj = colour[j];
+      if (cj < 0) {
+        if (higher(j, i)) { atomicAdd(remaining, 1); return; }  // wait for a higher-priority neighbour
+      } else {
+        used |= 1ULL << cj;
+      }
+    }
+    int c = 0;
+    while (c < 64 && ((used >> c) & 1ULL)) c++;
+    if (c >= 64) { atomicOr(overflow, 1); c = 63; }
+    colour[i] = c;
+  }
+};
+struct ColourCountKernel {
+  const int* colour; int* counts;
+  FVM_DEV void operator()(long long i) const { atomicAdd(&counts[colour[i]], 1); }
+};
+
+// ---- CSR -> SELL-32 with renumbering
+struct RowLenKernel {  // per NEW row
+  int n; const int* invp; const int* row; const int* col; int dropGhost; int* len;
+  FVM_DEV void operator()(long long r) const {
+    const int old = invp[r];
+    int c = 0;
+    for (int k = row[old]; k < row[old + 1]; k++)
+      if (!(dropGhost && col[k] >= n)) c++;
+    len[r] = c;
+  }
+};
+struct SliceWidthKernel {
+  int n; const int* len; int* width32;
+  FVM_DEV void operator()(long long s) const {
+    int w = 0;
+    const int r0 = (int)s * 32;
+    for (int r = r0; r < r0 + 32 && r < n; r++) w = len[r] > w ? len[r] : w;
+    width32[s] = w * 32;  // elements in the slice
+  }
+};
+struct SellFillKernel {
+  int n; const int* invp; const int* perm; const int* row; const int* col; const double* val;
+  const double* diagOld; int dropGhost; const int* sliceOff; int* scol; double* sval; double* diagNew;
+  FVM_DEV void operator()(long long rr) const {
+    const int r = (int)rr, old = invp[r];
+    const int s = r >> 5, lane = r & 31;
+    int p = sliceOff[s] + lane;
+    const int end = sliceOff[s + 1];
+    for (int k = row[old]; k < row[old + 1]; k++) {
+      const int c = col[k];
+      if (dropGhost && c >= n) continue;
+      scol[p] = c < n ? perm[c] : c;  // ghost columns keep their index (>= n)
+      sval[p] = val[k];
+      p += 32;
+    }
+    for (; p < end; p += 32) { scol[p] = r; sval[p] = 0.0; }
+    diagNew[r] = diagOld[old];
+  }
+};
+struct PermGatherKernel {  // dst[perm[i]] = src[i]
+  const int* perm; const double* src; double* dst;
+  FVM_DEV void operator()(long long i) const { dst[perm[i]] = src[i]; }
+};
+struct PermScatterKernel {  // dst[i] = src[perm[i]]
+  const int* perm; const double* src; double* dst;
+  FVM_DEV void operator()(long long i) const { dst[i] = src[perm[i]]; }
+};
+struct InvPermKernel { const int* invp; int* perm; FVM_DEV void operator()(long long r) const { perm[invp[r]] = (int)r; } };
+struct PermIntKernel {  // excl[perm[i]] = src[i]
+  const int* perm; const int* src; int* dst;
+  FVM_DEV void operator()(long long i) const { dst[perm[i]] = src[i]; }
+};
+
+// ---- smoothers / residual on SELL
+struct GsRows {  // one colour: rows [rowBegin, rowBegin+count)
+  int rowBegin; const int* sliceOff; const int* scol; const double* sval; const double* diag; const double* b;
+  double* x;
+  FVM_DEV void operator()(long long t) const {
+    const int r = rowBegin + (int)t;
+    const int s = r >> 5;
+    const int end = sliceOff[s + 1];
+    double sum = b[r];
+    for (int p = sliceOff[s] + (r & 31); p < end; p += 32) sum += sval[p] * x[scol[p]];
+    x[r] = -sum / diag[r];
+  }
+};
+struct GsFirstColourZeroRows {  // first colour of a sweep on x == 0: x_i = -b_i/a_ii, no matrix read
+  int rowBegin; const double* diag; const double* b; double* x;
+  FVM_DEV void operator()(long long t) const {
+    const int r = rowBegin + (int)t;
+    x[r] = -b[r] / diag[r];
+  }
+};
+struct JacobiRows {
+  const int* sliceOff; const int* scol; const double* sval; const double* diag; const double* b;
+  const double* xold; double* xnew;
+  FVM_DEV void operator()(long long rr) const {
+    const int r = (int)rr, s = r >> 5;
+    const int end = sliceOff[s + 1];
+    double sum = b[r];
+    for (int p = sliceOff[s] + (r & 31); p < end; p += 32) sum += sval[p] * xold[scol[p]];
+    xnew[r] = -sum / diag[r];
+  }
+};
+struct ResidualRows {  // r = b + A x
+  const int* sliceOff; const int* scol; const double* sval; const double* diag; const double* b;
+  const double* x; double* r;
+  FVM_DEV double compute(int i) const {
+    const int s = i >> 5;
+    const int end = sliceOff[s + 1];
+    double v = b[i] + diag[i] * x[i];
+    for (int p = sliceOff[s] + (i & 31); p < end; p += 32) v += sval[p] * x[scol[p]];
+    return v;
+  }
+  FVM_DEV void operator()(long long i) const { r[i] = compute((int)i); }
+  FVM_DEV void operator()(long long i, double* out) const {  // fused with the 1-norm
+    const double v = compute((int)i);
+    r[i] = v;
+    out[0] = fabs(v);
+  }
+};
+struct MultiplyRows {  // y = A x   (CRMatrix::multiply, F/CRMatrix.h:200-216)
+  const int* sliceOff; const int* scol; const double* sval; const double* diag; const double* x; double* y;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii, s = i >> 5;
+    const int end = sliceOff[s + 1];
+    double v = diag[i] * x[i];
+    for (int p = sliceOff[s] + (i & 31); p < end; p += 32) v += sval[p] * x[scol[p]];
+    y[i] = v;
+  }
+};
+struct InjectRows {  // coarse b[I] = sum of fine src over the aggregate (ascending fine row); coarse x = 0
+  const int* memOff; const int* mem; const double* src; double* bC; double* xC;
+  FVM_DEV void operator()(long long I) const {
+    double s = 0.0;
+    for (int p = memOff[I]; p < memOff[I + 1]; p++) s += src[mem[p]];
+    bC[I] = s;
+    xC[I] = 0.0;
+  }
+};
+struct CorrectRows {  // fine x[i] += coarse x[ci[i]]
+  const int* ci; const double* xC; double* x;
+  FVM_DEV void operator()(long long i) const {
+    const int c = ci[i];
+    if (c >= 0) x[i] += xC[c];
+  }
+};
+
+// ---- BLAS-1 (F/Array.h:243-311)
+struct AbsSumRows { const double* a; FVM_DEV void operator()(long long i, double* o) const { o[0] = fabs(a[i]); } };
+struct Dot1Rows { const double* a; const double* b; FVM_DEV void operator()(long long i, double* o) const { o[0] = a[i] * b[i]; } };
+struct Dot2Rows {  // (a.b, a.a)
+  const double* a; const double* b;
+  FVM_DEV void operator()(long long i, double* o) const { o[0] = a[i] * b[i]; o[1] = a[i] * a[i]; }
+};
+struct MsaxpyScalarPtr {  // y -= (*num / *den) * x ; optionally emits |y| for a fused norm
+  const double* num; const double* den; const double* x; double* y;
+  FVM_DEV void operator()(long long i) const { y[i] -= (num[0] / den[0]) * x[i]; }
+  FVM_DEV void operator()(long long i, double* o) const {
+    const double v = y[i] - (num[0] / den[0]) * x[i];
+    y[i] = v;
+    o[0] = fabs(v);
+  }
+};
+struct BcgUpdateP {  // p = (p - omega v) * beta + r,  beta = (rho/rhoPrev) * (alpha/omega)
+  const double* s;  // s[0]=rho s[1]=rhoPrev s[2]=alphaNum s[3]=alphaDen s[4]=omegaNum s[5]=omegaDen
+  const double* v; const double* r; double* p;
+  FVM_DEV void operator()(long long i) const {
+    const double alpha = s[2] / s[3], omega = s[4] / s[5];
+    const double beta = (s[0] / s[1]) * (alpha / omega);
+    double t = p[i];
+    t -= omega * v[i];
+    t *= beta;
+    t += r[i];
+    p[i] = t;
+  }
+};
+struct CopyKernel { const double* a; double* b; FVM_DEV void operator()(long long i) const { b[i] = a[i]; } };
+
+// ================================================================= aggregation
+// weight of entry (i,j): |a_ij| / max(|a_ii|,|a_jj|)            F/CRMatrix.h:520-528
+struct StrongestKernel {  // per row: the largest weight among eligible neighbours
+  int n; const int* sliceOff; const int* scol; const double* sval; const double* diag; const int* excluded;
+  double* strongest;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii, s = i >> 5;
+    double best = 0.0;
+    if (!(excluded && excluded[i])) {
+      const double di = fabs(diag[i]);
+      const int end = sliceOff[s + 1];
+      for (int p = sliceOff[s] + (i & 31); p < end; p += 32) {
+        const int j = scol[p];
+        if (j >= n || j == i || (excluded && excluded[j])) continue;
+        const double dj = fabs(diag[j]);
+        const double w = fabs(sval[p] / (di > dj ? di : dj));
+        best = w > best ? w : best;
+      }
+    }
+    strongest[i] = best;
+  }
+};
+struct ProposeKernel {  // unassigned rows propose to their best unassigned strong neighbour
+  int n; const int* sliceOff; const int* scol; const double* sval; const double* diag; const int* excluded;
+  const double* strongest; double threshold; const int* root; int* propose;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii, s = i >> 5;
+    int bestJ = -1;
+    if (root[i] < 0 && !(excluded && excluded[i])) {
+      const double di = fabs(diag[i]);
+      const double cut = threshold * strongest[i];
+      float bestW = -1.0f;
+      unsigned bestH = 0;
+      const int end = sliceOff[s + 1];
+      for (int p = sliceOff[s] + (i & 31); p < end; p += 32) {
+        const int j = scol[p];
+        if (j >= n || j == i || root[j] >= 0 || (excluded && excluded[j])) continue;
+        const double dj = fabs(diag[j]);
+        const double w = fabs(sval[p] / (di > dj ? di : dj));
+        if (!(w > cut) && !(w >= strongest[i])) continue;  // strong connections only
+        if (!(w > 0.0)) continue;
+        // compare in float so that last-bit noise does not order the edges; ties by a symmetric hash
+        const float wf = (float)w;
+        const unsigned h = edgeHash(i, j);
+        if (wf > bestW || (wf == bestW && h > bestH)) { bestW = wf; bestH = h; bestJ = j; }
+      }
+    }
+    propose[i] = bestJ;
+  }
+};
+struct HandshakeKernel {
+  const int* propose; int* root;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    const int j = propose[i];
+    if (j >= 0 && propose[j] == i) root[i] = i < j ? i : j;
+  }
+};
+struct JoinKernel {  // leftovers join the aggregate of their strongest paired neighbour
+  int n; const int* sliceOff; const int* scol; const double* sval; const double* diag; const int* excluded;
+  const int* root; int* join;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii, s = i >> 5;
+    int target = -1;
+    if (root[i] < 0 && !(excluded && excluded[i])) {
+      const double di = fabs(diag[i]);
+      double bestW = 0.0;
+      unsigned bestH = 0;
+      const int end = sliceOff[s + 1];
+      for (int p = sliceOff[s] + (i & 31); p < end; p += 32) {
+        const int j = scol[p];
+        if (j >= n || j == i || root[j] < 0) continue;
+        const double dj = fabs(diag[j]);
+        const double w = fabs(sval[p] / (di > dj ? di : dj));
+        const unsigned h = edgeHash(i, j);
+        if (w > bestW || (w == bestW && w > 0.0 && h > bestH)) { bestW = w; bestH = h; target = root[j]; }
+      }
+      if (target < 0) target = i;  // nobody to join: singleton
+    }
+    join[i] = target;
+  }
+};
+struct MergeJoinKernel {
+  const int* join; const int* excluded; int* root; int* isRoot;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    if (root[i] < 0 && join[i] >= 0) root[i] = join[i];
+    isRoot[i] = (root[i] == i) ? 1 : 0;
+  }
+};
+struct AggIdKernel {  // ci[i] = scanned id of the root (natural coarse numbering); excluded rows -1
+  const int* root; const int* rootScan; int* ci;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    ci[i] = root[i] >= 0 ? rootScan[root[i]] : -1;
+  }
+};
+struct SortKeyKernel {  // key = ci (or nc for -1), value = row
+  const int* ci; int nc; int* key; int* val;
+  FVM_DEV void operator()(long long i) const { const int c = ci[i]; key[i] = c >= 0 ? c : nc; val[i] = (int)i; }
+};
+struct MemOffKernel {  // starts of equal-key runs in the sorted key array (keys in [0, nc])
+  const int* key; int* memOff;
+  FVM_DEV void operator()(long long p) const {
+    const int k = key[p];
+    if (p == 0 || key[p - 1] != k) memOff[k] = (int)p;
+  }
+};
+struct ComposeKernel {  // o[i] = b[a[i]] (-1 passes through)
+  const int* a; const int* b; int* o;
+  FVM_DEV void operator()(long long i) const { const int c = a[i]; o[i] = c >= 0 ? b[c] : -1; }
+};
+struct UpperBoundKernel {
+  const int* memOff; const int* mem; const int* sliceOff; int* ub;
+  FVM_DEV void operator()(long long I) const {
+    int c = 0;
+    for (int p = memOff[I]; p < memOff[I + 1]; p++) {
+      const int s = mem[p] >> 5;
+      c += (sliceOff[s + 1] - sliceOff[s]) >> 5;
+    }
+    ub[I] = c;
+  }
+};
+struct CoarseRowKernel {  // Galerkin-by-summation for one coarse row (first-seen column order)
+  int n; const int* memOff; const int* mem; const int* sliceOff; const int* scol; const double* sval;
+  const double* diag; const int* ci; const int* ubOff; int* tmpCol; double* tmpVal; int* cnt; double* cdiag;
+  FVM_DEV void operator()(long long II) const {
+    const int I = (int)II;
+    const int base = ubOff[I];
+    int c = 0;
+    double d = 0.0;
+    for (int q = memOff[I]; q < memOff[I + 1]; q++) {
+      const int m = mem[q], s = m >> 5;
+      d += diag[m];
+      const int end = sliceOff[s + 1];
+      for (int p = sliceOff[s] + (m & 31); p < end; p += 32) {
+        const int j = scol[p];
+        const double v = sval[p];
+        if (j == m) continue;  // SELL padding
+        if (j >= n) continue;  // ghost column (multi-GPU coarse ghosts are handled by the halo layer)
+        const int J = ci[j];
+        if (J < 0) continue;
+        if (J == I) { d += v; continue; }
+        int k = 0;
+        while (k < c && tmpCol[base + k] != J) k++;
+        if (k == c) { tmpCol[base + c] = J; tmpVal[base + c] = v; c++; }
+        else tmpVal[base + k] += v;
+      }
+    }
+    cnt[I] = c;
+    cdiag[I] = d;
+  }
+};
+struct CompactKernel {
+  const int* ubOff; const int* crow; const int* tmpCol; const double* tmpVal; int* ccol; double* cval;
+  FVM_DEV void operator()(long long I) const {
+    const int src = ubOff[I], dst = crow[I], c = crow[I + 1] - crow[I];
+    for (int k = 0; k < c; k++) { ccol[dst + k] = tmpCol[src + k]; cval[dst + k] = tmpVal[src + k]; }
+  }
+};
+struct RemapCiKernel {
+  const int* perm; int* ci;
+  FVM_DEV void operator()(long long i) const { const int c = ci[i]; if (c >= 0) ci[i] = perm[c]; }
+};
+
+// ================================================================= level construction
+// Colour a CSR pattern; returns number of colours, fills colour[] (device)
+static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, std::vector<int>& counts) {
+  colour.alloc(n);
+  colour.fillBytes(0xff);
+  DBuf<int> flags(2);
+  int rounds = 0;
+  for (;;) {
+    flags.zero();
+    for (int k = 0; k < 4; k++) {
+      if (k) devMemset(flags.p, 0, sizeof(int));
+      parallelFor(n, ColourRoundKernel{n, row, col, colour.p, flags.p, flags.p + 1});
+      rounds++;
+    }
+    int h[2];
+    flags.download(h, 2);
+    if (h[1]) fail("amg: more than 64 colours needed (row with >= 64 distinct neighbour colours)");
+    if (h[0] == 0) break;
+    if (rounds > 4096) fail("amg: colouring did not terminate");
+  }
+  DBuf<int> cnt(64);
+  cnt.zero();
+  parallelFor(n, ColourCountKernel{colour.p, cnt.p});
+  std::vector<int> h = cnt.toHost();
+  int nc = 0;
+  for (int c = 0; c < 64; c++) if (h[c] > 0) nc = c + 1;
+  counts.assign(h.begin(), h.begin() + nc);
+  return nc;
+}
+
+// Build level L from a CSR system in "natural" numbering; returns perm (natural -> level numbering).
+static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, const double* val,
+                              const double* diag, bool dropGhost, DBuf<int>& perm) {
+  L.n = n;
+  std::vector<int> counts;
+  DBuf<int> colour;
+  L.nColours = colourCsr(n, row, col, colour, counts);
+  L.colourStart.assign(L.nColours + 1, 0);
+  for (int c = 0; c < L.nColours; c++) L.colourStart[c + 1] = L.colourStart[c] + counts[c];
+  // stable partition by colour: invp = rows sorted by colour
+  DBuf<int> invp(n);
+  parallelFor(n, IotaKernel{invp.p});
+  int bits = 1;
+  while ((1 << bits) < L.nColours + 1) bits++;
+  sortPairs(colour.p, invp.p, n, bits);
+  perm.alloc(n);
+  parallelFor(n, InvPermKernel{invp.p, perm.p});
+  // SELL-32
+  L.nSlices = ceilDiv(n, 32);
+  DBuf<int> len(n), width(L.nSlices + 1);
+  parallelFor(n, RowLenKernel{n, invp.p, row, col, dropGhost ? 1 : 0, len.p});
+  parallelFor(L.nSlices, SliceWidthKernel{n, len.p, width.p});
+  L.sliceOff.alloc(L.nSlices + 1);
+  exclusiveScan(width.p, L.sliceOff.p, L.nSlices);
+  const int total = L.sliceOff.hostAt(L.nSlices);
+  L.nnzStored = total;
+  L.scol.alloc(total > 0 ? total : 1);
+  L.sval.alloc(total > 0 ? total : 1);
+  L.diag.alloc(n); L.b.alloc(n); L.x.alloc(n); L.r.alloc(n);
+  L.b.zero(); L.x.zero(); L.r.zero();
+  parallelFor(n, SellFillKernel{n, invp.p, perm.p, row, col, val, diag, dropGhost ? 1 : 0, L.sliceOff.p, L.scol.p,
+                                L.sval.p, L.diag.p});
+  // true nnz (for the report)
+  DBuf<int> lenScan(n + 1);
+  exclusiveScan(len.p, lenScan.p, n);
+  L.nnzTrue = lenScan.hostAt(n);
+  streamSync();
+}
+
+// Coarsen level F into level C (one pairwise pass). Returns false if no reduction happened.
+static bool coarsenOnce(Level& F, const int* excluded, double threshold, DBuf<int>& ciNat, int& nc,
+                        DBuf<int>& crow, DBuf<int>& ccol, DBuf<double>& cval, DBuf<double>& cdiag) {
+  const int n = F.n;
+  DBuf<double> strongest(n);
+  DBuf<int> root(n), propose(n), join(n), isRoot(n), rootScan(n + 1);
+  root.fillBytes(0xff);
+  parallelFor(n, StrongestKernel{n, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, excluded, strongest.p});
+  const int kRounds = 6;
+  for (int r = 0; r < kRounds; r++) {
+    parallelFor(n, ProposeKernel{n, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, excluded, strongest.p, threshold,
+                                 root.p, propose.p});
+    parallelFor(n, HandshakeKernel{propose.p, root.p});
+  }
+  parallelFor(n, JoinKernel{n, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, excluded, root.p, join.p});
+  parallelFor(n, MergeJoinKernel{join.p, excluded, root.p, isRoot.p});
+  exclusiveScan(isRoot.p, rootScan.p, n);
+  nc = rootScan.hostAt(n);
+  ciNat.alloc(n);
+  parallelFor(n, AggIdKernel{root.p, rootScan.p, ciNat.p});
+  if (nc <= 0 || nc >= n) return false;
+  // members (natural coarse numbering)
+  DBuf<int> key(n), mem(n), memOff(nc + 2);
+  parallelFor(n, SortKeyKernel{ciNat.p, nc, key.p, mem.p});
+  int bits = 1;
+  while ((1LL << bits) < (long long)nc + 1) bits++;
+  sortPairs(key.p, mem.p, n, bits);
+  memOff.fillBytes(0xff);
+  parallelFor(n, MemOffKernel{key.p, memOff.p});
+  {  // if no excluded rows exist, memOff[nc] was set by the last element; otherwise by the first excluded
+    int last = memOff.hostAt(nc);
+    if (last < 0) { int nn = n; copyH2D(memOff.p + nc, &nn, sizeof(int)); }
+  }
+  // coarse matrix
+  DBuf<int> ub(nc + 1), ubOff(nc + 1), cnt(nc + 1);
+  parallelFor(nc, UpperBoundKernel{memOff.p, mem.p, F.sliceOff.p, ub.p});
+  exclusiveScan(ub.p, ubOff.p, nc);
+  const int ubTotal = ubOff.hostAt(nc);
+  DBuf<int> tmpCol(ubTotal > 0 ? ubTotal : 1);
+  DBuf<double> tmpVal(ubTotal > 0 ? ubTotal : 1);
+  cdiag.alloc(nc);
+  parallelFor(nc, CoarseRowKernel{n, memOff.p, mem.p, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, ciNat.p, ubOff.p,
+                                  tmpCol.p, tmpVal.p, cnt.p, cdiag.p});
+  crow.alloc(nc + 1);
+  exclusiveScan(cnt.p, crow.p, nc);
+  const int cnnz = crow.hostAt(nc);
+  ccol.alloc(cnnz > 0 ? cnnz : 1);
+  cval.alloc(cnnz > 0 ? cnnz : 1);
+  parallelFor(nc, CompactKernel{ubOff.p, crow.p, tmpCol.p, tmpVal.p, ccol.p, cval.p});
+  streamSync();
+  return true;
+}
+
+static void buildMembers(Level& F, int nc) {
+  // F.ci is in the coarse level's FINAL numbering; sort fine rows by it
+  const int n = F.n;
+  DBuf<int> key(n);
+  F.mem.alloc(n);
+  F.memOff.alloc(nc + 2);
+  parallelFor(n, SortKeyKernel{F.ci.p, nc, key.p, F.mem.p});
+  int bits = 1;
+  while ((1LL << bits) < (long long)nc + 1) bits++;
+  sortPairs(key.p, F.mem.p, n, bits);
+  F.memOff.fillBytes(0xff);
+  parallelFor(n, MemOffKernel{key.p, F.memOff.p});
+  int last = F.memOff.hostAt(nc);
+  if (last < 0) { int nn = n; copyH2D(F.memOff.p + nc, &nn, sizeof(int)); }
+}
+
+void Amg::cleanup() {
+  levels.clear();
+  builtFor = nullptr;
+  builtVersion = 0;
+}
+
+void Amg::setup(System* sys) {
+  requireReady();
+  levels.clear();
+  const int n = sys->nSelf;
+  // level 0 from the system's CSR; single GPU: ghost columns carry delta = 0 and are dropped
+  const bool dropGhost = !(sys->mesh && !sys->mesh->peers.empty());
+  levels.emplace_back(new Level);
+  buildLevelFromCsr(*levels[0], n, sys->row, sys->col, sys->off.p, sys->diag.p, dropGhost, perm0);
+  // rows marked as boundary inside the interior range (setDirichlet) are not coarsened
+  DBuf<int> excl0(n);
+  parallelFor(n, PermIntKernel{perm0.p, sys->isBoundary.p, excl0.p});
+
+  int passesPerLevel = 1;
+  while ((1 << passesPerLevel) < opts.coarseGroupSize) passesPerLevel++;
+  if (opts.coarseGroupSize <= 1) passesPerLevel = 0;
+
+  for (int lvl = 0; lvl < opts.maxCoarseLevels && passesPerLevel > 0; lvl++) {
+    Level& F = *levels.back();
+    if (F.n <= 1) break;
+    DBuf<int> ciNat, crow, ccol, perm;
+    DBuf<double> cval, cdiag;
+    int nc = 0;
+    const int* excl = (lvl == 0) ? excl0.p : nullptr;
+    if (!coarsenOnce(F, excl, opts.weightRatioThreshold, ciNat, nc, crow, ccol, cval, cdiag)) break;
+    std::unique_ptr<Level> C(new Level);
+    buildLevelFromCsr(*C, nc, crow.p, ccol.p, cval.p, cdiag.p, false, perm);
+    // coarseGroupSize > 2: pair again and compose the maps, dropping the intermediate level
+    for (int pass = 1; pass < passesPerLevel && C->n > 3; pass++) {
+      DBuf<int> ci2, crow2, ccol2, perm2;
+      DBuf<double> cval2, cdiag2;
+      int nc2 = 0;
+      parallelFor(F.n, RemapCiKernel{perm.p, ciNat.p});  // now in C numbering
+      if (!coarsenOnce(*C, nullptr, opts.weightRatioThreshold, ci2, nc2, crow2, ccol2, cval2, cdiag2)) {
+        // undo nothing: ciNat already final for C
+        perm.release();
+        break;
+      }
+      std::unique_ptr<Level> C2(new Level);
+      buildLevelFromCsr(*C2, nc2, crow2.p, ccol2.p, cval2.p, cdiag2.p, false, perm2);
+      // compose: fine -> C (ciNat) -> C2 natural (ci2) ; final remap by perm2 below
+      DBuf<int> composed(F.n);
+      parallelFor(F.n, ComposeKernel{ciNat.p, ci2.p, composed.p});
+      ciNat = std::move(composed);
+      perm = std::move(perm2);
+      C = std::move(C2);
+      nc = nc2;
+    }
+    if (perm.p) parallelFor(F.n, RemapCiKernel{perm.p, ciNat.p});
+    F.ci = std::move(ciNat);
+    buildMembers(F, C->n);
+    const int cn = C->n;
+    // reference (parallel build, F/AMG.cpp:171-180): push the level, then stop once it has <= 3 rows
+    levels.push_back(std::move(C));
+    if (cn <= 3) break;
+  }
+  streamSync();
+  builtFor = sys;
+  builtVersion = sys->version;
+}
+
+// ================================================================= cycle
+void Amg::sweeps(int nSweeps, int lvl) {
+  Level& L = *levels[lvl];
+  for (int s = 0; s < nSweeps; s++) {
+    if (opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL) {
+      for (int c = 0; c < L.nColours; c++) {
+        const int r0 = L.colourStart[c], cnt = L.colourStart[c + 1] - r0;
+        if (c == 0 && L.xZero) parallelFor(cnt, GsFirstColourZeroRows{r0, L.diag.p, L.b.p, L.x.p});
+        else parallelFor(cnt, GsRows{r0, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p});
+        L.xZero = false;
+      }
+      for (int c = L.nColours - 1; c >= 0; c--) {
+        const int r0 = L.colourStart[c], cnt = L.colourStart[c + 1] - r0;
+        parallelFor(cnt, GsRows{r0, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p});
+      }
+    } else {
+      // two Jacobi passes per sweep (F/AMG.cpp:59-63), ping-pong through r
+      parallelFor(L.n, JacobiRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p});
+      parallelFor(L.n, JacobiRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.r.p, L.x.p});
+      L.xZero = false;
+    }
+    L.rValid = false;
+  }
+}
+
+void Amg::residual(int lvl) {
+  Level& L = *levels[lvl];
+  parallelFor(L.n, ResidualRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p});
+  L.rValid = true;
+}
+
+double Amg::residualNorm(int lvl) {
+  Level& L = *levels[lvl];
+  reduceRows<1>(L.n, ResidualRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p}, scalars.p);
+  L.rValid = true;
+  double v;
+  copyD2H(&v, scalars.p, sizeof(double));
+  return v;
+}
+
+void Amg::cycle(int cycleType, int lvl) {
+  Level& L = *levels[lvl];
+  sweeps(opts.nPreSweeps, lvl);
+  if (lvl + 1 < (int)levels.size()) {
+    Level& C = *levels[lvl + 1];
+    const double* src;
+    if (L.xZero) src = L.b.p;  // r = b + A*0 = b exactly: skip the SpMV (nPreSweeps = 0 on a fresh level)
+    else {
+      if (!L.rValid) residual(lvl);
+      src = L.r.p;
+    }
+    parallelFor(C.n, InjectRows{L.memOff.p, L.mem.p, src, C.b.p, C.x.p});
+    C.xZero = true;
+    C.rValid = false;
+    cycle(cycleType, lvl + 1);
+    if (cycleType == FVMGPU_CYCLE_W) cycle(FVMGPU_CYCLE_W, lvl + 1);
+    else if (cycleType == FVMGPU_CYCLE_F) cycle(FVMGPU_CYCLE_V, lvl + 1);
+    parallelFor(L.n, CorrectRows{L.ci.p, C.x.p, L.x.p});
+    L.xZero = false;
+    L.rValid = false;
+  }
+  sweeps(opts.nPostSweeps, lvl);
+}
+
+void Amg::loadSystem(System* sys, const double* b_d, const double* x_d) {
+  Level& L0 = *levels[0];
+  parallelFor(L0.n, PermGatherKernel{perm0.p, b_d, L0.b.p});
+  if (x_d) { parallelFor(L0.n, PermGatherKernel{perm0.p, x_d, L0.x.p}); L0.xZero = false; }
+  else { L0.x.zero(); L0.xZero = true; }
+  L0.rValid = false;
+  (void)sys;
+}
+
+void Amg::storeDelta(double* delta_d) {
+  Level& L0 = *levels[0];
+  parallelFor(L0.n, PermScatterKernel{perm0.p, L0.x.p, delta_d});
+}
+
+void Amg::ensureSetup(System* sys) {
+  if (builtFor != sys || builtVersion != sys->version || levels.empty()) setup(sys);
+  if (!scalars.p) scalars.alloc(16);
+}
+
+// AMG::solve, F/AMG.cpp:219-282
+void Amg::solve(System* sys, double* rnorm0Out, double* rnormOut, int* itersOut) {
+  requireReady();
+  ensureSetup(sys);
+  history.clear();
+  loadSystem(sys, sys->b.p, sys->delta.p);
+  levels[0]->xZero = false;  // delta may be non-zero on entry
+  const double rNorm0 = residualNorm(0);
+  history.push_back(rNorm0);
+  double rNorm = rNorm0;
+  int iters = 0;
+  if (!(rNorm0 < opts.absoluteTolerance)) {
+    for (int i = 1; i < opts.nMaxIterations; i++) {
+      cycle(opts.cycleType, 0);
+      iters++;
+      rNorm = residualNorm(0);
+      history.push_back(rNorm);
+      if (rNorm < opts.absoluteTolerance || rNorm / rNorm0 < opts.relativeTolerance) break;
+    }
+  }
+  totalIterations += iters;
+  storeDelta(sys->delta.p);
+  if (rnorm0Out) *rnorm0Out = rNorm0;
+  if (rnormOut) *rnormOut = rNorm;
+  if (itersOut) *itersOut = iters;
+}
+
+// AMG::smooth, F/AMG.cpp:285-298: one cycle on (b, delta) of the system
+void Amg::smooth(System* sys) {
+  requireReady();
+  ensureSetup(sys);
+  loadSystem(sys, sys->b.p, sys->delta.p);
+  levels[0]->xZero = false;
+  cycle(opts.cycleType, 0);
+  storeDelta(sys->delta.p);
+}
+
+// one preconditioner application in LEVEL-0 numbering: xhat = cycle(b = rhs, x0 = 0)
+void Amg::precondition(const double* rhsPerm, double* outPerm) {
+  Level& L0 = *levels[0];
+  copyD2D(L0.b.p, rhsPerm, (size_t)L0.n * sizeof(double));
+  L0.x.zero();
+  L0.xZero = true;
+  L0.rValid = false;
+  cycle(opts.cycleType, 0);
+  copyD2D(outPerm, L0.x.p, (size_t)L0.n * sizeof(double));
+}
+
+// BCGStab::solve, F/BCGStab.cpp:26-170 (all vectors in level-0 numbering)
+void Amg::bcgstab(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0Out,
+                  double* rnormOut, int* itersOut) {
+  requireReady();
+  ensureSetup(sys);
+  history.clear();
+  Level& L0 = *levels[0];
+  const int n = L0.n;
+  DBuf<double> x(n), bOrig(n), r(n), rTilda(n), p(n), pHat(n), v(n), t(n);
+  parallelFor(n, PermGatherKernel{perm0.p, sys->b.p, bOrig.p});
+  parallelFor(n, PermGatherKernel{perm0.p, sys->delta.p, x.p});
+  auto A = [&](const double* xin) {
+    return MultiplyRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, xin, nullptr};
+  };
+  // r = b + A x ; rNorm0
+  reduceRows<1>(n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, bOrig.p, x.p, r.p}, scalars.p + 8);
+  double rNorm0;
+  copyD2H(&rNorm0, scalars.p + 8, sizeof(double));
+  history.push_back(rNorm0);
+  copyD2D(rTilda.p, r.p, (size_t)n * sizeof(double));
+  double* S = scalars.p;  // S[0]=rho S[1]=rhoPrev S[2]=alphaNum(rho) S[3]=alphaDen(rtv) S[4]=tdotr S[5]=tdott
+  double rNorm = rNorm0;
+  int iters = 0;
+  bool haveP = false;
+  for (int i = 0; i < nMaxIterations; i++) {
+    iters++;
+    copyD2D(S + 1, S + 0, sizeof(double));                       // rhoPrev = rho
+    reduceRows<1>(n, Dot1Rows{r.p, rTilda.p}, S + 0);            // rho = r . rTilda
+    if (!haveP) { copyD2D(p.p, r.p, (size_t)n * sizeof(double)); haveP = true; }
+    else parallelFor(n, BcgUpdateP{S, v.p, r.p, p.p});
+    precondition(p.p, pHat.p);                                   // pHat = M(p)
+    { MultiplyRows m = A(pHat.p); m.y = v.p; parallelFor(n, m); }  // v = A pHat
+    copyD2D(S + 2, S + 0, sizeof(double));                       // alpha = rho / (rTilda . v)
+    reduceRows<1>(n, Dot1Rows{rTilda.p, v.p}, S + 3);
+    parallelFor(n, MsaxpyScalarPtr{S + 2, S + 3, pHat.p, x.p});  // x -= alpha pHat
+    reduceRows<1>(n, MsaxpyScalarPtr{S + 2, S + 3, v.p, r.p}, S + 6);  // r -= alpha v ; |r|_1
+    copyD2H(&rNorm, S + 6, sizeof(double));
+    if (rNorm < absTol) break;
+    precondition(r.p, pHat.p);                                   // sHat = M(r)
+    { MultiplyRows m = A(pHat.p); m.y = t.p; parallelFor(n, m); }  // t = A sHat
+    reduceRows<2>(n, Dot2Rows{t.p, r.p}, S + 4);                 // (t.r, t.t)
+    parallelFor(n, MsaxpyScalarPtr{S + 4, S + 5, pHat.p, x.p});  // x -= omega sHat
+    reduceRows<1>(n, MsaxpyScalarPtr{S + 4, S + 5, t.p, r.p}, S + 6);  // r -= omega t ; |r|_1
+    copyD2H(&rNorm, S + 6, sizeof(double));
+    history.push_back(rNorm);
+    if (rNorm < absTol || rNorm / rNorm0 < relTol) break;
+  }
+  totalIterations += iters;
+  parallelFor(n, PermScatterKernel{perm0.p, x.p, sys->delta.p});
+  if (rnorm0Out) *rnorm0Out = rNorm0;
+  if (rnormOut) *rnormOut = rNorm;
+  if (itersOut) *itersOut = iters;
+}
+
+}  // namespace fvmgpu

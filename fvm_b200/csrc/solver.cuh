@@ -1,0 +1,70 @@
+// fvm_b200 / libfvmgpu -- AMG hierarchy and Krylov driver declarations (see solver.cu).
+#pragma once
+#include "structs.cuh"
+
+namespace fvmgpu {
+
+struct Level {
+  int n = 0;                 // solved rows of this level
+  long long nnzStored = 0;   // SELL elements incl. padding
+  long long nnzTrue = 0;     // off-diagonal entries
+  int nSlices = 0;
+  DBuf<int> sliceOff;        // nSlices+1 element offsets into scol/sval (multiples of 32)
+  DBuf<int> scol;
+  DBuf<double> sval;
+  DBuf<double> diag, b, x, r;
+  // colouring: rows [colourStart[c], colourStart[c+1]) have colour c
+  int nColours = 0;
+  std::vector<int> colourStart;
+  // link to the next coarser level (in ITS numbering)
+  DBuf<int> ci;              // n: coarse row of each fine row, -1 = not coarsened
+  DBuf<int> memOff, mem;     // coarse row -> its fine rows (ascending)
+  bool xZero = false;        // x is known to be identically zero
+  bool rValid = false;       // r holds b + A x for the current x
+};
+
+struct Amg {
+  fvmgpu_amg_opts opts;
+  std::vector<std::unique_ptr<Level>> levels;
+  DBuf<int> perm0;           // system (natural) row -> level-0 row
+  DBuf<double> scalars;      // device scalars for dots / norms
+  System* builtFor = nullptr;
+  unsigned long long builtVersion = 0;
+  std::vector<double> history;
+  long long totalIterations = 0;
+
+  void setup(System* sys);   // AMG::createCoarseLevels
+  void ensureSetup(System* sys);
+  void cleanup();
+  void solve(System* sys, double* rnorm0, double* rnorm, int* iters);
+  void smooth(System* sys);
+  void bcgstab(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0, double* rnorm,
+               int* iters);
+
+  void sweeps(int nSweeps, int lvl);
+  void residual(int lvl);
+  double residualNorm(int lvl);
+  void cycle(int cycleType, int lvl);
+  void loadSystem(System* sys, const double* b_d, const double* x_d);
+  void storeDelta(double* delta_d);
+  void precondition(const double* rhsPerm, double* outPerm);
+};
+
+// mesh.cu / assemble.cu entry points used by capi.cu
+Mesh* meshCreate(int dim, int nSelf, int nTotal, int nFaces, const int* faceCells, const int* ccRow,
+                 const int* ccCol, int nGroups, const int* gOff, const int* gCnt, const int* gId, const int* gKind);
+void meshSetGeometry(Mesh* m, const double* faceArea, const double* faceAreaMag, const double* faceCentroid,
+                     const double* cellCentroid, const double* cellVolume, const int* ibType);
+void meshSetHalo(Mesh* m, int nNeigh, const int* peerRank, const int* scatterOff, const int* scatterIdx,
+                 const int* gatherOff, const int* gatherIdx);
+System* systemCreate(Mesh* m);
+System* systemCreateRaw(int nSelf, int nGhost, const int* row, const int* col, const double* diag,
+                        const double* off, const double* b);
+void systemSetField(System* s, int field, const double* host, long long n, bool fill, double value);
+void systemGetField(System* s, int field, double* host, long long n);
+void systemSetBc(System* s, int groupId, int kind, const double* p, int np, const double* perFace);
+void computeGradient(System* s);
+void assemble(System* s, const fvmgpu_assemble_opts& o);
+void postSolveUpdate(System* s);
+
+}  // namespace fvmgpu

@@ -1,0 +1,204 @@
+/* fvmgpu.h -- C ABI of libfvmgpu.so: the B200 (sm_100a, FP64) implementation of MEMOSA-FVM's
+ * per-iteration hot path (cell-centred face-loop assembly + AMG / BCGStab linear solve).
+ *
+ * Plain C: opaque handles, raw pointers and sizes only. Unless a name ends in `_d` every
+ * pointer is HOST memory owned by the caller; the library copies what it needs during the
+ * call and never retains or frees a host pointer. All floating point is IEEE double, all
+ * indices int32. Every function returns 0 on success, non-zero on failure (the message is
+ * in fvmgpu_last_error()); no C++ exception crosses this boundary. There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails.
+ *
+ * Each entry point cites the reference interface it stands in for
+ * (paths relative to the reference tree; F/ = src/fvm/src/modules/fvmbase/).
+ * One caller thread per handle; one process per GPU (F/ has no threading either).
+ */
+#ifndef FVMGPU_H_
+#define FVMGPU_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FVMGPU_VERSION 100
+
+typedef struct fvmgpu_mesh_s* fvmgpu_mesh_t;     /* Mesh + StorageSite + CRConnectivity + GeomFields */
+typedef struct fvmgpu_system_s* fvmgpu_system_t; /* LinearSystem + CRMatrix<T,T,T> + its fields      */
+typedef struct fvmgpu_solver_s* fvmgpu_solver_t; /* AMG (optionally wrapped by BCGStab)              */
+
+/* ---- face-group kinds (FaceGroup::groupType, F/Mesh.h:28-43) ---- */
+enum {
+  FVMGPU_GROUP_INTERIOR = 0,
+  FVMGPU_GROUP_BOUNDARY = 1,  /* "wall", "velocity-inlet", "pressure-outlet", ...           */
+  FVMGPU_GROUP_INTERFACE = 2, /* partition interface (F/Mesh.cpp:267-274)                    */
+  FVMGPU_GROUP_SYMMETRY = 3   /* boundary whose ghost gradient is reflected (F/GradientModel.h:536-549) */
+};
+
+/* ---- boundary-condition kinds = GenericBCS::apply*BC (F/GenericBCS.h) ---- */
+enum {
+  FVMGPU_BC_DIRICHLET = 0,     /* applyDirichletBC     :77-115   p[0] = value                     */
+  FVMGPU_BC_NEUMANN = 1,       /* applyNeumannBC       :129-157  p[0] = specified flux (per area) */
+  FVMGPU_BC_EXTRAPOLATION = 2, /* applyExtrapolationBC :180-212                                   */
+  FVMGPU_BC_CONVECTIVE = 3,    /* applyConvectionBC    :214-245  p[0] = h, p[1] = Xinf            */
+  FVMGPU_BC_RADIATIVE = 4,     /* applyRadiationBC     :253-288  p[0] = emissivity, p[1] = Xinf   */
+  FVMGPU_BC_MIXED = 5,         /* applyMixedBC         :290-323  p[0] = h, p[1] = emissivity, p[2] = Xinf */
+  FVMGPU_BC_INTERFACE = 6,     /* applyInterfaceBC     :325-356                                   */
+  /* ThermalModel "SpecifiedTemperature" with a convecting flux present: per face
+   * extrapolation where flux>0 else Dirichlet (F/ThermalModel_impl.h:313-331); p[0] = value */
+  FVMGPU_BC_DIRICHLET_OR_OUTFLOW = 7
+};
+
+/* ---- named per-system device fields ---- */
+enum {
+  FVMGPU_FIELD_X = 0,          /* unknown, nCellsTotal (ls.getX(): aliases the model field)            */
+  FVMGPU_FIELD_DIFFUSIVITY = 1,/* nCellsTotal  (DiffusionDiscretization::_diffusivityField)           */
+  FVMGPU_FIELD_SOURCE = 2,     /* nCellsTotal  (SourceDiscretization::_sourceField)                   */
+  FVMGPU_FIELD_FACE_FLUX = 3,  /* nFaces       (ConvectionDiscretization::_convectingFluxField)       */
+  FVMGPU_FIELD_X_N1 = 4,       /* nCellsTotal  (TimeDerivativeDiscretization::_varN1Field)            */
+  FVMGPU_FIELD_X_N2 = 5,       /* nCellsTotal  (..::_varN2Field)                                      */
+  FVMGPU_FIELD_DENSITY = 6,    /* nCellsTotal  (..::_densityField; rho*cp for ThermalModel)           */
+  FVMGPU_FIELD_CONT_RESID = 7, /* nCellsTotal  (ConvectionDiscretization::_continuityResidualField)   */
+  FVMGPU_FIELD_GRADIENT = 8,   /* 3*nCellsTotal AoS (Gradient<T>, F/Gradient.h:199) -- output         */
+  FVMGPU_FIELD_BFLUX = 9,      /* nFaces: boundary flux unknowns (heatFlux, ls.getX()[fIndex]) -- output*/
+  FVMGPU_FIELD_DELTA = 10,     /* nCellsTotal  (ls.getDelta())                                        */
+  FVMGPU_FIELD_B = 11,         /* nCellsTotal  (ls.getB())                                            */
+  FVMGPU_FIELD_COUNT = 12
+};
+
+/* ---- assembly options: which Discretization objects of the list are present
+ *      (Linearizer::linearize, F/Linearizer.cpp:16-33; list built in
+ *      F/ThermalModel_impl.h:236-296) ---- */
+typedef struct {
+  int diffusion;        /* DiffusionDiscretization<T,T,T>       F/DiffusionDiscretization.h:65-232 */
+  int convection;       /* ConvectionDiscretization (upwind)    F/ConvectionDiscretization.h:166-199;
+                           2 = useCentralDifference branch :119-164 (incl. its x[c0]+x[c0] quirk)     */
+  int source;           /* SourceDiscretization                 F/SourceDiscretization.h:54-57      */
+  int time_order;       /* 0 steady, 1 / 2 = TimeDerivativeDiscretization order  :149-155 / :102-108 */
+  double dt;            /* time step for time_order>0                                               */
+  double underrelax;    /* >0: Underrelaxer diag /= urf          F/Underrelaxer.h:49-52; 0 = none    */
+  int apply_bcs;        /* run the per-group GenericBCS table set by fvmgpu_system_set_bc           */
+  int eliminate_boundary; /* LinearSystem::initSolve -> CRMatrix::eliminateBoundaryEquations
+                             F/LinearSystem.cpp:39-64, F/CRMatrix.h:899-944,1064-1085               */
+} fvmgpu_assemble_opts;
+
+/* ---- solver options = public tunables of AMG (F/AMG.h:74-81, defaults F/AMG.cpp:14-22)
+ *      and LinearSolver (F/LinearSolver.h:15-20) ---- */
+enum { FVMGPU_CYCLE_V = 0, FVMGPU_CYCLE_W = 1, FVMGPU_CYCLE_F = 2 };
+enum { FVMGPU_SMOOTHER_GAUSS_SEIDEL = 0, /* multicolour GS: forward = colours ascending, reverse = descending */
+       FVMGPU_SMOOTHER_JACOBI = 1 };
+typedef struct {
+  int nMaxIterations;
+  int verbosity;
+  double relativeTolerance;
+  double absoluteTolerance;
+  int maxCoarseLevels;
+  int nPreSweeps;
+  int nPostSweeps;
+  int coarseGroupSize;
+  double weightRatioThreshold;
+  int cycleType;
+  int smootherType;
+} fvmgpu_amg_opts;
+void fvmgpu_amg_default_opts(fvmgpu_amg_opts* o); /* the reference defaults */
+
+/* ---- library ---- */
+int fvmgpu_init(int device);                /* select device, create streams; idempotent */
+int fvmgpu_shutdown(void);
+const char* fvmgpu_last_error(void);        /* CException message equivalent (F/CException.h:16-21) */
+int fvmgpu_version(void);
+int fvmgpu_device_info(char* name, int cap, int* sm_count, double* mem_gb);
+int fvmgpu_synchronize(void);
+
+/* device-timeline stopwatch: CUDA events recorded on the library's compute stream */
+int fvmgpu_timer_start(int slot);           /* slot 0..15 */
+int fvmgpu_timer_stop(int slot, double* ms);/* records, synchronizes the stop event, returns elapsed */
+/* counts of kernels the library launched / bytes copied since init (gpu_launches claim) */
+int fvmgpu_counters(long long* kernel_launches, long long* h2d_bytes, long long* d2h_bytes);
+int fvmgpu_flush_l2(void);                  /* writes a 256 MiB scratch buffer (> 126 MB L2) */
+
+/* ---- mesh: what Mesh/StorageSite/CRConnectivity/GeomFields hold for one mesh ----
+ * faceCells[2*nFaces]        Mesh::getAllFaceCells()                  F/Mesh.h, F/CRConnectivity.h:48-222
+ * cellCellsRow/Col           Mesh::getCellCells() (diag implicit)     F/Mesh.cpp:479-492
+ * groups                     Mesh::getAllFaceGroups(): contiguous face ranges, interior first
+ * nCellsSelf/nCellsTotal     StorageSite::getSelfCount()/getCount()   F/StorageSite.h:18-112
+ */
+int fvmgpu_mesh_create(fvmgpu_mesh_t* out, int dim, int nCellsSelf, int nCellsTotal, int nFaces,
+                       const int* faceCells, const int* cellCellsRow, const int* cellCellsCol,
+                       int nGroups, const int* groupOffset, const int* groupCount,
+                       const int* groupId, const int* groupKind);
+/* GeomFields arrays (AoS Vector<double,3> as the reference stores them, F/Vector.h:229):
+ * area[3F], areaMag[F], coordinate[faces] (may be NULL), coordinate[cells][3Nt], volume[Nt],
+ * ibType[Nt] (may be NULL; anything but IBTYPE_FLUID=-1 is rejected: IB is out of scope).
+ * Also builds the least-squares gradient weights (GradientModel::getLeastSquaresGradientMatrix2D/3D,
+ * F/GradientModel.h:126-436), cached per mesh like the reference's static map (:453-468). */
+int fvmgpu_mesh_set_geometry(fvmgpu_mesh_t mesh, const double* faceArea, const double* faceAreaMag,
+                             const double* faceCentroid, const double* cellCentroid,
+                             const double* cellVolume, const int* ibType);
+/* StorageSite scatter/gather maps per neighbour rank (F/StorageSite.h:58-84); CSR-style offsets */
+int fvmgpu_mesh_set_halo(fvmgpu_mesh_t mesh, int nNeigh, const int* peerRank, const int* scatterOff,
+                         const int* scatterIdx, const int* gatherOff, const int* gatherIdx);
+int fvmgpu_mesh_destroy(fvmgpu_mesh_t mesh);
+/* parity hooks */
+int fvmgpu_mesh_download_pair_to_col(fvmgpu_mesh_t mesh, int* pairToCol /*2F*/); /* F/CRConnectivity.cpp:729-792 */
+int fvmgpu_mesh_download_gradient_weights(fvmgpu_mesh_t mesh, double* coeffs /*3*nnz AoS*/); /* GradientMatrix::_coeffs */
+
+/* ---- linear system on a mesh: CRMatrix<T,T,T>(cellCells) + x,b,delta,residual + per boundary
+ *      group FluxJacobianMatrix/DiagonalMatrix rows (F/ThermalModel_impl.h:181-234) ---- */
+int fvmgpu_system_create(fvmgpu_system_t* out, fvmgpu_mesh_t mesh);
+/* stand-alone system from a CSR pattern with separate diagonal, r = b + A x convention
+ * (MMReader::getLS, I/MMReader.cpp:79-184). Rows nSelf..nSelf+nGhost-1 are ghost rows. */
+int fvmgpu_system_create_raw(fvmgpu_system_t* out, int nSelf, int nGhost, const int* row,
+                             const int* col, const double* diag, const double* offdiag,
+                             const double* b);
+int fvmgpu_system_destroy(fvmgpu_system_t sys);
+int fvmgpu_system_set_field(fvmgpu_system_t sys, int field, const double* host, long long n);
+int fvmgpu_system_fill_field(fvmgpu_system_t sys, int field, double value);
+int fvmgpu_system_get_field(fvmgpu_system_t sys, int field, double* host, long long n);
+/* GenericBCS for one boundary group id; perFace (may be NULL) overrides p[0] per face
+ * (FloatValEvaluator with a Field, F/FloatVarDict.h:100-140) */
+int fvmgpu_system_set_bc(fvmgpu_system_t sys, int groupId, int bcKind, const double* p, int np,
+                         const double* perFace);
+
+/* GradientModel<T>::compute (F/GradientModel.h:472-602): gradient of FIELD_X into FIELD_GRADIENT,
+ * boundary ghost cells copy (or reflect, symmetry groups) the neighbour's gradient */
+int fvmgpu_compute_gradient(fvmgpu_system_t sys);
+/* initAssembly + Linearizer::linearize + BC loop (+ initSolve elimination): ONE fused
+ * gather kernel over rows, deterministic (no atomics), every output written once. */
+int fvmgpu_assemble(fvmgpu_system_t sys, const fvmgpu_assemble_opts* opts);
+/* parity hook: CRMatrix::getDiag()/getOffDiag() and ls.getB() (F/CRMatrix.h:856-865) */
+int fvmgpu_download_system(fvmgpu_system_t sys, double* diag /*Nt*/, double* offdiag /*nnz*/,
+                           double* b /*Nt*/, int* isBoundary /*Nt, may be NULL*/);
+
+/* ---- solvers: LinearSolver::{solve,smooth,cleanup} (F/LinearSolver.h:11-31) ---- */
+int fvmgpu_amg_create(fvmgpu_solver_t* out, const fvmgpu_amg_opts* opts);
+int fvmgpu_amg_set_opts(fvmgpu_solver_t s, const fvmgpu_amg_opts* opts);
+/* AMG::solve (F/AMG.cpp:219-282): builds the hierarchy when the system changed (createCoarseLevels
+ * :149-210), cycles until ||r||_1 < abs or ratio < rel. rnorm0 = initial residual 1-norm (the
+ * value the reference returns), iters = cycles run. delta is left in FIELD_DELTA. */
+int fvmgpu_amg_solve(fvmgpu_solver_t s, fvmgpu_system_t sys, double* rnorm0, double* rnorm,
+                     int* iters);
+int fvmgpu_amg_smooth(fvmgpu_solver_t s, fvmgpu_system_t sys); /* AMG::smooth :285-298 */
+int fvmgpu_amg_cleanup(fvmgpu_solver_t s);                      /* AMG::cleanup :212-217 */
+int fvmgpu_amg_destroy(fvmgpu_solver_t s);
+/* hierarchy report: sizes[l] rows and nnzs[l] off-diagonal entries per level (level 0 = finest) */
+int fvmgpu_amg_levels(fvmgpu_solver_t s, int cap, int* nLevels, long long* sizes, long long* nnzs,
+                      int* colours);
+/* residual history of the last solve: out[0..n-1], n returned */
+int fvmgpu_solver_history(fvmgpu_solver_t s, int cap, double* out, int* n);
+/* BCGStab::solve (F/BCGStab.cpp:26-170) right-preconditioned by one AMG cycle of `precond`;
+ * its own nMaxIterations / tolerances are passed here (LinearSolver fields of the BCGStab object) */
+int fvmgpu_bcgstab_solve(fvmgpu_solver_t precond, fvmgpu_system_t sys, int nMaxIterations,
+                         double relativeTolerance, double absoluteTolerance, double* rnorm0,
+                         double* rnorm, int* iters);
+/* LinearSystem::postSolve + updateSolution (F/LinearSystem.cpp:250-269): back-substitute the
+ * eliminated boundary rows, solve the boundary-flux rows, x += delta, flux += dflux */
+int fvmgpu_post_solve_update(fvmgpu_system_t sys);
+
+/* ---- multi-GPU plumbing (one process per GPU; NCCL resolved at run time with dlopen) ---- */
+int fvmgpu_comm_unique_id(void* out128);                               /* ncclGetUniqueId      */
+int fvmgpu_comm_init(int nranks, int rank, const void* uniqueId128);   /* ncclCommInitRank     */
+int fvmgpu_comm_destroy(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVMGPU_H_ */
