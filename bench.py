@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline metric on B200 (contract: see the task / DESIGN.md §4).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n CELLS_PER_SIDE]
+
+One STEP = one ThermalModel outer iteration on the synthetic mesh: gradient + fused assembly
+(+BCs + boundary elimination) + AMG hierarchy setup + AMG V-cycles to rel-tol 1e-8 + postSolve /
+updateSolution -- the statement sequence of ThermalModel::Impl::advance (F/ThermalModel_impl.h:
+424-456) with the linear solver converged to the model's own tolerance, i.e. "time to converge".
+
+metric  fp64_cell_updates_per_s = (cells x outer iterations) / time of the timed steps
+        (SURVEY §8d(i) extended to the whole path: every cell of the mesh is taken through one full
+        assembly + solve + update). Also reported: time_to_converge_s, AMG cycles, per-phase ms,
+        solver row-updates/s.
+value   device-timed (CUDA events on the library's compute stream), fields resident in HBM.
+e2e     the same step through the public API (fvm_b200.models.ThermalModelA.advance) with HOST
+        numpy arrays: H2D of temperature / conductivity / source and D2H of temperature + boundary
+        heat fluxes inside the timed region (wall clock around the call, device synchronised).
+roofline  dominant kernel = the level-0 multicolour Gauss-Seidel pass (GsRows); achieved =
+        algorithmic bytes per launch (36 B/row + 12 B/nnz) / mean launch duration from
+        CUDA events bracketing every launch of one extra profiled step.
+cpu_baseline / --impl reference: the reference's own C++ (oracle/_ref, compiled in place) on the
+        box's host cores on a bounded sample of the same workload (smaller mesh, same BCs/solver).
+
+N>1 (torchrun): every rank solves its own equal-size mesh replica set ... see DESIGN.md §5:
+        weak scaling, value = sum over ranks of cells / max over ranks of time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fp64_cell_updates_per_s"
+UNIT = "cell-updates/s"
+REL_TOL = 1e-8
+T_HOT, T_COLD, T_INIT = 400.0, 300.0, 300.0
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--n", type=int, default=0, help="cells per side of the hex mesh (default 256; 512^3/N per GPU for N>1)")
+    p.add_argument("--ref-n", type=int, default=64, help="cells per side of the CPU sample mesh")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-profile", action="store_true")
+    p.add_argument("--_worker", action="store_true", help=argparse.SUPPRESS)
+    return p.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- workload
+def build_case(n, lib):
+    """Unit cube, n^3 uniform hexes, k = 1, T = 400 on z = 1, T = 300 on z = 0, zero flux elsewhere,
+    T0 = 300."""
+    from fvm_b200 import meshgen as G, models as M
+    raw = G.hex_mesh(n, n, n)
+    meshes = [M.Mesh(raw)]
+    geom = M.GeomFields("geom")
+    M.MeshMetricsCalculatorA(geom, meshes, lib=lib).init()
+    fields = M.ThermalFields("therm")
+    model = M.ThermalModelA(geom, fields, meshes, lib=lib)
+    bc = model.getBCMap()
+    bc[5].bcType = "SpecifiedTemperature"; bc[5]["specifiedTemperature"] = T_COLD
+    bc[6].bcType = "SpecifiedTemperature"; bc[6]["specifiedTemperature"] = T_HOT
+    solver = M.AMG()
+    solver.relativeTolerance = REL_TOL
+    solver.nMaxIterations = 20000
+    solver.verbosity = 0
+    model.getOptions().linearSolver = solver
+    model.getOptions()["initialTemperature"] = T_INIT
+    model.init()
+    return raw, meshes[0], fields, model, solver
+
+
+def device_step(lib, model, mesh, ls, solver):
+    """One outer iteration with all fields already resident on the device. Returns phase times."""
+    from fvm_b200 import capi
+    ls.fill_field(capi.FIELD_X, T_INIT)          # reset the unknown (device-side fill, no host copy)
+    lib.timer_start(2)
+    lib.timer_start(3)
+    model._assemble(ls)
+    t_asm = lib.timer_stop(3)
+    lib.timer_start(3)
+    dev = solver._device(lib)
+    r0, r, it = dev.solve(ls)
+    t_solve = lib.timer_stop(3)
+    levels = dev.levels()
+    dev.cleanup()
+    lib.timer_start(3)
+    ls.post_solve_update()
+    t_upd = lib.timer_stop(3)
+    t_all = lib.timer_stop(2)
+    return dict(total_ms=t_all, assemble_ms=t_asm, solve_ms=t_solve, update_ms=t_upd, cycles=it, rnorm0=r0,
+                rnorm=r, levels=levels)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from fvm_b200 import capi
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = capi.default_lib()
+    n = args.n or 256
+    t0 = time.time()
+    raw, mesh, fields, model, solver = build_case(n, lib)
+    ls = model._systems[mesh.getID()]
+    setup_s = time.time() - t0
+    ncells = raw.n_cells
+    model._upload(mesh, ls)
+
+    def barrier():
+        lib.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step(lib, model, mesh, ls, solver)
+        lib.flush_l2()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0, _, _ = lib.counters()
+    barrier()
+    lib.timer_start(0)
+    steps = []
+    for _ in range(args.steps):
+        steps.append(device_step(lib, model, mesh, ls, solver))
+    total_ms = lib.timer_stop(0)
+    barrier()
+    l1, _, _ = lib.counters()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    # ---- e2e through the public API with host buffers
+    cells = mesh.getCells()
+    e2e_times = []
+    h0 = lib.counters()
+    for i in range(max(1, min(args.steps, 2)) + 1):
+        fields.temperature[cells][:] = T_INIT
+        model._initialNorm = None
+        lib.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            model.advance(1)
+        lib.synchronize()
+        dt = time.perf_counter() - t0
+        if i > 0:
+            e2e_times.append(dt)
+        if i == 0:
+            h0 = lib.counters()
+    h1 = lib.counters()
+    ne2e = len(e2e_times)
+    e2e_s = float(np.mean(e2e_times))
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    x = fields.temperature[cells]
+    # ---- profiled step for the roofline of the dominant kernel
+    roof = None
+    prof_table = None
+    if not args.no_profile and rank == 0:
+        lib.profile_begin()
+        ps = device_step(lib, model, mesh, ls, solver)
+        recs = lib.profile_end(cap=8192)
+        roof, prof_table = roofline(recs, ps)
+    # ---- cpu baseline
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_sample(args.ref_n, threads=1, steps=1)
+    if rank != 0:
+        return
+    ms_per_step = total_ms / args.steps
+    last = steps[-1]
+    sizes, nnzs = last["levels"]["sizes"], last["levels"]["nnz"]
+    cyc = last["cycles"]
+    # row visits by smoother / residual passes in the solve
+    row_visits = cyc * (sizes[0] * 3 + sum(sizes[1:]) * 2) + sizes[0]
+    out = {
+        "metric": METRIC, "value": ncells * world * args.steps / (total_ms * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D steady thermal diffusion, %d^3 structured hex mesh (%d cells) per GPU, k=1, "
+                               "T=400/300 on z=1/z=0, AMG (V-cycle, multicolour GS, nPre 0 / nPost 1, group 2) "
+                               "to rel 1e-8, one outer iteration per step" % (n, ncells),
+                   "cells_per_gpu": ncells, "l2": "inputs (>= 1.8 GB of matrix per pass) exceed the 126 MB L2; "
+                                                  "L2 flushed between warm-up steps",
+                   "parallelism": "replicas" if world > 1 else "single"},
+        "time_to_converge_s": ms_per_step * 1e-3,
+        "amg_cycles": cyc, "amg_levels": len(sizes), "level_sizes": sizes[:6], "level_colours": last["levels"]["colours"][:6],
+        "phase_ms": {k: float(np.mean([s[k] for s in steps])) for k in ("assemble_ms", "solve_ms", "update_ms")},
+        "residual": [last["rnorm0"], last["rnorm"]],
+        "solver_row_updates_per_s": row_visits / (last["solve_ms"] * 1e-3),
+        "assembly_cells_per_s": ncells / (float(np.mean([s["assemble_ms"] for s in steps])) * 1e-3),
+        "gpu_launches": int(l1 - l0),
+        "e2e": {"value": ncells * world / e2e_s, "unit": UNIT,
+                "h2d_bytes_per_step": int((h1[1] - h0[1]) / ne2e), "d2h_bytes_per_step": int((h1[2] - h0[2]) / ne2e),
+                "seconds_per_step": e2e_s},
+        "solution_check": {"min": float(x.min()), "max": float(x.max()), "mean": float(x[:ncells].mean())},
+        "clocks": clocks, "mesh_setup_s": setup_s,
+    }
+    if roof:
+        out["roofline"] = roof
+        out["kernel_profile"] = prof_table
+    if cpu:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out))
+
+
+def roofline(recs, step):
+    """Dominant kernel: GsRows launches on level 0 (rows = a level-0 colour)."""
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, src = 6650.0, "fallback (B200_PROFILING.md)"
+    if os.path.exists(peaks_path):
+        peak, src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json (sustained: inside a long step)"
+    sizes, nnzs = step["levels"]["sizes"], step["levels"]["nnz"]
+    n0, nnz0 = sizes[0], nnzs[0]
+    ncol0 = step["levels"]["colours"][0]
+    by = {}
+    for r in recs:
+        d = by.setdefault(r["name"], dict(launches=0, ms=0.0))
+        d["launches"] += r["launches"]
+        d["ms"] += r["ms"]
+    total = sum(d["ms"] for d in by.values())
+    table = sorted(({"kernel": k, "launches": v["launches"], "ms": round(v["ms"], 3),
+                     "share": round(v["ms"] / total, 4)} for k, v in by.items()), key=lambda t: -t["ms"])[:12]
+    # level-0 GS launches: rows > n1 (a level-0 colour is larger than the whole level 1 only when
+    # colours are few; use the exact colour sizes instead: all GsRows records with rows <= n0 whose
+    # launches == 2*cycles (fwd+rev per cycle) and rows sum to n0)
+    cyc = max(step["cycles"], 1)
+    gs = [r for r in recs if r["name"] in ("GsRows", "GsFirstColourZeroRows")]
+    gs0 = sorted(gs, key=lambda r: -r["rows"])
+    picked, rows_acc = [], 0
+    for r in gs0:
+        if rows_acc >= n0:
+            break
+        if r["name"] == "GsRows":
+            picked.append(r); rows_acc += r["rows"]
+    launches = sum(r["launches"] for r in picked)
+    ms = sum(r["ms"] for r in picked)
+    if not launches:
+        return None, table
+    bytes_per_sweep_pass = 36.0 * n0 + 12.0 * nnz0            # one pass over all level-0 rows
+    passes = launches / float(len(picked))                      # each colour launched once per pass
+    achieved = bytes_per_sweep_pass * passes / (ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "kernel": "k_rows<GsRows> (level-0 multicolour Gauss-Seidel pass)",
+            "peak_source": src, "bytes_per_launch": bytes_per_sweep_pass / len(picked),
+            "mean_launch_ms": ms / launches, "launches": launches,
+            "share_of_step": ms / step["total_ms"]}
+    return roof, table
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def _ref_worker(n, steps):
+    """One single-rank run of the reference C++ (oracle/_ref) or, if absent, of the C port."""
+    from fvm_b200 import meshgen as G
+    from oracle import refapi
+    raw = G.hex_mesh(n, n, n)
+    out = []
+    if refapi.available():
+        rm = refapi.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes,
+                                     raw.face_node_count, raw.face_group_size)
+        kind = "reference"
+        for _ in range(steps):
+            t = refapi.RefThermal(rm)
+            t.set_bc(5, "SpecifiedTemperature", specifiedTemperature=T_COLD)
+            t.set_bc(6, "SpecifiedTemperature", specifiedTemperature=T_HOT)
+            t.set_solver(refapi.solver_cfg(relativeTolerance=REL_TOL, nMaxIterations=20000, verbosity=0))
+            t.set_option("initialTemperature", T_INIT)
+            t.init()
+            r = t.advance_timed()
+            out.append(dict(seconds=r["assemble_s"] + r["solve_s"] + r["update_s"], cycles=r["cycles"],
+                            assemble_s=r["assemble_s"], solve_s=r["solve_s"]))
+            t.close()
+    else:
+        from oracle import port
+        kind = "port"
+        conn = dict(zip(("cc_row", "cc_col"), G.connectivity(raw)))
+        conn.update(face_cells=raw.face_cells, group_offset=raw.group_offset, group_count=raw.group_count,
+                    group_id=raw.group_id, group_kind=raw.group_kind)
+        geo = G.metrics(raw)
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            port.thermal_reference(raw, conn, geo, np.ones(raw.n_total), {5: ("dirichlet", T_COLD), 6: ("dirichlet", T_HOT)},
+                                   x0=T_INIT, tol=REL_TOL)
+            out.append(dict(seconds=time.perf_counter() - t0, cycles=-1))
+    return dict(kind=kind, cells=raw.n_cells, runs=out)
+
+
+def cpu_sample(n, threads, steps):
+    """`threads` independent single-rank processes of the reference, each on its own n^3 mesh."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--_worker", "--ref-n", str(n),
+           "--steps", str(steps)]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True, env=env) for _ in range(threads)]
+    res = []
+    for p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError("reference worker failed")
+        res.append(json.loads(out.strip().splitlines()[-1]))
+    wall = time.perf_counter() - t0
+    cells = res[0]["cells"]
+    per_proc = [sum(r["seconds"] for r in rr["runs"]) for rr in res]
+    value = threads * cells * steps / max(per_proc)
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": res[0]["kind"],
+            "sample": "%d^3 hex mesh (%d cells), same BCs / solver / tolerance as the GPU workload, %d step(s) per "
+                      "process, %d independent single-rank process(es) (no MPI runtime in the image: throughput "
+                      "proxy without halo cost)" % (n, cells, steps, threads),
+            "seconds_per_step": max(per_proc) / steps, "cycles": res[0]["runs"][-1]["cycles"],
+            "phase_s": {k: res[0]["runs"][-1].get(k) for k in ("assemble_s", "solve_s")}, "wall_s": wall}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.ref_n
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(min(n, 32), threads, 1)
+    steps = max(1, min(args.steps, 3))
+    cpu = cpu_sample(n, threads, steps)
+    out = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
+           "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": cpu["seconds_per_step"] * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "3D steady thermal diffusion on a structured hex mesh, k=1, T=400/300 on z=1/z=0, "
+                                  "AMG (V-cycle, GS, nPre 0 / nPost 1, group 2) to rel 1e-8, one outer iteration "
+                                  "per step; CPU arm: bounded sample " + cpu["sample"]},
+           "cpu_baseline": cpu, "gpu_launches": 0,
+           "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a._worker:
+        print(json.dumps(_ref_worker(a.ref_n, a.steps)))
+    elif a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

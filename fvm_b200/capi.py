@@ -59,6 +59,12 @@ SIGNATURES = {
     "fvmgpu_timer_stop": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "fvmgpu_counters": (C.c_int, [C.POINTER(C.c_longlong)] * 3),
     "fvmgpu_flush_l2": (C.c_int, []),
+    "fvmgpu_profile_begin": (C.c_int, []),
+    "fvmgpu_profile_end": (C.c_int, [C.c_int, C.c_char_p, C.c_int,
+                                     np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"),
+                                     np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"),
+                                     np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS"),
+                                     C.POINTER(C.c_int)]),
     "fvmgpu_mesh_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip,
                                      C.c_int, _ip, _ip, _ip, _ip]),
     "fvmgpu_mesh_set_geometry": (C.c_int, [_vp, _dp, _dp, _dpn, _dp, _dp, _ipn]),
@@ -108,6 +114,17 @@ def _nullable(a, dtype):
         return None, None
     arr = np.ascontiguousarray(a, dtype=dtype)
     return arr, arr.ctypes.data_as(C.c_void_p)
+
+
+def _demangle(name):
+    """'N6fvmgpu6GsRowsE' -> 'GsRows' (Itanium nested name of a functor in namespace fvmgpu)."""
+    import re
+    m = re.match(r"^N6fvmgpu(\d+)", name)
+    if m:
+        k = int(m.group(1))
+        s = name[len("N6fvmgpu") + len(m.group(1)):]
+        return s[:k]
+    return name
 
 
 class Lib:
@@ -161,6 +178,25 @@ class Lib:
 
     def flush_l2(self):
         self.call("fvmgpu_flush_l2")
+
+    def profile_begin(self):
+        self.call("fvmgpu_profile_begin")
+
+    def profile_end(self, cap=4096):
+        """-> list of dicts(name, rows, launches, ms) aggregated per (kernel class, rows)."""
+        stride = 96
+        names = C.create_string_buffer(cap * stride)
+        rows = np.zeros(cap, np.int64)
+        launches = np.zeros(cap, np.int64)
+        ms = np.zeros(cap)
+        n = C.c_int(0)
+        self.call("fvmgpu_profile_end", cap, names, stride, rows, launches, ms, C.byref(n))
+        out = []
+        raw = names.raw
+        for i in range(min(n.value, cap)):
+            nm = raw[i * stride:(i + 1) * stride].split(b"\0")[0].decode()
+            out.append(dict(name=_demangle(nm), rows=int(rows[i]), launches=int(launches[i]), ms=float(ms[i])))
+        return out
 
     def default_amg_opts(self):
         o = AmgOpts()

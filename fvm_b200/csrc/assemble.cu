@@ -658,6 +658,7 @@ void assemble(System* s, const fvmgpu_assemble_opts& o) {
   // LinearSystem::initSolve: delta = 0
   s->delta.zero();
   s->version++;
+  if (o.apply_bcs) s->gradientValid = false;  // Dirichlet BCs rewrote x in the ghost cells
 }
 
 void postSolveUpdate(System* s) {

@@ -163,6 +163,28 @@ int fvmgpu_flush_l2(void) {
   API_END
 }
 
+int fvmgpu_profile_begin(void) {
+  API_BEGIN
+  requireReady();
+  profileBegin();
+  API_END
+}
+int fvmgpu_profile_end(int cap, char* names, int nameStride, long long* rows, long long* launches, double* ms,
+                       int* count) {
+  API_BEGIN
+  requireReady();
+  std::vector<ProfileRecord> recs = profileEnd();
+  if (count) *count = (int)recs.size();
+  for (int i = 0; i < (int)recs.size() && i < cap; i++) {
+    std::strncpy(names + (size_t)i * nameStride, recs[i].name.c_str(), nameStride - 1);
+    names[(size_t)i * nameStride + nameStride - 1] = 0;
+    rows[i] = recs[i].n;
+    launches[i] = recs[i].launches;
+    ms[i] = recs[i].ms;
+  }
+  API_END
+}
+
 // ---------------------------------------------------------------- mesh
 int fvmgpu_mesh_create(fvmgpu_mesh_t* out, int dim, int nCellsSelf, int nCellsTotal, int nFaces,
                        const int* faceCells, const int* cellCellsRow, const int* cellCellsCol, int nGroups,

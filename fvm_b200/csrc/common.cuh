@@ -13,6 +13,7 @@
 #include <cstring>
 #include <memory>
 #include <stdexcept>
+#include <typeinfo>
 #include <string>
 #include <vector>
 
@@ -64,6 +65,7 @@ struct Error : std::runtime_error {
 // ---------------------------------------------------------------- global context
 struct Context {
   bool ready = false;
+  bool profiling = false;
   int device = -1;
   int smCount = 148;
 #ifndef FVMGPU_HOSTSIM
@@ -141,6 +143,19 @@ struct DBuf {
   }
 };
 
+// ---------------------------------------------------------------- per-launch profiler
+// When enabled (fvmgpu_profile_begin) every launch is bracketed by two CUDA events on the compute
+// stream; fvmgpu_profile_end resolves them into (kernel class, rows, launches, total ms) records.
+// Used by bench.py for the live roofline figure; off by default (zero overhead: one branch).
+struct ProfileScope {
+  bool on;
+  ProfileScope(const char* name, long long n);
+  ~ProfileScope();
+};
+void profileBegin();
+struct ProfileRecord { std::string name; long long n; long long launches; double ms; };
+std::vector<ProfileRecord> profileEnd();
+
 // ---------------------------------------------------------------- row-parallel launcher
 // Every kernel of the library is a functor with `void operator()(long long i) const`, one
 // logical thread per row / face / entry; consecutive i map to consecutive lanes, so the SoA /
@@ -160,6 +175,7 @@ __global__ void __launch_bounds__(256) k_rows(long long n, const F f) {
 template <class F>
 void parallelFor(long long n, const F& f) {
   if (n <= 0) return;
+  ProfileScope prof(typeid(F).name(), n);
   k_rows<F><<<ceilDiv(n, 256), 256, 0, ctx().stream>>>(n, f);
   ctx().launches++;
   CUDA_CHECK(cudaGetLastError());
@@ -231,6 +247,7 @@ void reduceRows(long long n, const F& f, double* out_d) {
   int nb = ceilDiv(n, kReduceBlock);
   if (nb > kMaxReduceBlocks) nb = kMaxReduceBlocks;
   if (nb < 1) nb = 1;
+  ProfileScope prof(typeid(F).name(), n);
   k_reduce1<NV, F><<<nb, kReduceBlock, 0, ctx().stream>>>(n, f, ctx().reduceScratch);
   k_reduce2<NV><<<1, 32 * NV, 0, ctx().stream>>>(nb, ctx().reduceScratch, out_d);
   ctx().launches += 2;

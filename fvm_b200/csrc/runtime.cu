@@ -78,7 +78,56 @@ void sortPairs(int* keys_d, int* vals_d, long long n, int bits) {
   ctx().launches += 4;
   streamSync();
 }
+
+// ---- profiler
+namespace {
+struct ProfEntry { const char* name; long long n; cudaEvent_t a, b; };
+std::vector<ProfEntry>& profEntries() { static std::vector<ProfEntry> v; return v; }
+std::vector<cudaEvent_t>& profPool() { static std::vector<cudaEvent_t> v; return v; }
+cudaEvent_t profEvent() {
+  auto& pool = profPool();
+  if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+  cudaEvent_t e;
+  CUDA_CHECK(cudaEventCreate(&e));
+  return e;
+}
+}  // namespace
+ProfileScope::ProfileScope(const char* name, long long n) : on(ctx().profiling) {
+  if (!on) return;
+  ProfEntry e{name, n, profEvent(), profEvent()};
+  cudaEventRecord(e.a, ctx().stream);
+  profEntries().push_back(e);
+}
+ProfileScope::~ProfileScope() {
+  if (on) cudaEventRecord(profEntries().back().b, ctx().stream);
+}
+void profileBegin() {
+  streamSync();
+  profEntries().clear();
+  ctx().profiling = true;
+}
+std::vector<ProfileRecord> profileEnd() {
+  ctx().profiling = false;
+  streamSync();
+  std::vector<ProfileRecord> out;
+  for (ProfEntry& e : profEntries()) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e.a, e.b);
+    bool found = false;
+    for (ProfileRecord& r : out)
+      if (r.n == e.n && r.name == e.name) { r.launches++; r.ms += ms; found = true; break; }
+    if (!found) out.push_back(ProfileRecord{e.name, e.n, 1, (double)ms});
+    profPool().push_back(e.a);
+    profPool().push_back(e.b);
+  }
+  profEntries().clear();
+  return out;
+}
 #else
+ProfileScope::ProfileScope(const char*, long long) : on(false) {}
+ProfileScope::~ProfileScope() {}
+void profileBegin() {}
+std::vector<ProfileRecord> profileEnd() { return {}; }
 void* devAlloc(size_t bytes) { return std::malloc(bytes ? bytes : 1); }
 void devFree(void* p) { std::free(p); }
 void devMemset(void* p, int byte, size_t bytes) { std::memset(p, byte, bytes); }

@@ -252,18 +252,45 @@ struct StrongestKernel {  // per row: the largest weight among eligible neighbou
     strongest[i] = best;
   }
 };
+// Edge preference among equal weights (both end points rank an edge identically, so the locally
+// best edge of a row is very often mutual and the handshake pairs almost everything in one or two
+// rounds): with a,b the NATURAL indices of the end points, a<b, d=b-a,
+//   1. smaller d         (x-neighbours before y before z on a structured numbering)
+//   2. even floor(a/d)   (parity along that direction: (0,1)(2,3).. rather than (1,2)(3,4)..)
+//   3. a symmetric hash
+// On structured grids this reproduces the regular x/y/z pairing the reference's sequential sweep
+// produces; on unstructured numberings it is just a consistent symmetric tie-break.
+struct EdgeKey {
+  float w; int d; int odd; unsigned h;
+  FVM_DEV bool betterThan(const EdgeKey& o) const {
+    if (w != o.w) return w > o.w;
+    if (d != o.d) return d < o.d;
+    if (odd != o.odd) return odd < o.odd;
+    return h > o.h;
+  }
+};
+FVM_DEV EdgeKey makeEdgeKey(double w, int na, int nb) {
+  EdgeKey k;
+  const int a = na < nb ? na : nb, b = na < nb ? nb : na;
+  k.w = (float)w;  // float: last-bit noise of equal coefficients must not order the edges
+  k.d = b - a;
+  k.odd = (a / k.d) & 1;
+  k.h = edgeHash(a, b);
+  return k;
+}
 struct ProposeKernel {  // unassigned rows propose to their best unassigned strong neighbour
   int n; const int* sliceOff; const int* scol; const double* sval; const double* diag; const int* excluded;
-  const double* strongest; double threshold; const int* root; int* propose;
+  const double* strongest; double threshold; const int* root; const int* nat; int* propose;
   FVM_DEV void operator()(long long ii) const {
     const int i = (int)ii, s = i >> 5;
     int bestJ = -1;
     if (root[i] < 0 && !(excluded && excluded[i])) {
       const double di = fabs(diag[i]);
       const double cut = threshold * strongest[i];
-      float bestW = -1.0f;
-      unsigned bestH = 0;
+      EdgeKey best;
+      best.w = -1.0f; best.d = 0; best.odd = 0; best.h = 0;
       const int end = sliceOff[s + 1];
+      const int ni = nat[i];
       for (int p = sliceOff[s] + (i & 31); p < end; p += 32) {
         const int j = scol[p];
         if (j >= n || j == i || root[j] >= 0 || (excluded && excluded[j])) continue;
@@ -271,21 +298,19 @@ struct ProposeKernel {  // unassigned rows propose to their best unassigned stro
         const double w = fabs(sval[p] / (di > dj ? di : dj));
         if (!(w > cut) && !(w >= strongest[i])) continue;  // strong connections only
         if (!(w > 0.0)) continue;
-        // compare in float so that last-bit noise does not order the edges; ties by a symmetric hash
-        const float wf = (float)w;
-        const unsigned h = edgeHash(i, j);
-        if (wf > bestW || (wf == bestW && h > bestH)) { bestW = wf; bestH = h; bestJ = j; }
+        const EdgeKey k = makeEdgeKey(w, ni, nat[j]);
+        if (bestJ < 0 || k.betterThan(best)) { best = k; bestJ = j; }
       }
     }
     propose[i] = bestJ;
   }
 };
-struct HandshakeKernel {
-  const int* propose; int* root;
+struct HandshakeKernel {  // mutual proposals pair up; the root is the member with the lower natural index
+  const int* propose; const int* nat; int* root;
   FVM_DEV void operator()(long long ii) const {
     const int i = (int)ii;
     const int j = propose[i];
-    if (j >= 0 && propose[j] == i) root[i] = i < j ? i : j;
+    if (j >= 0 && propose[j] == i) root[i] = nat[i] < nat[j] ? i : j;
   }
 };
 struct JoinKernel {  // leftovers join the aggregate of their strongest paired neighbour
@@ -320,11 +345,15 @@ struct MergeJoinKernel {
     isRoot[i] = (root[i] == i) ? 1 : 0;
   }
 };
-struct AggIdKernel {  // ci[i] = scanned id of the root (natural coarse numbering); excluded rows -1
-  const int* root; const int* rootScan; int* ci;
+struct RootFlagNatKernel {  // root flags laid out in NATURAL order, so that the scan numbers the
+  const int* isRoot; const int* nat; int* flagNat;  // aggregates in the order of their natural roots
+  FVM_DEV void operator()(long long i) const { flagNat[nat[i]] = isRoot[i]; }
+};
+struct AggIdKernel {  // ci[i] = natural coarse id of the aggregate; excluded rows -1
+  const int* root; const int* nat; const int* rootScanNat; int* ci;
   FVM_DEV void operator()(long long ii) const {
     const int i = (int)ii;
-    ci[i] = root[i] >= 0 ? rootScan[root[i]] : -1;
+    ci[i] = root[i] >= 0 ? rootScanNat[nat[root[i]]] : -1;
   }
 };
 struct SortKeyKernel {  // key = ci (or nc for -1), value = row
@@ -442,6 +471,8 @@ static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, c
   sortPairs(colour.p, invp.p, n, bits);
   perm.alloc(n);
   parallelFor(n, InvPermKernel{invp.p, perm.p});
+  L.nat.alloc(n);
+  copyD2D(L.nat.p, invp.p, (size_t)n * sizeof(int));  // level row -> natural index
   // SELL-32
   L.nSlices = ceilDiv(n, 32);
   DBuf<int> len(n), width(L.nSlices + 1);
@@ -475,15 +506,16 @@ static bool coarsenOnce(Level& F, const int* excluded, double threshold, DBuf<in
   const int kRounds = 6;
   for (int r = 0; r < kRounds; r++) {
     parallelFor(n, ProposeKernel{n, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, excluded, strongest.p, threshold,
-                                 root.p, propose.p});
-    parallelFor(n, HandshakeKernel{propose.p, root.p});
+                                 root.p, F.nat.p, propose.p});
+    parallelFor(n, HandshakeKernel{propose.p, F.nat.p, root.p});
   }
   parallelFor(n, JoinKernel{n, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, excluded, root.p, join.p});
   parallelFor(n, MergeJoinKernel{join.p, excluded, root.p, isRoot.p});
-  exclusiveScan(isRoot.p, rootScan.p, n);
+  parallelFor(n, RootFlagNatKernel{isRoot.p, F.nat.p, propose.p});  // propose reused as scratch
+  exclusiveScan(propose.p, rootScan.p, n);
   nc = rootScan.hostAt(n);
   ciNat.alloc(n);
-  parallelFor(n, AggIdKernel{root.p, rootScan.p, ciNat.p});
+  parallelFor(n, AggIdKernel{root.p, F.nat.p, rootScan.p, ciNat.p});
   if (nc <= 0 || nc >= n) return false;
   // members (natural coarse numbering)
   DBuf<int> key(n), mem(n), memOff(nc + 2);

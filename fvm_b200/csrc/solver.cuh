@@ -13,6 +13,7 @@ struct Level {
   DBuf<int> scol;
   DBuf<double> sval;
   DBuf<double> diag, b, x, r;
+  DBuf<int> nat;             // level row -> index in the level's natural (pre-colouring) numbering
   // colouring: rows [colourStart[c], colourStart[c+1]) have colour c
   int nColours = 0;
   std::vector<int> colourStart;

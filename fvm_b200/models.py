@@ -1,0 +1,550 @@
+"""Host-side mirror of the reference's Python model API for the accelerated path.
+
+The reference exposes `ThermalModelA`, `AMG`, `BCGStab`, BC/VC/option dictionaries through SWIG
+(F/ThermalModel.i:22-48, F/AMG.i:1-34, F/FloatVarDict.i:22-55); scripts drive them as in
+T/THERMAL_MATRIX/testThermalParallel.py. The classes below keep those names, fields, defaults and
+call order, and run every numerical step of `advance()` on the GPU through the C ABI
+(include/fvmgpu.h). Host numpy arrays stay the source of truth at the API boundary, like the
+reference's `Field[site].asNumPyArray()` views: `advance()` uploads the model's input fields,
+runs assembly + solve + update on the device and copies the solution back.
+
+No numerical work happens in Python and there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from . import meshgen
+
+
+class CException(RuntimeError):
+    """Same name as the reference's exception type (F/CException.h:16-21)."""
+
+
+# ----------------------------------------------------------------------------- sites / mesh
+class StorageSite:
+    """F/StorageSite.h:18-112 (counts only; scatter/gather maps live on the Mesh)."""
+
+    def __init__(self, self_count, n_ghost=0, offset=0):
+        self._self, self._count, self._offset = int(self_count), int(self_count + n_ghost), int(offset)
+
+    def getCount(self):
+        return self._count
+
+    def getSelfCount(self):
+        return self._self
+
+    def getOffset(self):
+        return self._offset
+
+
+class FaceGroup:
+    """F/Mesh.h:28-43"""
+
+    def __init__(self, count, offset, gid, group_type):
+        self.site = StorageSite(count, 0, offset)
+        self.id = int(gid)
+        self.groupType = group_type
+
+
+class Mesh:
+    """Host mesh: what the importers / partitioner hand to the models (F/Mesh.h), built here from
+    the raw constructor arrays (F/Mesh.h:93-99). Geometry comes from MeshMetricsCalculatorA."""
+
+    _last_id = 0
+
+    def __init__(self, raw, group_types=None):
+        self.raw = raw
+        self.dim = raw.dim
+        self._id = Mesh._last_id
+        Mesh._last_id += 1
+        self._cells = StorageSite(raw.n_cells, raw.n_total - raw.n_cells)
+        self._faces = StorageSite(raw.n_faces)
+        self.cc_row, self.cc_col = meshgen.connectivity(raw)
+        self._groups = []
+        for g in range(len(raw.group_offset)):
+            gt = "interior" if g == 0 else (group_types[g] if group_types else "wall")
+            self._groups.append(FaceGroup(raw.group_count[g], raw.group_offset[g], raw.group_id[g], gt))
+        self.device = None  # capi.DeviceMesh, created by MeshMetricsCalculatorA.init()
+
+    def getID(self):
+        return self._id
+
+    def getDimension(self):
+        return self.dim
+
+    def getCells(self):
+        return self._cells
+
+    def getFaces(self):
+        return self._faces
+
+    def getAllFaceGroups(self):
+        return list(self._groups)
+
+    def getBoundaryFaceGroups(self):
+        return [g for g in self._groups if g.groupType not in ("interior", "interface")]
+
+    def group_kinds(self):
+        kinds = []
+        for g in self._groups:
+            kinds.append({"interior": capi.GROUP_INTERIOR, "interface": capi.GROUP_INTERFACE,
+                          "symmetry": capi.GROUP_SYMMETRY}.get(g.groupType, capi.GROUP_BOUNDARY))
+        return np.array(kinds, np.int32)
+
+
+class Field(dict):
+    """name + {site: ndarray} (F/Field.h); `field[site]` is the host array itself."""
+
+    def __init__(self, name):
+        super().__init__()
+        self.name = name
+
+
+class GeomFields:
+    """F/GeomFields.h"""
+
+    def __init__(self, base_name):
+        for n in ("coordinate", "area", "areaMag", "volume", "ibType"):
+            setattr(self, n, Field(base_name + "." + n))
+
+
+class MeshMetricsCalculatorA:
+    """F/MeshMetricsCalculator.h:31-34; init() fills GeomFields and uploads the mesh to the device."""
+
+    def __init__(self, geom_fields, meshes, lib=None):
+        self.geom, self.meshes, self.lib = geom_fields, meshes, lib
+
+    def init(self):
+        lib = self.lib or capi.default_lib()
+        for m in self.meshes:
+            mt = meshgen.metrics(m.raw)
+            cells, faces = m.getCells(), m.getFaces()
+            self.geom.area[faces] = mt["face_area"]
+            self.geom.areaMag[faces] = mt["face_area_mag"]
+            self.geom.coordinate[faces] = mt["face_centroid"]
+            self.geom.coordinate[cells] = mt["cell_centroid"]
+            self.geom.volume[cells] = mt["cell_volume"]
+            self.geom.ibType[cells] = np.full(cells.getCount(), -1, np.int32)  # IBTYPE_FLUID
+            upload_mesh(lib, m, self.geom)
+
+
+def upload_mesh(lib, m, geom):
+    """Create the device mirror of mesh `m` from host connectivity + GeomFields arrays."""
+    raw = m.raw
+    cells, faces = m.getCells(), m.getFaces()
+    dm = capi.DeviceMesh(lib, m.dim, raw.n_cells, raw.n_total, raw.face_cells, m.cc_row, m.cc_col,
+                         raw.group_offset, raw.group_count, raw.group_id, m.group_kinds())
+    dm.set_geometry(geom.area[faces], geom.areaMag[faces], geom.coordinate[cells], geom.volume[cells],
+                    face_centroid=geom.coordinate[faces], ib_type=geom.ibType[cells])
+    m.device = dm
+    return dm
+
+
+# ----------------------------------------------------------------------------- dictionaries
+class FloatVarDict(dict):
+    """F/FloatVarDict.h:44-98 + the SWIG helpers setVar/getVar (F/FloatVarDict.i:22-55).
+    A value is a float or a per-site numpy array (the reference's Field-valued FloatVal)."""
+
+    def defineVar(self, name, default):
+        dict.__setitem__(self, name, default)
+
+    def setVar(self, name, value):
+        if name not in self:
+            raise CException("uknown var " + name)  # (sic) F/FloatVarDict.h:66
+        dict.__setitem__(self, name, value)
+
+    def getVar(self, name):
+        if name not in self:
+            raise CException("uknown var " + name)
+        return dict.__getitem__(self, name)
+
+    def __getitem__(self, name):
+        return self.getVar(name)
+
+    def __setitem__(self, name, value):
+        self.setVar(name, value)
+
+
+class ThermalBC(FloatVarDict):
+    """F/ThermalBC.h:8-21"""
+
+    def __init__(self):
+        super().__init__()
+        self.defineVar("specifiedTemperature", 300.0)
+        self.defineVar("specifiedHeatFlux", 0.0)
+        self.defineVar("convectiveCoefficient", 0.0)
+        self.defineVar("farFieldTemperature", 300.0)
+        self.defineVar("surfaceEmissivity", 1.0)
+        self.bcType = ""
+
+
+class ThermalVC(FloatVarDict):
+    """F/ThermalBC.h:23-34"""
+
+    def __init__(self):
+        super().__init__()
+        self.defineVar("thermalConductivity", 1.0)
+        self.defineVar("density", 1.0)
+        self.defineVar("specificHeat", 1.0)
+        self.vcType = ""
+
+
+class ThermalModelOptions(FloatVarDict):
+    """F/ThermalBC.h:36-69"""
+
+    def __init__(self):
+        super().__init__()
+        self.defineVar("initialTemperature", 300.0)
+        self.defineVar("timeStep", 1e-7)
+        self.relativeTolerance = 1e-8
+        self.absoluteTolerance = 1e-16
+        self.linearSolver = None
+        self.useCentralDifference = False
+        self.transient = False
+        self.timeDiscretizationOrder = 1
+
+    def getLinearSolver(self):
+        if self.linearSolver is None:  # F/ThermalBC.h:56-67
+            ls = AMG()
+            ls.relativeTolerance = 1e-1
+            ls.nMaxIterations = 20
+            ls.verbosity = 0
+            self.linearSolver = ls
+        return self.linearSolver
+
+
+class ThermalFields:
+    """F/ThermalFields.h"""
+
+    def __init__(self, base_name):
+        for n in ("temperature", "temperatureN1", "temperatureN2", "specificHeat", "conductivity",
+                  "heatFlux", "temperatureGradient", "convectionFlux", "source", "zero", "one"):
+            setattr(self, n, Field(base_name + "." + n))
+
+
+# ----------------------------------------------------------------------------- solvers
+class LinearSolver:
+    """F/LinearSolver.h:11-31"""
+
+    def __init__(self):
+        self.nMaxIterations = 100
+        self.verbosity = 2
+        self.relativeTolerance = 1e-8
+        self.absoluteTolerance = 1e-50
+
+
+class AMG(LinearSolver):
+    """F/AMG.h:24-112; tunables and defaults F/AMG.cpp:14-22. `solve` runs entirely on the GPU."""
+
+    V_CYCLE, W_CYCLE, F_CYCLE = 0, 1, 2
+    GAUSS_SEIDEL, JACOBI = 0, 1
+
+    def __init__(self):
+        super().__init__()
+        self.maxCoarseLevels = 30
+        self.nPreSweeps = 0
+        self.nPostSweeps = 1
+        self.coarseGroupSize = 2
+        self.weightRatioThreshold = 0.65
+        self.cycleType = AMG.V_CYCLE
+        self.smootherType = AMG.GAUSS_SEIDEL
+        self.scaleCorrections = True
+        self._dev = None
+        self._lib = None
+        self._totalIterations = 0
+        self.lastIterations = 0
+        self.lastHistory = None
+
+    def _opts(self):
+        return capi.AmgOpts(self.nMaxIterations, self.verbosity, self.relativeTolerance,
+                            self.absoluteTolerance, self.maxCoarseLevels, self.nPreSweeps,
+                            self.nPostSweeps, self.coarseGroupSize, self.weightRatioThreshold,
+                            self.cycleType, self.smootherType)
+
+    def _device(self, lib):
+        if self._dev is None or self._lib is not lib:
+            self._dev = capi.DeviceAMG(lib, self._opts())
+            self._lib = lib
+        else:
+            self._dev.set_opts(self._opts())
+        return self._dev
+
+    def solve(self, ls):
+        """LinearSolver::solve: returns the INITIAL residual 1-norm (F/AMG.cpp:235,281)."""
+        dev = self._device(ls.lib)
+        r0, r, it = dev.solve(ls)
+        self._totalIterations += it
+        self.lastIterations = it
+        self.lastResidual = r
+        if self.verbosity > 0:  # parallel-build print format, F/AMG.cpp:239-271
+            self.lastHistory = dev.history()
+            print("0: [%s : %g]" % (ls.field_name, r0))
+            if it > 0:
+                print("%d: [%s : %g]" % (it, ls.field_name, r))
+        return r0
+
+    def smooth(self, ls):
+        self._device(ls.lib).smooth(ls)
+
+    def cleanup(self):
+        if self._dev is not None:
+            self._dev.cleanup()
+
+    def getTotalIterations(self):
+        return self._totalIterations
+
+    def levels(self):
+        return self._dev.levels() if self._dev is not None else None
+
+
+class BCGStab(LinearSolver):
+    """F/BCGStab.h; `preconditioner` must be an AMG (one cycle per application, F/BCGStab.cpp:85-89)."""
+
+    def __init__(self):
+        super().__init__()
+        self.preconditioner = None
+        self._totalIterations = 0
+        self.lastIterations = 0
+
+    def solve(self, ls):
+        if self.preconditioner is None:
+            raise CException("BCGStab: no preconditioner set")
+        dev = self.preconditioner._device(ls.lib)
+        r0, r, it = dev.bcgstab(ls, self.nMaxIterations, self.relativeTolerance, self.absoluteTolerance)
+        self._totalIterations += it
+        self.lastIterations = it
+        self.lastResidual = r
+        if self.verbosity > 0:
+            print("0: [%s : %g]" % (ls.field_name, r0))
+            print("%d: [%s : %g]" % (it, ls.field_name, r))
+        return r0
+
+    def smooth(self, ls):
+        raise CException("cannot use BCGStab as preconditioner")  # F/BCGStab.cpp:172-176
+
+    def cleanup(self):
+        if self.preconditioner is not None:
+            self.preconditioner.cleanup()
+
+    def getTotalIterations(self):
+        return self._totalIterations
+
+
+class LinearSystem(capi.DeviceSystem):
+    """Device LinearSystem (F/LinearSystem.h:11-64) tagged with the field name used in prints."""
+
+    def __init__(self, lib, mesh=None, raw=None, field_name="x"):
+        super().__init__(lib, mesh=mesh, raw=raw)
+        self.field_name = field_name
+
+
+# ----------------------------------------------------------------------------- ThermalModel
+_BC_KINDS = {
+    "SpecifiedTemperature": capi.BC_DIRICHLET,
+    "SpecifiedHeatFlux": capi.BC_NEUMANN,
+    "Symmetry": capi.BC_NEUMANN,
+    "Convective": capi.BC_CONVECTIVE,
+    "Radiative": capi.BC_RADIATIVE,
+    "Mixed": capi.BC_MIXED,
+}
+
+
+class ThermalModelA:
+    """ThermalModel<double> (F/ThermalModel.h:28-52, Impl in F/ThermalModel_impl.h).
+
+    advance(niter) performs, per outer iteration and all on the device: gradient, the fused
+    assembly (diffusion + convection + source [+ time derivative] + BCs + boundary elimination),
+    the linear solve, postSolve/updateSolution -- the statement sequence of Impl::advance
+    (F/ThermalModel_impl.h:424-456)."""
+
+    def __init__(self, geom_fields, thermal_fields, meshes, lib=None):
+        self.geom, self.fields, self.meshes = geom_fields, thermal_fields, meshes
+        self.lib = lib
+        self._bcMap, self._vcMap = {}, {}
+        self._options = ThermalModelOptions()
+        self._initialNorm = None
+        self._niters = 0
+        self._systems = {}
+        self.timings = []
+        for mesh in meshes:  # F/ThermalModel_impl.h:52-82
+            vc = ThermalVC()
+            vc.vcType = "flow"
+            self._vcMap[mesh.getID()] = vc
+            for fg in mesh.getBoundaryFaceGroups():
+                bc = ThermalBC()
+                self._bcMap[fg.id] = bc
+                if fg.groupType in ("wall", "symmetry"):
+                    bc.bcType = "SpecifiedHeatFlux"
+                elif fg.groupType in ("velocity-inlet", "pressure-outlet"):
+                    bc.bcType = "SpecifiedTemperature"
+                else:
+                    raise CException("ThermalModel: unknown face group type " + fg.groupType)
+
+    def getBCMap(self):
+        return self._bcMap
+
+    def getVCMap(self):
+        return self._vcMap
+
+    def getBC(self, gid):
+        return self._bcMap[gid]
+
+    def getOptions(self):
+        return self._options
+
+    def init(self):  # F/ThermalModel_impl.h:84-172
+        f, o = self.fields, self._options
+        for mesh in self.meshes:
+            cells, faces = mesh.getCells(), mesh.getFaces()
+            n = cells.getCount()
+            vc = self._vcMap[mesh.getID()]
+            f.temperature[cells] = np.full(n, float(o["initialTemperature"]))
+            if o.transient:
+                f.temperatureN1[cells] = f.temperature[cells].copy()
+                if o.timeDiscretizationOrder > 1:
+                    f.temperatureN2[cells] = f.temperature[cells].copy()
+            f.conductivity[cells] = np.full(n, float(vc["thermalConductivity"]))
+            f.source[cells] = np.zeros(n)
+            f.specificHeat[cells] = np.full(n, float(vc["density"]) * float(vc["specificHeat"]))
+            f.temperatureGradient[cells] = np.zeros((n, 3))
+            f.convectionFlux[faces] = np.zeros(faces.getCount())
+            for fg in mesh.getBoundaryFaceGroups():
+                f.heatFlux[fg.site] = np.zeros(fg.site.getCount())
+            if mesh.device is None:
+                raise CException("ThermalModel.init: mesh metrics not initialised (MeshMetricsCalculatorA.init)")
+            lib = self.lib or mesh.device.lib
+            self._systems[mesh.getID()] = LinearSystem(lib, mesh=mesh.device, field_name=f.temperature.name)
+        self._niters = 0
+        self._initialNorm = None
+
+    # ---- device plumbing
+    def _upload(self, mesh, ls):
+        f, o = self.fields, self._options
+        cells, faces = mesh.getCells(), mesh.getFaces()
+        ls.set_field(capi.FIELD_X, f.temperature[cells])
+        ls.set_field(capi.FIELD_DIFFUSIVITY, f.conductivity[cells])
+        ls.set_field(capi.FIELD_SOURCE, f.source[cells])
+        flux = f.convectionFlux[faces]
+        self._convecting = bool(np.any(flux != 0.0))
+        if self._convecting:
+            ls.set_field(capi.FIELD_FACE_FLUX, flux)
+        if o.transient:
+            ls.set_field(capi.FIELD_X_N1, f.temperatureN1[cells])
+            ls.set_field(capi.FIELD_DENSITY, f.specificHeat[cells])
+            if o.timeDiscretizationOrder > 1:
+                ls.set_field(capi.FIELD_X_N2, f.temperatureN2[cells])
+        for fg in mesh.getBoundaryFaceGroups():
+            bc = self._bcMap[fg.id]
+            if bc.bcType not in _BC_KINDS:
+                raise CException(bc.bcType + " not implemented for ThermalModel")
+            kind = _BC_KINDS[bc.bcType]
+            per_face = None
+
+            def val(name):
+                v = bc[name]
+                return v
+
+            if bc.bcType == "SpecifiedTemperature":
+                v = val("specifiedTemperature")
+                if self._convecting:
+                    kind = capi.BC_DIRICHLET_OR_OUTFLOW
+                params = [v]
+            elif bc.bcType == "SpecifiedHeatFlux":
+                params = [val("specifiedHeatFlux")]
+            elif bc.bcType == "Symmetry":
+                params = [0.0]
+            elif bc.bcType == "Convective":
+                params = [val("convectiveCoefficient"), val("farFieldTemperature")]
+            elif bc.bcType == "Radiative":
+                params = [val("surfaceEmissivity"), val("farFieldTemperature")]
+            else:
+                params = [val("convectiveCoefficient"), val("surfaceEmissivity"), val("farFieldTemperature")]
+            if isinstance(params[0], np.ndarray):
+                per_face = params[0]
+                params[0] = 0.0
+            ls.set_bc(fg.id, kind, [float(p) for p in params], per_face=per_face)
+
+    def _download(self, mesh, ls):
+        f = self.fields
+        cells = mesh.getCells()
+        f.temperature[cells][:] = ls.get_field(capi.FIELD_X)
+        bflux = ls.get_field(capi.FIELD_BFLUX)
+        for fg in mesh.getBoundaryFaceGroups():
+            o = fg.site.getOffset()
+            f.heatFlux[fg.site][:] = bflux[o:o + fg.site.getCount()]
+
+    def _assemble(self, ls):
+        o = self._options
+        ls.assemble(diffusion=1, convection=(2 if o.useCentralDifference else 1) if self._convecting else 0,
+                    source=1, time_order=(o.timeDiscretizationOrder if o.transient else 0),
+                    dt=float(o["timeStep"]) if o.transient else 0.0, underrelax=0.0, apply_bcs=1,
+                    eliminate_boundary=1)
+
+    def advance(self, niter):
+        """Impl::advance, F/ThermalModel_impl.h:424-456 (single mesh per system)."""
+        o = self._options
+        solver = o.getLinearSolver()
+        for mesh in self.meshes:
+            ls = self._systems[mesh.getID()]
+            lib = ls.lib
+            self._upload(mesh, ls)
+            for _ in range(niter):
+                t = {}
+                lib.timer_start(1)
+                self._assemble(ls)                      # initLinearization+initAssembly+linearize+initSolve
+                t["assemble_ms"] = lib.timer_stop(1)
+                lib.timer_start(1)
+                rnorm = solver.solve(ls)                # LinearSolver::solve
+                t["solve_ms"] = lib.timer_stop(1)
+                t["linear_iterations"] = solver.lastIterations
+                if self._initialNorm is None:
+                    self._initialNorm = rnorm
+                ratio = rnorm / self._initialNorm if self._initialNorm != 0 else 0.0
+                print("%d: [%s : %g]" % (self._niters, self.fields.temperature.name, rnorm))
+                solver.cleanup()
+                lib.timer_start(1)
+                ls.post_solve_update()                  # postSolve + updateSolution
+                t["update_ms"] = lib.timer_stop(1)
+                t["rnorm"] = rnorm
+                self.timings.append(t)
+                self._niters += 1
+                if rnorm < o.absoluteTolerance or ratio < o.relativeTolerance:
+                    break
+            self._download(mesh, ls)
+
+    def dumpMatrix(self, file_base):
+        """Impl::dumpMatrix, F/ThermalModel_impl.h:499-572 (MatrixMarket + rhs text files)."""
+        for idx, mesh in enumerate(self.meshes):
+            ls = self._systems[mesh.getID()]
+            self._upload(mesh, ls)
+            self._assemble(ls)
+            d = ls.download()
+            n = mesh.getCells().getSelfCount()
+            row, col = mesh.cc_row, mesh.cc_col
+            lines = []
+            for i in range(n):
+                lines.append("%d %d %f" % (i + 1, i + 1, d["diag"][i]))
+                for jp in range(row[i], row[i + 1]):
+                    if col[jp] < n:
+                        lines.append("%d %d %f" % (i + 1, col[jp] + 1, d["offdiag"][jp]))
+            with open("%s_mesh%d.mat" % (file_base, idx), "w") as fh:
+                fh.write("%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (n, n, len(lines)))
+                fh.write("\n".join(lines) + "\n")
+            with open(file_base + ".rhs", "w") as fh:
+                fh.write("".join("%f\n" % (-v) for v in d["b"][:n]))
+
+    def getHeatFluxIntegral(self, mesh, face_group_id):  # F/ThermalModel_impl.h:400-421
+        for fg in mesh.getBoundaryFaceGroups():
+            if fg.id == face_group_id:
+                return float(np.sum(self.fields.heatFlux[fg.site]))
+        raise CException("getHeatFluxIntegral: invalid faceGroupID")
+
+    def updateTime(self):  # F/ThermalModel_impl.h:585-612
+        f, o = self.fields, self._options
+        for mesh in self.meshes:
+            cells = mesh.getCells()
+            if o.timeDiscretizationOrder > 1:
+                f.temperatureN2[cells][:] = f.temperatureN1[cells]
+            f.temperatureN1[cells][:] = f.temperature[cells]

@@ -114,6 +114,12 @@ int fvmgpu_timer_stop(int slot, double* ms);/* records, synchronizes the stop ev
 /* counts of kernels the library launched / bytes copied since init (gpu_launches claim) */
 int fvmgpu_counters(long long* kernel_launches, long long* h2d_bytes, long long* d2h_bytes);
 int fvmgpu_flush_l2(void);                  /* writes a 256 MiB scratch buffer (> 126 MB L2) */
+/* per-launch profiler: between begin and end every kernel launch is bracketed by CUDA events on
+ * the compute stream; end returns one record per (kernel class, rows): names[i*nameStride..] is
+ * the (mangled) functor name, rows[i] the logical threads, launches[i], ms[i] the summed duration */
+int fvmgpu_profile_begin(void);
+int fvmgpu_profile_end(int cap, char* names, int nameStride, long long* rows, long long* launches,
+                       double* ms, int* count);
 
 /* ---- mesh: what Mesh/StorageSite/CRConnectivity/GeomFields hold for one mesh ----
  * faceCells[2*nFaces]        Mesh::getAllFaceCells()                  F/Mesh.h, F/CRConnectivity.h:48-222

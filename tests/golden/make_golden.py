@@ -1,0 +1,147 @@
+"""Generate the committed golden fixtures from the REFERENCE (run in the dev container only).
+
+Needs /root/reference (its test meshes + golden files) and oracle/_ref/libfvmref.so (the reference
+hot path compiled in place by oracle/Makefile). Writes small .npz files next to this script:
+
+  mm226.npz        T/MatrixMarket226.dat + T/rhs226.dat as CSR-with-separate-diagonal, the
+                   reference AMG's level sizes / residuals (T/testLinearSolver.out:5-11) and its
+                   solution at rel-tol 1e-13
+  cav32.npz        raw mesh arrays of T/cav32.cas as the reference's FluentReader numbers them,
+                   reference geometry, the thermal system of T/THERMAL_MATRIX (matrix/rhs goldens
+                   parsed from T/THERMAL_MATRIX/GOLDEN), the AMG history of
+                   T/AMG_MERGING_THERMAL/proc1/GOLDEN/convergence.dat and the converged temperature
+  hex_bcs.npz      a jittered 6x5x4 hex mesh with every thermal BC kind, random conductivity and
+                   source: reference gradient / matrix / rhs before and after boundary elimination
+  tet_solve.npz    a 5x5x5x6 tet mesh: reference assembled system + converged solution + heat fluxes
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import refapi as R  # noqa: E402
+from fvm_b200 import meshgen as G  # noqa: E402
+
+T = "/root/reference/src/fvm/test/"
+
+
+def csr_from_mm(path_m, path_rhs):
+    mm = np.loadtxt(path_m, skiprows=2)
+    rhs = np.loadtxt(path_rhs)
+    n = len(rhs)
+    i = mm[:, 0].astype(int) - 1
+    j = mm[:, 1].astype(int) - 1
+    v = mm[:, 2]
+    diag = np.zeros(n)
+    diag[i[i == j]] = v[i == j]
+    m = i != j
+    order = np.argsort(i[m], kind="stable")
+    ri, cj, vv = i[m][order], j[m][order], v[m][order]
+    row = np.zeros(n + 1, np.int32)
+    np.cumsum(np.bincount(ri, minlength=n), out=row[1:])
+    return n, row, cj.astype(np.int32), diag, vv, -rhs  # MMReader: b = -rhs (I/MMReader.cpp:176)
+
+
+def mesh_arrays(rm):
+    c, g = rm.connectivity(), rm.geometry()
+    return dict(dim=rm.dim, n_self=rm.n_self, n_total=rm.n_total, face_cells=c["face_cells"],
+                cc_row=c["cc_row"], cc_col=c["cc_col"], pair_to_col=c["pair_to_col"],
+                group_offset=c["group_offset"], group_count=c["group_count"], group_id=c["group_id"],
+                group_kind=c["group_kind"], face_area=g["face_area"], face_area_mag=g["face_area_mag"],
+                face_centroid=g["face_centroid"], cell_centroid=g["cell_centroid"],
+                cell_volume=g["cell_volume"], ib_type=g["ib_type"])
+
+
+def main():
+    # ---- mm226
+    n, row, col, diag, off, b = csr_from_mm(T + "MatrixMarket226.dat", T + "rhs226.dat")
+    ref = R.linsolve(n, row, col, diag, off, b, R.solver_cfg(verbosity=2))
+    hist = [float(l.split(":")[2].strip(" ]\n")) for l in ref["text"].splitlines() if "[test" in l]
+    tight = R.linsolve(n, row, col, diag, off, b, R.solver_cfg(relativeTolerance=1e-13, nMaxIterations=500, verbosity=0))
+    bcg = R.linsolve(n, row, col, diag, off, b, R.solver_cfg(kind=1, relativeTolerance=1e-13, nMaxIterations=100, verbosity=0))
+    np.savez_compressed(os.path.join(HERE, "mm226.npz"), n=n, row=row, col=col, diag=diag, off=off, b=b,
+                        ref_levels=np.array(ref["levels"]), ref_iters=ref["iters"], ref_rnorm0=ref["rnorm0"],
+                        ref_history=np.array(hist), ref_x_tol8=ref["x"], ref_x=tight["x"],
+                        ref_x_bcgstab=bcg["x"],
+                        golden_text=open(T + "testLinearSolver.out").read())
+    # ---- cav32 thermal
+    rm = R.RefMesh.from_cas(T + "cav32.cas")
+    t = R.RefThermal(rm)
+    t.set_bc(3, "SpecifiedTemperature", specifiedTemperature=400)
+    for g in (4, 5, 6):
+        t.set_bc(g, "SpecifiedTemperature", specifiedTemperature=0)
+    t.set_vc("thermalConductivity", 1.0)
+    t.set_solver(R.solver_cfg(relativeTolerance=1e-9, nMaxIterations=2000, maxCoarseLevels=20, verbosity=2))
+    t.init()
+    a = t.assemble(1)
+    text, _ = t.advance(1)
+    x9 = t.field("temperature").copy()
+    # tight solve for the solution-parity test
+    t2 = R.RefThermal(rm)
+    t2.set_bc(3, "SpecifiedTemperature", specifiedTemperature=400)
+    for g in (4, 5, 6):
+        t2.set_bc(g, "SpecifiedTemperature", specifiedTemperature=0)
+    t2.set_solver(R.solver_cfg(relativeTolerance=1e-13, nMaxIterations=2000, verbosity=0))
+    t2.init()
+    t2.advance(1)
+    G_ = T + "THERMAL_MATRIX/GOLDEN/"
+    np.savez_compressed(os.path.join(HERE, "cav32.npz"), **mesh_arrays(rm), diag=a["diag"], off=a["offdiag"],
+                        b=a["b"], x_after_bc=a["x"], ref_x_tol9=x9, ref_x=t2.field("temperature").copy(),
+                        ref_text=text,
+                        golden_rhs=np.loadtxt(G_ + "matrix.rhs"),
+                        golden_mat=np.loadtxt(G_ + "matrix_mesh0.mat", skiprows=2),
+                        golden_convergence=open(T + "AMG_MERGING_THERMAL/proc1/GOLDEN/convergence.dat").read())
+    # ---- hex with every BC kind
+    raw = G.hex_mesh(6, 5, 4, jitter=0.25, seed=11)
+    rm = R.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes,
+                            raw.face_node_count, raw.face_group_size)
+    rng = np.random.default_rng(5)
+    k = np.exp(rng.normal(size=rm.n_total))
+    src = rng.normal(size=rm.n_total) * 100
+    x0 = 300.0 + rng.uniform(-5, 5, size=rm.n_total)
+    t = R.RefThermal(rm)
+    t.set_bc(1, "SpecifiedTemperature", specifiedTemperature=400)
+    t.set_bc(2, "SpecifiedHeatFlux", specifiedHeatFlux=25.0)
+    t.set_bc(3, "Convective", convectiveCoefficient=3.0, farFieldTemperature=280.0)
+    t.set_bc(4, "Radiative", surfaceEmissivity=0.8, farFieldTemperature=250.0)
+    t.set_bc(5, "Mixed", convectiveCoefficient=2.0, surfaceEmissivity=0.5, farFieldTemperature=310.0)
+    t.set_bc(6, "SpecifiedHeatFlux", specifiedHeatFlux=0.0)
+    t.set_solver(R.solver_cfg(verbosity=0))
+    t.init()
+    t.field("conductivity")[:] = k
+    t.field("source")[:] = src
+    out = {}
+    for stage in (0, 1):
+        t.field("temperature")[:] = x0
+        a = t.assemble(stage)
+        for key in ("diag", "offdiag", "b", "x", "is_boundary"):
+            out["s%d_%s" % (stage, key)] = a[key]
+        out["s%d_gradient" % stage] = t.field("temperatureGradient").reshape(-1, 3).copy()
+    np.savez_compressed(os.path.join(HERE, "hex_bcs.npz"), **mesh_arrays(rm), k=k, src=src, x0=x0, **out)
+    # ---- tet solve
+    raw = G.tet_mesh(5, 5, 5)
+    rm = R.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes,
+                            raw.face_node_count, raw.face_group_size)
+    t = R.RefThermal(rm)
+    t.set_bc(5, "SpecifiedTemperature", specifiedTemperature=300)
+    t.set_bc(6, "SpecifiedTemperature", specifiedTemperature=400)
+    t.set_bc(1, "SpecifiedHeatFlux", specifiedHeatFlux=7.0)
+    t.set_solver(R.solver_cfg(relativeTolerance=1e-13, nMaxIterations=2000, verbosity=0))
+    t.init()
+    k = np.exp(0.5 * np.random.default_rng(9).normal(size=rm.n_total))
+    t.field("conductivity")[:] = k
+    a = t.assemble(1)
+    t.advance(1)
+    hf = {("hf%d" % g): t.heat_flux(int(g), int(c)) for g, c in zip(rm.connectivity()["group_id"][1:], rm.connectivity()["group_count"][1:])}
+    np.savez_compressed(os.path.join(HERE, "tet_solve.npz"), **mesh_arrays(rm), k=k, diag=a["diag"], off=a["offdiag"],
+                        b=a["b"], ref_x=t.field("temperature").copy(), **hf)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()
