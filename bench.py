@@ -228,6 +228,12 @@ def run_ours(args):
         ps = device_step(lib, model, mesh, ls, solver)
         recs = lib.profile_end(cap=8192)
         roof, prof_table = roofline(recs, ps)
+        try:  # full per-(kernel, rows) records for offline analysis (scratch, not part of the contract)
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "profile_records_n%d.json" % n), "w") as fh:
+                json.dump(dict(records=recs, levels=ps["levels"], cycles=ps["cycles"], total_ms=ps["total_ms"]), fh)
+        except OSError:
+            pass
     # ---- cpu baseline
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -69,6 +69,12 @@ int fvmgpu_init(int device) {
   CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   c.smCount = prop.multiProcessorCount;
   CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  {
+    cudaMemPool_t pool;
+    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ULL;  // never trim: freed blocks are reused by the next hierarchy
+    CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   for (int i = 0; i < 16; i++) {
     CUDA_CHECK(cudaEventCreate(&c.timerStart[i]));
     CUDA_CHECK(cudaEventCreate(&c.timerStop[i]));
@@ -86,16 +92,16 @@ int fvmgpu_shutdown(void) {
   API_BEGIN
   Context& c = ctx();
   if (!c.ready) return 0;
+  if (c.reduceScratch) devFree(c.reduceScratch);
+  if (c.l2scratch) devFree(c.l2scratch);
+  c.reduceScratch = nullptr;
+  c.l2scratch = nullptr;
 #ifndef FVMGPU_HOSTSIM
   cudaStreamSynchronize(c.stream);
   for (int i = 0; i < 16; i++) { cudaEventDestroy(c.timerStart[i]); cudaEventDestroy(c.timerStop[i]); }
   cudaStreamDestroy(c.stream);
   c.stream = nullptr;
 #endif
-  if (c.reduceScratch) devFree(c.reduceScratch);
-  if (c.l2scratch) devFree(c.l2scratch);
-  c.reduceScratch = nullptr;
-  c.l2scratch = nullptr;
   c.ready = false;
   API_END
 }

@@ -29,6 +29,7 @@ inline int atomicCAS(int* a, int cmp, int v) { int o = *a; if (o == cmp) *a = v;
 inline int atomicOr(int* a, int v) { int o = *a; *a |= v; return o; }
 inline int atomicAdd(int* a, int v) { int o = *a; *a += v; return o; }
 inline int atomicMax(int* a, int v) { int o = *a; if (v > o) *a = v; return o; }
+inline int atomicMin(int* a, int v) { int o = *a; if (v < o) *a = v; return o; }
 inline double atomicAdd(double* a, double v) { double o = *a; *a += v; return o; }
 typedef int cudaStream_t_sim;
 #else

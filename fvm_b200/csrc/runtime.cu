@@ -23,12 +23,19 @@ void requireReady() {
 }
 
 #ifndef FVMGPU_HOSTSIM
+// Stream-ordered allocation from the device's default memory pool (release threshold = never):
+// the hierarchy is rebuilt every outer iteration (F/ThermalModel_impl.h:428,446), and a
+// cudaMalloc/cudaFree pair per buffer per iteration would cost more than the setup kernels.
 void* devAlloc(size_t bytes) {
   void* p = nullptr;
-  CUDA_CHECK(cudaMalloc(&p, bytes));
+  if (ctx().stream) CUDA_CHECK(cudaMallocAsync(&p, bytes, ctx().stream));
+  else CUDA_CHECK(cudaMalloc(&p, bytes));
   return p;
 }
-void devFree(void* p) { cudaFree(p); }
+void devFree(void* p) {
+  if (ctx().stream) cudaFreeAsync(p, ctx().stream);
+  else cudaFree(p);
+}
 void devMemset(void* p, int byte, size_t bytes) { CUDA_CHECK(cudaMemsetAsync(p, byte, bytes, ctx().stream)); }
 void copyH2D(void* d, const void* h, size_t bytes) {
   CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx().stream));

@@ -66,6 +66,34 @@ struct ColourRoundKernel {
     colour[i] = c;
   }
 };
+// ---- 2-colouring of bipartite patterns by breadth-first parity (structured hex / quad meshes and
+// their regularly paired coarse levels are bipartite; Jones-Plassmann needs 6-7 colours there).
+struct BfsRoundKernel {  // unreached rows adjacent to the current front join the next front
+  int n; const int* row; const int* col; int* depth; int d; int* flags;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    if (depth[i] != -1) return;
+    for (int k = row[i]; k < row[i + 1]; k++) {
+      const int j = col[k];
+      if (j < n && j != i && depth[j] == d) { depth[i] = d + 1; flags[0] = 1; return; }
+    }
+  }
+};
+struct BfsCheckKernel {  // flags[1]: an edge inside one parity class (odd cycle); flags[2]: min unreached row
+  int n; const int* row; const int* col; const int* depth; int* flags;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    const int di = depth[i];
+    if (di == -1) { atomicMin(&flags[2], i); return; }
+    for (int k = row[i]; k < row[i + 1]; k++) {
+      const int j = col[k];
+      if (j < n && j != i && depth[j] != -1 && ((depth[j] ^ di) & 1) == 0) { flags[1] = 1; return; }
+    }
+  }
+};
+struct SetIntKernel { int* p; int idx; int v; FVM_DEV void operator()(long long) const { p[idx] = v; } };
+struct ParityKernel { const int* depth; int* colour; FVM_DEV void operator()(long long i) const { colour[i] = depth[i] & 1; } };
+
 struct ColourCountKernel {
   const int* colour; int* counts;
   FVM_DEV void operator()(long long i) const { atomicAdd(&counts[colour[i]], 1); }
@@ -426,7 +454,46 @@ struct RemapCiKernel {
 
 // ================================================================= level construction
 // Colour a CSR pattern; returns number of colours, fills colour[] (device)
+static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& colour) {
+  DBuf<int> depth(n), flags(4);
+  depth.fillBytes(0xff);
+  int d = 0, seed = 0;
+  const int big = 0x7fffffff;
+  parallelFor(1, SetIntKernel{depth.p, seed, 0});
+  int rounds = 0;
+  for (;;) {
+    int h[4] = {0, 0, big, 0};
+    copyH2D(flags.p, h, sizeof(h));
+    const int burst = rounds < 2 ? 2 : 16;  // look for an odd cycle early: non-bipartite graphs bail out fast
+    for (int k = 0; k < burst; k++) {
+      parallelFor(n, BfsRoundKernel{n, row, col, depth.p, d, flags.p});
+      d++;
+      rounds++;
+    }
+    parallelFor(n, BfsCheckKernel{n, row, col, depth.p, flags.p});
+    flags.download(h, 4);
+    if (h[1]) return false;              // odd cycle: not bipartite
+    if (h[0]) continue;                  // the front is still moving
+    if (h[2] == big) break;              // everything reached
+    d = (d + 2) & ~1;                    // next component: restart from an even depth
+    parallelFor(1, SetIntKernel{depth.p, h[2], d});
+    if (rounds > 4 * n + 64) return false;
+  }
+  colour.alloc(n);
+  parallelFor(n, ParityKernel{depth.p, colour.p});
+  return true;
+}
+
 static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, std::vector<int>& counts) {
+  if (tryTwoColouring(n, row, col, colour)) {
+    DBuf<int> cnt2(64);
+    cnt2.zero();
+    parallelFor(n, ColourCountKernel{colour.p, cnt2.p});
+    std::vector<int> h2 = cnt2.toHost();
+    int nc2 = h2[1] > 0 ? 2 : 1;
+    counts.assign(h2.begin(), h2.begin() + nc2);
+    return nc2;
+  }
   colour.alloc(n);
   colour.fillBytes(0xff);
   DBuf<int> flags(2);
@@ -566,6 +633,8 @@ static void buildMembers(Level& F, int nc) {
 }
 
 void Amg::cleanup() {
+  dropGraphs();
+  tailStart = -1;
   levels.clear();
   builtFor = nullptr;
   builtVersion = 0;
@@ -573,6 +642,8 @@ void Amg::cleanup() {
 
 void Amg::setup(System* sys) {
   requireReady();
+  dropGraphs();
+  tailStart = -1;
   levels.clear();
   const int n = sys->nSelf;
   // level 0 from the system's CSR; single GPU: ghost columns carry delta = 0 and are dropped
@@ -626,25 +697,164 @@ void Amg::setup(System* sys) {
     levels.push_back(std::move(C));
     if (cn <= 3) break;
   }
+  buildTail();
   streamSync();
   builtFor = sys;
   builtVersion = sys->version;
 }
 
+// ================================================================= coarse tail in one CTA
+// All levels below kTailRows rows are latency-bound: a kernel launch per colour costs more than the
+// arithmetic. One 1024-thread CTA therefore runs the whole V-cycle tail (restrict down, smooth,
+// prolong up), with __syncthreads() where the launch boundaries would be. Same operations in the
+// same order as the per-level launches, so the results are bit-identical to them.
+#ifndef FVMGPU_HOSTSIM
+struct TailLevel {
+  int n, nColours;
+  const int* colourStart;  // device, nColours+1
+  const int* sliceOff; const int* scol; const double* sval; const double* diag;
+  double* b; double* x; double* r;
+  const int* ci; const int* memOff; const int* mem;  // links to the next level (null on the last)
+};
+constexpr int kTailThreads = 1024;
+
+__device__ __forceinline__ double tailRowSum(const TailLevel& L, int r, const double* x) {
+  const int s = r >> 5;
+  const int end = L.sliceOff[s + 1];
+  double sum = 0.0;
+  for (int p = L.sliceOff[s] + (r & 31); p < end; p += 32) sum += L.sval[p] * x[L.scol[p]];
+  return sum;
+}
+__device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& xZero) {
+  int lastColour = -1;
+  for (int sw = 0; sw < nSweeps; sw++) {
+    if (smoother == FVMGPU_SMOOTHER_GAUSS_SEIDEL) {
+      for (int pass = 0; pass < 2 * L.nColours; pass++) {
+        const int c = pass < L.nColours ? pass : 2 * L.nColours - 1 - pass;
+        if (c == lastColour) continue;
+        const int r1 = L.colourStart[c + 1];
+        for (int r = L.colourStart[c] + threadIdx.x; r < r1; r += kTailThreads) {
+          double sum = L.b[r];
+          if (!xZero) sum += tailRowSum(L, r, L.x);
+          L.x[r] = -sum / L.diag[r];
+        }
+        xZero = false;
+        lastColour = c;
+        __syncthreads();
+      }
+    } else {
+      for (int half = 0; half < 2; half++) {
+        const double* xo = half ? L.r : L.x;
+        double* xn = half ? L.x : L.r;
+        for (int r = threadIdx.x; r < L.n; r += kTailThreads) xn[r] = -(L.b[r] + tailRowSum(L, r, xo)) / L.diag[r];
+        __syncthreads();
+      }
+      xZero = false;
+    }
+  }
+}
+__global__ void __launch_bounds__(kTailThreads) k_tail_vcycle(const TailLevel* lv, int nLevels, int nPre, int nPost,
+                                                                int smoother) {
+  // on entry: level 0 of the tail has b set and x == 0
+  for (int l = 0; l < nLevels; l++) {
+    const TailLevel L = lv[l];
+    bool xZero = true;
+    tailSweeps(L, nPre, smoother, xZero);
+    if (l + 1 < nLevels) {
+      const TailLevel C = lv[l + 1];
+      const double* src = L.b;
+      if (!xZero) {  // r = b + A x
+        for (int r = threadIdx.x; r < L.n; r += kTailThreads) {
+          double v = L.b[r] + L.diag[r] * L.x[r];
+          v += tailRowSum(L, r, L.x);
+          L.r[r] = v;
+        }
+        __syncthreads();
+        src = L.r;
+      }
+      for (int I = threadIdx.x; I < C.n; I += kTailThreads) {
+        double s = 0.0;
+        for (int p = L.memOff[I]; p < L.memOff[I + 1]; p++) s += src[L.mem[p]];
+        C.b[I] = s;
+        C.x[I] = 0.0;
+      }
+      __syncthreads();
+    } else {
+      tailSweeps(L, nPost, smoother, xZero);  // coarsest level: pre + post sweeps
+    }
+  }
+  for (int l = nLevels - 2; l >= 0; l--) {
+    const TailLevel L = lv[l];
+    const TailLevel C = lv[l + 1];
+    for (int i = threadIdx.x; i < L.n; i += kTailThreads) {
+      const int c = L.ci[i];
+      if (c >= 0) L.x[i] += C.x[c];
+    }
+    __syncthreads();
+    bool xZero = false;
+    tailSweeps(L, nPost, smoother, xZero);
+  }
+}
+#endif
+
+void Amg::buildTail() {
+  tailStart = -1;
+#ifndef FVMGPU_HOSTSIM
+  const int nl = (int)levels.size();
+  int start = nl;
+  while (start > 1 && levels[start - 1]->n <= kTailRows) start--;
+  if (nl - start < 2) return;  // nothing worth fusing
+  std::vector<TailLevel> h;
+  tailColourStarts.clear();
+  for (int l = start; l < nl; l++) {
+    Level& L = *levels[l];
+    tailColourStarts.emplace_back();
+    tailColourStarts.back().upload(L.colourStart.data(), L.colourStart.size());
+  }
+  for (int l = start; l < nl; l++) {
+    Level& L = *levels[l];
+    TailLevel t;
+    t.n = L.n; t.nColours = L.nColours; t.colourStart = tailColourStarts[l - start].p;
+    t.sliceOff = L.sliceOff.p; t.scol = L.scol.p; t.sval = L.sval.p; t.diag = L.diag.p;
+    t.b = L.b.p; t.x = L.x.p; t.r = L.r.p;
+    t.ci = L.ci.p; t.memOff = L.memOff.p; t.mem = L.mem.p;
+    h.push_back(t);
+  }
+  tailLevels.alloc(h.size() * sizeof(TailLevel));
+  copyH2D(tailLevels.p, h.data(), h.size() * sizeof(TailLevel));
+  tailStart = start;
+  tailCount = nl - start;
+#endif
+}
+
+void Amg::runTail() {
+#ifndef FVMGPU_HOSTSIM
+  ProfileScope prof("N6fvmgpu13k_tail_vcycleE", levels[tailStart]->n);
+  k_tail_vcycle<<<1, kTailThreads, 0, ctx().stream>>>(reinterpret_cast<const TailLevel*>(tailLevels.p), tailCount,
+                                                      opts.nPreSweeps, opts.nPostSweeps, opts.smootherType);
+  ctx().launches++;
+  CUDA_CHECK(cudaGetLastError());
+  for (int l = tailStart; l < (int)levels.size(); l++) { levels[l]->xZero = false; levels[l]->rValid = false; }
+#endif
+}
+
 // ================================================================= cycle
 void Amg::sweeps(int nSweeps, int lvl) {
   Level& L = *levels[lvl];
+  // A colour pass only reads the OTHER colours, so repeating the pass that was just done changes
+  // nothing (bit for bit): the reverse half-sweep therefore starts at the last-but-one colour, and
+  // a following forward half-sweep skips colour 0.
+  int lastColour = -1;
   for (int s = 0; s < nSweeps; s++) {
     if (opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL) {
-      for (int c = 0; c < L.nColours; c++) {
+      for (int pass = 0; pass < 2 * L.nColours; pass++) {
+        const int c = pass < L.nColours ? pass : 2 * L.nColours - 1 - pass;
+        if (c == lastColour) continue;
         const int r0 = L.colourStart[c], cnt = L.colourStart[c + 1] - r0;
-        if (c == 0 && L.xZero) parallelFor(cnt, GsFirstColourZeroRows{r0, L.diag.p, L.b.p, L.x.p});
+        if (L.xZero) parallelFor(cnt, GsFirstColourZeroRows{r0, L.diag.p, L.b.p, L.x.p});
         else parallelFor(cnt, GsRows{r0, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p});
         L.xZero = false;
-      }
-      for (int c = L.nColours - 1; c >= 0; c--) {
-        const int r0 = L.colourStart[c], cnt = L.colourStart[c + 1] - r0;
-        parallelFor(cnt, GsRows{r0, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p});
+        lastColour = c;
       }
     } else {
       // two Jacobi passes per sweep (F/AMG.cpp:59-63), ping-pong through r
@@ -673,6 +883,7 @@ double Amg::residualNorm(int lvl) {
 
 void Amg::cycle(int cycleType, int lvl) {
   Level& L = *levels[lvl];
+  if (lvl == tailStart && cycleType == FVMGPU_CYCLE_V && L.xZero) { runTail(); return; }
   sweeps(opts.nPreSweeps, lvl);
   if (lvl + 1 < (int)levels.size()) {
     Level& C = *levels[lvl + 1];
@@ -714,6 +925,60 @@ void Amg::ensureSetup(System* sys) {
   if (!scalars.p) scalars.alloc(16);
 }
 
+// ---- CUDA graph of (one cycle + residual + 1-norm): the launch sequence of a cycle is the same
+// every time (the flags that steer it are identical at the start of every cycle), so it is captured
+// once per hierarchy and replayed; per-cycle host work drops to one graph launch + one 8-byte copy.
+void Amg::dropGraphs() {
+#ifndef FVMGPU_HOSTSIM
+  for (int k = 0; k < 2; k++) {
+    if (graphExec[k]) { cudaGraphExecDestroy((cudaGraphExec_t)graphExec[k]); graphExec[k] = nullptr; }
+  }
+#endif
+}
+
+// kind 0: solve loop body  (cycle on the current x, then r = b + A x and |r|_1 -> scalars[0])
+// kind 1: preconditioner   (x = 0, cycle; b already loaded)
+void Amg::cycleGraphed(int kind) {
+  Level& L0 = *levels[0];
+  auto body = [&]() {
+    if (kind == 1) { L0.x.zero(); L0.xZero = true; L0.rValid = false; }
+    cycle(opts.cycleType, 0);
+    if (kind == 0) {
+      reduceRows<1>(L0.n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, L0.b.p, L0.x.p, L0.r.p},
+                    scalars.p);
+      L0.rValid = true;
+    }
+  };
+#ifndef FVMGPU_HOSTSIM
+  if (!ctx().profiling && useGraphs) {
+    if (!graphExec[kind]) {
+      // flags at the start of the body must be what they are at the start of EVERY replay
+      const bool xz = L0.xZero, rv = L0.rValid;
+      cudaGraph_t g = nullptr;
+      const long long launchesBefore = ctx().launches;
+      CUDA_CHECK(cudaStreamBeginCapture(ctx().stream, cudaStreamCaptureModeThreadLocal));
+      body();
+      CUDA_CHECK(cudaStreamEndCapture(ctx().stream, &g));
+      graphLaunches[kind] = ctx().launches - launchesBefore;
+      ctx().launches = launchesBefore;
+      cudaGraphExec_t ge = nullptr;
+      CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      graphExec[kind] = ge;
+      L0.xZero = xz; L0.rValid = rv;
+    }
+    CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)graphExec[kind], ctx().stream));
+    ctx().launches += graphLaunches[kind];
+    // replay leaves the same flags as the captured run did
+    L0.xZero = false;
+    L0.rValid = (kind == 0);
+    for (size_t l = 1; l < levels.size(); l++) { levels[l]->xZero = false; levels[l]->rValid = false; }
+    return;
+  }
+#endif
+  body();
+}
+
 // AMG::solve, F/AMG.cpp:219-282
 void Amg::solve(System* sys, double* rnorm0Out, double* rnormOut, int* itersOut) {
   requireReady();
@@ -727,9 +992,9 @@ void Amg::solve(System* sys, double* rnorm0Out, double* rnormOut, int* itersOut)
   int iters = 0;
   if (!(rNorm0 < opts.absoluteTolerance)) {
     for (int i = 1; i < opts.nMaxIterations; i++) {
-      cycle(opts.cycleType, 0);
+      cycleGraphed(0);
       iters++;
-      rNorm = residualNorm(0);
+      copyD2H(&rNorm, scalars.p, sizeof(double));
       history.push_back(rNorm);
       if (rNorm < opts.absoluteTolerance || rNorm / rNorm0 < opts.relativeTolerance) break;
     }
@@ -755,10 +1020,9 @@ void Amg::smooth(System* sys) {
 void Amg::precondition(const double* rhsPerm, double* outPerm) {
   Level& L0 = *levels[0];
   copyD2D(L0.b.p, rhsPerm, (size_t)L0.n * sizeof(double));
-  L0.x.zero();
   L0.xZero = true;
   L0.rValid = false;
-  cycle(opts.cycleType, 0);
+  cycleGraphed(1);
   copyD2D(outPerm, L0.x.p, (size_t)L0.n * sizeof(double));
 }
 

@@ -33,6 +33,15 @@ struct Amg {
   unsigned long long builtVersion = 0;
   std::vector<double> history;
   long long totalIterations = 0;
+  // coarse tail fused into one CTA (levels [tailStart, end) have <= kTailRows rows)
+  static constexpr int kTailRows = 4096;
+  int tailStart = -1, tailCount = 0;
+  DBuf<char> tailLevels;
+  std::vector<DBuf<int>> tailColourStarts;
+  // captured (cycle [+ residual norm]) graphs
+  bool useGraphs = true;
+  void* graphExec[2] = {nullptr, nullptr};
+  long long graphLaunches[2] = {0, 0};
 
   void setup(System* sys);   // AMG::createCoarseLevels
   void ensureSetup(System* sys);
@@ -49,6 +58,11 @@ struct Amg {
   void loadSystem(System* sys, const double* b_d, const double* x_d);
   void storeDelta(double* delta_d);
   void precondition(const double* rhsPerm, double* outPerm);
+  void buildTail();
+  void runTail();
+  void dropGraphs();
+  void cycleGraphed(int kind);
+  ~Amg() { dropGraphs(); }
 };
 
 // mesh.cu / assemble.cu entry points used by capi.cu

@@ -1,0 +1,266 @@
+// fvm_gpu_adaptor.h -- the reference-side binding of libfvmgpu.so.
+//
+// This header is what a maintainer of btanasoi/fvm adds next to src/fvm/src/modules/fvmbase/: it
+// is compiled AGAINST THE REFERENCE'S OWN HEADERS and plugs the CUDA path in behind the two
+// interfaces the hot path sits behind, without touching the SWIG/Python surface:
+//
+//   class GpuAMG     : public LinearSolver   (F/LinearSolver.h:11-31)  -- drop-in for AMG
+//   class GpuBCGStab : public LinearSolver                              -- drop-in for BCGStab
+//   class GpuThermalLinearizer                                          -- replaces the body of
+//        ThermalModel<T>::Impl::linearize (F/ThermalModel_impl.h:236-398: GradientModel::compute,
+//        Linearizer::linearize over the discretization list and the GenericBCS loop) plus
+//        LinearSystem::initSolve's boundary elimination, writing into the reference's own
+//        CRMatrix<T,T,T> / MultiField arrays.
+//
+// Scripts select it exactly like any other solver:  tmodel.getOptions().linearSolver = GpuAMG()
+// Errors from the C ABI are rethrown as CException (F/CException.h:16-21).
+#ifndef FVM_GPU_ADAPTOR_H_
+#define FVM_GPU_ADAPTOR_H_
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "AMG.h"
+#include "CException.h"
+#include "CRMatrix.h"
+#include "GeomFields.h"
+#include "LinearSolver.h"
+#include "LinearSystem.h"
+#include "Mesh.h"
+#include "MultiFieldReduction.h"
+#include "fvmgpu.h"
+
+namespace fvmgpu_adaptor {
+
+inline void check(int rc) {
+  if (rc != 0) throw CException(std::string("libfvmgpu: ") + fvmgpu_last_error());
+}
+
+inline void ensureInit(int device = 0) { check(fvmgpu_init(device)); }
+
+typedef CRMatrix<double, double, double> ScalarMatrix;
+typedef Array<double> DArray;
+
+// The single scalar cell system of a LinearSystem: (ArrayIndex, matrix)
+struct ScalarSystemView {
+  MultiField::ArrayIndex index;
+  ScalarMatrix* matrix;
+  ScalarSystemView() : index(0, 0), matrix(0) {}
+};
+
+inline ScalarSystemView findScalarSystem(LinearSystem& ls) {
+  ScalarSystemView v;
+  const MultiField::ArrayIndexList& idx = ls.getB().getArrayIndices();
+  for (size_t i = 0; i < idx.size(); i++) {
+    if (!ls.getMatrix().hasMatrix(idx[i], idx[i])) continue;
+    ScalarMatrix* m = dynamic_cast<ScalarMatrix*>(&ls.getMatrix().getMatrix(idx[i], idx[i]));
+    if (m) {
+      if (v.matrix) throw CException("GpuAMG: more than one CRMatrix<double,double,double> block");
+      v.matrix = m;
+      v.index = idx[i];
+    }
+  }
+  if (!v.matrix) throw CException("GpuAMG: no CRMatrix<double,double,double> block in this LinearSystem");
+  return v;
+}
+
+// ------------------------------------------------------------------------------------ solvers
+class GpuAMG : public LinearSolver {
+ public:
+  GpuAMG()
+      : maxCoarseLevels(30), nPreSweeps(0), nPostSweeps(1), coarseGroupSize(2), weightRatioThreshold(0.65),
+        cycleType(AMG::V_CYCLE), smootherType(AMG::GAUSS_SEIDEL), scaleCorrections(true), _solver(0), _system(0),
+        _for(0), _totalIterations(0) {}
+  virtual ~GpuAMG() { cleanup(); if (_solver) fvmgpu_amg_destroy(_solver); }
+
+  // same public tunables as AMG (F/AMG.h:74-81)
+  int maxCoarseLevels, nPreSweeps, nPostSweeps, coarseGroupSize;
+  double weightRatioThreshold;
+  AMG::CycleType cycleType;
+  AMG::SmootherType smootherType;
+  bool scaleCorrections;
+
+  virtual MFRPtr solve(LinearSystem& ls) {
+    ScalarSystemView v = upload(ls);
+    double r0 = 0, r = 0;
+    int it = 0;
+    check(fvmgpu_amg_solve(_solver, _system, &r0, &r, &it));
+    _totalIterations += it;
+    download(ls, v);
+    if (verbosity > 0) {
+      std::cout << "0: [" << v.index.first->getName() << " : " << r0 << "]" << std::endl;
+      std::cout << it << ": [" << v.index.first->getName() << " : " << r << "]" << std::endl;
+    }
+    return norm(v, r0);
+  }
+  virtual void smooth(LinearSystem& ls) {  // one cycle on (b, delta), used by BCGStab (F/BCGStab.cpp:85-89)
+    ScalarSystemView v = upload(ls);
+    check(fvmgpu_amg_smooth(_solver, _system));
+    download(ls, v);
+  }
+  virtual void cleanup() {
+    if (_solver) fvmgpu_amg_cleanup(_solver);
+    if (_system) { fvmgpu_system_destroy(_system); _system = 0; }
+    _for = 0;
+  }
+  int getTotalIterations() const { return _totalIterations; }
+  fvmgpu_solver_t handle() { return _solver; }
+  fvmgpu_system_t system() { return _system; }
+
+  ScalarSystemView upload(LinearSystem& ls) {
+    ensureInit();
+    fvmgpu_amg_opts o;
+    o.nMaxIterations = nMaxIterations; o.verbosity = verbosity;
+    o.relativeTolerance = relativeTolerance; o.absoluteTolerance = absoluteTolerance;
+    o.maxCoarseLevels = maxCoarseLevels; o.nPreSweeps = nPreSweeps; o.nPostSweeps = nPostSweeps;
+    o.coarseGroupSize = coarseGroupSize; o.weightRatioThreshold = weightRatioThreshold;
+    o.cycleType = (int)cycleType; o.smootherType = (int)smootherType;
+    if (!_solver) check(fvmgpu_amg_create(&_solver, &o));
+    else check(fvmgpu_amg_set_opts(_solver, &o));
+    ScalarSystemView v = findScalarSystem(ls);
+    const CRConnectivity& conn = v.matrix->getConnectivity();
+    const StorageSite& site = conn.getRowSite();
+    const DArray& b = dynamic_cast<const DArray&>(ls.getB()[v.index]);
+    const DArray& delta = dynamic_cast<const DArray&>(ls.getDelta()[v.index]);
+    if (_for != &ls) {  // AMG keys its hierarchy on the LinearSystem (F/AMG.cpp:222-226)
+      if (_system) fvmgpu_system_destroy(_system);
+      _system = 0;
+      check(fvmgpu_system_create_raw(&_system, site.getSelfCount(), site.getCount() - site.getSelfCount(),
+                                     (const int*)conn.getRow().getData(), (const int*)conn.getCol().getData(),
+                                     (const double*)v.matrix->getDiag().getData(),
+                                     (const double*)v.matrix->getOffDiag().getData(), (const double*)b.getData()));
+      _for = &ls;
+    } else {
+      check(fvmgpu_system_set_field(_system, FVMGPU_FIELD_B, (const double*)b.getData(), b.getLength()));
+    }
+    check(fvmgpu_system_set_field(_system, FVMGPU_FIELD_DELTA, (const double*)delta.getData(), delta.getLength()));
+    return v;
+  }
+  void download(LinearSystem& ls, const ScalarSystemView& v) {
+    DArray& delta = dynamic_cast<DArray&>(ls.getDelta()[v.index]);
+    check(fvmgpu_system_get_field(_system, FVMGPU_FIELD_DELTA, (double*)delta.getData(), delta.getLength()));
+  }
+  static MFRPtr norm(const ScalarSystemView& v, double r0) {
+    MFRPtr r(new MultiFieldReduction());
+    shared_ptr<DArray> a(new DArray(1));
+    (*a)[0] = r0;
+    r->addArray(*v.index.first, a);
+    return r;
+  }
+
+ private:
+  fvmgpu_solver_t _solver;
+  fvmgpu_system_t _system;
+  LinearSystem* _for;
+  int _totalIterations;
+};
+
+class GpuBCGStab : public LinearSolver {
+ public:
+  GpuBCGStab() : preconditioner(0), _totalIterations(0) {}
+  GpuAMG* preconditioner;
+  virtual MFRPtr solve(LinearSystem& ls) {
+    if (!preconditioner) throw CException("GpuBCGStab: no preconditioner");
+    ScalarSystemView v = preconditioner->upload(ls);
+    double r0 = 0, r = 0;
+    int it = 0;
+    check(fvmgpu_bcgstab_solve(preconditioner->handle(), preconditioner->system(), nMaxIterations,
+                               relativeTolerance, absoluteTolerance, &r0, &r, &it));
+    _totalIterations += it;
+    preconditioner->download(ls, v);
+    if (verbosity > 0) {
+      std::cout << "0: [" << v.index.first->getName() << " : " << r0 << "]" << std::endl;
+      std::cout << it << ": [" << v.index.first->getName() << " : " << r << "]" << std::endl;
+    }
+    return GpuAMG::norm(v, r0);
+  }
+  virtual void smooth(LinearSystem&) { throw CException("cannot use BCGStab as preconditioner"); }
+  virtual void cleanup() { if (preconditioner) preconditioner->cleanup(); }
+  int getTotalIterations() const { return _totalIterations; }
+
+ private:
+  int _totalIterations;
+};
+
+// ------------------------------------------------------------------------------------ assembly
+// Device mirror of one reference Mesh + GeomFields, created once (geometry outlives the models).
+class GpuMesh {
+ public:
+  GpuMesh(const Mesh& mesh, const GeomFields& geom) : _h(0), _mesh(mesh) {
+    ensureInit();
+    const StorageSite& cells = mesh.getCells();
+    const StorageSite& faces = mesh.getFaces();
+    const CRConnectivity& fc = mesh.getAllFaceCells();
+    const CRConnectivity& cc = mesh.getCellCells();
+    std::vector<int> gOff, gCnt, gId, gKind;
+    foreach (const FaceGroupPtr fg, mesh.getAllFaceGroups()) {
+      gOff.push_back(fg->site.getOffset());
+      gCnt.push_back(fg->site.getCount());
+      gId.push_back(fg->id);
+      gKind.push_back(fg->groupType == "interior" ? FVMGPU_GROUP_INTERIOR
+                      : fg->groupType == "interface" ? FVMGPU_GROUP_INTERFACE
+                      : fg->groupType == "symmetry" ? FVMGPU_GROUP_SYMMETRY : FVMGPU_GROUP_BOUNDARY);
+    }
+    check(fvmgpu_mesh_create(&_h, mesh.getDimension(), cells.getSelfCount(), cells.getCount(), faces.getCount(),
+                             (const int*)fc.getCol().getData(), (const int*)cc.getRow().getData(),
+                             (const int*)cc.getCol().getData(), (int)gOff.size(), &gOff[0], &gCnt[0], &gId[0],
+                             &gKind[0]));
+    check(fvmgpu_mesh_set_geometry(_h, (const double*)geom.area[faces].getData(),
+                                   (const double*)geom.areaMag[faces].getData(),
+                                   (const double*)geom.coordinate[faces].getData(),
+                                   (const double*)geom.coordinate[cells].getData(),
+                                   (const double*)geom.volume[cells].getData(),
+                                   (const int*)geom.ibType[cells].getData()));
+  }
+  ~GpuMesh() { if (_h) fvmgpu_mesh_destroy(_h); }
+  fvmgpu_mesh_t handle() const { return _h; }
+  const Mesh& mesh() const { return _mesh; }
+
+ private:
+  GpuMesh(const GpuMesh&);
+  fvmgpu_mesh_t _h;
+  const Mesh& _mesh;
+};
+
+struct GpuBC {  // one GenericBCS call per boundary group
+  int groupId, kind;
+  double p[4];
+};
+
+// Scalar transport linearization on the GPU (thermal / electrostatic potential / any
+// CRMatrix<T,T,T> transport equation): gradient + diffusion + [convection] + source +
+// [time derivative] + BCs + boundary elimination, results copied into the reference's arrays.
+class GpuScalarLinearizer {
+ public:
+  explicit GpuScalarLinearizer(const GpuMesh& gm) : _gm(gm), _sys(0) { check(fvmgpu_system_create(&_sys, gm.handle())); }
+  ~GpuScalarLinearizer() { if (_sys) fvmgpu_system_destroy(_sys); }
+
+  void linearize(LinearSystem& ls, Field& varField, const Field& diffusivity, const Field& source,
+                 const std::vector<GpuBC>& bcs, const fvmgpu_assemble_opts& opts, Field* gradientField = 0) {
+    const StorageSite& cells = _gm.mesh().getCells();
+    MultiField::ArrayIndex xi(&varField, &cells);
+    ScalarMatrix& m = dynamic_cast<ScalarMatrix&>(ls.getMatrix().getMatrix(xi, xi));
+    DArray& x = dynamic_cast<DArray&>(ls.getX()[xi]);
+    DArray& b = dynamic_cast<DArray&>(ls.getB()[xi]);
+    const long long nt = cells.getCount();
+    check(fvmgpu_system_set_field(_sys, FVMGPU_FIELD_X, (const double*)x.getData(), nt));
+    check(fvmgpu_system_set_field(_sys, FVMGPU_FIELD_DIFFUSIVITY, (const double*)diffusivity[cells].getData(), nt));
+    check(fvmgpu_system_set_field(_sys, FVMGPU_FIELD_SOURCE, (const double*)source[cells].getData(), nt));
+    for (size_t i = 0; i < bcs.size(); i++) check(fvmgpu_system_set_bc(_sys, bcs[i].groupId, bcs[i].kind, bcs[i].p, 4, 0));
+    check(fvmgpu_assemble(_sys, &opts));
+    check(fvmgpu_download_system(_sys, (double*)m.getDiag().getData(), (double*)m.getOffDiag().getData(),
+                                 (double*)b.getData(), 0));
+    check(fvmgpu_system_get_field(_sys, FVMGPU_FIELD_X, (double*)x.getData(), nt));
+    if (gradientField)
+      check(fvmgpu_system_get_field(_sys, FVMGPU_FIELD_GRADIENT, (double*)(*gradientField)[cells].getData(), 3 * nt));
+  }
+  fvmgpu_system_t handle() { return _sys; }
+
+ private:
+  const GpuMesh& _gm;
+  fvmgpu_system_t _sys;
+};
+
+}  // namespace fvmgpu_adaptor
+#endif
