@@ -285,7 +285,6 @@ def roofline(recs, step):
         peak, src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json (sustained: inside a long step)"
     sizes, nnzs = step["levels"]["sizes"], step["levels"]["nnz"]
     n0, nnz0 = sizes[0], nnzs[0]
-    ncol0 = step["levels"]["colours"][0]
     by = {}
     for r in recs:
         d = by.setdefault(r["name"], dict(launches=0, ms=0.0))
@@ -294,28 +293,21 @@ def roofline(recs, step):
     total = sum(d["ms"] for d in by.values())
     table = sorted(({"kernel": k, "launches": v["launches"], "ms": round(v["ms"], 3),
                      "share": round(v["ms"] / total, 4)} for k, v in by.items()), key=lambda t: -t["ms"])[:12]
-    # level-0 GS launches: rows > n1 (a level-0 colour is larger than the whole level 1 only when
-    # colours are few; use the exact colour sizes instead: all GsRows records with rows <= n0 whose
-    # launches == 2*cycles (fwd+rev per cycle) and rows sum to n0)
-    cyc = max(step["cycles"], 1)
-    gs = [r for r in recs if r["name"] in ("GsRows", "GsFirstColourZeroRows")]
-    gs0 = sorted(gs, key=lambda r: -r["rows"])
-    picked, rows_acc = [], 0
-    for r in gs0:
-        if rows_acc >= n0:
-            break
-        if r["name"] == "GsRows":
-            picked.append(r); rows_acc += r["rows"]
+    # level-0 Gauss-Seidel launches (the profiler tags every solver launch with its AMG level). One
+    # launch = one colour = `rows` rows; algorithmic bytes of a launch (one SpMV-class row
+    # pass): 36 B per row + 12 B per off-diagonal entry, the level's nnz apportioned by rows.
+    picked = [r for r in recs if r["name"] == "GsRows" and r.get("level", -1) == 0]
     launches = sum(r["launches"] for r in picked)
     ms = sum(r["ms"] for r in picked)
     if not launches:
         return None, table
-    bytes_per_sweep_pass = 36.0 * n0 + 12.0 * nnz0            # one pass over all level-0 rows
-    passes = launches / float(len(picked))                      # each colour launched once per pass
-    achieved = bytes_per_sweep_pass * passes / (ms * 1e-3) / 1e9
+    per_row = 36.0 + 12.0 * nnz0 / n0
+    total_bytes = sum(r["launches"] * r["rows"] * per_row for r in picked)
+    achieved = total_bytes / (ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "k_rows<GsRows> (level-0 multicolour Gauss-Seidel pass)",
-            "peak_source": src, "bytes_per_launch": bytes_per_sweep_pass / len(picked),
+            "traffic": None, "kernel": "k_rows<GsRows> at AMG level 0 (one colour of the multicolour Gauss-Seidel sweep)",
+            "peak_source": src, "bytes_per_launch": total_bytes / launches,
+            "bytes_per_row": per_row, "rows_per_launch": sum(r["launches"] * r["rows"] for r in picked) / launches,
             "mean_launch_ms": ms / launches, "launches": launches,
             "share_of_step": ms / step["total_ms"]}
     return roof, table

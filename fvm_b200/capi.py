@@ -195,7 +195,12 @@ class Lib:
         raw = names.raw
         for i in range(min(n.value, cap)):
             nm = raw[i * stride:(i + 1) * stride].split(b"\0")[0].decode()
-            out.append(dict(name=_demangle(nm), rows=int(rows[i]), launches=int(launches[i]), ms=float(ms[i])))
+            level = -1
+            if "@L" in nm:
+                nm, lv = nm.rsplit("@L", 1)
+                level = int(lv)
+            out.append(dict(name=_demangle(nm), rows=int(rows[i]), launches=int(launches[i]), ms=float(ms[i]),
+                            level=level))
         return out
 
     def default_amg_opts(self):

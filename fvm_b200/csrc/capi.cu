@@ -182,7 +182,9 @@ int fvmgpu_profile_end(int cap, char* names, int nameStride, long long* rows, lo
   std::vector<ProfileRecord> recs = profileEnd();
   if (count) *count = (int)recs.size();
   for (int i = 0; i < (int)recs.size() && i < cap; i++) {
-    std::strncpy(names + (size_t)i * nameStride, recs[i].name.c_str(), nameStride - 1);
+    std::string nm = recs[i].name;
+    if (recs[i].tag >= 0) nm += "@L" + std::to_string(recs[i].tag);
+    std::strncpy(names + (size_t)i * nameStride, nm.c_str(), nameStride - 1);
     names[(size_t)i * nameStride + nameStride - 1] = 0;
     rows[i] = recs[i].n;
     launches[i] = recs[i].launches;

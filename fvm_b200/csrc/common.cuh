@@ -67,6 +67,7 @@ struct Error : std::runtime_error {
 struct Context {
   bool ready = false;
   bool profiling = false;
+  int profileTag = -1;  // AMG level of the launches being issued (-1: not inside the solver); suffix '@L<k>' of profile names
   int device = -1;
   int smCount = 148;
 #ifndef FVMGPU_HOSTSIM
@@ -154,7 +155,7 @@ struct ProfileScope {
   ~ProfileScope();
 };
 void profileBegin();
-struct ProfileRecord { std::string name; long long n; long long launches; double ms; };
+struct ProfileRecord { std::string name; long long n; long long launches; double ms; int tag; };
 std::vector<ProfileRecord> profileEnd();
 
 // ---------------------------------------------------------------- row-parallel launcher

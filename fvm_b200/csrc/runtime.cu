@@ -88,7 +88,7 @@ void sortPairs(int* keys_d, int* vals_d, long long n, int bits) {
 
 // ---- profiler
 namespace {
-struct ProfEntry { const char* name; long long n; cudaEvent_t a, b; };
+struct ProfEntry { const char* name; long long n; cudaEvent_t a, b; int tag; };
 std::vector<ProfEntry>& profEntries() { static std::vector<ProfEntry> v; return v; }
 std::vector<cudaEvent_t>& profPool() { static std::vector<cudaEvent_t> v; return v; }
 cudaEvent_t profEvent() {
@@ -101,7 +101,7 @@ cudaEvent_t profEvent() {
 }  // namespace
 ProfileScope::ProfileScope(const char* name, long long n) : on(ctx().profiling) {
   if (!on) return;
-  ProfEntry e{name, n, profEvent(), profEvent()};
+  ProfEntry e{name, n, profEvent(), profEvent(), ctx().profileTag};
   cudaEventRecord(e.a, ctx().stream);
   profEntries().push_back(e);
 }
@@ -122,8 +122,8 @@ std::vector<ProfileRecord> profileEnd() {
     cudaEventElapsedTime(&ms, e.a, e.b);
     bool found = false;
     for (ProfileRecord& r : out)
-      if (r.n == e.n && r.name == e.name) { r.launches++; r.ms += ms; found = true; break; }
-    if (!found) out.push_back(ProfileRecord{e.name, e.n, 1, (double)ms});
+      if (r.n == e.n && r.tag == e.tag && r.name == e.name) { r.launches++; r.ms += ms; found = true; break; }
+    if (!found) out.push_back(ProfileRecord{e.name, e.n, 1, (double)ms, e.tag});
     profPool().push_back(e.a);
     profPool().push_back(e.b);
   }

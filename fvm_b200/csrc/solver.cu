@@ -839,8 +839,15 @@ void Amg::runTail() {
 }
 
 // ================================================================= cycle
+struct LevelTag {  // profiler: launches issued in this scope carry the AMG level
+  int prev;
+  explicit LevelTag(int lvl) : prev(ctx().profileTag) { ctx().profileTag = lvl; }
+  ~LevelTag() { ctx().profileTag = prev; }
+};
+
 void Amg::sweeps(int nSweeps, int lvl) {
   Level& L = *levels[lvl];
+  LevelTag tag(lvl);
   // A colour pass only reads the OTHER colours, so repeating the pass that was just done changes
   // nothing (bit for bit): the reverse half-sweep therefore starts at the last-but-one colour, and
   // a following forward half-sweep skips colour 0.
@@ -868,12 +875,14 @@ void Amg::sweeps(int nSweeps, int lvl) {
 
 void Amg::residual(int lvl) {
   Level& L = *levels[lvl];
+  LevelTag tag(lvl);
   parallelFor(L.n, ResidualRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p});
   L.rValid = true;
 }
 
 double Amg::residualNorm(int lvl) {
   Level& L = *levels[lvl];
+  LevelTag tag(lvl);
   reduceRows<1>(L.n, ResidualRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p}, scalars.p);
   L.rValid = true;
   double v;
@@ -893,13 +902,13 @@ void Amg::cycle(int cycleType, int lvl) {
       if (!L.rValid) residual(lvl);
       src = L.r.p;
     }
-    parallelFor(C.n, InjectRows{L.memOff.p, L.mem.p, src, C.b.p, C.x.p});
+    { LevelTag tag(lvl); parallelFor(C.n, InjectRows{L.memOff.p, L.mem.p, src, C.b.p, C.x.p}); }
     C.xZero = true;
     C.rValid = false;
     cycle(cycleType, lvl + 1);
     if (cycleType == FVMGPU_CYCLE_W) cycle(FVMGPU_CYCLE_W, lvl + 1);
     else if (cycleType == FVMGPU_CYCLE_F) cycle(FVMGPU_CYCLE_V, lvl + 1);
-    parallelFor(L.n, CorrectRows{L.ci.p, C.x.p, L.x.p});
+    { LevelTag tag(lvl); parallelFor(L.n, CorrectRows{L.ci.p, C.x.p, L.x.p}); }
     L.xZero = false;
     L.rValid = false;
   }
@@ -944,6 +953,7 @@ void Amg::cycleGraphed(int kind) {
     if (kind == 1) { L0.x.zero(); L0.xZero = true; L0.rValid = false; }
     cycle(opts.cycleType, 0);
     if (kind == 0) {
+      LevelTag tag(0);
       reduceRows<1>(L0.n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, L0.b.p, L0.x.p, L0.r.p},
                     scalars.p);
       L0.rValid = true;

@@ -38,7 +38,7 @@ static Mesh* quadMesh(int n) {
   for (int j = 0; j < np; j++)
     for (int i = 0; i < np; i++) {
       coords[i + np * j][0] = double(i) / n;
-      coords[i + np * j][1] = double(j) / n + 0.03 * std::sin(7.0 * i / n) * (j > 0 && j < n);
+      coords[i + np * j][1] = double(j) / n + (0.3 / n) * std::sin(7.0 * i / n) * (j > 0 && j < n);
       coords[i + np * j][2] = 0;
     }
   std::vector<int> fc, fn;
