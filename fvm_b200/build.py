@@ -20,6 +20,7 @@ HOSTSIM_LIB = os.path.join(HOSTSIM_DIR, "libfvmgpu_hostsim.so")
 # sequence of IEEE operations as the reference's x86-64 build gives the same bits.
 SOURCES = [
     ("runtime.cu", []),
+    ("comm.cu", []),
     ("mesh.cu", ["-fmad=false"]),
     ("assemble.cu", ["-fmad=false"]),
     ("solver.cu", []),

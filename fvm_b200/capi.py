@@ -98,6 +98,8 @@ SIGNATURES = {
     "fvmgpu_comm_unique_id": (C.c_int, [C.c_char_p]),
     "fvmgpu_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p]),
     "fvmgpu_comm_destroy": (C.c_int, []),
+    "fvmgpu_comm_counters": (C.c_int, [C.POINTER(C.c_longlong)]),
+    "fvmgpu_system_halo_exchange": (C.c_int, [_vp, C.c_int]),
 }
 
 
@@ -203,6 +205,24 @@ class Lib:
                             level=level))
         return out
 
+    # ---- multi-GPU
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self.call("fvmgpu_comm_unique_id", buf)
+        return buf.raw
+
+    def comm_init(self, nranks, rank, unique_id=None):
+        self.call("fvmgpu_comm_init", int(nranks), int(rank), unique_id if unique_id is not None else b"\0" * 128)
+        self.nranks, self.rank = int(nranks), int(rank)
+
+    def comm_destroy(self):
+        self.call("fvmgpu_comm_destroy")
+
+    def comm_collectives(self):
+        n = C.c_longlong(0)
+        self.call("fvmgpu_comm_counters", C.byref(n))
+        return n.value
+
     def default_amg_opts(self):
         o = AmgOpts()
         self.dll.fvmgpu_amg_default_opts(C.byref(o))
@@ -247,6 +267,13 @@ class DeviceMesh:
         _b, ibp = _nullable(ib_type, np.int32)
         self.lib.call("fvmgpu_mesh_set_geometry", self.h, _f64(face_area).reshape(-1), _f64(face_area_mag),
                       fcp, _f64(cell_centroid).reshape(-1), _f64(cell_volume), ibp)
+
+    def set_halo(self, peers, scatter_off, scatter_idx, gather_off, gather_idx):
+        """StorageSite scatter/gather maps per neighbour rank (F/StorageSite.h:58-84)."""
+        z = np.zeros(1, np.int32)
+        self.lib.call("fvmgpu_mesh_set_halo", self.h, len(peers), _i32(peers) if len(peers) else z,
+                      _i32(scatter_off), _i32(scatter_idx) if len(scatter_idx) else z, _i32(gather_off),
+                      _i32(gather_idx) if len(gather_idx) else z)
 
     def pair_to_col(self):
         out = np.zeros(2 * self.n_faces, np.int32)
@@ -324,6 +351,9 @@ class DeviceSystem:
 
     def post_solve_update(self):
         self.lib.call("fvmgpu_post_solve_update", self.h)
+
+    def halo_exchange(self, field):
+        self.lib.call("fvmgpu_system_halo_exchange", self.h, int(field))
 
     def close(self):
         if self.h:

@@ -618,6 +618,16 @@ void systemSetBc(System* s, int groupId, int kind, const double* p, int np, cons
   fail("set_bc: no boundary face group with id %d", groupId);
 }
 
+void systemHaloExchange(System* s, int field) {
+  requireReady();
+  if (!s->mesh) fail("halo_exchange: raw systems have no halo maps");
+  size_t len = 0;
+  DBuf<double>* buf = fieldBuf(s, field, len);
+  if (!buf || !buf->p || len != (size_t)s->nTotal) fail("halo_exchange: field %d is not a cell field", field);
+  s->mesh->halo.exchange(buf->p, 1);
+  if (field == FVMGPU_FIELD_X) s->gradientValid = false;
+}
+
 void computeGradient(System* s) {
   requireReady();
   Mesh* m = s->mesh;
@@ -625,6 +635,9 @@ void computeGradient(System* s) {
   parallelFor(m->nTotal, GradientRows{m->nSelf, m->nInteriorFaces, m->row.p, m->col.p, m->entryFace.p,
                                       m->faceGroupOf.p, m->groupKindDev.p, m->faceGeom.p, s->x.p, m->gradW.p,
                                       m->nnz, s->cellState.p});
+  // interface ghost cells: {gradient, x} of the owning rank (GradientModel::compute ends with the
+  // gradient halo sync, F/GradientModel.h:600)
+  m->halo.exchange(reinterpret_cast<double*>(s->cellState.p), 4);
   s->gradientValid = true;
 }
 
@@ -668,6 +681,7 @@ void postSolveUpdate(System* s) {
     parallelFor(m->nTotal, PostSolveRows{m->nSelf, m->nInteriorFaces, m->row.p, m->col.p, m->entryFace.p,
                                          s->diag.p, s->off.p, s->b.p, s->isBoundary.p, s->delta.p, s->x.p,
                                          s->bflux.p, s->rflux.p, s->coeffL.p, s->coeffR.p, 1});
+    m->halo.exchange(s->x.p, 1);  // updateSolution: x.sync() (F/LinearSystem.cpp:268)
   } else {
     parallelFor(s->nTotal, PostSolveRows{s->nSelf, 0, s->row, s->col, nullptr, s->diag.p, s->off.p, s->b.p,
                                          s->isBoundary.p, s->delta.p, s->x.p, nullptr, nullptr, nullptr, nullptr, 0});

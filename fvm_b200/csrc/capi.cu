@@ -4,10 +4,6 @@
 // (F/CException.h:16-21, F/baseExt.i:49-59).
 #include "solver.cuh"
 
-#ifndef FVMGPU_HOSTSIM
-#include <dlfcn.h>
-#endif
-
 using namespace fvmgpu;
 
 static thread_local std::string g_lastError;
@@ -352,12 +348,17 @@ int fvmgpu_amg_destroy(fvmgpu_solver_t s) {
 int fvmgpu_amg_levels(fvmgpu_solver_t s, int cap, int* nLevels, long long* sizes, long long* nnzs, int* colours) {
   API_BEGIN
   Amg* a = A(s);
-  const int nl = (int)a->levels.size();
+  // distributed levels (this rank's rows), then the levels of the replicated merged hierarchy
+  // below the merged level (multi-GPU; its level 0 is the merged level itself in global size)
+  std::vector<Level*> all;
+  for (auto& l : a->levels) all.push_back(l.get());
+  if (a->nested) for (auto& l : a->nested->levels) all.push_back(l.get());
+  const int nl = (int)all.size();
   if (nLevels) *nLevels = nl;
   for (int l = 0; l < nl && l < cap; l++) {
-    if (sizes) sizes[l] = a->levels[l]->n;
-    if (nnzs) nnzs[l] = a->levels[l]->nnzTrue;
-    if (colours) colours[l] = a->levels[l]->nColours;
+    if (sizes) sizes[l] = all[l]->n;
+    if (nnzs) nnzs[l] = all[l]->nnzTrue;
+    if (colours) colours[l] = all[l]->nColours;
   }
   API_END
 }
@@ -375,83 +376,50 @@ int fvmgpu_bcgstab_solve(fvmgpu_solver_t precond, fvmgpu_system_t sys, int nMaxI
   A(precond)->bcgstab(S(sys), nMaxIterations, relativeTolerance, absoluteTolerance, rnorm0, rnorm, iters);
   API_END
 }
+int fvmgpu_system_halo_exchange(fvmgpu_system_t sys, int field) {
+  API_BEGIN
+  systemHaloExchange(S(sys), field);
+  API_END
+}
 int fvmgpu_post_solve_update(fvmgpu_system_t sys) {
   API_BEGIN
   postSolveUpdate(S(sys));
   API_END
 }
 
-// ---------------------------------------------------------------- multi-GPU plumbing
-// NCCL is resolved at run time (dlopen) so that libfvmgpu.so carries no link-time dependency;
-// in a torchrun-launched process torch has already loaded its bundled libnccl.so.2.
-#ifndef FVMGPU_HOSTSIM
-struct Id128 { char b[128]; };  // ncclUniqueId is passed BY VALUE (128 bytes)
-namespace {
-struct NcclApi {
-  void* lib = nullptr;
-  int (*GetUniqueId)(void*) = nullptr;
-  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
-  int (*CommDestroy)(void*) = nullptr;
-  const char* (*GetErrorString)(int) = nullptr;
-};
-}  // namespace
-static NcclApi& nccl() {
-  static NcclApi api;
-  if (!api.lib) {
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* nm : names) {
-      api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-      if (api.lib) break;
-    }
-    if (!api.lib) fail("multi-GPU: cannot dlopen libnccl.so.2 (%s)", dlerror());
-    api.GetUniqueId = (int (*)(void*))dlsym(api.lib, "ncclGetUniqueId");
-    api.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(api.lib, "ncclCommInitRank");
-    api.CommDestroy = (int (*)(void*))dlsym(api.lib, "ncclCommDestroy");
-    api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
-    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy) fail("multi-GPU: libnccl lacks required symbols");
-  }
-  return api;
-}
-#endif
-
+// ---------------------------------------------------------------- multi-GPU plumbing (comm.cu)
 int fvmgpu_comm_unique_id(void* out128) {
   API_BEGIN
-#ifndef FVMGPU_HOSTSIM
-  int rc = nccl().GetUniqueId(out128);
-  if (rc) fail("ncclGetUniqueId failed: %d", rc);
-#else
-  std::memset(out128, 0, 128);
-#endif
+  commUniqueId(out128);
   API_END
 }
 int fvmgpu_comm_init(int nranks, int rank, const void* uniqueId128) {
   API_BEGIN
   requireReady();
   if (nranks < 1 || rank < 0 || rank >= nranks) fail("comm_init: bad rank %d of %d", rank, nranks);
+  commInitNccl(nranks, rank, uniqueId128);
   ctx().nranks = nranks;
   ctx().rank = rank;
-#ifndef FVMGPU_HOSTSIM
-  if (nranks > 1) {
-    Id128 id;
-    std::memcpy(id.b, uniqueId128, 128);
-    void* comm = nullptr;
-    int rc = nccl().CommInitRank(&comm, nranks, id, rank);
-    if (rc) fail("ncclCommInitRank failed: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
-    ctx().ncclComm = comm;
-  }
-#else
-  (void)uniqueId128;
-#endif
   API_END
 }
 int fvmgpu_comm_destroy(void) {
   API_BEGIN
-#ifndef FVMGPU_HOSTSIM
-  if (ctx().ncclComm) { nccl().CommDestroy(ctx().ncclComm); ctx().ncclComm = nullptr; }
-#endif
+  commDestroy();
   ctx().nranks = 1;
   ctx().rank = 0;
   API_END
 }
+int fvmgpu_comm_counters(long long* collectives) {
+  API_BEGIN
+  if (collectives) *collectives = ctx().collectives;
+  API_END
+}
+#ifdef FVMGPU_HOSTSIM
+int fvmgpu_hostsim_set_comm(fvmgpu_hostsim_exchange_fn e, fvmgpu_hostsim_allreduce_fn r, fvmgpu_hostsim_allgather_fn g) {
+  API_BEGIN
+  hostsimSetComm(e, r, g);
+  API_END
+}
+#endif
 
 }  // extern "C"

@@ -1,0 +1,65 @@
+// fvm_b200 / libfvmgpu -- inter-rank communication of the hot path (one process per GPU).
+//
+// What the reference does with MPI                         here
+//   MultiField::sync / Field::syncLocal                     Halo::exchange: pack kernel -> grouped
+//     Isend/Irecv of packed ghost values + Waitall            ncclSend/ncclRecv over NVLink -> unpack
+//     (F/MultiField.cpp:488-551, F/Field.cpp:333-394)         kernel, all stream ordered
+//   MultiFieldReduction::reduceSum  Allreduce(SUM)          commAllreduceSum (ncclAllReduce, 1-8 doubles)
+//     (F/MultiFieldReduction.cpp:213-225)
+//   LinearSystemMerger Gatherv/Scatterv of coarse levels    commAllgather (ncclAllGather, equal-size
+//     (F/LinearSystemMerger.cpp:720-819)                      padded blocks)
+//
+// NCCL is resolved with dlopen (no link-time dependency). The FVMGPU_HOSTSIM test build replaces
+// the transport by callbacks the test harness registers (tests drive them with torch.distributed
+// gloo, world_size 2); the pack/unpack kernels and all index logic are the same code.
+#pragma once
+#include "common.cuh"
+
+namespace fvmgpu {
+
+struct HaloMsg {
+  int rank;              // peer
+  int sendOff, sendCnt;  // in entries of the send buffer
+  int recvOff, recvCnt;
+};
+
+inline bool commActive() { return ctx().nranks > 1; }
+// exchange `width` doubles per entry with every peer (send_d/recv_d are device buffers)
+void commExchange(const std::vector<HaloMsg>& msgs, const double* send_d, double* recv_d, int width);
+void commAllreduceSum(double* data_d, int n);                       // in place
+void commAllgather(const void* send_d, void* recv_d, size_t bytesPerRank);
+double commSumHost(double v);                                       // host scalar convenience (synchronises)
+double commMaxHost(double v);
+inline bool commAll(bool ok) { return !commActive() ? ok : commSumHost(ok ? 1.0 : 0.0) > ctx().nranks - 0.5; }
+inline bool commAny(bool ok) { return !commActive() ? ok : commSumHost(ok ? 1.0 : 0.0) > 0.5; }
+
+// One halo = scatter/gather index lists + staging buffers for one vector layout.
+struct Halo {
+  std::vector<HaloMsg> msgs;
+  DBuf<int> scatterIdx, gatherIdx;  // entries to send / slots to fill (indices into the vector)
+  DBuf<double> sendBuf, recvBuf;
+  int nSend = 0, nRecv = 0, widthCap = 0;
+  bool empty() const { return msgs.empty(); }
+  void build(const std::vector<HaloMsg>& m, const std::vector<int>& scatter, const std::vector<int>& gather);
+  // same with the scatter list already on the device
+  void buildDev(const std::vector<HaloMsg>& m, DBuf<int>&& scatterDev, int nSendEntries, const std::vector<int>& gather);
+  // x is `width` doubles per entry (AoS); ghost slots of x are overwritten with the peers' values
+  void exchange(double* x, int width = 1);
+};
+
+#ifdef FVMGPU_HOSTSIM
+// test-only transport: the harness (tests/multirank_worker.py) implements these with torch.distributed (gloo)
+extern "C" {
+typedef void (*fvmgpu_hostsim_exchange_fn)(int nMsgs, const int* peer, const int* sendOff, const int* sendCnt,
+                                           const double* send, const int* recvOff, const int* recvCnt, double* recv);
+typedef void (*fvmgpu_hostsim_allreduce_fn)(double* data, int n);
+typedef void (*fvmgpu_hostsim_allgather_fn)(const void* send, void* recv, long long bytesPerRank);
+}
+void hostsimSetComm(fvmgpu_hostsim_exchange_fn e, fvmgpu_hostsim_allreduce_fn r, fvmgpu_hostsim_allgather_fn g);
+#endif
+
+void commInitNccl(int nranks, int rank, const void* uniqueId128);
+void commUniqueId(void* out128);
+void commDestroy();
+
+}  // namespace fvmgpu

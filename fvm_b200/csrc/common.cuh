@@ -77,6 +77,7 @@ struct Context {
 #endif
   long long launches = 0;  // kernels launched by this library
   long long h2d = 0, d2h = 0;
+  long long collectives = 0;  // halo exchanges / all-reduces / all-gathers issued
   void* l2scratch = nullptr;
   double* reduceScratch = nullptr;  // per-block partial sums (deterministic two-stage reductions)
   double* reduceHost = nullptr;     // pinned host landing zone for reduction results

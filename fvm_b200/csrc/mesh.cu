@@ -232,22 +232,20 @@ void meshSetGeometry(Mesh* m, const double* faceArea, const double* faceAreaMag,
 void meshSetHalo(Mesh* m, int nNeigh, const int* peerRank, const int* scatterOff, const int* scatterIdx,
                  const int* gatherOff, const int* gatherIdx) {
   requireReady();
-  m->peers.clear();
+  std::vector<HaloMsg> msgs;
   for (int p = 0; p < nNeigh; p++) {
-    HaloPeer hp;
-    hp.rank = peerRank[p];
-    hp.scatterOff = scatterOff[p];
-    hp.gatherOff = gatherOff[p];
-    hp.nScatter = scatterOff[p + 1] - scatterOff[p];
-    hp.nGather = gatherOff[p + 1] - gatherOff[p];
-    m->peers.push_back(hp);
+    HaloMsg hm;
+    hm.rank = peerRank[p];
+    hm.sendOff = scatterOff[p]; hm.sendCnt = scatterOff[p + 1] - scatterOff[p];
+    hm.recvOff = gatherOff[p]; hm.recvCnt = gatherOff[p + 1] - gatherOff[p];
+    msgs.push_back(hm);
   }
-  m->nScatterTotal = nNeigh ? scatterOff[nNeigh] : 0;
-  m->nGatherTotal = nNeigh ? gatherOff[nNeigh] : 0;
-  m->scatterIdx.upload(scatterIdx, m->nScatterTotal);
-  m->gatherIdx.upload(gatherIdx, m->nGatherTotal);
-  m->sendBuf.alloc(3 * m->nScatterTotal + 1);
-  m->recvBuf.alloc(3 * m->nGatherTotal + 1);
+  const int ns = nNeigh ? scatterOff[nNeigh] : 0, ng = nNeigh ? gatherOff[nNeigh] : 0;
+  m->haloScatterHost.assign(scatterIdx, scatterIdx + ns);
+  m->haloGatherHost.assign(gatherIdx, gatherIdx + ng);
+  for (int v : m->haloScatterHost) if (v < 0 || v >= m->nSelf) fail("set_halo: scatter index %d is not an interior cell", v);
+  for (int v : m->haloGatherHost) if (v < m->nSelf || v >= m->nTotal) fail("set_halo: gather index %d is not a ghost cell", v);
+  m->halo.build(msgs, m->haloScatterHost, m->haloGatherHost);
   streamSync();
 }
 

@@ -23,7 +23,15 @@
 // FP64 arrays in the same numbering and stay resident in HBM for the whole solve.
 #include "solver.cuh"
 
+#include <algorithm>
+
 namespace fvmgpu {
+
+struct LevelTag {  // profiler: launches issued in this scope carry the AMG level
+  int prev;
+  explicit LevelTag(int lvl) : prev(ctx().profileTag) { ctx().profileTag = lvl; }
+  ~LevelTag() { ctx().profileTag = prev; }
+};
 
 // ================================================================= small kernels
 FVM_DEV unsigned hash32(unsigned a) {
@@ -89,6 +97,17 @@ struct BfsCheckKernel {  // flags[1]: an edge inside one parity class (odd cycle
       const int j = col[k];
       if (j < n && j != i && depth[j] != -1 && ((depth[j] ^ di) & 1) == 0) { flags[1] = 1; return; }
     }
+  }
+};
+struct BfsIsolatedKernel {  // rows without neighbours are their own (trivially 2-colourable) component
+  int n; const int* row; const int* col; int* depth;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    for (int k = row[i]; k < row[i + 1]; k++) {
+      const int j = col[k];
+      if (j < n && j != i) return;
+    }
+    depth[i] = 0;
   }
 };
 struct SetIntKernel { int* p; int idx; int v; FVM_DEV void operator()(long long) const { p[idx] = v; } };
@@ -412,7 +431,8 @@ struct UpperBoundKernel {
 };
 struct CoarseRowKernel {  // Galerkin-by-summation for one coarse row (first-seen column order)
   int n; const int* memOff; const int* mem; const int* sliceOff; const int* scol; const double* sval;
-  const double* diag; const int* ci; const int* ubOff; int* tmpCol; double* tmpVal; int* cnt; double* cdiag;
+  const double* diag; const int* ci; const int* ghostCoarse; const int* ubOff; int* tmpCol; double* tmpVal; int* cnt;
+  double* cdiag;
   FVM_DEV void operator()(long long II) const {
     const int I = (int)II;
     const int base = ubOff[I];
@@ -426,8 +446,8 @@ struct CoarseRowKernel {  // Galerkin-by-summation for one coarse row (first-see
         const int j = scol[p];
         const double v = sval[p];
         if (j == m) continue;  // SELL padding
-        if (j >= n) continue;  // ghost column (multi-GPU coarse ghosts are handled by the halo layer)
-        const int J = ci[j];
+        // ghost column: the coarse ghost slot of the owning rank's aggregate (multi-GPU), else dropped
+        const int J = j >= n ? (ghostCoarse ? ghostCoarse[j - n] : -1) : ci[j];
         if (J < 0) continue;
         if (J == I) { d += v; continue; }
         int k = 0;
@@ -452,6 +472,20 @@ struct RemapCiKernel {
   FVM_DEV void operator()(long long i) const { const int c = ci[i]; if (c >= 0) ci[i] = perm[c]; }
 };
 
+struct GatherIntAsDoubleKernel {  // out[k] = (double) src[idx[k]]
+  const int* idx; const int* src; double* out;
+  FVM_DEV void operator()(long long k) const { out[k] = (double)src[idx[k]]; }
+};
+struct GatherIntKernel {  // out[k] = src[idx[k]]
+  const int* idx; const int* src; int* out;
+  FVM_DEV void operator()(long long k) const { out[k] = src[idx[k]]; }
+};
+struct ComposeGhostKernel {  // o[g] = b[a[g] - nMid]  (a: x index in the middle level, -1 passes through)
+  const int* a; const int* b; int nMid; int* o;
+  FVM_DEV void operator()(long long g) const { const int c = a[g]; o[g] = c >= nMid ? b[c - nMid] : -1; }
+};
+struct IotaDblKernel { double* p; FVM_DEV void operator()(long long i) const { p[i] = (double)i; } };
+
 // ================================================================= level construction
 // Colour a CSR pattern; returns number of colours, fills colour[] (device)
 static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& colour) {
@@ -459,8 +493,9 @@ static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& co
   depth.fillBytes(0xff);
   int d = 0, seed = 0;
   const int big = 0x7fffffff;
+  parallelFor(n, BfsIsolatedKernel{n, row, col, depth.p});
   parallelFor(1, SetIntKernel{depth.p, seed, 0});
-  int rounds = 0;
+  int rounds = 0, components = 1;
   for (;;) {
     int h[4] = {0, 0, big, 0};
     copyH2D(flags.p, h, sizeof(h));
@@ -475,6 +510,7 @@ static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& co
     if (h[1]) return false;              // odd cycle: not bipartite
     if (h[0]) continue;                  // the front is still moving
     if (h[2] == big) break;              // everything reached
+    if (++components > 32) return false; // many components: leave it to the general colouring
     d = (d + 2) & ~1;                    // next component: restart from an even depth
     parallelFor(1, SetIntKernel{depth.p, h[2], d});
     if (rounds > 4 * n + 64) return false;
@@ -523,8 +559,9 @@ static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, s
 
 // Build level L from a CSR system in "natural" numbering; returns perm (natural -> level numbering).
 static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, const double* val,
-                              const double* diag, bool dropGhost, DBuf<int>& perm) {
+                              const double* diag, bool dropGhost, DBuf<int>& perm, int nGhost = 0) {
   L.n = n;
+  L.nGhost = dropGhost ? 0 : nGhost;
   std::vector<int> counts;
   DBuf<int> colour;
   L.nColours = colourCsr(n, row, col, colour, counts);
@@ -551,7 +588,7 @@ static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, c
   L.nnzStored = total;
   L.scol.alloc(total > 0 ? total : 1);
   L.sval.alloc(total > 0 ? total : 1);
-  L.diag.alloc(n); L.b.alloc(n); L.x.alloc(n); L.r.alloc(n);
+  L.diag.alloc(n); L.b.alloc(n); L.x.alloc((size_t)n + L.nGhost); L.r.alloc((size_t)n + L.nGhost);
   L.b.zero(); L.x.zero(); L.r.zero();
   parallelFor(n, SellFillKernel{n, invp.p, perm.p, row, col, val, diag, dropGhost ? 1 : 0, L.sliceOff.p, L.scol.p,
                                 L.sval.p, L.diag.p});
@@ -562,10 +599,13 @@ static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, c
   streamSync();
 }
 
-// Coarsen level F into level C (one pairwise pass). Returns false if no reduction happened.
-static bool coarsenOnce(Level& F, const int* excluded, double threshold, DBuf<int>& ciNat, int& nc,
-                        DBuf<int>& crow, DBuf<int>& ccol, DBuf<double>& cval, DBuf<double>& cdiag) {
+// ---- one pairwise coarsening pass of level F, in three steps
+// (1) aggregate: parallel handshake pairing -> ciNat[i] = aggregate of row i in the NATURAL coarse
+//     numbering (aggregates numbered in the order of their natural root rows), nc aggregates.
+static bool aggregate(Level& F, const int* excluded, double threshold, DBuf<int>& ciNat, int& nc) {
   const int n = F.n;
+  nc = 0;
+  if (n <= 1) return false;
   DBuf<double> strongest(n);
   DBuf<int> root(n), propose(n), join(n), isRoot(n), rootScan(n + 1);
   root.fillBytes(0xff);
@@ -583,7 +623,62 @@ static bool coarsenOnce(Level& F, const int* excluded, double threshold, DBuf<in
   nc = rootScan.hostAt(n);
   ciNat.alloc(n);
   parallelFor(n, AggIdKernel{root.p, F.nat.p, rootScan.p, ciNat.p});
-  if (nc <= 0 || nc >= n) return false;
+  streamSync();
+  return nc > 0 && nc < n;
+}
+
+// (2) multi-GPU only: the coarse level's halo. Every rank sends, for each row of its scatter list,
+//     the aggregate that row went into (its own natural coarse id); the receiver gives every
+//     distinct (peer, id) one coarse ghost slot, ordered by id, and the sender builds the very same
+//     ordered list from its own data -- so the coarse scatter/gather lists match without a second
+//     message (the reference renumbers ghost coarse indices per neighbour likewise,
+//     F/MultiFieldMatrix.cpp:475-624). Fills F.ghostCoarse (fine ghost slot -> coarse x index).
+struct CoarseHaloInfo {
+  std::vector<HaloMsg> msgs;
+  std::vector<int> scatterNat;  // natural coarse ids to send, concatenated per peer
+  int nGhost = 0;
+};
+static void coarseHalo(Level& F, const DBuf<int>& ciNat, int nc, CoarseHaloInfo& H) {
+  H.msgs.clear(); H.scatterNat.clear(); H.nGhost = 0;
+  std::vector<int> ghostCoarse((size_t)F.nGhost, -1);
+  const int ns = F.halo.nSend, nr = F.halo.nRecv;
+  DBuf<double> send((size_t)ns + 1), recv((size_t)nr + 1);
+  if (ns) parallelFor(ns, GatherIntAsDoubleKernel{F.halo.scatterIdx.p, ciNat.p, send.p});
+  commExchange(F.halo.msgs, send.p, recv.p, 1);
+  std::vector<double> hs((size_t)ns + 1), hr((size_t)nr + 1);
+  send.download(hs.data(), (size_t)ns + 1);
+  recv.download(hr.data(), (size_t)nr + 1);
+  int sOff = 0, gOff = 0;
+  for (const HaloMsg& m : F.halo.msgs) {
+    std::vector<int> us, ur;
+    for (int k = 0; k < m.sendCnt; k++) { const int id = (int)hs[(size_t)m.sendOff + k]; if (id >= 0) us.push_back(id); }
+    for (int k = 0; k < m.recvCnt; k++) { const int id = (int)hr[(size_t)m.recvOff + k]; if (id >= 0) ur.push_back(id); }
+    std::sort(us.begin(), us.end()); us.erase(std::unique(us.begin(), us.end()), us.end());
+    std::sort(ur.begin(), ur.end()); ur.erase(std::unique(ur.begin(), ur.end()), ur.end());
+    for (int k = 0; k < m.recvCnt; k++) {
+      const int id = (int)hr[(size_t)m.recvOff + k];
+      if (id < 0) continue;
+      const int slot = (int)(std::lower_bound(ur.begin(), ur.end(), id) - ur.begin());
+      ghostCoarse[(size_t)F.gatherHost[(size_t)m.recvOff + k] - F.n] = nc + gOff + slot;
+    }
+    HaloMsg cm;
+    cm.rank = m.rank;
+    cm.sendOff = sOff; cm.sendCnt = (int)us.size();
+    cm.recvOff = gOff; cm.recvCnt = (int)ur.size();
+    H.msgs.push_back(cm);
+    H.scatterNat.insert(H.scatterNat.end(), us.begin(), us.end());
+    sOff += (int)us.size();
+    gOff += (int)ur.size();
+  }
+  H.nGhost = gOff;
+  F.ghostCoarse.upload(ghostCoarse.data(), ghostCoarse.size());
+}
+
+// (3) Galerkin by summation through ciNat (and F.ghostCoarse for ghost columns): coarse CSR in the
+//     natural coarse numbering, ghost columns >= nc.
+static void galerkin(Level& F, const DBuf<int>& ciNat, int nc, DBuf<int>& crow, DBuf<int>& ccol, DBuf<double>& cval,
+                     DBuf<double>& cdiag) {
+  const int n = F.n;
   // members (natural coarse numbering)
   DBuf<int> key(n), mem(n), memOff(nc + 2);
   parallelFor(n, SortKeyKernel{ciNat.p, nc, key.p, mem.p});
@@ -596,7 +691,6 @@ static bool coarsenOnce(Level& F, const int* excluded, double threshold, DBuf<in
     int last = memOff.hostAt(nc);
     if (last < 0) { int nn = n; copyH2D(memOff.p + nc, &nn, sizeof(int)); }
   }
-  // coarse matrix
   DBuf<int> ub(nc + 1), ubOff(nc + 1), cnt(nc + 1);
   parallelFor(nc, UpperBoundKernel{memOff.p, mem.p, F.sliceOff.p, ub.p});
   exclusiveScan(ub.p, ubOff.p, nc);
@@ -604,8 +698,8 @@ static bool coarsenOnce(Level& F, const int* excluded, double threshold, DBuf<in
   DBuf<int> tmpCol(ubTotal > 0 ? ubTotal : 1);
   DBuf<double> tmpVal(ubTotal > 0 ? ubTotal : 1);
   cdiag.alloc(nc);
-  parallelFor(nc, CoarseRowKernel{n, memOff.p, mem.p, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, ciNat.p, ubOff.p,
-                                  tmpCol.p, tmpVal.p, cnt.p, cdiag.p});
+  parallelFor(nc, CoarseRowKernel{n, memOff.p, mem.p, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, ciNat.p,
+                                  F.ghostCoarse.p, ubOff.p, tmpCol.p, tmpVal.p, cnt.p, cdiag.p});
   crow.alloc(nc + 1);
   exclusiveScan(cnt.p, crow.p, nc);
   const int cnnz = crow.hostAt(nc);
@@ -613,7 +707,45 @@ static bool coarsenOnce(Level& F, const int* excluded, double threshold, DBuf<in
   cval.alloc(cnnz > 0 ? cnnz : 1);
   parallelFor(nc, CompactKernel{ubOff.p, crow.p, tmpCol.p, tmpVal.p, ccol.p, cval.p});
   streamSync();
-  return true;
+}
+
+// Every rank must issue the same number of colour passes (each is followed by a halo exchange):
+// ranks with fewer colours run empty passes for the missing ones.
+static void agreeColours(Level& L) {
+  const int ncg = (int)commMaxHost((double)L.nColours);
+  while ((int)L.colourStart.size() < ncg + 1) L.colourStart.push_back(L.n);
+  L.nColours = ncg;
+}
+
+// One full pass F -> C: returns the new level (rows renumbered colour by colour), ci = F row -> C row,
+// and (multi-GPU) F.ghostCoarse / C.halo. All ranks take the same branch (agreed by all-reduce).
+static std::unique_ptr<Level> coarsenPass(Level& F, const int* excluded, double threshold, bool multi, DBuf<int>& ci) {
+  DBuf<int> ciNat, crow, ccol, perm;
+  DBuf<double> cval, cdiag;
+  int nc = 0;
+  bool ok = aggregate(F, excluded, threshold, ciNat, nc);
+  if (multi) ok = commAll(ok);
+  if (!ok) return nullptr;
+  CoarseHaloInfo H;
+  F.ghostCoarse.release();
+  if (multi) coarseHalo(F, ciNat, nc, H);
+  galerkin(F, ciNat, nc, crow, ccol, cval, cdiag);
+  std::unique_ptr<Level> C(new Level);
+  buildLevelFromCsr(*C, nc, crow.p, ccol.p, cval.p, cdiag.p, !multi, perm, H.nGhost);
+  if (multi) {
+    const int ns = (int)H.scatterNat.size();
+    DBuf<int> natDev, scatterDev((size_t)ns + 1);
+    natDev.upload(H.scatterNat.data(), H.scatterNat.size());
+    if (ns) parallelFor(ns, GatherIntKernel{natDev.p, perm.p, scatterDev.p});
+    C->gatherHost.resize((size_t)H.nGhost);
+    for (int g = 0; g < H.nGhost; g++) C->gatherHost[(size_t)g] = nc + g;
+    C->halo.buildDev(H.msgs, std::move(scatterDev), ns, C->gatherHost);
+    agreeColours(*C);
+  }
+  parallelFor(F.n, RemapCiKernel{perm.p, ciNat.p});  // natural coarse id -> C's row numbering
+  ci = std::move(ciNat);
+  streamSync();
+  return C;
 }
 
 static void buildMembers(Level& F, int nc) {
@@ -635,6 +767,7 @@ static void buildMembers(Level& F, int nc) {
 void Amg::cleanup() {
   dropGraphs();
   tailStart = -1;
+  nested.reset(); mergedSys.reset(); mergedLevel = -1; nestedLoaded = false;
   levels.clear();
   builtFor = nullptr;
   builtVersion = 0;
@@ -645,11 +778,25 @@ void Amg::setup(System* sys) {
   dropGraphs();
   tailStart = -1;
   levels.clear();
+  nested.reset(); mergedSys.reset(); mergedLevel = -1; nestedLoaded = false;
   const int n = sys->nSelf;
-  // level 0 from the system's CSR; single GPU: ghost columns carry delta = 0 and are dropped
-  const bool dropGhost = !(sys->mesh && !sys->mesh->peers.empty());
+  // one GPU: ghost columns carry delta = 0 and are dropped. Several ranks: the interface ghost
+  // columns stay and their x slots are filled by the halo exchange.
+  multi = commActive() && sys->mesh && !sys->noHalo;
   levels.emplace_back(new Level);
-  buildLevelFromCsr(*levels[0], n, sys->row, sys->col, sys->off.p, sys->diag.p, dropGhost, perm0);
+  Level& L0 = *levels[0];
+  buildLevelFromCsr(L0, n, sys->row, sys->col, sys->off.p, sys->diag.p, !multi, perm0, sys->nTotal - n);
+  if (multi) {
+    Mesh* m = sys->mesh;
+    const int ns = m->halo.nSend;
+    DBuf<int> scatterDev((size_t)ns + 1);
+    if (ns) parallelFor(ns, GatherIntKernel{m->halo.scatterIdx.p, perm0.p, scatterDev.p});
+    L0.gatherHost = m->haloGatherHost;  // ghost columns keep their cell index (>= n)
+    L0.halo.buildDev(m->halo.msgs, std::move(scatterDev), ns, L0.gatherHost);
+    agreeColours(L0);
+    if (const char* e = getenv("FVMGPU_MULTI_GRAPHS")) useGraphs = atoi(e) != 0;
+    else useGraphs = false;
+  }
   // rows marked as boundary inside the interior range (setDirichlet) are not coarsened
   DBuf<int> excl0(n);
   parallelFor(n, PermIntKernel{perm0.p, sys->isBoundary.p, excl0.p});
@@ -657,50 +804,161 @@ void Amg::setup(System* sys) {
   int passesPerLevel = 1;
   while ((1 << passesPerLevel) < opts.coarseGroupSize) passesPerLevel++;
   if (opts.coarseGroupSize <= 1) passesPerLevel = 0;
+  int mergeRows = 32768;
+  if (const char* e = getenv("FVMGPU_MERGE_ROWS")) mergeRows = atoi(e);
 
   for (int lvl = 0; lvl < opts.maxCoarseLevels && passesPerLevel > 0; lvl++) {
     Level& F = *levels.back();
-    if (F.n <= 1) break;
-    DBuf<int> ciNat, crow, ccol, perm;
-    DBuf<double> cval, cdiag;
-    int nc = 0;
-    const int* excl = (lvl == 0) ? excl0.p : nullptr;
-    if (!coarsenOnce(F, excl, opts.weightRatioThreshold, ciNat, nc, crow, ccol, cval, cdiag)) break;
-    std::unique_ptr<Level> C(new Level);
-    buildLevelFromCsr(*C, nc, crow.p, ccol.p, cval.p, cdiag.p, false, perm);
+    DBuf<int> ci;
+    std::unique_ptr<Level> C = coarsenPass(F, lvl == 0 ? excl0.p : nullptr, opts.weightRatioThreshold, multi, ci);
+    if (!C) break;
     // coarseGroupSize > 2: pair again and compose the maps, dropping the intermediate level
-    for (int pass = 1; pass < passesPerLevel && C->n > 3; pass++) {
-      DBuf<int> ci2, crow2, ccol2, perm2;
-      DBuf<double> cval2, cdiag2;
-      int nc2 = 0;
-      parallelFor(F.n, RemapCiKernel{perm.p, ciNat.p});  // now in C numbering
-      if (!coarsenOnce(*C, nullptr, opts.weightRatioThreshold, ci2, nc2, crow2, ccol2, cval2, cdiag2)) {
-        // undo nothing: ciNat already final for C
-        perm.release();
-        break;
-      }
-      std::unique_ptr<Level> C2(new Level);
-      buildLevelFromCsr(*C2, nc2, crow2.p, ccol2.p, cval2.p, cdiag2.p, false, perm2);
-      // compose: fine -> C (ciNat) -> C2 natural (ci2) ; final remap by perm2 below
+    for (int pass = 1; pass < passesPerLevel; pass++) {
+      bool more = C->n > 3;
+      if (multi) more = commAll(more);
+      if (!more) break;
+      DBuf<int> ci2;
+      std::unique_ptr<Level> C2 = coarsenPass(*C, nullptr, opts.weightRatioThreshold, multi, ci2);
+      if (!C2) break;
       DBuf<int> composed(F.n);
-      parallelFor(F.n, ComposeKernel{ciNat.p, ci2.p, composed.p});
-      ciNat = std::move(composed);
-      perm = std::move(perm2);
+      parallelFor(F.n, ComposeKernel{ci.p, ci2.p, composed.p});
+      ci = std::move(composed);
+      if (multi && F.nGhost > 0) {
+        DBuf<int> g2((size_t)F.nGhost);
+        parallelFor(F.nGhost, ComposeGhostKernel{F.ghostCoarse.p, C->ghostCoarse.p, C->n, g2.p});
+        F.ghostCoarse = std::move(g2);
+      }
       C = std::move(C2);
-      nc = nc2;
     }
-    if (perm.p) parallelFor(F.n, RemapCiKernel{perm.p, ciNat.p});
-    F.ci = std::move(ciNat);
+    F.ci = std::move(ci);
     buildMembers(F, C->n);
     const int cn = C->n;
     // reference (parallel build, F/AMG.cpp:171-180): push the level, then stop once it has <= 3 rows
     levels.push_back(std::move(C));
-    if (cn <= 3) break;
+    if (multi) {
+      const double globalRows = commSumHost((double)cn);
+      if (globalRows <= (double)mergeRows || commAny(cn <= 3)) { buildMerged(); break; }
+    } else if (cn <= 3) {
+      break;
+    }
   }
-  buildTail();
+  if (!multi) buildTail();
   streamSync();
   builtFor = sys;
   builtVersion = sys->version;
+}
+
+// ================================================================= merged (replicated) coarse level
+// The last distributed level is all-gathered: rank r's row i gets the global id r*maxLocal + i
+// (blocks padded to the largest rank's row count with inert rows), ghost columns are rewritten to
+// the owner's global id, and every rank builds the same single-GPU hierarchy below it. During a
+// cycle the level's right-hand side is all-gathered, the replicated hierarchy runs one cycle on
+// every rank (bit-identical: same input, deterministic kernels) and each rank keeps its block.
+void Amg::buildMerged() {
+  mergedLevel = (int)levels.size() - 1;
+  Level& C = *levels[mergedLevel];
+  const int nr = ctx().nranks, me = ctx().rank;
+  // row counts / nnz of every rank
+  DBuf<double> cntSend(2), cntAll((size_t)2 * nr);
+  double hc[2] = {(double)C.n, (double)C.nnzStored};
+  copyH2D(cntSend.p, hc, sizeof(hc));
+  commAllgather(cntSend.p, cntAll.p, sizeof(hc));
+  std::vector<double> allCnt = cntAll.toHost();
+  int maxLocal = 1; long long maxStored = 1;
+  for (int r = 0; r < nr; r++) {
+    maxLocal = std::max(maxLocal, (int)allCnt[(size_t)2 * r]);
+    maxStored = std::max(maxStored, (long long)allCnt[(size_t)2 * r + 1]);
+  }
+  mergeMaxLocal = maxLocal;
+  // owner's row index of every ghost slot
+  DBuf<double> idx((size_t)C.n + C.nGhost + 1);
+  parallelFor(C.n + C.nGhost, IotaDblKernel{idx.p});
+  C.halo.exchange(idx.p, 1);
+  std::vector<double> hIdx = idx.toHost();
+  std::vector<int> slotPeer((size_t)C.nGhost, -1);
+  for (const HaloMsg& m : C.halo.msgs)
+    for (int k = 0; k < m.recvCnt; k++) slotPeer[(size_t)m.recvOff + k] = m.rank;
+  // local SELL -> padded CSR block with global column ids
+  std::vector<int> sliceOff = C.sliceOff.toHost(), scol = C.scol.toHost();
+  std::vector<double> sval = C.sval.toHost(), diag = C.diag.toHost();
+  const size_t maxNnz = (size_t)maxStored;
+  std::vector<int> bLen((size_t)maxLocal, 0), bCol(maxNnz, 0);
+  std::vector<double> bVal(maxNnz, 0.0), bDiag((size_t)maxLocal, -1.0);
+  size_t q = 0;
+  for (int r = 0; r < C.n; r++) {
+    const int s = r >> 5;
+    int len = 0;
+    for (int p = sliceOff[(size_t)s] + (r & 31); p < sliceOff[(size_t)s + 1]; p += 32) {
+      const int j = scol[(size_t)p];
+      if (j == r) continue;  // padding
+      int gid;
+      if (j < C.n) gid = me * maxLocal + j;
+      else gid = slotPeer[(size_t)j - C.n] * maxLocal + (int)hIdx[(size_t)j];
+      bCol[q] = gid; bVal[q] = sval[(size_t)p]; q++; len++;
+    }
+    bLen[(size_t)r] = len;
+    bDiag[(size_t)r] = diag[(size_t)r];
+  }
+  auto gatherVec = [&](const void* h, size_t bytes, std::vector<char>& out) {
+    DBuf<char> sd(bytes), rd(bytes * nr);
+    copyH2D(sd.p, h, bytes);
+    commAllgather(sd.p, rd.p, bytes);
+    out.resize(bytes * nr);
+    copyD2H(out.data(), rd.p, bytes * nr);
+  };
+  std::vector<char> gLen, gCol, gVal, gDiag;
+  gatherVec(bLen.data(), (size_t)maxLocal * sizeof(int), gLen);
+  gatherVec(bCol.data(), maxNnz * sizeof(int), gCol);
+  gatherVec(bVal.data(), maxNnz * sizeof(double), gVal);
+  gatherVec(bDiag.data(), (size_t)maxLocal * sizeof(double), gDiag);
+  const int N = nr * maxLocal;
+  std::vector<int> row((size_t)N + 1, 0), col, isB((size_t)N, 0);
+  std::vector<double> val, dg((size_t)N), bz((size_t)N, 0.0);
+  for (int r = 0; r < nr; r++) {
+    const int* len = reinterpret_cast<const int*>(gLen.data()) + (size_t)r * maxLocal;
+    const int* cc = reinterpret_cast<const int*>(gCol.data()) + (size_t)r * maxNnz;
+    const double* vv = reinterpret_cast<const double*>(gVal.data()) + (size_t)r * maxNnz;
+    const double* dd = reinterpret_cast<const double*>(gDiag.data()) + (size_t)r * maxLocal;
+    const int rows = (int)allCnt[(size_t)2 * r];
+    size_t pos = 0;
+    for (int i = 0; i < maxLocal; i++) {
+      const size_t g = (size_t)r * maxLocal + i;
+      dg[g] = dd[i];
+      if (i >= rows) isB[g] = 1;  // padding row: inert (x = -b/diag = 0), never coarsened
+      for (int k = 0; k < len[i]; k++) { col.push_back(cc[pos]); val.push_back(vv[pos]); pos++; }
+      row[g + 1] = (int)col.size();
+    }
+  }
+  if (col.empty()) { col.push_back(0); val.push_back(0.0); }
+  mergedSys.reset(systemCreateRaw(N, 0, row.data(), col.data(), dg.data(), val.data(), bz.data()));
+  mergedSys->isBoundary.upload(isB.data(), isB.size());
+  mergedSys->noHalo = true;
+  nested.reset(new Amg);
+  nested->opts = opts;
+  nested->setup(mergedSys.get());
+  mergeSend.alloc((size_t)maxLocal); mergeSend.zero();
+  mergeB.alloc((size_t)N); mergeX.alloc((size_t)N);
+  nestedLoaded = false;
+}
+
+void Amg::cycleMerged(int cycleType, int lvl) {
+  Level& C = *levels[lvl];
+  LevelTag tag(lvl);
+  if (C.xZero || !nestedLoaded) {
+    copyD2D(mergeSend.p, C.b.p, (size_t)C.n * sizeof(double));
+    commAllgather(mergeSend.p, mergeB.p, (size_t)mergeMaxLocal * sizeof(double));
+    nested->loadSystem(mergedSys.get(), mergeB.p, nullptr);
+    nestedLoaded = true;
+  }
+  nested->cycle(cycleType, 0);
+  nested->storeDelta(mergeX.p);
+  copyD2D(C.x.p, mergeX.p + (size_t)ctx().rank * mergeMaxLocal, (size_t)C.n * sizeof(double));
+  C.xZero = false;
+  C.rValid = false;
+}
+
+void Amg::exchange(Level& L, double* x) {
+  if (multi) L.halo.exchange(x, 1);
 }
 
 // ================================================================= coarse tail in one CTA
@@ -839,12 +1097,6 @@ void Amg::runTail() {
 }
 
 // ================================================================= cycle
-struct LevelTag {  // profiler: launches issued in this scope carry the AMG level
-  int prev;
-  explicit LevelTag(int lvl) : prev(ctx().profileTag) { ctx().profileTag = lvl; }
-  ~LevelTag() { ctx().profileTag = prev; }
-};
-
 void Amg::sweeps(int nSweeps, int lvl) {
   Level& L = *levels[lvl];
   LevelTag tag(lvl);
@@ -860,13 +1112,16 @@ void Amg::sweeps(int nSweeps, int lvl) {
         const int r0 = L.colourStart[c], cnt = L.colourStart[c + 1] - r0;
         if (L.xZero) parallelFor(cnt, GsFirstColourZeroRows{r0, L.diag.p, L.b.p, L.x.p});
         else parallelFor(cnt, GsRows{r0, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p});
+        exchange(L, L.x.p);  // the other ranks' next colour reads these rows (MultiField::sync)
         L.xZero = false;
         lastColour = c;
       }
     } else {
       // two Jacobi passes per sweep (F/AMG.cpp:59-63), ping-pong through r
       parallelFor(L.n, JacobiRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p});
+      exchange(L, L.r.p);
       parallelFor(L.n, JacobiRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.r.p, L.x.p});
+      exchange(L, L.x.p);
       L.xZero = false;
     }
     L.rValid = false;
@@ -884,6 +1139,7 @@ double Amg::residualNorm(int lvl) {
   Level& L = *levels[lvl];
   LevelTag tag(lvl);
   reduceRows<1>(L.n, ResidualRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p}, scalars.p);
+  if (multi) commAllreduceSum(scalars.p, 1);  // MultiFieldReduction::reduceSum
   L.rValid = true;
   double v;
   copyD2H(&v, scalars.p, sizeof(double));
@@ -893,6 +1149,7 @@ double Amg::residualNorm(int lvl) {
 void Amg::cycle(int cycleType, int lvl) {
   Level& L = *levels[lvl];
   if (lvl == tailStart && cycleType == FVMGPU_CYCLE_V && L.xZero) { runTail(); return; }
+  if (lvl == mergedLevel) { cycleMerged(cycleType, lvl); return; }
   sweeps(opts.nPreSweeps, lvl);
   if (lvl + 1 < (int)levels.size()) {
     Level& C = *levels[lvl + 1];
@@ -903,12 +1160,14 @@ void Amg::cycle(int cycleType, int lvl) {
       src = L.r.p;
     }
     { LevelTag tag(lvl); parallelFor(C.n, InjectRows{L.memOff.p, L.mem.p, src, C.b.p, C.x.p}); }
+    if (C.nGhost) devMemset(C.x.p + C.n, 0, (size_t)C.nGhost * sizeof(double));
     C.xZero = true;
     C.rValid = false;
     cycle(cycleType, lvl + 1);
     if (cycleType == FVMGPU_CYCLE_W) cycle(FVMGPU_CYCLE_W, lvl + 1);
     else if (cycleType == FVMGPU_CYCLE_F) cycle(FVMGPU_CYCLE_V, lvl + 1);
     { LevelTag tag(lvl); parallelFor(L.n, CorrectRows{L.ci.p, C.x.p, L.x.p}); }
+    exchange(L, L.x.p);
     L.xZero = false;
     L.rValid = false;
   }
@@ -918,8 +1177,17 @@ void Amg::cycle(int cycleType, int lvl) {
 void Amg::loadSystem(System* sys, const double* b_d, const double* x_d) {
   Level& L0 = *levels[0];
   parallelFor(L0.n, PermGatherKernel{perm0.p, b_d, L0.b.p});
-  if (x_d) { parallelFor(L0.n, PermGatherKernel{perm0.p, x_d, L0.x.p}); L0.xZero = false; }
-  else { L0.x.zero(); L0.xZero = true; }
+  if (x_d) {
+    parallelFor(L0.n, PermGatherKernel{perm0.p, x_d, L0.x.p});
+    if (L0.nGhost) {  // ghost columns keep their cell index: same layout behind the own rows
+      copyD2D(L0.x.p + L0.n, x_d + L0.n, (size_t)L0.nGhost * sizeof(double));
+      exchange(L0, L0.x.p);
+    }
+    L0.xZero = false;
+  } else {
+    L0.x.zero();
+    L0.xZero = true;
+  }
   L0.rValid = false;
   (void)sys;
 }
@@ -927,6 +1195,8 @@ void Amg::loadSystem(System* sys, const double* b_d, const double* x_d) {
 void Amg::storeDelta(double* delta_d) {
   Level& L0 = *levels[0];
   parallelFor(L0.n, PermScatterKernel{perm0.p, L0.x.p, delta_d});
+  // ghosts synced, as AMG::solve leaves them (F/AMG.cpp:279)
+  if (L0.nGhost) copyD2D(delta_d + L0.n, L0.x.p + L0.n, (size_t)L0.nGhost * sizeof(double));
 }
 
 void Amg::ensureSetup(System* sys) {
@@ -956,6 +1226,7 @@ void Amg::cycleGraphed(int kind) {
       LevelTag tag(0);
       reduceRows<1>(L0.n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, L0.b.p, L0.x.p, L0.r.p},
                     scalars.p);
+      if (multi) commAllreduceSum(scalars.p, 1);
       L0.rValid = true;
     }
   };
@@ -1033,10 +1304,11 @@ void Amg::precondition(const double* rhsPerm, double* outPerm) {
   L0.xZero = true;
   L0.rValid = false;
   cycleGraphed(1);
-  copyD2D(outPerm, L0.x.p, (size_t)L0.n * sizeof(double));
+  copyD2D(outPerm, L0.x.p, ((size_t)L0.n + L0.nGhost) * sizeof(double));
 }
 
-// BCGStab::solve, F/BCGStab.cpp:26-170 (all vectors in level-0 numbering)
+// BCGStab::solve, F/BCGStab.cpp:26-170 (all vectors in level-0 numbering; vectors that are
+// multiplied by A carry the level's ghost slots, dots are all-reduced across ranks)
 void Amg::bcgstab(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0Out,
                   double* rnormOut, int* itersOut) {
   requireReady();
@@ -1044,14 +1316,21 @@ void Amg::bcgstab(System* sys, int nMaxIterations, double relTol, double absTol,
   history.clear();
   Level& L0 = *levels[0];
   const int n = L0.n;
-  DBuf<double> x(n), bOrig(n), r(n), rTilda(n), p(n), pHat(n), v(n), t(n);
+  const size_t ng = (size_t)L0.nGhost;
+  DBuf<double> x(n + ng), bOrig(n), r(n), rTilda(n), p(n), pHat(n + ng), v(n), t(n);
   parallelFor(n, PermGatherKernel{perm0.p, sys->b.p, bOrig.p});
   parallelFor(n, PermGatherKernel{perm0.p, sys->delta.p, x.p});
+  if (ng) {
+    copyD2D(x.p + n, sys->delta.p + n, ng * sizeof(double));
+    exchange(L0, x.p);
+  }
   auto A = [&](const double* xin) {
     return MultiplyRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, xin, nullptr};
   };
+  auto allreduce = [&](double* ptr, int cnt) { if (multi) commAllreduceSum(ptr, cnt); };
   // r = b + A x ; rNorm0
   reduceRows<1>(n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, bOrig.p, x.p, r.p}, scalars.p + 8);
+  allreduce(scalars.p + 8, 1);
   double rNorm0;
   copyD2H(&rNorm0, scalars.p + 8, sizeof(double));
   history.push_back(rNorm0);
@@ -1064,27 +1343,37 @@ void Amg::bcgstab(System* sys, int nMaxIterations, double relTol, double absTol,
     iters++;
     copyD2D(S + 1, S + 0, sizeof(double));                       // rhoPrev = rho
     reduceRows<1>(n, Dot1Rows{r.p, rTilda.p}, S + 0);            // rho = r . rTilda
+    allreduce(S + 0, 1);
     if (!haveP) { copyD2D(p.p, r.p, (size_t)n * sizeof(double)); haveP = true; }
     else parallelFor(n, BcgUpdateP{S, v.p, r.p, p.p});
-    precondition(p.p, pHat.p);                                   // pHat = M(p)
+    precondition(p.p, pHat.p);                                   // pHat = M(p), ghosts synced
     { MultiplyRows m = A(pHat.p); m.y = v.p; parallelFor(n, m); }  // v = A pHat
     copyD2D(S + 2, S + 0, sizeof(double));                       // alpha = rho / (rTilda . v)
     reduceRows<1>(n, Dot1Rows{rTilda.p, v.p}, S + 3);
+    allreduce(S + 3, 1);
     parallelFor(n, MsaxpyScalarPtr{S + 2, S + 3, pHat.p, x.p});  // x -= alpha pHat
     reduceRows<1>(n, MsaxpyScalarPtr{S + 2, S + 3, v.p, r.p}, S + 6);  // r -= alpha v ; |r|_1
+    allreduce(S + 6, 1);
     copyD2H(&rNorm, S + 6, sizeof(double));
     if (rNorm < absTol) break;
     precondition(r.p, pHat.p);                                   // sHat = M(r)
     { MultiplyRows m = A(pHat.p); m.y = t.p; parallelFor(n, m); }  // t = A sHat
     reduceRows<2>(n, Dot2Rows{t.p, r.p}, S + 4);                 // (t.r, t.t)
+    allreduce(S + 4, 2);
     parallelFor(n, MsaxpyScalarPtr{S + 4, S + 5, pHat.p, x.p});  // x -= omega sHat
     reduceRows<1>(n, MsaxpyScalarPtr{S + 4, S + 5, t.p, r.p}, S + 6);  // r -= omega t ; |r|_1
+    allreduce(S + 6, 1);
     copyD2H(&rNorm, S + 6, sizeof(double));
     history.push_back(rNorm);
     if (rNorm < absTol || rNorm / rNorm0 < relTol) break;
   }
   totalIterations += iters;
   parallelFor(n, PermScatterKernel{perm0.p, x.p, sys->delta.p});
+  if (ng) {  // leave the ghosts of delta synced
+    copyD2D(L0.x.p, x.p, (size_t)n * sizeof(double));
+    exchange(L0, L0.x.p);
+    copyD2D(sys->delta.p + n, L0.x.p + n, ng * sizeof(double));
+  }
   if (rnorm0Out) *rnorm0Out = rNorm0;
   if (rnormOut) *rnormOut = rNorm;
   if (itersOut) *itersOut = iters;

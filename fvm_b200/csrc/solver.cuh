@@ -22,6 +22,13 @@ struct Level {
   DBuf<int> memOff, mem;     // coarse row -> its fine rows (ascending)
   bool xZero = false;        // x is known to be identically zero
   bool rValid = false;       // r holds b + A x for the current x
+  // multi-GPU: x and r carry nGhost extra slots (columns >= n of the matrix) filled by the halo
+  // exchange with the ranks that own those rows (the reference: MultiField::sync after every
+  // sweep, F/MultiFieldMatrix.cpp:164,216,397)
+  int nGhost = 0;
+  Halo halo;
+  std::vector<int> gatherHost;   // host copy of halo.gatherIdx (x indices >= n)
+  DBuf<int> ghostCoarse;         // per ghost slot: x index in the NEXT level (>= its n), -1 = none
 };
 
 struct Amg {
@@ -43,6 +50,17 @@ struct Amg {
   void* graphExec[2] = {nullptr, nullptr};
   long long graphLaunches[2] = {0, 0};
 
+  // multi-GPU: below `mergeRows` global rows the level is all-gathered and the rest of the cycle runs
+  // replicated on every rank with the single-GPU code (the reference's LinearSystemMerger idea,
+  // F/LinearSystemMerger.cpp: gather coarse levels instead of exchanging halos of tiny levels)
+  bool multi = false;
+  int mergedLevel = -1;            // index of the distributed level that is solved replicated
+  int mergeMaxLocal = 0;           // rows per rank block in the merged numbering (padded)
+  std::unique_ptr<System> mergedSys;
+  std::unique_ptr<Amg> nested;
+  DBuf<double> mergeSend, mergeB, mergeX;
+  bool nestedLoaded = false;
+
   void setup(System* sys);   // AMG::createCoarseLevels
   void ensureSetup(System* sys);
   void cleanup();
@@ -58,6 +76,9 @@ struct Amg {
   void loadSystem(System* sys, const double* b_d, const double* x_d);
   void storeDelta(double* delta_d);
   void precondition(const double* rhsPerm, double* outPerm);
+  void buildMerged();
+  void cycleMerged(int cycleType, int lvl);
+  void exchange(Level& L, double* x);
   void buildTail();
   void runTail();
   void dropGraphs();
@@ -78,6 +99,7 @@ System* systemCreateRaw(int nSelf, int nGhost, const int* row, const int* col, c
 void systemSetField(System* s, int field, const double* host, long long n, bool fill, double value);
 void systemGetField(System* s, int field, double* host, long long n);
 void systemSetBc(System* s, int groupId, int kind, const double* p, int np, const double* perFace);
+void systemHaloExchange(System* s, int field);
 void computeGradient(System* s);
 void assemble(System* s, const fvmgpu_assemble_opts& o);
 void postSolveUpdate(System* s);

@@ -12,19 +12,13 @@
 //   reference's pairToCol map (F/CRConnectivity.cpp:729-792), which makes the face loop a
 //   row-parallel GATHER in the same summation order as the reference's face-order scatter.
 #pragma once
-#include "common.cuh"
+#include "comm.cuh"
 #include "../../include/fvmgpu.h"
 
 namespace fvmgpu {
 
 struct FaceGroup {
   int offset, count, id, kind;
-};
-
-struct HaloPeer {
-  int rank;
-  int nScatter, nGather;
-  int scatterOff, gatherOff;  // offsets into the concatenated index arrays
 };
 
 struct Mesh {
@@ -44,11 +38,9 @@ struct Mesh {
   DBuf<double4> cellGeom;  // Nt
   DBuf<double4> faceGeom;  // F
   DBuf<double> gradW;      // 3*nnz, SoA: wx[nnz], wy[nnz], wz[nnz]
-  // halo (multi-GPU): one entry per neighbouring rank
-  std::vector<HaloPeer> peers;
-  DBuf<int> scatterIdx, gatherIdx;
-  DBuf<double> sendBuf, recvBuf;
-  long long nScatterTotal = 0, nGatherTotal = 0;
+  // halo (multi-GPU): StorageSite scatter/gather maps per neighbouring rank (F/StorageSite.h:58-84)
+  Halo halo;
+  std::vector<int> haloScatterHost, haloGatherHost;  // host copies (the AMG setup derives coarse maps from them)
 };
 
 // per boundary group GenericBCS entry, staged to shared memory by the assembly kernel
@@ -83,6 +75,7 @@ struct System {
   DBuf<BcEntry> bcsDev;
   bool bcsDirty = true;
   unsigned long long version = 0;  // bumped by every assemble (AMG rebuilds its hierarchy)
+  bool noHalo = false;             // replicated (merged coarse) system: solved without communication
 };
 
 }  // namespace fvmgpu

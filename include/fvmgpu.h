@@ -199,10 +199,22 @@ int fvmgpu_bcgstab_solve(fvmgpu_solver_t precond, fvmgpu_system_t sys, int nMaxI
  * eliminated boundary rows, solve the boundary-flux rows, x += delta, flux += dflux */
 int fvmgpu_post_solve_update(fvmgpu_system_t sys);
 
-/* ---- multi-GPU plumbing (one process per GPU; NCCL resolved at run time with dlopen) ---- */
+/* ---- multi-GPU (one process per GPU, one mesh part per GPU; NCCL resolved at run time with dlopen)
+ * The reference's MPI layer maps as follows (all stream ordered, no host staging):
+ *   MultiField::sync / Field::syncLocal  (Isend/Irecv of packed ghosts, F/MultiField.cpp:488-551,
+ *       F/Field.cpp:333-394)                    -> pack kernel + grouped ncclSend/ncclRecv + unpack kernel
+ *   MultiFieldReduction::reduceSum (Allreduce SUM, F/MultiFieldReduction.cpp:213-225) -> ncclAllReduce
+ *   LinearSystemMerger (coarse levels gathered below a size threshold, F/LinearSystemMerger.cpp)
+ *                                               -> coarse level all-gathered and solved replicated
+ * After fvmgpu_comm_init with nranks > 1, every rank must make the same sequence of solver /
+ * assembly calls on meshes that carry halo maps (fvmgpu_mesh_set_halo). */
 int fvmgpu_comm_unique_id(void* out128);                               /* ncclGetUniqueId      */
 int fvmgpu_comm_init(int nranks, int rank, const void* uniqueId128);   /* ncclCommInitRank     */
 int fvmgpu_comm_destroy(void);
+int fvmgpu_comm_counters(long long* collectives);  /* halo exchanges + reductions issued since init */
+/* Field::syncLocal for one cell field of the system (F/Field.cpp:333-394): ghost cells of the
+ * interface groups receive the owning rank's values */
+int fvmgpu_system_halo_exchange(fvmgpu_system_t sys, int field);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,170 @@
+"""Worker of tests/test_multirank.py: one process per rank (torch.distributed, gloo, CPU).
+
+Runs the PRODUCT's multi-rank code path -- partitioned meshes, halo exchange around the assembly,
+distributed AMG / BCGStab with per-level ghost maps and the merged (replicated) coarse level -- in
+the test-only host simulator build of the same sources (tests/hostsim, FVMGPU_HOSTSIM), whose
+transport is a set of callbacks implemented here with torch.distributed. The solution of every
+rank is compared with the single-partition oracle on the global mesh (north_star: 1e-8 rel L2).
+"""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch
+import torch.distributed as dist
+
+from fvm_b200 import build, capi as X, meshgen as G, partition as P
+
+EXCH = C.CFUNCTYPE(None, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double),
+                   C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double))
+ALLR = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int)
+ALLG = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_longlong)
+
+
+def _exchange(n, peer, so, sc, send, ro, rc, recv):
+    reqs, landing = [], []
+    for i in range(n):
+        if sc[i]:
+            t = torch.from_numpy(np.ctypeslib.as_array(send, shape=(so[i] + sc[i],))[so[i]:so[i] + sc[i]].copy())
+            reqs.append(dist.isend(t, int(peer[i])))
+        if rc[i]:
+            buf = torch.empty(rc[i], dtype=torch.float64)
+            reqs.append(dist.irecv(buf, int(peer[i])))
+            landing.append((buf, ro[i], rc[i]))
+    for r in reqs:
+        r.wait()
+    for buf, o, c in landing:
+        np.ctypeslib.as_array(recv, shape=(o + c,))[o:o + c] = buf.numpy()
+
+
+def _allreduce(data, n):
+    a = np.ctypeslib.as_array(data, shape=(n,))
+    t = torch.from_numpy(a.copy())
+    dist.all_reduce(t)
+    a[:] = t.numpy()
+
+
+def _allgather(send, recv, nbytes):
+    world = dist.get_world_size()
+    s = np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_ubyte)), shape=(nbytes,)).copy()
+    outs = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(world)]
+    dist.all_gather(outs, torch.from_numpy(s))
+    r = np.ctypeslib.as_array(C.cast(recv, C.POINTER(C.c_ubyte)), shape=(nbytes * world,))
+    for k, o in enumerate(outs):
+        r[k * nbytes:(k + 1) * nbytes] = o.numpy()
+
+
+_keep = (EXCH(_exchange), ALLR(_allreduce), ALLG(_allgather))
+
+
+def make_case(name):
+    if name == "hex_slabs":
+        raw = G.hex_mesh(10, 9, 12, jitter=0.15, seed=3)
+        method = "slabs"
+    elif name == "tet_rcb":
+        raw = G.tet_mesh(6, 5, 7, jitter=0.2, seed=7)
+        method = "rcb"
+    else:
+        raise ValueError(name)
+    return raw, method
+
+
+def main():
+    case, solver_kind = sys.argv[1], sys.argv[2]
+    merge_rows = sys.argv[3] if len(sys.argv) > 3 else None
+    if merge_rows:
+        os.environ["FVMGPU_MERGE_ROWS"] = merge_rows
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lib = X.Lib(build.HOSTSIM_LIB)
+    lib.init(0)
+    lib.dll.fvmgpu_hostsim_set_comm.restype = C.c_int
+    lib.dll.fvmgpu_hostsim_set_comm(*_keep)
+    lib.comm_init(world, rank)
+
+    raw, method = make_case(case)
+    geo = G.metrics(raw)
+    part = (P.assign_slabs(raw.n_cells, world) if method == "slabs"
+            else P.assign_rcb(geo["cell_centroid"][:raw.n_cells], world))
+    loc = P.partition_mesh(raw, geo, part, rank)
+    rng = np.random.default_rng(11)
+    k_glob = np.exp(0.5 * rng.normal(size=raw.n_total))
+    bcs = {5: ("dirichlet", 300.0), 6: ("dirichlet", 400.0), 1: ("neumann", 5.0)}
+
+    # ---- the checker: single-partition oracle on the global mesh
+    from oracle import port
+    conn = dict(zip(("cc_row", "cc_col"), G.connectivity(raw)))
+    conn.update(face_cells=raw.face_cells, group_offset=raw.group_offset, group_count=raw.group_count,
+                group_id=raw.group_id, group_kind=raw.group_kind)
+    g2 = dict(geo)
+    g2["ib_type"] = np.full(raw.n_total, -1, np.int32)
+    ref = port.thermal_reference(raw, conn, g2, k_glob, bcs, x0=300.0, tol=1e-13)
+
+    # ---- this rank's part through the library
+    row, col = G.connectivity(loc)
+    dm = X.DeviceMesh(lib, loc.dim, loc.n_cells, loc.n_total, loc.face_cells, row, col, loc.group_offset,
+                      loc.group_count, loc.group_id, loc.group_kind)
+    ge = loc.geometry
+    dm.set_geometry(ge["face_area"], ge["face_area_mag"], ge["cell_centroid"], ge["cell_volume"],
+                    face_centroid=ge["face_centroid"], ib_type=np.full(loc.n_total, -1, np.int32))
+    h = loc.halo
+    dm.set_halo(h["peers"], h["scatter_off"], h["scatter_idx"], h["gather_off"], h["gather_idx"])
+    ds = X.DeviceSystem(lib, dm)
+    ds.fill_field(X.FIELD_X, 300.0)
+    ds.set_field(X.FIELD_DIFFUSIVITY, k_glob[loc.cell_global])
+    kinds = {"dirichlet": X.BC_DIRICHLET, "neumann": X.BC_NEUMANN}
+    present = set(int(i) for i in loc.group_id)
+    for gid in range(1, 7):
+        if gid in present:
+            kind, v = bcs.get(gid, ("neumann", 0.0))
+            ds.set_bc(gid, kinds[kind], [v])
+    ds.assemble()
+    a = ds.download()
+    own = loc.cell_global[:loc.n_cells]
+    scale_d, scale_b = np.abs(ref["diag"]).max(), np.abs(ref["b"]).max()
+    err_diag = float(np.abs(a["diag"][:loc.n_cells] - ref["diag"][own]).max() / scale_d)
+    err_b = float(np.abs(a["b"][:loc.n_cells] - ref["b"][own]).max() / scale_b)
+
+    o = lib.default_amg_opts()
+    o.relativeTolerance, o.nMaxIterations = 1e-13, 3000
+    amg = X.DeviceAMG(lib, o)
+    if solver_kind == "bcgstab":
+        r0, r, it = amg.bcgstab(ds, 300, 1e-13, 1e-50)
+    else:
+        if solver_kind == "group4":
+            o.coarseGroupSize = 4
+            amg.set_opts(o)
+        elif solver_kind == "jacobi_w":
+            o.smootherType, o.cycleType = X.SMOOTHER_JACOBI, X.CYCLE_W
+            amg.set_opts(o)
+        r0, r, it = amg.solve(ds)
+    levels = amg.levels()
+    ds.post_solve_update()
+    x = ds.get_field(X.FIELD_X)
+    num = float(((x[:loc.n_cells] - ref["x"][own]) ** 2).sum())
+    den = float((ref["x"][own] ** 2).sum())
+    # interface ghosts hold the owner's converged values after updateSolution's sync
+    gi = h["gather_idx"]
+    ghost_err = float(np.abs(x[gi] - ref["x"][loc.cell_global[gi]]).max()) if len(gi) else 0.0
+    t = torch.tensor([num, den])
+    dist.all_reduce(t)
+    out = dict(rank=rank, world=world, n_self=int(loc.n_cells), peers=[int(p) for p in h["peers"]],
+               err_diag=err_diag, err_b=err_b, rel_l2=float(np.sqrt(float(t[0]) / float(t[1]))), ghost_err=ghost_err,
+               r0=r0, r=r, iters=it, levels=[int(s) for s in levels["sizes"]],
+               collectives=lib.comm_collectives())
+    with open(os.path.join(os.environ["FVM_RESULT_DIR"], "rank%d.json" % rank), "w") as fh:
+        json.dump(out, fh)
+    amg.close(); ds.close(); dm.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
