@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the hot path's headline metric on B200 (contract: see the task / DESIGN.md §4).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n CELLS_PER_SIDE]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size CELLS_PER_SIDE]
 
 One STEP = one ThermalModel outer iteration on the synthetic mesh: gradient + fused assembly
 (+BCs + boundary elimination) + AMG hierarchy setup + AMG V-cycles to rel-tol 1e-8 + postSolve /
@@ -51,7 +51,10 @@ def parse():
     p.add_argument("--steps", type=int, default=3)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--n", type=int, default=0, help="cells per side of the hex mesh (default 256; 512^3/N per GPU for N>1)")
+    # NB: no option of this script may be a prefix of a torchrun option ("--n" would be swallowed by
+    # `python -m torch.distributed.run ... bench.py --n 128` as an ambiguous --nnodes/--nproc-per-node)
+    p.add_argument("--size", dest="n", type=int, default=0,
+                   help="cells per side of the per-GPU hex block (default 256: 256^3 cells per GPU)")
     p.add_argument("--ref-n", type=int, default=64, help="cells per side of the CPU sample mesh")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-profile", action="store_true")
@@ -102,19 +105,40 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- workload
-def build_case(n, lib):
-    """Unit cube, n^3 uniform hexes, k = 1, T = 400 on z = 1, T = 300 on z = 0, zero flux elsewhere,
-    T0 = 300."""
-    from fvm_b200 import meshgen as G, models as M
-    raw = G.hex_mesh(n, n, n)
+def global_dims(n, world):
+    """Weak scaling: n^3 cells per GPU; the box doubles along x, then y, then z with the GPU count
+    (8 GPUs at n = 256: the 512^3 mesh of BASELINE.json configs[3]); z-slab partition."""
+    dims = [n, n, n]
+    k, axis = world, 0
+    while k > 1:
+        if k % 2:
+            raise ValueError("--gpus must be a power of two")
+        dims[axis % 3] *= 2
+        axis += 1
+        k //= 2
+    return dims
+
+
+def build_case(n, lib, rank=0, world=1):
+    """Box of uniform cubic hexes (h = 1/n), k = 1, T = 400 on z = top, T = 300 on z = 0, zero flux
+    elsewhere, T0 = 300. world > 1: this rank's z-slab of the global mesh, built
+    directly with the reference partitioner's local numbering (fvm_b200.partition.hex_slab)."""
+    from fvm_b200 import meshgen as G, models as M, partition as P
+    if world == 1:
+        raw = G.hex_mesh(n, n, n)
+    else:
+        nx, ny, nz = global_dims(n, world)
+        raw = P.hex_slab(nx, ny, nz, rank, world, nx / n, ny / n, nz / n)
     meshes = [M.Mesh(raw)]
     geom = M.GeomFields("geom")
     M.MeshMetricsCalculatorA(geom, meshes, lib=lib).init()
     fields = M.ThermalFields("therm")
     model = M.ThermalModelA(geom, fields, meshes, lib=lib)
     bc = model.getBCMap()
-    bc[5].bcType = "SpecifiedTemperature"; bc[5]["specifiedTemperature"] = T_COLD
-    bc[6].bcType = "SpecifiedTemperature"; bc[6]["specifiedTemperature"] = T_HOT
+    if 5 in bc:
+        bc[5].bcType = "SpecifiedTemperature"; bc[5]["specifiedTemperature"] = T_COLD
+    if 6 in bc:
+        bc[6].bcType = "SpecifiedTemperature"; bc[6]["specifiedTemperature"] = T_HOT
     solver = M.AMG()
     solver.relativeTolerance = REL_TOL
     solver.nMaxIterations = 20000
@@ -158,9 +182,11 @@ def run_ours(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = capi.default_lib()
+    if world > 1:
+        capi.init_comm_from_torch(lib)   # the library's own NCCL communicator (halo exchange, all-reduce)
     n = args.n or 256
     t0 = time.time()
-    raw, mesh, fields, model, solver = build_case(n, lib)
+    raw, mesh, fields, model, solver = build_case(n, lib, rank, world)
     ls = model._systems[mesh.getID()]
     setup_s = time.time() - t0
     ncells = raw.n_cells
@@ -179,6 +205,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     l0, _, _ = lib.counters()
+    c0 = lib.comm_collectives()
     barrier()
     lib.timer_start(0)
     steps = []
@@ -187,6 +214,7 @@ def run_ours(args):
     total_ms = lib.timer_stop(0)
     barrier()
     l1, _, _ = lib.counters()
+    c1 = lib.comm_collectives()
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -223,7 +251,7 @@ def run_ours(args):
     # ---- profiled step for the roofline of the dominant kernel
     roof = None
     prof_table = None
-    if not args.no_profile and rank == 0:
+    if not args.no_profile:   # every rank takes the step (it contains collectives); rank 0 reports
         lib.profile_begin()
         ps = device_step(lib, model, mesh, ls, solver)
         recs = lib.profile_end(cap=8192)
@@ -250,12 +278,15 @@ def run_ours(args):
         "metric": METRIC, "value": ncells * world * args.steps / (total_ms * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D steady thermal diffusion, %d^3 structured hex mesh (%d cells) per GPU, k=1, "
-                               "T=400/300 on z=1/z=0, AMG (V-cycle, multicolour GS, nPre 0 / nPost 1, group 2) "
-                               "to rel 1e-8, one outer iteration per step" % (n, ncells),
+        "config": {"workload": "3D steady thermal diffusion, %s structured hex mesh (%d cells, %d per GPU), k=1, "
+                               "T=400/300 on z=top/z=0, AMG (V-cycle, multicolour GS, nPre 0 / nPost 1, group 2) "
+                               "to rel 1e-8, one outer iteration per step"
+                               % ("x".join(str(d) for d in global_dims(n, world)), ncells * world, ncells),
                    "cells_per_gpu": ncells, "l2": "inputs (>= 1.8 GB of matrix per pass) exceed the 126 MB L2; "
                                                   "L2 flushed between warm-up steps",
-                   "parallelism": "replicas" if world > 1 else "single"},
+                   "parallelism": ("z-slab domain decomposition, one part per GPU, NCCL halo exchange per colour "
+                                   "pass + all-reduced norms, coarse levels merged and solved replicated")
+                   if world > 1 else "single"},
         "time_to_converge_s": ms_per_step * 1e-3,
         "amg_cycles": cyc, "amg_levels": len(sizes), "level_sizes": sizes[:6], "level_colours": last["levels"]["colours"][:6],
         "phase_ms": {k: float(np.mean([s[k] for s in steps])) for k in ("assemble_ms", "solve_ms", "update_ms")},
@@ -269,6 +300,8 @@ def run_ours(args):
         "solution_check": {"min": float(x.min()), "max": float(x.max()), "mean": float(x[:ncells].mean())},
         "clocks": clocks, "mesh_setup_s": setup_s,
     }
+    if world > 1:
+        out["collectives_per_step"] = int((c1 - c0) / args.steps)
     if roof:
         out["roofline"] = roof
         out["kernel_profile"] = prof_table

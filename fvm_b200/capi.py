@@ -232,6 +232,22 @@ class Lib:
 _default = None
 
 
+def init_comm_from_torch(lib):
+    """One NCCL communicator for the library, bootstrapped through the process group torchrun set
+    up: rank 0 creates the unique id, torch.distributed broadcasts its 128 bytes."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if world == 1:
+        return
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    buf = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(lib.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    lib.comm_init(world, rank, bytes(buf.cpu().numpy().tobytes()))
+
+
 def default_lib():
     """The product library (fvm_b200/libfvmgpu.so), initialised on device LOCAL_RANK (or 0)."""
     global _default

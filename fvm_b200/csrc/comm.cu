@@ -23,6 +23,19 @@ struct HaloUnpackKernel {
   }
 };
 
+void Halo::detectContiguous(const std::vector<int>& gather) {
+  gatherBase = -1;
+  if (gather.empty()) return;
+  int expect = 0;
+  for (const HaloMsg& hm : msgs) {  // message order must also be slot order
+    if (hm.recvOff != expect) return;
+    expect += hm.recvCnt;
+  }
+  for (size_t k = 1; k < gather.size(); k++)
+    if (gather[k] != gather[0] + (int)k) return;
+  gatherBase = gather[0];
+}
+
 void Halo::build(const std::vector<HaloMsg>& m, const std::vector<int>& scatter, const std::vector<int>& gather) {
   msgs = m;
   nSend = (int)scatter.size();
@@ -30,6 +43,7 @@ void Halo::build(const std::vector<HaloMsg>& m, const std::vector<int>& scatter,
   scatterIdx.upload(scatter.data(), scatter.size());
   gatherIdx.upload(gather.data(), gather.size());
   widthCap = 0;
+  detectContiguous(gather);
 }
 
 void Halo::buildDev(const std::vector<HaloMsg>& m, DBuf<int>&& scatterDev, int nSendEntries, const std::vector<int>& gather) {
@@ -39,6 +53,7 @@ void Halo::buildDev(const std::vector<HaloMsg>& m, DBuf<int>&& scatterDev, int n
   scatterIdx = std::move(scatterDev);
   gatherIdx.upload(gather.data(), gather.size());
   widthCap = 0;
+  detectContiguous(gather);
 }
 
 void Halo::exchange(double* x, int width) {
@@ -49,6 +64,10 @@ void Halo::exchange(double* x, int width) {
     widthCap = width;
   }
   if (nSend) parallelFor((long long)nSend * width, HaloPackKernel{scatterIdx.p, x, sendBuf.p, width});
+  if (gatherBase >= 0) {  // ghost slots are one contiguous run in message order: receive straight into x
+    commExchange(msgs, sendBuf.p, x + (size_t)gatherBase * width, width);
+    return;
+  }
   commExchange(msgs, sendBuf.p, recvBuf.p, width);
   if (nRecv) parallelFor((long long)nRecv * width, HaloUnpackKernel{gatherIdx.p, recvBuf.p, x, width});
 }

@@ -39,12 +39,14 @@ struct Halo {
   DBuf<int> scatterIdx, gatherIdx;  // entries to send / slots to fill (indices into the vector)
   DBuf<double> sendBuf, recvBuf;
   int nSend = 0, nRecv = 0, widthCap = 0;
+  int gatherBase = -1;  // >= 0: the ghost slots are gatherBase .. gatherBase+nRecv-1 in message order -> receive in place
   bool empty() const { return msgs.empty(); }
   void build(const std::vector<HaloMsg>& m, const std::vector<int>& scatter, const std::vector<int>& gather);
   // same with the scatter list already on the device
   void buildDev(const std::vector<HaloMsg>& m, DBuf<int>&& scatterDev, int nSendEntries, const std::vector<int>& gather);
   // x is `width` doubles per entry (AoS); ghost slots of x are overwritten with the peers' values
   void exchange(double* x, int width = 1);
+  void detectContiguous(const std::vector<int>& gather);
 };
 
 #ifdef FVMGPU_HOSTSIM

@@ -796,6 +796,7 @@ void Amg::setup(System* sys) {
     agreeColours(L0);
     if (const char* e = getenv("FVMGPU_MULTI_GRAPHS")) useGraphs = atoi(e) != 0;
     else useGraphs = false;
+    if (const char* e = getenv("FVMGPU_EXCHANGE_PER_COLOUR")) exchangePerColour = atoi(e) != 0;
   }
   // rows marked as boundary inside the interior range (setDirichlet) are not coarsened
   DBuf<int> excl0(n);
@@ -804,7 +805,7 @@ void Amg::setup(System* sys) {
   int passesPerLevel = 1;
   while ((1 << passesPerLevel) < opts.coarseGroupSize) passesPerLevel++;
   if (opts.coarseGroupSize <= 1) passesPerLevel = 0;
-  int mergeRows = 32768;
+  int mergeRows = 131072;
   if (const char* e = getenv("FVMGPU_MERGE_ROWS")) mergeRows = atoi(e);
 
   for (int lvl = 0; lvl < opts.maxCoarseLevels && passesPerLevel > 0; lvl++) {
@@ -935,6 +936,7 @@ void Amg::buildMerged() {
   mergedSys->noHalo = true;
   nested.reset(new Amg);
   nested->opts = opts;
+  nested->tagBase = tagBase + mergedLevel;
   nested->setup(mergedSys.get());
   mergeSend.alloc((size_t)maxLocal); mergeSend.zero();
   mergeB.alloc((size_t)N); mergeX.alloc((size_t)N);
@@ -943,7 +945,7 @@ void Amg::buildMerged() {
 
 void Amg::cycleMerged(int cycleType, int lvl) {
   Level& C = *levels[lvl];
-  LevelTag tag(lvl);
+  LevelTag tag(tagBase + lvl);
   if (C.xZero || !nestedLoaded) {
     copyD2D(mergeSend.p, C.b.p, (size_t)C.n * sizeof(double));
     commAllgather(mergeSend.p, mergeB.p, (size_t)mergeMaxLocal * sizeof(double));
@@ -1099,7 +1101,7 @@ void Amg::runTail() {
 // ================================================================= cycle
 void Amg::sweeps(int nSweeps, int lvl) {
   Level& L = *levels[lvl];
-  LevelTag tag(lvl);
+  LevelTag tag(tagBase + lvl);
   // A colour pass only reads the OTHER colours, so repeating the pass that was just done changes
   // nothing (bit for bit): the reverse half-sweep therefore starts at the last-but-one colour, and
   // a following forward half-sweep skips colour 0.
@@ -1112,7 +1114,11 @@ void Amg::sweeps(int nSweeps, int lvl) {
         const int r0 = L.colourStart[c], cnt = L.colourStart[c + 1] - r0;
         if (L.xZero) parallelFor(cnt, GsFirstColourZeroRows{r0, L.diag.p, L.b.p, L.x.p});
         else parallelFor(cnt, GsRows{r0, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p});
-        exchange(L, L.x.p);  // the other ranks' next colour reads these rows (MultiField::sync)
+        // Ghost values: refreshed after each half-sweep (forward / reverse), i.e. neighbours' rows
+        // are lagged by at most one half-sweep -- the reference lags them by a whole sweep
+        // (forwardGS+reverseGS, then x.sync(), F/MultiFieldMatrix.cpp:125-165). Per-colour exchange
+        // (exact multicolour GS across ranks) is available with FVMGPU_EXCHANGE_PER_COLOUR=1.
+        if (exchangePerColour || pass == L.nColours - 1 || pass == 2 * L.nColours - 1) exchange(L, L.x.p);
         L.xZero = false;
         lastColour = c;
       }
@@ -1130,14 +1136,14 @@ void Amg::sweeps(int nSweeps, int lvl) {
 
 void Amg::residual(int lvl) {
   Level& L = *levels[lvl];
-  LevelTag tag(lvl);
+  LevelTag tag(tagBase + lvl);
   parallelFor(L.n, ResidualRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p});
   L.rValid = true;
 }
 
 double Amg::residualNorm(int lvl) {
   Level& L = *levels[lvl];
-  LevelTag tag(lvl);
+  LevelTag tag(tagBase + lvl);
   reduceRows<1>(L.n, ResidualRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p}, scalars.p);
   if (multi) commAllreduceSum(scalars.p, 1);  // MultiFieldReduction::reduceSum
   L.rValid = true;
@@ -1159,14 +1165,14 @@ void Amg::cycle(int cycleType, int lvl) {
       if (!L.rValid) residual(lvl);
       src = L.r.p;
     }
-    { LevelTag tag(lvl); parallelFor(C.n, InjectRows{L.memOff.p, L.mem.p, src, C.b.p, C.x.p}); }
+    { LevelTag tag(tagBase + lvl); parallelFor(C.n, InjectRows{L.memOff.p, L.mem.p, src, C.b.p, C.x.p}); }
     if (C.nGhost) devMemset(C.x.p + C.n, 0, (size_t)C.nGhost * sizeof(double));
     C.xZero = true;
     C.rValid = false;
     cycle(cycleType, lvl + 1);
     if (cycleType == FVMGPU_CYCLE_W) cycle(FVMGPU_CYCLE_W, lvl + 1);
     else if (cycleType == FVMGPU_CYCLE_F) cycle(FVMGPU_CYCLE_V, lvl + 1);
-    { LevelTag tag(lvl); parallelFor(L.n, CorrectRows{L.ci.p, C.x.p, L.x.p}); }
+    { LevelTag tag(tagBase + lvl); parallelFor(L.n, CorrectRows{L.ci.p, C.x.p, L.x.p}); }
     exchange(L, L.x.p);
     L.xZero = false;
     L.rValid = false;
@@ -1223,7 +1229,7 @@ void Amg::cycleGraphed(int kind) {
     if (kind == 1) { L0.x.zero(); L0.xZero = true; L0.rValid = false; }
     cycle(opts.cycleType, 0);
     if (kind == 0) {
-      LevelTag tag(0);
+      LevelTag tag(tagBase);
       reduceRows<1>(L0.n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, L0.b.p, L0.x.p, L0.r.p},
                     scalars.p);
       if (multi) commAllreduceSum(scalars.p, 1);

@@ -54,6 +54,8 @@ struct Amg {
   // replicated on every rank with the single-GPU code (the reference's LinearSystemMerger idea,
   // F/LinearSystemMerger.cpp: gather coarse levels instead of exchanging halos of tiny levels)
   bool multi = false;
+  int tagBase = 0;                 // profiler level tags of a nested hierarchy continue after the merged level
+  bool exchangePerColour = false;  // true: halo exchange after every colour pass; false: after every half-sweep
   int mergedLevel = -1;            // index of the distributed level that is solved replicated
   int mergeMaxLocal = 0;           // rows per rank block in the merged numbering (padded)
   std::unique_ptr<System> mergedSys;

@@ -55,6 +55,8 @@ class Mesh:
     _last_id = 0
 
     def __init__(self, raw, group_types=None):
+        if group_types is None and "group_types" in raw:   # a partitioned mesh (fvm_b200.partition)
+            group_types = raw.group_types
         self.raw = raw
         self.dim = raw.dim
         self._id = Mesh._last_id
@@ -119,7 +121,8 @@ class MeshMetricsCalculatorA:
     def init(self):
         lib = self.lib or capi.default_lib()
         for m in self.meshes:
-            mt = meshgen.metrics(m.raw)
+            # a partitioned mesh carries its geometry (interface ghosts = the remote cells' metrics)
+            mt = m.raw.geometry if "geometry" in m.raw else meshgen.metrics(m.raw)
             cells, faces = m.getCells(), m.getFaces()
             self.geom.area[faces] = mt["face_area"]
             self.geom.areaMag[faces] = mt["face_area_mag"]
@@ -138,6 +141,9 @@ def upload_mesh(lib, m, geom):
                          raw.group_offset, raw.group_count, raw.group_id, m.group_kinds())
     dm.set_geometry(geom.area[faces], geom.areaMag[faces], geom.coordinate[cells], geom.volume[cells],
                     face_centroid=geom.coordinate[faces], ib_type=geom.ibType[cells])
+    if "halo" in raw:  # StorageSite scatter/gather maps of a partitioned mesh
+        h = raw.halo
+        dm.set_halo(h["peers"], h["scatter_off"], h["scatter_idx"], h["gather_off"], h["gather_idx"])
     m.device = dm
     return dm
 

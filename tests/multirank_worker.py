@@ -83,11 +83,16 @@ def main():
         os.environ["FVMGPU_MERGE_ROWS"] = merge_rows
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    lib = X.Lib(build.HOSTSIM_LIB)
-    lib.init(0)
-    lib.dll.fvmgpu_hostsim_set_comm.restype = C.c_int
-    lib.dll.fvmgpu_hostsim_set_comm(*_keep)
-    lib.comm_init(world, rank)
+    if os.environ.get("FVM_WORKER_GPU") == "1":
+        # the product library on one B200 per rank, halo exchange over NCCL (tests/test_multigpu.py)
+        lib = X.default_lib()
+        X.init_comm_from_torch(lib)
+    else:
+        lib = X.Lib(build.HOSTSIM_LIB)
+        lib.init(0)
+        lib.dll.fvmgpu_hostsim_set_comm.restype = C.c_int
+        lib.dll.fvmgpu_hostsim_set_comm(*_keep)
+        lib.comm_init(world, rank)
 
     raw, method = make_case(case)
     geo = G.metrics(raw)
@@ -106,6 +111,46 @@ def main():
     g2 = dict(geo)
     g2["ib_type"] = np.full(raw.n_total, -1, np.int32)
     ref = port.thermal_reference(raw, conn, g2, k_glob, bcs, x0=300.0, tol=1e-13)
+
+    if solver_kind == "model":
+        # the public (reference-mirroring) Python API on this rank's mesh: same script as single rank
+        import contextlib
+        import io
+        from fvm_b200 import models as M
+        ref = port.thermal_reference(raw, conn, g2, np.ones(raw.n_total), bcs, x0=300.0, tol=1e-13)
+        mesh = M.Mesh(loc)
+        geomf = M.GeomFields("geom")
+        M.MeshMetricsCalculatorA(geomf, [mesh], lib=lib).init()
+        tf = M.ThermalFields("therm")
+        tm = M.ThermalModelA(geomf, tf, [mesh], lib=lib)
+        bcm = tm.getBCMap()
+        for gid, (kind, v) in bcs.items():
+            if gid in bcm:
+                if kind == "dirichlet":
+                    bcm[gid].bcType = "SpecifiedTemperature"; bcm[gid]["specifiedTemperature"] = v
+                else:
+                    bcm[gid].bcType = "SpecifiedHeatFlux"; bcm[gid]["specifiedHeatFlux"] = v
+        sv = M.AMG()
+        sv.relativeTolerance, sv.nMaxIterations, sv.verbosity = 1e-13, 3000, 0
+        tm.getOptions().linearSolver = sv
+        tm.getOptions()["initialTemperature"] = 300.0
+        tm.init()
+        with contextlib.redirect_stdout(io.StringIO()):
+            tm.advance(1)
+        x = tf.temperature[mesh.getCells()]
+        own = loc.cell_global[:loc.n_cells]
+        t = torch.tensor([float(((x[:loc.n_cells] - ref["x"][own]) ** 2).sum()), float((ref["x"][own] ** 2).sum())])
+        dist.all_reduce(t)
+        gi = loc.halo["gather_idx"]
+        out = dict(rank=rank, world=world, n_self=int(loc.n_cells), peers=[int(p) for p in loc.halo["peers"]],
+                   err_diag=0.0, err_b=0.0, rel_l2=float(np.sqrt(float(t[0]) / float(t[1]))),
+                   ghost_err=float(np.abs(x[gi] - ref["x"][loc.cell_global[gi]]).max()), r0=1.0, r=0.0,
+                   iters=int(sv.lastIterations), levels=[], collectives=lib.comm_collectives())
+        with open(os.path.join(os.environ["FVM_RESULT_DIR"], "rank%d.json" % rank), "w") as fh:
+            json.dump(out, fh)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
 
     # ---- this rank's part through the library
     row, col = G.connectivity(loc)

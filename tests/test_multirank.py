@@ -22,17 +22,19 @@ def _free_port():
     return p
 
 
-def run_world(world, case, solver, merge_rows=None):
+def run_world(world, case, solver, merge_rows=None, extra_env=None):
     from fvm_b200 import build
-    build.build_hostsim()
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=True)
+    if os.environ.get("FVM_WORKER_GPU") != "1":
+        build.build_hostsim()
+    if not os.path.exists(os.path.join(ROOT, "oracle", "libfvmoracle.so")):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"], check=True)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(ROOT, "tests", "multirank_worker.py"), case, solver]
     if merge_rows is not None:
         cmd.append(str(merge_rows))
     with tempfile.TemporaryDirectory() as tmp:
-        env = dict(os.environ, OMP_NUM_THREADS="1", FVM_RESULT_DIR=tmp)
+        env = dict(os.environ, OMP_NUM_THREADS="1", FVM_RESULT_DIR=tmp, **(extra_env or {}))
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
         assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
         res = [json.load(open(os.path.join(tmp, "rank%d.json" % k))) for k in range(world)]
@@ -67,4 +69,18 @@ def test_three_ranks_with_a_middle_part():
 def test_merge_everything_at_level_one():
     """A merge threshold above the level-1 size: only level 0 is distributed."""
     res = run_world(2, "tet_rcb", "amg", 100000)
+    check(res)
+
+
+def test_thermal_model_api_on_partitioned_meshes():
+    """fvm_b200.models.ThermalModelA.advance on each rank's mesh (the reference's parallel scripts,
+    T/THERMAL_MATRIX/testThermalParallel.py, run the same model code on every rank)."""
+    res = run_world(2, "tet_rcb", "model", 200)
+    check(res)
+
+
+def test_exchange_after_every_colour_pass():
+    """FVMGPU_EXCHANGE_PER_COLOUR=1: exact multicolour Gauss-Seidel across ranks (default: ghosts lag
+    by half a sweep; the reference lags them by a whole sweep)."""
+    res = run_world(2, "hex_slabs", "amg", 64, extra_env={"FVMGPU_EXCHANGE_PER_COLOUR": "1"})
     check(res)
