@@ -40,6 +40,13 @@ class AmgOpts(C.Structure):
                 ("cycleType", C.c_int), ("smootherType", C.c_int)]
 
 
+class FlowOpts(C.Structure):
+    """fvmgpu_flow_opts"""
+
+    _fields_ = [("momentumURF", C.c_double), ("pressureURF", C.c_double), ("transient", C.c_int),
+                ("time_order", C.c_int), ("dt", C.c_double), ("correctVelocity", C.c_int)]
+
+
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 _vp = C.c_void_p
@@ -95,6 +102,20 @@ SIGNATURES = {
     "fvmgpu_bcgstab_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "fvmgpu_post_solve_update": (C.c_int, [_vp]),
+    "fvmgpu_flow_create": (C.c_int, [C.POINTER(_vp), _vp]),
+    "fvmgpu_flow_destroy": (C.c_int, [_vp]),
+    "fvmgpu_flow_set_field": (C.c_int, [_vp, C.c_int, _dp, C.c_longlong]),
+    "fvmgpu_flow_fill_field": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "fvmgpu_flow_get_field": (C.c_int, [_vp, C.c_int, _dp, C.c_longlong]),
+    "fvmgpu_flow_set_bc": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int]),
+    "fvmgpu_flow_init": (C.c_int, [_vp]),
+    "fvmgpu_flow_assemble_momentum": (C.c_int, [_vp, C.POINTER(FlowOpts)]),
+    "fvmgpu_flow_download_momentum": (C.c_int, [_vp, _dp, _dp, _dp]),
+    "fvmgpu_flow_solve_momentum": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_double, C.c_double, _dp, _ip]),
+    "fvmgpu_flow_assemble_continuity": (C.c_int, [_vp, C.POINTER(FlowOpts)]),
+    "fvmgpu_flow_download_continuity": (C.c_int, [_vp, _dp, _dp, _dp, _ipn]),
+    "fvmgpu_flow_solve_continuity": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_double, C.c_double,
+                                               C.POINTER(FlowOpts), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "fvmgpu_comm_unique_id": (C.c_int, [C.c_char_p]),
     "fvmgpu_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p]),
     "fvmgpu_comm_destroy": (C.c_int, []),
@@ -227,6 +248,90 @@ class Lib:
         o = AmgOpts()
         self.dll.fvmgpu_amg_default_opts(C.byref(o))
         return o
+
+
+(FLOW_VELOCITY, FLOW_PRESSURE, FLOW_DENSITY, FLOW_VISCOSITY, FLOW_MASS_FLUX, FLOW_FACE_PRESSURE,
+ FLOW_PRESSURE_GRADIENT, FLOW_VELOCITY_GRADIENT, FLOW_CONT_RESID, FLOW_MOM_AP, FLOW_PREV_VELOCITY,
+ FLOW_VELOCITY_N1, FLOW_VELOCITY_N2) = range(13)
+FLOWBC_NOSLIP_WALL = 0
+_FLOW_WIDTH = {FLOW_VELOCITY: 3, FLOW_PRESSURE_GRADIENT: 3, FLOW_VELOCITY_GRADIENT: 9, FLOW_MOM_AP: 3,
+               FLOW_PREV_VELOCITY: 3, FLOW_VELOCITY_N1: 3, FLOW_VELOCITY_N2: 3}
+_FLOW_FACE = (FLOW_MASS_FLUX, FLOW_FACE_PRESSURE)
+
+
+class DeviceFlow:
+    """Device mirror of FlowFields + the momentum / pressure-correction systems of one mesh."""
+
+    def __init__(self, lib, mesh):
+        self.lib, self.mesh = lib, mesh
+        self.h = _vp()
+        lib.call("fvmgpu_flow_create", C.byref(self.h), mesh.h)
+
+    def _len(self, field):
+        base = self.mesh.n_faces if field in _FLOW_FACE else self.mesh.n_total
+        return base * _FLOW_WIDTH.get(field, 1)
+
+    def set_field(self, field, values):
+        a = _f64(values).reshape(-1)
+        self.lib.call("fvmgpu_flow_set_field", self.h, int(field), a, a.size)
+
+    def fill_field(self, field, value):
+        self.lib.call("fvmgpu_flow_fill_field", self.h, int(field), float(value))
+
+    def get_field(self, field):
+        out = np.zeros(self._len(field))
+        self.lib.call("fvmgpu_flow_get_field", self.h, int(field), out, out.size)
+        w = _FLOW_WIDTH.get(field, 1)
+        return out.reshape(-1, w) if w > 1 else out
+
+    def set_bc(self, group_id, kind, params):
+        p = _f64(list(params) + [0.0] * (4 - len(params)))
+        self.lib.call("fvmgpu_flow_set_bc", self.h, int(group_id), int(kind), p, 4)
+
+    def init(self):
+        self.lib.call("fvmgpu_flow_init", self.h)
+
+    @staticmethod
+    def opts(momentumURF=0.7, pressureURF=0.3, transient=0, time_order=1, dt=0.1, correctVelocity=1):
+        return FlowOpts(momentumURF, pressureURF, int(transient), int(time_order), dt, int(correctVelocity))
+
+    def assemble_momentum(self, o):
+        self.lib.call("fvmgpu_flow_assemble_momentum", self.h, C.byref(o))
+
+    def download_momentum(self):
+        nt, nnz = self.mesh.n_total, self.mesh.nnz
+        d, off, b = np.zeros(3 * nt), np.zeros(max(nnz, 1)), np.zeros(3 * nt)
+        self.lib.call("fvmgpu_flow_download_momentum", self.h, d, off, b)
+        return dict(diag=d.reshape(-1, 3), offdiag=off[:nnz], b=b.reshape(-1, 3))
+
+    def solve_momentum(self, amg, bcgstab=None):
+        """bcgstab: None or (nMaxIterations, relTol, absTol) of a BCGStab wrapped around `amg`."""
+        r0, it = np.zeros(3), np.zeros(3, np.int32)
+        b = bcgstab or (0, 0.0, 0.0)
+        self.lib.call("fvmgpu_flow_solve_momentum", self.h, amg.h, 1 if bcgstab else 0, int(b[0]), float(b[1]),
+                      float(b[2]), r0, it)
+        return r0, it
+
+    def assemble_continuity(self, o):
+        self.lib.call("fvmgpu_flow_assemble_continuity", self.h, C.byref(o))
+
+    def download_continuity(self):
+        nt, nnz = self.mesh.n_total, self.mesh.nnz
+        d, off, b, isb = np.zeros(nt), np.zeros(max(nnz, 1)), np.zeros(nt), np.zeros(nt, np.int32)
+        self.lib.call("fvmgpu_flow_download_continuity", self.h, d, off, b, isb.ctypes.data_as(C.c_void_p))
+        return dict(diag=d, offdiag=off[:nnz], b=b, is_boundary=isb)
+
+    def solve_continuity(self, amg, o, bcgstab=None):
+        r0, it = C.c_double(0), C.c_int(0)
+        b = bcgstab or (0, 0.0, 0.0)
+        self.lib.call("fvmgpu_flow_solve_continuity", self.h, amg.h, 1 if bcgstab else 0, int(b[0]), float(b[1]),
+                      float(b[2]), C.byref(o), C.byref(r0), C.byref(it))
+        return r0.value, it.value
+
+    def close(self):
+        if self.h:
+            self.lib.call("fvmgpu_flow_destroy", self.h)
+            self.h = None
 
 
 _default = None

@@ -25,6 +25,7 @@ static thread_local std::string g_lastError;
 static Mesh* M(fvmgpu_mesh_t h) { if (!h) fail("null mesh handle"); return reinterpret_cast<Mesh*>(h); }
 static System* S(fvmgpu_system_t h) { if (!h) fail("null system handle"); return reinterpret_cast<System*>(h); }
 static Amg* A(fvmgpu_solver_t h) { if (!h) fail("null solver handle"); return reinterpret_cast<Amg*>(h); }
+static Flow* FL(fvmgpu_flow_t h) { if (!h) fail("null flow handle"); return reinterpret_cast<Flow*>(h); }
 
 extern "C" {
 
@@ -384,6 +385,82 @@ int fvmgpu_system_halo_exchange(fvmgpu_system_t sys, int field) {
 int fvmgpu_post_solve_update(fvmgpu_system_t sys) {
   API_BEGIN
   postSolveUpdate(S(sys));
+  API_END
+}
+
+// ---------------------------------------------------------------- FlowModel (flow.cu)
+int fvmgpu_flow_create(fvmgpu_flow_t* out, fvmgpu_mesh_t mesh) {
+  API_BEGIN
+  if (!out) fail("null output handle");
+  *out = reinterpret_cast<fvmgpu_flow_t>(flowCreate(M(mesh)));
+  API_END
+}
+int fvmgpu_flow_destroy(fvmgpu_flow_t flow) {
+  API_BEGIN
+  if (flow) flowDestroy(FL(flow));
+  API_END
+}
+int fvmgpu_flow_set_field(fvmgpu_flow_t flow, int field, const double* host, long long n) {
+  API_BEGIN
+  if (!host) fail("flow_set_field: null array");
+  flowSetField(FL(flow), field, host, n, false, 0.0);
+  API_END
+}
+int fvmgpu_flow_fill_field(fvmgpu_flow_t flow, int field, double value) {
+  API_BEGIN
+  flowSetField(FL(flow), field, nullptr, 0, true, value);
+  API_END
+}
+int fvmgpu_flow_get_field(fvmgpu_flow_t flow, int field, double* host, long long n) {
+  API_BEGIN
+  if (!host) fail("flow_get_field: null array");
+  flowGetField(FL(flow), field, host, n);
+  API_END
+}
+int fvmgpu_flow_set_bc(fvmgpu_flow_t flow, int groupId, int bcKind, const double* p, int np) {
+  API_BEGIN
+  flowSetBc(FL(flow), groupId, bcKind, p, np);
+  API_END
+}
+int fvmgpu_flow_init(fvmgpu_flow_t flow) {
+  API_BEGIN
+  flowInit(FL(flow));
+  API_END
+}
+int fvmgpu_flow_assemble_momentum(fvmgpu_flow_t flow, const fvmgpu_flow_opts* opts) {
+  API_BEGIN
+  if (!opts) fail("null options");
+  flowAssembleMomentum(FL(flow), *opts);
+  API_END
+}
+int fvmgpu_flow_download_momentum(fvmgpu_flow_t flow, double* diag3, double* offdiag, double* b3) {
+  API_BEGIN
+  flowDownloadMomentum(FL(flow), diag3, offdiag, b3);
+  API_END
+}
+int fvmgpu_flow_solve_momentum(fvmgpu_flow_t flow, fvmgpu_solver_t solver, int bcgstab, int bcgMaxIterations,
+                               double bcgRelTol, double bcgAbsTol, double* rnorm0, int* iters) {
+  API_BEGIN
+  flowSolveMomentum(FL(flow), A(solver), bcgstab, bcgMaxIterations, bcgRelTol, bcgAbsTol, rnorm0, iters);
+  API_END
+}
+int fvmgpu_flow_assemble_continuity(fvmgpu_flow_t flow, const fvmgpu_flow_opts* opts) {
+  API_BEGIN
+  if (!opts) fail("null options");
+  flowAssembleContinuity(FL(flow), *opts);
+  API_END
+}
+int fvmgpu_flow_download_continuity(fvmgpu_flow_t flow, double* diag, double* offdiag, double* b, int* isBoundary) {
+  API_BEGIN
+  flowDownloadContinuity(FL(flow), diag, offdiag, b, isBoundary);
+  API_END
+}
+int fvmgpu_flow_solve_continuity(fvmgpu_flow_t flow, fvmgpu_solver_t solver, int bcgstab, int bcgMaxIterations,
+                                 double bcgRelTol, double bcgAbsTol, const fvmgpu_flow_opts* opts, double* rnorm0,
+                                 int* iters) {
+  API_BEGIN
+  if (!opts) fail("null options");
+  flowSolveContinuity(FL(flow), A(solver), bcgstab, bcgMaxIterations, bcgRelTol, bcgAbsTol, *opts, rnorm0, iters);
   API_END
 }
 

@@ -42,7 +42,11 @@ void Halo::build(const std::vector<HaloMsg>& m, const std::vector<int>& scatter,
   nRecv = (int)gather.size();
   scatterIdx.upload(scatter.data(), scatter.size());
   gatherIdx.upload(gather.data(), gather.size());
-  widthCap = 0;
+  // staging buffers for the common width-1 exchange are allocated here, not lazily: the first
+  // exchange may happen inside a CUDA-graph capture, where an allocation would become a graph node
+  sendBuf.alloc((size_t)nSend + 1);
+  recvBuf.alloc((size_t)nRecv + 1);
+  widthCap = 1;
   detectContiguous(gather);
 }
 
@@ -52,7 +56,9 @@ void Halo::buildDev(const std::vector<HaloMsg>& m, DBuf<int>&& scatterDev, int n
   nRecv = (int)gather.size();
   scatterIdx = std::move(scatterDev);
   gatherIdx.upload(gather.data(), gather.size());
-  widthCap = 0;
+  sendBuf.alloc((size_t)nSend + 1);
+  recvBuf.alloc((size_t)nRecv + 1);
+  widthCap = 1;
   detectContiguous(gather);
 }
 

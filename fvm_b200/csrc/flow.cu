@@ -1,0 +1,771 @@
+// fvm_b200 / libfvmgpu -- FlowModel (SIMPLE) hot path on the device, FP64, sm_100a.
+//
+// Per outer iteration the reference runs (F/FlowModel_impl.h:1433-1471)
+//   solveMomentum   (:730-770)  velocity gradient, Diffusion<Vec3,DiagTensor3,T> + Convection +
+//                               MomentumPressureGradient (+TimeDerivative) + BCs + Underrelaxer,
+//                               AMG on CRMatrix<DiagTensor3,T,Vec3>, x += delta, momAp = diag
+//   solveContinuity (:1410-1430) Rhie-Chow face mass flux + pressure-correction matrix
+//                               (F/FlowModelInterior.h:8-218), fixed-flux boundaries
+//                               (F/FlowModelVelocityBC.h:11-103), net-flux redistribution and the
+//                               reference cell (:1133-1188, :906-994), AMG, then correctPressure,
+//                               correctMassFlux, correctVelocity, updateFacePressure,
+//                               computeContinuityResidual (:1263-1339)
+// Here every face loop that scatters into cells is a row-parallel GATHER over the cell's faces in
+// ascending face order (the order in which the reference's scatter reaches that cell), so all sums
+// are deterministic; loops whose outputs are per face (mass flux, pCoeff, face pressure) are
+// face-parallel. Compiled with -fmad=false like assemble.cu (same IEEE operation sequence as the
+// reference's x86-64 build).
+//
+// Scope of this round: wall-bounded flows (bcType "NoSlipWall" with a specified wall velocity, e.g.
+// the lid-driven cavity of BASELINE.json configs[2]); other FlowBC types are rejected loudly.
+// The momentum system's diagonal is a DiagonalTensor (one value per velocity component) with a
+// shared scalar off-diagonal: the three components are solved one after the other by the scalar
+// AMG on ONE hierarchy when their diagonals coincide (always the case without symmetry planes).
+#include "solver.cuh"
+
+namespace fvmgpu {
+
+struct FlowBcEntry {
+  int offset, count;
+  int kind;       // FVMGPU_FLOWBC_* or -1
+  int groupKind;
+  double p[4];    // vx, vy, vz, specifiedPressure
+};
+
+struct Flow {
+  Mesh* mesh = nullptr;
+  int nSelf = 0, nTotal = 0, nFaces = 0;
+  long long nnz = 0;
+  DBuf<double> V, Vprev, VN1, VN2;          // 3*Nt AoS
+  DBuf<double> p, pFace, rho, mu, massFlux, contResid;
+  DBuf<double> pGrad;                        // 3*Nt
+  DBuf<double> vGrad;                        // 9*Nt  [cell][direction i][component k]
+  DBuf<double> momAp;                        // 3*Nt
+  DBuf<double> mDiag, mOff, mB, mDelta;      // momentum system: diag/b/delta 3*Nt AoS, off nnz
+  DBuf<double> pCoeff;                       // per face
+  std::unique_ptr<System> comp;              // scalar system reused for each velocity component
+  std::unique_ptr<System> pp;                // pressure-correction system
+  DBuf<double> lastDiag;                     // diagonal the current momentum hierarchy was built for
+  std::vector<FlowBcEntry> bcs;
+  DBuf<FlowBcEntry> bcsDev;
+  bool bcsDirty = true;
+  bool hasMomAp = false, hasVN1 = false, hasVN2 = false;
+  int refCell = 0;
+  DBuf<double> scal;                         // device scalars: [0] netFlux, [1] volumeSum, [2..4] norms
+};
+
+// ---------------------------------------------------------------- small helpers
+struct V3 { double x, y, z; };
+FVM_DEV V3 ld3(const double* a, int i) { V3 v; v.x = a[3 * (size_t)i]; v.y = a[3 * (size_t)i + 1]; v.z = a[3 * (size_t)i + 2]; return v; }
+FVM_DEV void st3(double* a, int i, const V3& v) { a[3 * (size_t)i] = v.x; a[3 * (size_t)i + 1] = v.y; a[3 * (size_t)i + 2] = v.z; }
+FVM_DEV double dot3(const V3& a, const V3& b) {  // Vector::dot: sum over components in order (F/Vector.h)
+  double s = 0.0;
+  s += a.x * b.x; s += a.y * b.y; s += a.z * b.z;
+  return s;
+}
+FVM_DEV double harmonicAvg(double x0, double x1) {  // F/DiffusionDiscretization.h:19-27
+  const double sum = x0 + x1;
+  if (x0 + x1 != 0.0) return 2.0 * x0 * x1 / sum;
+  return sum;
+}
+
+FVM_DEV const FlowBcEntry* faceBc(const FlowBcEntry* bcs, const int* faceGroupOf, int nInteriorFaces, int f) {
+  return &bcs[faceGroupOf[f - nInteriorFaces]];
+}
+
+// ---------------------------------------------------------------- init: default mass flux
+struct FlowInitMassFluxFaces {  // FlowModel::init, F/FlowModel_impl.h:222-244, 297-312
+  int nInteriorFaces; const int* faceCells; const int* faceGroupOf; const double4* faceGeom; const double* V;
+  const double* rho; const FlowBcEntry* bcs; double* massFlux;
+  FVM_DEV void operator()(long long ff) const {
+    const int f = (int)ff;
+    const int c0 = faceCells[2 * f], c1 = faceCells[2 * f + 1];
+    const double4 fg = faceGeom[f];
+    const V3 A = {fg.x, fg.y, fg.z};
+    if (f >= nInteriorFaces) {
+      const FlowBcEntry* bc = faceBc(bcs, faceGroupOf, nInteriorFaces, f);
+      if (bc->kind == FVMGPU_FLOWBC_NOSLIP_WALL) {
+        const V3 bv = {bc->p[0], bc->p[1], bc->p[2]};
+        massFlux[f] = rho[c0] * dot3(bv, A);
+        return;
+      }
+    }
+    massFlux[f] = 0.5 * (rho[c0] * dot3(ld3(V, c0), A) + rho[c1] * dot3(ld3(V, c1), A));
+  }
+};
+
+struct ContResidRows {  // computeContinuityResidual, F/FlowModel_impl.h:1235-1261
+  const int* row; const int* entryFace; const double* massFlux; double* r;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    double s = 0.0;
+    for (int k = row[i]; k < row[i + 1]; k++) {
+      const int ef = entryFace[k];
+      const double mf = massFlux[ef >> 1];
+      if (ef & 1) s -= mf; else s += mf;
+    }
+    r[i] = s;
+  }
+};
+
+// ---------------------------------------------------------------- gradients
+// GradientModel<Vector<T,3>>::compute: g[i] += w[i] * (x_nb - x_c)   (F/GradientMatrix.h:55-76)
+FVM_DEV void velGradOf(int c, const int* row, const int* col, const double* V, const double* w, long long nnz,
+                       double* g /*9*/) {
+#pragma unroll
+  for (int q = 0; q < 9; q++) g[q] = 0.0;
+  const V3 xc = ld3(V, c);
+  for (int k = row[c]; k < row[c + 1]; k++) {
+    const V3 xn = ld3(V, col[k]);
+    const double d0 = xn.x - xc.x, d1 = xn.y - xc.y, d2 = xn.z - xc.z;
+    const double w0 = w[k], w1 = w[nnz + k], w2 = w[2 * nnz + k];
+    g[0] += w0 * d0; g[1] += w0 * d1; g[2] += w0 * d2;
+    g[3] += w1 * d0; g[4] += w1 * d1; g[5] += w1 * d2;
+    g[6] += w2 * d0; g[7] += w2 * d1; g[8] += w2 * d2;
+  }
+}
+struct VelGradRows {  // ghost cells copy their neighbour's gradient (F/GradientModel.h:550-566)
+  int nSelf; const int* row; const int* col; const double* V; const double* w; long long nnz; double* vGrad;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    int c = i;
+    if (i >= nSelf) {
+      if (row[i + 1] - row[i] != 1) { for (int q = 0; q < 9; q++) vGrad[9 * (size_t)i + q] = 0.0; return; }
+      c = col[row[i]];
+    }
+    double g[9];
+    velGradOf(c, row, col, V, w, nnz, g);
+#pragma unroll
+    for (int q = 0; q < 9; q++) vGrad[9 * (size_t)i + q] = g[q];
+  }
+};
+
+// MomentumPressureGradientDiscretization, F/MomentumPressureGradientDiscretization.h:83-135:
+// Green-Gauss gradient from the face pressures; ghost cells copy their neighbour's
+FVM_DEV V3 pressGradOf(int c, const int* row, const int* entryFace, const double4* faceGeom, const double* pFace,
+                       double vol) {
+  V3 g = {0.0, 0.0, 0.0};
+  for (int k = row[c]; k < row[c + 1]; k++) {
+    const int ef = entryFace[k];
+    const double4 fg = faceGeom[ef >> 1];
+    const double pf = (ef & 1) ? -pFace[ef >> 1] : pFace[ef >> 1];
+    g.x += fg.x * pf; g.y += fg.y * pf; g.z += fg.z * pf;
+  }
+  g.x /= vol; g.y /= vol; g.z /= vol;
+  return g;
+}
+struct PressGradRows {
+  int nSelf; const int* row; const int* col; const int* entryFace; const double4* faceGeom; const double4* cellGeom;
+  const double* pFace; double* pGrad;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    int c = i;
+    if (i >= nSelf) {
+      if (row[i + 1] - row[i] != 1) { st3(pGrad, i, V3{0, 0, 0}); return; }
+      c = col[row[i]];
+    }
+    st3(pGrad, i, pressGradOf(c, row, entryFace, faceGeom, pFace, cellGeom[c].w));
+  }
+};
+
+// ---------------------------------------------------------------- momentum assembly
+struct MomParams {
+  int nSelf, nInteriorFaces;
+  const int* row; const int* col; const int* entryFace; const int* faceGroupOf;
+  const double4* cellGeom; const double4* faceGeom;
+  const double* V; const double* vGrad; const double* mu; const double* rho; const double* massFlux;
+  const double* contResid; const double* pGrad; const double* VN1; const double* VN2;
+  const FlowBcEntry* bcs;
+  double* Vnew;   // snapshot of V after the BCs (Dirichlet ghosts hold the wall velocity) = _previousVelocity
+  double* diag; double* off; double* b; int* isBoundary;
+  double urf; int timeOrder; double dt;
+};
+
+// DiffusionDiscretization<Vec3,DiagTensor3,T> for one face seen from (c0,c1)  F/DiffusionDiscretization.h:165-209
+FVM_DEV void momDiffusionFace(const MomParams& P, const double4 fg, int c0, int c1, double& diffCoeff, V3& dFlux) {
+  const double4 g0 = P.cellGeom[c0], g1 = P.cellGeom[c1];
+  const double vol0 = g0.w, vol1 = g1.w;
+  const double ds0 = g1.x - g0.x, ds1 = g1.y - g0.y, ds2 = g1.z - g0.z;
+  double fd;
+  if (vol0 == 0.) fd = P.mu[c1];
+  else if (vol1 == 0.) fd = P.mu[c0];
+  else fd = harmonicAvg(P.mu[c0], P.mu[c1]);
+  const double diffMetric = fg.w * fg.w / (fg.x * ds0 + fg.y * ds1 + fg.z * ds2);
+  diffCoeff = fd * diffMetric;
+  const double sc0 = fd * (fg.x - ds0 * diffMetric);
+  const double sc1 = fd * (fg.y - ds1 * diffMetric);
+  const double sc2 = fd * (fg.z - ds2 * diffMetric);
+  const double vs = vol0 + vol1;
+  const double* G0 = P.vGrad + 9 * (size_t)c0;
+  const double* G1 = P.vGrad + 9 * (size_t)c1;
+  const V3 x0 = ld3(P.V, c0), x1 = ld3(P.V, c1);
+  double sec[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {  // (gradF * secondaryCoeff)[k] = sum_i gradF[i][k] * sc_i
+    const double gf0 = (G0[0 + k] * vol0 + G1[0 + k] * vol1) / vs;
+    const double gf1 = (G0[3 + k] * vol0 + G1[3 + k] * vol1) / vs;
+    const double gf2 = (G0[6 + k] * vol0 + G1[6 + k] * vol1) / vs;
+    double s = 0.0;
+    s += gf0 * sc0; s += gf1 * sc1; s += gf2 * sc2;
+    sec[k] = s;
+  }
+  dFlux.x = diffCoeff * (x1.x - x0.x) + sec[0];
+  dFlux.y = diffCoeff * (x1.y - x0.y) + sec[1];
+  dFlux.z = diffCoeff * (x1.z - x0.z) + sec[2];
+}
+
+struct MomentumRows {
+  MomParams P;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    const int r0 = P.row[i], r1 = P.row[i + 1];
+    const V3 xi = ld3(P.V, i);
+    if (i >= P.nSelf) {
+      // ghost row of a boundary face. NoSlipWall = applyDirichletBC (F/GenericBCS.h:77-115):
+      // x[c1] = wall velocity, identity correction equation.
+      V3 xnew = xi;
+      int marks = 0;
+      if (r1 - r0 == 1) {
+        const int f = P.entryFace[r0] >> 1;
+        if (f >= P.nInteriorFaces) {
+          const FlowBcEntry* bc = faceBc(P.bcs, P.faceGroupOf, P.nInteriorFaces, f);
+          if (bc->kind == FVMGPU_FLOWBC_NOSLIP_WALL) xnew = V3{bc->p[0], bc->p[1], bc->p[2]};
+        }
+        P.off[r0] = 0.0;
+      }
+      st3(P.Vnew, i, xnew);
+      st3(P.diag, i, V3{-1.0, -1.0, -1.0});
+      st3(P.b, i, V3{0.0, 0.0, 0.0});
+      P.isBoundary[i] = marks;
+      return;
+    }
+    double diag = 0.0;
+    V3 r = {0.0, 0.0, 0.0};
+    bool hasB = false;
+    // ---- DiffusionDiscretization (all faces in face order)
+    for (int k = r0; k < r1; k++) {
+      const int ef = P.entryFace[k];
+      const int f = ef >> 1, side = ef & 1;
+      if (f >= P.nInteriorFaces) hasB = true;
+      const double4 fg = P.faceGeom[f];
+      double dc; V3 df;
+      if (side == 0) { momDiffusionFace(P, fg, i, P.col[k], dc, df); r.x += df.x; r.y += df.y; r.z += df.z; }
+      else { momDiffusionFace(P, fg, P.col[k], i, dc, df); r.x -= df.x; r.y -= df.y; r.z -= df.z; }
+      P.off[k] = dc;
+      diag -= dc;
+    }
+    // ---- ConvectionDiscretization (upwind, F/ConvectionDiscretization.h:166-199)
+    for (int k = r0; k < r1; k++) {
+      const int ef = P.entryFace[k];
+      const int f = ef >> 1, side = ef & 1;
+      const double flux = P.massFlux[f];
+      const V3 xo = ld3(P.V, P.col[k]);
+      const V3 x0 = side ? xo : xi, x1 = side ? xi : xo;
+      const V3 up = (flux > 0.0) ? x0 : x1;
+      const V3 vf = {flux * up.x, flux * up.y, flux * up.z};
+      if (side == 0) {
+        if (flux > 0.0) diag -= flux; else P.off[k] -= flux;
+        r.x -= vf.x; r.y -= vf.y; r.z -= vf.z;
+      } else {
+        if (flux > 0.0) P.off[k] += flux; else diag += flux;
+        r.x += vf.x; r.y += vf.y; r.z += vf.z;
+      }
+    }
+    diag += P.contResid[i];
+    // ---- MomentumPressureGradientDiscretization :124-130
+    const double vol = P.cellGeom[i].w;
+    {
+      const V3 pg = ld3(P.pGrad, i);
+      r.x -= vol * pg.x; r.y -= vol * pg.y; r.z -= vol * pg.z;
+    }
+    // ---- TimeDerivativeDiscretization (static mesh), F/TimeDerivativeDiscretization.h:102-108,149-155
+    if (P.timeOrder == 1) {
+      const double rhoVbydT = P.rho[i] * vol / P.dt;
+      const V3 n1 = ld3(P.VN1, i);
+      r.x -= rhoVbydT * (xi.x - n1.x); r.y -= rhoVbydT * (xi.y - n1.y); r.z -= rhoVbydT * (xi.z - n1.z);
+      diag -= rhoVbydT;
+    } else if (P.timeOrder == 2) {
+      const double rhoVbydT = P.rho[i] * vol / P.dt;
+      const V3 n1 = ld3(P.VN1, i), n2 = ld3(P.VN2, i);
+      r.x -= rhoVbydT * (1.5 * xi.x - 2.0 * n1.x + 0.5 * n2.x);
+      r.y -= rhoVbydT * (1.5 * xi.y - 2.0 * n1.y + 0.5 * n2.y);
+      r.z -= rhoVbydT * (1.5 * xi.z - 2.0 * n1.z + 0.5 * n2.z);
+      diag -= rhoVbydT * 1.5;
+    }
+    // ---- BC loop (NoSlipWall -> applyDirichletBC): r[c0] += coeff01 * (bValue - x[c1]); coeff01 = 0
+    if (hasB) {
+      for (int k = r0; k < r1; k++) {
+        const int f = P.entryFace[k] >> 1;
+        if (f < P.nInteriorFaces) continue;
+        const FlowBcEntry* bc = faceBc(P.bcs, P.faceGroupOf, P.nInteriorFaces, f);
+        if (bc->kind != FVMGPU_FLOWBC_NOSLIP_WALL) continue;
+        const V3 x1 = ld3(P.V, P.col[k]);
+        const double c01 = P.off[k];
+        r.x += c01 * (bc->p[0] - x1.x); r.y += c01 * (bc->p[1] - x1.y); r.z += c01 * (bc->p[2] - x1.z);
+        P.off[k] = 0.0;
+      }
+    }
+    // ---- Underrelaxer, F/Underrelaxer.h:49-52
+    diag /= P.urf;
+    st3(P.Vnew, i, xi);
+    st3(P.diag, i, V3{diag, diag, diag});
+    st3(P.b, i, r);
+    P.isBoundary[i] = 0;
+  }
+};
+
+struct SplitComponent {  // scalar system of velocity component k
+  int k; const double* diag3; const double* b3; double* diag; double* b; double* delta;
+  FVM_DEV void operator()(long long i) const { diag[i] = diag3[3 * i + k]; b[i] = b3[3 * i + k]; delta[i] = 0.0; }
+};
+struct DiffCountRows {  // number of rows whose diagonal differs from the one the hierarchy was built for
+  const double* a; const double* b;
+  FVM_DEV void operator()(long long i, double* o) const { o[0] = (a[i] != b[i]) ? 1.0 : 0.0; }
+};
+struct AbsRows3 {  // 1-norms of the three components of an AoS vector field
+  const double* a;
+  FVM_DEV void operator()(long long i, double* o) const { o[0] = fabs(a[3 * i]); o[1] = fabs(a[3 * i + 1]); o[2] = fabs(a[3 * i + 2]); }
+};
+struct MergeComponent {  // delta3[.][k] = delta ; V[.][k] += delta  (ls.updateSolution)
+  int k; const double* delta; double* delta3; double* V;
+  FVM_DEV void operator()(long long i) const { const double d = delta[i]; delta3[3 * i + k] = d; V[3 * i + k] += d; }
+};
+struct CopyRows { const double* a; double* b; FVM_DEV void operator()(long long i) const { b[i] = a[i]; } };
+
+// ---------------------------------------------------------------- continuity
+struct ContParams {
+  int nSelf, nInteriorFaces;
+  const int* faceCells; const int* row; const int* col; const int* entryFace; const int* faceGroupOf;
+  const double4* cellGeom; const double4* faceGeom;
+  const double* V; const double* Vprev; const double* momAp; const double* p; const double* pGrad; const double* rho;
+  const FlowBcEntry* bcs;
+  double* massFlux; double* pCoeff;
+  double urf;
+};
+
+// discretizeMassFluxInterior for one interior face, F/FlowModelInterior.h:68-117
+struct MassFluxFaces {
+  ContParams P;
+  FVM_DEV void operator()(long long ff) const {
+    const int f = (int)ff;
+    const int c0 = P.faceCells[2 * f], c1 = P.faceCells[2 * f + 1];
+    const double4 fg = P.faceGeom[f];
+    const V3 Af = {fg.x, fg.y, fg.z};
+    if (f >= P.nInteriorFaces) {  // fixedFluxContinuityBC, F/FlowModelVelocityBC.h:64-70
+      const FlowBcEntry* bc = faceBc(P.bcs, P.faceGroupOf, P.nInteriorFaces, f);
+      const V3 bv = {bc->p[0], bc->p[1], bc->p[2]};
+      P.massFlux[f] = P.rho[c0] * dot3(bv, Af);
+      P.pCoeff[f] = 0.0;
+      return;
+    }
+    const double4 g0 = P.cellGeom[c0], g1 = P.cellGeom[c1];
+    const V3 ds = {g1.x - g0.x, g1.y - g0.y, g1.z - g0.z};
+    const double Ads = dot3(Af, ds);
+    const double diffMetric = fg.w * fg.w / Ads;
+    const V3 a0 = ld3(P.momAp, c0), a1 = ld3(P.momAp, c1);
+    const double momApBar0 = (a0.x + a0.y + a0.z) / 3.0;
+    const double momApBar1 = (a1.x + a1.y + a1.z) / 3.0;
+    const double momApBarFace = momApBar0 + momApBar1;
+    const double oneMinusUrf = 1.0 - P.urf;
+    const double VdotA0 = dot3(ld3(P.V, c0), Af) - oneMinusUrf * dot3(ld3(P.Vprev, c0), Af);
+    const double VdotA1 = dot3(ld3(P.V, c1), Af) - oneMinusUrf * dot3(ld3(P.Vprev, c1), Af);
+    const double dpf = g0.w * dot3(ld3(P.pGrad, c0), ds) + g1.w * dot3(ld3(P.pGrad, c1), ds);
+    const double Vn = (VdotA0 * momApBar0 + VdotA1 * momApBar1 - dpf * diffMetric) / momApBarFace;
+    const double rhoF = 0.5 * (P.rho[c0] + P.rho[c1]);
+    const double aByMomAp = Af.x * Af.x / (a0.x + a1.x) + Af.y * Af.y / (a0.y + a1.y) + Af.z * Af.z / (a0.z + a1.z);
+    const double pCoeff = rhoF * aByMomAp * (g0.w + g1.w) / Ads;
+    P.massFlux[f] = rhoF * Vn - pCoeff * (P.p[c0] - P.p[c1]) + (1 - P.urf) * P.massFlux[f];
+    P.pCoeff[f] = pCoeff;
+  }
+};
+
+struct BoundaryFluxSum {  // netFlux over the fixed-flux boundary faces; volume of the interior cells
+  int nInteriorFaces; const double* massFlux;
+  FVM_DEV void operator()(long long k, double* o) const { o[0] = massFlux[nInteriorFaces + k]; }
+};
+struct VolumeSum { const double4* cellGeom; FVM_DEV void operator()(long long i, double* o) const { o[0] = cellGeom[i].w; } };
+
+struct ContinuityRows {  // pressure-correction matrix rows, F/FlowModelInterior.h:105-117 + BCs + :1144-1188
+  ContParams P;
+  const double* scal;  // [0] netFlux, [1] volumeSum
+  int useReferencePressure, refCell;
+  double* diag; double* off; double* b; int* isBoundary;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    const int r0 = P.row[i], r1 = P.row[i + 1];
+    if (i >= P.nSelf) {
+      // fixedFluxContinuityBC on the ghost: ppDiag = -1, r = 0, coeff10 = 1, setBoundary
+      for (int k = r0; k < r1; k++) off[k] = 1.0;
+      diag[i] = -1.0;
+      b[i] = 0.0;
+      isBoundary[i] = 1;
+      return;
+    }
+    double d = 0.0, r = 0.0;
+    for (int k = r0; k < r1; k++) {
+      const int ef = P.entryFace[k];
+      const int f = ef >> 1;
+      const double mf = P.massFlux[f];
+      if (f < P.nInteriorFaces) {
+        const double pc = P.pCoeff[f];
+        if (ef & 1) r += mf; else r -= mf;
+        off[k] = -pc;
+        d += pc;
+      } else {
+        r -= mf;       // this row is c0 of the boundary face
+        off[k] = 0.0;  // coeff01 = 0
+      }
+    }
+    if (useReferencePressure) {
+      r += (scal[0] / scal[1]) * P.cellGeom[i].w;
+      if (i == refCell) {  // setDirichlet, F/FlowModel_impl.h:970-975
+        d = -1.0;
+        r = 0.0;
+        for (int k = r0; k < r1; k++) off[k] = 0.0;
+      }
+    }
+    diag[i] = d;
+    b[i] = r;
+    isBoundary[i] = 0;
+  }
+};
+
+// ---- after the pressure-correction solve
+struct PpGhostRows {  // CRMatrix::solveBoundary for the marked ghost rows, F/CRMatrix.h:433-454
+  int nSelf; const int* row; const int* col; const double* diag; const double* off; const double* b; double* pp;
+  FVM_DEV void operator()(long long k) const {
+    const int i = nSelf + (int)k;
+    double sum = b[i];
+    for (int q = row[i]; q < row[i + 1]; q++) sum += off[q] * pp[col[q]];
+    pp[i] = -sum / diag[i];
+  }
+};
+struct CorrectPressureRows {  // correctPressure, F/FlowModel_impl.h:844-861
+  const double* pp; const double* refPP; double urf; double* p;
+  FVM_DEV void operator()(long long i) const { p[i] += urf * (pp[i] - (refPP ? refPP[0] : 0.0)); }
+};
+struct CorrectMassFluxFaces {  // correctMassFluxInterior, F/FlowModelInterior.h:390-399
+  const int* faceCells; const int* pairToCol; const double* off; const double* pp; double* massFlux;
+  FVM_DEV void operator()(long long ff) const {
+    const int f = (int)ff;
+    const int c0 = faceCells[2 * f], c1 = faceCells[2 * f + 1];
+    massFlux[f] -= off[pairToCol[2 * f]] * pp[c1] - off[pairToCol[2 * f + 1]] * pp[c0];
+  }
+};
+// coefficients of the face pressure interpolation, F/FlowModelInterior.h:252-266, 335-349
+FVM_DEV void facePressureWeights(const ContParams& P, int f, int c0, int c1, double& coeff0, double& coeff1) {
+  const double4 fg = P.faceGeom[f];
+  const double4 g0 = P.cellGeom[c0], g1 = P.cellGeom[c1];
+  const V3 ds = {g1.x - g0.x, g1.y - g0.y, g1.z - g0.z};
+  const V3 Af = {fg.x, fg.y, fg.z};
+  const V3 a0 = ld3(P.momAp, c0), a1 = ld3(P.momAp, c1);
+  const double aBy0 = Af.x * Af.x / a0.x + Af.y * Af.y / a0.y + Af.z * Af.z / a0.z;
+  const double aBy1 = Af.x * Af.x / a1.x + Af.y * Af.y / a1.y + Af.z * Af.z / a1.z;
+  const double Adotes = dot3(Af, ds) / sqrt(dot3(ds, ds));
+  coeff0 = g0.w * P.rho[c0] * aBy0 / Adotes;
+  coeff1 = g1.w * P.rho[c1] * aBy1 / Adotes;
+}
+struct CorrectVelocityRows {  // correctVelocityInterior + correctVelocityBoundary as a per-cell gather
+  ContParams P; const double* pp; double* Vout;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    V3 v = ld3(P.V, i);
+    const V3 ap = ld3(P.momAp, i);
+    for (int k = P.row[i]; k < P.row[i + 1]; k++) {
+      const int ef = P.entryFace[k];
+      const int f = ef >> 1, side = ef & 1;
+      const double4 fg = P.faceGeom[f];
+      if (f < P.nInteriorFaces) {
+        const int c0 = side ? P.col[k] : i, c1 = side ? i : P.col[k];
+        double w0, w1;
+        facePressureWeights(P, f, c0, c1, w0, w1);
+        const double ppFace = (w0 * pp[c0] + w1 * pp[c1]) / (w0 + w1);
+        const V3 ppA = {ppFace * fg.x, ppFace * fg.y, ppFace * fg.z};
+        if (side == 0) { v.x += ppA.x / ap.x; v.y += ppA.y / ap.y; v.z += ppA.z / ap.z; }
+        else { v.x -= ppA.x / ap.x; v.y -= ppA.y / ap.y; v.z -= ppA.z / ap.z; }
+      } else {  // correctVelocityBoundary, F/FlowModel_impl.h:803-828
+        const double ppFace = pp[P.col[k]];
+        v.x += ppFace * fg.x / ap.x; v.y += ppFace * fg.y / ap.y; v.z += ppFace * fg.z / ap.z;
+      }
+    }
+    st3(Vout, i, v);
+  }
+};
+struct FacePressureFaces {  // updateFacePressureInterior / Boundary
+  ContParams P; double* pFace;
+  FVM_DEV void operator()(long long ff) const {
+    const int f = (int)ff;
+    const int c0 = P.faceCells[2 * f], c1 = P.faceCells[2 * f + 1];
+    if (f >= P.nInteriorFaces) { pFace[f] = P.p[c1]; return; }
+    double w0, w1;
+    facePressureWeights(P, f, c0, c1, w0, w1);
+    pFace[f] = (w0 * P.p[c0] + w1 * P.p[c1]) / (w0 + w1);
+  }
+};
+struct FillRows { double* p; double v; FVM_DEV void operator()(long long i) const { p[i] = v; } };
+
+// ================================================================= host side
+static System* makeScalarSystem(Mesh* m) {
+  std::unique_ptr<System> s(new System);
+  s->mesh = nullptr;  // solved as a stand-alone CSR system on the mesh's cellCells pattern
+  s->nSelf = m->nSelf; s->nTotal = m->nTotal; s->nnz = m->nnz;
+  s->row = m->row.p; s->col = m->col.p;
+  const size_t nt = (size_t)m->nTotal;
+  s->diag.alloc(nt); s->b.alloc(nt); s->delta.alloc(nt); s->x.alloc(nt); s->off.alloc((size_t)m->nnz);
+  s->isBoundary.alloc(nt);
+  s->diag.zero(); s->b.zero(); s->delta.zero(); s->x.zero(); s->off.zero(); s->isBoundary.zero();
+  s->version = 1;
+  return s.release();
+}
+
+Flow* flowCreate(Mesh* m) {
+  requireReady();
+  if (!m->hasGeometry) fail("flow: mesh geometry not set (fvmgpu_mesh_set_geometry)");
+  if (commActive()) fail("flow: the FlowModel path is single-GPU in this release");
+  std::unique_ptr<Flow> F(new Flow);
+  F->mesh = m;
+  F->nSelf = m->nSelf; F->nTotal = m->nTotal; F->nFaces = m->nFaces; F->nnz = m->nnz;
+  const size_t nt = (size_t)m->nTotal, nf = (size_t)m->nFaces;
+  F->V.alloc(3 * nt); F->Vprev.alloc(3 * nt); F->p.alloc(nt); F->pFace.alloc(nf); F->rho.alloc(nt); F->mu.alloc(nt);
+  F->massFlux.alloc(nf); F->contResid.alloc(nt); F->pGrad.alloc(3 * nt); F->vGrad.alloc(9 * nt); F->momAp.alloc(3 * nt);
+  F->mDiag.alloc(3 * nt); F->mOff.alloc((size_t)m->nnz); F->mB.alloc(3 * nt); F->mDelta.alloc(3 * nt);
+  F->pCoeff.alloc(nf);
+  F->V.zero(); F->Vprev.zero(); F->p.zero(); F->pFace.zero(); F->massFlux.zero(); F->contResid.zero();
+  F->pGrad.zero(); F->vGrad.zero(); F->momAp.zero(); F->mDiag.zero(); F->mOff.zero(); F->mB.zero(); F->mDelta.zero();
+  F->pCoeff.zero();
+  parallelFor((long long)nt, FillRows{F->rho.p, 1.0});
+  parallelFor((long long)nt, FillRows{F->mu.p, 1e-3});
+  F->comp.reset(makeScalarSystem(m));
+  F->pp.reset(makeScalarSystem(m));
+  F->lastDiag.alloc(nt);
+  F->scal.alloc(16);
+  F->scal.zero();
+  for (const FaceGroup& g : m->groups) {
+    FlowBcEntry e;
+    e.offset = g.offset; e.count = g.count; e.kind = -1; e.groupKind = g.kind;
+    e.p[0] = e.p[1] = e.p[2] = e.p[3] = 0.0;
+    F->bcs.push_back(e);
+  }
+  streamSync();
+  return F.release();
+}
+
+static DBuf<double>* flowField(Flow* F, int field, size_t& len) {
+  const size_t nt = (size_t)F->nTotal, nf = (size_t)F->nFaces;
+  switch (field) {
+    case FVMGPU_FLOW_VELOCITY: len = 3 * nt; return &F->V;
+    case FVMGPU_FLOW_PRESSURE: len = nt; return &F->p;
+    case FVMGPU_FLOW_DENSITY: len = nt; return &F->rho;
+    case FVMGPU_FLOW_VISCOSITY: len = nt; return &F->mu;
+    case FVMGPU_FLOW_MASS_FLUX: len = nf; return &F->massFlux;
+    case FVMGPU_FLOW_FACE_PRESSURE: len = nf; return &F->pFace;
+    case FVMGPU_FLOW_PRESSURE_GRADIENT: len = 3 * nt; return &F->pGrad;
+    case FVMGPU_FLOW_VELOCITY_GRADIENT: len = 9 * nt; return &F->vGrad;
+    case FVMGPU_FLOW_CONT_RESID: len = nt; return &F->contResid;
+    case FVMGPU_FLOW_MOM_AP: len = 3 * nt; return &F->momAp;
+    case FVMGPU_FLOW_PREV_VELOCITY: len = 3 * nt; return &F->Vprev;
+    case FVMGPU_FLOW_VELOCITY_N1: len = 3 * nt; return &F->VN1;
+    case FVMGPU_FLOW_VELOCITY_N2: len = 3 * nt; return &F->VN2;
+    default: return nullptr;
+  }
+}
+void flowSetField(Flow* F, int field, const double* host, long long n, bool fill, double value) {
+  requireReady();
+  size_t len = 0;
+  DBuf<double>* buf = flowField(F, field, len);
+  if (!buf) fail("flow_set_field: unknown field %d", field);
+  if (!fill && (size_t)n != len) fail("flow_set_field: field %d expects %zu values, got %lld", field, len, n);
+  if (buf->n < len) buf->alloc(len);
+  if (fill) parallelFor((long long)len, FillRows{buf->p, value});
+  else buf->upload(host, len);
+  if (field == FVMGPU_FLOW_MOM_AP) F->hasMomAp = true;
+  if (field == FVMGPU_FLOW_VELOCITY_N1) F->hasVN1 = true;
+  if (field == FVMGPU_FLOW_VELOCITY_N2) F->hasVN2 = true;
+}
+void flowGetField(Flow* F, int field, double* host, long long n) {
+  requireReady();
+  size_t len = 0;
+  DBuf<double>* buf = flowField(F, field, len);
+  if (!buf || !buf->p) fail("flow_get_field: field %d not available", field);
+  if ((size_t)n != len) fail("flow_get_field: field %d has %zu values, asked for %lld", field, len, n);
+  buf->download(host, len);
+}
+void flowSetBc(Flow* F, int groupId, int kind, const double* p, int np) {
+  requireReady();
+  if (kind != FVMGPU_FLOWBC_NOSLIP_WALL) fail("flow_set_bc: only NoSlipWall boundaries are supported in this release (kind %d)", kind);
+  for (size_t g = 0; g < F->bcs.size(); g++) {
+    const FaceGroup& fg = F->mesh->groups[g];
+    if (fg.id == groupId && fg.kind != FVMGPU_GROUP_INTERIOR) {
+      FlowBcEntry& e = F->bcs[g];
+      e.kind = kind;
+      for (int i = 0; i < 4; i++) e.p[i] = (i < np && p) ? p[i] : 0.0;
+      F->bcsDirty = true;
+      return;
+    }
+  }
+  fail("flow_set_bc: no boundary face group with id %d", groupId);
+}
+static void flowSyncBcs(Flow* F) {
+  if (!F->bcsDirty) return;
+  for (size_t g = 1; g < F->bcs.size(); g++)
+    if (F->bcs[g].kind < 0) fail("flow: boundary group %d has no boundary condition", F->mesh->groups[g].id);
+  F->bcsDev.upload(F->bcs.data(), F->bcs.size());
+  F->bcsDirty = false;
+}
+static ContParams contParams(Flow* F, double urf) {
+  Mesh* m = F->mesh;
+  ContParams P;
+  P.nSelf = m->nSelf; P.nInteriorFaces = m->nInteriorFaces;
+  P.faceCells = m->faceCells.p; P.row = m->row.p; P.col = m->col.p; P.entryFace = m->entryFace.p;
+  P.faceGroupOf = m->faceGroupOf.p; P.cellGeom = m->cellGeom.p; P.faceGeom = m->faceGeom.p;
+  P.V = F->V.p; P.Vprev = F->Vprev.p; P.momAp = F->momAp.p; P.p = F->p.p; P.pGrad = F->pGrad.p; P.rho = F->rho.p;
+  P.bcs = F->bcsDev.p; P.massFlux = F->massFlux.p; P.pCoeff = F->pCoeff.p; P.urf = urf;
+  return P;
+}
+static void flowContinuityResidual(Flow* F) {
+  Mesh* m = F->mesh;
+  parallelFor(m->nTotal, ContResidRows{m->row.p, m->entryFace.p, F->massFlux.p, F->contResid.p});
+}
+
+// FlowModel::init: default face mass fluxes + continuity residual (F/FlowModel_impl.h:222-340)
+void flowInit(Flow* F) {
+  requireReady();
+  flowSyncBcs(F);
+  Mesh* m = F->mesh;
+  parallelFor(m->nFaces, FlowInitMassFluxFaces{m->nInteriorFaces, m->faceCells.p, m->faceGroupOf.p, m->faceGeom.p,
+                                               F->V.p, F->rho.p, F->bcsDev.p, F->massFlux.p});
+  flowContinuityResidual(F);
+  F->hasMomAp = false;
+}
+
+// initMomentumLinearization + initAssembly + linearizeMomentum + initSolve (F/FlowModel_impl.h:522-737)
+void flowAssembleMomentum(Flow* F, const fvmgpu_flow_opts& o) {
+  requireReady();
+  flowSyncBcs(F);
+  Mesh* m = F->mesh;
+  if (!(o.momentumURF > 0)) fail("flow: momentumURF must be positive");
+  if (o.transient && (!F->hasVN1 || (o.time_order > 1 && !F->hasVN2))) fail("flow: transient run needs VELOCITY_N1 (and _N2)");
+  parallelFor(m->nTotal, VelGradRows{m->nSelf, m->row.p, m->col.p, F->V.p, m->gradW.p, m->nnz, F->vGrad.p});
+  parallelFor(m->nTotal, PressGradRows{m->nSelf, m->row.p, m->col.p, m->entryFace.p, m->faceGeom.p, m->cellGeom.p,
+                                       F->pFace.p, F->pGrad.p});
+  MomParams P;
+  P.nSelf = m->nSelf; P.nInteriorFaces = m->nInteriorFaces;
+  P.row = m->row.p; P.col = m->col.p; P.entryFace = m->entryFace.p; P.faceGroupOf = m->faceGroupOf.p;
+  P.cellGeom = m->cellGeom.p; P.faceGeom = m->faceGeom.p;
+  P.V = F->V.p; P.vGrad = F->vGrad.p; P.mu = F->mu.p; P.rho = F->rho.p; P.massFlux = F->massFlux.p;
+  P.contResid = F->contResid.p; P.pGrad = F->pGrad.p; P.VN1 = F->VN1.p; P.VN2 = F->VN2.p;
+  P.bcs = F->bcsDev.p;
+  P.Vnew = F->Vprev.p;
+  P.diag = F->mDiag.p; P.off = F->mOff.p; P.b = F->mB.p; P.isBoundary = F->comp->isBoundary.p;
+  P.urf = o.momentumURF; P.timeOrder = o.transient ? o.time_order : 0; P.dt = o.dt;
+  parallelFor(m->nTotal, MomentumRows{P});
+  // x[c1] = wall velocity for the Dirichlet ghosts; Vprev is the reference's _previousVelocity snapshot
+  copyD2D(F->V.p, F->Vprev.p, 3 * (size_t)m->nTotal * sizeof(double));
+  F->mDelta.zero();
+}
+
+void flowDownloadMomentum(Flow* F, double* diag3, double* off, double* b3) {
+  requireReady();
+  if (diag3) F->mDiag.download(diag3, 3 * (size_t)F->nTotal);
+  if (off) F->mOff.download(off, (size_t)F->nnz);
+  if (b3) F->mB.download(b3, 3 * (size_t)F->nTotal);
+}
+
+// LinearSolver::solve on the momentum system + postSolve + updateSolution + momAp (F/FlowModel_impl.h:744-768).
+// useBcgstab: BCGStab preconditioned by `solver` with its own iteration limit / tolerances.
+void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, double bcgRel, double bcgAbs,
+                       double* rnorm0 /*3*/, int* iters /*3*/) {
+  requireReady();
+  Mesh* m = F->mesh;
+  const int nt = m->nTotal;
+  System* s = F->comp.get();
+  // the reference returns the 1-norm of b per component (F/AMG.cpp:235)
+  reduceRows<3>(m->nSelf, AbsRows3{F->mB.p}, F->scal.p + 2);
+  double norms[3];
+  copyD2H(norms, F->scal.p + 2, sizeof(norms));
+  copyD2D(s->off.p, F->mOff.p, (size_t)m->nnz * sizeof(double));
+  bool haveHierarchy = false;
+  for (int k = 0; k < 3; k++) {
+    parallelFor(nt, SplitComponent{k, F->mDiag.p, F->mB.p, s->diag.p, s->b.p, s->delta.p});
+    bool same = false;
+    if (haveHierarchy) {
+      reduceRows<1>(m->nSelf, DiffCountRows{s->diag.p, F->lastDiag.p}, F->scal.p + 5);
+      double nd;
+      copyD2H(&nd, F->scal.p + 5, sizeof(double));
+      same = nd == 0.0;
+    }
+    if (!same) {
+      s->version++;  // the hierarchy is rebuilt for this component's diagonal
+      copyD2D(F->lastDiag.p, s->diag.p, (size_t)nt * sizeof(double));
+      haveHierarchy = true;
+    }
+    double r0 = 0, r = 0;
+    int it = 0;
+    if (norms[k] > 0.0) {
+      if (useBcgstab) solver->bcgstab(s, bcgMaxIter, bcgRel, bcgAbs, &r0, &r, &it);
+      else solver->solve(s, &r0, &r, &it);
+    }
+    if (rnorm0) rnorm0[k] = norms[k];
+    if (iters) iters[k] = it;
+    parallelFor(nt, MergeComponent{k, s->delta.p, F->mDelta.p, F->V.p});
+  }
+  copyD2D(F->momAp.p, F->mDiag.p, 3 * (size_t)nt * sizeof(double));
+  F->hasMomAp = true;
+}
+
+// initContinuityLinearization + initAssembly + linearizeContinuity + initSolve (F/FlowModel_impl.h:998-1198,1394-1407)
+void flowAssembleContinuity(Flow* F, const fvmgpu_flow_opts& o) {
+  requireReady();
+  flowSyncBcs(F);
+  if (!F->hasMomAp) fail("flow: continuity needs the momentum coefficients (solve the momentum equations first)");
+  Mesh* m = F->mesh;
+  ContParams P = contParams(F, o.momentumURF);
+  parallelFor(m->nFaces, MassFluxFaces{P});
+  const int nb = m->nFaces - m->nInteriorFaces;
+  reduceRows<1>(nb, BoundaryFluxSum{m->nInteriorFaces, F->massFlux.p}, F->scal.p + 0);
+  reduceRows<1>(m->nSelf, VolumeSum{m->cellGeom.p}, F->scal.p + 1);
+  System* s = F->pp.get();
+  ContinuityRows K{P, F->scal.p, 1, F->refCell, s->diag.p, s->off.p, s->b.p, s->isBoundary.p};
+  parallelFor(m->nTotal, K);
+  s->delta.zero();
+  s->version++;
+}
+
+void flowDownloadContinuity(Flow* F, double* diag, double* off, double* b, int* isBoundary) {
+  requireReady();
+  System* s = F->pp.get();
+  if (diag) s->diag.download(diag, (size_t)F->nTotal);
+  if (off) s->off.download(off, (size_t)F->nnz);
+  if (b) s->b.download(b, (size_t)F->nTotal);
+  if (isBoundary) s->isBoundary.download(isBoundary, (size_t)F->nTotal);
+}
+
+// solve + postSolve + postContinuitySolve (F/FlowModel_impl.h:1410-1430, 1263-1339)
+void flowSolveContinuity(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, double bcgRel, double bcgAbs,
+                         const fvmgpu_flow_opts& o, double* rnorm0, int* iters) {
+  requireReady();
+  Mesh* m = F->mesh;
+  System* s = F->pp.get();
+  double r0 = 0, r = 0;
+  int it = 0;
+  if (useBcgstab) solver->bcgstab(s, bcgMaxIter, bcgRel, bcgAbs, &r0, &r, &it);
+  else solver->solve(s, &r0, &r, &it);
+  if (rnorm0) *rnorm0 = r0;
+  if (iters) *iters = it;
+  double* pp = s->delta.p;
+  parallelFor(m->nTotal - m->nSelf, PpGhostRows{m->nSelf, m->row.p, m->col.p, s->diag.p, s->off.p, s->b.p, pp});
+  // setReferencePP: pp of the reference cell (read on the device, no host round trip)
+  parallelFor(m->nTotal, CorrectPressureRows{pp, pp + F->refCell, o.pressureURF, F->p.p});
+  parallelFor(m->nInteriorFaces, CorrectMassFluxFaces{m->faceCells.p, m->pairToCol.p, s->off.p, pp, F->massFlux.p});
+  ContParams P = contParams(F, o.momentumURF);
+  if (o.correctVelocity) {
+    parallelFor(m->nSelf, CorrectVelocityRows{P, pp, F->V.p});  // in place: a row reads only its own velocity
+  }
+  parallelFor(m->nFaces, FacePressureFaces{P, F->pFace.p});
+  flowContinuityResidual(F);
+  F->hasMomAp = false;  // the reference discards momAp after the continuity step
+}
+
+void flowDestroy(Flow* F) { delete F; }
+
+}  // namespace fvmgpu

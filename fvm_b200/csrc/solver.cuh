@@ -106,4 +106,21 @@ void computeGradient(System* s);
 void assemble(System* s, const fvmgpu_assemble_opts& o);
 void postSolveUpdate(System* s);
 
+// flow.cu
+struct Flow;
+Flow* flowCreate(Mesh* m);
+void flowDestroy(Flow* F);
+void flowSetField(Flow* F, int field, const double* host, long long n, bool fill, double value);
+void flowGetField(Flow* F, int field, double* host, long long n);
+void flowSetBc(Flow* F, int groupId, int kind, const double* p, int np);
+void flowInit(Flow* F);
+void flowAssembleMomentum(Flow* F, const fvmgpu_flow_opts& o);
+void flowDownloadMomentum(Flow* F, double* diag3, double* off, double* b3);
+void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, double bcgRel, double bcgAbs,
+                       double* rnorm0, int* iters);
+void flowAssembleContinuity(Flow* F, const fvmgpu_flow_opts& o);
+void flowDownloadContinuity(Flow* F, double* diag, double* off, double* b, int* isBoundary);
+void flowSolveContinuity(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, double bcgRel, double bcgAbs,
+                         const fvmgpu_flow_opts& o, double* rnorm0, int* iters);
+
 }  // namespace fvmgpu

@@ -554,3 +554,281 @@ class ThermalModelA:
             if o.timeDiscretizationOrder > 1:
                 f.temperatureN2[cells][:] = f.temperatureN1[cells]
             f.temperatureN1[cells][:] = f.temperature[cells]
+
+
+# ----------------------------------------------------------------------------- FlowModel (SIMPLE)
+class FlowBC(FloatVarDict):
+    """F/FlowBC.h:9-21"""
+
+    def __init__(self):
+        super().__init__()
+        self.defineVar("specifiedXVelocity", 0.0)
+        self.defineVar("specifiedYVelocity", 0.0)
+        self.defineVar("specifiedZVelocity", 0.0)
+        self.defineVar("specifiedPressure", 0.0)
+        self.defineVar("accomodationCoefficient", 1.0)
+        self.bcType = ""
+
+
+class FlowVC(FloatVarDict):
+    """F/FlowBC.h:23-34"""
+
+    def __init__(self):
+        super().__init__()
+        self.defineVar("viscosity", 1e-3)
+        self.defineVar("density", 1.0)
+        self.defineVar("eddyviscosity", 1e-5)
+        self.defineVar("totalviscosity", 2e-3)
+        self.vcType = ""
+
+
+class FlowModelOptions(FloatVarDict):
+    """F/FlowBC.h:37-115"""
+
+    def __init__(self):
+        super().__init__()
+        for name, v in (("initialXVelocity", 0.0), ("initialYVelocity", 0.0), ("initialZVelocity", 0.0),
+                        ("initialPressure", 0.0), ("momentumURF", 0.7), ("velocityURF", 1.0),
+                        ("pressureURF", 0.3), ("timeStep", 0.1), ("operatingPressure", 101325.0),
+                        ("operatingTemperature", 300.0), ("molecularWeight", 28.966)):
+            self.defineVar(name, v)
+        self.momentumTolerance = 1e-3
+        self.continuityTolerance = 1e-3
+        self.printNormalizedResiduals = True
+        self.transient = False
+        self.correctVelocity = True
+        self.timeDiscretizationOrder = 1
+        self.momentumLinearSolver = None
+        self.pressureLinearSolver = None
+        self.coupledLinearSolver = None
+        self.incompressible = True
+        self.turbulent = False
+
+    @staticmethod
+    def _default_solver():
+        ls = AMG()
+        ls.relativeTolerance = 1e-1
+        ls.nMaxIterations = 20
+        ls.verbosity = 0
+        return ls
+
+    def getMomentumLinearSolver(self):  # F/FlowBC.h:87-99
+        if self.momentumLinearSolver is None:
+            self.momentumLinearSolver = self._default_solver()
+        return self.momentumLinearSolver
+
+    def getPressureLinearSolver(self):  # F/FlowBC.h:101-113
+        if self.pressureLinearSolver is None:
+            self.pressureLinearSolver = self._default_solver()
+        return self.pressureLinearSolver
+
+
+class FlowFields:
+    """F/FlowFields.h:15-41 (the fields the SIMPLE path reads or writes)"""
+
+    def __init__(self, base_name):
+        for n in ("velocity", "pressure", "massFlux", "velocityGradient", "pressureGradient", "momentumFlux",
+                  "viscosity", "density", "continuityResidual", "velocityN1", "velocityN2"):
+            setattr(self, n, Field(base_name + "." + n))
+
+
+def _solver_args(solver):
+    """(DeviceAMG-providing AMG mirror, bcgstab tuple or None) of a LinearSolver mirror."""
+    if isinstance(solver, BCGStab):
+        if solver.preconditioner is None:
+            raise CException("BCGStab: no preconditioner set")
+        return solver.preconditioner, (solver.nMaxIterations, solver.relativeTolerance, solver.absoluteTolerance)
+    return solver, None
+
+
+class FlowModelA:
+    """Mirror of `models_atyped_double.FlowModelA` (F/FlowModel.h:17-95, F/FlowModel.i): SIMPLE
+    iterations -- momentum assembly + solve, Rhie-Chow pressure correction assembly + solve, the
+    pressure / mass-flux / velocity corrections -- all on the device through the C ABI
+    (fvmgpu_flow_*). Boundary types of this release: "NoSlipWall" (F/FlowModel_impl.h:636-640)."""
+
+    def __init__(self, geom_fields, flow_fields, meshes, lib=None):
+        self.geom, self.fields, self.meshes, self.lib = geom_fields, flow_fields, list(meshes), lib
+        self._bcMap, self._vcMap = {}, {}
+        self._options = FlowModelOptions()
+        self._flows = {}
+        self._niters = 0
+        self._initialMomentumNorm = None
+        self._initialContinuityNorm = None
+        self.timings = []
+        for mesh in self.meshes:  # FlowModel::Impl ctor, F/FlowModel_impl.h:93-141
+            vc = FlowVC()
+            vc.vcType = "flow"
+            self._vcMap[mesh.getID()] = vc
+            for fg in mesh.getBoundaryFaceGroups():
+                bc = FlowBC()
+                self._bcMap[fg.id] = bc
+                if fg.groupType == "wall":
+                    bc.bcType = "NoSlipWall"
+                elif fg.groupType == "velocity-inlet":
+                    bc.bcType = "VelocityBoundary"
+                elif fg.groupType == "pressure-inlet" or fg.groupType == "pressure-outlet":
+                    bc.bcType = "PressureBoundary"
+                elif fg.groupType == "symmetry":
+                    bc.bcType = "Symmetry"
+                else:
+                    raise CException("FlowModel: unknown face group type " + fg.groupType)
+
+    def getBCMap(self):
+        return self._bcMap
+
+    def getVCMap(self):
+        return self._vcMap
+
+    def getOptions(self):
+        return self._options
+
+    def printBCs(self):  # F/FlowModel_impl.h:1569-1585
+        for gid, bc in self._bcMap.items():
+            print("Face Group %d:" % gid)
+            print("    bc type " + bc.bcType)
+            for k, v in bc.items():
+                print("   %s  %s" % (k, v))
+
+    def _flow_opts(self):
+        o = self._options
+        return capi.DeviceFlow.opts(float(o["momentumURF"]), float(o["pressureURF"]), int(o.transient),
+                                    int(o.timeDiscretizationOrder), float(o["timeStep"]), int(o.correctVelocity))
+
+    def init(self):  # F/FlowModel_impl.h:148-340
+        f, o = self.fields, self._options
+        for mesh in self.meshes:
+            if mesh.device is None:
+                raise CException("FlowModel.init: mesh metrics not initialised (MeshMetricsCalculatorA.init)")
+            cells, faces = mesh.getCells(), mesh.getFaces()
+            n, nf = cells.getCount(), faces.getCount()
+            vc = self._vcMap[mesh.getID()]
+            v0 = np.array([o["initialXVelocity"], o["initialYVelocity"], o["initialZVelocity"]], float)
+            f.velocity[cells] = np.tile(v0, (n, 1))
+            if o.transient:
+                f.velocityN1[cells] = f.velocity[cells].copy()
+                if o.timeDiscretizationOrder > 1:
+                    f.velocityN2[cells] = f.velocity[cells].copy()
+            f.pressure[cells] = np.full(n, float(o["initialPressure"]))
+            f.pressure[faces] = np.full(nf, float(o["initialPressure"]))
+            f.density[cells] = np.full(n, float(vc["density"]))
+            f.viscosity[cells] = np.full(n, float(vc["viscosity"]))
+            f.pressureGradient[cells] = np.zeros((n, 3))
+            f.velocityGradient[cells] = np.zeros((n, 9))
+            f.continuityResidual[cells] = np.zeros(n)
+            f.massFlux[faces] = np.zeros(nf)
+            lib = self.lib or mesh.device.lib
+            fl = capi.DeviceFlow(lib, mesh.device)
+            self._flows[mesh.getID()] = fl
+            self._upload(mesh, fl, with_flux=False)
+            fl.init()
+            f.massFlux[faces][:] = fl.get_field(capi.FLOW_MASS_FLUX)
+            f.continuityResidual[cells][:] = fl.get_field(capi.FLOW_CONT_RESID)
+        self._niters = 0
+        self._initialMomentumNorm = None
+        self._initialContinuityNorm = None
+
+    def _upload(self, mesh, fl, with_flux=True):
+        f, o = self.fields, self._options
+        cells, faces = mesh.getCells(), mesh.getFaces()
+        fl.set_field(capi.FLOW_VELOCITY, f.velocity[cells])
+        fl.set_field(capi.FLOW_PRESSURE, f.pressure[cells])
+        fl.set_field(capi.FLOW_FACE_PRESSURE, f.pressure[faces])
+        fl.set_field(capi.FLOW_DENSITY, f.density[cells])
+        fl.set_field(capi.FLOW_VISCOSITY, f.viscosity[cells])
+        if with_flux:
+            fl.set_field(capi.FLOW_MASS_FLUX, f.massFlux[faces])
+            fl.set_field(capi.FLOW_CONT_RESID, f.continuityResidual[cells])
+        if o.transient:
+            fl.set_field(capi.FLOW_VELOCITY_N1, f.velocityN1[cells])
+            if o.timeDiscretizationOrder > 1:
+                fl.set_field(capi.FLOW_VELOCITY_N2, f.velocityN2[cells])
+        for fg in mesh.getBoundaryFaceGroups():
+            bc = self._bcMap[fg.id]
+            if bc.bcType != "NoSlipWall":
+                raise CException(bc.bcType + " not implemented for FlowModel")
+            fl.set_bc(fg.id, capi.FLOWBC_NOSLIP_WALL, [float(bc["specifiedXVelocity"]), float(bc["specifiedYVelocity"]),
+                                                        float(bc["specifiedZVelocity"])])
+
+    def _download(self, mesh, fl):
+        f = self.fields
+        cells, faces = mesh.getCells(), mesh.getFaces()
+        f.velocity[cells][:] = fl.get_field(capi.FLOW_VELOCITY)
+        f.pressure[cells][:] = fl.get_field(capi.FLOW_PRESSURE)
+        f.pressure[faces][:] = fl.get_field(capi.FLOW_FACE_PRESSURE)
+        f.massFlux[faces][:] = fl.get_field(capi.FLOW_MASS_FLUX)
+        f.continuityResidual[cells][:] = fl.get_field(capi.FLOW_CONT_RESID)
+        f.pressureGradient[cells][:] = fl.get_field(capi.FLOW_PRESSURE_GRADIENT)
+        f.velocityGradient[cells][:] = fl.get_field(capi.FLOW_VELOCITY_GRADIENT)
+
+    def advance(self, niter):
+        """FlowModel::advance, F/FlowModel_impl.h:1433-1471 (one mesh per model). Returns True when
+        both normalised residuals fall below the tolerances."""
+        o = self._options
+        if len(self.meshes) != 1:
+            raise CException("FlowModelA: one mesh per model in this release")
+        mesh = self.meshes[0]
+        fl = self._flows[mesh.getID()]
+        lib = fl.lib
+        msolver, mbcg = _solver_args(o.getMomentumLinearSolver())
+        psolver, pbcg = _solver_args(o.getPressureLinearSolver())
+        mdev, pdev = msolver._device(lib), psolver._device(lib)
+        if mdev is pdev:
+            raise CException("FlowModelA: momentum and pressure solvers must be distinct objects")
+        self._upload(mesh, fl)
+        fo = self._flow_opts()
+        converged = False
+        vname, pname = self.fields.velocity.name, self.fields.pressure.name
+        for _ in range(niter):
+            t = {}
+            lib.timer_start(1)
+            fl.assemble_momentum(fo)
+            t["momentum_assemble_ms"] = lib.timer_stop(1)
+            lib.timer_start(1)
+            mnorm, mits = fl.solve_momentum(mdev, mbcg)            # solveMomentum :730-770
+            t["momentum_solve_ms"] = lib.timer_stop(1)
+            mdev.cleanup()
+            lib.timer_start(1)
+            fl.assemble_continuity(fo)
+            t["continuity_assemble_ms"] = lib.timer_stop(1)
+            lib.timer_start(1)
+            cnorm, cits = fl.solve_continuity(pdev, fo, pbcg)      # solveContinuity :1410-1430
+            t["continuity_solve_ms"] = lib.timer_stop(1)
+            pdev.cleanup()
+            t["momentum_iterations"], t["pressure_iterations"] = [int(i) for i in mits], int(cits)
+            if self._initialMomentumNorm is None:
+                self._initialMomentumNorm = mnorm.copy()
+            if self._initialContinuityNorm is None:
+                self._initialContinuityNorm = cnorm
+            if self._niters < 5:  # setMax of the first iterations' norms, :1441-1445
+                self._initialMomentumNorm = np.maximum(self._initialMomentumNorm, mnorm)
+                self._initialContinuityNorm = max(self._initialContinuityNorm, cnorm)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                mratio = np.where(self._initialMomentumNorm > 0, mnorm / self._initialMomentumNorm, 0.0)
+            cratio = cnorm / self._initialContinuityNorm if self._initialContinuityNorm > 0 else 0.0
+            mshow, cshow = (mratio, cratio) if o.printNormalizedResiduals else (mnorm, cnorm)
+            print("%d: [%s : [%g %g %g]];[%s : %g]" % (self._niters, vname, mshow[0], mshow[1], mshow[2], pname, cshow))
+            t["momentum_norm"], t["continuity_norm"] = mnorm, cnorm
+            self.timings.append(t)
+            self._niters += 1
+            if np.all(mratio < o.momentumTolerance) and cratio < o.continuityTolerance:
+                converged = True
+                break
+        self._download(mesh, fl)
+        return converged
+
+    def updateTime(self):  # F/FlowModel_impl.h:351-370
+        f, o = self.fields, self._options
+        for mesh in self.meshes:
+            cells = mesh.getCells()
+            if o.timeDiscretizationOrder > 1:
+                f.velocityN2[cells][:] = f.velocityN1[cells]
+            f.velocityN1[cells][:] = f.velocity[cells]
+
+    def getPressureIntegral(self, mesh, face_group_id):  # F/FlowModel_impl.h:1587-1611: sum of pFace * A
+        faces = mesh.getFaces()
+        for fg in mesh.getBoundaryFaceGroups():
+            if fg.id == face_group_id:
+                o, c = fg.site.getOffset(), fg.site.getCount()
+                return (self.fields.pressure[faces][o:o + c, None] * self.geom.area[faces][o:o + c]).sum(axis=0)
+        raise CException("getPressureIntegral: invalid faceGroupID")

@@ -199,6 +199,61 @@ int fvmgpu_bcgstab_solve(fvmgpu_solver_t precond, fvmgpu_system_t sys, int nMaxI
  * eliminated boundary rows, solve the boundary-flux rows, x += delta, flux += dflux */
 int fvmgpu_post_solve_update(fvmgpu_system_t sys);
 
+/* ---- FlowModel (SIMPLE): momentum + pressure-correction hot path (F/FlowModel_impl.h:522-1471,
+ *      F/FlowModelInterior.h, F/FlowModelVelocityBC.h, F/MomentumPressureGradientDiscretization.h).
+ *      This release covers wall-bounded flows (FlowBC::bcType "NoSlipWall", e.g. the lid-driven
+ *      cavity); other boundary types are rejected. Vector cell fields are AoS (Vector<T,3>,
+ *      F/Vector.h:229; Gradient<Vector<T,3>> = 9 doubles [direction][component], F/Gradient.h:199). ---- */
+typedef struct fvmgpu_flow_s* fvmgpu_flow_t;  /* FlowFields of one mesh + the two linear systems */
+enum {
+  FVMGPU_FLOW_VELOCITY = 0,          /* 3*nCellsTotal  FlowFields::velocity                        */
+  FVMGPU_FLOW_PRESSURE = 1,          /* nCellsTotal    FlowFields::pressure[cells]                 */
+  FVMGPU_FLOW_DENSITY = 2,           /* nCellsTotal                                                */
+  FVMGPU_FLOW_VISCOSITY = 3,         /* nCellsTotal                                                */
+  FVMGPU_FLOW_MASS_FLUX = 4,         /* nFaces         FlowFields::massFlux                        */
+  FVMGPU_FLOW_FACE_PRESSURE = 5,     /* nFaces         FlowFields::pressure[faces]                 */
+  FVMGPU_FLOW_PRESSURE_GRADIENT = 6, /* 3*nCellsTotal                                              */
+  FVMGPU_FLOW_VELOCITY_GRADIENT = 7, /* 9*nCellsTotal                                              */
+  FVMGPU_FLOW_CONT_RESID = 8,        /* nCellsTotal    FlowFields::continuityResidual              */
+  FVMGPU_FLOW_MOM_AP = 9,            /* 3*nCellsTotal  Impl::_momApField (momentum diagonal)       */
+  FVMGPU_FLOW_PREV_VELOCITY = 10,    /* 3*nCellsTotal  Impl::_previousVelocity                     */
+  FVMGPU_FLOW_VELOCITY_N1 = 11,      /* 3*nCellsTotal  (transient)                                 */
+  FVMGPU_FLOW_VELOCITY_N2 = 12
+};
+enum { FVMGPU_FLOWBC_NOSLIP_WALL = 0 }; /* p[0..2] = specifiedX/Y/ZVelocity (F/FlowBC.h:10-21) */
+typedef struct {
+  double momentumURF;   /* FlowModelOptions "momentumURF" (0.7)  F/FlowBC.h:42-50 */
+  double pressureURF;   /* "pressureURF" (0.3)                                  */
+  int transient;        /* TimeDerivativeDiscretization on the momentum equations */
+  int time_order;
+  double dt;
+  int correctVelocity;  /* FlowModelOptions::correctVelocity (true)             */
+} fvmgpu_flow_opts;
+int fvmgpu_flow_create(fvmgpu_flow_t* out, fvmgpu_mesh_t mesh);
+int fvmgpu_flow_destroy(fvmgpu_flow_t flow);
+int fvmgpu_flow_set_field(fvmgpu_flow_t flow, int field, const double* host, long long n);
+int fvmgpu_flow_fill_field(fvmgpu_flow_t flow, int field, double value);
+int fvmgpu_flow_get_field(fvmgpu_flow_t flow, int field, double* host, long long n);
+int fvmgpu_flow_set_bc(fvmgpu_flow_t flow, int groupId, int bcKind, const double* p, int np);
+/* FlowModel::init: default face mass fluxes + continuity residual (F/FlowModel_impl.h:222-340) */
+int fvmgpu_flow_init(fvmgpu_flow_t flow);
+/* initMomentumLinearization + initAssembly + linearizeMomentum + initSolve (:522-737) */
+int fvmgpu_flow_assemble_momentum(fvmgpu_flow_t flow, const fvmgpu_flow_opts* opts);
+/* parity hook: VVMatrix diag (3 per cell) / scalar offdiag / b (3 per cell) */
+int fvmgpu_flow_download_momentum(fvmgpu_flow_t flow, double* diag3, double* offdiag, double* b3);
+/* momentumLinearSolver.solve + postSolve + updateSolution + momAp (:744-768). bcgstab != 0:
+ * BCGStab (its nMaxIterations / tolerances given here) preconditioned by `solver`.
+ * rnorm0[3] = initial residual 1-norm per velocity component, iters[3] */
+int fvmgpu_flow_solve_momentum(fvmgpu_flow_t flow, fvmgpu_solver_t solver, int bcgstab, int bcgMaxIterations,
+                               double bcgRelTol, double bcgAbsTol, double* rnorm0, int* iters);
+/* discretizeContinuity (:1394-1407): Rhie-Chow mass fluxes + pressure-correction matrix */
+int fvmgpu_flow_assemble_continuity(fvmgpu_flow_t flow, const fvmgpu_flow_opts* opts);
+int fvmgpu_flow_download_continuity(fvmgpu_flow_t flow, double* diag, double* offdiag, double* b, int* isBoundary);
+/* pressureLinearSolver.solve + postSolve + postContinuitySolve (:1410-1430, 1263-1339) */
+int fvmgpu_flow_solve_continuity(fvmgpu_flow_t flow, fvmgpu_solver_t solver, int bcgstab, int bcgMaxIterations,
+                                 double bcgRelTol, double bcgAbsTol, const fvmgpu_flow_opts* opts, double* rnorm0,
+                                 int* iters);
+
 /* ---- multi-GPU (one process per GPU, one mesh part per GPU; NCCL resolved at run time with dlopen)
  * The reference's MPI layer maps as follows (all stream ordered, no host staging):
  *   MultiField::sync / Field::syncLocal  (Isend/Irecv of packed ghosts, F/MultiField.cpp:488-551,

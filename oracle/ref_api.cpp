@@ -12,6 +12,8 @@
 //   FluentReader                  I/FluentReader.h:82-89
 //   MeshMetricsCalculator::init   F/MeshMetricsCalculator_impl.h:1944-2041
 //   ThermalModel<double>          F/ThermalModel.h:28-52, Impl F/ThermalModel_impl.h
+//   FlowModel<double>             F/FlowModel.h:17-95, Impl F/FlowModel_impl.h (SIMPLE: solveMomentum :730-770,
+//                                 discretizeContinuity :1394-1407, solveContinuity :1410-1430, advance :1433-1471)
 //   AMG / BCGStab                 F/AMG.cpp:219-298, F/BCGStab.cpp:26-170
 // `Impl` of the models is a private nested class; to read the assembled system at the same
 // points as Impl::dumpMatrix (F/ThermalModel_impl.h:499-539) this TU (and only this TU)
@@ -44,11 +46,15 @@
 #include "ThermalFields.h"
 #include "ThermalModel.h"
 #include "ThermalModel_impl.h"
+#include "FlowFields.h"
+#include "FlowModel.h"
+#include "FlowModel_impl.h"
 #undef private
 #undef protected
 
 template class MeshMetricsCalculator<double>;
 template class ThermalModel<double>;
+template class FlowModel<double>;
 
 typedef Vector<double, 3> Vec3;
 typedef Array<Vec3> Vec3Array;
@@ -158,6 +164,16 @@ static void finish_mesh(RefMesh* rm) {
   rm->geom.reset(new GeomFields("geom"));
   rm->metrics.reset(new MeshMetricsCalculator<double>(*rm->geom, rm->meshes));
   rm->metrics->init();
+  // single-rank identity local<->global cell maps: the -DFVM_PARALLEL build of FlowModel reads
+  // them (setDirichlet, F/FlowModel_impl.h:943-968); MeshPartitioner fills them even for one part
+  for (Mesh* mesh : rm->meshes) {
+    if (!mesh->_localToGlobal) {
+      const int n = mesh->getCells().getCount();
+      std::shared_ptr<Array<int>> l2g(new Array<int>(n));
+      for (int i = 0; i < n; i++) { (*l2g)[i] = i; mesh->_globalToLocal[i] = i; }
+      mesh->_localToGlobal = l2g;
+    }
+  }
 }
 
 void* fvmref_mesh_from_cas(const char* path) {
@@ -474,6 +490,189 @@ int fvmref_thermal_advance_timed(void* h, double* times, char* text, int textCap
 // pattern with separate diagonal (row/col exclude the diagonal), sign convention
 // r = b + A x (F/CRMatrix.h:407-426), then runs the reference solver. nGhost extra rows
 // follow the nSelf interior rows (F/CRMatrix.h:308,414).
+// ---------------------------------------------------------------- FlowModel (SIMPLE)
+struct RefFlow {
+  RefMesh* m;
+  std::shared_ptr<FlowFields> fields;
+  std::shared_ptr<FlowModel<double>> model;
+  RefSolver momSolver, prSolver;
+  std::shared_ptr<LinearSystem> keep;  // keeps the last assembled system alive
+};
+
+void* fvmref_flow_create(void* h) {
+  TRY RefMesh* rm = (RefMesh*)h;
+  RefFlow* t = new RefFlow;
+  t->m = rm;
+  t->fields.reset(new FlowFields("flow"));
+  t->model.reset(new FlowModel<double>(*rm->geom, *t->fields, rm->meshes));
+  return t;
+  CATCH(nullptr)
+}
+void fvmref_flow_free(void* h) { delete (RefFlow*)h; }
+
+int fvmref_flow_set_bc(void* h, int id, const char* bcType, const char* var, double value) {
+  TRY RefFlow* t = (RefFlow*)h;
+  auto& bcMap = t->model->getBCMap();
+  if (bcMap.find(id) == bcMap.end()) throw CException("no such boundary id");
+  FlowBC<double>& bc = *bcMap[id];
+  if (bcType && bcType[0]) bc.bcType = bcType;
+  if (var && var[0]) {
+    auto pos = bc.find(var);
+    if (pos == bc.end()) throw CException(std::string("unknown bc var ") + var);
+    pos->second.constant = value;
+  }
+  return 0;
+  CATCH(-1)
+}
+int fvmref_flow_set_vc(void* h, const char* var, double value) {
+  TRY RefFlow* t = (RefFlow*)h;
+  for (auto& kv : t->model->getVCMap()) {
+    auto pos = kv.second->find(var);
+    if (pos == kv.second->end()) throw CException(std::string("unknown vc var ") + var);
+    pos->second.constant = value;
+  }
+  return 0;
+  CATCH(-1)
+}
+int fvmref_flow_set_option(void* h, const char* name, double value) {
+  TRY RefFlow* t = (RefFlow*)h;
+  FlowModelOptions<double>& o = t->model->getOptions();
+  std::string n(name);
+  if (n == "momentumTolerance") o.momentumTolerance = value;
+  else if (n == "continuityTolerance") o.continuityTolerance = value;
+  else if (n == "transient") o.transient = value != 0;
+  else if (n == "correctVelocity") o.correctVelocity = value != 0;
+  else if (n == "timeDiscretizationOrder") o.timeDiscretizationOrder = (int)value;
+  else if (n == "printNormalizedResiduals") o.printNormalizedResiduals = value != 0;
+  else {
+    auto pos = o.find(n);
+    if (pos == o.end()) throw CException("unknown option " + n);
+    pos->second.constant = value;
+  }
+  return 0;
+  CATCH(-1)
+}
+int fvmref_flow_set_solver(void* h, int which, const SolverCfg* cfg) {
+  TRY RefFlow* t = (RefFlow*)h;
+  if (which == 0) { t->momSolver = make_solver(*cfg); t->model->getOptions().momentumLinearSolver = t->momSolver.top; }
+  else { t->prSolver = make_solver(*cfg); t->model->getOptions().pressureLinearSolver = t->prSolver.top; }
+  return 0;
+  CATCH(-1)
+}
+int fvmref_flow_init(void* h) {
+  TRY RefFlow* t = (RefFlow*)h;
+  CoutCapture cap;
+  t->model->init();
+  return 0;
+  CATCH(-1)
+}
+// VIEW of a reference host array (doubles); cell vectors are AoS (3 / 9 doubles per cell)
+double* fvmref_flow_field(void* h, const char* name, int* len) {
+  TRY RefFlow* t = (RefFlow*)h;
+  Mesh& mesh = t->m->mesh();
+  const StorageSite& cells = mesh.getCells();
+  const StorageSite& faces = mesh.getFaces();
+  FlowFields& f = *t->fields;
+  FlowModel<double>::Impl& impl = *t->model->_impl;
+  std::string n(name);
+  ArrayBase* a = nullptr;
+  int width = 1;
+  if (n == "velocity") { a = &f.velocity[cells]; width = 3; }
+  else if (n == "pressure") a = &f.pressure[cells];
+  else if (n == "facePressure") a = &f.pressure[faces];
+  else if (n == "massFlux") a = &f.massFlux[faces];
+  else if (n == "density") a = &f.density[cells];
+  else if (n == "viscosity") a = &f.viscosity[cells];
+  else if (n == "continuityResidual") a = &f.continuityResidual[cells];
+  else if (n == "pressureGradient") { a = &f.pressureGradient[cells]; width = 3; }
+  else if (n == "velocityGradient") { a = &f.velocityGradient[cells]; width = 9; }
+  else if (n == "momAp") { if (!impl._momApField) throw CException("momAp not available"); a = &(*impl._momApField)[cells]; width = 3; }
+  else if (n == "previousVelocity") { if (!impl._previousVelocity) throw CException("previousVelocity not available"); a = &(*impl._previousVelocity)[cells]; width = 3; }
+  else throw CException("unknown field " + n);
+  if (len) *len = a->getLength() * width;
+  return (double*)a->getData();
+  CATCH(nullptr)
+}
+// initMomentumLinearization + initAssembly + linearizeMomentum + initSolve (F/FlowModel_impl.h:730-737)
+int fvmref_flow_momentum_system(void* h, double* diag3, double* offdiag, double* b3) {
+  TRY RefFlow* t = (RefFlow*)h;
+  FlowModel<double>::Impl& impl = *t->model->_impl;
+  Mesh& mesh = t->m->mesh();
+  const StorageSite& cells = mesh.getCells();
+  std::shared_ptr<LinearSystem> ls(new LinearSystem());
+  impl.initMomentumLinearization(*ls);
+  ls->initAssembly();
+  impl.linearizeMomentum(*ls);
+  ls->initSolve();
+  MultiField::ArrayIndex vIndex(&t->fields->velocity, &cells);
+  typedef CRMatrix<DiagonalTensor<double, 3>, double, Vec3> M;
+  M& m = dynamic_cast<M&>(ls->getMatrix().getMatrix(vIndex, vIndex));
+  const Array<DiagonalTensor<double, 3>>& d = m.getDiag();
+  const DArray& od = m.getOffDiag();
+  const Vec3Array& bb = dynamic_cast<const Vec3Array&>(ls->getB()[vIndex]);
+  for (int i = 0; i < d.getLength(); i++)
+    for (int k = 0; k < 3; k++) { diag3[3 * i + k] = d[i][k]; b3[3 * i + k] = bb[i][k]; }
+  for (int i = 0; i < od.getLength(); i++) offdiag[i] = od[i];
+  t->keep = ls;
+  return 0;
+  CATCH(-1)
+}
+// Impl::solveMomentum (:730-770): returns the initial residual 1-norms of the 3 components
+int fvmref_flow_solve_momentum(void* h, double* rnorm3) {
+  TRY RefFlow* t = (RefFlow*)h;
+  FlowModel<double>::Impl& impl = *t->model->_impl;
+  CoutCapture cap;
+  MFRPtr r = impl.solveMomentum();
+  const Vec3Array& a = dynamic_cast<const Vec3Array&>((*r)[t->fields->velocity]);
+  for (int k = 0; k < 3; k++) rnorm3[k] = a[0][k];
+  return 0;
+  CATCH(-1)
+}
+// Impl::discretizeContinuity (:1394-1407): needs a preceding solve_momentum (momAp, previousVelocity);
+// NB it also overwrites massFlux with the Rhie-Chow face fluxes
+int fvmref_flow_continuity_system(void* h, double* diag, double* offdiag, double* b, int* isBoundary) {
+  TRY RefFlow* t = (RefFlow*)h;
+  FlowModel<double>::Impl& impl = *t->model->_impl;
+  Mesh& mesh = t->m->mesh();
+  const StorageSite& cells = mesh.getCells();
+  std::shared_ptr<LinearSystem> ls = impl.discretizeContinuity();
+  MultiField::ArrayIndex pIndex(&t->fields->pressure, &cells);
+  typedef CRMatrix<double, double, double> M;
+  M& m = dynamic_cast<M&>(ls->getMatrix().getMatrix(pIndex, pIndex));
+  const DArray& d = m.getDiag();
+  const DArray& od = m.getOffDiag();
+  const DArray& bb = dynamic_cast<const DArray&>(ls->getB()[pIndex]);
+  for (int i = 0; i < d.getLength(); i++) {
+    diag[i] = d[i]; b[i] = bb[i];
+    if (isBoundary) isBoundary[i] = m._isBoundary[i] ? 1 : 0;
+  }
+  for (int i = 0; i < od.getLength(); i++) offdiag[i] = od[i];
+  t->keep = ls;
+  return 0;
+  CATCH(-1)
+}
+int fvmref_flow_solve_continuity(void* h, double* rnorm) {
+  TRY RefFlow* t = (RefFlow*)h;
+  FlowModel<double>::Impl& impl = *t->model->_impl;
+  CoutCapture cap;
+  MFRPtr r = impl.solveContinuity();
+  const DArray& a = dynamic_cast<const DArray&>((*r)[t->fields->pressure]);
+  rnorm[0] = a[0];
+  return 0;
+  CATCH(-1)
+}
+// FlowModel::advance (:1433-1471); returns 1 if converged, stdout (residual history) captured
+int fvmref_flow_advance(void* h, int niter, char* text, int textCap, double* seconds) {
+  TRY RefFlow* t = (RefFlow*)h;
+  CoutCapture cap;
+  double t0 = now_s();
+  bool conv = t->model->advance(niter);
+  if (seconds) *seconds = now_s() - t0;
+  copy_text(cap.os.str(), text, textCap);
+  return conv ? 1 : 0;
+  CATCH(-1)
+}
+
 // levelSizes (cap 64 ints, -1 terminated) receives the coarse level sizes.
 int fvmref_linsolve(int nSelf, int nGhost, const int* row, const int* col, const double* diag,
                     const double* offdiag, const double* b, const SolverCfg* cfg, double* x,

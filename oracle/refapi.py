@@ -86,6 +86,21 @@ def lib():
                                       C.POINTER(SolverCfg), _dp, C.POINTER(C.c_double),
                                       C.POINTER(C.c_int), _ip, C.c_char_p, C.c_int,
                                       C.POINTER(C.c_double)]
+        L.fvmref_flow_create.restype = C.c_void_p
+        L.fvmref_flow_create.argtypes = [C.c_void_p]
+        L.fvmref_flow_free.argtypes = [C.c_void_p]
+        L.fvmref_flow_set_bc.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_double]
+        L.fvmref_flow_set_vc.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.fvmref_flow_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.fvmref_flow_set_solver.argtypes = [C.c_void_p, C.c_int, C.POINTER(SolverCfg)]
+        L.fvmref_flow_init.argtypes = [C.c_void_p]
+        L.fvmref_flow_field.restype = C.POINTER(C.c_double)
+        L.fvmref_flow_field.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
+        L.fvmref_flow_momentum_system.argtypes = [C.c_void_p, _dp, _dp, _dp]
+        L.fvmref_flow_solve_momentum.argtypes = [C.c_void_p, _dp]
+        L.fvmref_flow_continuity_system.argtypes = [C.c_void_p, _dp, _dp, _dp, _ip]
+        L.fvmref_flow_solve_continuity.argtypes = [C.c_void_p, _dp]
+        L.fvmref_flow_advance.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -252,3 +267,75 @@ def linsolve(n_self, row, col, diag, offdiag, b, cfg, n_ghost=0):
         levels.append(int(v))
     return dict(x=x, rnorm0=rn0.value, iters=it.value, levels=levels, text=buf.value.decode(),
                 seconds=sec.value)
+
+
+class RefFlow:
+    """The reference `FlowModel<double>` (SIMPLE) on a RefMesh (F/FlowModel.h:17-95)."""
+
+    def __init__(self, mesh):
+        self.mesh = mesh
+        self.h = lib().fvmref_flow_create(mesh.h)
+        if not self.h:
+            raise RuntimeError("reference: " + lib().fvmref_last_error().decode())
+
+    def set_bc(self, gid, bc_type="", **vars_):
+        _check(lib().fvmref_flow_set_bc(self.h, gid, bc_type.encode(), b"", 0.0))
+        for k, v in vars_.items():
+            _check(lib().fvmref_flow_set_bc(self.h, gid, b"", k.encode(), float(v)))
+
+    def set_vc(self, name, value):
+        _check(lib().fvmref_flow_set_vc(self.h, name.encode(), float(value)))
+
+    def set_option(self, name, value):
+        _check(lib().fvmref_flow_set_option(self.h, name.encode(), float(value)))
+
+    def set_solver(self, which, cfg):
+        """which: 0 momentum, 1 pressure correction"""
+        setattr(self, "_cfg%d" % which, cfg)
+        _check(lib().fvmref_flow_set_solver(self.h, which, C.byref(cfg)))
+
+    def init(self):
+        _check(lib().fvmref_flow_init(self.h))
+
+    def field(self, name):
+        """numpy VIEW of the reference's host Array (vectors AoS: 3 or 9 doubles per cell)."""
+        n = C.c_int(0)
+        p = lib().fvmref_flow_field(self.h, name.encode(), C.byref(n))
+        if not p:
+            raise RuntimeError("reference: " + lib().fvmref_last_error().decode())
+        return np.ctypeslib.as_array(p, shape=(n.value,))
+
+    def momentum_system(self):
+        m = self.mesh
+        diag, off, b = np.zeros(3 * m.n_total), np.zeros(m.nnz), np.zeros(3 * m.n_total)
+        _check(lib().fvmref_flow_momentum_system(self.h, diag, off, b))
+        return dict(diag=diag.reshape(-1, 3), offdiag=off, b=b.reshape(-1, 3))
+
+    def solve_momentum(self):
+        r = np.zeros(3)
+        _check(lib().fvmref_flow_solve_momentum(self.h, r))
+        return r
+
+    def continuity_system(self):
+        m = self.mesh
+        diag, off, b = np.zeros(m.n_total), np.zeros(m.nnz), np.zeros(m.n_total)
+        isb = np.zeros(m.n_total, np.int32)
+        _check(lib().fvmref_flow_continuity_system(self.h, diag, off, b, isb))
+        return dict(diag=diag, offdiag=off, b=b, is_boundary=isb)
+
+    def solve_continuity(self):
+        r = np.zeros(1)
+        _check(lib().fvmref_flow_solve_continuity(self.h, r))
+        return float(r[0])
+
+    def advance(self, niter=1):
+        buf = C.create_string_buffer(1 << 18)
+        sec = C.c_double(0)
+        rc = lib().fvmref_flow_advance(self.h, niter, buf, len(buf), C.byref(sec))
+        _check(rc)
+        return bool(rc), buf.value.decode(), sec.value
+
+    def close(self):
+        if self.h:
+            lib().fvmref_flow_free(self.h)
+            self.h = None

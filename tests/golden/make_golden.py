@@ -13,6 +13,10 @@ hot path compiled in place by oracle/Makefile). Writes small .npz files next to 
   hex_bcs.npz      a jittered 6x5x4 hex mesh with every thermal BC kind, random conductivity and
                    source: reference gradient / matrix / rhs before and after boundary elimination
   tet_solve.npz    a 5x5x5x6 tet mesh: reference assembled system + converged solution + heat fluxes
+  flow_cavity.npz  lid-driven cavity on a jittered 12x10 quad mesh (FlowModel, NoSlipWall, lid u = 1,
+                   mu = 0.1, rho = 1.3): the reference state after 6 SIMPLE iterations, its momentum
+                   system assembled from that state, the post-momentum state, the pressure-correction
+                   system, and the converged steady flow field (tolerances 1e-9)
 """
 import os
 import sys
@@ -143,5 +147,50 @@ def main():
             print(f, os.path.getsize(os.path.join(HERE, f)))
 
 
+def flow_golden():
+    raw = G.quad_mesh(12, 10, jitter=0.2, seed=5)
+    rm = R.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes, raw.face_node_count,
+                            raw.face_group_size)
+
+    def make():
+        f = R.RefFlow(rm)
+        for g in (1, 2, 3):
+            f.set_bc(g, "NoSlipWall")
+        f.set_bc(4, "NoSlipWall", specifiedXVelocity=1.0)
+        f.set_vc("viscosity", 0.1)
+        f.set_vc("density", 1.3)
+        return f
+
+    f = make()
+    f.init()
+    f.advance(6)
+    out = {}
+    for nm in ("velocity", "pressure", "facePressure", "massFlux", "continuityResidual"):
+        out["s0_" + nm] = f.field(nm).copy()
+    ms = f.momentum_system()
+    out.update(mom_diag=ms["diag"], mom_off=ms["offdiag"], mom_b=ms["b"],
+               mom_vgrad=f.field("velocityGradient").copy(), mom_pgrad=f.field("pressureGradient").copy())
+    out["mom_rnorm"] = f.solve_momentum()
+    for nm in ("velocity", "previousVelocity", "momAp", "pressureGradient", "massFlux", "pressure"):
+        out["s1_" + nm] = f.field(nm).copy()
+    cs = f.continuity_system()
+    out.update(pp_diag=cs["diag"], pp_off=cs["offdiag"], pp_b=cs["b"], pp_is_boundary=cs["is_boundary"],
+               pp_massFlux=f.field("massFlux").copy())
+    f.close()
+    f = make()
+    f.set_option("momentumTolerance", 1e-9)
+    f.set_option("continuityTolerance", 1e-9)
+    f.init()
+    conv, txt, _ = f.advance(600)
+    assert conv
+    out.update(conv_iters=len(txt.splitlines()), conv_velocity=f.field("velocity").copy(),
+               conv_pressure=f.field("pressure").copy(), conv_massFlux=f.field("massFlux").copy())
+    np.savez_compressed(os.path.join(HERE, "flow_cavity.npz"), **mesh_arrays(rm), **out)
+    print("flow_cavity.npz: %d cells, converged in %d SIMPLE iterations" % (rm.n_self, out["conv_iters"]))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "flow":
+        flow_golden()
+        sys.exit(0)
     main()
