@@ -343,6 +343,15 @@ def roofline(recs, step):
             "bytes_per_row": per_row, "rows_per_launch": sum(r["launches"] * r["rows"] for r in picked) / launches,
             "mean_launch_ms": ms / launches, "launches": launches,
             "share_of_step": ms / step["total_ms"]}
+    # DRAM traffic of that kernel from the committed `ncu --set full` capture (per launch), when the
+    # capture was taken on this workload size
+    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath))
+        g = t.get("GsRows_level0", {})
+        if t.get("workload_cells") == n0 and g.get("rows_per_launch") == int(round(roof["rows_per_launch"])):
+            roof["traffic"] = g["dram_bytes_read"] + g["dram_bytes_write"]
+            roof["traffic_source"] = t["source"]
     return roof, table
 
 

@@ -25,6 +25,7 @@ SOURCES = [
     ("assemble.cu", ["-fmad=false"]),
     ("solver.cu", []),
     ("flow.cu", ["-fmad=false"]),
+    ("electric.cu", ["-fmad=false"]),
     ("capi.cu", []),
 ]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

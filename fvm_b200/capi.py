@@ -102,6 +102,8 @@ SIGNATURES = {
     "fvmgpu_bcgstab_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "fvmgpu_post_solve_update": (C.c_int, [_vp]),
+    "fvmgpu_electric_field": (C.c_int, [_vp, _dpn]),
+    "fvmgpu_electric_drift_flux": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_int, _ip, _dpn]),
     "fvmgpu_flow_create": (C.c_int, [C.POINTER(_vp), _vp]),
     "fvmgpu_flow_destroy": (C.c_int, [_vp]),
     "fvmgpu_flow_set_field": (C.c_int, [_vp, C.c_int, _dp, C.c_longlong]),
@@ -472,6 +474,20 @@ class DeviceSystem:
 
     def post_solve_update(self):
         self.lib.call("fvmgpu_post_solve_update", self.h)
+
+    def electric_field(self, want=True):
+        """updateElectricField: E = -grad(x) for every cell -> [n_total, 3]"""
+        out = np.zeros(3 * self.n_total) if want else None
+        self.lib.call("fvmgpu_electric_field", self.h, out.ctypes.data_as(C.c_void_p) if want else None)
+        return out.reshape(-1, 3) if want else None
+
+    def drift_flux_into(self, charge_system, mobility, vsat, symmetry_group_ids=(), want_velocity=True):
+        """updateElectronVelocity + updateConvectionFlux; the face flux goes to charge_system's FACE_FLUX"""
+        ids = _i32(list(symmetry_group_ids) or [0])
+        out = np.zeros(3 * self.n_total) if want_velocity else None
+        self.lib.call("fvmgpu_electric_drift_flux", self.h, charge_system.h, float(mobility), float(vsat),
+                      len(symmetry_group_ids), ids, out.ctypes.data_as(C.c_void_p) if want_velocity else None)
+        return out.reshape(-1, 3) if want_velocity else None
 
     def halo_exchange(self, field):
         self.lib.call("fvmgpu_system_halo_exchange", self.h, int(field))

@@ -388,6 +388,19 @@ int fvmgpu_post_solve_update(fvmgpu_system_t sys) {
   API_END
 }
 
+// ---------------------------------------------------------------- ElectricModel (electric.cu)
+int fvmgpu_electric_field(fvmgpu_system_t potential, double* E_host) {
+  API_BEGIN
+  electricField(S(potential), E_host);
+  API_END
+}
+int fvmgpu_electric_drift_flux(fvmgpu_system_t potential, fvmgpu_system_t charge, double mobility, double vsat,
+                               int nSymmetryGroups, const int* symmetryGroupIds, double* velocity_host) {
+  API_BEGIN
+  electricDriftFlux(S(potential), S(charge), mobility, vsat, nSymmetryGroups, symmetryGroupIds, velocity_host);
+  API_END
+}
+
 // ---------------------------------------------------------------- FlowModel (flow.cu)
 int fvmgpu_flow_create(fvmgpu_flow_t* out, fvmgpu_mesh_t mesh) {
   API_BEGIN

@@ -106,6 +106,11 @@ void computeGradient(System* s);
 void assemble(System* s, const fvmgpu_assemble_opts& o);
 void postSolveUpdate(System* s);
 
+// electric.cu
+void electricField(System* s, double* E_host);
+void electricDriftFlux(System* potential, System* charge, double mobility, double vsat, int nSym, const int* symGroupIds,
+                       double* vel_host);
+
 // flow.cu
 struct Flow;
 Flow* flowCreate(Mesh* m);

@@ -66,6 +66,7 @@ struct System {
   DBuf<double> x, diffusivity, source, faceFlux, xN1, xN2, density, contResid;
   bool hasFaceFlux = false, hasXN1 = false, hasXN2 = false;
   DBuf<double4> cellState;  // {gx,gy,gz,x}
+  DBuf<double> aux3a, aux3b;  // ElectricModel: electric field / electron velocity (3*Nt AoS)
   bool gradientValid = false;
   DBuf<double> xGhostNew;   // staged Dirichlet values for ghost cells (Nt - nSelf)
   // boundary flux side system, indexed by (face - nInteriorFaces)

@@ -199,6 +199,19 @@ int fvmgpu_bcgstab_solve(fvmgpu_solver_t precond, fvmgpu_system_t sys, int nMaxI
  * eliminated boundary rows, solve the boundary-flux rows, x += delta, flux += dflux */
 int fvmgpu_post_solve_update(fvmgpu_system_t sys);
 
+/* ---- ElectricModel: the electrostatics step is the scalar path above (potential = FIELD_X,
+ *      dielectric_constant = FIELD_DIFFUSIVITY, total_charge = FIELD_SOURCE; SpecifiedPotential =
+ *      DIRICHLET, SpecifiedPotentialFlux / Symmetry = NEUMANN, SpecialDielectricBoundary =
+ *      CONVECTIVE with h = eps/thickness: applyDielectricInterfaceBC with zero source,
+ *      F/GenericBCS.h:367-407). Model-specific updates (F/ElectricModel_impl.h:1001-1092): ---- */
+/* updateElectricField: potential gradient (GradientModel::compute) and E = -grad; E_host[3*nCellsTotal] or NULL */
+int fvmgpu_electric_field(fvmgpu_system_t potential, double* E_host);
+/* updateElectronVelocity + updateConvectionFlux: v = -mobility E limited to vsat (velocity_host
+ * [3*nCellsTotal] or NULL); the drift face flux lands in `charge`'s FIELD_FACE_FLUX (device to
+ * device), zero on the listed symmetry boundary groups. Call fvmgpu_electric_field first. */
+int fvmgpu_electric_drift_flux(fvmgpu_system_t potential, fvmgpu_system_t charge, double mobility, double vsat,
+                               int nSymmetryGroups, const int* symmetryGroupIds, double* velocity_host);
+
 /* ---- FlowModel (SIMPLE): momentum + pressure-correction hot path (F/FlowModel_impl.h:522-1471,
  *      F/FlowModelInterior.h, F/FlowModelVelocityBC.h, F/MomentumPressureGradientDiscretization.h).
  *      This release covers wall-bounded flows (FlowBC::bcType "NoSlipWall", e.g. the lid-driven

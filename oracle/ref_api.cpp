@@ -49,12 +49,16 @@
 #include "FlowFields.h"
 #include "FlowModel.h"
 #include "FlowModel_impl.h"
+#include "ElectricFields.h"
+#include "ElectricModel.h"
+#include "ElectricModel_impl.h"
 #undef private
 #undef protected
 
 template class MeshMetricsCalculator<double>;
 template class ThermalModel<double>;
 template class FlowModel<double>;
+template class ElectricModel<double>;
 
 typedef Vector<double, 3> Vec3;
 typedef Array<Vec3> Vec3Array;
@@ -670,6 +674,144 @@ int fvmref_flow_advance(void* h, int niter, char* text, int textCap, double* sec
   if (seconds) *seconds = now_s() - t0;
   copy_text(cap.os.str(), text, textCap);
   return conv ? 1 : 0;
+  CATCH(-1)
+}
+
+// ---------------------------------------------------------------- ElectricModel
+struct RefElectric {
+  RefMesh* m;
+  std::shared_ptr<ElectricFields> fields;
+  std::shared_ptr<ElectricModel<double>> model;
+  RefSolver esSolver, ctSolver;
+};
+void* fvmref_electric_create(void* h) {
+  TRY RefMesh* rm = (RefMesh*)h;
+  RefElectric* t = new RefElectric;
+  t->m = rm;
+  t->fields.reset(new ElectricFields("elec"));
+  t->model.reset(new ElectricModel<double>(*rm->geom, *t->fields, rm->meshes));
+  return t;
+  CATCH(nullptr)
+}
+void fvmref_electric_free(void* h) { delete (RefElectric*)h; }
+int fvmref_electric_set_bc(void* h, int id, const char* bcType, const char* var, double value) {
+  TRY RefElectric* t = (RefElectric*)h;
+  auto& bcMap = t->model->getBCMap();
+  if (bcMap.find(id) == bcMap.end()) throw CException("no such boundary id");
+  ElectricBC<double>& bc = *bcMap[id];
+  if (bcType && bcType[0]) bc.bcType = bcType;
+  if (var && var[0]) {
+    auto pos = bc.find(var);
+    if (pos == bc.end()) throw CException(std::string("unknown bc var ") + var);
+    pos->second.constant = value;
+  }
+  return 0;
+  CATCH(-1)
+}
+// kind 0: VC var, 1: option (float var or named flag), 2: constant
+int fvmref_electric_set(void* h, int kind, const char* name, double value) {
+  TRY RefElectric* t = (RefElectric*)h;
+  std::string n(name);
+  if (kind == 0) {
+    for (auto& kv : t->model->getVCMap()) {
+      auto pos = kv.second->find(n);
+      if (pos == kv.second->end()) throw CException("unknown vc var " + n);
+      pos->second.constant = value;
+    }
+  } else if (kind == 1) {
+    ElectricModelOptions<double>& o = t->model->getOptions();
+    if (n == "electrostaticsTolerance") o.electrostaticsTolerance = value;
+    else if (n == "chargetransportTolerance") o.chargetransportTolerance = value;
+    else if (n == "electrostatics_enable") o.electrostatics_enable = value != 0;
+    else if (n == "chargetransport_enable") o.chargetransport_enable = value != 0;
+    else if (n == "transient_enable") o.transient_enable = value != 0;
+    else if (n == "drift_enable") o.drift_enable = value != 0;
+    else if (n == "timeDiscretizationOrder") o.timeDiscretizationOrder = (int)value;
+    else if (n == "printNormalizedResiduals") o.printNormalizedResiduals = value != 0;
+    else {
+      auto pos = o.find(n);
+      if (pos == o.end()) throw CException("unknown option " + n);
+      pos->second.constant = value;
+    }
+  } else {
+    ElectricModelConstants<double>& c = t->model->getConstants();
+    auto pos = c.find(n);
+    if (pos == c.end()) throw CException("unknown constant " + n);
+    pos->second.constant = value;
+  }
+  return 0;
+  CATCH(-1)
+}
+int fvmref_electric_set_solver(void* h, int which, const SolverCfg* cfg) {
+  TRY RefElectric* t = (RefElectric*)h;
+  if (which == 0) { t->esSolver = make_solver(*cfg); t->model->getOptions().electrostaticsLinearSolver = t->esSolver.top; }
+  else { t->ctSolver = make_solver(*cfg); t->model->getOptions().chargetransportLinearSolver = t->ctSolver.top; }
+  return 0;
+  CATCH(-1)
+}
+int fvmref_electric_init(void* h) {
+  TRY RefElectric* t = (RefElectric*)h;
+  CoutCapture cap;
+  t->model->init();
+  return 0;
+  CATCH(-1)
+}
+double* fvmref_electric_field(void* h, const char* name, int* len) {
+  TRY RefElectric* t = (RefElectric*)h;
+  Mesh& mesh = t->m->mesh();
+  const StorageSite& cells = mesh.getCells();
+  const StorageSite& faces = mesh.getFaces();
+  ElectricFields& f = *t->fields;
+  std::string n(name);
+  ArrayBase* a = nullptr;
+  int width = 1;
+  if (n == "potential") a = &f.potential[cells];
+  else if (n == "dielectric_constant") a = &f.dielectric_constant[cells];
+  else if (n == "total_charge") a = &f.total_charge[cells];
+  else if (n == "potential_gradient") { a = &f.potential_gradient[cells]; width = 3; }
+  else if (n == "electric_field") { a = &f.electric_field[cells]; width = 3; }
+  else if (n == "electron_velocity") { a = &f.electron_velocity[cells]; width = 3; }
+  else if (n == "convectionFlux") a = &f.convectionFlux[faces];
+  else if (n == "charge") { a = &f.charge[cells]; width = 3; }
+  else if (n == "chargeN1") { a = &f.chargeN1[cells]; width = 3; }
+  else throw CException("unknown field " + n);
+  if (len) *len = a->getLength() * width;
+  return (double*)a->getData();
+  CATCH(nullptr)
+}
+// initElectroStaticsLinearization + initAssembly + linearizeElectroStatics + initSolve (:377-385)
+int fvmref_electric_potential_system(void* h, double* diag, double* offdiag, double* b) {
+  TRY RefElectric* t = (RefElectric*)h;
+  ElectricModel<double>::Impl& impl = *t->model->_impl;
+  const StorageSite& cells = t->m->mesh().getCells();
+  LinearSystem ls;
+  impl.initElectroStaticsLinearization(ls);
+  ls.initAssembly();
+  impl.linearizeElectroStatics(ls);
+  ls.initSolve();
+  MultiField::ArrayIndex pIndex(&t->fields->potential, &cells);
+  typedef CRMatrix<double, double, double> M;
+  M& m = dynamic_cast<M&>(ls.getMatrix().getMatrix(pIndex, pIndex));
+  const DArray& bb = dynamic_cast<const DArray&>(ls.getB()[pIndex]);
+  for (int i = 0; i < m.getDiag().getLength(); i++) { diag[i] = m.getDiag()[i]; b[i] = bb[i]; }
+  for (int i = 0; i < m.getOffDiag().getLength(); i++) offdiag[i] = m.getOffDiag()[i];
+  return 0;
+  CATCH(-1)
+}
+// ElectricModel::advance (:929-998); stdout captured; returns 1 if electrostatics converged
+int fvmref_electric_advance(void* h, int niter, char* text, int textCap) {
+  TRY RefElectric* t = (RefElectric*)h;
+  CoutCapture cap;
+  bool conv = t->model->advance(niter);
+  copy_text(cap.os.str(), text, textCap);
+  return conv ? 1 : 0;
+  CATCH(-1)
+}
+int fvmref_electric_update_time(void* h) {
+  TRY RefElectric* t = (RefElectric*)h;
+  CoutCapture cap;
+  t->model->updateTime();
+  return 0;
   CATCH(-1)
 }
 
