@@ -38,8 +38,11 @@ struct ElectronVelocityRows {  // F/ElectricModel_impl.h:1037-1045
     }
   }
 };
+// NB (reference quirk, reproduced for parity): the boundary loop (:1070-1088) indexes
+// mesh.getAllFaceCells() with the GROUP-LOCAL face index, i.e. boundary face k of a group takes the
+// velocity of cell c0 of face k of the whole mesh (an interior face), not of its own neighbour cell.
 struct DriftFluxFaces {  // F/ElectricModel_impl.h:1064-1088
-  int nInteriorFaces; const int* faceCells; const int* faceGroupOf; const int* groupIsSymmetry;
+  int nInteriorFaces; const int* faceCells; const int* faceGroupOf; const int* groupIsSymmetry; const int* groupOffset;
   const double4* faceGeom; const double* vel; double* flux;
   FVM_DEV double vdotA(int c, const double4 fg) const {
     double s = 0.0;
@@ -51,7 +54,9 @@ struct DriftFluxFaces {  // F/ElectricModel_impl.h:1064-1088
     const int c0 = faceCells[2 * f], c1 = faceCells[2 * f + 1];
     const double4 fg = faceGeom[f];
     if (f >= nInteriorFaces) {
-      flux[f] = groupIsSymmetry[faceGroupOf[f - nInteriorFaces]] ? 0.0 : vdotA(c0, fg);
+      const int g = faceGroupOf[f - nInteriorFaces];
+      const int cq = faceCells[2 * (f - groupOffset[g])];  // see NB above
+      flux[f] = groupIsSymmetry[g] ? 0.0 : vdotA(cq, fg);
       return;
     }
     flux[f] = 0.5 * (vdotA(c0, fg) + vdotA(c1, fg));
@@ -83,10 +88,13 @@ void electricDriftFlux(System* potential, System* charge, double mobility, doubl
   for (size_t g = 0; g < m->groups.size(); g++)
     for (int k = 0; k < nSym; k++)
       if (m->groups[g].id == symGroupIds[k] && m->groups[g].kind != FVMGPU_GROUP_INTERIOR) isSym[g] = 1;
-  DBuf<int> isSymDev;
+  std::vector<int> gOff(m->groups.size(), 0);
+  for (size_t g = 0; g < m->groups.size(); g++) gOff[g] = m->groups[g].offset;
+  DBuf<int> isSymDev, gOffDev;
   isSymDev.upload(isSym.data(), isSym.size());
+  gOffDev.upload(gOff.data(), gOff.size());
   if (charge->faceFlux.n < (size_t)m->nFaces) charge->faceFlux.alloc((size_t)m->nFaces);
-  parallelFor(m->nFaces, DriftFluxFaces{m->nInteriorFaces, m->faceCells.p, m->faceGroupOf.p, isSymDev.p, m->faceGeom.p,
+  parallelFor(m->nFaces, DriftFluxFaces{m->nInteriorFaces, m->faceCells.p, m->faceGroupOf.p, isSymDev.p, gOffDev.p, m->faceGeom.p,
                                         potential->aux3b.p, charge->faceFlux.p});
   charge->hasFaceFlux = true;
   if (vel_host) potential->aux3b.download(vel_host, 3 * nt);

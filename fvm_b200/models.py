@@ -832,3 +832,318 @@ class FlowModelA:
                 o, c = fg.site.getOffset(), fg.site.getCount()
                 return (self.fields.pressure[faces][o:o + c, None] * self.geom.area[faces][o:o + c]).sum(axis=0)
         raise CException("getPressureIntegral: invalid faceGroupID")
+
+
+# ----------------------------------------------------------------------------- ElectricModel
+K_SI, QE, E0_SI = 1.3806503e-23, 1.60217646e-19, 8.854187826e-12   # F/PhysicsConstant.h
+
+
+class ElectricBC(FloatVarDict):
+    """F/ElectricBC.h:13-29"""
+
+    def __init__(self):
+        super().__init__()
+        for name, v in (("specifiedPotential", 300.0), ("specifiedPotentialFlux", 0.0), ("specifiedXElecField", 0.0),
+                        ("specifiedYElecField", 0.0), ("specifiedZElecField", 0.0), ("specifiedCharge", 0.0),
+                        ("specifiedChargeFlux", 0.0), ("timeStep", 1.0)):
+            self.defineVar(name, v)
+        self.bcType = ""
+
+
+class ElectricVC(FloatVarDict):
+    """F/ElectricBC.h:31-39"""
+
+    def __init__(self):
+        super().__init__()
+        self.defineVar("dielectric_constant", 7.9)
+        self.vcType = ""
+
+
+class ElectricModelConstants(FloatVarDict):
+    """F/ElectricBC.h:41-75"""
+
+    def __init__(self):
+        super().__init__()
+        for name, v in (("dielectric_ionization", 3.0), ("dielectric_bandgap", 5.0), ("optical_dielectric_constant", 4.0),
+                        ("dielectric_thickness", 2.5e-7), ("dielectric_constant", 7.9), ("electron_capture_cross", 1e-17),
+                        ("membrane_workfunction", 5.0), ("substrate_workfunction", 5.0), ("membrane_voltage", 0.0),
+                        ("substrate_voltage", 0.0), ("OP_temperature", 300.0), ("electron_effmass", 0.5),
+                        ("poole_frenkel_emission_frequency", 1.0e12), ("electron_mobility", 50e4),
+                        ("electron_saturation_velocity", 1e9), ("voltage", 100.0), ("substrate_id", 5), ("membrane_id", 4),
+                        ("nLevel", 0), ("normal_direction", 2), ("nTrap", 1)):
+            self.defineVar(name, v)
+        self.electron_trapdensity = []
+        self.electron_trapdepth = []
+
+
+class ElectricModelOptions(FloatVarDict):
+    """F/ElectricBC.h:78-169"""
+
+    def __init__(self):
+        super().__init__()
+        for name, v in (("initialCharge", 0.0), ("initialPotential", 0.0), ("initialTotalCharge", 0.0),
+                        ("initialTunnelingCharge", 1.0), ("timeStep", 0.1), ("Interface_A_coeff", 1.0),
+                        ("Interface_B_coeff", 0.0)):
+            self.defineVar(name, v)
+        self.electrostaticsTolerance = 1e-8
+        self.chargetransportTolerance = 1e-8
+        self.electrostaticsLinearSolver = None
+        self.chargetransportLinearSolver = None
+        self.timeDiscretizationOrder = 1
+        self.transient_enable = True
+        self.ibm_enable = False
+        self.electrostatics_enable = True
+        self.chargetransport_enable = True
+        self.tunneling_enable = False
+        self.emission_enable = False
+        self.capture_enable = False
+        self.injection_enable = False
+        self.drift_enable = False
+        self.diffusion_enable = False
+        self.trapbandtunneling_enable = False
+        self.ButlerVolmer = False
+        self.printNormalizedResiduals = True
+
+    @staticmethod
+    def _default_solver():  # F/ElectricBC.h:140-165
+        ls = AMG()
+        ls.relativeTolerance = 1e-3
+        ls.nMaxIterations = 20
+        ls.verbosity = 0
+        return ls
+
+    def getElectroStaticsLinearSolver(self):
+        if self.electrostaticsLinearSolver is None:
+            self.electrostaticsLinearSolver = self._default_solver()
+        return self.electrostaticsLinearSolver
+
+    def getChargeTransportLinearSolver(self):
+        if self.chargetransportLinearSolver is None:
+            self.chargetransportLinearSolver = self._default_solver()
+        return self.chargetransportLinearSolver
+
+
+class ElectricFields:
+    """F/ElectricFields.h:18-52 (fields the electrostatics + drift path reads or writes)"""
+
+    def __init__(self, base_name):
+        for n in ("potential", "potential_flux", "potential_gradient", "electric_field", "dielectric_constant",
+                  "total_charge", "electron_velocity", "charge", "chargeFlux", "convectionFlux", "chargeN1",
+                  "chargeN2", "one", "zero"):
+            setattr(self, n, Field(base_name + "." + n))
+
+
+class ElectricModelA:
+    """Mirror of `models_atyped_double.ElectricModelA` (F/ElectricModel.h, F/ElectricModel_impl.h).
+
+    * electrostatics (F/ElectricModel_impl.h:377-410, 552-767): Poisson equation for the potential --
+      diffusion with dielectric_constant, total_charge source, BCs SpecifiedPotential,
+      SpecifiedPotentialFlux, Symmetry, SpecialDielectricBoundary -- then updateElectricField.
+    * charge transport (:412-436, 771-924) with the drift and transient terms: only component nTrap of
+      the charge vector is convected (DriftDiscretization); without the tunnelling / injection /
+      emission / capture source models (out of scope, SURVEY §2: 1-D column physics) the reference's
+      3x3 blocks stay diagonal, so each component is solved as a scalar system on the device.
+    Everything numerical runs on the GPU through the C ABI."""
+
+    def __init__(self, geom_fields, electric_fields, meshes, lib=None):
+        self.geom, self.fields, self.meshes, self.lib = geom_fields, electric_fields, list(meshes), lib
+        self._bcMap, self._vcMap = {}, {}
+        self._options, self._constants = ElectricModelOptions(), ElectricModelConstants()
+        self._pot, self._chg = {}, {}
+        self._niters = 0
+        self._initialElectroStaticsNorm = None
+        self._initialChargeTransportNorm = None
+        for mesh in self.meshes:  # Impl ctor, F/ElectricModel_impl.h:71-110
+            vc = ElectricVC()
+            vc.vcType = "dielectric"
+            self._vcMap[mesh.getID()] = vc
+            for fg in mesh.getBoundaryFaceGroups():
+                bc = ElectricBC()
+                self._bcMap[fg.id] = bc
+                if fg.groupType == "wall":
+                    bc.bcType = "SpecifiedPotential"
+                elif fg.groupType == "symmetry":
+                    bc.bcType = "Symmetry"
+
+    def getBCMap(self):
+        return self._bcMap
+
+    def getBC(self, gid):
+        return self._bcMap[gid]
+
+    def getVCMap(self):
+        return self._vcMap
+
+    def getVC(self, mid):
+        return self._vcMap[mid]
+
+    def getOptions(self):
+        return self._options
+
+    def getConstants(self):
+        return self._constants
+
+    def _unsupported(self):
+        o = self._options
+        for flag in ("tunneling_enable", "emission_enable", "capture_enable", "injection_enable",
+                     "trapbandtunneling_enable", "diffusion_enable", "ibm_enable", "ButlerVolmer"):
+            if getattr(o, flag):
+                raise CException("ElectricModelA: %s is not supported on the GPU path" % flag)
+
+    def init(self):  # F/ElectricModel_impl.h:112-330
+        f, o, c = self.fields, self._options, self._constants
+        self._unsupported()
+        for mesh in self.meshes:
+            if mesh.device is None:
+                raise CException("ElectricModel.init: mesh metrics not initialised (MeshMetricsCalculatorA.init)")
+            cells, faces = mesh.getCells(), mesh.getFaces()
+            n, nf = cells.getCount(), faces.getCount()
+            vc = self._vcMap[mesh.getID()]
+            lib = self.lib or mesh.device.lib
+            if o.electrostatics_enable:
+                f.potential[cells] = np.full(n, float(o["initialPotential"]))
+                f.dielectric_constant[cells] = np.full(n, float(vc["dielectric_constant"]) * E0_SI)
+                f.total_charge[cells] = (np.full(n, float(o["initialTotalCharge"]) * -QE)
+                                         if vc.vcType == "dielectric" else np.zeros(n))
+                f.potential_gradient[cells] = np.zeros((n, 3))
+                f.electric_field[cells] = np.zeros((n, 3))
+                for fg in mesh.getBoundaryFaceGroups():
+                    f.potential_flux[fg.site] = np.zeros(fg.site.getCount())
+                self._pot[mesh.getID()] = LinearSystem(lib, mesh=mesh.device, field_name=f.potential.name)
+            if o.chargetransport_enable and vc.vcType == "dielectric":
+                f.charge[cells] = np.zeros((n, 3))
+                if o.transient_enable:
+                    f.chargeN1[cells] = np.zeros((n, 3))
+                    if o.timeDiscretizationOrder > 1:
+                        f.chargeN2[cells] = np.zeros((n, 3))
+                f.electron_velocity[cells] = np.zeros((n, 3))
+                f.convectionFlux[faces] = np.zeros(nf)
+                f.one[cells] = np.ones(n)
+                f.zero[cells] = np.zeros(n)
+                self._chg[mesh.getID()] = LinearSystem(lib, mesh=mesh.device, field_name=f.charge.name)
+        self._niters = 0
+        self._initialElectroStaticsNorm = None
+        self._initialChargeTransportNorm = None
+
+    def updateTime(self):  # F/ElectricModel_impl.h:338-375
+        f, o = self.fields, self._options
+        for mesh in self.meshes:
+            cells = mesh.getCells()
+            if o.timeDiscretizationOrder > 1:
+                f.chargeN2[cells][:] = f.chargeN1[cells]
+            f.chargeN1[cells][:] = f.charge[cells]
+
+    # ---- electrostatics
+    def _solve_electrostatics(self, mesh):
+        f, o, c = self.fields, self._options, self._constants
+        ls = self._pot[mesh.getID()]
+        cells = mesh.getCells()
+        ls.set_field(capi.FIELD_X, f.potential[cells])
+        ls.set_field(capi.FIELD_DIFFUSIVITY, f.dielectric_constant[cells])
+        ls.set_field(capi.FIELD_SOURCE, f.total_charge[cells])
+        sym = []
+        for fg in mesh.getBoundaryFaceGroups():
+            bc = self._bcMap[fg.id]
+            if bc.bcType == "SpecifiedPotential":
+                v = bc["specifiedPotential"]
+                if isinstance(v, np.ndarray):
+                    ls.set_bc(fg.id, capi.BC_DIRICHLET, [0.0], per_face=v)
+                else:
+                    ls.set_bc(fg.id, capi.BC_DIRICHLET, [float(v)])
+            elif bc.bcType == "SpecifiedPotentialFlux":
+                ls.set_bc(fg.id, capi.BC_NEUMANN, [float(bc["specifiedPotentialFlux"])])
+            elif bc.bcType == "Symmetry":
+                ls.set_bc(fg.id, capi.BC_NEUMANN, [0.0])
+                sym.append(fg.id)
+            elif bc.bcType == "SpecialDielectricBoundary":  # applyDielectricInterfaceBC with src = 0, :734-745
+                coeff = float(c["dielectric_constant"]) * E0_SI / float(c["dielectric_thickness"])
+                ls.set_bc(fg.id, capi.BC_CONVECTIVE, [coeff, float(bc["specifiedPotential"])])
+            else:
+                raise CException(bc.bcType + " not implemented for ElectricModel")
+        ls.assemble(diffusion=1, convection=0, source=1, time_order=0, dt=0.0, underrelax=0.0, apply_bcs=1,
+                    eliminate_boundary=1)
+        solver = o.getElectroStaticsLinearSolver()
+        rnorm = solver.solve(ls)
+        solver.cleanup()
+        ls.post_solve_update()
+        f.potential[cells][:] = ls.get_field(capi.FIELD_X)
+        bflux = ls.get_field(capi.FIELD_BFLUX)
+        for fg in mesh.getBoundaryFaceGroups():
+            off = fg.site.getOffset()
+            f.potential_flux[fg.site][:] = bflux[off:off + fg.site.getCount()]
+        # updateElectricField (+ updateElectronVelocity, updateConvectionFlux when charge transport is on)
+        f.electric_field[cells][:] = ls.electric_field()
+        f.potential_gradient[cells][:] = -f.electric_field[cells]
+        if o.chargetransport_enable and mesh.getID() in self._chg:
+            vel = ls.drift_flux_into(self._chg[mesh.getID()], float(c["electron_mobility"]),
+                                     float(c["electron_saturation_velocity"]), sym)
+            f.electron_velocity[cells][:] = vel
+            f.convectionFlux[mesh.getFaces()][:] = self._chg[mesh.getID()].get_field(capi.FIELD_FACE_FLUX)
+        return rnorm
+
+    # ---- charge transport: one scalar system per component of the charge vector
+    def _solve_charge_transport(self, mesh):
+        f, o, c = self.fields, self._options, self._constants
+        ls = self._chg[mesh.getID()]
+        cells, faces = mesh.getCells(), mesh.getFaces()
+        n_trap = int(c["nTrap"])
+        if not 0 <= n_trap <= 2:
+            raise CException("ElectricModelA: nTrap must be 0..2 (the charge vector has 3 components)")
+        ls.set_field(capi.FIELD_FACE_FLUX, f.convectionFlux[faces])
+        ls.set_field(capi.FIELD_DENSITY, f.one[cells])
+        bcs_on = o.drift_enable or o.diffusion_enable
+        for fg in mesh.getBoundaryFaceGroups():   # "dielectric charging uses fixed zero dirichlet bc", :893-905
+            ls.set_bc(fg.id, capi.BC_DIRICHLET, [0.0])
+        norms = np.zeros(3)
+        solver = o.getChargeTransportLinearSolver()
+        for k in range(3):
+            ls.set_field(capi.FIELD_X, np.ascontiguousarray(f.charge[cells][:, k]))
+            order = 0
+            if o.transient_enable:
+                order = o.timeDiscretizationOrder
+                ls.set_field(capi.FIELD_X_N1, np.ascontiguousarray(f.chargeN1[cells][:, k]))
+                if order > 1:
+                    ls.set_field(capi.FIELD_X_N2, np.ascontiguousarray(f.chargeN2[cells][:, k]))
+            ls.assemble(diffusion=0, convection=1 if (o.drift_enable and k == n_trap) else 0, source=0,
+                        time_order=order, dt=float(o["timeStep"]), underrelax=0.0, apply_bcs=1 if bcs_on else 0,
+                        eliminate_boundary=1)
+            norms[k] = solver.solve(ls)
+            solver.cleanup()
+            ls.post_solve_update()
+            f.charge[cells][:, k] = ls.get_field(capi.FIELD_X)
+        return norms
+
+    def advance(self, niter):
+        """ElectricModel::advance, F/ElectricModel_impl.h:929-998. Returns the electrostatics flag."""
+        o = self._options
+        self._unsupported()
+        if len(self.meshes) != 1:
+            raise CException("ElectricModelA: one mesh per model in this release")
+        mesh = self.meshes[0]
+        flag1 = False
+        if o.electrostatics_enable:
+            for _ in range(niter):
+                e = self._solve_electrostatics(mesh)
+                if self._initialElectroStaticsNorm is None:
+                    self._initialElectroStaticsNorm = e
+                if self._niters < 5:
+                    self._initialElectroStaticsNorm = max(self._initialElectroStaticsNorm, e)
+                ratio = e / self._initialElectroStaticsNorm if self._initialElectroStaticsNorm > 0 else 0.0
+                print("%d: [%s : %g];" % (self._niters, self.fields.potential.name,
+                                          ratio if o.printNormalizedResiduals else e))
+                if ratio < o.electrostaticsTolerance:
+                    flag1 = True
+                    break
+        if o.chargetransport_enable and mesh.getID() in self._chg:
+            for _ in range(niter):
+                cn = self._solve_charge_transport(mesh)
+                if self._initialChargeTransportNorm is None:
+                    self._initialChargeTransportNorm = cn.copy()
+                if self._niters < 5:
+                    self._initialChargeTransportNorm = np.maximum(self._initialChargeTransportNorm, cn)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    cr = np.where(self._initialChargeTransportNorm > 0, cn / self._initialChargeTransportNorm, 0.0)
+                show = cr if o.printNormalizedResiduals else cn
+                print("%d: [%s : [%g %g %g]]" % (self._niters, self.fields.charge.name, show[0], show[1], show[2]))
+        self._niters += 1
+        return flag1

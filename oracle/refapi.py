@@ -101,6 +101,18 @@ def lib():
         L.fvmref_flow_continuity_system.argtypes = [C.c_void_p, _dp, _dp, _dp, _ip]
         L.fvmref_flow_solve_continuity.argtypes = [C.c_void_p, _dp]
         L.fvmref_flow_advance.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double)]
+        L.fvmref_electric_create.restype = C.c_void_p
+        L.fvmref_electric_create.argtypes = [C.c_void_p]
+        L.fvmref_electric_free.argtypes = [C.c_void_p]
+        L.fvmref_electric_set_bc.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_double]
+        L.fvmref_electric_set.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_double]
+        L.fvmref_electric_set_solver.argtypes = [C.c_void_p, C.c_int, C.POINTER(SolverCfg)]
+        L.fvmref_electric_init.argtypes = [C.c_void_p]
+        L.fvmref_electric_field.restype = C.POINTER(C.c_double)
+        L.fvmref_electric_field.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
+        L.fvmref_electric_potential_system.argtypes = [C.c_void_p, _dp, _dp, _dp]
+        L.fvmref_electric_advance.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+        L.fvmref_electric_update_time.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -338,4 +350,63 @@ class RefFlow:
     def close(self):
         if self.h:
             lib().fvmref_flow_free(self.h)
+            self.h = None
+
+
+class RefElectric:
+    """The reference `ElectricModel<double>` on a RefMesh (F/ElectricModel.h)."""
+
+    def __init__(self, mesh):
+        self.mesh = mesh
+        self.h = lib().fvmref_electric_create(mesh.h)
+        if not self.h:
+            raise RuntimeError("reference: " + lib().fvmref_last_error().decode())
+
+    def set_bc(self, gid, bc_type="", **vars_):
+        _check(lib().fvmref_electric_set_bc(self.h, gid, bc_type.encode(), b"", 0.0))
+        for k, v in vars_.items():
+            _check(lib().fvmref_electric_set_bc(self.h, gid, b"", k.encode(), float(v)))
+
+    def set_vc(self, name, value):
+        _check(lib().fvmref_electric_set(self.h, 0, name.encode(), float(value)))
+
+    def set_option(self, name, value):
+        _check(lib().fvmref_electric_set(self.h, 1, name.encode(), float(value)))
+
+    def set_constant(self, name, value):
+        _check(lib().fvmref_electric_set(self.h, 2, name.encode(), float(value)))
+
+    def set_solver(self, which, cfg):
+        """which: 0 electrostatics, 1 charge transport"""
+        setattr(self, "_cfg%d" % which, cfg)
+        _check(lib().fvmref_electric_set_solver(self.h, which, C.byref(cfg)))
+
+    def init(self):
+        _check(lib().fvmref_electric_init(self.h))
+
+    def field(self, name):
+        n = C.c_int(0)
+        p = lib().fvmref_electric_field(self.h, name.encode(), C.byref(n))
+        if not p:
+            raise RuntimeError("reference: " + lib().fvmref_last_error().decode())
+        return np.ctypeslib.as_array(p, shape=(n.value,))
+
+    def potential_system(self):
+        m = self.mesh
+        diag, off, b = np.zeros(m.n_total), np.zeros(m.nnz), np.zeros(m.n_total)
+        _check(lib().fvmref_electric_potential_system(self.h, diag, off, b))
+        return dict(diag=diag, offdiag=off, b=b)
+
+    def advance(self, niter=1):
+        buf = C.create_string_buffer(1 << 18)
+        rc = lib().fvmref_electric_advance(self.h, niter, buf, len(buf))
+        _check(rc)
+        return bool(rc), buf.value.decode()
+
+    def update_time(self):
+        _check(lib().fvmref_electric_update_time(self.h))
+
+    def close(self):
+        if self.h:
+            lib().fvmref_electric_free(self.h)
             self.h = None

@@ -17,6 +17,10 @@ hot path compiled in place by oracle/Makefile). Writes small .npz files next to 
                    mu = 0.1, rho = 1.3): the reference state after 6 SIMPLE iterations, its momentum
                    system assembled from that state, the post-momentum state, the pressure-correction
                    system, and the converged steady flow field (tolerances 1e-9)
+  electric_box.npz ElectricModel on a jittered 6x5x7 hex box (1 x 1 x 2 um): Poisson equation with
+                   SpecifiedPotential / SpecifiedPotentialFlux / Symmetry / SpecialDielectricBoundary
+                   BCs and a uniform total charge, then drift + transient charge transport of the
+                   conduction-band component (nTrap = 2): reference fields after two time steps
 """
 import os
 import sys
@@ -189,7 +193,47 @@ def flow_golden():
     print("flow_cavity.npz: %d cells, converged in %d SIMPLE iterations" % (rm.n_self, out["conv_iters"]))
 
 
+def electric_golden():
+    raw = G.hex_mesh(6, 5, 7, lx=1e-6, ly=1e-6, lz=2e-6, jitter=0.15, seed=2)
+    rm = R.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes, raw.face_node_count,
+                            raw.face_group_size)
+    tight = dict(relativeTolerance=1e-13, nMaxIterations=2000, verbosity=0)
+    e = R.RefElectric(rm)
+    e.set_bc(5, "SpecifiedPotential", specifiedPotential=0.0)
+    e.set_bc(6, "SpecifiedPotential", specifiedPotential=100.0)
+    e.set_bc(1, "Symmetry")
+    e.set_bc(2, "Symmetry")
+    e.set_bc(3, "SpecifiedPotentialFlux", specifiedPotentialFlux=1e-3)
+    e.set_bc(4, "SpecialDielectricBoundary", specifiedPotential=20.0)
+    e.set_option("drift_enable", 1)
+    e.set_option("initialTotalCharge", 1e18)
+    e.set_option("timeStep", 1e-12)
+    e.set_constant("nTrap", 2)
+    e.set_constant("electron_mobility", 1e-3)
+    e.set_constant("electron_saturation_velocity", 1e5)
+    e.set_solver(0, R.solver_cfg(**tight))
+    e.set_solver(1, R.solver_cfg(**tight))
+    e.init()
+    charge0 = 1e15 * (1 + np.arange(raw.n_cells) % 7)
+    e.field("charge").reshape(-1, 3)[:raw.n_cells, 2] = charge0
+    e.field("chargeN1").reshape(-1, 3)[:] = e.field("charge").reshape(-1, 3)
+    out = dict(charge0=charge0)
+    for step in range(2):
+        _, txt = e.advance(1)
+        for nm in ("potential", "electric_field", "electron_velocity", "convectionFlux", "charge"):
+            out["s%d_%s" % (step, nm)] = e.field(nm).copy()
+        out["s%d_text" % step] = np.array(txt)
+        e.update_time()
+    np.savez_compressed(os.path.join(HERE, "electric_box.npz"), **mesh_arrays(rm), nodes=raw.nodes,
+                        face_nodes=raw.face_nodes, face_node_count=raw.face_node_count,
+                        face_group_size=raw.face_group_size, **out)
+    print("electric_box.npz: %d cells" % rm.n_self)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "electric":
+        electric_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "flow":
         flow_golden()
         sys.exit(0)
