@@ -74,31 +74,12 @@ struct ColourRoundKernel {
     colour[i] = c;
   }
 };
-// ---- 2-colouring of bipartite patterns by breadth-first parity (structured hex / quad meshes and
-// their regularly paired coarse levels are bipartite; Jones-Plassmann needs 6-7 colours there).
-struct BfsRoundKernel {  // unreached rows adjacent to the current front join the next front
-  int n; const int* row; const int* col; int* depth; int d; int* flags;
-  FVM_DEV void operator()(long long ii) const {
-    const int i = (int)ii;
-    if (depth[i] != -1) return;
-    for (int k = row[i]; k < row[i + 1]; k++) {
-      const int j = col[k];
-      if (j < n && j != i && depth[j] == d) { depth[i] = d + 1; flags[0] = 1; return; }
-    }
-  }
-};
-struct BfsCheckKernel {  // flags[1]: an edge inside one parity class (odd cycle); flags[2]: min unreached row
-  int n; const int* row; const int* col; const int* depth; int* flags;
-  FVM_DEV void operator()(long long ii) const {
-    const int i = (int)ii;
-    const int di = depth[i];
-    if (di == -1) { atomicMin(&flags[2], i); return; }
-    for (int k = row[i]; k < row[i + 1]; k++) {
-      const int j = col[k];
-      if (j < n && j != i && depth[j] != -1 && ((depth[j] ^ di) & 1) == 0) { flags[1] = 1; return; }
-    }
-  }
-};
+// ---- 2-colouring of bipartite patterns by breadth-first parity (structured hex / quad meshes are
+// bipartite; Jones-Plassmann needs 6-7 colours there). The search runs as ONE cooperative kernel:
+// frontier queues (work proportional to the edges, not rows x diameter) and a grid-wide barrier per
+// BFS level, so a 256^3 mesh (diameter 768) costs ~800 barriers instead of ~800 launches over all
+// 16.8 M rows. BFS levels are unique, so the colouring is deterministic even though the order of
+// the queue entries is not. An edge inside one parity class (odd cycle) aborts the search.
 struct BfsIsolatedKernel {  // rows without neighbours are their own (trivially 2-colourable) component
   int n; const int* row; const int* col; int* depth;
   FVM_DEV void operator()(long long ii) const {
@@ -110,8 +91,47 @@ struct BfsIsolatedKernel {  // rows without neighbours are their own (trivially 
     depth[i] = 0;
   }
 };
-struct SetIntKernel { int* p; int idx; int v; FVM_DEV void operator()(long long) const { p[idx] = v; } };
+struct MinUnreachedKernel {  // flags[0] = smallest row index not reached yet
+  const int* depth; int* flags;
+  FVM_DEV void operator()(long long i) const { if (depth[i] == -1) atomicMin(&flags[0], (int)i); }
+};
 struct ParityKernel { const int* depth; int* colour; FVM_DEV void operator()(long long i) const { colour[i] = depth[i] & 1; } };
+
+// state[0], state[1]: sizes of the two queues; state[2]: odd-cycle flag; state[3]: last depth used
+FVM_DEV void bfsExpand(int i, int d, int n, const int* row, const int* col, int* depth, int* qout, int* cout, int* odd) {
+  for (int k = row[i]; k < row[i + 1]; k++) {
+    const int j = col[k];
+    if (j >= n || j == i) continue;
+    const int old = atomicCAS(&depth[j], -1, d + 1);
+    if (old == -1) qout[atomicAdd(cout, 1)] = j;
+    else if (((old ^ d) & 1) == 0) *odd = 1;
+  }
+}
+#ifndef FVMGPU_HOSTSIM
+}  // namespace fvmgpu
+#include <cooperative_groups.h>
+namespace fvmgpu {
+__global__ void __launch_bounds__(256) k_bfs_component(int n, const int* row, const int* col, int* depth, int* qA, int* qB,
+                                                        int* state, int d0) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  int d = d0;
+  int* qin = qA; int* qout = qB;
+  int* cin = &state[0]; int* cout = &state[1];
+  for (;;) {
+    const int m = *(volatile int*)cin;
+    if (m == 0 || *(volatile int*)&state[2]) break;
+    for (long long idx = tid; idx < m; idx += nthreads) bfsExpand(qin[idx], d, n, row, col, depth, qout, cout, &state[2]);
+    grid.sync();
+    if (tid == 0) { *cin = 0; state[3] = d + 1; }
+    int* t = qin; qin = qout; qout = t;
+    t = cin; cin = cout; cout = t;
+    d++;
+    grid.sync();
+  }
+}
+#endif
 
 struct ColourCountKernel {
   const int* colour; int* counts;
@@ -360,6 +380,66 @@ struct HandshakeKernel {  // mutual proposals pair up; the root is the member wi
     if (j >= 0 && propose[j] == i) root[i] = nat[i] < nat[j] ? i : j;
   }
 };
+// Directed strength (upwind convection: a row's strongest coefficient points upstream, the
+// upstream row's points further upstream) never produces MUTUAL proposals. Leftover rows are then
+// matched with per-round roles: a hash of (natural index, round) makes every unassigned row either
+// a proposer or an acceptor; proposers pick their strongest acceptor neighbour, an acceptor takes
+// the best of the proposals it received. A row has one role per round, so no chains can form.
+FVM_DEV int pairRole(int nat, int round) { return (int)(hash32((unsigned)nat * 0x9e3779b9U + (unsigned)round * 0x85ebca6bU) & 1U); }
+struct RoleProposeKernel {
+  int n; const int* sliceOff; const int* scol; const double* sval; const double* diag; const int* excluded;
+  const double* strongest; double threshold; const int* root; const int* nat; int round; int* propose;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii, s = i >> 5;
+    int bestJ = -1;
+    if (root[i] < 0 && !(excluded && excluded[i]) && pairRole(nat[i], round) == 1) {
+      const double di = fabs(diag[i]);
+      const double cut = threshold * strongest[i];
+      EdgeKey best;
+      best.w = -1.0f; best.d = 0; best.odd = 0; best.h = 0;
+      const int end = sliceOff[s + 1];
+      for (int p = sliceOff[s] + (i & 31); p < end; p += 32) {
+        const int j = scol[p];
+        if (j >= n || j == i || root[j] >= 0 || (excluded && excluded[j]) || pairRole(nat[j], round) != 0) continue;
+        const double dj = fabs(diag[j]);
+        const double w = fabs(sval[p] / (di > dj ? di : dj));
+        if (!(w > cut) && !(w >= strongest[i])) continue;
+        if (!(w > 0.0)) continue;
+        const EdgeKey k = makeEdgeKey(w, nat[i], nat[j]);
+        if (bestJ < 0 || k.betterThan(best)) { best = k; bestJ = j; }
+      }
+    }
+    propose[i] = bestJ;
+  }
+};
+struct RoleAcceptKernel {  // run over acceptors; writes root of both members (only the acceptor writes its proposer)
+  int n; const int* sliceOff; const int* scol; const double* sval; const int* excluded; const int* propose;
+  const int* nat; int round; int* root;
+  FVM_DEV void operator()(long long jj) const {
+    const int j = (int)jj, s = j >> 5;
+    if (root[j] >= 0 || (excluded && excluded[j]) || pairRole(nat[j], round) != 0) return;
+    int bestI = -1;
+    EdgeKey best;
+    best.w = -1.0f; best.d = 0; best.odd = 0; best.h = 0;
+    const int end = sliceOff[s + 1];
+    for (int p = sliceOff[s] + (j & 31); p < end; p += 32) {
+      const int i = scol[p];
+      if (i >= n || i == j || propose[i] != j) continue;
+      const EdgeKey k = makeEdgeKey(fabs(sval[p]), nat[i], nat[j]);
+      if (bestI < 0 || k.betterThan(best)) { best = k; bestI = i; }
+    }
+    if (bestI >= 0) {
+      const int r = nat[bestI] < nat[j] ? bestI : j;
+      root[j] = r;
+      root[bestI] = r;
+    }
+  }
+};
+struct UnassignedRows {
+  const int* root; const int* excluded;
+  FVM_DEV void operator()(long long i, double* o) const { o[0] = (root[i] < 0 && !(excluded && excluded[i])) ? 1.0 : 0.0; }
+};
+
 struct JoinKernel {  // leftovers join the aggregate of their strongest paired neighbour
   int n; const int* sliceOff; const int* scol; const double* sval; const double* diag; const int* excluded;
   const int* root; int* join;
@@ -489,35 +569,61 @@ struct IotaDblKernel { double* p; FVM_DEV void operator()(long long i) const { p
 // ================================================================= level construction
 // Colour a CSR pattern; returns number of colours, fills colour[] (device)
 static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& colour) {
-  DBuf<int> depth(n), flags(4);
+  DBuf<int> depth(n), qA(n), qB(n), state(4), flags(1);
   depth.fillBytes(0xff);
-  int d = 0, seed = 0;
-  const int big = 0x7fffffff;
   parallelFor(n, BfsIsolatedKernel{n, row, col, depth.p});
-  parallelFor(1, SetIntKernel{depth.p, seed, 0});
-  int rounds = 0, components = 1;
-  for (;;) {
-    int h[4] = {0, 0, big, 0};
-    copyH2D(flags.p, h, sizeof(h));
-    const int burst = rounds < 2 ? 2 : 16;  // look for an odd cycle early: non-bipartite graphs bail out fast
-    for (int k = 0; k < burst; k++) {
-      parallelFor(n, BfsRoundKernel{n, row, col, depth.p, d, flags.p});
-      d++;
-      rounds++;
+  const int big = 0x7fffffff;
+  int d0 = 0;
+  for (int component = 0; component < 32; component++) {
+    int hf = big;
+    copyH2D(flags.p, &hf, sizeof(int));
+    parallelFor(n, MinUnreachedKernel{depth.p, flags.p});
+    flags.download(&hf, 1);
+    if (hf == big) {  // everything reached
+      colour.alloc(n);
+      parallelFor(n, ParityKernel{depth.p, colour.p});
+      return true;
     }
-    parallelFor(n, BfsCheckKernel{n, row, col, depth.p, flags.p});
-    flags.download(h, 4);
-    if (h[1]) return false;              // odd cycle: not bipartite
-    if (h[0]) continue;                  // the front is still moving
-    if (h[2] == big) break;              // everything reached
-    if (++components > 32) return false; // many components: leave it to the general colouring
-    d = (d + 2) & ~1;                    // next component: restart from an even depth
-    parallelFor(1, SetIntKernel{depth.p, h[2], d});
-    if (rounds > 4 * n + 64) return false;
+    const int seed = hf;
+    int hs[4] = {1, 0, 0, d0};
+    copyH2D(state.p, hs, sizeof(hs));
+    copyH2D(qA.p, &seed, sizeof(int));
+    copyH2D(depth.p + seed, &d0, sizeof(int));
+#ifdef FVMGPU_HOSTSIM
+    {
+      int d = d0;
+      int* qin = qA.p; int* qout = qB.p;
+      int* cin = &state.p[0]; int* cout = &state.p[1];
+      while (*cin > 0 && !state.p[2]) {
+        const int m = *cin;
+        for (int idx = 0; idx < m; idx++) bfsExpand(qin[idx], d, n, row, col, depth.p, qout, cout, &state.p[2]);
+        *cin = 0; state.p[3] = d + 1;
+        std::swap(qin, qout); std::swap(cin, cout);
+        d++;
+      }
+      ctx().launches++;
+    }
+#else
+    {
+      static int maxBlocks = 0;
+      if (!maxBlocks) {
+        int perSm = 0;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_bfs_component, 256, 0));
+        maxBlocks = perSm * ctx().smCount;
+      }
+      int nn = n, dd = d0;
+      int* depthP = depth.p; int* a = qA.p; int* b = qB.p; int* st = state.p;
+      void* args[] = {&nn, (void*)&row, (void*)&col, &depthP, &a, &b, &st, &dd};
+      ProfileScope prof("N6fvmgpu15k_bfs_componentE", n);
+      CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_bfs_component, dim3(maxBlocks), dim3(256), args, 0, ctx().stream));
+      ctx().launches++;
+    }
+#endif
+    state.download(hs, 4);
+    if (hs[2]) return false;       // odd cycle: not bipartite
+    d0 = (hs[3] + 2) & ~1;         // next component restarts from an even depth
   }
-  colour.alloc(n);
-  parallelFor(n, ParityKernel{depth.p, colour.p});
-  return true;
+  return false;                    // many components: leave it to the general colouring
 }
 
 static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, std::vector<int>& counts) {
@@ -615,6 +721,19 @@ static bool aggregate(Level& F, const int* excluded, double threshold, DBuf<int>
     parallelFor(n, ProposeKernel{n, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, excluded, strongest.p, threshold,
                                  root.p, F.nat.p, propose.p});
     parallelFor(n, HandshakeKernel{propose.p, F.nat.p, root.p});
+  }
+  {  // directed strength: many rows left without a mutual partner -> role-based matching rounds
+    DBuf<double> cnt(1);
+    reduceRows<1>(n, UnassignedRows{root.p, excluded}, cnt.p);
+    double left = 0;
+    copyD2H(&left, cnt.p, sizeof(double));
+    if (left > 0.1 * n) {
+      for (int r = 0; r < 8; r++) {
+        parallelFor(n, RoleProposeKernel{n, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, excluded, strongest.p, threshold,
+                                         root.p, F.nat.p, r, propose.p});
+        parallelFor(n, RoleAcceptKernel{n, F.sliceOff.p, F.scol.p, F.sval.p, excluded, propose.p, F.nat.p, r, root.p});
+      }
+    }
   }
   parallelFor(n, JoinKernel{n, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, excluded, root.p, join.p});
   parallelFor(n, MergeJoinKernel{join.p, excluded, root.p, isRoot.p});
