@@ -120,8 +120,13 @@ __global__ void __launch_bounds__(256) k_bfs_component(int n, const int* row, co
   int* qin = qA; int* qout = qB;
   int* cin = &state[0]; int* cout = &state[1];
   for (;;) {
+    // read the loop state, THEN synchronise, then decide: the odd-cycle flag is written during the
+    // expansion phase, so a decision taken before every thread has read it would not be uniform
+    // (some threads would leave while the others wait at the barrier)
     const int m = *(volatile int*)cin;
-    if (m == 0 || *(volatile int*)&state[2]) break;
+    const int odd = *(volatile int*)&state[2];
+    grid.sync();
+    if (m == 0 || odd) break;
     for (long long idx = tid; idx < m; idx += nthreads) bfsExpand(qin[idx], d, n, row, col, depth, qout, cout, &state[2]);
     grid.sync();
     if (tid == 0) { *cin = 0; state[3] = d + 1; }
