@@ -55,6 +55,9 @@ def parse():
     # `python -m torch.distributed.run ... bench.py --n 128` as an ambiguous --nnodes/--nproc-per-node)
     p.add_argument("--size", dest="n", type=int, default=0,
                    help="cells per side of the per-GPU hex block (default 256: 256^3 cells per GPU)")
+    p.add_argument("--krylov", action="store_true",
+                   help="NOT the headline: solve with the reference's BCGStab preconditioned by one AMG cycle "
+                        "(F/BCGStab.cpp) instead of stand-alone AMG cycles; both arms honour it")
     p.add_argument("--ref-n", type=int, default=64, help="cells per side of the CPU sample mesh")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-profile", action="store_true")
@@ -119,6 +122,9 @@ def global_dims(n, world):
     return dims
 
 
+KRYLOV = False
+
+
 def build_case(n, lib, rank=0, world=1):
     """Box of uniform cubic hexes (h = 1/n), k = 1, T = 400 on z = top, T = 300 on z = 0, zero flux
     elsewhere, T0 = 300. world > 1: this rank's z-slab of the global mesh, built
@@ -143,6 +149,11 @@ def build_case(n, lib, rank=0, world=1):
     solver.relativeTolerance = REL_TOL
     solver.nMaxIterations = 20000
     solver.verbosity = 0
+    if KRYLOV:
+        top = M.BCGStab()
+        top.preconditioner = solver
+        top.relativeTolerance, top.nMaxIterations, top.verbosity = REL_TOL, 2000, 0
+        solver = top
     model.getOptions().linearSolver = solver
     model.getOptions()["initialTemperature"] = T_INIT
     model.init()
@@ -158,8 +169,12 @@ def device_step(lib, model, mesh, ls, solver):
     model._assemble(ls)
     t_asm = lib.timer_stop(3)
     lib.timer_start(3)
-    dev = solver._device(lib)
-    r0, r, it = dev.solve(ls)
+    if KRYLOV:
+        dev = solver.preconditioner._device(lib)
+        r0, r, it = dev.bcgstab(ls, solver.nMaxIterations, solver.relativeTolerance, solver.absoluteTolerance)
+    else:
+        dev = solver._device(lib)
+        r0, r, it = dev.solve(ls)
     t_solve = lib.timer_stop(3)
     levels = dev.levels()
     dev.cleanup()
@@ -279,9 +294,10 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "3D steady thermal diffusion, %s structured hex mesh (%d cells, %d per GPU), k=1, "
-                               "T=400/300 on z=top/z=0, AMG (V-cycle, multicolour GS, nPre 0 / nPost 1, group 2) "
+                               "T=400/300 on z=top/z=0, %sAMG (V-cycle, multicolour GS, nPre 0 / nPost 1, group 2) "
                                "to rel 1e-8, one outer iteration per step"
-                               % ("x".join(str(d) for d in global_dims(n, world)), ncells * world, ncells),
+                               % ("x".join(str(d) for d in global_dims(n, world)), ncells * world, ncells,
+                                  "BCGStab preconditioned by one cycle of " if KRYLOV else ""),
                    "cells_per_gpu": ncells, "l2": "inputs (>= 1.8 GB of matrix per pass) exceed the 126 MB L2; "
                                                   "L2 flushed between warm-up steps",
                    "parallelism": ("z-slab domain decomposition, one part per GPU, NCCL halo exchange per colour "
@@ -370,7 +386,8 @@ def _ref_worker(n, steps):
             t = refapi.RefThermal(rm)
             t.set_bc(5, "SpecifiedTemperature", specifiedTemperature=T_COLD)
             t.set_bc(6, "SpecifiedTemperature", specifiedTemperature=T_HOT)
-            t.set_solver(refapi.solver_cfg(relativeTolerance=REL_TOL, nMaxIterations=20000, verbosity=0))
+            t.set_solver(refapi.solver_cfg(kind=1 if KRYLOV else 0, relativeTolerance=REL_TOL,
+                                           nMaxIterations=2000 if KRYLOV else 20000, verbosity=0))
             t.set_option("initialTemperature", T_INIT)
             t.init()
             r = t.advance_timed()
@@ -395,7 +412,7 @@ def _ref_worker(n, steps):
 def cpu_sample(n, threads, steps):
     """`threads` independent single-rank processes of the reference, each on its own n^3 mesh."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--_worker", "--ref-n", str(n),
-           "--steps", str(steps)]
+           "--steps", str(steps)] + (["--krylov"] if KRYLOV else [])
     env = dict(os.environ)
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
@@ -442,6 +459,7 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse()
+    KRYLOV = bool(a.krylov)
     if a._worker:
         print(json.dumps(_ref_worker(a.ref_n, a.steps)))
     elif a.impl == "reference":

@@ -138,6 +138,29 @@ __global__ void __launch_bounds__(256) k_bfs_component(int n, const int* row, co
 }
 #endif
 
+// Iterated greedy (Culberson): rebuild the colouring class by class in REVERSE class order; a row takes
+// the smallest colour not held by its already re-coloured neighbours. The rows of an old class are
+// pairwise non-adjacent, so a class is one parallel launch; the number of colours never goes up and
+// usually drops by 1-3 on the coarse levels.
+struct RecolourClassKernel {
+  int n; const int* row; const int* col; int cls; const int* oldColour; int* newColour;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    if (oldColour[i] != cls) return;
+    unsigned long long used = 0ULL;
+    for (int k = row[i]; k < row[i + 1]; k++) {
+      const int j = col[k];
+      if (j >= n || j == i) continue;
+      const int cj = newColour[j];
+      if (cj >= 0) used |= 1ULL << cj;
+    }
+    int c = 0;
+    while ((used >> c) & 1ULL) c++;
+    newColour[i] = c;
+  }
+};
+struct ClampColourKernel { int K; int* colour; FVM_DEV void operator()(long long i) const { if (colour[i] > K) colour[i] = K; } };
+struct RemapColourKernel { const int* remap; int* colour; FVM_DEV void operator()(long long i) const { colour[i] = remap[colour[i]]; } };
 struct ColourCountKernel {
   const int* colour; int* counts;
   FVM_DEV void operator()(long long i) const { atomicAdd(&counts[colour[i]], 1); }
@@ -209,6 +232,19 @@ struct GsRows {  // one colour: rows [rowBegin, rowBegin+count)
     x[r] = -sum / diag[r];
   }
 };
+struct GsRemainderRows {  // remainder class of the hybrid smoother: new values from the OLD x, parked in tmp
+  int rowBegin; const int* sliceOff; const int* scol; const double* sval; const double* diag; const double* b;
+  const double* x; double* tmp;
+  FVM_DEV void operator()(long long t) const {
+    const int r = rowBegin + (int)t;
+    const int s = r >> 5;
+    const int end = sliceOff[s + 1];
+    double sum = b[r];
+    for (int p = sliceOff[s] + (r & 31); p < end; p += 32) sum += sval[p] * x[scol[p]];
+    tmp[r] = -sum / diag[r];
+  }
+};
+struct CopyRangeRows { int rowBegin; const double* src; double* dst; FVM_DEV void operator()(long long t) const { dst[rowBegin + t] = src[rowBegin + t]; } };
 struct GsFirstColourZeroRows {  // first colour of a sweep on x == 0: x_i = -b_i/a_ii, no matrix read
   int rowBegin; const double* diag; const double* b; double* x;
   FVM_DEV void operator()(long long t) const {
@@ -659,11 +695,25 @@ static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, s
     if (rounds > 4096) fail("amg: colouring did not terminate");
   }
   DBuf<int> cnt(64);
-  cnt.zero();
-  parallelFor(n, ColourCountKernel{colour.p, cnt.p});
-  std::vector<int> h = cnt.toHost();
-  int nc = 0;
-  for (int c = 0; c < 64; c++) if (h[c] > 0) nc = c + 1;
+  std::vector<int> h;
+  int nc = 64;
+  // off by default: on the meshes tried it saves 7-9 % of the colour passes but the re-ordered
+  // Gauss-Seidel needed up to 10 % more cycles (hex 40^3: 84 -> 93), a net loss
+  const bool recolour = getenv("FVMGPU_RECOLOUR") && atoi(getenv("FVMGPU_RECOLOUR")) != 0;
+  for (int sweep = 0; sweep < 4; sweep++) {
+    cnt.zero();
+    parallelFor(n, ColourCountKernel{colour.p, cnt.p});
+    h = cnt.toHost();
+    int now = 0;
+    for (int c = 0; c < 64; c++) if (h[c] > 0) now = c + 1;
+    const bool improved = now < nc;
+    nc = now;
+    if (!recolour || sweep == 3 || (sweep > 0 && !improved) || nc <= 2) break;
+    DBuf<int> next(n);
+    next.fillBytes(0xff);
+    for (int c = nc - 1; c >= 0; c--) parallelFor(n, RecolourClassKernel{n, row, col, c, colour.p, next.p});
+    colour = std::move(next);
+  }
   counts.assign(h.begin(), h.begin() + nc);
   return nc;
 }
@@ -676,6 +726,22 @@ static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, c
   std::vector<int> counts;
   DBuf<int> colour;
   L.nColours = colourCsr(n, row, col, colour, counts);
+  L.hybridLast = false;
+  {
+    // Hybrid smoother (opt-in, FVMGPU_HYBRID_COLOURS=K): keep the K largest-priority classes exact and
+    // merge all later (small) classes into one remainder class that is relaxed Jacobi-style among
+    // itself -- the late Jones-Plassmann classes hold a few per cent of the rows but each costs a
+    // full latency-bound pass.
+    int K = 0;
+    if (const char* e = getenv("FVMGPU_HYBRID_COLOURS")) K = atoi(e);
+    if (K >= 2 && L.nColours > K + 1) {
+      parallelFor(n, ClampColourKernel{K, colour.p});
+      for (int c = K + 1; c < L.nColours; c++) counts[K] += counts[c];
+      counts.resize(K + 1);
+      L.nColours = K + 1;
+      L.hybridLast = true;
+    }
+  }
   L.colourStart.assign(L.nColours + 1, 0);
   for (int c = 0; c < L.nColours; c++) L.colourStart[c + 1] = L.colourStart[c] + counts[c];
   // stable partition by colour: invp = rows sorted by colour
@@ -929,7 +995,7 @@ void Amg::setup(System* sys) {
   int passesPerLevel = 1;
   while ((1 << passesPerLevel) < opts.coarseGroupSize) passesPerLevel++;
   if (opts.coarseGroupSize <= 1) passesPerLevel = 0;
-  int mergeRows = 131072;
+  int mergeRows = 262144;
   if (const char* e = getenv("FVMGPU_MERGE_ROWS")) mergeRows = atoi(e);
 
   for (int lvl = 0; lvl < opts.maxCoarseLevels && passesPerLevel > 0; lvl++) {
@@ -1087,11 +1153,15 @@ void Amg::exchange(Level& L, double* x) {
   if (multi) L.halo.exchange(x, 1);
 }
 
-// ================================================================= coarse tail in one CTA
-// All levels below kTailRows rows are latency-bound: a kernel launch per colour costs more than the
-// arithmetic. One 1024-thread CTA therefore runs the whole V-cycle tail (restrict down, smooth,
-// prolong up), with __syncthreads() where the launch boundaries would be. Same operations in the
-// same order as the per-level launches, so the results are bit-identical to them.
+// ================================================================= coarse levels without launches
+// Below ~1 M rows a colour pass is latency-bound: the dependent loads of one row (slice offset ->
+// column/value -> x -> divide) take longer than the pass has work for, and every launch boundary
+// adds its own gap. Two kernels run whole stretches of the V-cycle (restrict down, smooth, prolong
+// up) with a barrier where the launch boundaries would be -- the same operations in the same order
+// as the per-level launches, so the results are bit-identical to them:
+//   k_tail_vcycle   levels with <= kTailRows rows in ONE 1024-thread CTA, __syncthreads() barriers
+//   k_coop_vcycle   levels with <= coopRows rows in one COOPERATIVE grid (one CTA per SM),
+//                   grid.sync() barriers; it hands its last levels to the same code path
 #ifndef FVMGPU_HOSTSIM
 struct TailLevel {
   int n, nColours;
@@ -1102,6 +1172,34 @@ struct TailLevel {
 };
 constexpr int kTailThreads = 1024;
 
+struct CtaSync {   // one CTA
+  __device__ __forceinline__ long long tid() const { return threadIdx.x; }
+  __device__ __forceinline__ long long stride() const { return blockDim.x; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+// Grid-wide barrier for the cooperative kernel: one arrival counter that only grows (zeroed by the
+// host before the launch); the CTA's thread 0 arrives and spins until the whole grid has arrived
+// for this generation. Cheaper than cooperative_groups' grid.sync() (~1.5 us vs ~3.5 us measured
+// per barrier step here), and all CTAs are co-resident by construction (cooperative launch).
+struct GridSync {
+  unsigned* bar;
+  __device__ __forceinline__ long long tid() const { return (long long)blockIdx.x * blockDim.x + threadIdx.x; }
+  __device__ __forceinline__ long long stride() const { return (long long)gridDim.x * blockDim.x; }
+  __device__ __forceinline__ void sync() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned old = atomicAdd(bar, 1u);
+      const unsigned target = (old / gridDim.x + 1u) * gridDim.x;
+      unsigned now;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(bar) : "memory");
+      } while (now < target);
+    }
+    __syncthreads();
+  }
+};
+
 __device__ __forceinline__ double tailRowSum(const TailLevel& L, int r, const double* x) {
   const int s = r >> 5;
   const int end = L.sliceOff[s + 1];
@@ -1109,75 +1207,109 @@ __device__ __forceinline__ double tailRowSum(const TailLevel& L, int r, const do
   for (int p = L.sliceOff[s] + (r & 31); p < end; p += 32) sum += L.sval[p] * x[L.scol[p]];
   return sum;
 }
-__device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& xZero) {
+template <class S>
+__device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& xZero, S& sy) {
   int lastColour = -1;
+  const long long t0 = sy.tid(), st = sy.stride();
   for (int sw = 0; sw < nSweeps; sw++) {
     if (smoother == FVMGPU_SMOOTHER_GAUSS_SEIDEL) {
       for (int pass = 0; pass < 2 * L.nColours; pass++) {
         const int c = pass < L.nColours ? pass : 2 * L.nColours - 1 - pass;
         if (c == lastColour) continue;
         const int r1 = L.colourStart[c + 1];
-        for (int r = L.colourStart[c] + threadIdx.x; r < r1; r += kTailThreads) {
+        for (long long r = L.colourStart[c] + t0; r < r1; r += st) {
           double sum = L.b[r];
-          if (!xZero) sum += tailRowSum(L, r, L.x);
+          if (!xZero) sum += tailRowSum(L, (int)r, L.x);
           L.x[r] = -sum / L.diag[r];
         }
         xZero = false;
         lastColour = c;
-        __syncthreads();
+        sy.sync();
       }
     } else {
       for (int half = 0; half < 2; half++) {
         const double* xo = half ? L.r : L.x;
         double* xn = half ? L.x : L.r;
-        for (int r = threadIdx.x; r < L.n; r += kTailThreads) xn[r] = -(L.b[r] + tailRowSum(L, r, xo)) / L.diag[r];
-        __syncthreads();
+        for (long long r = t0; r < L.n; r += st) xn[r] = -(L.b[r] + tailRowSum(L, (int)r, xo)) / L.diag[r];
+        sy.sync();
       }
       xZero = false;
     }
   }
 }
-__global__ void __launch_bounds__(kTailThreads) k_tail_vcycle(const TailLevel* lv, int nLevels, int nPre, int nPost,
-                                                                int smoother) {
-  // on entry: level 0 of the tail has b set and x == 0
-  for (int l = 0; l < nLevels; l++) {
-    const TailLevel L = lv[l];
-    bool xZero = true;
-    tailSweeps(L, nPre, smoother, xZero);
-    if (l + 1 < nLevels) {
-      const TailLevel C = lv[l + 1];
-      const double* src = L.b;
-      if (!xZero) {  // r = b + A x
-        for (int r = threadIdx.x; r < L.n; r += kTailThreads) {
-          double v = L.b[r] + L.diag[r] * L.x[r];
-          v += tailRowSum(L, r, L.x);
-          L.r[r] = v;
-        }
-        __syncthreads();
-        src = L.r;
-      }
-      for (int I = threadIdx.x; I < C.n; I += kTailThreads) {
-        double s = 0.0;
-        for (int p = L.memOff[I]; p < L.memOff[I + 1]; p++) s += src[L.mem[p]];
-        C.b[I] = s;
-        C.x[I] = 0.0;
-      }
-      __syncthreads();
-    } else {
-      tailSweeps(L, nPost, smoother, xZero);  // coarsest level: pre + post sweeps
-    }
-  }
-  for (int l = nLevels - 2; l >= 0; l--) {
+// levels [l0, l1): pre-sweeps, then restriction of the residual into the next level (which gets x = 0)
+template <class S>
+__device__ void stretchDown(const TailLevel* lv, int l0, int l1, int nPre, int smoother, S& sy) {
+  const long long t0 = sy.tid(), st = sy.stride();
+  for (int l = l0; l < l1; l++) {
     const TailLevel L = lv[l];
     const TailLevel C = lv[l + 1];
-    for (int i = threadIdx.x; i < L.n; i += kTailThreads) {
+    bool xZero = true;
+    tailSweeps(L, nPre, smoother, xZero, sy);
+    const double* src = L.b;
+    if (!xZero) {  // r = b + A x
+      for (long long r = t0; r < L.n; r += st) {
+        double v = L.b[r] + L.diag[r] * L.x[r];
+        v += tailRowSum(L, (int)r, L.x);
+        L.r[r] = v;
+      }
+      sy.sync();
+      src = L.r;
+    }
+    for (long long I = t0; I < C.n; I += st) {
+      double s = 0.0;
+      for (int p = L.memOff[I]; p < L.memOff[I + 1]; p++) s += src[L.mem[p]];
+      C.b[I] = s;
+      C.x[I] = 0.0;
+    }
+    sy.sync();
+  }
+}
+template <class S>
+__device__ void stretchBottom(const TailLevel* lv, int l, int nPre, int nPost, int smoother, S& sy) {
+  const TailLevel L = lv[l];
+  bool xZero = true;
+  tailSweeps(L, nPre, smoother, xZero, sy);
+  tailSweeps(L, nPost, smoother, xZero, sy);  // coarsest level: pre + post sweeps
+}
+// levels l1-1 down to l0: prolongation of the next level's correction, then post-sweeps
+template <class S>
+__device__ void stretchUp(const TailLevel* lv, int l0, int l1, int nPost, int smoother, S& sy) {
+  const long long t0 = sy.tid(), st = sy.stride();
+  for (int l = l1 - 1; l >= l0; l--) {
+    const TailLevel L = lv[l];
+    const TailLevel C = lv[l + 1];
+    for (long long i = t0; i < L.n; i += st) {
       const int c = L.ci[i];
       if (c >= 0) L.x[i] += C.x[c];
     }
-    __syncthreads();
+    sy.sync();
     bool xZero = false;
-    tailSweeps(L, nPost, smoother, xZero);
+    tailSweeps(L, nPost, smoother, xZero, sy);
   }
+}
+// on entry: level 0 of the stretch has b set and x == 0
+__global__ void __launch_bounds__(kTailThreads) k_tail_vcycle(const TailLevel* lv, int nLevels, int nPre, int nPost,
+                                                                int smoother) {
+  CtaSync sy;
+  stretchDown(lv, 0, nLevels - 1, nPre, smoother, sy);
+  stretchBottom(lv, nLevels - 1, nPre, nPost, smoother, sy);
+  stretchUp(lv, 0, nLevels - 1, nPost, smoother, sy);
+}
+// levels [0, nGrid) by the whole grid, levels [nGrid, nLevels) by CTA 0 alone (they have <= kTailRows
+// rows: one CTA is enough and its barrier is __syncthreads())
+__global__ void __launch_bounds__(kTailThreads) k_coop_vcycle(const TailLevel* lv, int nLevels, int nGrid, int nPre,
+                                                                int nPost, int smoother, unsigned* bar) {
+  GridSync gs{bar};
+  stretchDown(lv, 0, nGrid, nPre, smoother, gs);   // ends with a grid barrier after filling level nGrid's b
+  if (blockIdx.x == 0) {
+    CtaSync cs;
+    stretchDown(lv, nGrid, nLevels - 1, nPre, smoother, cs);
+    stretchBottom(lv, nLevels - 1, nPre, nPost, smoother, cs);
+    stretchUp(lv, nGrid, nLevels - 1, nPost, smoother, cs);
+  }
+  gs.sync();
+  stretchUp(lv, 0, nGrid, nPost, smoother, gs);
 }
 #endif
 
@@ -1185,9 +1317,26 @@ void Amg::buildTail() {
   tailStart = -1;
 #ifndef FVMGPU_HOSTSIM
   const int nl = (int)levels.size();
+  int coopRows = 1200000;
+  if (const char* e = getenv("FVMGPU_COOP_ROWS")) coopRows = atoi(e);
   int start = nl;
   while (start > 1 && levels[start - 1]->n <= kTailRows) start--;
+  int cstart = start;
+  while (cstart > 1 && levels[cstart - 1]->n <= coopRows) cstart--;
+  tailIsCoop = cstart < start;   // some levels are too large for one CTA: use the cooperative grid for the stretch
+  if (tailIsCoop) {
+    static int coopOk = -1;
+    if (coopOk < 0) {
+      int perSm = 0, dev = ctx().device, attr = 0;
+      cudaDeviceGetAttribute(&attr, cudaDevAttrCooperativeLaunch, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_coop_vcycle, kTailThreads, 0);
+      coopOk = (attr && perSm >= 1) ? 1 : 0;
+    }
+    if (coopOk) start = cstart; else tailIsCoop = false;
+  }
   if (nl - start < 2) return;  // nothing worth fusing
+  for (int l = start; l < nl; l++)
+    if (levels[l]->hybridLast) return;  // the fused kernels implement the exact multicolour sweep only
   std::vector<TailLevel> h;
   tailColourStarts.clear();
   for (int l = start; l < nl; l++) {
@@ -1208,16 +1357,32 @@ void Amg::buildTail() {
   copyH2D(tailLevels.p, h.data(), h.size() * sizeof(TailLevel));
   tailStart = start;
   tailCount = nl - start;
+  tailGridLevels = 0;
+  if (tailIsCoop) {
+    while (tailGridLevels < tailCount - 1 && levels[start + tailGridLevels]->n > kTailRows) tailGridLevels++;
+    if (!coopBarrier.p) coopBarrier.alloc(4);
+  }
 #endif
 }
 
 void Amg::runTail() {
 #ifndef FVMGPU_HOSTSIM
-  ProfileScope prof("N6fvmgpu13k_tail_vcycleE", levels[tailStart]->n);
-  k_tail_vcycle<<<1, kTailThreads, 0, ctx().stream>>>(reinterpret_cast<const TailLevel*>(tailLevels.p), tailCount,
-                                                      opts.nPreSweeps, opts.nPostSweeps, opts.smootherType);
+  const TailLevel* lv = reinterpret_cast<const TailLevel*>(tailLevels.p);
+  int cnt = tailCount, nPre = opts.nPreSweeps, nPost = opts.nPostSweeps, sm = opts.smootherType;
+  if (tailIsCoop) {
+    ProfileScope prof("N6fvmgpu13k_coop_vcycleE", levels[tailStart]->n);
+    int nGrid = tailGridLevels;
+    unsigned* bar = coopBarrier.p;
+    devMemset(bar, 0, sizeof(unsigned));
+    void* args[] = {(void*)&lv, &cnt, &nGrid, &nPre, &nPost, &sm, &bar};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coop_vcycle, dim3(ctx().smCount), dim3(kTailThreads), args, 0,
+                                           ctx().stream));
+  } else {
+    ProfileScope prof("N6fvmgpu13k_tail_vcycleE", levels[tailStart]->n);
+    k_tail_vcycle<<<1, kTailThreads, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
+    CUDA_CHECK(cudaGetLastError());
+  }
   ctx().launches++;
-  CUDA_CHECK(cudaGetLastError());
   for (int l = tailStart; l < (int)levels.size(); l++) { levels[l]->xZero = false; levels[l]->rValid = false; }
 #endif
 }
@@ -1237,6 +1402,10 @@ void Amg::sweeps(int nSweeps, int lvl) {
         if (c == lastColour) continue;
         const int r0 = L.colourStart[c], cnt = L.colourStart[c + 1] - r0;
         if (L.xZero) parallelFor(cnt, GsFirstColourZeroRows{r0, L.diag.p, L.b.p, L.x.p});
+        else if (L.hybridLast && c == L.nColours - 1) {
+          parallelFor(cnt, GsRemainderRows{r0, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p});
+          parallelFor(cnt, CopyRangeRows{r0, L.r.p, L.x.p});
+        }
         else parallelFor(cnt, GsRows{r0, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p});
         // Ghost values: refreshed after each half-sweep (forward / reverse), i.e. neighbours' rows
         // are lagged by at most one half-sweep -- the reference lags them by a whole sweep

@@ -20,6 +20,7 @@ struct Level {
   // link to the next coarser level (in ITS numbering)
   DBuf<int> ci;              // n: coarse row of each fine row, -1 = not coarsened
   DBuf<int> memOff, mem;     // coarse row -> its fine rows (ascending)
+  bool hybridLast = false;   // the last colour class is a Jacobi-relaxed remainder (hybrid smoother)
   bool xZero = false;        // x is known to be identically zero
   bool rValid = false;       // r holds b + A x for the current x
   // multi-GPU: x and r carry nGhost extra slots (columns >= n of the matrix) filled by the halo
@@ -43,6 +44,9 @@ struct Amg {
   // coarse tail fused into one CTA (levels [tailStart, end) have <= kTailRows rows)
   static constexpr int kTailRows = 4096;
   int tailStart = -1, tailCount = 0;
+  int tailGridLevels = 0;    // leading levels of the stretch worked by the whole grid; the rest by CTA 0
+  DBuf<unsigned> coopBarrier;
+  bool tailIsCoop = false;   // the stretch runs in the cooperative grid kernel (levels up to ~1.2 M rows)
   DBuf<char> tailLevels;
   std::vector<DBuf<int>> tailColourStarts;
   // captured (cycle [+ residual norm]) graphs
