@@ -984,8 +984,9 @@ void Amg::setup(System* sys) {
     L0.gatherHost = m->haloGatherHost;  // ghost columns keep their cell index (>= n)
     L0.halo.buildDev(m->halo.msgs, std::move(scatterDev), ns, L0.gatherHost);
     agreeColours(L0);
+    // the captured cycle contains the NCCL send/recv, all-reduce and all-gather calls (NCCL >= 2.9
+    // supports stream capture); measured on 2 B200s: 7.5 -> 5.35 ms per cycle
     if (const char* e = getenv("FVMGPU_MULTI_GRAPHS")) useGraphs = atoi(e) != 0;
-    else useGraphs = false;
     if (const char* e = getenv("FVMGPU_EXCHANGE_PER_COLOUR")) exchangePerColour = atoi(e) != 0;
   }
   // rows marked as boundary inside the interior range (setDirichlet) are not coarsened
@@ -1159,7 +1160,7 @@ void Amg::exchange(Level& L, double* x) {
 // adds its own gap. Two kernels run whole stretches of the V-cycle (restrict down, smooth, prolong
 // up) with a barrier where the launch boundaries would be -- the same operations in the same order
 // as the per-level launches, so the results are bit-identical to them:
-//   k_tail_vcycle   levels with <= kTailRows rows in ONE 1024-thread CTA, __syncthreads() barriers
+//   k_tail_vcycle   levels with <= kTailRows rows in ONE CTA, __syncthreads() barriers
 //   k_coop_vcycle   levels with <= coopRows rows in one COOPERATIVE grid (one CTA per SM),
 //                   grid.sync() barriers; it hands its last levels to the same code path
 #ifndef FVMGPU_HOSTSIM
@@ -1170,7 +1171,8 @@ struct TailLevel {
   double* b; double* x; double* r;
   const int* ci; const int* memOff; const int* mem;  // links to the next level (null on the last)
 };
-constexpr int kTailThreads = 1024;
+constexpr int kTailThreads = 512;  // default CTA size of the fused kernels (127 registers, no spills);
+                                   // a 1024-thread variant (64 registers, spills) exists for comparison: FVMGPU_FUSED_THREADS=1024
 
 struct CtaSync {   // one CTA
   __device__ __forceinline__ long long tid() const { return threadIdx.x; }
@@ -1207,26 +1209,81 @@ __device__ __forceinline__ double tailRowSum(const TailLevel& L, int r, const do
   for (int p = L.sliceOff[s] + (r & 31); p < end; p += 32) sum += L.sval[p] * x[L.scol[p]];
   return sum;
 }
+// Everything a colour pass needs of its FIRST row except the x values: loaded BEFORE the barrier that
+// ends the previous pass (the matrix, b and diag do not change during a cycle), so that after the
+// barrier only the x gathers are left on the critical path (one dependent load instead of three).
+constexpr int kPrefetch = 6;
+struct RowPrefetch {
+  long long r;       // row, -1 = none
+  int beg, end;      // SELL element range of the row (stride 32)
+  double b, d;
+  int col[kPrefetch];
+  double val[kPrefetch];
+};
+__device__ __forceinline__ void prefetchRow(const TailLevel& L, int c, long long t0, RowPrefetch& P) {
+  P.r = -1;
+  if (c < 0) return;
+  const long long r = L.colourStart[c] + t0;
+  if (r >= L.colourStart[c + 1]) return;
+  P.r = r;
+  const int s = (int)(r >> 5);
+  P.beg = L.sliceOff[s] + (int)(r & 31);
+  P.end = L.sliceOff[s + 1];
+  P.b = L.b[r];
+  P.d = L.diag[r];
+#pragma unroll
+  for (int k = 0; k < kPrefetch; k++) {
+    const int p = P.beg + 32 * k;
+    if (p < P.end) { P.col[k] = L.scol[p]; P.val[k] = L.sval[p]; }
+  }
+}
 template <class S>
 __device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& xZero, S& sy) {
   int lastColour = -1;
   const long long t0 = sy.tid(), st = sy.stride();
-  for (int sw = 0; sw < nSweeps; sw++) {
-    if (smoother == FVMGPU_SMOOTHER_GAUSS_SEIDEL) {
-      for (int pass = 0; pass < 2 * L.nColours; pass++) {
-        const int c = pass < L.nColours ? pass : 2 * L.nColours - 1 - pass;
-        if (c == lastColour) continue;
-        const int r1 = L.colourStart[c + 1];
-        for (long long r = L.colourStart[c] + t0; r < r1; r += st) {
-          double sum = L.b[r];
+  if (smoother == FVMGPU_SMOOTHER_GAUSS_SEIDEL) {
+    // the colour sequence of all sweeps (a pass that would repeat the previous colour is skipped)
+    const int nPass = 2 * L.nColours * nSweeps;
+    auto colourOf = [&](int q) { const int pass = q % (2 * L.nColours); return pass < L.nColours ? pass : 2 * L.nColours - 1 - pass; };
+    RowPrefetch P;
+    P.r = -1;
+    for (int q = 0; q < nPass; q++) {
+      const int c = colourOf(q);
+      if (c == lastColour) continue;
+      const int r1 = L.colourStart[c + 1];
+      long long r = L.colourStart[c] + t0;
+      if (r < r1) {
+        // first row of the pass: use the prefetched pieces when they belong to it
+        double sum, d;
+        if (P.r == r) {
+          sum = P.b; d = P.d;
+          if (!xZero) {
+#pragma unroll
+            for (int k = 0; k < kPrefetch; k++)
+              if (P.beg + 32 * k < P.end) sum += P.val[k] * L.x[P.col[k]];
+            for (int p = P.beg + 32 * kPrefetch; p < P.end; p += 32) sum += L.sval[p] * L.x[L.scol[p]];
+          }
+        } else {
+          sum = L.b[r]; d = L.diag[r];
           if (!xZero) sum += tailRowSum(L, (int)r, L.x);
-          L.x[r] = -sum / L.diag[r];
         }
-        xZero = false;
-        lastColour = c;
-        sy.sync();
+        L.x[r] = -sum / d;
+        for (r += st; r < r1; r += st) {
+          double s2 = L.b[r];
+          if (!xZero) s2 += tailRowSum(L, (int)r, L.x);
+          L.x[r] = -s2 / L.diag[r];
+        }
       }
-    } else {
+      xZero = false;
+      lastColour = c;
+      // next colour of this sweep sequence (if any): fetch its first row's data before the barrier
+      int cn = -1;
+      for (int q2 = q + 1; q2 < nPass; q2++) { const int c2 = colourOf(q2); if (c2 != c) { cn = c2; break; } }
+      prefetchRow(L, cn, t0, P);
+      sy.sync();
+    }
+  } else {
+    for (int sw = 0; sw < nSweeps; sw++) {
       for (int half = 0; half < 2; half++) {
         const double* xo = half ? L.r : L.x;
         double* xn = half ? L.x : L.r;
@@ -1289,8 +1346,9 @@ __device__ void stretchUp(const TailLevel* lv, int l0, int l1, int nPost, int sm
   }
 }
 // on entry: level 0 of the stretch has b set and x == 0
-__global__ void __launch_bounds__(kTailThreads) k_tail_vcycle(const TailLevel* lv, int nLevels, int nPre, int nPost,
-                                                                int smoother) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_tail_vcycle(const TailLevel* lv, int nLevels, int nPre, int nPost,
+                                                           int smoother) {
   CtaSync sy;
   stretchDown(lv, 0, nLevels - 1, nPre, smoother, sy);
   stretchBottom(lv, nLevels - 1, nPre, nPost, smoother, sy);
@@ -1298,8 +1356,9 @@ __global__ void __launch_bounds__(kTailThreads) k_tail_vcycle(const TailLevel* l
 }
 // levels [0, nGrid) by the whole grid, levels [nGrid, nLevels) by CTA 0 alone (they have <= kTailRows
 // rows: one CTA is enough and its barrier is __syncthreads())
-__global__ void __launch_bounds__(kTailThreads) k_coop_vcycle(const TailLevel* lv, int nLevels, int nGrid, int nPre,
-                                                                int nPost, int smoother, unsigned* bar) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_coop_vcycle(const TailLevel* lv, int nLevels, int nGrid, int nPre,
+                                                           int nPost, int smoother, unsigned* bar) {
   GridSync gs{bar};
   stretchDown(lv, 0, nGrid, nPre, smoother, gs);   // ends with a grid barrier after filling level nGrid's b
   if (blockIdx.x == 0) {
@@ -1313,8 +1372,16 @@ __global__ void __launch_bounds__(kTailThreads) k_coop_vcycle(const TailLevel* l
 }
 #endif
 
+#ifndef FVMGPU_HOSTSIM
+static int fusedThreads() {
+  const char* e = getenv("FVMGPU_FUSED_THREADS");
+  return (e && atoi(e) == 1024) ? 1024 : kTailThreads;
+}
+#endif
+
 void Amg::buildTail() {
   tailStart = -1;
+  if (const char* e = getenv("FVMGPU_NO_FUSED")) { if (atoi(e)) return; }
 #ifndef FVMGPU_HOSTSIM
   const int nl = (int)levels.size();
   int coopRows = 1200000;
@@ -1329,7 +1396,7 @@ void Amg::buildTail() {
     if (coopOk < 0) {
       int perSm = 0, dev = ctx().device, attr = 0;
       cudaDeviceGetAttribute(&attr, cudaDevAttrCooperativeLaunch, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_coop_vcycle, kTailThreads, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_coop_vcycle<kTailThreads>, kTailThreads, 0);
       coopOk = (attr && perSm >= 1) ? 1 : 0;
     }
     if (coopOk) start = cstart; else tailIsCoop = false;
@@ -1375,11 +1442,15 @@ void Amg::runTail() {
     unsigned* bar = coopBarrier.p;
     devMemset(bar, 0, sizeof(unsigned));
     void* args[] = {(void*)&lv, &cnt, &nGrid, &nPre, &nPost, &sm, &bar};
-    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coop_vcycle, dim3(ctx().smCount), dim3(kTailThreads), args, 0,
-                                           ctx().stream));
+    if (fusedThreads() == 1024)
+      CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coop_vcycle<1024>, dim3(ctx().smCount), dim3(1024), args, 0, ctx().stream));
+    else
+      CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coop_vcycle<kTailThreads>, dim3(ctx().smCount), dim3(kTailThreads), args, 0,
+                                             ctx().stream));
   } else {
     ProfileScope prof("N6fvmgpu13k_tail_vcycleE", levels[tailStart]->n);
-    k_tail_vcycle<<<1, kTailThreads, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
+    if (fusedThreads() == 1024) k_tail_vcycle<1024><<<1, 1024, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
+    else k_tail_vcycle<kTailThreads><<<1, kTailThreads, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
     CUDA_CHECK(cudaGetLastError());
   }
   ctx().launches++;

@@ -155,3 +155,46 @@ def test_hierarchy_is_rebuilt_when_the_matrix_changes(devlib):
     ds.post_solve_update()
     assert rel_l2(ds.get_field(X.FIELD_X), x1) > 1e-3
     amg.close(); ds.close(); dm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["coop512", "coop1024", "tail_only"])
+def test_fused_vcycle_kernels_are_bit_identical_to_per_level_launches(gpu_lib, variant):
+    """k_coop_vcycle (cooperative grid, levels <= 1.2 M rows) and k_tail_vcycle (one CTA, levels <= 4096
+    rows) run the same operations in the same order as the per-level launches they replace."""
+    import os
+    from fvm_b200 import meshgen as G
+    raw = G.hex_mesh(36, 40, 44, jitter=0.1, seed=4)
+    geo = G.metrics(raw)
+    row, col = G.connectivity(raw)
+    dm = X.DeviceMesh(gpu_lib, 3, raw.n_cells, raw.n_total, raw.face_cells, row, col, raw.group_offset,
+                      raw.group_count, raw.group_id, raw.group_kind)
+    dm.set_geometry(geo["face_area"], geo["face_area_mag"], geo["cell_centroid"], geo["cell_volume"],
+                    ib_type=np.full(raw.n_total, -1, np.int32))
+    env = {"coop512": {}, "coop1024": {"FVMGPU_FUSED_THREADS": "1024"}, "tail_only": {"FVMGPU_COOP_ROWS": "0"}}[variant]
+    out = []
+    for fused in (True, False):
+        for k in ("FVMGPU_NO_FUSED", "FVMGPU_FUSED_THREADS", "FVMGPU_COOP_ROWS"):
+            os.environ.pop(k, None)
+        if fused:
+            os.environ.update(env)
+        else:
+            os.environ["FVMGPU_NO_FUSED"] = "1"
+        ds = X.DeviceSystem(gpu_lib, dm)
+        ds.fill_field(X.FIELD_X, 300.0)
+        ds.set_bc(5, X.BC_DIRICHLET, [300.0])
+        ds.set_bc(6, X.BC_DIRICHLET, [400.0])
+        for g in (1, 2, 3, 4):
+            ds.set_bc(g, X.BC_NEUMANN, [1.0])
+        ds.assemble()
+        o = gpu_lib.default_amg_opts()
+        o.nMaxIterations, o.relativeTolerance = 60, 1e-30
+        amg = X.DeviceAMG(gpu_lib, o)
+        r0, r, it = amg.solve(ds)
+        out.append((ds.get_field(X.FIELD_DELTA), r, amg.history()))
+        amg.close(); ds.close()
+    for k in ("FVMGPU_NO_FUSED", "FVMGPU_FUSED_THREADS", "FVMGPU_COOP_ROWS"):
+        os.environ.pop(k, None)
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+    assert np.array_equal(out[0][2], out[1][2])
+    dm.close()
