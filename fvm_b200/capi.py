@@ -75,6 +75,7 @@ SIGNATURES = {
     "fvmgpu_mesh_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _ip,
                                      C.c_int, _ip, _ip, _ip, _ip]),
     "fvmgpu_mesh_set_geometry": (C.c_int, [_vp, _dp, _dp, _dpn, _dp, _dp, _ipn]),
+    "fvmgpu_mesh_compute_geometry": (C.c_int, [_vp, C.c_int, _dp, _ip, _ip, _dpn, _dpn, _dpn, _dpn, _dpn]),
     "fvmgpu_mesh_set_halo": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _ip, _ip]),
     "fvmgpu_mesh_destroy": (C.c_int, [_vp]),
     "fvmgpu_mesh_download_pair_to_col": (C.c_int, [_vp, _ip]),
@@ -390,6 +391,18 @@ class DeviceMesh:
         _b, ibp = _nullable(ib_type, np.int32)
         self.lib.call("fvmgpu_mesh_set_geometry", self.h, _f64(face_area).reshape(-1), _f64(face_area_mag),
                       fcp, _f64(cell_centroid).reshape(-1), _f64(cell_volume), ibp)
+
+    def compute_geometry(self, nodes, face_node_count, face_nodes):
+        """MeshMetricsCalculator on the device; returns the GeomFields arrays (host copies)."""
+        nodes = _f64(nodes).reshape(-1)
+        off = np.zeros(self.n_faces + 1, np.int32)
+        np.cumsum(_i32(face_node_count), out=off[1:])
+        fa, fam, fc = np.zeros((self.n_faces, 3)), np.zeros(self.n_faces), np.zeros((self.n_faces, 3))
+        cc, cv = np.zeros((self.n_total, 3)), np.zeros(self.n_total)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.lib.call("fvmgpu_mesh_compute_geometry", self.h, len(nodes) // 3, nodes, off, _i32(face_nodes).reshape(-1),
+                      p(fa), p(fam), p(fc), p(cc), p(cv))
+        return dict(face_area=fa, face_area_mag=fam, face_centroid=fc, cell_centroid=cc, cell_volume=cv)
 
     def set_halo(self, peers, scatter_off, scatter_idx, gather_off, gather_idx):
         """StorageSite scatter/gather maps per neighbour rank (F/StorageSite.h:58-84)."""

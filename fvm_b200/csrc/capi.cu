@@ -208,6 +208,15 @@ int fvmgpu_mesh_set_geometry(fvmgpu_mesh_t mesh, const double* faceArea, const d
   meshSetGeometry(M(mesh), faceArea, faceAreaMag, faceCentroid, cellCentroid, cellVolume, ibType);
   API_END
 }
+int fvmgpu_mesh_compute_geometry(fvmgpu_mesh_t mesh, int nNodes, const double* nodeCoords, const int* faceNodeOffsets,
+                                 const int* faceNodes, double* faceArea, double* faceAreaMag, double* faceCentroid,
+                                 double* cellCentroid, double* cellVolume) {
+  API_BEGIN
+  if (!nodeCoords || !faceNodeOffsets || !faceNodes) fail("compute_geometry: null array");
+  meshComputeGeometry(M(mesh), nNodes, nodeCoords, faceNodeOffsets, faceNodes, faceArea, faceAreaMag, faceCentroid,
+                      cellCentroid, cellVolume);
+  API_END
+}
 int fvmgpu_mesh_set_halo(fvmgpu_mesh_t mesh, int nNeigh, const int* peerRank, const int* scatterOff,
                          const int* scatterIdx, const int* gatherOff, const int* gatherIdx) {
   API_BEGIN

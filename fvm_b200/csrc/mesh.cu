@@ -229,6 +229,179 @@ void meshSetGeometry(Mesh* m, const double* faceArea, const double* faceAreaMag,
   m->hasGeometry = true;
 }
 
+// ================================================================= MeshMetricsCalculator on the device
+// face areas (F/MeshMetricsCalculator_impl.h:238-304), area magnitudes (:373-389),
+// face centroids with the non-planar correction (:58-120), cell centroids (:128-236: area-weighted
+// face centroids, boundary ghosts = the face centroid, reflected on symmetry groups) and cell
+// volumes (:392-460: divergence theorem, boundary ghosts = the neighbour's volume). Face loops that
+// scatter into cells are per-cell gathers in ascending face order -- the order in which the
+// reference's face loop reaches a cell -- and the file is compiled with -fmad=false, so the results
+// are bit-identical to the reference's (tests/test_geometry.py).
+struct V3g { double x, y, z; };
+FVM_DEV V3g ldn(const double* a, int i) { return V3g{a[3 * (size_t)i], a[3 * (size_t)i + 1], a[3 * (size_t)i + 2]}; }
+FVM_DEV V3g sub3(V3g a, V3g b) { return V3g{a.x - b.x, a.y - b.y, a.z - b.z}; }
+FVM_DEV V3g add3(V3g a, V3g b) { return V3g{a.x + b.x, a.y + b.y, a.z + b.z}; }
+FVM_DEV V3g scl3(double s, V3g a) { return V3g{s * a.x, s * a.y, s * a.z}; }
+FVM_DEV V3g cross3(V3g a, V3g b) { return V3g{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+FVM_DEV double dotg(V3g a, V3g b) { double s = 0.0; s += a.x * b.x; s += a.y * b.y; s += a.z * b.z; return s; }
+
+struct FaceMetricsKernel {
+  const double* nodes; const int* fnOff; const int* fn; double4* faceGeom; double* fcen;
+  FVM_DEV void operator()(long long ff) const {
+    const int f = (int)ff;
+    const int o = fnOff[f], k = fnOff[f + 1] - o;
+    V3g A = {0.0, 0.0, 0.0};
+    if (k == 2) {
+      const V3g dr = sub3(ldn(nodes, fn[o + 1]), ldn(nodes, fn[o]));
+      A = V3g{dr.y, -dr.x, 0.0};
+    } else if (k == 3) {
+      const V3g p0 = ldn(nodes, fn[o]);
+      A = scl3(0.5, cross3(sub3(ldn(nodes, fn[o + 1]), p0), sub3(ldn(nodes, fn[o + 2]), p0)));
+    } else if (k == 4) {
+      A = scl3(0.5, cross3(sub3(ldn(nodes, fn[o + 2]), ldn(nodes, fn[o])), sub3(ldn(nodes, fn[o + 3]), ldn(nodes, fn[o + 1]))));
+    } else {
+      for (int nn = 0; nn < k; nn++) {
+        const V3g n0 = ldn(nodes, fn[o + nn]), n1 = ldn(nodes, fn[o + (nn + 1) % k]);
+        const V3g xm = scl3(0.5, add3(n1, n0)), dr = sub3(n1, n0);
+        A.x += xm.y * dr.z; A.y += xm.z * dr.x; A.z += xm.x * dr.y;
+      }
+    }
+    const double mag = sqrt(dotg(A, A));
+    V3g c = {0.0, 0.0, 0.0};
+    if (k > 0) {
+      c = ldn(nodes, fn[o]);
+      for (int nn = 1; nn < k; nn++) c = add3(c, ldn(nodes, fn[o + nn]));
+      const double kk = (double)k;
+      c = V3g{c.x / kk, c.y / kk, c.z / kk};
+    }
+    if (k > 3) {  // correction for non-planar quads and polygons
+      const V3g en = {A.x / mag, A.y / mag, A.z / mag};
+      double denom = 0.0;
+      V3g cfc = {0.0, 0.0, 0.0};
+      const double twoThirds = 2. / 3.;
+      for (int nn = 0; nn < k; nn++) {
+        const V3g n0 = ldn(nodes, fn[o + nn]), n1 = ldn(nodes, fn[o + (nn + 1) % k]);
+        const V3g tri = scl3(0.5, cross3(sub3(n0, c), sub3(n1, c)));
+        const double triP = dotg(tri, en);
+        const V3g xm = scl3(0.5, add3(n0, n1));
+        const V3g t = scl3(twoThirds, sub3(xm, c));
+        cfc.x += t.x * triP; cfc.y += t.y * triP; cfc.z += t.z * triP;
+        denom += triP;
+      }
+      c.x += cfc.x / denom; c.y += cfc.y / denom; c.z += cfc.z / denom;
+    }
+    faceGeom[f] = make_double4(A.x, A.y, A.z, mag);
+    fcen[3 * (size_t)f] = c.x; fcen[3 * (size_t)f + 1] = c.y; fcen[3 * (size_t)f + 2] = c.z;
+  }
+};
+struct CellCentroidKernel {
+  int nSelf, nInteriorFaces; const int* row; const int* col; const int* entryFace; const int* faceGroupOf; const int* groupKind;
+  const double4* faceGeom; const double* fcen; double* ccen; int* err;
+  FVM_DEV V3g interior(int c) const {
+    V3g s = {0.0, 0.0, 0.0};
+    double w = 0.0;
+    for (int k = row[c]; k < row[c + 1]; k++) {
+      const int f = entryFace[k] >> 1;
+      const double am = faceGeom[f].w;
+      s.x += fcen[3 * (size_t)f] * am; s.y += fcen[3 * (size_t)f + 1] * am; s.z += fcen[3 * (size_t)f + 2] * am;
+      w += am;
+    }
+    return V3g{s.x / w, s.y / w, s.z / w};
+  }
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    V3g c;
+    if (i < nSelf) {
+      c = interior(i);
+    } else {
+      const int k = row[i];
+      const int f = entryFace[k] >> 1;
+      const int kind = f >= nInteriorFaces ? groupKind[faceGroupOf[f - nInteriorFaces]] : FVMGPU_GROUP_INTERIOR;
+      const V3g fc = ldn(fcen, f);
+      if (kind == FVMGPU_GROUP_SYMMETRY) {
+        const double4 fg = faceGeom[f];
+        const V3g en = {fg.x / fg.w, fg.y / fg.w, fg.z / fg.w};
+        const V3g c0 = interior(col[k]);
+        const V3g dr0 = sub3(fc, c0);
+        const double d = dotg(dr0, en);
+        const V3g dr1 = {dr0.x - 2. * d * en.x, dr0.y - 2. * d * en.y, dr0.z - 2. * d * en.z};
+        c = V3g{c0.x + dr0.x - dr1.x, c0.y + dr0.y - dr1.y, c0.z + dr0.z - dr1.z};
+      } else {
+        if (kind != FVMGPU_GROUP_BOUNDARY) atomicOr(err, 1);  // interface ghosts get their geometry from the partitioner
+        c = fc;
+      }
+    }
+    ccen[3 * (size_t)i] = c.x; ccen[3 * (size_t)i + 1] = c.y; ccen[3 * (size_t)i + 2] = c.z;
+  }
+};
+struct CellVolumeKernel {
+  int nSelf; double dim; const int* row; const int* col; const int* entryFace; const double4* faceGeom; const double* fcen;
+  const double* ccen; double* vol;
+  FVM_DEV double interior(int c) const {
+    const V3g cc = ldn(ccen, c);
+    double v = 0.0;
+    for (int k = row[c]; k < row[c + 1]; k++) {
+      const int ef = entryFace[k];
+      const int f = ef >> 1;
+      const double4 fg = faceGeom[f];
+      const double t = dotg(sub3(ldn(fcen, f), cc), V3g{fg.x, fg.y, fg.z}) / dim;
+      if (ef & 1) v -= t; else v += t;
+    }
+    return v;
+  }
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    vol[i] = i < nSelf ? interior(i) : interior(col[row[i]]);
+  }
+};
+struct PackCellGeomKernel {
+  const double* ccen; const double* vol; double4* out;
+  FVM_DEV void operator()(long long i) const { out[i] = make_double4(ccen[3 * i], ccen[3 * i + 1], ccen[3 * i + 2], vol[i]); }
+};
+struct UnpackFaceGeomKernel {
+  const double4* fg; double* area; double* mag;
+  FVM_DEV void operator()(long long f) const { const double4 g = fg[f]; area[3 * f] = g.x; area[3 * f + 1] = g.y; area[3 * f + 2] = g.z; mag[f] = g.w; }
+};
+
+void meshComputeGeometry(Mesh* m, int nNodes, const double* nodes, const int* faceNodeOffsets, const int* faceNodes,
+                         double* faceArea, double* faceAreaMag, double* faceCentroid, double* cellCentroid,
+                         double* cellVolume) {
+  requireReady();
+  const size_t nf = (size_t)m->nFaces, nt = (size_t)m->nTotal;
+  DBuf<double> dn, fcen(3 * nf), ccen(3 * nt), vol(nt);
+  DBuf<int> dOff, dFn, err(1);
+  dn.upload(nodes, 3 * (size_t)nNodes);
+  dOff.upload(faceNodeOffsets, nf + 1);
+  dFn.upload(faceNodes, (size_t)faceNodeOffsets[nf]);
+  err.zero();
+  m->faceGeom.alloc(nf);
+  m->cellGeom.alloc(nt);
+  parallelFor((long long)nf, FaceMetricsKernel{dn.p, dOff.p, dFn.p, m->faceGeom.p, fcen.p});
+  parallelFor((long long)nt, CellCentroidKernel{m->nSelf, m->nInteriorFaces, m->row.p, m->col.p, m->entryFace.p,
+                                                m->faceGroupOf.p, m->groupKindDev.p, m->faceGeom.p, fcen.p, ccen.p, err.p});
+  parallelFor((long long)nt, CellVolumeKernel{m->nSelf, (double)m->dim, m->row.p, m->col.p, m->entryFace.p, m->faceGeom.p,
+                                              fcen.p, ccen.p, vol.p});
+  parallelFor((long long)nt, PackCellGeomKernel{ccen.p, vol.p, m->cellGeom.p});
+  int e = 0;
+  err.download(&e, 1);
+  if (e) fail("compute_geometry: interface ghost cells take their geometry from the partitioner (use fvmgpu_mesh_set_geometry)");
+  m->gradW.alloc(3 * (size_t)m->nnz);
+  m->gradW.zero();
+  parallelFor(m->nSelf, LsWeightsKernel{m->dim, m->row.p, m->col.p, m->entryFace.p, m->cellGeom.p, m->faceGeom.p,
+                                        m->nnz, m->gradW.p});
+  m->hasGeometry = true;
+  if (faceArea || faceAreaMag) {
+    DBuf<double> a3(3 * nf), am(nf);
+    parallelFor((long long)nf, UnpackFaceGeomKernel{m->faceGeom.p, a3.p, am.p});
+    if (faceArea) a3.download(faceArea, 3 * nf);
+    if (faceAreaMag) am.download(faceAreaMag, nf);
+  }
+  if (faceCentroid) fcen.download(faceCentroid, 3 * nf);
+  if (cellCentroid) ccen.download(cellCentroid, 3 * nt);
+  if (cellVolume) vol.download(cellVolume, nt);
+  streamSync();
+}
+
 void meshSetHalo(Mesh* m, int nNeigh, const int* peerRank, const int* scatterOff, const int* scatterIdx,
                  const int* gatherOff, const int* gatherIdx) {
   requireReady();

@@ -97,6 +97,9 @@ Mesh* meshCreate(int dim, int nSelf, int nTotal, int nFaces, const int* faceCell
                  const int* ccCol, int nGroups, const int* gOff, const int* gCnt, const int* gId, const int* gKind);
 void meshSetGeometry(Mesh* m, const double* faceArea, const double* faceAreaMag, const double* faceCentroid,
                      const double* cellCentroid, const double* cellVolume, const int* ibType);
+void meshComputeGeometry(Mesh* m, int nNodes, const double* nodes, const int* faceNodeOffsets, const int* faceNodes,
+                         double* faceArea, double* faceAreaMag, double* faceCentroid, double* cellCentroid,
+                         double* cellVolume);
 void meshSetHalo(Mesh* m, int nNeigh, const int* peerRank, const int* scatterOff, const int* scatterIdx,
                  const int* gatherOff, const int* gatherIdx);
 System* systemCreate(Mesh* m);

@@ -121,16 +121,29 @@ class MeshMetricsCalculatorA:
     def init(self):
         lib = self.lib or capi.default_lib()
         for m in self.meshes:
-            # a partitioned mesh carries its geometry (interface ghosts = the remote cells' metrics)
-            mt = m.raw.geometry if "geometry" in m.raw else meshgen.metrics(m.raw)
             cells, faces = m.getCells(), m.getFaces()
+            raw = m.raw
+            dm = capi.DeviceMesh(lib, m.dim, raw.n_cells, raw.n_total, raw.face_cells, m.cc_row, m.cc_col,
+                                 raw.group_offset, raw.group_count, raw.group_id, m.group_kinds())
+            ib = np.full(cells.getCount(), -1, np.int32)  # IBTYPE_FLUID
+            if "geometry" in raw:
+                # a partitioned mesh carries its geometry (interface ghosts = the remote cells' metrics)
+                mt = raw.geometry
+                dm.set_geometry(mt["face_area"], mt["face_area_mag"], mt["cell_centroid"], mt["cell_volume"],
+                                face_centroid=mt["face_centroid"], ib_type=ib)
+            else:
+                # face areas / centroids, cell centroids / volumes computed on the device from the nodes
+                mt = dm.compute_geometry(raw.nodes, raw.face_node_count, raw.face_nodes)
             self.geom.area[faces] = mt["face_area"]
             self.geom.areaMag[faces] = mt["face_area_mag"]
             self.geom.coordinate[faces] = mt["face_centroid"]
             self.geom.coordinate[cells] = mt["cell_centroid"]
             self.geom.volume[cells] = mt["cell_volume"]
-            self.geom.ibType[cells] = np.full(cells.getCount(), -1, np.int32)  # IBTYPE_FLUID
-            upload_mesh(lib, m, self.geom)
+            self.geom.ibType[cells] = ib
+            if "halo" in raw:  # StorageSite scatter/gather maps of a partitioned mesh
+                h = raw.halo
+                dm.set_halo(h["peers"], h["scatter_off"], h["scatter_idx"], h["gather_off"], h["gather_idx"])
+            m.device = dm
 
 
 def upload_mesh(lib, m, geom):

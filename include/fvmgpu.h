@@ -139,6 +139,15 @@ int fvmgpu_mesh_create(fvmgpu_mesh_t* out, int dim, int nCellsSelf, int nCellsTo
 int fvmgpu_mesh_set_geometry(fvmgpu_mesh_t mesh, const double* faceArea, const double* faceAreaMag,
                              const double* faceCentroid, const double* cellCentroid,
                              const double* cellVolume, const int* ibType);
+/* MeshMetricsCalculator<T>::init on the device (F/MeshMetricsCalculator_impl.h:58-120, 128-236, 238-304,
+ * 373-389, 392-460): face areas / magnitudes / centroids, cell centroids and volumes from the node
+ * coordinates and the face-node connectivity (CSR: faceNodeOffsets[nFaces+1], faceNodes), installed in
+ * the mesh exactly like fvmgpu_mesh_set_geometry (incl. the gradient weights) and copied to the host
+ * arrays that are not NULL (the GeomFields arrays of the reference). Unpartitioned meshes only:
+ * interface ghosts take the remote cell's geometry from the partitioner. */
+int fvmgpu_mesh_compute_geometry(fvmgpu_mesh_t mesh, int nNodes, const double* nodeCoords, const int* faceNodeOffsets,
+                                 const int* faceNodes, double* faceArea, double* faceAreaMag, double* faceCentroid,
+                                 double* cellCentroid, double* cellVolume);
 /* StorageSite scatter/gather maps per neighbour rank (F/StorageSite.h:58-84); CSR-style offsets */
 int fvmgpu_mesh_set_halo(fvmgpu_mesh_t mesh, int nNeigh, const int* peerRank, const int* scatterOff,
                          const int* scatterIdx, const int* gatherOff, const int* gatherIdx);
