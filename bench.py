@@ -134,7 +134,7 @@ def build_case(n, lib, rank=0, world=1):
         raw = G.hex_mesh(n, n, n)
     else:
         nx, ny, nz = global_dims(n, world)
-        raw = P.hex_slab(nx, ny, nz, rank, world, nx / n, ny / n, nz / n)
+        raw = P.hex_slab(nx, ny, nz, rank, world, nx / n, ny / n, nz / n, lib=lib)
     meshes = [M.Mesh(raw)]
     geom = M.GeomFields("geom")
     M.MeshMetricsCalculatorA(geom, meshes, lib=lib).init()

@@ -102,6 +102,10 @@ SIGNATURES = {
     "fvmgpu_solver_history": (C.c_int, [_vp, C.c_int, _dp, C.POINTER(C.c_int)]),
     "fvmgpu_bcgstab_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "fvmgpu_cg_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
+                                  C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "fvmgpu_jacobi_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "fvmgpu_post_solve_update": (C.c_int, [_vp]),
     "fvmgpu_electric_field": (C.c_int, [_vp, _dpn]),
     "fvmgpu_electric_drift_flux": (C.c_int, [_vp, _vp, C.c_double, C.c_double, C.c_int, _ip, _dpn]),
@@ -537,6 +541,20 @@ class DeviceAMG:
         self.lib.call("fvmgpu_bcgstab_solve", self.h, system.h, int(n_max_iterations),
                       float(relative_tolerance), float(absolute_tolerance), C.byref(r0), C.byref(r),
                       C.byref(it))
+        return r0.value, r.value, it.value
+
+    def cg(self, system, n_max_iterations, relative_tolerance, absolute_tolerance):
+        """CG preconditioned by one cycle of this AMG (F/CG.cpp:24-140)"""
+        r0, r, it = C.c_double(0), C.c_double(0), C.c_int(0)
+        self.lib.call("fvmgpu_cg_solve", self.h, system.h, int(n_max_iterations), float(relative_tolerance),
+                      float(absolute_tolerance), C.byref(r0), C.byref(r), C.byref(it))
+        return r0.value, r.value, it.value
+
+    def jacobi(self, system, n_max_iterations, relative_tolerance, absolute_tolerance):
+        """JacobiSolver::solve (F/JacobiSolver.cpp:46-95)"""
+        r0, r, it = C.c_double(0), C.c_double(0), C.c_int(0)
+        self.lib.call("fvmgpu_jacobi_solve", self.h, system.h, int(n_max_iterations), float(relative_tolerance),
+                      float(absolute_tolerance), C.byref(r0), C.byref(r), C.byref(it))
         return r0.value, r.value, it.value
 
     def levels(self):

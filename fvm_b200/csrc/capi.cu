@@ -386,6 +386,18 @@ int fvmgpu_bcgstab_solve(fvmgpu_solver_t precond, fvmgpu_system_t sys, int nMaxI
   A(precond)->bcgstab(S(sys), nMaxIterations, relativeTolerance, absoluteTolerance, rnorm0, rnorm, iters);
   API_END
 }
+int fvmgpu_cg_solve(fvmgpu_solver_t precond, fvmgpu_system_t sys, int nMaxIterations, double relativeTolerance,
+                    double absoluteTolerance, double* rnorm0, double* rnorm, int* iters) {
+  API_BEGIN
+  A(precond)->cg(S(sys), nMaxIterations, relativeTolerance, absoluteTolerance, rnorm0, rnorm, iters);
+  API_END
+}
+int fvmgpu_jacobi_solve(fvmgpu_solver_t s, fvmgpu_system_t sys, int nMaxIterations, double relativeTolerance,
+                        double absoluteTolerance, double* rnorm0, double* rnorm, int* iters) {
+  API_BEGIN
+  A(s)->jacobiSolve(S(sys), nMaxIterations, relativeTolerance, absoluteTolerance, rnorm0, rnorm, iters);
+  API_END
+}
 int fvmgpu_system_halo_exchange(fvmgpu_system_t sys, int field) {
   API_BEGIN
   systemHaloExchange(S(sys), field);

@@ -1202,10 +1202,11 @@ struct GridSync {
   }
 };
 
-__device__ __forceinline__ double tailRowSum(const TailLevel& L, int r, const double* x) {
+// init + sum_j a_rj x_j accumulated in entry order, exactly like GsRows / JacobiRows / ResidualRows
+__device__ __forceinline__ double tailRowAcc(const TailLevel& L, int r, const double* x, double init) {
   const int s = r >> 5;
   const int end = L.sliceOff[s + 1];
-  double sum = 0.0;
+  double sum = init;
   for (int p = L.sliceOff[s] + (r & 31); p < end; p += 32) sum += L.sval[p] * x[L.scol[p]];
   return sum;
 }
@@ -1265,12 +1266,12 @@ __device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& 
           }
         } else {
           sum = L.b[r]; d = L.diag[r];
-          if (!xZero) sum += tailRowSum(L, (int)r, L.x);
+          if (!xZero) sum = tailRowAcc(L, (int)r, L.x, sum);
         }
         L.x[r] = -sum / d;
         for (r += st; r < r1; r += st) {
           double s2 = L.b[r];
-          if (!xZero) s2 += tailRowSum(L, (int)r, L.x);
+          if (!xZero) s2 = tailRowAcc(L, (int)r, L.x, s2);
           L.x[r] = -s2 / L.diag[r];
         }
       }
@@ -1287,7 +1288,7 @@ __device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& 
       for (int half = 0; half < 2; half++) {
         const double* xo = half ? L.r : L.x;
         double* xn = half ? L.x : L.r;
-        for (long long r = t0; r < L.n; r += st) xn[r] = -(L.b[r] + tailRowSum(L, (int)r, xo)) / L.diag[r];
+        for (long long r = t0; r < L.n; r += st) xn[r] = -tailRowAcc(L, (int)r, xo, L.b[r]) / L.diag[r];
         sy.sync();
       }
       xZero = false;
@@ -1306,9 +1307,7 @@ __device__ void stretchDown(const TailLevel* lv, int l0, int l1, int nPre, int s
     const double* src = L.b;
     if (!xZero) {  // r = b + A x
       for (long long r = t0; r < L.n; r += st) {
-        double v = L.b[r] + L.diag[r] * L.x[r];
-        v += tailRowSum(L, (int)r, L.x);
-        L.r[r] = v;
+        L.r[r] = tailRowAcc(L, (int)r, L.x, L.b[r] + L.diag[r] * L.x[r]);
       }
       sy.sync();
       src = L.r;
@@ -1744,6 +1743,101 @@ void Amg::bcgstab(System* sys, int nMaxIterations, double relTol, double absTol,
     exchange(L0, L0.x.p);
     copyD2D(sys->delta.p + n, L0.x.p + n, ng * sizeof(double));
   }
+  if (rnorm0Out) *rnorm0Out = rNorm0;
+  if (rnormOut) *rnormOut = rNorm;
+  if (itersOut) *itersOut = iters;
+}
+
+// CG::solve, F/CG.cpp:24-140: conjugate gradients preconditioned by one AMG cycle from a zero guess
+// (preconditioner->smooth on (delta := z = 0, b := r)). Sign convention of the library: r = b + A x,
+// the cycle solves A z + r = 0, so x -= alpha p and r -= alpha q exactly as the reference's msaxpy calls.
+struct ScaleAddRows {  // p = p * (num/den) + z
+  const double* num; const double* den; const double* z; double* p;
+  FVM_DEV void operator()(long long i) const { p[i] = p[i] * (num[0] / den[0]) + z[i]; }
+};
+void Amg::cg(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0Out, double* rnormOut,
+             int* itersOut) {
+  requireReady();
+  ensureSetup(sys);
+  history.clear();
+  Level& L0 = *levels[0];
+  const int n = L0.n;
+  const size_t ng = (size_t)L0.nGhost;
+  DBuf<double> x(n + ng), bOrig(n), r(n), z(n + ng), p(n + ng), q(n);
+  parallelFor(n, PermGatherKernel{perm0.p, sys->b.p, bOrig.p});
+  parallelFor(n, PermGatherKernel{perm0.p, sys->delta.p, x.p});
+  if (ng) { copyD2D(x.p + n, sys->delta.p + n, ng * sizeof(double)); exchange(L0, x.p); }
+  auto allreduce = [&](double* ptr, int cnt) { if (multi) commAllreduceSum(ptr, cnt); };
+  double* S = scalars.p;  // S[0]=rho S[1]=rhoPrev S[2]=p.q S[6]=|r|_1
+  reduceRows<1>(n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, bOrig.p, x.p, r.p}, S + 6);
+  allreduce(S + 6, 1);
+  double rNorm0;
+  copyD2H(&rNorm0, S + 6, sizeof(double));
+  history.push_back(rNorm0);
+  double rNorm = rNorm0;
+  int iters = 0;
+  bool haveP = false;
+  for (int i = 0; i < nMaxIterations; i++) {
+    iters++;
+    precondition(r.p, z.p);                                     // z = M(r)
+    copyD2D(S + 1, S + 0, sizeof(double));                      // rhoPrev = rho
+    reduceRows<1>(n, Dot1Rows{r.p, z.p}, S + 0);                // rho = r . z
+    allreduce(S + 0, 1);
+    if (!haveP) { copyD2D(p.p, z.p, (size_t)n * sizeof(double)); haveP = true; }
+    else parallelFor(n, ScaleAddRows{S + 0, S + 1, z.p, p.p});  // p = p * (rho/rhoPrev) + z
+    if (ng) exchange(L0, p.p);
+    { MultiplyRows m{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, p.p, q.p}; parallelFor(n, m); }  // q = A p
+    reduceRows<1>(n, Dot1Rows{p.p, q.p}, S + 2);
+    allreduce(S + 2, 1);
+    parallelFor(n, MsaxpyScalarPtr{S + 0, S + 2, p.p, x.p});    // x -= alpha p, alpha = rho / p.q
+    reduceRows<1>(n, MsaxpyScalarPtr{S + 0, S + 2, q.p, r.p}, S + 6);  // r -= alpha q ; |r|_1
+    allreduce(S + 6, 1);
+    copyD2H(&rNorm, S + 6, sizeof(double));
+    history.push_back(rNorm);
+    if (rNorm < absTol || rNorm / rNorm0 < relTol) break;
+  }
+  totalIterations += iters;
+  parallelFor(n, PermScatterKernel{perm0.p, x.p, sys->delta.p});
+  if (ng) {
+    copyD2D(L0.x.p, x.p, (size_t)n * sizeof(double));
+    exchange(L0, L0.x.p);
+    copyD2D(sys->delta.p + n, L0.x.p + n, ng * sizeof(double));
+  }
+  if (rnorm0Out) *rnorm0Out = rNorm0;
+  if (rnormOut) *rnormOut = rNorm;
+  if (itersOut) *itersOut = iters;
+}
+
+// JacobiSolver::solve, F/JacobiSolver.cpp:46-95: one Jacobi pass (F/CRMatrix.h:353-374) per iteration,
+// convergence on the residual 1-norm. Needs level 0 only (maxCoarseLevels is ignored: no coarsening).
+void Amg::jacobiSolve(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0Out,
+                      double* rnormOut, int* itersOut) {
+  requireReady();
+  const int keep = opts.maxCoarseLevels;
+  opts.maxCoarseLevels = 0;
+  ensureSetup(sys);
+  opts.maxCoarseLevels = keep;
+  history.clear();
+  loadSystem(sys, sys->b.p, sys->delta.p);
+  Level& L0 = *levels[0];
+  L0.xZero = false;
+  const double rNorm0 = residualNorm(0);
+  history.push_back(rNorm0);
+  double rNorm = rNorm0;
+  int iters = 0;
+  if (!(rNorm0 < absTol)) {
+    for (int i = 1; i < nMaxIterations; i++) {
+      parallelFor(L0.n, JacobiRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, L0.b.p, L0.x.p, L0.r.p});
+      copyD2D(L0.x.p, L0.r.p, (size_t)L0.n * sizeof(double));
+      exchange(L0, L0.x.p);
+      iters++;
+      rNorm = residualNorm(0);
+      history.push_back(rNorm);
+      if (rNorm < absTol || rNorm / rNorm0 < relTol) break;
+    }
+  }
+  totalIterations += iters;
+  storeDelta(sys->delta.p);
   if (rnorm0Out) *rnorm0Out = rNorm0;
   if (rnormOut) *rnormOut = rNorm;
   if (itersOut) *itersOut = iters;

@@ -74,6 +74,9 @@ struct Amg {
   void smooth(System* sys);
   void bcgstab(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0, double* rnorm,
                int* iters);
+  void cg(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0, double* rnorm, int* iters);
+  void jacobiSolve(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0, double* rnorm,
+                   int* iters);
 
   void sweeps(int nSweeps, int lvl);
   void residual(int lvl);

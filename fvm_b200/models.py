@@ -351,6 +351,65 @@ class BCGStab(LinearSolver):
         return self._totalIterations
 
 
+class CG(LinearSolver):
+    """F/CG.h, F/CG.cpp:24-140: conjugate gradients, `preconditioner` must be an AMG (one cycle per
+    application). For symmetric systems (pure diffusion)."""
+
+    def __init__(self):
+        super().__init__()
+        self.preconditioner = None
+        self._totalIterations = 0
+        self.lastIterations = 0
+
+    def solve(self, ls):
+        if self.preconditioner is None:
+            raise CException("CG: no preconditioner set")
+        dev = self.preconditioner._device(ls.lib)
+        r0, r, it = dev.cg(ls, self.nMaxIterations, self.relativeTolerance, self.absoluteTolerance)
+        self._totalIterations += it
+        self.lastIterations = it
+        self.lastResidual = r
+        if self.verbosity > 0:
+            print("0: [%s : %g]" % (ls.field_name, r0))
+            print("%d: [%s : %g]" % (it, ls.field_name, r))
+        return r0
+
+    def smooth(self, ls):
+        raise CException("cannot use CG as preconditioner")  # F/CG.cpp:142-146
+
+    def cleanup(self):
+        if self.preconditioner is not None:
+            self.preconditioner.cleanup()
+
+    def getTotalIterations(self):
+        return self._totalIterations
+
+
+class JacobiSolver(LinearSolver):
+    """F/JacobiSolver.h, F/JacobiSolver.cpp:46-95: plain Jacobi iterations on the finest level."""
+
+    def __init__(self):
+        super().__init__()
+        self._amg = AMG()
+        self.lastIterations = 0
+
+    def solve(self, ls):
+        dev = self._amg._device(ls.lib)
+        r0, r, it = dev.jacobi(ls, self.nMaxIterations, self.relativeTolerance, self.absoluteTolerance)
+        self.lastIterations = it
+        self.lastResidual = r
+        if self.verbosity > 0:
+            print("0: [%s : %g]" % (ls.field_name, r0))
+            print("%d: [%s : %g]" % (it, ls.field_name, r))
+        return r0
+
+    def smooth(self, ls):
+        raise CException("JacobiSolver.smooth: use AMG with smootherType = JACOBI as a preconditioner")
+
+    def cleanup(self):
+        self._amg.cleanup()
+
+
 class LinearSystem(capi.DeviceSystem):
     """Device LinearSystem (F/LinearSystem.h:11-64) tagged with the field name used in prints."""
 

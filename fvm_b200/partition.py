@@ -167,9 +167,11 @@ def partition_mesh(raw, geo, part, rank, group_types=None):
     return m
 
 
-def hex_slab(nx, ny, nz, rank, nparts, lx=1.0, ly=1.0, lz=1.0):
+def hex_slab(nx, ny, nz, rank, nparts, lx=1.0, ly=1.0, lz=1.0, lib=None):
     """Local mesh of z-slab `rank` of the uniform nx x ny x nz hex box, built without the global
-    mesh. Identical (arrays and numbering) to partition_mesh(hex_mesh(nx,ny,nz), assign_slabs)."""
+    mesh. Identical (arrays and numbering) to partition_mesh(hex_mesh(nx,ny,nz), assign_slabs).
+    With `lib` (a loaded libfvmgpu) the slab's metrics are computed on the device
+    (fvmgpu_mesh_compute_geometry) instead of by the numpy restatement."""
     bounds = (np.arange(nparts + 1, dtype=np.int64) * (nx * ny * nz)) // nparts
     if np.any(bounds % (nx * ny)):
         raise ValueError("hex_slab: nz*%d must split into whole z-layers per part" % nparts)
@@ -178,7 +180,15 @@ def hex_slab(nx, ny, nz, rank, nparts, lx=1.0, ly=1.0, lz=1.0):
     hz = lz / nz
     loc = meshgen.hex_mesh(nx, ny, nzl, lx, ly, hz * nzl)
     loc.nodes[:, 2] += k0 * hz
-    geo = meshgen.metrics(loc)
+    if lib is None:
+        geo = meshgen.metrics(loc)
+    else:
+        from . import capi
+        row, col = meshgen.connectivity(loc)
+        tmp = capi.DeviceMesh(lib, 3, loc.n_cells, loc.n_total, loc.face_cells, row, col, loc.group_offset,
+                              loc.group_count, loc.group_id, loc.group_kind)
+        geo = tmp.compute_geometry(loc.nodes, loc.face_node_count, loc.face_nodes)
+        tmp.close()
     lower, upper = rank > 0, rank < nparts - 1
     # hex_mesh groups: 0 interior, 1..4 sides, 5 z-, 6 z+ ; reference order: boundaries, then interfaces by peer id
     order = [0, 1, 2, 3, 4] + ([] if lower else [5]) + ([] if upper else [6]) + ([5] if lower else []) + ([6] if upper else [])

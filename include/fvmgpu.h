@@ -204,6 +204,15 @@ int fvmgpu_solver_history(fvmgpu_solver_t s, int cap, double* out, int* n);
 int fvmgpu_bcgstab_solve(fvmgpu_solver_t precond, fvmgpu_system_t sys, int nMaxIterations,
                          double relativeTolerance, double absoluteTolerance, double* rnorm0,
                          double* rnorm, int* iters);
+/* CG::solve (F/CG.cpp:24-140): conjugate gradients preconditioned by one AMG cycle of `precond` */
+int fvmgpu_cg_solve(fvmgpu_solver_t precond, fvmgpu_system_t sys, int nMaxIterations,
+                    double relativeTolerance, double absoluteTolerance, double* rnorm0, double* rnorm,
+                    int* iters);
+/* JacobiSolver::solve (F/JacobiSolver.cpp:46-95): Jacobi passes on the finest level only; `s` is any
+ * solver handle (its hierarchy is not used) */
+int fvmgpu_jacobi_solve(fvmgpu_solver_t s, fvmgpu_system_t sys, int nMaxIterations,
+                        double relativeTolerance, double absoluteTolerance, double* rnorm0, double* rnorm,
+                        int* iters);
 /* LinearSystem::postSolve + updateSolution (F/LinearSystem.cpp:250-269): back-substitute the
  * eliminated boundary rows, solve the boundary-flux rows, x += delta, flux += dflux */
 int fvmgpu_post_solve_update(fvmgpu_system_t sys);

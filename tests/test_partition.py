@@ -25,6 +25,12 @@ def test_direct_slab_mesh_equals_partition_of_the_global_mesh(nparts):
             assert np.array_equal(a.halo[k], b.halo[k]), k
 
 
+def test_direct_slab_mesh_with_device_geometry(hostsim_lib):
+    a, b = P.hex_slab(5, 4, 12, 1, 3), P.hex_slab(5, 4, 12, 1, 3, lib=hostsim_lib)
+    for k in a.geometry:
+        assert np.allclose(a.geometry[k], b.geometry[k], atol=1e-14), k
+
+
 def test_numbering_follows_the_reference_partitioner():
     raw = G.tet_mesh(4, 3, 5)
     geo = G.metrics(raw)

@@ -35,7 +35,7 @@ def test_mm226_default_options(devlib):
     amg.close(); ds.close()
 
 
-@pytest.mark.parametrize("variant", ["v_gs", "w_gs", "f_gs", "pre_post", "jacobi", "group4", "bcgstab"])
+@pytest.mark.parametrize("variant", ["v_gs", "w_gs", "f_gs", "pre_post", "jacobi", "group4", "bcgstab", "jacobi_solver"])
 def test_mm226_converged_solution(devlib, variant):
     g = load_golden("mm226.npz")
     ds = mm226_system(devlib, g)
@@ -54,6 +54,8 @@ def test_mm226_converged_solution(devlib, variant):
     amg = X.DeviceAMG(devlib, o)
     if variant == "bcgstab":
         r0, r, it = amg.bcgstab(ds, 200, 1e-13, 1e-50)
+    elif variant == "jacobi_solver":   # F/JacobiSolver.cpp: slow but convergent on this diagonally dominant system
+        r0, r, it = amg.jacobi(ds, 200000, 1e-13, 1e-50)
     else:
         r0, r, it = amg.solve(ds)
     assert r / r0 < 1e-13, (variant, it, r / r0)
@@ -198,3 +200,18 @@ def test_fused_vcycle_kernels_are_bit_identical_to_per_level_launches(gpu_lib, v
     assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
     assert np.array_equal(out[0][2], out[1][2])
     dm.close()
+
+
+def test_cg_on_the_symmetric_thermal_system(devlib):
+    """CG preconditioned by one AMG cycle (F/CG.cpp): the cav32 conduction matrix is symmetric."""
+    g = load_golden("cav32.npz")
+    dm, ds = thermal_system(devlib, g, {3: (X.BC_DIRICHLET, [400.0]), 4: (X.BC_DIRICHLET, [0.0]),
+                                        5: (X.BC_DIRICHLET, [0.0]), 6: (X.BC_DIRICHLET, [0.0])})
+    ds.assemble()
+    o = devlib.default_amg_opts()
+    amg = X.DeviceAMG(devlib, o)
+    r0, r, it = amg.cg(ds, 200, 1e-13, 1e-50)
+    assert r / r0 < 1e-13 and it < 40
+    ds.post_solve_update()
+    assert rel_l2(ds.get_field(X.FIELD_X), g["ref_x"]) <= SOL_TOL
+    amg.close(); ds.close(); dm.close()
