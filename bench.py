@@ -58,7 +58,9 @@ def parse():
     p.add_argument("--krylov", action="store_true",
                    help="NOT the headline: solve with the reference's BCGStab preconditioned by one AMG cycle "
                         "(F/BCGStab.cpp) instead of stand-alone AMG cycles; both arms honour it")
-    p.add_argument("--ref-n", type=int, default=64, help="cells per side of the CPU sample mesh")
+    p.add_argument("--ref-n", type=int, default=0,
+                   help="cells per side of the CPU sample mesh (default: 128 for --impl reference, 96 for the "
+                        "cpu_baseline leg of the GPU arm)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-profile", action="store_true")
     p.add_argument("--_worker", action="store_true", help=argparse.SUPPRESS)
@@ -280,7 +282,7 @@ def run_ours(args):
     # ---- cpu baseline
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu = cpu_sample(args.ref_n, threads=1, steps=1)
+        cpu = cpu_sample(args.ref_n or 96, threads=1, steps=1)   # ~15 s of single-core reference work
     if rank != 0:
         return
     ms_per_step = total_ms / args.steps
@@ -441,10 +443,12 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n = args.ref_n
+    # bounded sample: the reference needs O(n) more cycles per doubling of the mesh (165 at 64^3, ~330 at
+    # 128^3, ~700 at 256^3), so the sample is taken as large as a few minutes allow (128^3, <= 2 steps)
+    n = args.ref_n or 128
     for _ in range(min(args.warmup, 1)):
         cpu_sample(min(n, 32), threads, 1)
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 2))
     cpu = cpu_sample(n, threads, steps)
     out = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": cpu["seconds_per_step"] * 1e3,

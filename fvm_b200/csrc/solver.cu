@@ -159,6 +159,21 @@ struct RecolourClassKernel {
     newColour[i] = c;
   }
 };
+// sort key of a row: 2*colour + (0 if the row has a halo column, else 1): inside a colour the rows the
+// other ranks need (and that need the other ranks) come first, so that a pass can run them apart
+// from the interior rows and overlap the halo exchange with the latter
+struct IfaceKeyKernel {
+  int n; const int* row; const int* col; const int* ghostIsHalo; int* colour;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    int iface = 0;
+    for (int k = row[i]; k < row[i + 1]; k++) {
+      const int j = col[k];
+      if (j >= n && (!ghostIsHalo || ghostIsHalo[j - n])) { iface = 1; break; }
+    }
+    colour[i] = 2 * colour[i] + (iface ? 0 : 1);
+  }
+};
 struct ClampColourKernel { int K; int* colour; FVM_DEV void operator()(long long i) const { if (colour[i] > K) colour[i] = K; } };
 struct RemapColourKernel { const int* remap; int* colour; FVM_DEV void operator()(long long i) const { colour[i] = remap[colour[i]]; } };
 struct ColourCountKernel {
@@ -720,7 +735,8 @@ static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, s
 
 // Build level L from a CSR system in "natural" numbering; returns perm (natural -> level numbering).
 static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, const double* val,
-                              const double* diag, bool dropGhost, DBuf<int>& perm, int nGhost = 0) {
+                              const double* diag, bool dropGhost, DBuf<int>& perm, int nGhost = 0,
+                              bool splitIface = false, const int* ghostIsHalo = nullptr) {
   L.n = n;
   L.nGhost = dropGhost ? 0 : nGhost;
   std::vector<int> counts;
@@ -744,11 +760,22 @@ static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, c
   }
   L.colourStart.assign(L.nColours + 1, 0);
   for (int c = 0; c < L.nColours; c++) L.colourStart[c + 1] = L.colourStart[c] + counts[c];
-  // stable partition by colour: invp = rows sorted by colour
+  L.ifaceCount.assign(L.nColours, 0);
+  int keyRange = L.nColours + 1;
+  if (splitIface && !dropGhost) {
+    parallelFor(n, IfaceKeyKernel{n, row, col, ghostIsHalo, colour.p});
+    DBuf<int> cnt2(2 * 64);
+    cnt2.zero();
+    parallelFor(n, ColourCountKernel{colour.p, cnt2.p});
+    std::vector<int> h2 = cnt2.toHost();
+    for (int c = 0; c < L.nColours; c++) L.ifaceCount[c] = h2[2 * c];
+    keyRange = 2 * L.nColours + 1;
+  }
+  // stable partition by (colour[, interface first]): invp = rows sorted by the key
   DBuf<int> invp(n);
   parallelFor(n, IotaKernel{invp.p});
   int bits = 1;
-  while ((1 << bits) < L.nColours + 1) bits++;
+  while ((1 << bits) < keyRange) bits++;
   sortPairs(colour.p, invp.p, n, bits);
   perm.alloc(n);
   parallelFor(n, InvPermKernel{invp.p, perm.p});
@@ -904,6 +931,7 @@ static void galerkin(Level& F, const DBuf<int>& ciNat, int nc, DBuf<int>& crow, 
 static void agreeColours(Level& L) {
   const int ncg = (int)commMaxHost((double)L.nColours);
   while ((int)L.colourStart.size() < ncg + 1) L.colourStart.push_back(L.n);
+  while ((int)L.ifaceCount.size() < ncg) L.ifaceCount.push_back(0);
   L.nColours = ncg;
 }
 
@@ -921,7 +949,7 @@ static std::unique_ptr<Level> coarsenPass(Level& F, const int* excluded, double 
   if (multi) coarseHalo(F, ciNat, nc, H);
   galerkin(F, ciNat, nc, crow, ccol, cval, cdiag);
   std::unique_ptr<Level> C(new Level);
-  buildLevelFromCsr(*C, nc, crow.p, ccol.p, cval.p, cdiag.p, !multi, perm, H.nGhost);
+  buildLevelFromCsr(*C, nc, crow.p, ccol.p, cval.p, cdiag.p, !multi, perm, H.nGhost, multi, nullptr);
   if (multi) {
     const int ns = (int)H.scatterNat.size();
     DBuf<int> natDev, scatterDev((size_t)ns + 1);
@@ -975,7 +1003,14 @@ void Amg::setup(System* sys) {
   multi = commActive() && sys->mesh && !sys->noHalo;
   levels.emplace_back(new Level);
   Level& L0 = *levels[0];
-  buildLevelFromCsr(L0, n, sys->row, sys->col, sys->off.p, sys->diag.p, !multi, perm0, sys->nTotal - n);
+  DBuf<int> ghostIsHalo;
+  if (multi) {  // ghost cells that belong to an interface group (the others are eliminated boundary ghosts)
+    std::vector<int> mask((size_t)(sys->nTotal - n) + 1, 0);
+    for (int g : sys->mesh->haloGatherHost) mask[(size_t)g - n] = 1;
+    ghostIsHalo.upload(mask.data(), mask.size());
+  }
+  buildLevelFromCsr(L0, n, sys->row, sys->col, sys->off.p, sys->diag.p, !multi, perm0, sys->nTotal - n, multi,
+                    ghostIsHalo.p);
   if (multi) {
     Mesh* m = sys->mesh;
     const int ns = m->halo.nSend;
@@ -988,6 +1023,7 @@ void Amg::setup(System* sys) {
     // supports stream capture); measured on 2 B200s: 7.5 -> 5.35 ms per cycle
     if (const char* e = getenv("FVMGPU_MULTI_GRAPHS")) useGraphs = atoi(e) != 0;
     if (const char* e = getenv("FVMGPU_EXCHANGE_PER_COLOUR")) exchangePerColour = atoi(e) != 0;
+    if (const char* e = getenv("FVMGPU_OVERLAP")) overlapExchange = atoi(e) != 0;
   }
   // rows marked as boundary inside the interior range (setDirichlet) are not coarsened
   DBuf<int> excl0(n);
@@ -1152,6 +1188,32 @@ void Amg::cycleMerged(int cycleType, int lvl) {
 
 void Amg::exchange(Level& L, double* x) {
   if (multi) L.halo.exchange(x, 1);
+}
+
+// Overlapped exchange: the pack kernel and the NCCL calls are issued on the communication stream,
+// ordered after everything issued so far on the compute stream; joinExchange() makes the compute
+// stream wait for it. Both work inside a stream capture (fork / join of the graph).
+void Amg::forkExchange(Level& L, double* x) {
+#ifndef FVMGPU_HOSTSIM
+  Context& c = ctx();
+  CUDA_CHECK(cudaEventRecord(c.evFork, c.stream));
+  CUDA_CHECK(cudaStreamWaitEvent(c.commStream, c.evFork, 0));
+  cudaStream_t compute = c.stream;
+  c.stream = c.commStream;
+  try { L.halo.exchange(x, 1); } catch (...) { c.stream = compute; throw; }
+  c.stream = compute;
+  CUDA_CHECK(cudaEventRecord(c.evJoin, c.commStream));
+  exchangePending = true;
+#else
+  L.halo.exchange(x, 1);
+#endif
+}
+void Amg::joinExchange() {
+#ifndef FVMGPU_HOSTSIM
+  if (!exchangePending) return;
+  CUDA_CHECK(cudaStreamWaitEvent(ctx().stream, ctx().evJoin, 0));
+  exchangePending = false;
+#endif
 }
 
 // ================================================================= coarse levels without launches
@@ -1471,20 +1533,37 @@ void Amg::sweeps(int nSweeps, int lvl) {
         const int c = pass < L.nColours ? pass : 2 * L.nColours - 1 - pass;
         if (c == lastColour) continue;
         const int r0 = L.colourStart[c], cnt = L.colourStart[c + 1] - r0;
-        if (L.xZero) parallelFor(cnt, GsFirstColourZeroRows{r0, L.diag.p, L.b.p, L.x.p});
-        else if (L.hybridLast && c == L.nColours - 1) {
-          parallelFor(cnt, GsRemainderRows{r0, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p});
-          parallelFor(cnt, CopyRangeRows{r0, L.r.p, L.x.p});
-        }
-        else parallelFor(cnt, GsRows{r0, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p});
+        auto rowsOf = [&](int begin, int count) {
+          if (count <= 0) return;
+          if (L.xZero) parallelFor(count, GsFirstColourZeroRows{begin, L.diag.p, L.b.p, L.x.p});
+          else if (L.hybridLast && c == L.nColours - 1) {
+            parallelFor(count, GsRemainderRows{begin, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p});
+            parallelFor(count, CopyRangeRows{begin, L.r.p, L.x.p});
+          }
+          else parallelFor(count, GsRows{begin, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p});
+        };
         // Ghost values: refreshed after each half-sweep (forward / reverse), i.e. neighbours' rows
         // are lagged by at most one half-sweep -- the reference lags them by a whole sweep
         // (forwardGS+reverseGS, then x.sync(), F/MultiFieldMatrix.cpp:125-165). Per-colour exchange
         // (exact multicolour GS across ranks) is available with FVMGPU_EXCHANGE_PER_COLOUR=1.
-        if (exchangePerColour || pass == L.nColours - 1 || pass == 2 * L.nColours - 1) exchange(L, L.x.p);
+        const bool exchangeNow = multi && (exchangePerColour || pass == L.nColours - 1 || pass == 2 * L.nColours - 1);
+        if (multi && overlapExchange) {
+          // interior rows first (they read no ghost slot), then wait for the exchange started by the
+          // previous half-sweep, then the interface rows; the exchange this pass starts runs on the
+          // communication stream underneath the NEXT pass's interior rows
+          const int ni = L.ifaceCount[c];
+          rowsOf(r0 + ni, cnt - ni);
+          joinExchange();
+          rowsOf(r0, ni);
+          if (exchangeNow) forkExchange(L, L.x.p);
+        } else {
+          rowsOf(r0, cnt);
+          if (exchangeNow) exchange(L, L.x.p);
+        }
         L.xZero = false;
         lastColour = c;
       }
+      joinExchange();
     } else {
       // two Jacobi passes per sweep (F/AMG.cpp:59-63), ping-pong through r
       parallelFor(L.n, JacobiRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p});

@@ -17,6 +17,7 @@ struct Level {
   // colouring: rows [colourStart[c], colourStart[c+1]) have colour c
   int nColours = 0;
   std::vector<int> colourStart;
+  std::vector<int> ifaceCount;  // multi-GPU: the first ifaceCount[c] rows of colour c have a halo column
   // link to the next coarser level (in ITS numbering)
   DBuf<int> ci;              // n: coarse row of each fine row, -1 = not coarsened
   DBuf<int> memOff, mem;     // coarse row -> its fine rows (ascending)
@@ -59,6 +60,8 @@ struct Amg {
   // F/LinearSystemMerger.cpp: gather coarse levels instead of exchanging halos of tiny levels)
   bool multi = false;
   int tagBase = 0;                 // profiler level tags of a nested hierarchy continue after the merged level
+  bool overlapExchange = true;     // run the exchange on the communication stream under the next pass's interior rows
+  bool exchangePending = false;
   bool exchangePerColour = false;  // true: halo exchange after every colour pass; false: after every half-sweep
   int mergedLevel = -1;            // index of the distributed level that is solved replicated
   int mergeMaxLocal = 0;           // rows per rank block in the merged numbering (padded)
@@ -88,6 +91,8 @@ struct Amg {
   void buildMerged();
   void cycleMerged(int cycleType, int lvl);
   void exchange(Level& L, double* x);
+  void forkExchange(Level& L, double* x);
+  void joinExchange();
   void buildTail();
   void runTail();
   void dropGraphs();

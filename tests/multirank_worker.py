@@ -112,6 +112,68 @@ def main():
     g2["ib_type"] = np.full(raw.n_total, -1, np.int32)
     ref = port.thermal_reference(raw, conn, g2, k_glob, bcs, x0=300.0, tol=1e-13)
 
+    if solver_kind == "electric":
+        # ElectricModelA (electrostatics + drift / transient charge transport) on this rank's part of a
+        # tet mesh, two time steps; checked against the single-partition run of the same code, which
+        # tests/test_electric.py pins to the reference's ElectricModel
+        import contextlib
+        import io
+        from fvm_b200 import models as M
+
+        def run(mesh_raw, use_lib):
+            mesh = M.Mesh(mesh_raw)
+            geomf = M.GeomFields("geom")
+            M.MeshMetricsCalculatorA(geomf, [mesh], lib=use_lib).init()
+            ef = M.ElectricFields("elec")
+            em = M.ElectricModelA(geomf, ef, [mesh], lib=use_lib)
+            bcm = em.getBCMap()
+            for gid, bc in bcm.items():
+                bc.bcType = "SpecifiedPotentialFlux"
+                bc["specifiedPotentialFlux"] = 0.0
+            if 5 in bcm:
+                bcm[5].bcType = "SpecifiedPotential"; bcm[5]["specifiedPotential"] = 0.0
+            if 6 in bcm:
+                bcm[6].bcType = "SpecifiedPotential"; bcm[6]["specifiedPotential"] = 50.0
+            o = em.getOptions()
+            o.drift_enable = True
+            o["initialTotalCharge"] = 1e10
+            o["timeStep"] = 1e-6
+            c = em.getConstants()
+            c["nTrap"] = 2; c["electron_mobility"] = 1e-4; c["electron_saturation_velocity"] = 1e9
+            for nm in ("electrostaticsLinearSolver", "chargetransportLinearSolver"):
+                sv = M.AMG()
+                sv.relativeTolerance, sv.nMaxIterations, sv.verbosity = 1e-13, 3000, 0
+                setattr(o, nm, sv)
+            em.init()
+            cells = mesh.getCells()
+            gids = mesh_raw.cell_global if "cell_global" in mesh_raw else np.arange(mesh_raw.n_total)
+            ef.charge[cells][:, 2] = np.where(gids < raw.n_cells, 1e12 * (1 + gids % 5), 0.0)
+            ef.chargeN1[cells][:] = ef.charge[cells]
+            for _ in range(2):
+                with contextlib.redirect_stdout(io.StringIO()):
+                    em.advance(1)
+                em.updateTime()
+            return ef.potential[cells].copy(), ef.charge[cells].copy()
+
+        # single-partition run of the same code BEFORE this process joins the communicator
+        lib.comm_destroy()
+        pot_ref, chg_ref = run(raw, lib)
+        lib.comm_init(world, rank)
+        pot, chg = run(loc, lib)
+        own = loc.cell_global[:loc.n_cells]
+        num = float(((pot[:loc.n_cells] - pot_ref[own]) ** 2).sum()) + float(((chg[:loc.n_cells, 2] / 1e12 - chg_ref[own, 2] / 1e12) ** 2).sum())
+        den = float((pot_ref[own] ** 2).sum()) + float(((chg_ref[own, 2] / 1e12) ** 2).sum())
+        t = torch.tensor([num, den])
+        dist.all_reduce(t)
+        out = dict(rank=rank, world=world, n_self=int(loc.n_cells), peers=[int(p) for p in loc.halo["peers"]],
+                   err_diag=0.0, err_b=0.0, rel_l2=float(np.sqrt(float(t[0]) / float(t[1]))), ghost_err=0.0,
+                   r0=1.0, r=0.0, iters=0, levels=[], collectives=lib.comm_collectives())
+        with open(os.path.join(os.environ["FVM_RESULT_DIR"], "rank%d.json" % rank), "w") as fh:
+            json.dump(out, fh)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
     if solver_kind == "model":
         # the public (reference-mirroring) Python API on this rank's mesh: same script as single rank
         import contextlib

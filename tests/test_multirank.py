@@ -84,3 +84,10 @@ def test_exchange_after_every_colour_pass():
     by half a sweep; the reference lags them by a whole sweep)."""
     res = run_world(2, "hex_slabs", "amg", 64, extra_env={"FVMGPU_EXCHANGE_PER_COLOUR": "1"})
     check(res)
+
+
+def test_electric_model_on_partitioned_tets():
+    """BASELINE configs[4] in miniature: ElectricModelA (Poisson + drift / transient charge transport) on
+    an RCB-partitioned tet mesh, 2 ranks, against the single-partition run of the same model."""
+    res = run_world(2, "tet_rcb", "electric", 200)
+    check(res)
