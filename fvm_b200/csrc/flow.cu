@@ -89,6 +89,7 @@ struct FlowInitMassFluxFaces {  // FlowModel::init, F/FlowModel_impl.h:222-244, 
         massFlux[f] = rho[c0] * dot3(bv, A);
         return;
       }
+      if (bc->kind == FVMGPU_FLOWBC_SYMMETRY) { massFlux[f] = 0.0; return; }  // F/FlowModel_impl.h:324-328
     }
     massFlux[f] = 0.5 * (rho[c0] * dot3(ld3(V, c0), A) + rho[c1] * dot3(ld3(V, c1), A));
   }
@@ -124,17 +125,42 @@ FVM_DEV void velGradOf(int c, const int* row, const int* col, const double* V, c
     g[6] += w2 * d0; g[7] += w2 * d1; g[8] += w2 * d2;
   }
 }
-struct VelGradRows {  // ghost cells copy their neighbour's gradient (F/GradientModel.h:550-566)
-  int nSelf; const int* row; const int* col; const double* V; const double* w; long long nnz; double* vGrad;
+// ghost cells copy their neighbour's gradient, or reflect it on face groups of kind SYMMETRY
+// (F/GradientModel.h:530-566; reflectGradient for Vector<T,3>: GTR = R * GT0 * R, :62-86)
+struct VelGradRows {
+  int nSelf, nInteriorFaces; const int* row; const int* col; const int* entryFace; const int* faceGroupOf;
+  const int* groupKind; const double4* faceGeom; const double* V; const double* w; long long nnz; double* vGrad;
   FVM_DEV void operator()(long long ii) const {
     const int i = (int)ii;
     int c = i;
+    bool reflect = false;
+    double4 fg = make_double4(0, 0, 0, 1);
     if (i >= nSelf) {
       if (row[i + 1] - row[i] != 1) { for (int q = 0; q < 9; q++) vGrad[9 * (size_t)i + q] = 0.0; return; }
       c = col[row[i]];
+      const int f = entryFace[row[i]] >> 1;
+      if (f >= nInteriorFaces && groupKind[faceGroupOf[f - nInteriorFaces]] == FVMGPU_GROUP_SYMMETRY) {
+        reflect = true;
+        fg = faceGeom[f];
+      }
     }
     double g[9];
     velGradOf(c, row, col, V, w, nnz, g);
+    if (reflect) {
+      const double en[3] = {fg.x / fg.w, fg.y / fg.w, fg.z / fg.w};
+      double R[3][3], GT0[3][3], T1[3][3], GTR[3][3];
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) {
+          R[a][b] = (a == b) ? 1.0 - 2 * en[a] * en[b] : -2 * en[a] * en[b];
+          GT0[a][b] = g[3 * b + a];  // GT0(i,j) = g0[j][i]
+        }
+      for (int a = 0; a < 3; a++)      // SquareTensor product: sum over k from zero, in order
+        for (int b = 0; b < 3; b++) { double t = 0.0; for (int k = 0; k < 3; k++) t += R[a][k] * GT0[k][b]; T1[a][b] = t; }
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) { double t = 0.0; for (int k = 0; k < 3; k++) t += T1[a][k] * R[k][b]; GTR[a][b] = t; }
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) g[3 * b + a] = GTR[a][b];  // gr[j][i] = GTR(i,j)
+    }
 #pragma unroll
     for (int q = 0; q < 9; q++) vGrad[9 * (size_t)i + q] = g[q];
   }
@@ -155,16 +181,29 @@ FVM_DEV V3 pressGradOf(int c, const int* row, const int* entryFace, const double
   return g;
 }
 struct PressGradRows {
-  int nSelf; const int* row; const int* col; const int* entryFace; const double4* faceGeom; const double4* cellGeom;
-  const double* pFace; double* pGrad;
+  int nSelf, nInteriorFaces; const int* row; const int* col; const int* entryFace; const int* faceGroupOf;
+  const int* groupKind; const double4* faceGeom; const double4* cellGeom; const double* pFace; double* pGrad;
   FVM_DEV void operator()(long long ii) const {
     const int i = (int)ii;
     int c = i;
+    bool reflect = false;
+    double4 fg = make_double4(0, 0, 0, 1);
     if (i >= nSelf) {
       if (row[i + 1] - row[i] != 1) { st3(pGrad, i, V3{0, 0, 0}); return; }
       c = col[row[i]];
+      const int f = entryFace[row[i]] >> 1;
+      if (f >= nInteriorFaces && groupKind[faceGroupOf[f - nInteriorFaces]] == FVMGPU_GROUP_SYMMETRY) {
+        reflect = true;
+        fg = faceGeom[f];
+      }
     }
-    st3(pGrad, i, pressGradOf(c, row, entryFace, faceGeom, pFace, cellGeom[c].w));
+    V3 g = pressGradOf(c, row, entryFace, faceGeom, pFace, cellGeom[c].w);
+    if (reflect) {  // reflectGradient (scalar), F/GradientModel.h:21-28
+      const V3 en = {fg.x / fg.w, fg.y / fg.w, fg.z / fg.w};
+      const double t = 2.0 * dot3(g, en);
+      g = V3{g.x - t * en.x, g.y - t * en.y, g.z - t * en.z};
+    }
+    st3(pGrad, i, g);
   }
 };
 
@@ -230,11 +269,19 @@ struct MomentumRows {
         if (f >= P.nInteriorFaces) {
           const FlowBcEntry* bc = faceBc(P.bcs, P.faceGroupOf, P.nInteriorFaces, f);
           if (bc->kind == FVMGPU_FLOWBC_NOSLIP_WALL) xnew = V3{bc->p[0], bc->p[1], bc->p[2]};
+          else if (bc->kind == FVMGPU_FLOWBC_SYMMETRY) {  // x[c1] = x[c0] - 2 (x[c0].en) en, F/GenericBCS.h:583-596
+            const double4 fg = P.faceGeom[f];
+            const V3 en = {fg.x / fg.w, fg.y / fg.w, fg.z / fg.w};
+            const V3 x0 = ld3(P.V, P.col[r0]);
+            const double d = dot3(x0, en);
+            xnew = V3{x0.x - 2 * d * en.x, x0.y - 2 * d * en.y, x0.z - 2 * d * en.z};
+            marks = 1;  // setBoundary(c1); its diagonal (= the neighbour's, :603) is written by the neighbour's thread
+          }
         }
         P.off[r0] = 0.0;
       }
       st3(P.Vnew, i, xnew);
-      st3(P.diag, i, V3{-1.0, -1.0, -1.0});
+      if (!marks) st3(P.diag, i, V3{-1.0, -1.0, -1.0});
       st3(P.b, i, V3{0.0, 0.0, 0.0});
       P.isBoundary[i] = marks;
       return;
@@ -298,11 +345,20 @@ struct MomentumRows {
         const int f = P.entryFace[k] >> 1;
         if (f < P.nInteriorFaces) continue;
         const FlowBcEntry* bc = faceBc(P.bcs, P.faceGroupOf, P.nInteriorFaces, f);
-        if (bc->kind != FVMGPU_FLOWBC_NOSLIP_WALL) continue;
         const V3 x1 = ld3(P.V, P.col[k]);
         const double c01 = P.off[k];
-        r.x += c01 * (bc->p[0] - x1.x); r.y += c01 * (bc->p[1] - x1.y); r.z += c01 * (bc->p[2] - x1.z);
-        P.off[k] = 0.0;
+        if (bc->kind == FVMGPU_FLOWBC_NOSLIP_WALL) {
+          r.x += c01 * (bc->p[0] - x1.x); r.y += c01 * (bc->p[1] - x1.y); r.z += c01 * (bc->p[2] - x1.z);
+          P.off[k] = 0.0;
+        } else if (bc->kind == FVMGPU_FLOWBC_SYMMETRY) {  // applySymmetryBC, F/GenericBCS.h:569-615
+          const double4 fg = P.faceGeom[f];
+          const V3 en = {fg.x / fg.w, fg.y / fg.w, fg.z / fg.w};
+          const double d = dot3(xi, en);
+          const V3 xB = {xi.x - 2 * d * en.x, xi.y - 2 * d * en.y, xi.z - 2 * d * en.z};
+          r.x += c01 * (xB.x - x1.x); r.y += c01 * (xB.y - x1.y); r.z += c01 * (xB.z - x1.z);
+          P.off[k] = 0.0;
+          st3(P.diag, P.col[k], V3{diag, diag, diag});  // _dRdXDiag[c1] = _dRdXDiag[c0] (before the under-relaxation)
+        }
       }
     }
     // ---- Underrelaxer, F/Underrelaxer.h:49-52
@@ -592,7 +648,8 @@ void flowGetField(Flow* F, int field, double* host, long long n) {
 }
 void flowSetBc(Flow* F, int groupId, int kind, const double* p, int np) {
   requireReady();
-  if (kind != FVMGPU_FLOWBC_NOSLIP_WALL) fail("flow_set_bc: only NoSlipWall boundaries are supported in this release (kind %d)", kind);
+  if (kind != FVMGPU_FLOWBC_NOSLIP_WALL && kind != FVMGPU_FLOWBC_SYMMETRY)
+    fail("flow_set_bc: only NoSlipWall and Symmetry boundaries are supported in this release (kind %d)", kind);
   for (size_t g = 0; g < F->bcs.size(); g++) {
     const FaceGroup& fg = F->mesh->groups[g];
     if (fg.id == groupId && fg.kind != FVMGPU_GROUP_INTERIOR) {
@@ -645,9 +702,11 @@ void flowAssembleMomentum(Flow* F, const fvmgpu_flow_opts& o) {
   Mesh* m = F->mesh;
   if (!(o.momentumURF > 0)) fail("flow: momentumURF must be positive");
   if (o.transient && (!F->hasVN1 || (o.time_order > 1 && !F->hasVN2))) fail("flow: transient run needs VELOCITY_N1 (and _N2)");
-  parallelFor(m->nTotal, VelGradRows{m->nSelf, m->row.p, m->col.p, F->V.p, m->gradW.p, m->nnz, F->vGrad.p});
-  parallelFor(m->nTotal, PressGradRows{m->nSelf, m->row.p, m->col.p, m->entryFace.p, m->faceGeom.p, m->cellGeom.p,
-                                       F->pFace.p, F->pGrad.p});
+  parallelFor(m->nTotal, VelGradRows{m->nSelf, m->nInteriorFaces, m->row.p, m->col.p, m->entryFace.p, m->faceGroupOf.p,
+                                     m->groupKindDev.p, m->faceGeom.p, F->V.p, m->gradW.p, m->nnz, F->vGrad.p});
+  parallelFor(m->nTotal, PressGradRows{m->nSelf, m->nInteriorFaces, m->row.p, m->col.p, m->entryFace.p,
+                                       m->faceGroupOf.p, m->groupKindDev.p, m->faceGeom.p, m->cellGeom.p, F->pFace.p,
+                                       F->pGrad.p});
   MomParams P;
   P.nSelf = m->nSelf; P.nInteriorFaces = m->nInteriorFaces;
   P.row = m->row.p; P.col = m->col.p; P.entryFace = m->entryFace.p; P.faceGroupOf = m->faceGroupOf.p;

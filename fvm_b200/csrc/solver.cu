@@ -1024,6 +1024,7 @@ void Amg::setup(System* sys) {
     if (const char* e = getenv("FVMGPU_MULTI_GRAPHS")) useGraphs = atoi(e) != 0;
     if (const char* e = getenv("FVMGPU_EXCHANGE_PER_COLOUR")) exchangePerColour = atoi(e) != 0;
     if (const char* e = getenv("FVMGPU_OVERLAP")) overlapExchange = atoi(e) != 0;
+    if (const char* e = getenv("FVMGPU_OVERLAP_MIN_ROWS")) overlapMinRows = atoi(e);
   }
   // rows marked as boundary inside the interior range (setDirichlet) are not coarsened
   DBuf<int> excl0(n);
@@ -1547,7 +1548,7 @@ void Amg::sweeps(int nSweeps, int lvl) {
         // (forwardGS+reverseGS, then x.sync(), F/MultiFieldMatrix.cpp:125-165). Per-colour exchange
         // (exact multicolour GS across ranks) is available with FVMGPU_EXCHANGE_PER_COLOUR=1.
         const bool exchangeNow = multi && (exchangePerColour || pass == L.nColours - 1 || pass == 2 * L.nColours - 1);
-        if (multi && overlapExchange) {
+        if (multi && overlapExchange && L.n >= overlapMinRows) {
           // interior rows first (they read no ghost slot), then wait for the exchange started by the
           // previous half-sweep, then the interface rows; the exchange this pass starts runs on the
           // communication stream underneath the NEXT pass's interior rows

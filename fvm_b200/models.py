@@ -717,7 +717,7 @@ class FlowModelA:
     """Mirror of `models_atyped_double.FlowModelA` (F/FlowModel.h:17-95, F/FlowModel.i): SIMPLE
     iterations -- momentum assembly + solve, Rhie-Chow pressure correction assembly + solve, the
     pressure / mass-flux / velocity corrections -- all on the device through the C ABI
-    (fvmgpu_flow_*). Boundary types of this release: "NoSlipWall" (F/FlowModel_impl.h:636-640)."""
+    (fvmgpu_flow_*). Boundary types of this release: "NoSlipWall" and "Symmetry" (F/FlowModel_impl.h:636-640, 674-677)."""
 
     def __init__(self, geom_fields, flow_fields, meshes, lib=None):
         self.geom, self.fields, self.meshes, self.lib = geom_fields, flow_fields, list(meshes), lib
@@ -817,10 +817,14 @@ class FlowModelA:
                 fl.set_field(capi.FLOW_VELOCITY_N2, f.velocityN2[cells])
         for fg in mesh.getBoundaryFaceGroups():
             bc = self._bcMap[fg.id]
-            if bc.bcType != "NoSlipWall":
+            if bc.bcType == "NoSlipWall":
+                fl.set_bc(fg.id, capi.FLOWBC_NOSLIP_WALL, [float(bc["specifiedXVelocity"]),
+                                                            float(bc["specifiedYVelocity"]),
+                                                            float(bc["specifiedZVelocity"])])
+            elif bc.bcType == "Symmetry":
+                fl.set_bc(fg.id, capi.FLOWBC_SYMMETRY, [0.0, 0.0, 0.0])
+            else:
                 raise CException(bc.bcType + " not implemented for FlowModel")
-            fl.set_bc(fg.id, capi.FLOWBC_NOSLIP_WALL, [float(bc["specifiedXVelocity"]), float(bc["specifiedYVelocity"]),
-                                                        float(bc["specifiedZVelocity"])])
 
     def _download(self, mesh, fl):
         f = self.fields

@@ -251,7 +251,12 @@ enum {
   FVMGPU_FLOW_VELOCITY_N1 = 11,      /* 3*nCellsTotal  (transient)                                 */
   FVMGPU_FLOW_VELOCITY_N2 = 12
 };
-enum { FVMGPU_FLOWBC_NOSLIP_WALL = 0 }; /* p[0..2] = specifiedX/Y/ZVelocity (F/FlowBC.h:10-21) */
+enum {
+  FVMGPU_FLOWBC_NOSLIP_WALL = 0, /* applyDirichletBC(bVelocity); p[0..2] = specifiedX/Y/ZVelocity (F/FlowBC.h:10-21) */
+  FVMGPU_FLOWBC_SYMMETRY = 1     /* GenericBCS<Vector,DiagTensor,T>::applySymmetryBC (F/GenericBCS.h:569-615);
+                                    zero mass flux; on face groups of kind SYMMETRY the velocity and pressure
+                                    gradients of the ghost cells are reflected (F/GradientModel.h:21-86) */
+};
 typedef struct {
   double momentumURF;   /* FlowModelOptions "momentumURF" (0.7)  F/FlowBC.h:42-50 */
   double pressureURF;   /* "pressureURF" (0.3)                                  */

@@ -217,6 +217,38 @@ void* fvmref_mesh_from_raw(int dim, int nCells, int nNodes, const double* nodes,
   CATCH(nullptr)
 }
 
+// same, with some boundary groups re-typed "symmetry" BEFORE the metrics are computed (the raw Mesh
+// ctor makes every boundary group a "wall", F/Mesh.cpp:188-200): ghost centroids are reflected
+// (F/MeshMetricsCalculator_impl.h:205-220) and gradients reflected (F/GradientModel.h:536-549)
+void* fvmref_mesh_from_raw_sym(int dim, int nCells, int nNodes, const double* nodes, int nFaces,
+                               const int* faceCells, const int* faceNodes, const int* faceNodeCount,
+                               int nGroups, const int* faceGroupSize, int nSym, const int* symGroupIds) {
+  TRY RefMesh* rm = new RefMesh;
+  Vec3Array coords(nNodes);
+  for (int i = 0; i < nNodes; i++)
+    for (int k = 0; k < 3; k++) coords[i][k] = nodes[3 * i + k];
+  IArray fc(2 * nFaces), fnc(nFaces), fgs(nGroups);
+  long nfn = 0;
+  for (int f = 0; f < nFaces; f++) {
+    fc[2 * f] = faceCells[2 * f];
+    fc[2 * f + 1] = faceCells[2 * f + 1];
+    fnc[f] = faceNodeCount[f];
+    nfn += faceNodeCount[f];
+  }
+  IArray fn((int)nfn);
+  for (long i = 0; i < nfn; i++) fn[(int)i] = faceNodes[i];
+  for (int g = 0; g < nGroups; g++) fgs[g] = faceGroupSize[g];
+  std::shared_ptr<Mesh> mesh(new Mesh(dim, nCells, coords, fc, fn, fnc, fgs));
+  for (const FaceGroupPtr fg : mesh->getBoundaryFaceGroups())
+    for (int k = 0; k < nSym; k++)
+      if (fg->id == symGroupIds[k]) fg->groupType = "symmetry";
+  rm->owned.push_back(mesh);
+  rm->meshes.push_back(mesh.get());
+  finish_mesh(rm);
+  return rm;
+  CATCH(nullptr)
+}
+
 void fvmref_mesh_free(void* h) { delete (RefMesh*)h; }
 
 // out[0..7] = dim, nCellsSelf, nCellsTotal, nFaces, nnz(cellCells), nFaceGroups(all), nNodes, meshId
@@ -261,7 +293,7 @@ int fvmref_mesh_connectivity(void* h, int* faceCells, int* ccRow, int* ccCol, in
     groupOffset[g] = fg->site.getOffset();
     groupCount[g] = fg->site.getCount();
     groupId[g] = fg->id;
-    groupKind[g] = fg->groupType == "interior" ? 0 : (fg->groupType == "interface" ? 2 : 1);
+    groupKind[g] = fg->groupType == "interior" ? 0 : (fg->groupType == "interface" ? 2 : (fg->groupType == "symmetry" ? 3 : 1));
     g++;
   }
   return 0;

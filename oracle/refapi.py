@@ -62,6 +62,9 @@ def lib():
         L.fvmref_mesh_from_raw.restype = C.c_void_p
         L.fvmref_mesh_from_raw.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_int, _ip, _ip, _ip,
                                            C.c_int, _ip]
+        L.fvmref_mesh_from_raw_sym.restype = C.c_void_p
+        L.fvmref_mesh_from_raw_sym.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_int, _ip, _ip, _ip,
+                                               C.c_int, _ip, C.c_int, _ip]
         L.fvmref_mesh_free.argtypes = [C.c_void_p]
         L.fvmref_mesh_sizes.argtypes = [C.c_void_p, _ip]
         L.fvmref_mesh_connectivity.argtypes = [C.c_void_p] + [_ip] * 8
@@ -141,7 +144,17 @@ class RefMesh:
         return cls(lib().fvmref_mesh_from_cas(path.encode()))
 
     @classmethod
-    def from_raw(cls, dim, n_cells, nodes, face_cells, face_nodes, face_node_count, face_group_size):
+    def from_raw(cls, dim, n_cells, nodes, face_cells, face_nodes, face_node_count, face_group_size,
+                 symmetry_groups=()):
+        if len(symmetry_groups):
+            nodes = np.ascontiguousarray(nodes, np.float64).reshape(-1, 3)
+            fc = np.ascontiguousarray(face_cells, np.int32).reshape(-1)
+            fn = np.ascontiguousarray(face_nodes, np.int32).reshape(-1)
+            fnc = np.ascontiguousarray(face_node_count, np.int32)
+            fgs = np.ascontiguousarray(face_group_size, np.int32)
+            sym = np.ascontiguousarray(list(symmetry_groups), np.int32)
+            return cls(lib().fvmref_mesh_from_raw_sym(dim, n_cells, len(nodes), nodes, len(fnc), fc, fn, fnc,
+                                                      len(fgs), fgs, len(sym), sym))
         nodes = np.ascontiguousarray(nodes, np.float64).reshape(-1, 3)
         fc = np.ascontiguousarray(face_cells, np.int32).reshape(-1)
         fn = np.ascontiguousarray(face_nodes, np.int32).reshape(-1)

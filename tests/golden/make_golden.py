@@ -17,6 +17,9 @@ hot path compiled in place by oracle/Makefile). Writes small .npz files next to 
                    mu = 0.1, rho = 1.3): the reference state after 6 SIMPLE iterations, its momentum
                    system assembled from that state, the post-momentum state, the pressure-correction
                    system, and the converged steady flow field (tolerances 1e-9)
+  flow_symmetry.npz FlowModel in a jittered 6x5x4 hex box with two "symmetry" face groups and a moving lid:
+                   momentum system from a developed state and the fields after 6 SIMPLE iterations with
+                   tight inner solves
   electric_box.npz ElectricModel on a jittered 6x5x7 hex box (1 x 1 x 2 um): Poisson equation with
                    SpecifiedPotential / SpecifiedPotentialFlux / Symmetry / SpecialDielectricBoundary
                    BCs and a uniform total charge, then drift + transient charge transport of the
@@ -193,6 +196,40 @@ def flow_golden():
     print("flow_cavity.npz: %d cells, converged in %d SIMPLE iterations" % (rm.n_self, out["conv_iters"]))
 
 
+def flow_symmetry_golden():
+    """3-D box with two symmetry planes (face groups 1 and 3 typed "symmetry", bcType Symmetry) and a
+    moving lid: exercises the vector applySymmetryBC and the gradient / centroid reflections."""
+    raw = G.hex_mesh(6, 5, 4, jitter=0.2, seed=9)
+    rm = R.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes, raw.face_node_count,
+                            raw.face_group_size, symmetry_groups=(1, 3))
+    f = R.RefFlow(rm)
+    for g in (2, 4, 5):
+        f.set_bc(g, "NoSlipWall")
+    f.set_bc(1, "Symmetry")
+    f.set_bc(3, "Symmetry")
+    f.set_bc(6, "NoSlipWall", specifiedXVelocity=1.0, specifiedYVelocity=0.3)
+    f.set_vc("viscosity", 0.05)
+    f.set_vc("density", 1.1)
+    tight = dict(relativeTolerance=1e-14, nMaxIterations=3000, verbosity=0)
+    f.set_solver(0, R.solver_cfg(**tight))
+    f.set_solver(1, R.solver_cfg(**tight))
+    f.init()
+    out = {}
+    for it in range(6):
+        if it == 4:
+            for nm in ("velocity", "pressure", "facePressure", "massFlux", "continuityResidual"):
+                out["s0_" + nm] = f.field(nm).copy()
+            ms = f.momentum_system()
+            out.update(mom_diag=ms["diag"], mom_off=ms["offdiag"], mom_b=ms["b"],
+                       mom_vgrad=f.field("velocityGradient").copy(), mom_pgrad=f.field("pressureGradient").copy())
+        f.solve_momentum()
+        f.solve_continuity()
+    for nm in ("velocity", "pressure", "massFlux"):
+        out["end_" + nm] = f.field(nm).copy()
+    np.savez_compressed(os.path.join(HERE, "flow_symmetry.npz"), **mesh_arrays(rm), **out)
+    print("flow_symmetry.npz: %d cells, group kinds %s" % (rm.n_self, rm.connectivity()["group_kind"]))
+
+
 def electric_golden():
     raw = G.hex_mesh(6, 5, 7, lx=1e-6, ly=1e-6, lz=2e-6, jitter=0.15, seed=2)
     rm = R.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes, raw.face_node_count,
@@ -231,6 +268,9 @@ def electric_golden():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "flowsym":
+        flow_symmetry_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "electric":
         electric_golden()
         sys.exit(0)
