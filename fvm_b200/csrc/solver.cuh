@@ -60,11 +60,13 @@ struct Amg {
   // F/LinearSystemMerger.cpp: gather coarse levels instead of exchanging halos of tiny levels)
   bool multi = false;
   int tagBase = 0;                 // profiler level tags of a nested hierarchy continue after the merged level
-  // Run the exchange on the communication stream under the next pass's interior rows -- only on levels
-  // whose passes are long enough to hide it: measured on 2 B200s, overlapping on EVERY level cost
-  // 6.6 ms per cycle against 4.8 without (two launches per colour and a graph fork/join per exchange
-  // outweigh the ~25 us hidden on the latency-bound levels)
-  bool overlapExchange = true;
+  // Overlap (FVMGPU_OVERLAP=1, off by default): run the exchange on the communication stream under the
+  // next pass's interior rows (rows are ordered interface-first inside every colour for this).
+  // Measured on 2 B200s at 256^3 per GPU: 4.82 ms per cycle without, 5.18 ms with overlap on the
+  // levels >= 2 M rows, 6.60 ms with overlap on every level -- an exchange is ~1 MB over NVLink
+  // (~10 us) and costs less than the second launch per colour plus the graph fork/join that hiding it
+  // needs. Kept for slower interconnects / larger interfaces.
+  bool overlapExchange = false;
   int overlapMinRows = 2000000;
   bool exchangePending = false;
   bool exchangePerColour = false;  // true: halo exchange after every colour pass; false: after every half-sweep
