@@ -262,6 +262,8 @@ class Lib:
  FLOW_VELOCITY_N1, FLOW_VELOCITY_N2) = range(13)
 FLOWBC_NOSLIP_WALL = 0
 FLOWBC_SYMMETRY = 1
+FLOWBC_VELOCITY = 2
+FLOWBC_PRESSURE = 3
 _FLOW_WIDTH = {FLOW_VELOCITY: 3, FLOW_PRESSURE_GRADIENT: 3, FLOW_VELOCITY_GRADIENT: 9, FLOW_MOM_AP: 3,
                FLOW_PREV_VELOCITY: 3, FLOW_VELOCITY_N1: 3, FLOW_VELOCITY_N2: 3}
 _FLOW_FACE = (FLOW_MASS_FLUX, FLOW_FACE_PRESSURE)

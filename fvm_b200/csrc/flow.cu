@@ -16,8 +16,10 @@
 // face-parallel. Compiled with -fmad=false like assemble.cu (same IEEE operation sequence as the
 // reference's x86-64 build).
 //
-// Scope of this round: wall-bounded flows (bcType "NoSlipWall" with a specified wall velocity, e.g.
-// the lid-driven cavity of BASELINE.json configs[2]); other FlowBC types are rejected loudly.
+// Boundary types: NoSlipWall (applyDirichletBC), Symmetry (vector applySymmetryBC + reflected gradients),
+// VelocityBoundary and PressureBoundary (per-face extrapolation / Dirichlet, fixedPressureMomentumBC,
+// fixedPressureContinuityBC, boundary mass-flux rows, pressureBoundaryPostContinuitySolve); SlipJump,
+// turbulence and the PV-coupled solve are not built. One GPU per model in this release.
 // The momentum system's diagonal is a DiagonalTensor (one value per velocity component) with a
 // shared scalar off-diagonal: the three components are solved one after the other by the scalar
 // AMG on ONE hierarchy when their diagonals coincide (always the case without symmetry planes).
@@ -43,6 +45,8 @@ struct Flow {
   DBuf<double> momAp;                        // 3*Nt
   DBuf<double> mDiag, mOff, mB, mDelta;      // momentum system: diag/b/delta 3*Nt AoS, off nnz
   DBuf<double> pCoeff;                       // per face
+  DBuf<double> bDiagAdd, bOff10, bCoeffL;     // per boundary face: pressure-boundary continuity coefficients
+  bool hasPressureBoundary = false;
   std::unique_ptr<System> comp;              // scalar system reused for each velocity component
   std::unique_ptr<System> pp;                // pressure-correction system
   DBuf<double> lastDiag;                     // diagonal the current momentum hierarchy was built for
@@ -84,7 +88,7 @@ struct FlowInitMassFluxFaces {  // FlowModel::init, F/FlowModel_impl.h:222-244, 
     const V3 A = {fg.x, fg.y, fg.z};
     if (f >= nInteriorFaces) {
       const FlowBcEntry* bc = faceBc(bcs, faceGroupOf, nInteriorFaces, f);
-      if (bc->kind == FVMGPU_FLOWBC_NOSLIP_WALL) {
+      if (bc->kind == FVMGPU_FLOWBC_NOSLIP_WALL || bc->kind == FVMGPU_FLOWBC_VELOCITY) {  // F/FlowModel_impl.h:297-312
         const V3 bv = {bc->p[0], bc->p[1], bc->p[2]};
         massFlux[f] = rho[c0] * dot3(bv, A);
         return;
@@ -268,7 +272,18 @@ struct MomentumRows {
         const int f = P.entryFace[r0] >> 1;
         if (f >= P.nInteriorFaces) {
           const FlowBcEntry* bc = faceBc(P.bcs, P.faceGroupOf, P.nInteriorFaces, f);
-          if (bc->kind == FVMGPU_FLOWBC_NOSLIP_WALL) xnew = V3{bc->p[0], bc->p[1], bc->p[2]};
+          const bool inflowOutflow = bc->kind == FVMGPU_FLOWBC_VELOCITY || bc->kind == FVMGPU_FLOWBC_PRESSURE;
+          if (inflowOutflow && P.massFlux[f] > 0.) {
+            // applyExtrapolationBC (F/GenericBCS.h:180-212): identity-like boundary row x1 = x0
+            const V3 x0 = ld3(P.V, P.col[r0]);
+            st3(P.Vnew, i, xi);
+            st3(P.diag, i, V3{-1.0, -1.0, -1.0});
+            st3(P.b, i, V3{x0.x - xi.x, x0.y - xi.y, x0.z - xi.z});
+            P.off[r0] = 1.0;
+            P.isBoundary[i] = 1;
+            return;
+          }
+          if (bc->kind == FVMGPU_FLOWBC_NOSLIP_WALL || inflowOutflow) xnew = V3{bc->p[0], bc->p[1], bc->p[2]};
           else if (bc->kind == FVMGPU_FLOWBC_SYMMETRY) {  // x[c1] = x[c0] - 2 (x[c0].en) en, F/GenericBCS.h:583-596
             const double4 fg = P.faceGeom[f];
             const V3 en = {fg.x / fg.w, fg.y / fg.w, fg.z / fg.w};
@@ -286,7 +301,8 @@ struct MomentumRows {
       P.isBoundary[i] = marks;
       return;
     }
-    double diag = 0.0;
+    double diag = 0.0;          // common part of the DiagonalTensor diagonal
+    V3 dpd = {0.0, 0.0, 0.0};   // per-component part (fixedPressureMomentumBC)
     V3 r = {0.0, 0.0, 0.0};
     bool hasB = false;
     // ---- DiffusionDiscretization (all faces in face order)
@@ -347,7 +363,15 @@ struct MomentumRows {
         const FlowBcEntry* bc = faceBc(P.bcs, P.faceGroupOf, P.nInteriorFaces, f);
         const V3 x1 = ld3(P.V, P.col[k]);
         const double c01 = P.off[k];
-        if (bc->kind == FVMGPU_FLOWBC_NOSLIP_WALL) {
+        const bool inflowOutflow = bc->kind == FVMGPU_FLOWBC_VELOCITY || bc->kind == FVMGPU_FLOWBC_PRESSURE;
+        if (inflowOutflow && P.massFlux[f] > 0.) {
+          // applyExtrapolationBC: dFluxdXC1 = -diag[c1]; for an outflow face the ghost row's diagonal is
+          // -diffCoeff (upwind convection adds nothing to it) and coeff01 is +diffCoeff
+          const double dFluxdXC1 = c01;
+          diag += dFluxdXC1;
+          r.x += dFluxdXC1 * (xi.x - x1.x); r.y += dFluxdXC1 * (xi.y - x1.y); r.z += dFluxdXC1 * (xi.z - x1.z);
+          P.off[k] = 0.0;
+        } else if (bc->kind == FVMGPU_FLOWBC_NOSLIP_WALL || inflowOutflow) {
           r.x += c01 * (bc->p[0] - x1.x); r.y += c01 * (bc->p[1] - x1.y); r.z += c01 * (bc->p[2] - x1.z);
           P.off[k] = 0.0;
         } else if (bc->kind == FVMGPU_FLOWBC_SYMMETRY) {  // applySymmetryBC, F/GenericBCS.h:569-615
@@ -360,11 +384,22 @@ struct MomentumRows {
           st3(P.diag, P.col[k], V3{diag, diag, diag});  // _dRdXDiag[c1] = _dRdXDiag[c0] (before the under-relaxation)
         }
       }
+      // fixedPressureMomentumBC (F/FlowModelPressureBC.h:11-50): inflow faces of pressure boundaries
+      for (int k = r0; k < r1; k++) {
+        const int f = P.entryFace[k] >> 1;
+        if (f < P.nInteriorFaces) continue;
+        const FlowBcEntry* bc = faceBc(P.bcs, P.faceGroupOf, P.nInteriorFaces, f);
+        if (bc->kind != FVMGPU_FLOWBC_PRESSURE || !(P.massFlux[f] < 0.)) continue;
+        const double4 fg = P.faceGeom[f];
+        const V3 vb = {bc->p[0], bc->p[1], bc->p[2]};   // V[c1] after the Dirichlet BC of this face
+        const double dpdV = -P.rho[i] * dot3(vb, vb) / P.urf;
+        dpd.x += dpdV * fg.x * fg.x / fg.w; dpd.y += dpdV * fg.y * fg.y / fg.w; dpd.z += dpdV * fg.z * fg.z / fg.w;
+      }
     }
     // ---- Underrelaxer, F/Underrelaxer.h:49-52
-    diag /= P.urf;
+    const V3 dg = {(diag + dpd.x) / P.urf, (diag + dpd.y) / P.urf, (diag + dpd.z) / P.urf};
     st3(P.Vnew, i, xi);
-    st3(P.diag, i, V3{diag, diag, diag});
+    st3(P.diag, i, dg);
     st3(P.b, i, r);
     P.isBoundary[i] = 0;
   }
@@ -387,6 +422,24 @@ struct MergeComponent {  // delta3[.][k] = delta ; V[.][k] += delta  (ls.updateS
   FVM_DEV void operator()(long long i) const { const double d = delta[i]; delta3[3 * i + k] = d; V[3 * i + k] += d; }
 };
 struct CopyRows { const double* a; double* b; FVM_DEV void operator()(long long i) const { b[i] = a[i]; } };
+// CRMatrix::solveBoundary for the marked ghost rows of the momentum system (extrapolation boundaries),
+// F/CRMatrix.h:433-454, then x += delta
+struct MomentumGhostRows {
+  int nSelf; const int* row; const int* col; const int* isBoundary; const double* diag3; const double* off;
+  const double* b3; double* delta3; double* V;
+  FVM_DEV void operator()(long long k) const {
+    const int i = nSelf + (int)k;
+    if (!isBoundary[i]) return;
+    const int q = row[i];
+    if (row[i + 1] - q != 1) return;
+    const int c0 = col[q];
+    for (int c = 0; c < 3; c++) {
+      const double d = -(b3[3 * (size_t)i + c] + off[q] * delta3[3 * (size_t)c0 + c]) / diag3[3 * (size_t)i + c];
+      delta3[3 * (size_t)i + c] = d;
+      V[3 * (size_t)i + c] += d;
+    }
+  }
+};
 
 // ---------------------------------------------------------------- continuity
 struct ContParams {
@@ -396,6 +449,7 @@ struct ContParams {
   const double* V; const double* Vprev; const double* momAp; const double* p; const double* pGrad; const double* rho;
   const FlowBcEntry* bcs;
   double* massFlux; double* pCoeff;
+  double* bDiagAdd; double* bOff10; double* bCoeffL;   // per boundary face (index f - nInteriorFaces)
   double urf;
 };
 
@@ -407,11 +461,42 @@ struct MassFluxFaces {
     const int c0 = P.faceCells[2 * f], c1 = P.faceCells[2 * f + 1];
     const double4 fg = P.faceGeom[f];
     const V3 Af = {fg.x, fg.y, fg.z};
-    if (f >= P.nInteriorFaces) {  // fixedFluxContinuityBC, F/FlowModelVelocityBC.h:64-70
+    if (f >= P.nInteriorFaces) {
       const FlowBcEntry* bc = faceBc(P.bcs, P.faceGroupOf, P.nInteriorFaces, f);
-      const V3 bv = {bc->p[0], bc->p[1], bc->p[2]};
-      P.massFlux[f] = P.rho[c0] * dot3(bv, Af);
+      const int bf = f - P.nInteriorFaces;
       P.pCoeff[f] = 0.0;
+      if (bc->kind != FVMGPU_FLOWBC_PRESSURE) {  // fixedFluxContinuityBC, F/FlowModelVelocityBC.h:64-92
+        const V3 bv = {bc->p[0], bc->p[1], bc->p[2]};
+        P.massFlux[f] = P.rho[c0] * dot3(bv, Af);
+        P.bDiagAdd[bf] = 0.0; P.bOff10[bf] = 1.0; P.bCoeffL[bf] = 0.0;
+        return;
+      }
+      // fixedPressureContinuityBC, F/FlowModelPressureBC.h:104-158
+      const double4 g0 = P.cellGeom[c0], g1 = P.cellGeom[c1];
+      const V3 ds = {g1.x - g0.x, g1.y - g0.y, g1.z - g0.z};
+      const double dpf = dot3(ld3(P.pGrad, c0), ds) - P.p[c1] + P.p[c0];
+      const double rhoF = P.rho[c0];
+      const V3 a0 = ld3(P.momAp, c0);
+      const double Q = rhoF * (Af.x * Af.x / a0.x + Af.y * Af.y / a0.y + Af.z * Af.z / a0.z) * g0.w / dot3(Af, ds);
+      const double oneMinusUrf = 1.0 - P.urf;
+      const double massFluxI = rhoF * (dot3(ld3(P.V, c0), Af) - oneMinusUrf * dot3(ld3(P.Vprev, c0), Af)) - Q * dpf +
+                               oneMinusUrf * P.massFlux[f];
+      const V3 Vb = ld3(P.V, c1);
+      const double massFluxB = rhoF * dot3(Vb, Af);
+      P.massFlux[f] = massFluxI;
+      double Vb_dpdVb = 0.0;
+      if (massFluxB < 0) Vb_dpdVb = -dot3(Vb, Vb) * rhoF;
+      const double denom = massFluxI - Q * Vb_dpdVb;
+      if (denom != 0) {
+        const double dMassFluxdp0 = -Q * massFluxI / denom;
+        P.bCoeffL[bf] = dMassFluxdp0;
+        P.bDiagAdd[bf] = -dMassFluxdp0;          // ppDiag[c0] -= dMassFluxdp0
+        P.bOff10[bf] = -Q * Vb_dpdVb / denom;    // coeff10 = dpbdp0
+      } else {                                   // treat as fixed pressure
+        P.bCoeffL[bf] = -Q;
+        P.bDiagAdd[bf] = Q;
+        P.bOff10[bf] = 0.0;
+      }
       return;
     }
     const double4 g0 = P.cellGeom[c0], g1 = P.cellGeom[c1];
@@ -450,8 +535,12 @@ struct ContinuityRows {  // pressure-correction matrix rows, F/FlowModelInterior
     const int i = (int)ii;
     const int r0 = P.row[i], r1 = P.row[i + 1];
     if (i >= P.nSelf) {
-      // fixedFluxContinuityBC on the ghost: ppDiag = -1, r = 0, coeff10 = 1, setBoundary
-      for (int k = r0; k < r1; k++) off[k] = 1.0;
+      // fixedFlux / fixedPressure ContinuityBC on the ghost: ppDiag = -1, r = 0, coeff10 = 1 (fixed flux) or
+      // dpbdp0 (pressure boundary), setBoundary
+      for (int k = r0; k < r1; k++) {
+        const int f = P.entryFace[k] >> 1;
+        off[k] = f >= P.nInteriorFaces ? P.bOff10[f - P.nInteriorFaces] : 1.0;
+      }
       diag[i] = -1.0;
       b[i] = 0.0;
       isBoundary[i] = 1;
@@ -470,6 +559,7 @@ struct ContinuityRows {  // pressure-correction matrix rows, F/FlowModelInterior
       } else {
         r -= mf;       // this row is c0 of the boundary face
         off[k] = 0.0;  // coeff01 = 0
+        d += P.bDiagAdd[f - P.nInteriorFaces];
       }
     }
     if (useReferencePressure) {
@@ -547,6 +637,50 @@ struct CorrectVelocityRows {  // correctVelocityInterior + correctVelocityBounda
     st3(Vout, i, v);
   }
 };
+struct CorrectBoundaryMassFluxFaces {  // flux row of a boundary face: dMassFlux = coeffL * pp[c0] (coeffR = 0, rFlux = 0)
+  int nInteriorFaces; const int* faceCells; const double* coeffL; const double* pp; double* massFlux;
+  FVM_DEV void operator()(long long k) const {
+    const int f = nInteriorFaces + (int)k;
+    massFlux[f] -= coeffL[k] * pp[faceCells[2 * f]];
+  }
+};
+// pressureBoundaryPostContinuitySolve, F/FlowModelPressureBC.h:161-212.
+// NB (reference ordering, reproduced): the reference treats the boundary groups one after the other
+// (correctVelocityBoundary, then this function, F/FlowModel_impl.h:1309-1330), so the neighbour's
+// velocity copied into an outflow ghost does not yet contain the velocity corrections of the boundary
+// faces in LATER groups (a corner cell touching the outlet and a wall). Here all corrections are
+// already applied, so those later contributions are taken out again.
+struct PressureBoundaryPostFaces {
+  ContParams P; const double* pp; double* V; double* p;
+  FVM_DEV void operator()(long long k) const {
+    const int f = P.nInteriorFaces + (int)k;
+    const FlowBcEntry* bc = faceBc(P.bcs, P.faceGroupOf, P.nInteriorFaces, f);
+    if (bc->kind != FVMGPU_FLOWBC_PRESSURE) return;
+    const int c0 = P.faceCells[2 * f], c1 = P.faceCells[2 * f + 1];
+    const double bp = bc->p[3];
+    const double rhoF = P.rho[c0];
+    const double4 fg = P.faceGeom[f];
+    if (P.massFlux[f] > 0) {
+      V3 v = ld3(V, c0);
+      const int myGroup = P.faceGroupOf[f - P.nInteriorFaces];
+      const V3 ap = ld3(P.momAp, c0);
+      for (int q = P.row[c0]; q < P.row[c0 + 1]; q++) {
+        const int f2 = P.entryFace[q] >> 1;
+        if (f2 < P.nInteriorFaces || P.faceGroupOf[f2 - P.nInteriorFaces] <= myGroup) continue;
+        const double4 g2 = P.faceGeom[f2];
+        const double ppFace = pp[P.col[q]];
+        v.x -= ppFace * g2.x / ap.x; v.y -= ppFace * g2.y / ap.y; v.z -= ppFace * g2.z / ap.z;
+      }
+      st3(V, c1, v);
+      p[c1] = bp;
+    } else {
+      const double Vn = -P.massFlux[f] / (rhoF * fg.w);
+      const V3 v = {-Vn * fg.x / fg.w, -Vn * fg.y / fg.w, -Vn * fg.z / fg.w};
+      st3(V, c1, v);
+      p[c1] = bp - 0.5 * rhoF * dot3(v, v);
+    }
+  }
+};
 struct FacePressureFaces {  // updateFacePressureInterior / Boundary
   ContParams P; double* pFace;
   FVM_DEV void operator()(long long ff) const {
@@ -586,6 +720,11 @@ Flow* flowCreate(Mesh* m) {
   F->massFlux.alloc(nf); F->contResid.alloc(nt); F->pGrad.alloc(3 * nt); F->vGrad.alloc(9 * nt); F->momAp.alloc(3 * nt);
   F->mDiag.alloc(3 * nt); F->mOff.alloc((size_t)m->nnz); F->mB.alloc(3 * nt); F->mDelta.alloc(3 * nt);
   F->pCoeff.alloc(nf);
+  {
+    const size_t nb = nf - (size_t)m->nInteriorFaces + 1;
+    F->bDiagAdd.alloc(nb); F->bOff10.alloc(nb); F->bCoeffL.alloc(nb);
+    F->bDiagAdd.zero(); F->bOff10.zero(); F->bCoeffL.zero();
+  }
   F->V.zero(); F->Vprev.zero(); F->p.zero(); F->pFace.zero(); F->massFlux.zero(); F->contResid.zero();
   F->pGrad.zero(); F->vGrad.zero(); F->momAp.zero(); F->mDiag.zero(); F->mOff.zero(); F->mB.zero(); F->mDelta.zero();
   F->pCoeff.zero();
@@ -648,8 +787,7 @@ void flowGetField(Flow* F, int field, double* host, long long n) {
 }
 void flowSetBc(Flow* F, int groupId, int kind, const double* p, int np) {
   requireReady();
-  if (kind != FVMGPU_FLOWBC_NOSLIP_WALL && kind != FVMGPU_FLOWBC_SYMMETRY)
-    fail("flow_set_bc: only NoSlipWall and Symmetry boundaries are supported in this release (kind %d)", kind);
+  if (kind < FVMGPU_FLOWBC_NOSLIP_WALL || kind > FVMGPU_FLOWBC_PRESSURE) fail("flow_set_bc: unknown boundary kind %d", kind);
   for (size_t g = 0; g < F->bcs.size(); g++) {
     const FaceGroup& fg = F->mesh->groups[g];
     if (fg.id == groupId && fg.kind != FVMGPU_GROUP_INTERIOR) {
@@ -667,6 +805,8 @@ static void flowSyncBcs(Flow* F) {
   for (size_t g = 1; g < F->bcs.size(); g++)
     if (F->bcs[g].kind < 0) fail("flow: boundary group %d has no boundary condition", F->mesh->groups[g].id);
   F->bcsDev.upload(F->bcs.data(), F->bcs.size());
+  F->hasPressureBoundary = false;
+  for (const FlowBcEntry& e : F->bcs) if (e.kind == FVMGPU_FLOWBC_PRESSURE) F->hasPressureBoundary = true;
   F->bcsDirty = false;
 }
 static ContParams contParams(Flow* F, double urf) {
@@ -677,6 +817,7 @@ static ContParams contParams(Flow* F, double urf) {
   P.faceGroupOf = m->faceGroupOf.p; P.cellGeom = m->cellGeom.p; P.faceGeom = m->faceGeom.p;
   P.V = F->V.p; P.Vprev = F->Vprev.p; P.momAp = F->momAp.p; P.p = F->p.p; P.pGrad = F->pGrad.p; P.rho = F->rho.p;
   P.bcs = F->bcsDev.p; P.massFlux = F->massFlux.p; P.pCoeff = F->pCoeff.p; P.urf = urf;
+  P.bDiagAdd = F->bDiagAdd.p; P.bOff10 = F->bOff10.p; P.bCoeffL = F->bCoeffL.p;
   return P;
 }
 static void flowContinuityResidual(Flow* F) {
@@ -768,6 +909,8 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
     if (iters) iters[k] = it;
     parallelFor(nt, MergeComponent{k, s->delta.p, F->mDelta.p, F->V.p});
   }
+  parallelFor(nt - m->nSelf, MomentumGhostRows{m->nSelf, m->row.p, m->col.p, s->isBoundary.p, F->mDiag.p, F->mOff.p,
+                                               F->mB.p, F->mDelta.p, F->V.p});
   copyD2D(F->momAp.p, F->mDiag.p, 3 * (size_t)nt * sizeof(double));
   F->hasMomAp = true;
 }
@@ -784,7 +927,8 @@ void flowAssembleContinuity(Flow* F, const fvmgpu_flow_opts& o) {
   reduceRows<1>(nb, BoundaryFluxSum{m->nInteriorFaces, F->massFlux.p}, F->scal.p + 0);
   reduceRows<1>(m->nSelf, VolumeSum{m->cellGeom.p}, F->scal.p + 1);
   System* s = F->pp.get();
-  ContinuityRows K{P, F->scal.p, 1, F->refCell, s->diag.p, s->off.p, s->b.p, s->isBoundary.p};
+  // a pressure boundary anchors the pressure level: no reference cell, no net-flux redistribution (:1052-1056)
+  ContinuityRows K{P, F->scal.p, F->hasPressureBoundary ? 0 : 1, F->refCell, s->diag.p, s->off.p, s->b.p, s->isBoundary.p};
   parallelFor(m->nTotal, K);
   s->delta.zero();
   s->version++;
@@ -814,12 +958,17 @@ void flowSolveContinuity(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, d
   double* pp = s->delta.p;
   parallelFor(m->nTotal - m->nSelf, PpGhostRows{m->nSelf, m->row.p, m->col.p, s->diag.p, s->off.p, s->b.p, pp});
   // setReferencePP: pp of the reference cell (read on the device, no host round trip)
-  parallelFor(m->nTotal, CorrectPressureRows{pp, pp + F->refCell, o.pressureURF, F->p.p});
+  parallelFor(m->nTotal, CorrectPressureRows{pp, F->hasPressureBoundary ? nullptr : pp + F->refCell, o.pressureURF, F->p.p});
   parallelFor(m->nInteriorFaces, CorrectMassFluxFaces{m->faceCells.p, m->pairToCol.p, s->off.p, pp, F->massFlux.p});
+  if (F->hasPressureBoundary)  // correctMassFluxBoundary: massFlux -= dMassFlux, the flux rows' solution (:831-842)
+    parallelFor(m->nFaces - m->nInteriorFaces, CorrectBoundaryMassFluxFaces{m->nInteriorFaces, m->faceCells.p, F->bCoeffL.p,
+                                                                            pp, F->massFlux.p});
   ContParams P = contParams(F, o.momentumURF);
   if (o.correctVelocity) {
     parallelFor(m->nSelf, CorrectVelocityRows{P, pp, F->V.p});  // in place: a row reads only its own velocity
   }
+  if (F->hasPressureBoundary)
+    parallelFor(m->nFaces - m->nInteriorFaces, PressureBoundaryPostFaces{P, pp, F->V.p, F->p.p});
   parallelFor(m->nFaces, FacePressureFaces{P, F->pFace.p});
   flowContinuityResidual(F);
   F->hasMomAp = false;  // the reference discards momAp after the continuity step

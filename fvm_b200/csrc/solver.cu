@@ -108,14 +108,34 @@ FVM_DEV void bfsExpand(int i, int d, int n, const int* row, const int* col, int*
   }
 }
 #ifndef FVMGPU_HOSTSIM
-}  // namespace fvmgpu
-#include <cooperative_groups.h>
-namespace fvmgpu {
+// Grid-wide barrier for cooperative kernels: one arrival counter that only grows (zeroed by the host
+// before the launch); the CTA's thread 0 arrives and spins until the whole grid has arrived for
+// this generation. Cheaper than cooperative_groups' grid.sync() (~1.5 us vs ~3.5 us measured per
+// barrier step here); all CTAs are co-resident by construction (cooperative launch).
+struct GridSync {
+  unsigned* bar;
+  __device__ __forceinline__ long long tid() const { return (long long)blockIdx.x * blockDim.x + threadIdx.x; }
+  __device__ __forceinline__ long long stride() const { return (long long)gridDim.x * blockDim.x; }
+  __device__ __forceinline__ void sync() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned old = atomicAdd(bar, 1u);
+      const unsigned target = (old / gridDim.x + 1u) * gridDim.x;
+      unsigned now;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(bar) : "memory");
+      } while (now < target);
+    }
+    __syncthreads();
+  }
+};
+// state[0], state[1]: queue sizes; state[2]: odd-cycle flag; state[3]: last depth; state[4]: barrier counter
 __global__ void __launch_bounds__(256) k_bfs_component(int n, const int* row, const int* col, int* depth, int* qA, int* qB,
                                                         int* state, int d0) {
-  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  GridSync grid{reinterpret_cast<unsigned*>(&state[4])};
+  const long long tid = grid.tid();
+  const long long nthreads = grid.stride();
   int d = d0;
   int* qin = qA; int* qout = qB;
   int* cin = &state[0]; int* cout = &state[1];
@@ -129,11 +149,12 @@ __global__ void __launch_bounds__(256) k_bfs_component(int n, const int* row, co
     if (m == 0 || odd) break;
     for (long long idx = tid; idx < m; idx += nthreads) bfsExpand(qin[idx], d, n, row, col, depth, qout, cout, &state[2]);
     grid.sync();
+    // the consumed counter becomes the next round's output counter: thread 0 clears it before it
+    // reaches the barrier at the top of the next round, i.e. before anybody appends to it
     if (tid == 0) { *cin = 0; state[3] = d + 1; }
     int* t = qin; qin = qout; qout = t;
     t = cin; cin = cout; cout = t;
     d++;
-    grid.sync();
   }
 }
 #endif
@@ -625,7 +646,7 @@ struct IotaDblKernel { double* p; FVM_DEV void operator()(long long i) const { p
 // ================================================================= level construction
 // Colour a CSR pattern; returns number of colours, fills colour[] (device)
 static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& colour) {
-  DBuf<int> depth(n), qA(n), qB(n), state(4), flags(1);
+  DBuf<int> depth(n), qA(n), qB(n), state(8), flags(1);
   depth.fillBytes(0xff);
   parallelFor(n, BfsIsolatedKernel{n, row, col, depth.p});
   const int big = 0x7fffffff;
@@ -641,7 +662,7 @@ static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& co
       return true;
     }
     const int seed = hf;
-    int hs[4] = {1, 0, 0, d0};
+    int hs[8] = {1, 0, 0, d0, 0, 0, 0, 0};
     copyH2D(state.p, hs, sizeof(hs));
     copyH2D(qA.p, &seed, sizeof(int));
     copyH2D(depth.p + seed, &d0, sizeof(int));
@@ -1242,29 +1263,6 @@ struct CtaSync {   // one CTA
   __device__ __forceinline__ long long stride() const { return blockDim.x; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
-// Grid-wide barrier for the cooperative kernel: one arrival counter that only grows (zeroed by the
-// host before the launch); the CTA's thread 0 arrives and spins until the whole grid has arrived
-// for this generation. Cheaper than cooperative_groups' grid.sync() (~1.5 us vs ~3.5 us measured
-// per barrier step here), and all CTAs are co-resident by construction (cooperative launch).
-struct GridSync {
-  unsigned* bar;
-  __device__ __forceinline__ long long tid() const { return (long long)blockIdx.x * blockDim.x + threadIdx.x; }
-  __device__ __forceinline__ long long stride() const { return (long long)gridDim.x * blockDim.x; }
-  __device__ __forceinline__ void sync() {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned old = atomicAdd(bar, 1u);
-      const unsigned target = (old / gridDim.x + 1u) * gridDim.x;
-      unsigned now;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(bar) : "memory");
-      } while (now < target);
-    }
-    __syncthreads();
-  }
-};
-
 // init + sum_j a_rj x_j accumulated in entry order, exactly like GsRows / JacobiRows / ResidualRows
 __device__ __forceinline__ double tailRowAcc(const TailLevel& L, int r, const double* x, double init) {
   const int s = r >> 5;

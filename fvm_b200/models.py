@@ -717,7 +717,8 @@ class FlowModelA:
     """Mirror of `models_atyped_double.FlowModelA` (F/FlowModel.h:17-95, F/FlowModel.i): SIMPLE
     iterations -- momentum assembly + solve, Rhie-Chow pressure correction assembly + solve, the
     pressure / mass-flux / velocity corrections -- all on the device through the C ABI
-    (fvmgpu_flow_*). Boundary types of this release: "NoSlipWall" and "Symmetry" (F/FlowModel_impl.h:636-640, 674-677)."""
+    (fvmgpu_flow_*). Boundary types: "NoSlipWall", "Symmetry", "VelocityBoundary", "PressureBoundary"
+    (F/FlowModel_impl.h:636-677); "SlipJump" is not built."""
 
     def __init__(self, geom_fields, flow_fields, meshes, lib=None):
         self.geom, self.fields, self.meshes, self.lib = geom_fields, flow_fields, list(meshes), lib
@@ -823,6 +824,10 @@ class FlowModelA:
                                                             float(bc["specifiedZVelocity"])])
             elif bc.bcType == "Symmetry":
                 fl.set_bc(fg.id, capi.FLOWBC_SYMMETRY, [0.0, 0.0, 0.0])
+            elif bc.bcType in ("VelocityBoundary", "PressureBoundary"):
+                kind = capi.FLOWBC_VELOCITY if bc.bcType == "VelocityBoundary" else capi.FLOWBC_PRESSURE
+                fl.set_bc(fg.id, kind, [float(bc["specifiedXVelocity"]), float(bc["specifiedYVelocity"]),
+                                        float(bc["specifiedZVelocity"]), float(bc["specifiedPressure"])])
             else:
                 raise CException(bc.bcType + " not implemented for FlowModel")
 

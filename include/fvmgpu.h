@@ -232,8 +232,8 @@ int fvmgpu_electric_drift_flux(fvmgpu_system_t potential, fvmgpu_system_t charge
 
 /* ---- FlowModel (SIMPLE): momentum + pressure-correction hot path (F/FlowModel_impl.h:522-1471,
  *      F/FlowModelInterior.h, F/FlowModelVelocityBC.h, F/MomentumPressureGradientDiscretization.h).
- *      This release covers wall-bounded flows (FlowBC::bcType "NoSlipWall", e.g. the lid-driven
- *      cavity); other boundary types are rejected. Vector cell fields are AoS (Vector<T,3>,
+ *      Boundary types: NoSlipWall, Symmetry, VelocityBoundary, PressureBoundary (SlipJump is not
+ *      built). One GPU per model in this release. Vector cell fields are AoS (Vector<T,3>,
  *      F/Vector.h:229; Gradient<Vector<T,3>> = 9 doubles [direction][component], F/Gradient.h:199). ---- */
 typedef struct fvmgpu_flow_s* fvmgpu_flow_t;  /* FlowFields of one mesh + the two linear systems */
 enum {
@@ -253,9 +253,16 @@ enum {
 };
 enum {
   FVMGPU_FLOWBC_NOSLIP_WALL = 0, /* applyDirichletBC(bVelocity); p[0..2] = specifiedX/Y/ZVelocity (F/FlowBC.h:10-21) */
-  FVMGPU_FLOWBC_SYMMETRY = 1     /* GenericBCS<Vector,DiagTensor,T>::applySymmetryBC (F/GenericBCS.h:569-615);
+  FVMGPU_FLOWBC_SYMMETRY = 1,    /* GenericBCS<Vector,DiagTensor,T>::applySymmetryBC (F/GenericBCS.h:569-615);
                                     zero mass flux; on face groups of kind SYMMETRY the velocity and pressure
                                     gradients of the ghost cells are reflected (F/GradientModel.h:21-86) */
+  FVMGPU_FLOWBC_VELOCITY = 2,    /* "VelocityBoundary": per face extrapolation where massFlux > 0, else Dirichlet
+                                    with p[0..2] (F/FlowModel_impl.h:650-668); fixed mass flux rho v.A in the
+                                    continuity equation (F/FlowModelVelocityBC.h:11-103) */
+  FVMGPU_FLOWBC_PRESSURE = 3     /* "PressureBoundary": the same momentum treatment + fixedPressureMomentumBC,
+                                    fixedPressureContinuityBC, pressureBoundaryPostContinuitySolve
+                                    (F/FlowModelPressureBC.h:11-216); p[3] = specifiedPressure. With a pressure
+                                    boundary present no reference cell / net-flux redistribution is used */
 };
 typedef struct {
   double momentumURF;   /* FlowModelOptions "momentumURF" (0.7)  F/FlowBC.h:42-50 */

@@ -20,6 +20,9 @@ hot path compiled in place by oracle/Makefile). Writes small .npz files next to 
   flow_symmetry.npz FlowModel in a jittered 6x5x4 hex box with two "symmetry" face groups and a moving lid:
                    momentum system from a developed state and the fields after 6 SIMPLE iterations with
                    tight inner solves
+  flow_channel.npz FlowModel channel flow on a jittered 14x8 quad mesh: VelocityBoundary inlet, PressureBoundary
+                   outlet, walls: momentum + pressure-correction systems from a developed state and the
+                   fields after 8 SIMPLE iterations with tight inner solves
   electric_box.npz ElectricModel on a jittered 6x5x7 hex box (1 x 1 x 2 um): Poisson equation with
                    SpecifiedPotential / SpecifiedPotentialFlux / Symmetry / SpecialDielectricBoundary
                    BCs and a uniform total charge, then drift + transient charge transport of the
@@ -230,6 +233,43 @@ def flow_symmetry_golden():
     print("flow_symmetry.npz: %d cells, group kinds %s" % (rm.n_self, rm.connectivity()["group_kind"]))
 
 
+def flow_channel_golden():
+    """Channel: VelocityBoundary inlet (u = 1), PressureBoundary outlet (p = 0.5), two walls."""
+    raw = G.quad_mesh(14, 8, lx=2.0, ly=1.0, jitter=0.15, seed=4)
+    rm = R.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes, raw.face_node_count,
+                            raw.face_group_size)
+    f = R.RefFlow(rm)
+    f.set_bc(1, "VelocityBoundary", specifiedXVelocity=1.0)
+    f.set_bc(2, "PressureBoundary", specifiedPressure=0.5)
+    f.set_bc(3, "NoSlipWall")
+    f.set_bc(4, "NoSlipWall")
+    f.set_vc("viscosity", 0.05)
+    f.set_vc("density", 1.2)
+    tight = dict(relativeTolerance=1e-14, nMaxIterations=3000, verbosity=0)
+    f.set_solver(0, R.solver_cfg(**tight))
+    f.set_solver(1, R.solver_cfg(**tight))
+    f.init()
+    out = {}
+    for it in range(8):
+        if it == 3:
+            for nm in ("velocity", "pressure", "facePressure", "massFlux", "continuityResidual"):
+                out["s0_" + nm] = f.field(nm).copy()
+            ms = f.momentum_system()
+            out.update(mom_diag=ms["diag"], mom_off=ms["offdiag"], mom_b=ms["b"])
+        f.solve_momentum()
+        if it == 3:
+            for nm in ("velocity", "previousVelocity", "momAp", "pressureGradient", "massFlux", "pressure"):
+                out["s1_" + nm] = f.field(nm).copy()
+            cs = f.continuity_system()
+            out.update(pp_diag=cs["diag"], pp_off=cs["offdiag"], pp_b=cs["b"], pp_is_boundary=cs["is_boundary"])
+            f.field("massFlux")[:] = out["s1_massFlux"]   # continuity_system advanced the face fluxes: restore
+        f.solve_continuity()
+    for nm in ("velocity", "pressure", "facePressure", "massFlux"):
+        out["end_" + nm] = f.field(nm).copy()
+    np.savez_compressed(os.path.join(HERE, "flow_channel.npz"), **mesh_arrays(rm), **out)
+    print("flow_channel.npz: %d cells" % rm.n_self)
+
+
 def electric_golden():
     raw = G.hex_mesh(6, 5, 7, lx=1e-6, ly=1e-6, lz=2e-6, jitter=0.15, seed=2)
     rm = R.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes, raw.face_node_count,
@@ -268,6 +308,9 @@ def electric_golden():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "flowchan":
+        flow_channel_golden()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "flowsym":
         flow_symmetry_golden()
         sys.exit(0)
