@@ -126,6 +126,7 @@ struct GridSync {
       do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(bar) : "memory");
       } while (now < target);
+      __threadfence();  // as cooperative_groups does after its spin: nothing read after the barrier may be stale
     }
     __syncthreads();
   }

@@ -24,13 +24,18 @@ def build_model(lib, raw, tol=1e-9, solver="amg"):
     tSolver.nMaxIterations = 2000
     tSolver.maxCoarseLevels = 20
     tSolver.verbosity = 2
-    if solver == "bcgstab":
+    if solver in ("bcgstab", "cg"):
         pc = tSolver
         pc.verbosity = 0
-        tSolver = M.BCGStab()
+        tSolver = M.BCGStab() if solver == "bcgstab" else M.CG()
         tSolver.preconditioner = pc
         tSolver.relativeTolerance = tol
         tSolver.nMaxIterations = 200
+    elif solver == "jacobi":
+        tSolver = M.JacobiSolver()
+        tSolver.relativeTolerance = tol
+        tSolver.nMaxIterations = 100000
+        tSolver.verbosity = 0
     tmodel.getOptions().linearSolver = tSolver
     return meshes, geomFields, thermalFields, tmodel, tSolver
 
@@ -83,7 +88,7 @@ def test_thermal_script_quad32(devlib, ref, tmp_path):
         assert abs(tmodel.getHeatFluxIntegral(meshes[0], fg.id) - hf.sum()) <= 1e-6 * max(abs(hf.sum()), 1.0)
 
 
-@pytest.mark.parametrize("solver", ["amg", "bcgstab"])
+@pytest.mark.parametrize("solver", ["amg", "bcgstab", "cg", "jacobi"])
 def test_default_outer_loop_converges(devlib, solver):
     """Default ThermalModel options: outer iterations until ratio < 1e-8 (F/ThermalBC.h:42-43)."""
     raw = G.hex_mesh(10, 10, 10, jitter=0.1, seed=2)
