@@ -99,6 +99,8 @@ SIGNATURES = {
     "fvmgpu_amg_levels": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int),
                                     np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"),
                                     np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), _ip]),
+    "fvmgpu_amg_level_order": (C.c_int, [_vp, C.c_int, C.c_longlong, _ip, C.POINTER(C.c_int),
+                                         np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]),
     "fvmgpu_solver_history": (C.c_int, [_vp, C.c_int, _dp, C.POINTER(C.c_int)]),
     "fvmgpu_bcgstab_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -568,6 +570,16 @@ class DeviceAMG:
         self.lib.call("fvmgpu_amg_levels", self.h, 64, C.byref(n), sizes, nnzs, cols)
         k = n.value
         return dict(sizes=sizes[:k].tolist(), nnz=nnzs[:k].tolist(), colours=cols[:k].tolist())
+
+    def level_order(self, level=0):
+        """(nat, colourStart): nat[r] = source row of level-row r; colour class c = level-rows
+        colourStart[c]:colourStart[c+1]."""
+        n = self.levels()["sizes"][level]
+        nat = np.zeros(max(n, 1), np.int32)
+        nc = C.c_int(0)
+        cs = np.zeros(65, np.int64)
+        self.lib.call("fvmgpu_amg_level_order", self.h, level, n, nat, C.byref(nc), cs)
+        return nat[:n], cs[:nc.value + 1].copy()
 
     def history(self):
         n = C.c_int(0)

@@ -377,6 +377,20 @@ int fvmgpu_amg_levels(fvmgpu_solver_t s, int cap, int* nLevels, long long* sizes
   }
   API_END
 }
+int fvmgpu_amg_level_order(fvmgpu_solver_t s, int level, long long cap, int* nat, int* nColours,
+                           long long* colourStart) {
+  API_BEGIN
+  Amg* a = A(s);
+  if (level < 0 || level >= (int)a->levels.size()) fail("fvmgpu_amg_level_order: no such level");
+  Level& L = *a->levels[level];
+  if (nColours) *nColours = L.nColours;
+  if (colourStart) for (int c = 0; c <= L.nColours; c++) colourStart[c] = L.colourStart[c];
+  if (nat) {
+    if (cap < L.n) fail("fvmgpu_amg_level_order: buffer too small");
+    if (L.n) L.nat.download(nat, (size_t)L.n);
+  }
+  API_END
+}
 int fvmgpu_solver_history(fvmgpu_solver_t s, int cap, double* out, int* n) {
   API_BEGIN
   Amg* a = A(s);

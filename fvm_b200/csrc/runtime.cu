@@ -26,10 +26,19 @@ void requireReady() {
 // Stream-ordered allocation from the device's default memory pool (release threshold = never):
 // the hierarchy is rebuilt every outer iteration (F/ThermalModel_impl.h:428,446), and a
 // cudaMalloc/cudaFree pair per buffer per iteration would cost more than the setup kernels.
+// FVMGPU_POISON=1 (debug): fill every new allocation with 0xFF bytes (NaN doubles, -1 ints) so that a
+// read of memory the library never wrote shows up as NaN / a fault instead of depending on what the
+// pool handed back
+static bool poisonAllocs() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("FVMGPU_POISON"); on = (e && atoi(e)) ? 1 : 0; }
+  return on == 1;
+}
 void* devAlloc(size_t bytes) {
   void* p = nullptr;
   if (ctx().stream) CUDA_CHECK(cudaMallocAsync(&p, bytes, ctx().stream));
   else CUDA_CHECK(cudaMalloc(&p, bytes));
+  if (poisonAllocs() && bytes) CUDA_CHECK(cudaMemsetAsync(p, 0xff, bytes, ctx().stream));
   return p;
 }
 void devFree(void* p) {
@@ -135,7 +144,13 @@ ProfileScope::ProfileScope(const char*, long long) : on(false) {}
 ProfileScope::~ProfileScope() {}
 void profileBegin() {}
 std::vector<ProfileRecord> profileEnd() { return {}; }
-void* devAlloc(size_t bytes) { return std::malloc(bytes ? bytes : 1); }
+void* devAlloc(size_t bytes) {
+  void* p = std::malloc(bytes ? bytes : 1);
+  static int poison = -1;
+  if (poison < 0) { const char* e = getenv("FVMGPU_POISON"); poison = (e && atoi(e)) ? 1 : 0; }
+  if (poison == 1 && p) std::memset(p, 0xff, bytes);
+  return p;
+}
 void devFree(void* p) { std::free(p); }
 void devMemset(void* p, int byte, size_t bytes) { std::memset(p, byte, bytes); }
 void copyH2D(void* d, const void* h, size_t bytes) { std::memcpy(d, h, bytes); ctx().h2d += (long long)bytes; }

@@ -74,6 +74,38 @@ struct ColourRoundKernel {
     colour[i] = c;
   }
 };
+// ---- structurally unsymmetric patterns (the reference's own testLinearSolver matrix mm226 stores 223
+// one-way entries): Jones-Plassmann must see i~j whenever EITHER a_ij or a_ji is stored, otherwise the
+// row that holds the one-way entry can end up in its neighbour's colour class -- a data race inside the
+// colour sweep and a colouring that depends on kernel timing. Detected per level; the symmetrised
+// pattern (duplicates allowed, they are harmless for colouring) is only built when needed.
+struct AsymmetryKernel {
+  int n; const int* row; const int* col; int* flag;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    for (int k = row[i]; k < row[i + 1]; k++) {
+      const int j = col[k];
+      if (j >= n || j == i) continue;
+      bool found = false;
+      for (int q = row[j]; q < row[j + 1]; q++) if (col[q] == i) { found = true; break; }
+      if (!found) { *flag = 1; return; }
+    }
+  }
+};
+struct SymEntriesKernel {  // entry k of row i -> (i, j) and (j, i); ghost / diagonal columns go to dummy row n
+  int n; const int* row; const int* col; int m; int* key; int* val; int* count;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    for (int k = row[i]; k < row[i + 1]; k++) {
+      const int j = col[k];
+      const bool real = j < n && j != i;
+      key[k] = real ? i : n;      val[k] = real ? j : 0;
+      key[m + k] = real ? j : n;  val[m + k] = real ? i : 0;
+      if (real) { atomicAdd(&count[i], 1); atomicAdd(&count[j], 1); }
+      else atomicAdd(&count[n], 2);
+    }
+  }
+};
 // ---- 2-colouring of bipartite patterns by breadth-first parity (structured hex / quad meshes are
 // bipartite; Jones-Plassmann needs 6-7 colours there). The search runs as ONE cooperative kernel:
 // frontier queues (work proportional to the edges, not rows x diameter) and a grid-wide barrier per
@@ -717,6 +749,28 @@ static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, s
   colour.alloc(n);
   colour.fillBytes(0xff);
   DBuf<int> flags(2);
+  DBuf<int> symRow, symCol;
+  {
+    flags.zero();
+    parallelFor(n, AsymmetryKernel{n, row, col, flags.p});
+    int asym = 0;
+    flags.download(&asym, 1);
+    if (asym) {
+      int m = 0;
+      copyD2H(&m, row + n, sizeof(int));
+      DBuf<int> key((size_t)2 * m), count((size_t)n + 1);
+      symCol.alloc((size_t)2 * m);
+      count.zero();
+      parallelFor(n, SymEntriesKernel{n, row, col, m, key.p, symCol.p, count.p});
+      symRow.alloc((size_t)n + 2);
+      exclusiveScan(count.p, symRow.p, (long long)n + 1);
+      int bits = 1;
+      while ((1 << bits) < n + 1) bits++;
+      sortPairs(key.p, symCol.p, 2LL * m, bits);  // stable: rows 0..n-1 first, the dummy row n last
+      row = symRow.p;
+      col = symCol.p;
+    }
+  }
   int rounds = 0;
   for (;;) {
     flags.zero();

@@ -197,6 +197,11 @@ int fvmgpu_amg_destroy(fvmgpu_solver_t s);
 /* hierarchy report: sizes[l] rows and nnzs[l] off-diagonal entries per level (level 0 = finest) */
 int fvmgpu_amg_levels(fvmgpu_solver_t s, int cap, int* nLevels, long long* sizes, long long* nnzs,
                       int* colours);
+/* smoother ordering of one level (inspection / tests): nat[r] = row of level-row r in the numbering the
+ * level was built from (level 0: the system's rows), colourStart[0..nColours] = first level-row of each
+ * colour class. Rows of one class are relaxed concurrently, so no stored a_ij may join two of them. */
+int fvmgpu_amg_level_order(fvmgpu_solver_t s, int level, long long cap, int* nat, int* nColours,
+                           long long* colourStart);
 /* residual history of the last solve: out[0..n-1], n returned */
 int fvmgpu_solver_history(fvmgpu_solver_t s, int cap, double* out, int* n);
 /* BCGStab::solve (F/BCGStab.cpp:26-170) right-preconditioned by one AMG cycle of `precond`;

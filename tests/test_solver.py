@@ -134,6 +134,26 @@ def test_solver_is_deterministic(devlib):
     assert np.array_equal(xs[0], xs[1])
 
 
+def test_colour_classes_are_independent_on_unsymmetric_pattern(devlib):
+    """mm226 (the reference's testLinearSolver matrix) stores 223 one-way entries. Rows of one colour class
+    are relaxed concurrently, so no stored a_ij -- in either direction -- may join two rows of a class."""
+    g = load_golden("mm226.npz")
+    n, row, col = int(g["n"]), g["row"], g["col"]
+    pairs = {(i, int(col[k])) for i in range(n) for k in range(row[i], row[i + 1])}
+    assert any((j, i) not in pairs for (i, j) in pairs if i != j)   # the fixture really is unsymmetric
+    ds = mm226_system(devlib, g)
+    amg = X.DeviceAMG(devlib)
+    amg.solve(ds)
+    nat, cs = amg.level_order(0)
+    assert sorted(nat.tolist()) == list(range(n))
+    colour = np.empty(n, np.int64)
+    for c in range(len(cs) - 1):
+        colour[nat[cs[c]:cs[c + 1]]] = c
+    bad = [(i, j) for (i, j) in pairs if i != j and j < n and colour[i] == colour[j]]
+    assert not bad, bad[:5]
+    amg.close(); ds.close()
+
+
 def test_hierarchy_is_rebuilt_when_the_matrix_changes(devlib):
     """AMG::solve keys its hierarchy on the LinearSystem (F/AMG.cpp:222-226); a re-assembled system
     must not be solved with stale coarse matrices."""
