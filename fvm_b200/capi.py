@@ -101,6 +101,7 @@ SIGNATURES = {
                                     np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), _ip]),
     "fvmgpu_amg_level_order": (C.c_int, [_vp, C.c_int, C.c_longlong, _ip, C.POINTER(C.c_int),
                                          np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]),
+    "fvmgpu_amg_last_timing": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "fvmgpu_solver_history": (C.c_int, [_vp, C.c_int, _dp, C.POINTER(C.c_int)]),
     "fvmgpu_bcgstab_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -580,6 +581,11 @@ class DeviceAMG:
         cs = np.zeros(65, np.int64)
         self.lib.call("fvmgpu_amg_level_order", self.h, level, n, nat, C.byref(nc), cs)
         return nat[:n], cs[:nc.value + 1].copy()
+
+    def last_timing(self):
+        a, b = C.c_double(0), C.c_double(0)
+        self.lib.call("fvmgpu_amg_last_timing", self.h, C.byref(a), C.byref(b))
+        return dict(setup_ms=a.value, cycles_ms=b.value)
 
     def history(self):
         n = C.c_int(0)

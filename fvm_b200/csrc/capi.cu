@@ -97,6 +97,7 @@ int fvmgpu_shutdown(void) {
   c.reduceScratch = nullptr;
   c.l2scratch = nullptr;
 #ifndef FVMGPU_HOSTSIM
+  devTrimCache();
   cudaStreamSynchronize(c.stream);
   for (int i = 0; i < 16; i++) { cudaEventDestroy(c.timerStart[i]); cudaEventDestroy(c.timerStop[i]); }
   cudaStreamDestroy(c.stream);
@@ -389,6 +390,13 @@ int fvmgpu_amg_level_order(fvmgpu_solver_t s, int level, long long cap, int* nat
     if (cap < L.n) fail("fvmgpu_amg_level_order: buffer too small");
     if (L.n) L.nat.download(nat, (size_t)L.n);
   }
+  API_END
+}
+int fvmgpu_amg_last_timing(fvmgpu_solver_t s, double* setup_ms, double* cycles_ms) {
+  API_BEGIN
+  Amg* a = A(s);
+  if (setup_ms) *setup_ms = a->lastSetupMs;
+  if (cycles_ms) *cycles_ms = a->lastCyclesMs;
   API_END
 }
 int fvmgpu_solver_history(fvmgpu_solver_t s, int cap, double* out, int* n) {

@@ -95,6 +95,7 @@ inline int ceilDiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 // ---------------------------------------------------------------- raw device memory
 void* devAlloc(size_t bytes);
 void devFree(void* p);
+void devTrimCache();  // device build: hand the cached free blocks back to the CUDA pool
 void devMemset(void* p, int byte, size_t bytes);          // stream ordered
 void copyH2D(void* d, const void* h, size_t bytes);       // stream ordered (pageable source: staged by the driver)
 void copyD2H(void* h, const void* d, size_t bytes);       // stream ordered + synchronises

@@ -6,6 +6,11 @@
 #ifndef FVMGPU_HOSTSIM
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <chrono>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 #else
 #include <algorithm>
 #include <numeric>
@@ -34,14 +39,97 @@ static bool poisonAllocs() {
   if (on < 0) { const char* e = getenv("FVMGPU_POISON"); on = (e && atoi(e)) ? 1 : 0; }
   return on == 1;
 }
+// FVMGPU_TRACE_ALLOC=1 (debug): report allocator calls that block the host for more than 1 ms
+static bool traceAllocs() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("FVMGPU_TRACE_ALLOC"); on = (e && atoi(e)) ? 1 : 0; }
+  return on == 1;
+}
+// Block cache in front of the pool. The hierarchy is rebuilt every outer iteration with the same
+// sequence of buffer sizes, but the pool cannot always serve an 800 MB request from its free list and
+// then maps fresh physical memory -- measured: single cudaMallocAsync calls blocking the host for
+// 100-770 ms inside a 640 ms step. Freed blocks of >= 1 MB are therefore kept here, keyed by size, and
+// handed back to the next request of (nearly) that size; everything runs on the one context stream, so
+// reuse is stream-ordered like the pool's own. The cache is capped (FVMGPU_CACHE_GB, default a quarter
+// of the device memory): past the cap it is released to the pool wholesale.
+namespace {
+struct BlockCache {
+  std::mutex mu;
+  std::multimap<size_t, void*> freeBlocks;
+  std::unordered_map<void*, size_t> live;  // big blocks handed out
+  size_t cachedBytes = 0, capBytes = 0;
+};
+BlockCache& blockCache() { static BlockCache c; return c; }
+constexpr size_t kCacheMinBytes = 1u << 20;
+}  // namespace
+void devTrimCache() {
+  BlockCache& c = blockCache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  for (auto& kv : c.freeBlocks) {
+    if (ctx().stream) cudaFreeAsync(kv.second, ctx().stream);
+    else cudaFree(kv.second);
+  }
+  c.freeBlocks.clear();
+  c.cachedBytes = 0;
+}
 void* devAlloc(size_t bytes) {
   void* p = nullptr;
-  if (ctx().stream) CUDA_CHECK(cudaMallocAsync(&p, bytes, ctx().stream));
-  else CUDA_CHECK(cudaMalloc(&p, bytes));
+  const bool big = bytes >= kCacheMinBytes && ctx().stream;
+  if (big) {
+    BlockCache& c = blockCache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.freeBlocks.lower_bound(bytes);
+    if (it != c.freeBlocks.end() && it->first <= bytes + bytes / 8) {
+      p = it->second;
+      c.live[p] = it->first;
+      c.cachedBytes -= it->first;
+      c.freeBlocks.erase(it);
+    }
+  }
+  if (!p) {
+    const auto t0 = std::chrono::steady_clock::now();
+    if (ctx().stream) CUDA_CHECK(cudaMallocAsync(&p, bytes, ctx().stream));
+    else CUDA_CHECK(cudaMalloc(&p, bytes));
+    if (traceAllocs()) {
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (ms > 1.0) fprintf(stderr, "[fvmgpu] alloc of %zu bytes blocked the host for %.2f ms\n", bytes, ms);
+    }
+    if (big) {
+      BlockCache& c = blockCache();
+      std::lock_guard<std::mutex> lock(c.mu);
+      c.live[p] = bytes;
+    }
+  }
   if (poisonAllocs() && bytes) CUDA_CHECK(cudaMemsetAsync(p, 0xff, bytes, ctx().stream));
   return p;
 }
 void devFree(void* p) {
+  if (!p) return;
+  bool trim = false;
+  {
+    BlockCache& c = blockCache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    auto it = c.live.find(p);
+    if (it != c.live.end() && ctx().stream) {
+      if (!c.capBytes) {
+        size_t freeB = 0, totalB = 0;
+        double gb = 0;
+        if (const char* e = getenv("FVMGPU_CACHE_GB")) gb = atof(e);
+        if (gb > 0) c.capBytes = (size_t)(gb * 1e9);
+        else if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) c.capBytes = totalB / 4;
+        else c.capBytes = (size_t)8 << 30;
+      }
+      c.freeBlocks.emplace(it->second, p);
+      c.cachedBytes += it->second;
+      c.live.erase(it);
+      trim = c.cachedBytes > c.capBytes;
+      p = nullptr;
+    } else if (it != c.live.end()) {
+      c.live.erase(it);
+    }
+  }
+  if (trim) devTrimCache();
+  if (!p) return;
   if (ctx().stream) cudaFreeAsync(p, ctx().stream);
   else cudaFree(p);
 }

@@ -24,6 +24,8 @@
 #include "solver.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cmath>
 
 namespace fvmgpu {
 
@@ -135,7 +137,21 @@ FVM_DEV void bfsExpand(int i, int d, int n, const int* row, const int* col, int*
     const int j = col[k];
     if (j >= n || j == i) continue;
     const int old = atomicCAS(&depth[j], -1, d + 1);
-    if (old == -1) qout[atomicAdd(cout, 1)] = j;
+    if (old == -1) {
+#if defined(__CUDA_ARCH__)
+      // one queue-tail atomic per warp instead of one per discovered row: a BFS appends every row of
+      // the level exactly once, and n atomics on ONE address cost more than the traversal itself
+      const unsigned active = __activemask();
+      const int lane = threadIdx.x & 31;
+      const int leader = __ffs(active) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(cout, __popc(active));
+      base = __shfl_sync(active, base, leader);
+      qout[base + __popc(active & ((1u << lane) - 1u))] = j;
+#else
+      qout[atomicAdd(cout, 1)] = j;
+#endif
+    }
     else if (((old ^ d) & 1) == 0) *odd = 1;
   }
 }
@@ -163,32 +179,33 @@ struct GridSync {
     __syncthreads();
   }
 };
-// state[0], state[1]: queue sizes; state[2]: odd-cycle flag; state[3]: last depth; state[4]: barrier counter
-__global__ void __launch_bounds__(256) k_bfs_component(int n, const int* row, const int* col, int* depth, int* qA, int* qB,
-                                                        int* state, int d0) {
+// state[0..2]: queue counters, rotating (round k consumes [k%3], fills [(k+1)%3], thread 0 clears [(k+2)%3]
+// for the round after); state[5], state[6]: odd-cycle flags, alternating per round; state[4]: barrier
+// counter; on exit state[7] = odd cycle seen, state[3] = last depth. What a round reads at its top (the
+// size of its queue, the previous round's flag) was final before the barrier that ended the previous
+// round, and nothing written during a round is read in the same round -- so ONE grid barrier per BFS
+// level is enough and every thread takes the same exit decision.
+__global__ void __launch_bounds__(1024) k_bfs_component(int n, const int* row, const int* col, int* depth, int* qA, int* qB,
+                                                         int* state, int d0) {
   GridSync grid{reinterpret_cast<unsigned*>(&state[4])};
   const long long tid = grid.tid();
   const long long nthreads = grid.stride();
   int d = d0;
   int* qin = qA; int* qout = qB;
-  int* cin = &state[0]; int* cout = &state[1];
-  for (;;) {
-    // read the loop state, THEN synchronise, then decide: the odd-cycle flag is written during the
-    // expansion phase, so a decision taken before every thread has read it would not be uniform
-    // (some threads would leave while the others wait at the barrier)
-    const int m = *(volatile int*)cin;
-    const int odd = *(volatile int*)&state[2];
-    grid.sync();
+  int odd = 0;
+  for (int k = 0;; k++) {
+    const int m = *(volatile int*)&state[k % 3];
+    odd = k > 0 ? *(volatile int*)&state[5 + ((k - 1) & 1)] : 0;
     if (m == 0 || odd) break;
-    for (long long idx = tid; idx < m; idx += nthreads) bfsExpand(qin[idx], d, n, row, col, depth, qout, cout, &state[2]);
+    if (tid == 0) state[(k + 2) % 3] = 0;
+    int* cout = &state[(k + 1) % 3];
+    int* oddOut = &state[5 + (k & 1)];
+    for (long long idx = tid; idx < m; idx += nthreads) bfsExpand(qin[idx], d, n, row, col, depth, qout, cout, oddOut);
     grid.sync();
-    // the consumed counter becomes the next round's output counter: thread 0 clears it before it
-    // reaches the barrier at the top of the next round, i.e. before anybody appends to it
-    if (tid == 0) { *cin = 0; state[3] = d + 1; }
     int* t = qin; qin = qout; qout = t;
-    t = cin; cin = cout; cout = t;
     d++;
   }
+  if (tid == 0) { state[7] = odd; state[3] = d; }
 }
 #endif
 
@@ -230,6 +247,7 @@ struct IfaceKeyKernel {
 };
 struct ClampColourKernel { int K; int* colour; FVM_DEV void operator()(long long i) const { if (colour[i] > K) colour[i] = K; } };
 struct RemapColourKernel { const int* remap; int* colour; FVM_DEV void operator()(long long i) const { colour[i] = remap[colour[i]]; } };
+struct ColourOneRows { const int* colour; FVM_DEV void operator()(long long i, double* o) const { o[0] = (double)colour[i]; } };
 struct ColourCountKernel {
   const int* colour; int* counts;
   FVM_DEV void operator()(long long i) const { atomicAdd(&counts[colour[i]], 1); }
@@ -349,6 +367,17 @@ struct ResidualRows {  // r = b + A x
     out[0] = fabs(v);
   }
 };
+// Residual after a multicolour Gauss-Seidel sweep: the rows of the colour relaxed LAST satisfy their
+// equation exactly (their neighbours are all of other colours and have not moved since), so only the
+// rows from `begin` on (the other colours) need the SpMV; the caller zeroes r[0, begin).
+struct ResidualRowsFrom {
+  int begin; ResidualRows R;
+  FVM_DEV void operator()(long long i, double* out) const {
+    const double v = R.compute(begin + (int)i);
+    R.r[begin + i] = v;
+    out[0] = fabs(v);
+  }
+};
 struct MultiplyRows {  // y = A x   (CRMatrix::multiply, F/CRMatrix.h:200-216)
   const int* sliceOff; const int* scol; const double* sval; const double* diag; const double* x; double* y;
   FVM_DEV void operator()(long long ii) const {
@@ -429,27 +458,36 @@ struct StrongestKernel {  // per row: the largest weight among eligible neighbou
     strongest[i] = best;
   }
 };
-// Edge preference among equal weights (both end points rank an edge identically, so the locally
-// best edge of a row is very often mutual and the handshake pairs almost everything in one or two
-// rounds): with a,b the NATURAL indices of the end points, a<b, d=b-a,
+// Edge preference among the STRONG connections of a row (weight within weightRatioThreshold of the
+// row's strongest -- the reference's own notion of "large enough", F/CRMatrix.h:553-555). Both end
+// points rank an edge identically, so the locally best edge of a row is very often mutual and the
+// handshake pairs almost everything in one or two rounds. With a,b the NATURAL indices of the end
+// points, a<b, d=b-a:
 //   1. smaller d         (x-neighbours before y before z on a structured numbering)
 //   2. even floor(a/d)   (parity along that direction: (0,1)(2,3).. rather than (1,2)(3,4)..)
-//   3. a symmetric hash
-// On structured grids this reproduces the regular x/y/z pairing the reference's sequential sweep
-// produces; on unstructured numberings it is just a consistent symmetric tie-break.
+//   3. larger weight, 4. a symmetric hash
+// On structured grids this gives the regular x / y / z pairing the reference's sequential sweep
+// produces in the interior AND keeps it regular along Neumann / Dirichlet boundaries (where the
+// diagonal-normalised weights differ by 1/5 : 1/6 and a strictly strongest-first choice pairs the
+// boundary layers in-plane): every coarse level of a hex / quad mesh is again a structured grid, i.e.
+// bipartite -> 2 colours instead of 7-10, and the cycle count drops by a third (hex 32^3: 76 -> 48).
+// On unstructured numberings it is a consistent symmetric choice among the strong connections.
+// FVMGPU_PAIR_STRONGEST_FIRST=1 restores weight-first ordering (w0 carries the weight then).
 struct EdgeKey {
-  float w; int d; int odd; unsigned h;
+  float w0, w; int d; int odd; unsigned h;
   FVM_DEV bool betterThan(const EdgeKey& o) const {
-    if (w != o.w) return w > o.w;
+    if (w0 != o.w0) return w0 > o.w0;
     if (d != o.d) return d < o.d;
     if (odd != o.odd) return odd < o.odd;
+    if (w != o.w) return w > o.w;
     return h > o.h;
   }
 };
-FVM_DEV EdgeKey makeEdgeKey(double w, int na, int nb) {
+FVM_DEV EdgeKey makeEdgeKey(double w, int na, int nb, int strongestFirst) {
   EdgeKey k;
   const int a = na < nb ? na : nb, b = na < nb ? nb : na;
   k.w = (float)w;  // float: last-bit noise of equal coefficients must not order the edges
+  k.w0 = strongestFirst ? k.w : 0.0f;
   k.d = b - a;
   k.odd = (a / k.d) & 1;
   k.h = edgeHash(a, b);
@@ -457,7 +495,7 @@ FVM_DEV EdgeKey makeEdgeKey(double w, int na, int nb) {
 }
 struct ProposeKernel {  // unassigned rows propose to their best unassigned strong neighbour
   int n; const int* sliceOff; const int* scol; const double* sval; const double* diag; const int* excluded;
-  const double* strongest; double threshold; const int* root; const int* nat; int* propose;
+  const double* strongest; double threshold; const int* root; const int* nat; int strongestFirst; int* propose;
   FVM_DEV void operator()(long long ii) const {
     const int i = (int)ii, s = i >> 5;
     int bestJ = -1;
@@ -465,7 +503,7 @@ struct ProposeKernel {  // unassigned rows propose to their best unassigned stro
       const double di = fabs(diag[i]);
       const double cut = threshold * strongest[i];
       EdgeKey best;
-      best.w = -1.0f; best.d = 0; best.odd = 0; best.h = 0;
+      best.w0 = 0.0f; best.w = -1.0f; best.d = 0; best.odd = 0; best.h = 0;
       const int end = sliceOff[s + 1];
       const int ni = nat[i];
       for (int p = sliceOff[s] + (i & 31); p < end; p += 32) {
@@ -475,7 +513,7 @@ struct ProposeKernel {  // unassigned rows propose to their best unassigned stro
         const double w = fabs(sval[p] / (di > dj ? di : dj));
         if (!(w > cut) && !(w >= strongest[i])) continue;  // strong connections only
         if (!(w > 0.0)) continue;
-        const EdgeKey k = makeEdgeKey(w, ni, nat[j]);
+        const EdgeKey k = makeEdgeKey(w, ni, nat[j], strongestFirst);
         if (bestJ < 0 || k.betterThan(best)) { best = k; bestJ = j; }
       }
     }
@@ -506,7 +544,7 @@ struct RoleProposeKernel {
       const double di = fabs(diag[i]);
       const double cut = threshold * strongest[i];
       EdgeKey best;
-      best.w = -1.0f; best.d = 0; best.odd = 0; best.h = 0;
+      best.w0 = 0.0f; best.w = -1.0f; best.d = 0; best.odd = 0; best.h = 0;
       const int end = sliceOff[s + 1];
       for (int p = sliceOff[s] + (i & 31); p < end; p += 32) {
         const int j = scol[p];
@@ -515,7 +553,7 @@ struct RoleProposeKernel {
         const double w = fabs(sval[p] / (di > dj ? di : dj));
         if (!(w > cut) && !(w >= strongest[i])) continue;
         if (!(w > 0.0)) continue;
-        const EdgeKey k = makeEdgeKey(w, nat[i], nat[j]);
+        const EdgeKey k = makeEdgeKey(w, nat[i], nat[j], 1);
         if (bestJ < 0 || k.betterThan(best)) { best = k; bestJ = j; }
       }
     }
@@ -530,12 +568,12 @@ struct RoleAcceptKernel {  // run over acceptors; writes root of both members (o
     if (root[j] >= 0 || (excluded && excluded[j]) || pairRole(nat[j], round) != 0) return;
     int bestI = -1;
     EdgeKey best;
-    best.w = -1.0f; best.d = 0; best.odd = 0; best.h = 0;
+    best.w0 = 0.0f; best.w = -1.0f; best.d = 0; best.odd = 0; best.h = 0;
     const int end = sliceOff[s + 1];
     for (int p = sliceOff[s] + (j & 31); p < end; p += 32) {
       const int i = scol[p];
       if (i >= n || i == j || propose[i] != j) continue;
-      const EdgeKey k = makeEdgeKey(fabs(sval[p]), nat[i], nat[j]);
+      const EdgeKey k = makeEdgeKey(fabs(sval[p]), nat[i], nat[j], 1);
       if (bestI < 0 || k.betterThan(best)) { best = k; bestI = i; }
     }
     if (bestI >= 0) {
@@ -694,7 +732,19 @@ static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& co
       parallelFor(n, ParityKernel{depth.p, colour.p});
       return true;
     }
-    const int seed = hf;
+    int seed = hf;
+    if (component == 0 && n > 4096) {
+      // The search costs one barrier + one dependent gather chain per BFS level, i.e. it scales with
+      // the eccentricity of the seed. The lowest row index is a corner of a structured mesh; the row in
+      // the middle of an (assumed cubic) natural numbering is near its centre and halves the depth.
+      // Any unreached row is a valid seed, so a wrong guess costs nothing.
+      const double c = std::cbrt((double)n);
+      long long cand = (long long)n / 2 + (long long)(c * c / 2) + (long long)(c / 2);
+      if (cand >= n) cand = n - 1;
+      int dc = 0;
+      copyD2H(&dc, depth.p + cand, sizeof(int));
+      if (dc == -1) seed = (int)cand;
+    }
     int hs[8] = {1, 0, 0, d0, 0, 0, 0, 0};
     copyH2D(state.p, hs, sizeof(hs));
     copyH2D(qA.p, &seed, sizeof(int));
@@ -711,26 +761,33 @@ static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& co
         std::swap(qin, qout); std::swap(cin, cout);
         d++;
       }
+      state.p[7] = state.p[2];
       ctx().launches++;
     }
 #else
     {
-      static int maxBlocks = 0;
+      // one 1024-thread CTA per SM: the arrival-counter barrier costs ~10 ns per arriving CTA, and a BFS
+      // level of a 256^3 mesh (<= 50 k frontier rows) never needs more threads than that
+      // (FVMGPU_BFS_CTAS_PER_SM=k launches k 256-thread CTAs per SM instead, for comparison)
+      static int maxBlocks = 0, threads = 1024;
       if (!maxBlocks) {
-        int perSm = 0;
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_bfs_component, 256, 0));
-        maxBlocks = perSm * ctx().smCount;
+        int perSm = 0, want = 0;
+        if (const char* e = getenv("FVMGPU_BFS_CTAS_PER_SM")) want = atoi(e);
+        if (want > 0) threads = 256;
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_bfs_component, threads, 0));
+        if (perSm < 1) fail("amg: k_bfs_component cannot be made resident");
+        maxBlocks = ctx().smCount * (want > 0 ? (want < perSm ? want : perSm) : 1);
       }
       int nn = n, dd = d0;
       int* depthP = depth.p; int* a = qA.p; int* b = qB.p; int* st = state.p;
       void* args[] = {&nn, (void*)&row, (void*)&col, &depthP, &a, &b, &st, &dd};
       ProfileScope prof("N6fvmgpu15k_bfs_componentE", n);
-      CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_bfs_component, dim3(maxBlocks), dim3(256), args, 0, ctx().stream));
+      CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_bfs_component, dim3(maxBlocks), dim3(threads), args, 0, ctx().stream));
       ctx().launches++;
     }
 #endif
-    state.download(hs, 4);
-    if (hs[2]) return false;       // odd cycle: not bipartite
+    state.download(hs, 8);
+    if (hs[7]) return false;       // odd cycle: not bipartite
     d0 = (hs[3] + 2) & ~1;         // next component restarts from an even depth
   }
   return false;                    // many components: leave it to the general colouring
@@ -738,13 +795,15 @@ static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& co
 
 static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, std::vector<int>& counts) {
   if (tryTwoColouring(n, row, col, colour)) {
-    DBuf<int> cnt2(64);
-    cnt2.zero();
-    parallelFor(n, ColourCountKernel{colour.p, cnt2.p});
-    std::vector<int> h2 = cnt2.toHost();
-    int nc2 = h2[1] > 0 ? 2 : 1;
-    counts.assign(h2.begin(), h2.begin() + nc2);
-    return nc2;
+    // class sizes: a sum of the 0/1 colours (exact in a double) instead of n atomics on two counters
+    DBuf<double> ones(1);
+    reduceRows<1>(n, ColourOneRows{colour.p}, ones.p);
+    double h1 = 0;
+    copyD2H(&h1, ones.p, sizeof(double));
+    const int n1 = (int)h1;
+    counts.assign(1, n - n1);
+    if (n1 > 0) counts.push_back(n1);
+    return (int)counts.size();
   }
   colour.alloc(n);
   colour.fillBytes(0xff);
@@ -891,9 +950,10 @@ static bool aggregate(Level& F, const int* excluded, double threshold, DBuf<int>
   root.fillBytes(0xff);
   parallelFor(n, StrongestKernel{n, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, excluded, strongest.p});
   const int kRounds = 6;
+  const int strongestFirst = (getenv("FVMGPU_PAIR_STRONGEST_FIRST") && atoi(getenv("FVMGPU_PAIR_STRONGEST_FIRST"))) ? 1 : 0;
   for (int r = 0; r < kRounds; r++) {
     parallelFor(n, ProposeKernel{n, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, excluded, strongest.p, threshold,
-                                 root.p, F.nat.p, propose.p});
+                                 root.p, F.nat.p, strongestFirst, propose.p});
     parallelFor(n, HandshakeKernel{propose.p, F.nat.p, root.p});
   }
   {  // directed strength: many rows left without a mutual partner -> role-based matching rounds
@@ -1726,8 +1786,17 @@ void Amg::cycleGraphed(int kind) {
     cycle(opts.cycleType, 0);
     if (kind == 0) {
       LevelTag tag(tagBase);
-      reduceRows<1>(L0.n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, L0.b.p, L0.x.p, L0.r.p},
-                    scalars.p);
+      const ResidualRows R{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, L0.b.p, L0.x.p, L0.r.p};
+      // the cycle ends with a post-sweep on level 0 whose last pass relaxes colour 0 = rows [0, colourStart[1])
+      static const bool fullResidual = getenv("FVMGPU_FULL_RESIDUAL") && atoi(getenv("FVMGPU_FULL_RESIDUAL")) != 0;
+      const bool lastColourExact = !fullResidual && !multi && opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL &&
+                                   opts.nPostSweeps >= 1 && !L0.hybridLast && L0.nColours >= 2;
+      if (lastColourExact) {
+        const int z = L0.colourStart[1];
+        devMemset(L0.r.p, 0, (size_t)z * sizeof(double));
+        reduceRows<1>(L0.n - z, ResidualRowsFrom{z, R}, scalars.p);
+      } else
+      reduceRows<1>(L0.n, R, scalars.p);
       if (multi) commAllreduceSum(scalars.p, 1);
       L0.rValid = true;
     }
@@ -1765,7 +1834,10 @@ void Amg::cycleGraphed(int kind) {
 // AMG::solve, F/AMG.cpp:219-282
 void Amg::solve(System* sys, double* rnorm0Out, double* rnormOut, int* itersOut) {
   requireReady();
+  const auto t0 = std::chrono::steady_clock::now();
   ensureSetup(sys);
+  streamSync();
+  const auto t1 = std::chrono::steady_clock::now();
   history.clear();
   loadSystem(sys, sys->b.p, sys->delta.p);
   levels[0]->xZero = false;  // delta may be non-zero on entry
@@ -1784,6 +1856,10 @@ void Amg::solve(System* sys, double* rnorm0Out, double* rnormOut, int* itersOut)
   }
   totalIterations += iters;
   storeDelta(sys->delta.p);
+  streamSync();
+  const auto t2 = std::chrono::steady_clock::now();
+  lastSetupMs = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  lastCyclesMs = std::chrono::duration<double, std::milli>(t2 - t1).count();
   if (rnorm0Out) *rnorm0Out = rNorm0;
   if (rnormOut) *rnormOut = rNorm;
   if (itersOut) *itersOut = iters;

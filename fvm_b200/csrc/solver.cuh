@@ -42,6 +42,7 @@ struct Amg {
   unsigned long long builtVersion = 0;
   std::vector<double> history;
   long long totalIterations = 0;
+  double lastSetupMs = 0, lastCyclesMs = 0;  // host wall clock of the last solve(): hierarchy build / cycle loop
   // coarse tail fused into one CTA (levels [tailStart, end) have <= kTailRows rows)
   static constexpr int kTailRows = 4096;
   int tailStart = -1, tailCount = 0;

@@ -202,6 +202,9 @@ int fvmgpu_amg_levels(fvmgpu_solver_t s, int cap, int* nLevels, long long* sizes
  * colour class. Rows of one class are relaxed concurrently, so no stored a_ij may join two of them. */
 int fvmgpu_amg_level_order(fvmgpu_solver_t s, int level, long long cap, int* nat, int* nColours,
                            long long* colourStart);
+/* host wall clock of the last fvmgpu_amg_solve, split into the hierarchy build (0 when the hierarchy
+ * was reused) and the cycle loop, in milliseconds */
+int fvmgpu_amg_last_timing(fvmgpu_solver_t s, double* setup_ms, double* cycles_ms);
 /* residual history of the last solve: out[0..n-1], n returned */
 int fvmgpu_solver_history(fvmgpu_solver_t s, int cap, double* out, int* n);
 /* BCGStab::solve (F/BCGStab.cpp:26-170) right-preconditioned by one AMG cycle of `precond`;
