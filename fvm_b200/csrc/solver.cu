@@ -1147,6 +1147,11 @@ void Amg::setup(System* sys) {
   }
   buildLevelFromCsr(L0, n, sys->row, sys->col, sys->off.p, sys->diag.p, !multi, perm0, sys->nTotal - n, multi,
                     ghostIsHalo.p);
+  if (natHint.p) {
+    DBuf<int> natural(n);
+    parallelFor(n, ComposeKernel{L0.nat.p, natHint.p, natural.p});
+    L0.nat = std::move(natural);
+  }
   if (multi) {
     Mesh* m = sys->mesh;
     const int ns = m->halo.nSend;
@@ -1271,7 +1276,14 @@ void Amg::buildMerged() {
     out.resize(bytes * nr);
     copyD2H(out.data(), rd.p, bytes * nr);
   };
-  std::vector<char> gLen, gCol, gVal, gDiag;
+  std::vector<char> gLen, gCol, gVal, gDiag, gNat;
+  {
+    // natural index of every row of this rank's level (padding rows: their own slot)
+    std::vector<int> natLocal = C.nat.toHost();
+    natLocal.resize((size_t)maxLocal);
+    for (int i = C.n; i < maxLocal; i++) natLocal[(size_t)i] = i;
+    gatherVec(natLocal.data(), (size_t)maxLocal * sizeof(int), gNat);
+  }
   gatherVec(bLen.data(), (size_t)maxLocal * sizeof(int), gLen);
   gatherVec(bCol.data(), maxNnz * sizeof(int), gCol);
   gatherVec(bVal.data(), maxNnz * sizeof(double), gVal);
@@ -1301,6 +1313,15 @@ void Amg::buildMerged() {
   nested.reset(new Amg);
   nested->opts = opts;
   nested->tagBase = tagBase + mergedLevel;
+  {
+    // the merged rows are the ranks' level rows in THEIR (colour-sorted) order; the pairing preference
+    // of the nested hierarchy needs the rank-major NATURAL order, in which index distance means something
+    std::vector<int> hint((size_t)N);
+    const int* gn = reinterpret_cast<const int*>(gNat.data());
+    for (int r = 0; r < nr; r++)
+      for (int i = 0; i < maxLocal; i++) hint[(size_t)r * maxLocal + i] = r * maxLocal + gn[(size_t)r * maxLocal + i];
+    nested->natHint.upload(hint.data(), hint.size());
+  }
   nested->setup(mergedSys.get());
   mergeSend.alloc((size_t)maxLocal); mergeSend.zero();
   mergeB.alloc((size_t)N); mergeX.alloc((size_t)N);

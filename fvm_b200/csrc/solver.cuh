@@ -53,6 +53,9 @@ struct Amg {
   std::vector<DBuf<int>> tailColourStarts;
   // captured (cycle [+ residual norm]) graphs
   bool useGraphs = true;
+  // optional: a permutation of [0, n) giving each system row a "natural" index for the pairing
+  // preference (merged coarse systems arrive in the colour-sorted order of the ranks' levels)
+  DBuf<int> natHint;
   void* graphExec[2] = {nullptr, nullptr};
   long long graphLaunches[2] = {0, 0};
 
