@@ -68,6 +68,9 @@ def make_case(name):
     if name == "hex_slabs":
         raw = G.hex_mesh(10, 9, 12, jitter=0.15, seed=3)
         method = "slabs"
+    elif name == "hex_box":      # uniform, even dimensions: the hierarchy must stay structured on every rank
+        raw = G.hex_mesh(16, 16, 16)
+        method = "slabs"
     elif name == "tet_rcb":
         raw = G.tet_mesh(6, 5, 7, jitter=0.2, seed=7)
         method = "rcb"
@@ -101,6 +104,8 @@ def main():
     loc = P.partition_mesh(raw, geo, part, rank)
     rng = np.random.default_rng(11)
     k_glob = np.exp(0.5 * rng.normal(size=raw.n_total))
+    if case == "hex_box":
+        k_glob[:] = 1.0
     bcs = {5: ("dirichlet", 300.0), 6: ("dirichlet", 400.0), 1: ("neumann", 5.0)}
 
     # ---- the checker: single-partition oracle on the global mesh
@@ -265,6 +270,7 @@ def main():
     out = dict(rank=rank, world=world, n_self=int(loc.n_cells), peers=[int(p) for p in h["peers"]],
                err_diag=err_diag, err_b=err_b, rel_l2=float(np.sqrt(float(t[0]) / float(t[1]))), ghost_err=ghost_err,
                r0=r0, r=r, iters=it, levels=[int(s) for s in levels["sizes"]],
+               colours=[int(c) for c in levels["colours"]],
                collectives=lib.comm_collectives())
     with open(os.path.join(os.environ["FVM_RESULT_DIR"], "rank%d.json" % rank), "w") as fh:
         json.dump(out, fh)

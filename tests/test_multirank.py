@@ -60,6 +60,17 @@ def test_two_ranks_match_single_partition_oracle(case, solver, merge):
     assert res[0]["r0"] == res[1]["r0"] and res[0]["iters"] == res[1]["iters"]
 
 
+def test_partitioned_hex_box_keeps_the_single_rank_hierarchy_quality():
+    """Aggregates never cross ranks and the merged coarse system is paired in the ranks' natural row
+    order, so a z-slab partition of a hex box coarsens exactly like the undivided box: two colours on
+    every level (distributed and merged) and the same cycle count up to the half-sweep ghost lag."""
+    one = run_world(1, "hex_box", "amg", 512)
+    two = run_world(2, "hex_box", "amg", 512)
+    check(two)
+    assert set(one[0]["colours"]) == {2} and set(two[0]["colours"]) == {2}
+    assert abs(two[0]["iters"] - one[0]["iters"]) <= max(3, one[0]["iters"] // 10), (one[0]["iters"], two[0]["iters"])
+
+
 def test_three_ranks_with_a_middle_part():
     res = run_world(3, "hex_slabs", "amg", 100)
     check(res)

@@ -154,6 +154,43 @@ def test_colour_classes_are_independent_on_unsymmetric_pattern(devlib):
     amg.close(); ds.close()
 
 
+def _hex_conduction(lib, nx, ny, nz, jitter=0.0):
+    from fvm_b200 import meshgen as G
+    raw = G.hex_mesh(nx, ny, nz, jitter=jitter, seed=4)
+    geo = G.metrics(raw)
+    row, col = G.connectivity(raw)
+    dm = X.DeviceMesh(lib, 3, raw.n_cells, raw.n_total, raw.face_cells, row, col, raw.group_offset,
+                      raw.group_count, raw.group_id, raw.group_kind)
+    dm.set_geometry(geo["face_area"], geo["face_area_mag"], geo["cell_centroid"], geo["cell_volume"],
+                    ib_type=np.full(raw.n_total, -1, np.int32))
+    ds = X.DeviceSystem(lib, dm)
+    ds.fill_field(X.FIELD_X, 300.0)
+    ds.set_bc(5, X.BC_DIRICHLET, [300.0])
+    ds.set_bc(6, X.BC_DIRICHLET, [400.0])
+    ds.assemble()
+    return dm, ds
+
+
+def test_hex_hierarchy_stays_structured(devlib):
+    """Pairing prefers, among the strong connections, the index-nearest partner with even parity: on a
+    hex mesh every coarse level is again a structured grid (x-, y-, z-pairs in turn), halves exactly and
+    is bipartite -- two colour classes per level, also along the Neumann / Dirichlet boundaries where the
+    diagonal-normalised weights (1/5 vs 1/6) would otherwise pair the boundary layers in-plane. The
+    reference's sequential sweep (F/CRMatrix.h:485-583) needs 165 cycles for 64^3; 16^3 takes 42 cycles
+    with strongest-first pairing and about 30 with this one."""
+    dm, ds = _hex_conduction(devlib, 16, 16, 16)
+    amg = X.DeviceAMG(devlib)
+    r0, r, it = amg.solve(ds)
+    lv = amg.levels()
+    assert lv["sizes"] == [4096 >> k for k in range(12)]
+    assert lv["colours"] == [2] * 12
+    assert r / r0 < 1e-8 and it <= 36
+    # both classes of a level have the same size (red-black)
+    nat, cs = amg.level_order(1)
+    assert cs.tolist() == [0, 1024, 2048]
+    amg.close(); ds.close(); dm.close()
+
+
 def test_hierarchy_is_rebuilt_when_the_matrix_changes(devlib):
     """AMG::solve keys its hierarchy on the LinearSystem (F/AMG.cpp:222-226); a re-assembled system
     must not be solved with stale coarse matrices."""
