@@ -55,6 +55,9 @@ def parse():
     # `python -m torch.distributed.run ... bench.py --n 128` as an ambiguous --nnodes/--nproc-per-node)
     p.add_argument("--size", dest="n", type=int, default=0,
                    help="cells per side of the per-GPU hex block (default 256: 256^3 cells per GPU)")
+    p.add_argument("--mesh", choices=("hex", "tet"), default="hex",
+                   help="tet: the same box cut into 6 jittered tetrahedra per hex (unstructured numbering of the "
+                        "coarse levels; single GPU; not the headline workload)")
     p.add_argument("--krylov", action="store_true",
                    help="NOT the headline: solve with the reference's BCGStab preconditioned by one AMG cycle "
                         "(F/BCGStab.cpp) instead of stand-alone AMG cycles; both arms honour it")
@@ -125,6 +128,7 @@ def global_dims(n, world):
 
 
 KRYLOV = False
+MESH = "hex"
 
 
 def build_case(n, lib, rank=0, world=1):
@@ -132,7 +136,11 @@ def build_case(n, lib, rank=0, world=1):
     elsewhere, T0 = 300. world > 1: this rank's z-slab of the global mesh, built
     directly with the reference partitioner's local numbering (fvm_b200.partition.hex_slab)."""
     from fvm_b200 import meshgen as G, models as M, partition as P
-    if world == 1:
+    if MESH == "tet":
+        if world != 1:
+            raise SystemExit("--mesh tet runs on one GPU (use tests/test_multigpu.py for partitioned tets)")
+        raw = G.tet_mesh(n, n, n)
+    elif world == 1:
         raw = G.hex_mesh(n, n, n)
     else:
         nx, ny, nz = global_dims(n, world)
@@ -293,14 +301,17 @@ def run_ours(args):
     sizes, nnzs = last["levels"]["sizes"], last["levels"]["nnz"]
     cyc = last["cycles"]
     # row visits by smoother / residual passes in the solve
-    row_visits = cyc * (sizes[0] * 3 + sum(sizes[1:]) * 2) + sizes[0]
+    # (a sweep with k colour classes visits (2k-1)/k of a level's rows; the level-0 residual (k-1)/k)
+    cols_ = [max(int(k), 1) for k in last["levels"]["colours"]]
+    row_visits = cyc * (sum(sz * (2 * k - 1) / k for sz, k in zip(sizes, cols_)) + sizes[0] * (cols_[0] - 1) / cols_[0]) + sizes[0]
+    mesh_desc = "structured hex mesh" if MESH == "hex" else "box cut into jittered tetrahedra (unstructured tet mesh)"
     out = {
-        "metric": METRIC, "value": ncells * world * args.steps / (total_ms * 1e-3), "unit": UNIT,
+        "metric": METRIC, "value": ncells * world * args.steps / max(total_ms * 1e-3, 1e-12), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D steady thermal diffusion, %s structured hex mesh (%d cells, %d per GPU), k=1, "
-                               "T=400/300 on z=top/z=0, %sAMG (V-cycle, multicolour GS, nPre 0 / nPost 1, group 2) "
-                               "to rel 1e-8, one outer iteration per step"
+        "config": {"workload": ("3D steady thermal diffusion, %s " + mesh_desc + " (%d cells, %d per GPU), k=1, "
+                                "T=400/300 on z=top/z=0, %sAMG (V-cycle, multicolour GS, nPre 0 / nPost 1, group 2) "
+                                "to rel 1e-8, one outer iteration per step")
                                % ("x".join(str(d) for d in global_dims(n, world)), ncells * world, ncells,
                                   "BCGStab preconditioned by one cycle of " if KRYLOV else ""),
                    "cells_per_gpu": ncells, "l2": "inputs (>= 1.8 GB of matrix per pass) exceed the 126 MB L2; "
@@ -314,8 +325,8 @@ def run_ours(args):
         "amg_cycles": cyc, "amg_levels": len(sizes), "level_sizes": sizes[:6], "level_colours": last["levels"]["colours"][:6],
         "phase_ms": {k: float(np.mean([s[k] for s in steps])) for k in ("assemble_ms", "solve_ms", "update_ms")},
         "residual": [last["rnorm0"], last["rnorm"]],
-        "solver_row_updates_per_s": row_visits / (last["solve_ms"] * 1e-3),
-        "assembly_cells_per_s": ncells / (float(np.mean([s["assemble_ms"] for s in steps])) * 1e-3),
+        "solver_row_updates_per_s": row_visits / max(last["solve_ms"] * 1e-3, 1e-12),
+        "assembly_cells_per_s": ncells / max(float(np.mean([s["assemble_ms"] for s in steps])) * 1e-3, 1e-12),
         "gpu_launches": int(l1 - l0),
         "e2e": {"value": ncells * world / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": int((h1[1] - h0[1]) / ne2e), "d2h_bytes_per_step": int((h1[2] - h0[2]) / ne2e),
@@ -362,7 +373,7 @@ def cycle_hbm(step, cycles_ms):
             total += 20.0 * n + 8.0 * sizes[l + 1]             # prolongation: ci, x read + write | coarse x
     peak, src = hbm_peak()
     cyc = max(int(step["cycles"]), 1)
-    achieved = total * cyc / (cycles_ms * 1e-3) / 1e9
+    achieved = total * cyc / max(cycles_ms * 1e-3, 1e-12) / 1e9
     return {"bytes_per_cycle": total, "ms_per_cycle": cycles_ms / cyc, "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "peak_source": src,
             "scope": "cycle loop of one GPU (all levels, graph launches, convergence checks); hierarchy build excluded"}
@@ -501,6 +512,7 @@ def run_reference(args):
 if __name__ == "__main__":
     a = parse()
     KRYLOV = bool(a.krylov)
+    MESH = a.mesh
     if a._worker:
         print(json.dumps(_ref_worker(a.ref_n, a.steps)))
     elif a.impl == "reference":

@@ -132,27 +132,36 @@ struct MinUnreachedKernel {  // flags[0] = smallest row index not reached yet
 struct ParityKernel { const int* depth; int* colour; FVM_DEV void operator()(long long i) const { colour[i] = depth[i] & 1; } };
 
 // state[0], state[1]: sizes of the two queues; state[2]: odd-cycle flag; state[3]: last depth used
+// A BFS level is one dependent chain per frontier row (queue -> row range -> columns -> depth CAS ->
+// queue tail -> store), so the neighbours of a row are taken in batches of 8: all column loads, then all
+// compare-and-swaps in flight together, then ONE queue-tail atomic for the rows the batch discovered --
+// instead of a CAS + tail atomic round trip per neighbour, one after the other.
 FVM_DEV void bfsExpand(int i, int d, int n, const int* row, const int* col, int* depth, int* qout, int* cout, int* odd) {
-  for (int k = row[i]; k < row[i + 1]; k++) {
-    const int j = col[k];
-    if (j >= n || j == i) continue;
-    const int old = atomicCAS(&depth[j], -1, d + 1);
-    if (old == -1) {
-#if defined(__CUDA_ARCH__)
-      // one queue-tail atomic per warp instead of one per discovered row: a BFS appends every row of
-      // the level exactly once, and n atomics on ONE address cost more than the traversal itself
-      const unsigned active = __activemask();
-      const int lane = threadIdx.x & 31;
-      const int leader = __ffs(active) - 1;
-      int base = 0;
-      if (lane == leader) base = atomicAdd(cout, __popc(active));
-      base = __shfl_sync(active, base, leader);
-      qout[base + __popc(active & ((1u << lane) - 1u))] = j;
-#else
-      qout[atomicAdd(cout, 1)] = j;
-#endif
+  const int end = row[i + 1];
+  for (int k0 = row[i]; k0 < end; k0 += 8) {
+    int js[8], olds[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      const int j = (k0 + t < end) ? col[k0 + t] : -1;
+      js[t] = (j >= 0 && j < n && j != i) ? j : -1;
     }
-    else if (((old ^ d) & 1) == 0) *odd = 1;
+#pragma unroll
+    for (int t = 0; t < 8; t++) olds[t] = js[t] >= 0 ? atomicCAS(&depth[js[t]], -1, d + 1) : 0x7ffffffe;
+    int fresh = 0;
+    bool sameParity = false;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      if (js[t] < 0) continue;
+      if (olds[t] == -1) fresh++;
+      else if (((olds[t] ^ d) & 1) == 0) sameParity = true;
+    }
+    if (sameParity) *odd = 1;
+    if (fresh) {
+      int base = atomicAdd(cout, fresh);
+#pragma unroll
+      for (int t = 0; t < 8; t++)
+        if (js[t] >= 0 && olds[t] == -1) qout[base++] = js[t];
+    }
   }
 }
 #ifndef FVMGPU_HOSTSIM

@@ -1,0 +1,36 @@
+"""bench.py's reporting logic on the GPU-less box: the kernels' host simulator stands in for the library
+(monkeypatched; the real bench loads fvm_b200/libfvmgpu.so and needs a B200), a tiny mesh for the
+workload. Checks that the one JSON line carries every key of the measurement contract."""
+import io
+import json
+import types
+from contextlib import redirect_stdout
+
+import pytest
+
+
+@pytest.mark.parametrize("mesh", ["hex", "tet"])
+def test_bench_json_line_has_the_contract_keys(hostsim_lib, monkeypatch, mesh):
+    import bench
+    from fvm_b200 import capi
+    monkeypatch.setattr(capi, "default_lib", lambda: hostsim_lib)
+    monkeypatch.setattr(bench, "MESH", mesh)
+    monkeypatch.setattr(bench, "KRYLOV", False)
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, n=6, no_profile=False, no_cpu_baseline=True, ref_n=0)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        bench.run_ours(args)
+    line = [l for l in buf.getvalue().splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "step_ms", "solve_split_ms",
+              "solve_hbm", "amg_cycles"):
+        assert k in d, k
+    assert d["metric"] == "fp64_cell_updates_per_s" and d["unit"] == "cell-updates/s" and d["dtype"] == "f64"
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert ("hex" in d["config"]["workload"]) == (mesh == "hex") and "%" not in d["config"]["workload"]
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["gpu_launches"] > 0 and d["amg_cycles"] > 0 and len(d["step_ms"]) == 2
+    assert 0 < d["solve_hbm"]["bytes_per_cycle"]
