@@ -723,6 +723,106 @@ struct ComposeGhostKernel {  // o[g] = b[a[g] - nMid]  (a: x index in the middle
 };
 struct IotaDblKernel { double* p; FVM_DEV void operator()(long long i) const { p[i] = (double)i; } };
 
+// ---- 2-colouring by tree parity (the default; the BFS below is kept for comparison, FVMGPU_BFS_COLOURING=1)
+// A bipartite graph has exactly one proper 2-colouring per component (up to the swap), and the depth
+// parity in ANY spanning tree gives it. So: every row links to its smallest-index neighbour below itself
+// (a forest, links strictly decrease), pointer jumping turns link[i] = 2*ancestor + parity-of-the-path
+// into 2*root + parity in O(log depth) full-width passes, trees joined by an edge are hooked root-to-
+// smaller-root with the parity offset that edge implies (Shiloach-Vishkin style, the tree count at
+// least halves per round), and a last pass over the edges VERIFIES the colouring -- an edge inside one
+// class means an odd cycle, i.e. the pattern is not bipartite and the general colouring takes over.
+// O((n + nnz) log n) work in ~15 streaming passes instead of one latency-bound step per BFS level
+// (256^3 hexes: 7.4 ms -> under 1 ms; a 2048^2 quad mesh has 4096 BFS levels). Colour 0 is the class of
+// the component's lowest row, whatever the order of the atomics: deterministic.
+struct TreeInitKernel {
+  int n; const int* row; const int* col; int* link;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    int best = i;
+    for (int k = row[i]; k < row[i + 1]; k++) {
+      const int j = col[k];
+      if (j < n && j < best) best = j;
+    }
+    link[i] = best == i ? 2 * i : 2 * best + 1;
+  }
+};
+struct TreeJumpKernel {  // in place: any value read from link[] is a valid (ancestor, parity) pair
+  int* link; int* changed;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    const int l = link[i], p = l >> 1;
+    if (p == i) return;
+    const int lp = *(volatile int*)&link[p];
+    const int gp = lp >> 1;
+    if (gp != p) { link[i] = 2 * gp + ((l ^ lp) & 1); *changed = 1; }
+  }
+};
+struct TreeHookKernel {  // links are fully jumped: link >> 1 is the root
+  int n; const int* row; const int* col; const int* link; int* hook; int* any;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    const int li = link[i], ri = li >> 1;
+    for (int k = row[i]; k < row[i + 1]; k++) {
+      const int j = col[k];
+      if (j >= n || j == i) continue;
+      const int lj = link[j], rj = lj >> 1;
+      if (rj == ri) continue;
+      const int q = (li ^ lj ^ 1) & 1;  // parity of root-to-root through this edge
+      atomicMin(&hook[ri > rj ? ri : rj], 2 * (ri < rj ? ri : rj) + q);
+      *any = 1;
+    }
+  }
+};
+struct TreeApplyHookKernel {
+  int* link; int* hook;
+  FVM_DEV void operator()(long long r) const {
+    const int h = hook[r];
+    if (h != 0x7f7f7f7f) { link[r] = h; hook[r] = 0x7f7f7f7f; }
+  }
+};
+struct TreeVerifyKernel {  // also writes the colour
+  int n; const int* row; const int* col; const int* link; int* colour; int* bad;
+  FVM_DEV void operator()(long long ii) const {
+    const int i = (int)ii;
+    const int li = link[i];
+    colour[i] = li & 1;
+    for (int k = row[i]; k < row[i + 1]; k++) {
+      const int j = col[k];
+      if (j >= n || j == i) continue;
+      const int lj = link[j];
+      if ((lj >> 1) != (li >> 1) || ((li ^ lj) & 1) == 0) { *bad = 1; return; }
+    }
+  }
+};
+static bool twoColouringByTreeParity(int n, const int* row, const int* col, DBuf<int>& colour) {
+  if (n >= (1 << 29)) return false;
+  DBuf<int> link(n), hook(n), flags(2);
+  hook.fillBytes(0x7f);
+  parallelFor(n, TreeInitKernel{n, row, col, link.p});
+  int h[2];
+  for (int round = 0; round < 64; round++) {
+    for (int jump = 0;; jump++) {
+      flags.zero();
+      parallelFor(n, TreeJumpKernel{link.p, flags.p});
+      flags.download(h, 1);
+      if (!h[0]) break;
+      if (jump > 64) return false;
+    }
+    flags.zero();
+    parallelFor(n, TreeHookKernel{n, row, col, link.p, hook.p, flags.p});
+    flags.download(h, 1);
+    if (!h[0]) {
+      colour.alloc(n);
+      flags.zero();
+      parallelFor(n, TreeVerifyKernel{n, row, col, link.p, colour.p, flags.p});
+      flags.download(h, 1);
+      return h[0] == 0;
+    }
+    parallelFor(n, TreeApplyHookKernel{link.p, hook.p});
+  }
+  return false;
+}
+
 // ================================================================= level construction
 // Colour a CSR pattern; returns number of colours, fills colour[] (device)
 static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& colour) {
@@ -803,7 +903,8 @@ static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& co
 }
 
 static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, std::vector<int>& counts) {
-  if (tryTwoColouring(n, row, col, colour)) {
+  static const bool useBfs = getenv("FVMGPU_BFS_COLOURING") && atoi(getenv("FVMGPU_BFS_COLOURING")) != 0;
+  if (useBfs ? tryTwoColouring(n, row, col, colour) : twoColouringByTreeParity(n, row, col, colour)) {
     // class sizes: a sum of the 0/1 colours (exact in a double) instead of n atomics on two counters
     DBuf<double> ones(1);
     reduceRows<1>(n, ColourOneRows{colour.p}, ones.p);

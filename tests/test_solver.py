@@ -191,6 +191,49 @@ def test_hex_hierarchy_stays_structured(devlib):
     amg.close(); ds.close(); dm.close()
 
 
+def test_two_colouring_of_a_scrambled_bipartite_pattern(devlib):
+    """Tree-parity 2-colouring (link to the lowest neighbour, pointer jumping, hooking of adjacent trees,
+    verification): two disjoint grids under a random renumbering have hundreds of local index minima,
+    so the forest needs several hooking rounds; the result must still be THE proper 2-colouring. A
+    triangle added to the pattern makes it non-bipartite: the verification must reject and the general
+    colouring take over (more than two classes, still valid)."""
+    rng = np.random.default_rng(5)
+
+    def grid_edges(nx, ny, base):
+        e = []
+        for y in range(ny):
+            for x in range(nx):
+                i = base + y * nx + x
+                if x + 1 < nx: e.append((i, i + 1))
+                if y + 1 < ny: e.append((i, i + nx))
+        return e
+
+    edges = grid_edges(23, 17, 0) + grid_edges(9, 31, 23 * 17)
+    n = 23 * 17 + 9 * 31
+    for extra in ([], [(0, 24)]):          # (0,1),(1,24),(0,24): a triangle
+        perm = rng.permutation(n)
+        adj = [[] for _ in range(n)]
+        for a, b in edges + extra:
+            adj[perm[a]].append(int(perm[b])); adj[perm[b]].append(int(perm[a]))
+        row = np.zeros(n + 1, np.int32)
+        row[1:] = np.cumsum([len(a) for a in adj])
+        col = np.array([j for a in adj for j in a], np.int32)
+        off = -np.ones(len(col))
+        diag = np.array([len(a) + 0.5 for a in adj], float)
+        b = rng.normal(size=n)
+        ds = X.DeviceSystem(devlib, raw=(n, 0, row, col, diag, off, b))
+        amg = X.DeviceAMG(devlib)
+        r0, r, it = amg.solve(ds)
+        assert r / r0 < 1e-8
+        nat, cs = amg.level_order(0)
+        colour = np.empty(n, np.int64)
+        for c in range(len(cs) - 1):
+            colour[nat[cs[c]:cs[c + 1]]] = c
+        assert all(colour[i] != colour[j] for i in range(n) for j in adj[i])
+        assert (len(cs) - 1 == 2) == (not extra)
+        amg.close(); ds.close()
+
+
 def test_hierarchy_is_rebuilt_when_the_matrix_changes(devlib):
     """AMG::solve keys its hierarchy on the LinearSystem (F/AMG.cpp:222-226); a re-assembled system
     must not be solved with stale coarse matrices."""
