@@ -378,12 +378,15 @@ struct ResidualRows {  // r = b + A x
 };
 // Residual after a multicolour Gauss-Seidel sweep: the rows of the colour relaxed LAST satisfy their
 // equation exactly (their neighbours are all of other colours and have not moved since), so only the
-// rows from `begin` on (the other colours) need the SpMV; the caller zeroes r[0, begin).
-struct ResidualRowsFrom {
-  int begin; ResidualRows R;
-  FVM_DEV void operator()(long long i, double* out) const {
-    const double v = R.compute(begin + (int)i);
-    R.r[begin + i] = v;
+// other rows need the SpMV; the caller zeroes r[skipFrom, skipTo). Across ranks this holds for the
+// INTERIOR rows of that colour only (the interface rows see ghost values refreshed after the pass);
+// rows are ordered interface-first inside a colour, so the skipped range starts behind them.
+struct ResidualRowsFrom {  // logical row t -> t below skipFrom, t + (skipTo - skipFrom) from there on
+  int skipFrom, skipTo; ResidualRows R;
+  FVM_DEV void operator()(long long t, double* out) const {
+    const int i = (int)t < skipFrom ? (int)t : (int)t + (skipTo - skipFrom);
+    const double v = R.compute(i);
+    R.r[i] = v;
     out[0] = fabs(v);
   }
 };
@@ -1920,12 +1923,12 @@ void Amg::cycleGraphed(int kind) {
       const ResidualRows R{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, L0.b.p, L0.x.p, L0.r.p};
       // the cycle ends with a post-sweep on level 0 whose last pass relaxes colour 0 = rows [0, colourStart[1])
       static const bool fullResidual = getenv("FVMGPU_FULL_RESIDUAL") && atoi(getenv("FVMGPU_FULL_RESIDUAL")) != 0;
-      const bool lastColourExact = !fullResidual && !multi && opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL &&
+      const bool lastColourExact = !fullResidual && opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL &&
                                    opts.nPostSweeps >= 1 && !L0.hybridLast && L0.nColours >= 2;
       if (lastColourExact) {
-        const int z = L0.colourStart[1];
-        devMemset(L0.r.p, 0, (size_t)z * sizeof(double));
-        reduceRows<1>(L0.n - z, ResidualRowsFrom{z, R}, scalars.p);
+        const int z0 = multi ? L0.ifaceCount[0] : 0, z1 = L0.colourStart[1];
+        if (z1 > z0) devMemset(L0.r.p + z0, 0, (size_t)(z1 - z0) * sizeof(double));
+        reduceRows<1>(L0.n - (z1 - z0), ResidualRowsFrom{z0, z1, R}, scalars.p);
       } else
       reduceRows<1>(L0.n, R, scalars.p);
       if (multi) commAllreduceSum(scalars.p, 1);
