@@ -119,6 +119,7 @@ SIGNATURES = {
     "fvmgpu_flow_get_field": (C.c_int, [_vp, C.c_int, _dp, C.c_longlong]),
     "fvmgpu_flow_set_bc": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int]),
     "fvmgpu_flow_init": (C.c_int, [_vp]),
+    "fvmgpu_flow_set_reference_cell": (C.c_int, [_vp, C.c_int]),
     "fvmgpu_flow_assemble_momentum": (C.c_int, [_vp, C.POINTER(FlowOpts)]),
     "fvmgpu_flow_download_momentum": (C.c_int, [_vp, _dp, _dp, _dp]),
     "fvmgpu_flow_solve_momentum": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_double, C.c_double, _dp, _ip]),
@@ -300,6 +301,10 @@ class DeviceFlow:
     def set_bc(self, group_id, kind, params):
         p = _f64(list(params) + [0.0] * (4 - len(params)))
         self.lib.call("fvmgpu_flow_set_bc", self.h, int(group_id), int(kind), p, 4)
+
+    def set_reference_cell(self, local_cell):
+        """Mesh parts only: local index of the globally lowest cell on the rank that owns it, -1 elsewhere."""
+        self.lib.call("fvmgpu_flow_set_reference_cell", self.h, int(local_cell))
 
     def init(self):
         self.lib.call("fvmgpu_flow_init", self.h)

@@ -478,6 +478,11 @@ int fvmgpu_flow_get_field(fvmgpu_flow_t flow, int field, double* host, long long
   flowGetField(FL(flow), field, host, n);
   API_END
 }
+int fvmgpu_flow_set_reference_cell(fvmgpu_flow_t flow, int localCell) {
+  API_BEGIN
+  flowSetReferenceCell(FL(flow), localCell);
+  API_END
+}
 int fvmgpu_flow_set_bc(fvmgpu_flow_t flow, int groupId, int bcKind, const double* p, int np) {
   API_BEGIN
   flowSetBc(FL(flow), groupId, bcKind, p, np);

@@ -19,7 +19,14 @@
 // Boundary types: NoSlipWall (applyDirichletBC), Symmetry (vector applySymmetryBC + reflected gradients),
 // VelocityBoundary and PressureBoundary (per-face extrapolation / Dirichlet, fixedPressureMomentumBC,
 // fixedPressureContinuityBC, boundary mass-flux rows, pressureBoundaryPostContinuitySolve); SlipJump,
-// turbulence and the PV-coupled solve are not built. One GPU per model in this release.
+// turbulence and the PV-coupled solve are not built.
+// Several GPUs (one mesh part each): partition-interface faces are treated like interior faces
+// everywhere (the reference loops discretizeMassFluxInterior / correctMassFluxInterior /
+// correctVelocityInterior / updateFacePressureInterior over mesh.getInterfaceGroups(),
+// F/FlowModel_impl.h:1027-1035,1297-1309), the ghost copies of V, p, grad V, grad p and momAp are
+// refreshed where the reference calls syncLocal (:768, :1011, :1334-1335) or its gradient / linear-system
+// syncs, net flux / volume / norms are all-reduced (:1134-1141, :1167-1169) and the reference pressure
+// correction comes from the rank that owns the globally lowest cell (:931-994, :1216-1230).
 // The momentum system's diagonal is a DiagonalTensor (one value per velocity component) with a
 // shared scalar off-diagonal: the three components are solved one after the other by the scalar
 // AMG on ONE hierarchy when their diagonals coincide (always the case without symmetry planes).
@@ -54,8 +61,10 @@ struct Flow {
   DBuf<FlowBcEntry> bcsDev;
   bool bcsDirty = true;
   bool hasMomAp = false, hasVN1 = false, hasVN2 = false;
-  int refCell = 0;
-  DBuf<double> scal;                         // device scalars: [0] netFlux, [1] volumeSum, [2..4] norms
+  int refCell = 0;                           // local index of the reference cell, -1: another rank owns it
+  bool multi = false;                        // mesh part of a partitioned mesh: halo exchanges + all-reduces
+  bool pressureBoundaryAnywhere = false;     // hasPressureBoundary or-ed over the ranks (agreed in flowInit)
+  DBuf<double> scal;                         // device scalars: [0] netFlux, [1] volumeSum, [2..4] norms, [6] reference pp
 };
 
 // ---------------------------------------------------------------- small helpers
@@ -75,6 +84,10 @@ FVM_DEV double harmonicAvg(double x0, double x1) {  // F/DiffusionDiscretization
 
 FVM_DEV const FlowBcEntry* faceBc(const FlowBcEntry* bcs, const int* faceGroupOf, int nInteriorFaces, int f) {
   return &bcs[faceGroupOf[f - nInteriorFaces]];
+}
+// interior faces and partition-interface faces (whose c1 is the ghost copy of a neighbour rank's cell)
+FVM_DEV bool interiorLike(const FlowBcEntry* bcs, const int* faceGroupOf, int nInteriorFaces, int f) {
+  return f < nInteriorFaces || bcs[faceGroupOf[f - nInteriorFaces]].groupKind == FVMGPU_GROUP_INTERFACE;
 }
 
 // ---------------------------------------------------------------- init: default mass flux
@@ -461,7 +474,7 @@ struct MassFluxFaces {
     const int c0 = P.faceCells[2 * f], c1 = P.faceCells[2 * f + 1];
     const double4 fg = P.faceGeom[f];
     const V3 Af = {fg.x, fg.y, fg.z};
-    if (f >= P.nInteriorFaces) {
+    if (!interiorLike(P.bcs, P.faceGroupOf, P.nInteriorFaces, f)) {
       const FlowBcEntry* bc = faceBc(P.bcs, P.faceGroupOf, P.nInteriorFaces, f);
       const int bf = f - P.nInteriorFaces;
       P.pCoeff[f] = 0.0;
@@ -520,9 +533,11 @@ struct MassFluxFaces {
   }
 };
 
-struct BoundaryFluxSum {  // netFlux over the fixed-flux boundary faces; volume of the interior cells
-  int nInteriorFaces; const double* massFlux;
-  FVM_DEV void operator()(long long k, double* o) const { o[0] = massFlux[nInteriorFaces + k]; }
+struct BoundaryFluxSum {  // netFlux over the boundary faces (not the partition interfaces); volume of the interior cells
+  int nInteriorFaces; const double* massFlux; const FlowBcEntry* bcs; const int* faceGroupOf;
+  FVM_DEV void operator()(long long k, double* o) const {
+    o[0] = bcs[faceGroupOf[k]].groupKind == FVMGPU_GROUP_INTERFACE ? 0.0 : massFlux[nInteriorFaces + k];
+  }
 };
 struct VolumeSum { const double4* cellGeom; FVM_DEV void operator()(long long i, double* o) const { o[0] = cellGeom[i].w; } };
 
@@ -551,7 +566,7 @@ struct ContinuityRows {  // pressure-correction matrix rows, F/FlowModelInterior
       const int ef = P.entryFace[k];
       const int f = ef >> 1;
       const double mf = P.massFlux[f];
-      if (f < P.nInteriorFaces) {
+      if (interiorLike(P.bcs, P.faceGroupOf, P.nInteriorFaces, f)) {
         const double pc = P.pCoeff[f];
         if (ef & 1) r += mf; else r -= mf;
         off[k] = -pc;
@@ -598,6 +613,20 @@ struct CorrectMassFluxFaces {  // correctMassFluxInterior, F/FlowModelInterior.h
     massFlux[f] -= off[pairToCol[2 * f]] * pp[c1] - off[pairToCol[2 * f + 1]] * pp[c0];
   }
 };
+// the same for the partition-interface faces: coeff01 = coeff10 = -pCoeff (the ghost row of the pressure-
+// correction matrix is not assembled here, F/FlowModelInterior.h:105-117)
+struct CorrectInterfaceMassFluxFaces {
+  int nInteriorFaces; const int* faceCells; const FlowBcEntry* bcs; const int* faceGroupOf; const double* pCoeff;
+  const double* pp; double* massFlux;
+  FVM_DEV void operator()(long long k) const {
+    if (bcs[faceGroupOf[k]].groupKind != FVMGPU_GROUP_INTERFACE) return;
+    const int f = nInteriorFaces + (int)k;
+    const int c0 = faceCells[2 * f], c1 = faceCells[2 * f + 1];
+    const double c = -pCoeff[f];
+    massFlux[f] -= c * pp[c1] - c * pp[c0];
+  }
+};
+struct ReferencePpKernel { const double* pp; int refCell; double* out; FVM_DEV void operator()(long long) const { out[0] = refCell >= 0 ? pp[refCell] : 0.0; } };
 // coefficients of the face pressure interpolation, F/FlowModelInterior.h:252-266, 335-349
 FVM_DEV void facePressureWeights(const ContParams& P, int f, int c0, int c1, double& coeff0, double& coeff1) {
   const double4 fg = P.faceGeom[f];
@@ -621,7 +650,7 @@ struct CorrectVelocityRows {  // correctVelocityInterior + correctVelocityBounda
       const int ef = P.entryFace[k];
       const int f = ef >> 1, side = ef & 1;
       const double4 fg = P.faceGeom[f];
-      if (f < P.nInteriorFaces) {
+      if (interiorLike(P.bcs, P.faceGroupOf, P.nInteriorFaces, f)) {
         const int c0 = side ? P.col[k] : i, c1 = side ? i : P.col[k];
         double w0, w1;
         facePressureWeights(P, f, c0, c1, w0, w1);
@@ -666,7 +695,8 @@ struct PressureBoundaryPostFaces {
       const V3 ap = ld3(P.momAp, c0);
       for (int q = P.row[c0]; q < P.row[c0 + 1]; q++) {
         const int f2 = P.entryFace[q] >> 1;
-        if (f2 < P.nInteriorFaces || P.faceGroupOf[f2 - P.nInteriorFaces] <= myGroup) continue;
+        if (interiorLike(P.bcs, P.faceGroupOf, P.nInteriorFaces, f2) || P.faceGroupOf[f2 - P.nInteriorFaces] <= myGroup)
+          continue;  // (interfaces are corrected with the interior faces, before every boundary group)
         const double4 g2 = P.faceGeom[f2];
         const double ppFace = pp[P.col[q]];
         v.x -= ppFace * g2.x / ap.x; v.y -= ppFace * g2.y / ap.y; v.z -= ppFace * g2.z / ap.z;
@@ -686,7 +716,7 @@ struct FacePressureFaces {  // updateFacePressureInterior / Boundary
   FVM_DEV void operator()(long long ff) const {
     const int f = (int)ff;
     const int c0 = P.faceCells[2 * f], c1 = P.faceCells[2 * f + 1];
-    if (f >= P.nInteriorFaces) { pFace[f] = P.p[c1]; return; }
+    if (!interiorLike(P.bcs, P.faceGroupOf, P.nInteriorFaces, f)) { pFace[f] = P.p[c1]; return; }
     double w0, w1;
     facePressureWeights(P, f, c0, c1, w0, w1);
     pFace[f] = (w0 * P.p[c0] + w1 * P.p[c1]) / (w0 + w1);
@@ -695,9 +725,11 @@ struct FacePressureFaces {  // updateFacePressureInterior / Boundary
 struct FillRows { double* p; double v; FVM_DEV void operator()(long long i) const { p[i] = v; } };
 
 // ================================================================= host side
-static System* makeScalarSystem(Mesh* m) {
+static System* makeScalarSystem(Mesh* m, bool multi) {
   std::unique_ptr<System> s(new System);
-  s->mesh = nullptr;  // solved as a stand-alone CSR system on the mesh's cellCells pattern
+  // solved as a stand-alone CSR system on the mesh's cellCells pattern; a mesh part keeps its mesh so that
+  // the solver finds the halo maps (interface ghost columns, distributed hierarchy)
+  s->mesh = multi ? m : nullptr;
   s->nSelf = m->nSelf; s->nTotal = m->nTotal; s->nnz = m->nnz;
   s->row = m->row.p; s->col = m->col.p;
   const size_t nt = (size_t)m->nTotal;
@@ -711,9 +743,9 @@ static System* makeScalarSystem(Mesh* m) {
 Flow* flowCreate(Mesh* m) {
   requireReady();
   if (!m->hasGeometry) fail("flow: mesh geometry not set (fvmgpu_mesh_set_geometry)");
-  if (commActive()) fail("flow: the FlowModel path is single-GPU in this release");
   std::unique_ptr<Flow> F(new Flow);
   F->mesh = m;
+  F->multi = commActive();  // every rank takes part in the all-reduces; an empty halo exchanges nothing
   F->nSelf = m->nSelf; F->nTotal = m->nTotal; F->nFaces = m->nFaces; F->nnz = m->nnz;
   const size_t nt = (size_t)m->nTotal, nf = (size_t)m->nFaces;
   F->V.alloc(3 * nt); F->Vprev.alloc(3 * nt); F->p.alloc(nt); F->pFace.alloc(nf); F->rho.alloc(nt); F->mu.alloc(nt);
@@ -730,8 +762,8 @@ Flow* flowCreate(Mesh* m) {
   F->pCoeff.zero();
   parallelFor((long long)nt, FillRows{F->rho.p, 1.0});
   parallelFor((long long)nt, FillRows{F->mu.p, 1e-3});
-  F->comp.reset(makeScalarSystem(m));
-  F->pp.reset(makeScalarSystem(m));
+  F->comp.reset(makeScalarSystem(m, F->multi));
+  F->pp.reset(makeScalarSystem(m, F->multi));
   F->lastDiag.alloc(nt);
   F->scal.alloc(16);
   F->scal.zero();
@@ -803,10 +835,12 @@ void flowSetBc(Flow* F, int groupId, int kind, const double* p, int np) {
 static void flowSyncBcs(Flow* F) {
   if (!F->bcsDirty) return;
   for (size_t g = 1; g < F->bcs.size(); g++)
-    if (F->bcs[g].kind < 0) fail("flow: boundary group %d has no boundary condition", F->mesh->groups[g].id);
+    if (F->bcs[g].kind < 0 && F->bcs[g].groupKind != FVMGPU_GROUP_INTERFACE)
+      fail("flow: boundary group %d has no boundary condition", F->mesh->groups[g].id);
   F->bcsDev.upload(F->bcs.data(), F->bcs.size());
   F->hasPressureBoundary = false;
   for (const FlowBcEntry& e : F->bcs) if (e.kind == FVMGPU_FLOWBC_PRESSURE) F->hasPressureBoundary = true;
+  if (!F->multi) F->pressureBoundaryAnywhere = F->hasPressureBoundary;  // across ranks: agreed in flowInit
   F->bcsDirty = false;
 }
 static ContParams contParams(Flow* F, double urf) {
@@ -820,6 +854,10 @@ static ContParams contParams(Flow* F, double urf) {
   P.bDiagAdd = F->bDiagAdd.p; P.bOff10 = F->bOff10.p; P.bCoeffL = F->bCoeffL.p;
   return P;
 }
+// MultiField::syncLocal for one cell field (width doubles per cell, AoS)
+static void flowExchange(Flow* F, DBuf<double>& field, int width) {
+  if (F->multi) F->mesh->halo.exchange(field.p, width);
+}
 static void flowContinuityResidual(Flow* F) {
   Mesh* m = F->mesh;
   parallelFor(m->nTotal, ContResidRows{m->row.p, m->entryFace.p, F->massFlux.p, F->contResid.p});
@@ -830,6 +868,9 @@ void flowInit(Flow* F) {
   requireReady();
   flowSyncBcs(F);
   Mesh* m = F->mesh;
+  F->pressureBoundaryAnywhere = F->multi ? commAny(F->hasPressureBoundary) : F->hasPressureBoundary;
+  // ghost copies of the fields the host uploaded (the reference's arrays arrive synced from the partitioner)
+  flowExchange(F, F->V, 3); flowExchange(F, F->p, 1); flowExchange(F, F->rho, 1); flowExchange(F, F->mu, 1);
   parallelFor(m->nFaces, FlowInitMassFluxFaces{m->nInteriorFaces, m->faceCells.p, m->faceGroupOf.p, m->faceGeom.p,
                                                F->V.p, F->rho.p, F->bcsDev.p, F->massFlux.p});
   flowContinuityResidual(F);
@@ -848,6 +889,8 @@ void flowAssembleMomentum(Flow* F, const fvmgpu_flow_opts& o) {
   parallelFor(m->nTotal, PressGradRows{m->nSelf, m->nInteriorFaces, m->row.p, m->col.p, m->entryFace.p,
                                        m->faceGroupOf.p, m->groupKindDev.p, m->faceGeom.p, m->cellGeom.p, F->pFace.p,
                                        F->pGrad.p});
+  flowExchange(F, F->vGrad, 9);   // GradientModel::compute ends with a sync of the gradient field
+  flowExchange(F, F->pGrad, 3);   // _flowFields.pressureGradient.syncLocal(), F/FlowModel_impl.h:1011
   MomParams P;
   P.nSelf = m->nSelf; P.nInteriorFaces = m->nInteriorFaces;
   P.row = m->row.p; P.col = m->col.p; P.entryFace = m->entryFace.p; P.faceGroupOf = m->faceGroupOf.p;
@@ -881,6 +924,7 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
   System* s = F->comp.get();
   // the reference returns the 1-norm of b per component (F/AMG.cpp:235)
   reduceRows<3>(m->nSelf, AbsRows3{F->mB.p}, F->scal.p + 2);
+  if (F->multi) commAllreduceSum(F->scal.p + 2, 3);
   double norms[3];
   copyD2H(norms, F->scal.p + 2, sizeof(norms));
   copyD2D(s->off.p, F->mOff.p, (size_t)m->nnz * sizeof(double));
@@ -890,6 +934,7 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
     bool same = false;
     if (haveHierarchy) {
       reduceRows<1>(m->nSelf, DiffCountRows{s->diag.p, F->lastDiag.p}, F->scal.p + 5);
+      if (F->multi) commAllreduceSum(F->scal.p + 5, 1);  // every rank must take the same decision
       double nd;
       copyD2H(&nd, F->scal.p + 5, sizeof(double));
       same = nd == 0.0;
@@ -912,6 +957,7 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
   parallelFor(nt - m->nSelf, MomentumGhostRows{m->nSelf, m->row.p, m->col.p, s->isBoundary.p, F->mDiag.p, F->mOff.p,
                                                F->mB.p, F->mDelta.p, F->V.p});
   copyD2D(F->momAp.p, F->mDiag.p, 3 * (size_t)nt * sizeof(double));
+  flowExchange(F, F->momAp, 3);   // _momApField->syncLocal(), F/FlowModel_impl.h:768
   F->hasMomAp = true;
 }
 
@@ -924,11 +970,12 @@ void flowAssembleContinuity(Flow* F, const fvmgpu_flow_opts& o) {
   ContParams P = contParams(F, o.momentumURF);
   parallelFor(m->nFaces, MassFluxFaces{P});
   const int nb = m->nFaces - m->nInteriorFaces;
-  reduceRows<1>(nb, BoundaryFluxSum{m->nInteriorFaces, F->massFlux.p}, F->scal.p + 0);
+  reduceRows<1>(nb, BoundaryFluxSum{m->nInteriorFaces, F->massFlux.p, F->bcsDev.p, m->faceGroupOf.p}, F->scal.p + 0);
   reduceRows<1>(m->nSelf, VolumeSum{m->cellGeom.p}, F->scal.p + 1);
+  if (F->multi) commAllreduceSum(F->scal.p, 2);   // F/FlowModel_impl.h:1134-1141, 1167-1169
   System* s = F->pp.get();
   // a pressure boundary anchors the pressure level: no reference cell, no net-flux redistribution (:1052-1056)
-  ContinuityRows K{P, F->scal.p, F->hasPressureBoundary ? 0 : 1, F->refCell, s->diag.p, s->off.p, s->b.p, s->isBoundary.p};
+  ContinuityRows K{P, F->scal.p, F->pressureBoundaryAnywhere ? 0 : 1, F->refCell, s->diag.p, s->off.p, s->b.p, s->isBoundary.p};
   parallelFor(m->nTotal, K);
   s->delta.zero();
   s->version++;
@@ -957,9 +1004,24 @@ void flowSolveContinuity(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, d
   if (iters) *iters = it;
   double* pp = s->delta.p;
   parallelFor(m->nTotal - m->nSelf, PpGhostRows{m->nSelf, m->row.p, m->col.p, s->diag.p, s->off.p, s->b.p, pp});
-  // setReferencePP: pp of the reference cell (read on the device, no host round trip)
-  parallelFor(m->nTotal, CorrectPressureRows{pp, F->hasPressureBoundary ? nullptr : pp + F->refCell, o.pressureURF, F->p.p});
+  if (F->multi) m->halo.exchange(pp, 1);  // the interface ghosts hold the owner's pp again (their rows are not equations here)
+  // setReferencePP: pp of the reference cell (read on the device, no host round trip); across ranks the
+  // owner of the globally lowest cell contributes it and the others 0 (F/FlowModel_impl.h:1216-1230)
+  const double* refPP = nullptr;
+  if (!F->pressureBoundaryAnywhere) {
+    if (F->multi) {
+      parallelFor(1, ReferencePpKernel{pp, F->refCell, F->scal.p + 6});
+      commAllreduceSum(F->scal.p + 6, 1);
+      refPP = F->scal.p + 6;
+    } else {
+      refPP = pp + F->refCell;
+    }
+  }
+  parallelFor(m->nTotal, CorrectPressureRows{pp, refPP, o.pressureURF, F->p.p});
   parallelFor(m->nInteriorFaces, CorrectMassFluxFaces{m->faceCells.p, m->pairToCol.p, s->off.p, pp, F->massFlux.p});
+  if (F->multi)
+    parallelFor(m->nFaces - m->nInteriorFaces, CorrectInterfaceMassFluxFaces{m->nInteriorFaces, m->faceCells.p, F->bcsDev.p,
+                                                                             m->faceGroupOf.p, F->pCoeff.p, pp, F->massFlux.p});
   if (F->hasPressureBoundary)  // correctMassFluxBoundary: massFlux -= dMassFlux, the flux rows' solution (:831-842)
     parallelFor(m->nFaces - m->nInteriorFaces, CorrectBoundaryMassFluxFaces{m->nInteriorFaces, m->faceCells.p, F->bCoeffL.p,
                                                                             pp, F->massFlux.p});
@@ -969,9 +1031,18 @@ void flowSolveContinuity(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, d
   }
   if (F->hasPressureBoundary)
     parallelFor(m->nFaces - m->nInteriorFaces, PressureBoundaryPostFaces{P, pp, F->V.p, F->p.p});
+  flowExchange(F, F->V, 3);   // _flowFields.velocity.syncLocal(); pressure.syncLocal(), F/FlowModel_impl.h:1334-1335
+  flowExchange(F, F->p, 1);
   parallelFor(m->nFaces, FacePressureFaces{P, F->pFace.p});
   flowContinuityResidual(F);
   F->hasMomAp = false;  // the reference discards momAp after the continuity step
+}
+
+// F/FlowModel_impl.h:931-994: the reference cell is the globally lowest fluid cell; the rank that owns it
+// passes its local index, every other rank -1
+void flowSetReferenceCell(Flow* F, int localCell) {
+  if (localCell >= F->nSelf) fail("flow_set_reference_cell: cell %d is not an interior cell of this mesh part", localCell);
+  F->refCell = localCell;
 }
 
 void flowDestroy(Flow* F) { delete F; }

@@ -145,6 +145,7 @@ void flowSetField(Flow* F, int field, const double* host, long long n, bool fill
 void flowGetField(Flow* F, int field, double* host, long long n);
 void flowSetBc(Flow* F, int groupId, int kind, const double* p, int np);
 void flowInit(Flow* F);
+void flowSetReferenceCell(Flow* F, int localCell);
 void flowAssembleMomentum(Flow* F, const fvmgpu_flow_opts& o);
 void flowDownloadMomentum(Flow* F, double* diag3, double* off, double* b3);
 void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, double bcgRel, double bcgAbs,

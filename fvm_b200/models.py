@@ -718,7 +718,8 @@ class FlowModelA:
     iterations -- momentum assembly + solve, Rhie-Chow pressure correction assembly + solve, the
     pressure / mass-flux / velocity corrections -- all on the device through the C ABI
     (fvmgpu_flow_*). Boundary types: "NoSlipWall", "Symmetry", "VelocityBoundary", "PressureBoundary"
-    (F/FlowModel_impl.h:636-677); "SlipJump" is not built."""
+    (F/FlowModel_impl.h:636-677); "SlipJump" is not built. On a partitioned mesh (fvm_b200.partition) every
+    rank runs this same code on its part; halo exchanges and all-reduces happen inside the library."""
 
     def __init__(self, geom_fields, flow_fields, meshes, lib=None):
         self.geom, self.fields, self.meshes, self.lib = geom_fields, flow_fields, list(meshes), lib
@@ -793,6 +794,10 @@ class FlowModelA:
             lib = self.lib or mesh.device.lib
             fl = capi.DeviceFlow(lib, mesh.device)
             self._flows[mesh.getID()] = fl
+            if "cell_global" in mesh.raw:   # a mesh part: the reference cell is the globally lowest cell (:931-994)
+                own = np.asarray(mesh.raw.cell_global)[:mesh.raw.n_cells]
+                hit = np.nonzero(own == 0)[0]
+                fl.set_reference_cell(int(hit[0]) if len(hit) else -1)
             self._upload(mesh, fl, with_flux=False)
             fl.init()
             f.massFlux[faces][:] = fl.get_field(capi.FLOW_MASS_FLUX)

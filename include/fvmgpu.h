@@ -286,6 +286,9 @@ int fvmgpu_flow_set_field(fvmgpu_flow_t flow, int field, const double* host, lon
 int fvmgpu_flow_fill_field(fvmgpu_flow_t flow, int field, double value);
 int fvmgpu_flow_get_field(fvmgpu_flow_t flow, int field, double* host, long long n);
 int fvmgpu_flow_set_bc(fvmgpu_flow_t flow, int groupId, int bcKind, const double* p, int np);
+/* multi-GPU only: the reference pressure-correction cell is the globally lowest fluid cell
+ * (F/FlowModel_impl.h:931-994); its owner passes the local index, every other rank -1 (default 0) */
+int fvmgpu_flow_set_reference_cell(fvmgpu_flow_t flow, int localCell);
 /* FlowModel::init: default face mass fluxes + continuity residual (F/FlowModel_impl.h:222-340) */
 int fvmgpu_flow_init(fvmgpu_flow_t flow);
 /* initMomentumLinearization + initAssembly + linearizeMomentum + initSolve (:522-737) */

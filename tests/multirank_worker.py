@@ -179,6 +179,60 @@ def main():
         dist.destroy_process_group()
         return
 
+    if solver_kind == "flow":
+        # FlowModelA (SIMPLE: momentum + Rhie-Chow pressure correction) on this rank's part of a lid-driven
+        # box, three outer iterations with tight inner solves; checked against the single-partition run of
+        # the same code, which tests/test_flow.py pins to the reference's FlowModel
+        import contextlib
+        import io
+        from fvm_b200 import models as M
+
+        def run(mesh_raw, use_lib):
+            mesh = M.Mesh(mesh_raw)
+            geomf = M.GeomFields("geom")
+            M.MeshMetricsCalculatorA(geomf, [mesh], lib=use_lib).init()
+            ff = M.FlowFields("flow")
+            fm = M.FlowModelA(geomf, ff, [mesh], lib=use_lib)
+            bcm = fm.getBCMap()
+            for gid, bc in bcm.items():
+                bc.bcType = "NoSlipWall"
+            if 4 in bcm:
+                bcm[4]["specifiedXVelocity"] = 1.0     # the lid (y = top) moves along x
+                bcm[4]["specifiedZVelocity"] = 0.3
+            o = fm.getOptions()
+            for nm in ("momentumLinearSolver", "pressureLinearSolver"):
+                sv = M.AMG()
+                sv.relativeTolerance, sv.nMaxIterations, sv.verbosity = 1e-13, 3000, 0
+                setattr(o, nm, sv)
+            vc = fm.getVCMap()[mesh.getID()]
+            vc["viscosity"] = 0.05
+            fm.init()
+            with contextlib.redirect_stdout(io.StringIO()):
+                fm.advance(3)
+            cells, faces = mesh.getCells(), mesh.getFaces()
+            return ff.velocity[cells].copy(), ff.pressure[cells].copy(), ff.massFlux[faces].copy()
+
+        lib.comm_destroy()
+        v_ref, p_ref, _ = run(raw, lib)
+        lib.comm_init(world, rank)
+        v, pr, mf = run(loc, lib)
+        own = loc.cell_global[:loc.n_cells]
+        num = float(((v[:loc.n_cells] - v_ref[own]) ** 2).sum()) + float(((pr[:loc.n_cells] - p_ref[own]) ** 2).sum())
+        den = float((v_ref[own] ** 2).sum()) + float((p_ref[own] ** 2).sum())
+        t = torch.tensor([num, den])
+        dist.all_reduce(t)
+        gi = loc.halo["gather_idx"]
+        ghost_err = float(np.abs(v[gi] - v_ref[loc.cell_global[gi]]).max()) if len(gi) else 0.0
+        out = dict(rank=rank, world=world, n_self=int(loc.n_cells), peers=[int(p) for p in loc.halo["peers"]],
+                   err_diag=0.0, err_b=0.0, rel_l2=float(np.sqrt(float(t[0]) / float(t[1]))), ghost_err=ghost_err,
+                   r0=1.0, r=0.0, iters=0, levels=[], collectives=lib.comm_collectives(),
+                   vmax=float(np.abs(v_ref[:raw.n_cells]).max()))   # interior cells only
+        with open(os.path.join(os.environ["FVM_RESULT_DIR"], "rank%d.json" % rank), "w") as fh:
+            json.dump(out, fh)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
     if solver_kind == "model":
         # the public (reference-mirroring) Python API on this rank's mesh: same script as single rank
         import contextlib

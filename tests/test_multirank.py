@@ -97,6 +97,17 @@ def test_exchange_after_every_colour_pass():
     check(res)
 
 
+@pytest.mark.parametrize("world,case", [(2, "hex_slabs"), (3, "hex_slabs"), (2, "tet_rcb")])
+def test_flow_model_on_partitioned_meshes(world, case):
+    """FlowModelA (SIMPLE) on mesh parts: interface faces handled like interior faces, ghost copies of V, p,
+    their gradients and momAp refreshed where the reference calls syncLocal, net flux / volume / norms
+    all-reduced, reference pressure correction from the owner of global cell 0 -- against the
+    single-partition run of the same model after three outer iterations."""
+    res = run_world(world, case, "flow", 200)
+    check(res)
+    assert res[0]["vmax"] > 0.02    # the lid actually drives a flow in the interior cells
+
+
 def test_electric_model_on_partitioned_tets():
     """BASELINE configs[4] in miniature: ElectricModelA (Poisson + drift / transient charge transport) on
     an RCB-partitioned tet mesh, 2 ranks, against the single-partition run of the same model."""
