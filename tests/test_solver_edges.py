@@ -1,0 +1,125 @@
+"""Edge cases of the linear-solver path (degenerate sizes, empty right-hand sides, iteration
+limits, disconnected patterns). Host logic + index logic in the kernels' host simulator; the same functors
+run on the device (tests/test_solver.py covers the device with the reference's own matrices)."""
+import numpy as np
+import pytest
+
+from fvm_b200 import capi as X
+
+
+def raw_system(lib, n, edges, diag, b, vals=None):
+    adj = [[] for _ in range(n)]
+    for k, (i, j) in enumerate(edges):
+        v = -1.0 if vals is None else vals[k]
+        adj[i].append((j, v)); adj[j].append((i, v))
+    row = np.zeros(n + 1, np.int32)
+    row[1:] = np.cumsum([len(a) for a in adj])
+    col = np.array([j for a in adj for j, _ in a] or [0], np.int32)[: row[-1]] if row[-1] else np.zeros(0, np.int32)
+    off = np.array([v for a in adj for _, v in a], float)
+    return X.DeviceSystem(lib, raw=(n, 0, row, col, np.asarray(diag, float), off, np.asarray(b, float)))
+
+
+def residual(n, edges, diag, b, x, vals=None):
+    r = np.asarray(b, float) + np.asarray(diag, float) * x
+    for k, (i, j) in enumerate(edges):
+        v = -1.0 if vals is None else vals[k]
+        r[i] += v * x[j]; r[j] += v * x[i]
+    return r
+
+
+def test_single_row_system(hostsim_lib):
+    ds = raw_system(hostsim_lib, 1, [], [4.0], [2.0])
+    amg = X.DeviceAMG(hostsim_lib)
+    r0, r, it = amg.solve(ds)
+    assert r0 == 2.0 and it >= 1 and r <= 1e-8 * r0
+    assert ds.get_field(X.FIELD_DELTA)[0] == -0.5        # A delta + b = 0
+    amg.close(); ds.close()
+
+
+def test_zero_right_hand_side_needs_no_cycle(hostsim_lib):
+    """AMG::solve returns at once when the initial residual is below the absolute tolerance (F/AMG.cpp:240)."""
+    edges = [(i, i + 1) for i in range(9)]
+    ds = raw_system(hostsim_lib, 10, edges, np.full(10, 2.5), np.zeros(10))
+    amg = X.DeviceAMG(hostsim_lib)
+    r0, r, it = amg.solve(ds)
+    assert r0 == 0.0 and it == 0 and not ds.get_field(X.FIELD_DELTA).any()
+    amg.close(); ds.close()
+
+
+def test_iteration_limit_is_respected(hostsim_lib):
+    """for (i = 1; i < nMaxIterations; i++) -- F/AMG.cpp:245: at most nMaxIterations - 1 cycles."""
+    n = 400
+    edges = [(i, i + 1) for i in range(n - 1)]
+    diag = np.full(n, 2.0); diag[0] = 3.0
+    ds = raw_system(hostsim_lib, n, edges, diag, np.ones(n))
+    o = hostsim_lib.default_amg_opts()
+    o.nMaxIterations, o.relativeTolerance = 4, 1e-30
+    amg = X.DeviceAMG(hostsim_lib, o)
+    r0, r, it = amg.solve(ds)
+    assert it == 3 and 0 < r < r0 and len(amg.history()) == 4
+    amg.close(); ds.close()
+
+
+def test_diagonal_matrix_is_one_colour_and_one_cycle(hostsim_lib):
+    n = 50
+    rng = np.random.default_rng(1)
+    diag, b = rng.uniform(1, 3, n), rng.normal(size=n)
+    ds = raw_system(hostsim_lib, n, [], diag, b)
+    amg = X.DeviceAMG(hostsim_lib)
+    r0, r, it = amg.solve(ds)
+    assert it == 1 and amg.levels()["colours"][0] == 1
+    assert np.allclose(ds.get_field(X.FIELD_DELTA), -b / diag, rtol=1e-15, atol=0)
+    amg.close(); ds.close()
+
+
+def test_disconnected_blocks_and_isolated_rows(hostsim_lib):
+    """Two chains, a ring of odd length (not bipartite) and three isolated rows in one system."""
+    edges = [(i, i + 1) for i in range(0, 19)] + [(i, i + 1) for i in range(20, 39)]
+    ring = list(range(40, 47))
+    edges += [(ring[k], ring[(k + 1) % 7]) for k in range(7)]
+    n = 50
+    rng = np.random.default_rng(2)
+    diag = np.full(n, 2.2)
+    b = rng.normal(size=n)
+    ds = raw_system(hostsim_lib, n, edges, diag, b)
+    o = hostsim_lib.default_amg_opts()
+    o.relativeTolerance, o.nMaxIterations = 1e-13, 500
+    amg = X.DeviceAMG(hostsim_lib, o)
+    r0, r, it = amg.solve(ds)
+    x = ds.get_field(X.FIELD_DELTA)
+    assert np.abs(residual(n, edges, diag, b, x)).sum() <= 1e-12 * r0
+    assert amg.levels()["colours"][0] == 3           # the odd ring needs a third class
+    amg.close(); ds.close()
+
+
+@pytest.mark.parametrize("levels", [0, 1, 3])
+def test_max_coarse_levels_is_a_hard_cap(hostsim_lib, levels):
+    """AMG::maxCoarseLevels (F/AMG.cpp:154): 0 = smoothing on the fine level only."""
+    n = 256
+    edges = [(i, i + 1) for i in range(n - 1)]
+    diag = np.full(n, 2.0); diag[0] = 3.0; diag[-1] = 3.0
+    ds = raw_system(hostsim_lib, n, edges, diag, np.ones(n))
+    o = hostsim_lib.default_amg_opts()
+    o.maxCoarseLevels, o.nMaxIterations, o.relativeTolerance = levels, 30, 1e-30
+    amg = X.DeviceAMG(hostsim_lib, o)
+    r0, r, it = amg.solve(ds)
+    assert len(amg.levels()["sizes"]) == levels + 1 and r < r0
+    amg.close(); ds.close()
+
+
+def test_w_and_f_cycles_converge_in_fewer_cycles_than_v(hostsim_lib):
+    n = 900
+    edges = [(y * 30 + x, y * 30 + x + 1) for y in range(30) for x in range(29)]
+    edges += [(y * 30 + x, (y + 1) * 30 + x) for y in range(29) for x in range(30)]
+    diag = np.full(n, 4.0 + 1e-3)
+    its = {}
+    for name, ct in (("V", X.CYCLE_V), ("F", X.CYCLE_F), ("W", X.CYCLE_W)):
+        ds = raw_system(hostsim_lib, n, edges, diag, np.ones(n))
+        o = hostsim_lib.default_amg_opts()
+        o.cycleType, o.relativeTolerance, o.nMaxIterations = ct, 1e-10, 2000
+        amg = X.DeviceAMG(hostsim_lib, o)
+        r0, r, it = amg.solve(ds)
+        assert r / r0 < 1e-10
+        its[name] = it
+        amg.close(); ds.close()
+    assert its["W"] <= its["F"] <= its["V"]
