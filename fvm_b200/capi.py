@@ -44,7 +44,9 @@ class FlowOpts(C.Structure):
     """fvmgpu_flow_opts"""
 
     _fields_ = [("momentumURF", C.c_double), ("pressureURF", C.c_double), ("transient", C.c_int),
-                ("time_order", C.c_int), ("dt", C.c_double), ("correctVelocity", C.c_int)]
+                ("time_order", C.c_int), ("dt", C.c_double), ("correctVelocity", C.c_int),
+                ("operatingPressure", C.c_double), ("operatingTemperature", C.c_double),
+                ("molecularWeight", C.c_double), ("incompressible", C.c_int)]
 
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -268,6 +270,7 @@ FLOWBC_NOSLIP_WALL = 0
 FLOWBC_SYMMETRY = 1
 FLOWBC_VELOCITY = 2
 FLOWBC_PRESSURE = 3
+FLOWBC_SLIP_JUMP = 4
 _FLOW_WIDTH = {FLOW_VELOCITY: 3, FLOW_PRESSURE_GRADIENT: 3, FLOW_VELOCITY_GRADIENT: 9, FLOW_MOM_AP: 3,
                FLOW_PREV_VELOCITY: 3, FLOW_VELOCITY_N1: 3, FLOW_VELOCITY_N2: 3}
 _FLOW_FACE = (FLOW_MASS_FLUX, FLOW_FACE_PRESSURE)
@@ -299,8 +302,8 @@ class DeviceFlow:
         return out.reshape(-1, w) if w > 1 else out
 
     def set_bc(self, group_id, kind, params):
-        p = _f64(list(params) + [0.0] * (4 - len(params)))
-        self.lib.call("fvmgpu_flow_set_bc", self.h, int(group_id), int(kind), p, 4)
+        p = _f64(list(params) + [0.0] * max(0, 4 - len(params)))
+        self.lib.call("fvmgpu_flow_set_bc", self.h, int(group_id), int(kind), p, len(p))
 
     def set_reference_cell(self, local_cell):
         """Mesh parts only: local index of the globally lowest cell on the rank that owns it, -1 elsewhere."""
@@ -310,8 +313,11 @@ class DeviceFlow:
         self.lib.call("fvmgpu_flow_init", self.h)
 
     @staticmethod
-    def opts(momentumURF=0.7, pressureURF=0.3, transient=0, time_order=1, dt=0.1, correctVelocity=1):
-        return FlowOpts(momentumURF, pressureURF, int(transient), int(time_order), dt, int(correctVelocity))
+    def opts(momentumURF=0.7, pressureURF=0.3, transient=0, time_order=1, dt=0.1, correctVelocity=1,
+             operatingPressure=101325.0, operatingTemperature=300.0, molecularWeight=28.966, incompressible=1):
+        return FlowOpts(momentumURF, pressureURF, int(transient), int(time_order), dt, int(correctVelocity),
+                        float(operatingPressure), float(operatingTemperature), float(molecularWeight),
+                        int(incompressible))
 
     def assemble_momentum(self, o):
         self.lib.call("fvmgpu_flow_assemble_momentum", self.h, C.byref(o))

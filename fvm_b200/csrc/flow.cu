@@ -38,7 +38,7 @@ struct FlowBcEntry {
   int offset, count;
   int kind;       // FVMGPU_FLOWBC_* or -1
   int groupKind;
-  double p[4];    // vx, vy, vz, specifiedPressure
+  double p[5];    // vx, vy, vz, specifiedPressure, accomodationCoefficient
 };
 
 struct Flow {
@@ -101,7 +101,8 @@ struct FlowInitMassFluxFaces {  // FlowModel::init, F/FlowModel_impl.h:222-244, 
     const V3 A = {fg.x, fg.y, fg.z};
     if (f >= nInteriorFaces) {
       const FlowBcEntry* bc = faceBc(bcs, faceGroupOf, nInteriorFaces, f);
-      if (bc->kind == FVMGPU_FLOWBC_NOSLIP_WALL || bc->kind == FVMGPU_FLOWBC_VELOCITY) {  // F/FlowModel_impl.h:297-312
+      if (bc->kind == FVMGPU_FLOWBC_NOSLIP_WALL || bc->kind == FVMGPU_FLOWBC_VELOCITY ||
+          bc->kind == FVMGPU_FLOWBC_SLIP_JUMP) {  // F/FlowModel_impl.h:297-312
         const V3 bv = {bc->p[0], bc->p[1], bc->p[2]};
         massFlux[f] = rho[c0] * dot3(bv, A);
         return;
@@ -235,7 +236,32 @@ struct MomParams {
   double* Vnew;   // snapshot of V after the BCs (Dirichlet ghosts hold the wall velocity) = _previousVelocity
   double* diag; double* off; double* b; int* isBoundary;
   double urf; int timeOrder; double dt;
+  const double* p; const double* bFaceCen;   // slip walls: cell pressure, boundary-face centroids
+  double opPressure, opTemperature, molWt; int incompressible;
 };
+
+// slipJumpMomentumBC, F/FlowModelSlipJump.h:47-85: the Dirichlet value of one slip-wall face
+FVM_DEV V3 slipWallVelocity(const MomParams& P, const FlowBcEntry* bc, int f, int c0) {
+  const double4 fg = P.faceGeom[f];
+  const V3 en = {fg.x / fg.w, fg.y / fg.w, fg.z / fg.w};
+  const V3 v0 = ld3(P.V, c0);
+  const double Vn = dot3(v0, en);
+  const V3 Vp = {v0.x - Vn * en.x, v0.y - Vn * en.y, v0.z - Vn * en.z};
+  const double4 g0 = P.cellGeom[c0];
+  const double* fc = P.bFaceCen + 3 * (size_t)(f - P.nInteriorFaces);
+  const V3 ds = {fc[0] - g0.x, fc[1] - g0.y, fc[2] - g0.z};
+  const double dn = dot3(ds, en);
+  const double pAbs = P.incompressible ? P.opPressure : (P.p[c0] + P.opPressure);
+  const double Rgas = 8314.472 / P.molWt;
+  const double meanFreePath = P.mu[c0] / pAbs * sqrt(0.5 * M_PI * Rgas * P.opTemperature);
+  const double acc = bc->p[4];
+  const double coeff = acc * meanFreePath / (dn + (acc * meanFreePath));
+  const V3 Vwp = {Vp.x * coeff, Vp.y * coeff, Vp.z * coeff};
+  const V3 bv = {bc->p[0], bc->p[1], bc->p[2]};
+  const double bn = dot3(bv, en);
+  const V3 Vwn = {bv.x - bn * bv.x, bv.y - bn * bv.y, bv.z - bn * bv.z};   // (sic) bv - dot(bv,en)*bv, :80
+  return V3{Vwn.x + Vwp.x, Vwn.y + Vwp.y, Vwn.z + Vwp.z};
+}
 
 // DiffusionDiscretization<Vec3,DiagTensor3,T> for one face seen from (c0,c1)  F/DiffusionDiscretization.h:165-209
 FVM_DEV void momDiffusionFace(const MomParams& P, const double4 fg, int c0, int c1, double& diffCoeff, V3& dFlux) {
@@ -297,6 +323,7 @@ struct MomentumRows {
             return;
           }
           if (bc->kind == FVMGPU_FLOWBC_NOSLIP_WALL || inflowOutflow) xnew = V3{bc->p[0], bc->p[1], bc->p[2]};
+          else if (bc->kind == FVMGPU_FLOWBC_SLIP_JUMP) xnew = slipWallVelocity(P, bc, f, P.col[r0]);
           else if (bc->kind == FVMGPU_FLOWBC_SYMMETRY) {  // x[c1] = x[c0] - 2 (x[c0].en) en, F/GenericBCS.h:583-596
             const double4 fg = P.faceGeom[f];
             const V3 en = {fg.x / fg.w, fg.y / fg.w, fg.z / fg.w};
@@ -386,6 +413,10 @@ struct MomentumRows {
           P.off[k] = 0.0;
         } else if (bc->kind == FVMGPU_FLOWBC_NOSLIP_WALL || inflowOutflow) {
           r.x += c01 * (bc->p[0] - x1.x); r.y += c01 * (bc->p[1] - x1.y); r.z += c01 * (bc->p[2] - x1.z);
+          P.off[k] = 0.0;
+        } else if (bc->kind == FVMGPU_FLOWBC_SLIP_JUMP) {  // applyDirichletBC(f, Vw)
+          const V3 vw = slipWallVelocity(P, bc, f, i);
+          r.x += c01 * (vw.x - x1.x); r.y += c01 * (vw.y - x1.y); r.z += c01 * (vw.z - x1.z);
           P.off[k] = 0.0;
         } else if (bc->kind == FVMGPU_FLOWBC_SYMMETRY) {  // applySymmetryBC, F/GenericBCS.h:569-615
           const double4 fg = P.faceGeom[f];
@@ -770,7 +801,7 @@ Flow* flowCreate(Mesh* m) {
   for (const FaceGroup& g : m->groups) {
     FlowBcEntry e;
     e.offset = g.offset; e.count = g.count; e.kind = -1; e.groupKind = g.kind;
-    e.p[0] = e.p[1] = e.p[2] = e.p[3] = 0.0;
+    e.p[0] = e.p[1] = e.p[2] = e.p[3] = 0.0; e.p[4] = 1.0;
     F->bcs.push_back(e);
   }
   streamSync();
@@ -819,13 +850,15 @@ void flowGetField(Flow* F, int field, double* host, long long n) {
 }
 void flowSetBc(Flow* F, int groupId, int kind, const double* p, int np) {
   requireReady();
-  if (kind < FVMGPU_FLOWBC_NOSLIP_WALL || kind > FVMGPU_FLOWBC_PRESSURE) fail("flow_set_bc: unknown boundary kind %d", kind);
+  if (kind < FVMGPU_FLOWBC_NOSLIP_WALL || kind > FVMGPU_FLOWBC_SLIP_JUMP) fail("flow_set_bc: unknown boundary kind %d", kind);
+  if (kind == FVMGPU_FLOWBC_SLIP_JUMP && !F->mesh->bFaceCen.p)
+    fail("flow_set_bc: SlipJump needs the face centroids (pass them to fvmgpu_mesh_set_geometry)");
   for (size_t g = 0; g < F->bcs.size(); g++) {
     const FaceGroup& fg = F->mesh->groups[g];
     if (fg.id == groupId && fg.kind != FVMGPU_GROUP_INTERIOR) {
       FlowBcEntry& e = F->bcs[g];
       e.kind = kind;
-      for (int i = 0; i < 4; i++) e.p[i] = (i < np && p) ? p[i] : 0.0;
+      for (int i = 0; i < 5; i++) e.p[i] = (i < np && p) ? p[i] : (i == 4 ? 1.0 : 0.0);
       F->bcsDirty = true;
       return;
     }
@@ -901,6 +934,9 @@ void flowAssembleMomentum(Flow* F, const fvmgpu_flow_opts& o) {
   P.Vnew = F->Vprev.p;
   P.diag = F->mDiag.p; P.off = F->mOff.p; P.b = F->mB.p; P.isBoundary = F->comp->isBoundary.p;
   P.urf = o.momentumURF; P.timeOrder = o.transient ? o.time_order : 0; P.dt = o.dt;
+  P.p = F->p.p; P.bFaceCen = m->bFaceCen.p;
+  P.opPressure = o.operatingPressure; P.opTemperature = o.operatingTemperature; P.molWt = o.molecularWeight;
+  P.incompressible = o.incompressible;
   parallelFor(m->nTotal, MomentumRows{P});
   // x[c1] = wall velocity for the Dirichlet ghosts; Vprev is the reference's _previousVelocity snapshot
   copyD2D(F->V.p, F->Vprev.p, 3 * (size_t)m->nTotal * sizeof(double));

@@ -199,7 +199,9 @@ struct LsWeightsKernel {
 void meshSetGeometry(Mesh* m, const double* faceArea, const double* faceAreaMag, const double* faceCentroid,
                      const double* cellCentroid, const double* cellVolume, const int* ibType) {
   requireReady();
-  (void)faceCentroid;  // only the immersed-boundary branches read it (out of scope)
+  // face centroids: only the slip-wall boundary condition reads them, and only on boundary faces
+  if (faceCentroid && m->nFaces > m->nInteriorFaces)
+    m->bFaceCen.upload(faceCentroid + 3 * (size_t)m->nInteriorFaces, 3 * (size_t)(m->nFaces - m->nInteriorFaces));
   if (ibType) {
     DBuf<int> ib, err(1);
     ib.upload(ibType, m->nTotal);
@@ -395,6 +397,11 @@ void meshComputeGeometry(Mesh* m, int nNodes, const double* nodes, const int* fa
     parallelFor((long long)nf, UnpackFaceGeomKernel{m->faceGeom.p, a3.p, am.p});
     if (faceArea) a3.download(faceArea, 3 * nf);
     if (faceAreaMag) am.download(faceAreaMag, nf);
+  }
+  if (m->nFaces > m->nInteriorFaces) {
+    const size_t nb3 = 3 * (size_t)(m->nFaces - m->nInteriorFaces);
+    m->bFaceCen.alloc(nb3);
+    copyD2D(m->bFaceCen.p, fcen.p + 3 * (size_t)m->nInteriorFaces, nb3 * sizeof(double));
   }
   if (faceCentroid) fcen.download(faceCentroid, 3 * nf);
   if (cellCentroid) ccen.download(cellCentroid, 3 * nt);

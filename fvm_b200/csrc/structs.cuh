@@ -37,6 +37,7 @@ struct Mesh {
   bool hasGeometry = false;
   DBuf<double4> cellGeom;  // Nt
   DBuf<double4> faceGeom;  // F
+  DBuf<double> bFaceCen;   // centroids of the boundary faces only, 3 * (F - nInteriorFaces) (SlipJump walls)
   DBuf<double> gradW;      // 3*nnz, SoA: wx[nnz], wy[nnz], wz[nnz]
   // halo (multi-GPU): StorageSite scatter/gather maps per neighbouring rank (F/StorageSite.h:58-84)
   Halo halo;

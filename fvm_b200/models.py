@@ -717,8 +717,8 @@ class FlowModelA:
     """Mirror of `models_atyped_double.FlowModelA` (F/FlowModel.h:17-95, F/FlowModel.i): SIMPLE
     iterations -- momentum assembly + solve, Rhie-Chow pressure correction assembly + solve, the
     pressure / mass-flux / velocity corrections -- all on the device through the C ABI
-    (fvmgpu_flow_*). Boundary types: "NoSlipWall", "Symmetry", "VelocityBoundary", "PressureBoundary"
-    (F/FlowModel_impl.h:636-677); "SlipJump" is not built. On a partitioned mesh (fvm_b200.partition) every
+    (fvmgpu_flow_*). Boundary types: "NoSlipWall", "SlipJump", "Symmetry", "VelocityBoundary",
+    "PressureBoundary" (F/FlowModel_impl.h:636-677). On a partitioned mesh (fvm_b200.partition) every
     rank runs this same code on its part; halo exchanges and all-reduces happen inside the library."""
 
     def __init__(self, geom_fields, flow_fields, meshes, lib=None):
@@ -767,7 +767,9 @@ class FlowModelA:
     def _flow_opts(self):
         o = self._options
         return capi.DeviceFlow.opts(float(o["momentumURF"]), float(o["pressureURF"]), int(o.transient),
-                                    int(o.timeDiscretizationOrder), float(o["timeStep"]), int(o.correctVelocity))
+                                    int(o.timeDiscretizationOrder), float(o["timeStep"]), int(o.correctVelocity),
+                                    float(o["operatingPressure"]), float(o["operatingTemperature"]),
+                                    float(o["molecularWeight"]), int(o.incompressible))
 
     def init(self):  # F/FlowModel_impl.h:148-340
         f, o = self.fields, self._options
@@ -827,6 +829,10 @@ class FlowModelA:
                 fl.set_bc(fg.id, capi.FLOWBC_NOSLIP_WALL, [float(bc["specifiedXVelocity"]),
                                                             float(bc["specifiedYVelocity"]),
                                                             float(bc["specifiedZVelocity"])])
+            elif bc.bcType == "SlipJump":   # F/FlowModel_impl.h:666-672
+                fl.set_bc(fg.id, capi.FLOWBC_SLIP_JUMP, [float(bc["specifiedXVelocity"]), float(bc["specifiedYVelocity"]),
+                                                         float(bc["specifiedZVelocity"]), 0.0,
+                                                         float(bc["accomodationCoefficient"])])
             elif bc.bcType == "Symmetry":
                 fl.set_bc(fg.id, capi.FLOWBC_SYMMETRY, [0.0, 0.0, 0.0])
             elif bc.bcType in ("VelocityBoundary", "PressureBoundary"):

@@ -267,10 +267,15 @@ enum {
   FVMGPU_FLOWBC_VELOCITY = 2,    /* "VelocityBoundary": per face extrapolation where massFlux > 0, else Dirichlet
                                     with p[0..2] (F/FlowModel_impl.h:650-668); fixed mass flux rho v.A in the
                                     continuity equation (F/FlowModelVelocityBC.h:11-103) */
-  FVMGPU_FLOWBC_PRESSURE = 3     /* "PressureBoundary": the same momentum treatment + fixedPressureMomentumBC,
+  FVMGPU_FLOWBC_PRESSURE = 3,    /* "PressureBoundary": the same momentum treatment + fixedPressureMomentumBC,
                                     fixedPressureContinuityBC, pressureBoundaryPostContinuitySolve
                                     (F/FlowModelPressureBC.h:11-216); p[3] = specifiedPressure. With a pressure
                                     boundary present no reference cell / net-flux redistribution is used */
+  FVMGPU_FLOWBC_SLIP_JUMP = 4    /* "SlipJump": slipJumpMomentumBC (F/FlowModelSlipJump.h:11-88): Dirichlet value
+                                    per face = wall-parallel cell velocity * a*lambda / (dn + a*lambda) + the
+                                    specified velocity's part; p[0..2] = specified velocity, p[4] =
+                                    accomodationCoefficient; fixed-flux continuity like a wall. Needs the face
+                                    centroids (fvmgpu_mesh_set_geometry / _compute_geometry) */
 };
 typedef struct {
   double momentumURF;   /* FlowModelOptions "momentumURF" (0.7)  F/FlowBC.h:42-50 */
@@ -279,6 +284,11 @@ typedef struct {
   int time_order;
   double dt;
   int correctVelocity;  /* FlowModelOptions::correctVelocity (true)             */
+  /* gas state for the slip-wall mean free path (F/FlowBC.h:50-52,64; F/FlowModelSlipJump.h:38-43,67-71) */
+  double operatingPressure;     /* 101325 */
+  double operatingTemperature;  /* 300    */
+  double molecularWeight;       /* 28.966 */
+  int incompressible;           /* true: pAbs = operatingPressure, else p[c0] + operatingPressure */
 } fvmgpu_flow_opts;
 int fvmgpu_flow_create(fvmgpu_flow_t* out, fvmgpu_mesh_t mesh);
 int fvmgpu_flow_destroy(fvmgpu_flow_t flow);

@@ -270,6 +270,41 @@ def flow_channel_golden():
     print("flow_channel.npz: %d cells" % rm.n_self)
 
 
+def flow_slip_golden():
+    """Lid-driven box whose lid and floor are SlipJump walls (F/FlowModelSlipJump.h): a low operating
+    pressure makes the mean free path comparable to the wall distance, so the slip is not negligible."""
+    raw = G.quad_mesh(11, 9, jitter=0.2, seed=6)
+    rm = R.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes, raw.face_node_count,
+                            raw.face_group_size)
+    f = R.RefFlow(rm)
+    f.set_bc(1, "NoSlipWall")
+    f.set_bc(2, "NoSlipWall")
+    f.set_bc(3, "SlipJump", accomodationCoefficient=0.9)
+    f.set_bc(4, "SlipJump", specifiedXVelocity=1.0, accomodationCoefficient=0.8)
+    f.set_vc("viscosity", 0.08)
+    f.set_vc("density", 1.2)
+    f.set_option("operatingPressure", 900.0)
+    f.set_option("operatingTemperature", 320.0)
+    tight = dict(relativeTolerance=1e-14, nMaxIterations=3000, verbosity=0)
+    f.set_solver(0, R.solver_cfg(**tight))
+    f.set_solver(1, R.solver_cfg(**tight))
+    f.init()
+    out = {}
+    for it in range(6):
+        if it == 3:
+            for nm in ("velocity", "pressure", "facePressure", "massFlux", "continuityResidual"):
+                out["s0_" + nm] = f.field(nm).copy()
+            ms = f.momentum_system()
+            out.update(mom_diag=ms["diag"], mom_off=ms["offdiag"], mom_b=ms["b"])
+        f.solve_momentum()
+        f.solve_continuity()
+    for nm in ("velocity", "pressure", "massFlux"):
+        out["end_" + nm] = f.field(nm).copy()
+    np.savez_compressed(os.path.join(HERE, "flow_slip.npz"), **mesh_arrays(rm), **out)
+    v = out["end_velocity"].reshape(-1, 3)
+    print("flow_slip.npz: %d cells, max |u| on the slip-wall ghosts %.4f" % (rm.n_self, np.abs(v[rm.n_self:, 0]).max()))
+
+
 def electric_golden():
     raw = G.hex_mesh(6, 5, 7, lx=1e-6, ly=1e-6, lz=2e-6, jitter=0.15, seed=2)
     rm = R.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes, raw.face_node_count,
@@ -310,6 +345,9 @@ def electric_golden():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "flowchan":
         flow_channel_golden()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "flowslip":
+        flow_slip_golden()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "flowsym":
         flow_symmetry_golden()
