@@ -88,8 +88,19 @@ void* devAlloc(size_t bytes) {
   }
   if (!p) {
     const auto t0 = std::chrono::steady_clock::now();
-    if (ctx().stream) CUDA_CHECK(cudaMallocAsync(&p, bytes, ctx().stream));
-    else CUDA_CHECK(cudaMalloc(&p, bytes));
+    if (ctx().stream) {
+      cudaError_t e = cudaMallocAsync(&p, bytes, ctx().stream);
+      if (e == cudaErrorMemoryAllocation) {
+        // the cached blocks count as used memory: hand them back and try once more
+        (void)cudaGetLastError();
+        devTrimCache();
+        cudaStreamSynchronize(ctx().stream);
+        e = cudaMallocAsync(&p, bytes, ctx().stream);
+      }
+      CUDA_CHECK(e);
+    } else {
+      CUDA_CHECK(cudaMalloc(&p, bytes));
+    }
     if (traceAllocs()) {
       const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
       if (ms > 1.0) fprintf(stderr, "[fvmgpu] alloc of %zu bytes blocked the host for %.2f ms\n", bytes, ms);
