@@ -608,7 +608,7 @@ class ThermalModelA:
                     if col[jp] < n:
                         lines.append("%d %d %f" % (i + 1, col[jp] + 1, d["offdiag"][jp]))
             with open("%s_mesh%d.mat" % (file_base, idx), "w") as fh:
-                fh.write("%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (n, n, len(lines)))
+                fh.write("%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (n, n, len(lines)))
                 fh.write("\n".join(lines) + "\n")
             with open(file_base + ".rhs", "w") as fh:
                 fh.write("".join("%f\n" % (-v) for v in d["b"][:n]))

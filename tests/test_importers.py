@@ -1,0 +1,139 @@
+"""Fluent .cas import (fvm_b200/importers.py, mirror of I/FluentReader.cpp): the NUMBERING the reference
+reader produces -- face order, interior cell first, ghost cells in file order of the boundary faces,
+one face group per boundary zone -- decides the summation order of the assembly, so it is compared entry
+by entry with the mesh the reference itself read from T/CellMark/cav32.cas (fixture cav32.npz), and the
+reference's own thermal test (T/THERMAL_MATRIX/testThermalParallel.py: cav32, T = 400 on zone 3, 0 on
+4-6) is run from the case file through to dumpMatrix and checked against T/THERMAL_MATRIX/GOLDEN."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from fvm_b200 import importers, models as M
+
+CAV32 = "/root/reference/src/fvm/test/CellMark/cav32.cas"
+
+TINY = """(0 "two quads, written by the test")
+(2 2)
+(10 (0 1 6 0 2))
+(12 (0 1 2 0))
+(13 (0 1 7 0))
+(12 (7 1 2 1 3))
+(10 (1 1 6 1 2)(
+0 0
+1 0
+2 0
+0 1
+1 1
+2 1))
+(13 (9 1 1 2 2)(
+2 5 1 2))
+(13 (3 2 4 3 2)(
+1 2 1 0
+2 3 2 0
+3 6 2 0))
+(13 (4 5 7 a 2)(
+6 5 0 2
+5 4 0 1
+4 1 1 0))
+(45 (7 fluid fluid-7)())
+(45 (9 interior int-9)())
+(45 (3 wall bottom-right)())
+(45 (4 velocity-inlet top-left)())
+"""
+
+
+def test_tiny_case_numbering(tmp_path):
+    p = tmp_path / "tiny.cas"
+    p.write_text(TINY)
+    fc = importers.FluentCase(str(p))
+    fc.read()
+    mesh, = fc.getMeshList()
+    raw = mesh.raw
+    assert (raw.dim, raw.n_cells, raw.n_total, raw.n_faces) == (2, 2, 8, 7)
+    assert raw.group_count.tolist() == [1, 3, 3] and raw.group_id.tolist() == [0, 3, 4]
+    assert [g.groupType for g in mesh.getBoundaryFaceGroups()] == ["wall", "velocity-inlet"]
+    # interior cell first, ghosts numbered in file order of the boundary faces
+    assert raw.face_cells.tolist() == [[0, 1], [0, 2], [1, 3], [1, 4], [1, 5], [0, 6], [0, 7]]
+    # 2-D: node order reversed exactly where the file had c0 == 0
+    fn = raw.face_nodes.reshape(-1, 2).tolist()
+    assert fn == [[1, 4], [0, 1], [1, 2], [2, 5], [4, 5], [3, 4], [3, 0]]
+
+
+def test_unsupported_files_fail_loudly(tmp_path):
+    p = tmp_path / "bin.cas"                      # a binary node section cut off after its header
+    p.write_text("(2 2)\n(10 (0 1 4 0 2))\n(2010 (1 1 4 1 2)(")
+    with pytest.raises(M.CException):
+        importers.FluentCase(str(p)).read()
+    p2 = tmp_path / "empty.cas"
+    p2.write_text('(0 "nothing")\n(2 3)\n')
+    with pytest.raises(M.CException):
+        importers.FluentCase(str(p2)).read()
+
+
+@pytest.mark.skipif(not os.path.exists(CAV32), reason="reference tree not mounted")
+def test_cav32_case_file_reproduces_the_reference_mesh_and_golden_matrix(hostsim_lib, tmp_path):
+    g = load_golden("cav32.npz")
+    fc = importers.FluentCase(CAV32)
+    fc.read()
+    mesh, = fc.getMeshList()
+    raw = mesh.raw
+    assert (raw.n_cells, raw.n_total) == (int(g["n_self"]), int(g["n_total"]))
+    assert np.array_equal(raw.face_cells, g["face_cells"])
+    for k in ("group_id", "group_count", "group_offset"):
+        assert np.array_equal(raw[k], g[k]), k
+    assert np.array_equal(mesh.cc_row, g["cc_row"]) and np.array_equal(mesh.cc_col, g["cc_col"])
+    geom = M.GeomFields("geom")
+    M.MeshMetricsCalculatorA(geom, [mesh], lib=hostsim_lib).init()
+    cells, faces = mesh.getCells(), mesh.getFaces()
+    assert np.array_equal(geom.area[faces], g["face_area"]) and np.array_equal(geom.volume[cells], g["cell_volume"])
+    assert np.array_equal(geom.coordinate[cells], g["cell_centroid"])
+    # T/THERMAL_MATRIX/testThermalParallel.py
+    tf = M.ThermalFields("therm")
+    tm = M.ThermalModelA(geom, tf, [mesh], lib=hostsim_lib)
+    bc = tm.getBCMap()
+    bc[3].bcType = "SpecifiedTemperature"; bc[3].setVar("specifiedTemperature", 400)
+    for gid in (4, 5, 6):
+        bc[gid].bcType = "SpecifiedTemperature"; bc[gid].setVar("specifiedTemperature", 0)
+    tm.init()
+    base = str(tmp_path / "matrix")
+    tm.dumpMatrix(base)
+    mat = open(base + "_mesh0.mat").read().splitlines()
+    assert mat[0] == "%%MatrixMarket matrix coordinate real general" and mat[1] == "1024 1024 4992"
+    want = ["%d %d %f" % (int(r), int(c), v) for r, c, v in g["golden_mat"]]
+    assert mat[2:] == want
+    assert open(base + ".rhs").read().splitlines() == ["%f" % v for v in g["golden_rhs"]]
+    golden_dir = "/root/reference/src/fvm/test/THERMAL_MATRIX/GOLDEN/"
+    if os.path.exists(golden_dir + "matrix_mesh0.mat"):   # byte for byte against the reference's own files
+        assert open(base + "_mesh0.mat", "rb").read() == open(golden_dir + "matrix_mesh0.mat", "rb").read()
+        assert open(base + ".rhs", "rb").read() == open(golden_dir + "matrix.rhs", "rb").read()
+
+
+REF_CASES = ["3d-cube.cas", "CellMark/cube-15k.cas", "1x1x1000.cas", "DampingESBGK/Damping100x100.cas"]
+
+
+@pytest.mark.parametrize("case", REF_CASES)
+def test_binary_case_files_match_the_reference_reader(hostsim_lib, case):
+    """Binary (single / double precision) 2-D and 3-D case files of the reference's test tree, read by this
+    importer and by the reference's own FluentReader (oracle/_ref): same faceCells, same face groups, and --
+    through the device MeshMetricsCalculator -- bit-identical areas, centroids and volumes."""
+    path = "/root/reference/src/fvm/test/" + case
+    from oracle import refapi as R
+    if not os.path.exists(path) or not R.available():
+        pytest.skip("reference tree / oracle/_ref not available")
+    fc = importers.FluentCase(path)
+    fc.read()
+    mesh, = fc.getMeshList()
+    rm = R.RefMesh.from_cas(path)
+    c, g = rm.connectivity(), rm.geometry()
+    raw = mesh.raw
+    assert np.array_equal(raw.face_cells, c["face_cells"])
+    for k in ("group_id", "group_count", "group_offset"):
+        assert np.array_equal(raw[k], c[k]), k
+    geom = M.GeomFields("geom")
+    M.MeshMetricsCalculatorA(geom, [mesh], lib=hostsim_lib).init()
+    cells, faces = mesh.getCells(), mesh.getFaces()
+    assert np.array_equal(geom.area[faces], g["face_area"])
+    assert np.array_equal(geom.coordinate[cells], g["cell_centroid"])
+    assert np.array_equal(geom.volume[cells], g["cell_volume"])
