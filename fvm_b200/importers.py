@@ -84,6 +84,7 @@ class FluentCase:
         self._cell_zones = {}        # id -> (iBeg, iEnd, type)
         self._face_zones = {}        # id -> dict(iBeg, iEnd, type)
         self._zone_types = {}        # id -> type string of sections 39 / 45
+        self._zone_names, self._zone_vars, self._rp_vars = {}, {}, ""
         face_blocks = []             # (zoneId, iBeg, iEnd, shape, ints) in file order
         head = re.compile(rb"\(\s*(\d+)\s*")
         hdr = re.compile(rb"\(\s*\d+\s*\(\s*([0-9a-fA-F]+)\s+([0-9a-fA-F]+)\s+([0-9a-fA-F]+)\s+([0-9a-fA-F]+)\s*"
@@ -183,10 +184,21 @@ class FluentCase:
                     else:
                         self._num_faces -= count
             elif kind in (39, 45) and not binary:
+                end = self._close(buf, i)
                 h = zone_re.match(buf, i, i + 256)
                 if h:
-                    self._zone_types[int(h.group(1))] = h.group(2).decode("latin-1")
-                i = self._close(buf, i)
+                    zid = int(h.group(1))
+                    self._zone_types[zid] = h.group(2).decode("latin-1")
+                    self._zone_names[zid] = h.group(3).decode("latin-1")
+                    k = self._skip_ws(buf, self._close(buf, buf.find(b"(", i + 1)))   # past the header list
+                    if k < end and buf[k] == 40:
+                        self._zone_vars[zid] = buf[k:self._close(buf, k)].decode("latin-1")
+                i = end
+            elif kind == 37 and not binary:
+                end = self._close(buf, i)
+                k = buf.find(b"(", i + 1)
+                self._rp_vars = buf[k:self._close(buf, k)].decode("latin-1")
+                i = end
             elif binary:   # a binary section this reader does not use (node flags, cell trees, ...): skip to its end mark
                 mm = re.compile(rb"End of Binary Section\s+%d\s*\)" % sid).search(buf, i)
                 if not mm:
@@ -269,4 +281,198 @@ class FluentCase:
         raw.group_kind = np.array([0] + [3 if t == "symmetry" else 1 for t in types[1:]], np.int32)
         raw.cell_zone_id = czid
         mesh = Mesh(raw, group_types=types)
+        self._mesh_of_zone = {czid: mesh}
+        self._interior_zone_ids = {czid: interior}
         return [mesh]
+
+    def getCellZones(self):
+        """{id: zone} with .ID, .iBeg, .iEnd (0-based, inclusive), .mesh, .interiorZoneIds (I/FluentReader.h:30-60)"""
+        out = {}
+        for zid, (beg, end, _) in self._cell_zones.items():
+            z = type("FluentCellZone", (), {})()
+            z.ID, z.iBeg, z.iEnd = zid, beg, end
+            z.mesh = getattr(self, "_mesh_of_zone", {}).get(zid)
+            z.interiorZoneIds = list(getattr(self, "_interior_zone_ids", {}).get(zid, []))
+            out[zid] = z
+        return out
+
+    def getFaceZones(self):
+        out = {}
+        for zid, d in self._face_zones.items():
+            z = type("FluentFaceZone", (), {})()
+            z.ID, z.iBeg, z.iEnd, z.threadType = zid, d["iBeg"], d["iEnd"], d["type"]
+            z.zoneType, z.zoneName = self._zone_types.get(zid, ""), self._zone_names.get(zid, "")
+            out[zid] = z
+        return out
+
+    # ------------------------------------------------------------------ case variables / boundary conditions
+    def getVar(self, name):
+        """rp-variable of the case file (section 37), e.g. 'mom/relax' (scripts/FluentCase.py:165-183)"""
+        return self._vars()[name]
+
+    def _vars(self):
+        if not hasattr(self, "_vars_dict"):
+            self._vars_dict = _alist(_parse_scheme(self._rp_vars)) if self._rp_vars else {}
+        return self._vars_dict
+
+    def _zone(self, zid):
+        if not hasattr(self, "_zones"):
+            self._zones = {}
+        if zid not in self._zones:
+            txt = self._zone_vars.get(zid, "")
+            self._zones[zid] = _FluentZone(zid, self._zone_names.get(zid, ""), self._zone_types.get(zid, ""),
+                                           _alist(_parse_scheme(txt)) if txt else {})
+        return self._zones[zid]
+
+    def importThermalBCs(self, tmodel):
+        """scripts/FluentCase.py:218-249"""
+        for gid, bc in tmodel.getBCMap().items():
+            z = self._zone(gid)
+            if z.zoneType == "wall":
+                kind = z.getVar("thermal-bc")
+                if kind == 0:
+                    bc.bcType = "SpecifiedTemperature"
+                    bc.setVar("specifiedTemperature", z.getConstantVar("t"))
+                elif kind == 1:
+                    bc.bcType = "SpecifiedHeatFlux"
+                    bc.setVar("specifiedHeatFlux", z.getConstantVar("q"))
+                elif kind == 3:
+                    bc.bcType = "CoupledWall"
+                else:
+                    raise TypeError("thermal BCType %d not handled" % kind)
+            elif z.zoneType in ("velocity-inlet", "pressure-inlet", "pressure-outlet", "mass-flow-inlet", "exhaust-fan",
+                                "intake-fan", "inlet-vent", "outlet-vent"):
+                bc.bcType = "SpecifiedTemperature"
+                bc.setVar("specifiedTemperature", z.getConstantVar("t" if z.zoneType == "velocity-inlet" else "t0"))
+            elif z.zoneType == "symmetry":
+                pass
+            else:
+                raise TypeError("invalid boundary type : " + z.zoneType)
+
+    def importFlowBCs(self, fmodel, meshes):
+        """scripts/FluentCase.py:251-318: initial values and under-relaxation factors from the case variables,
+        one boundary condition per face zone, density / viscosity from the cell zone's material."""
+        o = fmodel.getOptions()
+        o["initialXVelocity"] = self.getVar("x-velocity/default")
+        o["initialYVelocity"] = self.getVar("y-velocity/default")
+        o["initialZVelocity"] = self.getVar("z-velocity/default")
+        o["initialPressure"] = self.getVar("pressure/default")
+        o["momentumURF"] = self.getVar("mom/relax")
+        o["pressureURF"] = self.getVar("pressure/relax")
+        for gid, bc in fmodel.getBCMap().items():
+            z = self._zone(gid)
+            if z.zoneType == "wall":
+                motion = z.getVar("motion-bc")
+                bc.bcType = "NoSlipWall"
+                if motion == 1:
+                    vmag = z.getVar("vmag")
+                    bc["specifiedXVelocity"] = vmag * z.getConstantVar("ni")
+                    bc["specifiedYVelocity"] = vmag * z.getConstantVar("nj")
+                    bc["specifiedZVelocity"] = vmag * z.getConstantVar("nk")
+                elif motion != 0:
+                    raise TypeError("flow BCType %d not handled" % motion)
+            elif z.zoneType == "velocity-inlet":
+                spec = z.getVar("velocity-spec")
+                bc.bcType = "VelocityBoundary"
+                if spec == 0:
+                    vmag = z.getVar("vmag")
+                    bc["specifiedXVelocity"] = vmag * z.getConstantVar("ni")
+                    bc["specifiedYVelocity"] = vmag * z.getConstantVar("nj")
+                    bc["specifiedZVelocity"] = vmag * z.getConstantVar("nk")
+                elif spec == 1:
+                    bc["specifiedXVelocity"] = z.getConstantVar("u")
+                    bc["specifiedYVelocity"] = z.getConstantVar("v")
+                    bc["specifiedZVelocity"] = z.getConstantVar("w")
+                else:
+                    raise TypeError("flow BCType %d not handled" % spec)
+            elif z.zoneType == "pressure-outlet":
+                bc.bcType = "PressureBoundary"
+                bc["specifiedPressure"] = z.getConstantVar("p")
+            elif z.zoneType == "pressure-inlet":
+                bc.bcType = "PressureBoundary"
+                bc["specifiedPressure"] = z.getConstantVar("p0")
+            elif z.zoneType == "symmetry":
+                bc.bcType = "Symmetry"
+            else:
+                raise TypeError("invalid boundary type : " + z.zoneType)
+        materials = _alist(self.getVar("materials")) if isinstance(self.getVar("materials"), list) else {}
+        for mesh in meshes:
+            vc = fmodel.getVCMap()[mesh.getID()]
+            cz = self._zone(mesh.raw.cell_zone_id)
+            mat = materials[cz.getVar("material")]
+            props = _alist(mat[1:]) if isinstance(mat, list) else {}
+            vc["density"] = _constant(props["density"])
+            vc["viscosity"] = _constant(props["viscosity"])
+
+
+class _FluentZone:
+    """scripts/FluentCase.py:86-130"""
+
+    def __init__(self, zid, name, zone_type, vars_):
+        self.id, self.zoneName, self.zoneType, self.varsDict = zid, name or "%s_%d" % (zone_type, zid), zone_type, vars_
+
+    def getVar(self, v):
+        return self.varsDict[v]
+
+    def getConstantVar(self, v):
+        return _constant(self.varsDict[v])
+
+
+def _constant(val):
+    """(name (constant . 300) (profile "" "")) -> 300"""
+    if not isinstance(val, list):
+        return val
+    if val and isinstance(val[0], list):
+        val = val[0]
+    if val and val[0] == "constant":
+        return val[1]
+    raise ValueError("value is not constant: %r" % (val,))
+
+
+def _parse_scheme(text):
+    """Scheme data -> nested Python lists; a dotted pair (a . b) becomes [a, b]; #t / #f -> bool; numbers -> int / float;
+    strings and symbols -> str. Enough for the association lists Fluent writes into a case file."""
+    tok = re.findall(r'"(?:[^"\\]|\\.)*"|[()]|[^\s()"]+', text)
+    pos = 0
+
+    def atom(t):
+        if t[0] == '"':
+            return t[1:-1]
+        if t == "#t":
+            return True
+        if t == "#f":
+            return False
+        try:
+            return int(t)
+        except ValueError:
+            try:
+                return float(t)
+            except ValueError:
+                return t
+
+    def parse():
+        nonlocal pos
+        t = tok[pos]
+        pos += 1
+        if t != "(":
+            return atom(t)
+        out = []
+        while tok[pos] != ")":
+            if tok[pos] == ".":
+                pos += 1
+                continue
+            out.append(parse())
+        pos += 1
+        return out
+
+    return parse() if tok else []
+
+
+def _alist(items):
+    """[[key, value...], ...] -> {key: value}: one value stays itself, several stay a list"""
+    d = {}
+    for it in items:
+        if isinstance(it, list) and it and isinstance(it[0], str):
+            rest = it[1:]
+            d[it[0]] = rest[0] if len(rest) == 1 else rest
+    return d
