@@ -26,6 +26,7 @@ SOURCES = [
     ("solver.cu", []),
     ("flow.cu", ["-fmad=false"]),
     ("electric.cu", ["-fmad=false"]),
+    ("ilu.cu", ["-fmad=false"]),
     ("capi.cu", []),
 ]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -107,6 +107,10 @@ SIGNATURES = {
     "fvmgpu_solver_history": (C.c_int, [_vp, C.c_int, _dp, C.POINTER(C.c_int)]),
     "fvmgpu_bcgstab_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "fvmgpu_bcgstab_ilu0_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
+                                            C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "fvmgpu_ilu0_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fvmgpu_cg_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
                                   C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "fvmgpu_jacobi_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
@@ -332,7 +336,7 @@ class DeviceFlow:
         """bcgstab: None or (nMaxIterations, relTol, absTol) of a BCGStab wrapped around `amg`."""
         r0, it = np.zeros(3), np.zeros(3, np.int32)
         b = bcgstab or (0, 0.0, 0.0)
-        self.lib.call("fvmgpu_flow_solve_momentum", self.h, amg.h, 1 if bcgstab else 0, int(b[0]), float(b[1]),
+        self.lib.call("fvmgpu_flow_solve_momentum", self.h, amg.h, (b[3] if len(b) > 3 else 1) if bcgstab else 0, int(b[0]), float(b[1]),
                       float(b[2]), r0, it)
         return r0, it
 
@@ -348,7 +352,7 @@ class DeviceFlow:
     def solve_continuity(self, amg, o, bcgstab=None):
         r0, it = C.c_double(0), C.c_int(0)
         b = bcgstab or (0, 0.0, 0.0)
-        self.lib.call("fvmgpu_flow_solve_continuity", self.h, amg.h, 1 if bcgstab else 0, int(b[0]), float(b[1]),
+        self.lib.call("fvmgpu_flow_solve_continuity", self.h, amg.h, (b[3] if len(b) > 3 else 1) if bcgstab else 0, int(b[0]), float(b[1]),
                       float(b[2]), C.byref(o), C.byref(r0), C.byref(it))
         return r0.value, it.value
 
@@ -572,6 +576,19 @@ class DeviceAMG:
         r0, r, it = C.c_double(0), C.c_double(0), C.c_int(0)
         self.lib.call("fvmgpu_jacobi_solve", self.h, system.h, int(n_max_iterations), float(relative_tolerance),
                       float(absolute_tolerance), C.byref(r0), C.byref(r), C.byref(it))
+        return r0.value, r.value, it.value
+
+    def bcgstab_ilu0(self, ds, n_max_iterations, relative_tolerance, absolute_tolerance=1e-50):
+        r0, r, it = C.c_double(0), C.c_double(0), C.c_int(0)
+        self.lib.call("fvmgpu_bcgstab_ilu0_solve", self.h, ds.h, int(n_max_iterations), float(relative_tolerance),
+                      float(absolute_tolerance), C.byref(r0), C.byref(r), C.byref(it))
+        return r0.value, r.value, it.value
+
+    def ilu0(self, ds, n_max_iterations, relative_tolerance, absolute_tolerance=1e-50):
+        r0, r, it, lv = C.c_double(0), C.c_double(0), C.c_int(0), C.c_int(0)
+        self.lib.call("fvmgpu_ilu0_solve", self.h, ds.h, int(n_max_iterations), float(relative_tolerance),
+                      float(absolute_tolerance), C.byref(r0), C.byref(r), C.byref(it), C.byref(lv))
+        self.ilu_levels = lv.value
         return r0.value, r.value, it.value
 
     def levels(self):

@@ -413,6 +413,32 @@ int fvmgpu_bcgstab_solve(fvmgpu_solver_t precond, fvmgpu_system_t sys, int nMaxI
   A(precond)->bcgstab(S(sys), nMaxIterations, relativeTolerance, absoluteTolerance, rnorm0, rnorm, iters);
   API_END
 }
+int fvmgpu_bcgstab_ilu0_solve(fvmgpu_solver_t s, fvmgpu_system_t sys, int nMaxIterations, double relativeTolerance,
+                              double absoluteTolerance, double* rnorm0, double* rnorm, int* iters) {
+  API_BEGIN
+  Amg* a = A(s);
+  // the Krylov vectors live on level 0 of a hierarchy; its coarse levels are not needed here
+  const int keepLevels = a->opts.maxCoarseLevels, keepKind = a->precondKind;
+  a->opts.maxCoarseLevels = 0;
+  a->precondKind = 1;
+  try {
+    a->bcgstab(S(sys), nMaxIterations, relativeTolerance, absoluteTolerance, rnorm0, rnorm, iters);
+  } catch (...) {
+    a->opts.maxCoarseLevels = keepLevels; a->precondKind = keepKind;
+    a->cleanup();
+    throw;
+  }
+  a->opts.maxCoarseLevels = keepLevels; a->precondKind = keepKind;
+  a->cleanup();
+  API_END
+}
+int fvmgpu_ilu0_solve(fvmgpu_solver_t s, fvmgpu_system_t sys, int nMaxIterations, double relativeTolerance,
+                      double absoluteTolerance, double* rnorm0, double* rnorm, int* iters, int* levels) {
+  API_BEGIN
+  A(s)->iluSolve(S(sys), nMaxIterations, relativeTolerance, absoluteTolerance, rnorm0, rnorm, iters);
+  if (levels) *levels = A(s)->iluLevels(S(sys));
+  API_END
+}
 int fvmgpu_cg_solve(fvmgpu_solver_t precond, fvmgpu_system_t sys, int nMaxIterations, double relativeTolerance,
                     double absoluteTolerance, double* rnorm0, double* rnorm, int* iters) {
   API_BEGIN

@@ -983,8 +983,12 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
     double r0 = 0, r = 0;
     int it = 0;
     if (norms[k] > 0.0) {
-      if (useBcgstab) solver->bcgstab(s, bcgMaxIter, bcgRel, bcgAbs, &r0, &r, &it);
-      else solver->solve(s, &r0, &r, &it);
+      if (useBcgstab) {   // 1: preconditioned by one AMG cycle, 2: by the reference's ILU(0)
+        const int keep = solver->precondKind;
+        solver->precondKind = useBcgstab == 2 ? 1 : 0;
+        solver->bcgstab(s, bcgMaxIter, bcgRel, bcgAbs, &r0, &r, &it);
+        solver->precondKind = keep;
+      } else solver->solve(s, &r0, &r, &it);
     }
     if (rnorm0) rnorm0[k] = norms[k];
     if (iters) iters[k] = it;
@@ -1034,8 +1038,12 @@ void flowSolveContinuity(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, d
   System* s = F->pp.get();
   double r0 = 0, r = 0;
   int it = 0;
-  if (useBcgstab) solver->bcgstab(s, bcgMaxIter, bcgRel, bcgAbs, &r0, &r, &it);
-  else solver->solve(s, &r0, &r, &it);
+  if (useBcgstab) {
+    const int keep = solver->precondKind;
+    solver->precondKind = useBcgstab == 2 ? 1 : 0;
+    solver->bcgstab(s, bcgMaxIter, bcgRel, bcgAbs, &r0, &r, &it);
+    solver->precondKind = keep;
+  } else solver->solve(s, &r0, &r, &it);
   if (rnorm0) *rnorm0 = r0;
   if (iters) *iters = it;
   double* pp = s->delta.p;

@@ -2020,6 +2020,19 @@ void Amg::smooth(System* sys) {
 // one preconditioner application in LEVEL-0 numbering: xhat = cycle(b = rhs, x0 = 0)
 void Amg::precondition(const double* rhsPerm, double* outPerm) {
   Level& L0 = *levels[0];
+  if (precondKind == 1) {
+    // ILU0Solver::smooth works in the system's own numbering: level rows -> natural rows and back
+    const size_t nt = (size_t)builtFor->nTotal;
+    if (natIn.n < nt) { natIn.alloc(nt); natOut.alloc(nt); natIn.zero(); natOut.zero(); }
+    parallelFor(L0.n, PermScatterKernel{perm0.p, rhsPerm, natIn.p});
+    iluSmooth(builtFor, natIn.p, natOut.p);
+    parallelFor(L0.n, PermGatherKernel{perm0.p, natOut.p, outPerm});
+    if (L0.nGhost) {
+      devMemset(outPerm + L0.n, 0, (size_t)L0.nGhost * sizeof(double));
+      exchange(L0, outPerm);
+    }
+    return;
+  }
   copyD2D(L0.b.p, rhsPerm, (size_t)L0.n * sizeof(double));
   L0.xZero = true;
   L0.rValid = false;

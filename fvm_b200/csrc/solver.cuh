@@ -33,8 +33,19 @@ struct Level {
   DBuf<int> ghostCoarse;         // per ghost slot: x index in the NEXT level (>= its n), -1 = none
 };
 
+struct Ilu0;
+struct Ilu0Deleter { void operator()(Ilu0* p) const; };
+
 struct Amg {
   fvmgpu_amg_opts opts;
+  // ILU(0) factors of the last system (csrc/ilu.cu): ILU0Solver and BCGStab's ILU0 preconditioner
+  std::unique_ptr<Ilu0, Ilu0Deleter> ilu;
+  Ilu0& iluFor(System* sys);
+  void iluSmooth(System* sys, const double* rhs, double* out);
+  int iluLevels(System* sys);
+  void iluSolve(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0, double* rnorm, int* iters);
+  int precondKind = 0;   // what bcgstab() applies: 0 one AMG cycle, 1 ILU(0)
+  DBuf<double> natIn, natOut;
   std::vector<std::unique_ptr<Level>> levels;
   DBuf<int> perm0;           // system (natural) row -> level-0 row
   DBuf<double> scalars;      // device scalars for dots / norms

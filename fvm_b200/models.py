@@ -319,7 +319,8 @@ class AMG(LinearSolver):
 
 
 class BCGStab(LinearSolver):
-    """F/BCGStab.h; `preconditioner` must be an AMG (one cycle per application, F/BCGStab.cpp:85-89)."""
+    """F/BCGStab.h; `preconditioner` is an AMG (one cycle per application, F/BCGStab.cpp:85-89) or an
+    ILU0Solver (one ILU(0) solve per application, T/PARALLEL_CAVITY_ILU0)."""
 
     def __init__(self):
         super().__init__()
@@ -331,7 +332,10 @@ class BCGStab(LinearSolver):
         if self.preconditioner is None:
             raise CException("BCGStab: no preconditioner set")
         dev = self.preconditioner._device(ls.lib)
-        r0, r, it = dev.bcgstab(ls, self.nMaxIterations, self.relativeTolerance, self.absoluteTolerance)
+        if isinstance(self.preconditioner, ILU0Solver):
+            r0, r, it = dev.bcgstab_ilu0(ls, self.nMaxIterations, self.relativeTolerance, self.absoluteTolerance)
+        else:
+            r0, r, it = dev.bcgstab(ls, self.nMaxIterations, self.relativeTolerance, self.absoluteTolerance)
         self._totalIterations += it
         self.lastIterations = it
         self.lastResidual = r
@@ -405,6 +409,36 @@ class JacobiSolver(LinearSolver):
 
     def smooth(self, ls):
         raise CException("JacobiSolver.smooth: use AMG with smootherType = JACOBI as a preconditioner")
+
+    def cleanup(self):
+        self._amg.cleanup()
+
+
+class ILU0Solver(LinearSolver):
+    """F/ILU0Solver.h, F/ILU0Solver.cpp:46-93: delta = U^-1 L^-1 (-b) per sweep with the reference's ILU(0)
+    (F/CRMatrix.h:1546-1715, factors bit-identical to the reference's). On its own every sweep recomputes the
+    same delta -- exactly as in the reference -- so it is meant as BCGStab's preconditioner."""
+
+    def __init__(self):
+        super().__init__()
+        self._amg = AMG()
+        self.lastIterations = 0
+
+    def _device(self, lib):
+        return self._amg._device(lib)
+
+    def solve(self, ls):
+        dev = self._device(ls.lib)
+        r0, r, it = dev.ilu0(ls, self.nMaxIterations, self.relativeTolerance, self.absoluteTolerance)
+        self.lastIterations = it
+        self.lastResidual = r
+        if self.verbosity > 0:
+            print("0: [%s : %g]" % (ls.field_name, r0))
+            print("%d: [%s : %g]" % (it, ls.field_name, r))
+        return r0
+
+    def smooth(self, ls):
+        self._device(ls.lib).ilu0(ls, 2, 0.0, 0.0)   # one sweep
 
     def cleanup(self):
         self._amg.cleanup()
@@ -709,7 +743,8 @@ def _solver_args(solver):
     if isinstance(solver, BCGStab):
         if solver.preconditioner is None:
             raise CException("BCGStab: no preconditioner set")
-        return solver.preconditioner, (solver.nMaxIterations, solver.relativeTolerance, solver.absoluteTolerance)
+        kind = 2 if isinstance(solver.preconditioner, ILU0Solver) else 1   # fvmgpu_flow_solve_*'s bcgstab argument
+        return solver.preconditioner, (solver.nMaxIterations, solver.relativeTolerance, solver.absoluteTolerance, kind)
     return solver, None
 
 

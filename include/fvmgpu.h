@@ -212,6 +212,15 @@ int fvmgpu_solver_history(fvmgpu_solver_t s, int cap, double* out, int* n);
 int fvmgpu_bcgstab_solve(fvmgpu_solver_t precond, fvmgpu_system_t sys, int nMaxIterations,
                          double relativeTolerance, double absoluteTolerance, double* rnorm0,
                          double* rnorm, int* iters);
+/* the same with ILU0Solver::smooth as the preconditioner (T/PARALLEL_CAVITY_ILU0): x = U^-1 L^-1 (-r) with the
+ * reference's own ILU(0) (CRMatrix::compute_ILU0 / lowerSolve / upperSolve, F/CRMatrix.h:1546-1715); `s` is any
+ * solver handle, it keeps the factors */
+int fvmgpu_bcgstab_ilu0_solve(fvmgpu_solver_t s, fvmgpu_system_t sys, int nMaxIterations, double relativeTolerance,
+                              double absoluteTolerance, double* rnorm0, double* rnorm, int* iters);
+/* ILU0Solver::solve (F/ILU0Solver.cpp:46-93): delta = U^-1 L^-1 (-b) per sweep, residual 1-norm test.
+ * levels (optional): dependency levels of the factorisation (one kernel launch each) */
+int fvmgpu_ilu0_solve(fvmgpu_solver_t s, fvmgpu_system_t sys, int nMaxIterations, double relativeTolerance,
+                      double absoluteTolerance, double* rnorm0, double* rnorm, int* iters, int* levels);
 /* CG::solve (F/CG.cpp:24-140): conjugate gradients preconditioned by one AMG cycle of `precond` */
 int fvmgpu_cg_solve(fvmgpu_solver_t precond, fvmgpu_system_t sys, int nMaxIterations,
                     double relativeTolerance, double absoluteTolerance, double* rnorm0, double* rnorm,
@@ -306,7 +315,8 @@ int fvmgpu_flow_assemble_momentum(fvmgpu_flow_t flow, const fvmgpu_flow_opts* op
 /* parity hook: VVMatrix diag (3 per cell) / scalar offdiag / b (3 per cell) */
 int fvmgpu_flow_download_momentum(fvmgpu_flow_t flow, double* diag3, double* offdiag, double* b3);
 /* momentumLinearSolver.solve + postSolve + updateSolution + momAp (:744-768). bcgstab != 0:
- * BCGStab (its nMaxIterations / tolerances given here) preconditioned by `solver`.
+ * BCGStab (its nMaxIterations / tolerances given here) preconditioned by `solver` (1: one AMG cycle,
+ * 2: the reference's ILU(0), see fvmgpu_bcgstab_ilu0_solve).
  * rnorm0[3] = initial residual 1-norm per velocity component, iters[3] */
 int fvmgpu_flow_solve_momentum(fvmgpu_flow_t flow, fvmgpu_solver_t solver, int bcgstab, int bcgMaxIterations,
                                double bcgRelTol, double bcgAbsTol, double* rnorm0, int* iters);

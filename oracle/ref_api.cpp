@@ -37,6 +37,9 @@
 #include <atype.h>
 #include "AMG.h"
 #include "BCGStab.h"
+#include "ILU0Solver.h"
+#include "CG.h"
+#include "JacobiSolver.h"
 #include "CRMatrix.h"
 #include "FluentReader.h"
 #include "GeomFields.h"
@@ -80,7 +83,8 @@ struct RefMesh {
 };
 
 struct SolverCfg {  // mirrors the public tunables of F/AMG.h:74-81 and F/LinearSolver.h:15-20
-  int kind;         // 0 = AMG, 1 = BCGStab preconditioned by one AMG cycle
+  int kind;         // 0 = AMG, 1 = BCGStab preconditioned by one AMG cycle, 2 = ILU0Solver,
+                    // 3 = BCGStab preconditioned by ILU0Solver, 4 = CG preconditioned by AMG, 5 = JacobiSolver
   int nMaxIterations;
   int verbosity;
   double relativeTolerance;
@@ -97,6 +101,9 @@ struct SolverCfg {  // mirrors the public tunables of F/AMG.h:74-81 and F/Linear
 struct RefSolver {
   std::shared_ptr<AMG> amg;
   std::shared_ptr<BCGStab> bcg;
+  std::shared_ptr<ILU0Solver> ilu;
+  std::shared_ptr<CG> cg;
+  std::shared_ptr<JacobiSolver> jac;
   LinearSolver* top = nullptr;
 };
 
@@ -112,6 +119,23 @@ static RefSolver make_solver(const SolverCfg& c) {
   s.amg->smootherType = (AMG::SmootherType)c.smootherType;
   if (c.kind == 0) {
     s.top = s.amg.get();
+  } else if (c.kind == 2) {
+    s.ilu.reset(new ILU0Solver());
+    s.top = s.ilu.get();
+  } else if (c.kind == 3) {
+    s.ilu.reset(new ILU0Solver());
+    s.ilu->verbosity = 0;
+    s.bcg.reset(new BCGStab());
+    s.bcg->preconditioner = s.ilu.get();
+    s.top = s.bcg.get();
+  } else if (c.kind == 4) {
+    s.cg.reset(new CG());
+    s.cg->preconditioner = s.amg.get();
+    s.amg->verbosity = 0;
+    s.top = s.cg.get();
+  } else if (c.kind == 5) {
+    s.jac.reset(new JacobiSolver());
+    s.top = s.jac.get();
   } else {
     s.bcg.reset(new BCGStab());
     s.bcg->preconditioner = s.amg.get();
