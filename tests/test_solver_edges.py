@@ -205,3 +205,24 @@ def test_ilu0_solver_classes_in_the_model_api(hostsim_lib):
             tm.advance(1)
         out[name] = tf.temperature[mesh.getCells()].copy()
     assert np.abs(out["amg"] - out["ilu0"]).max() <= 1e-9 * np.abs(out["amg"]).max()
+
+
+def test_jacobi_solver_is_bit_identical_to_the_reference_class(hostsim_lib):
+    """F/JacobiSolver.cpp on T/MatrixMarket226.dat: 1265 iterations to rel 1e-12 in the reference and here, the
+    same last residual to the last digit and the same delta bit for bit (every row's sum runs in entry order)."""
+    from conftest import load_golden
+    from oracle import refapi as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
+    g = load_golden("mm226.npz")
+    n = int(g["n"])
+    ds = X.DeviceSystem(hostsim_lib, raw=(n, 0, g["row"], g["col"], g["diag"], g["off"], g["b"]))
+    amg = X.DeviceAMG(hostsim_lib)
+    r0, r, it = amg.jacobi(ds, 20000, 1e-12, 1e-50)
+    ref = R.linsolve(n, g["row"], g["col"], g["diag"], g["off"], g["b"],
+                     R.solver_cfg(kind=5, nMaxIterations=20000, verbosity=1, relativeTolerance=1e-12))
+    last = ref["text"].splitlines()[-1]
+    assert it == int(last.split(":")[0]) == 1265
+    assert "%g" % r == last.split(":")[-1].strip(" ]")
+    assert np.array_equal(ds.get_field(X.FIELD_DELTA), ref["x"])
+    amg.close(); ds.close()
