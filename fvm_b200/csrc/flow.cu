@@ -952,6 +952,28 @@ void flowDownloadMomentum(Flow* F, double* diag3, double* off, double* b3) {
 
 // LinearSolver::solve on the momentum system + postSolve + updateSolution + momAp (F/FlowModel_impl.h:744-768).
 // useBcgstab: BCGStab preconditioned by `solver` with its own iteration limit / tolerances.
+//
+// The reference solves ONE system whose unknowns are Vector<T,3>. Every reduction (norms, BCGStab's dot
+// products) is a Vector of per-component sums (F/Vector.h:189-199), so the three components run independent
+// recurrences -- but the convergence test is shared: `normRatio < relativeTolerance` compares the MAGNITUDE of
+// the vector of component ratios (Vector::operator<, F/Vector.h:169-172; zero components divide safely and
+// count 0). All components therefore take the same number of cycles / iterations N, the first one at which
+// |(r_x, r_y, r_z)|_2 < tol * |(r0_x, r0_y, r0_z)|_2 (r_k = 1-norm of component k's residual). Here the components
+// are advanced in rounds -- an AMG cycle continues from the stored delta, a Krylov recurrence is re-run for
+// exactly N iterations -- and the shared test ends the rounds. With the loose inner tolerances of the reference's own scripts (1e-1) this is what makes the
+// outer SIMPLE iterates follow the reference's.
+struct SplitComponentKeep {  // scalar system of velocity component k, continuing from its stored delta
+  int k; const double* diag3; const double* b3; const double* delta3; double* diag; double* b; double* delta;
+  FVM_DEV void operator()(long long i) const { diag[i] = diag3[3 * i + k]; b[i] = b3[3 * i + k]; delta[i] = delta3[3 * i + k]; }
+};
+struct DiagTensorDiffRows {  // rows whose three diagonal components are not all equal
+  const double* d3;
+  FVM_DEV void operator()(long long i, double* o) const { o[0] = (d3[3 * i] != d3[3 * i + 1] || d3[3 * i] != d3[3 * i + 2]) ? 1.0 : 0.0; }
+};
+struct StoreComponent { int k; const double* delta; double* delta3; FVM_DEV void operator()(long long i) const { delta3[3 * i + k] = delta[i]; } };
+struct ZeroComponent { int k; double* delta3; FVM_DEV void operator()(long long i) const { delta3[3 * i + k] = 0.0; } };
+struct AddRows { const double* a; double* b; FVM_DEV void operator()(long long i) const { b[i] += a[i]; } };
+
 void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, double bcgRel, double bcgAbs,
                        double* rnorm0 /*3*/, int* iters /*3*/) {
   requireReady();
@@ -965,8 +987,8 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
   copyD2H(norms, F->scal.p + 2, sizeof(norms));
   copyD2D(s->off.p, F->mOff.p, (size_t)m->nnz * sizeof(double));
   bool haveHierarchy = false;
-  for (int k = 0; k < 3; k++) {
-    parallelFor(nt, SplitComponent{k, F->mDiag.p, F->mB.p, s->diag.p, s->b.p, s->delta.p});
+  auto select = [&](int k) {   // component k (with its current delta) becomes the scalar system
+    parallelFor(nt, SplitComponentKeep{k, F->mDiag.p, F->mB.p, F->mDelta.p, s->diag.p, s->b.p, s->delta.p});
     bool same = false;
     if (haveHierarchy) {
       reduceRows<1>(m->nSelf, DiffCountRows{s->diag.p, F->lastDiag.p}, F->scal.p + 5);
@@ -980,20 +1002,78 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
       copyD2D(F->lastDiag.p, s->diag.p, (size_t)nt * sizeof(double));
       haveHierarchy = true;
     }
+  };
+  auto store = [&](int k) { parallelFor(nt, StoreComponent{k, s->delta.p, F->mDelta.p}); };
+  auto krylov = [&](int maxIter, double rel, double abs, int* it) {   // 1: one AMG cycle, 2: the reference's ILU(0)
+    const int keep = solver->precondKind;
     double r0 = 0, r = 0;
-    int it = 0;
-    if (norms[k] > 0.0) {
-      if (useBcgstab) {   // 1: preconditioned by one AMG cycle, 2: by the reference's ILU(0)
-        const int keep = solver->precondKind;
-        solver->precondKind = useBcgstab == 2 ? 1 : 0;
-        solver->bcgstab(s, bcgMaxIter, bcgRel, bcgAbs, &r0, &r, &it);
-        solver->precondKind = keep;
-      } else solver->solve(s, &r0, &r, &it);
-    }
-    if (rnorm0) rnorm0[k] = norms[k];
-    if (iters) iters[k] = it;
-    parallelFor(nt, MergeComponent{k, s->delta.p, F->mDelta.p, F->V.p});
+    solver->precondKind = useBcgstab == 2 ? 1 : 0;
+    solver->bcgstab(s, maxIter, rel, abs, &r0, &r, it);
+    solver->precondKind = keep;
+  };
+  const fvmgpu_amg_opts userOpts = solver->opts;
+  const int limit = useBcgstab ? bcgMaxIter : userOpts.nMaxIterations - 1;
+  const double rel = useBcgstab ? bcgRel : userOpts.relativeTolerance;
+  const double abs = useBcgstab ? bcgAbs : userOpts.absoluteTolerance;
+  std::vector<double> hist[3];
+  for (int k = 0; k < 3; k++) hist[k].assign(1, norms[k]);
+  // ---- the shared convergence test: |rNorm|_2 / |rNorm0|_2 over the vector of component 1-norms
+  // (MultiFieldReduction::normalize + Vector::operator<, F/AMG.cpp:256-272, F/BCGStab.cpp:131-147)
+  double den = 0;
+  for (int k = 0; k < 3; k++) den += norms[k] * norms[k];
+  auto converged = [&](int i) {
+    double num = 0;
+    for (int k = 0; k < 3; k++) { const double r = hist[k][(size_t)std::min<int>(i, (int)hist[k].size() - 1)]; num += r * r; }
+    return num < abs * abs || (den > 0 ? num / den : num) < rel * rel;
+  };
+  int N = 0;
+  bool coupledKrylov = false;
+  if (useBcgstab && den > 0 && !(den < abs * abs)) {
+    // the reference's BCGStab shares its scalars between the components (Amg::bcgstabMulti); that needs one
+    // diagonal for all three (always the case without symmetry planes)
+    reduceRows<1>(m->nSelf, DiagTensorDiffRows{F->mDiag.p}, F->scal.p + 5);
+    if (F->multi) commAllreduceSum(F->scal.p + 5, 1);
+    double nd;
+    copyD2H(&nd, F->scal.p + 5, sizeof(double));
+    coupledKrylov = nd == 0.0;
   }
+  if (coupledKrylov) {
+    select(0);
+    const int keep = solver->precondKind;
+    solver->precondKind = useBcgstab == 2 ? 1 : 0;
+    double r0v[3], rv[3];
+    solver->bcgstabMulti(s, 3, F->mB.p, F->mDelta.p, bcgMaxIter, bcgRel, bcgAbs, r0v, rv, &N);
+    solver->precondKind = keep;
+  } else if (den > 0 && !(den < abs * abs)) {
+    while (N < limit) {
+      N++;
+      for (int k = 0; k < 3; k++) {
+        if (!(norms[k] > 0.0)) continue;
+        if (useBcgstab) {   // a Krylov recurrence cannot be resumed: run it again for exactly N iterations
+          parallelFor(nt, ZeroComponent{k, F->mDelta.p});
+          select(k);
+          int done = 0;
+          krylov(N, 0.0, 0.0, &done);
+          hist[k] = solver->history;
+        } else {            // stationary iteration: one more cycle from the stored delta
+          select(k);
+          solver->opts.nMaxIterations = 2; solver->opts.relativeTolerance = 0.0; solver->opts.absoluteTolerance = 0.0;
+          double r0 = 0, r = 0;
+          int one = 0;
+          solver->solve(s, &r0, &r, &one);
+          solver->opts = userOpts;
+          hist[k].push_back(r);
+        }
+        store(k);
+      }
+      if (converged(N)) break;
+    }
+  }
+  for (int k = 0; k < 3; k++) {
+    if (rnorm0) rnorm0[k] = norms[k];
+    if (iters) iters[k] = (norms[k] > 0.0 || coupledKrylov) ? N : 0;
+  }
+  parallelFor(3LL * nt, AddRows{F->mDelta.p, F->V.p});   // ls.updateSolution: x += delta
   parallelFor(nt - m->nSelf, MomentumGhostRows{m->nSelf, m->row.p, m->col.p, s->isBoundary.p, F->mDiag.p, F->mOff.p,
                                                F->mB.p, F->mDelta.p, F->V.p});
   copyD2D(F->momAp.p, F->mDiag.p, 3 * (size_t)nt * sizeof(double));

@@ -2112,6 +2112,115 @@ void Amg::bcgstab(System* sys, int nMaxIterations, double relTol, double absTol,
   if (itersOut) *itersOut = iters;
 }
 
+// BCGStab on a system whose unknowns are Vector<T,NC> with one scalar off-diagonal and one diagonal shared by
+// the components (the momentum system, F/FlowModel_impl.h:744-768): the reference's dot products are summed
+// over the components as well (MultiFieldReduction::reduceSum after every dotWith, F/BCGStab.cpp:67-69,
+// 95-96, 121-125; F/MultiFieldReduction.cpp:165-185), so alpha, beta and omega are SHARED and the components do
+// not run independent recurrences; the norms stay per component and the convergence test compares the
+// magnitude of that vector with the initial one's (normalize, :131-147). b3 / delta3: NC values per row (AoS) in
+// the system's natural numbering; sys supplies pattern, off-diagonal and the common diagonal.
+struct PermGatherAoS {  // dst[perm[i]] = src[nc*i + k]
+  const int* perm; const double* src; int nc, k; double* dst;
+  FVM_DEV void operator()(long long i) const { dst[perm[i]] = src[(size_t)nc * i + k]; }
+};
+struct PermScatterAoS {  // dst[nc*i + k] = src[perm[i]]
+  const int* perm; const double* src; int nc, k; double* dst;
+  FVM_DEV void operator()(long long i) const { dst[(size_t)nc * i + k] = src[perm[i]]; }
+};
+struct PermScatterGhostAoS {  // ghost slots keep their cell index: dst[nc*(n+g) + k] = src[g]
+  const double* src; int nc, k, n; double* dst;
+  FVM_DEV void operator()(long long g) const { dst[(size_t)nc * (n + g) + k] = src[g]; }
+};
+struct AbsRowsStrided {  // 1-norms of up to 3 component vectors stored one after the other
+  const double* a; long long stride; int nc;
+  FVM_DEV void operator()(long long i, double* o) const {
+    o[0] = fabs(a[i]); o[1] = nc > 1 ? fabs(a[stride + i]) : 0.0; o[2] = nc > 2 ? fabs(a[2 * stride + i]) : 0.0;
+  }
+};
+void Amg::bcgstabMulti(System* sys, int nc, const double* b3, double* delta3, int nMaxIterations, double relTol,
+                       double absTol, double* rnorm0Out, double* rnormOut, int* itersOut) {
+  requireReady();
+  if (nc < 1 || nc > 3) fail("bcgstabMulti: 1 to 3 components");
+  ensureSetup(sys);
+  history.clear();
+  Level& L0 = *levels[0];
+  const int n = L0.n;
+  const size_t ng = (size_t)L0.nGhost, ns = (size_t)n + ng, N = (size_t)nc * n;
+  DBuf<double> x(nc * ns), pHat(nc * ns), bOrig(N), r(N), rTilda(N), p(N), v(N), t(N);
+  x.zero(); pHat.zero();
+  for (int k = 0; k < nc; k++) {
+    parallelFor(n, PermGatherAoS{perm0.p, b3, nc, k, bOrig.p + (size_t)k * n});
+    parallelFor(n, PermGatherAoS{perm0.p, delta3, nc, k, x.p + k * ns});
+    if (ng) exchange(L0, x.p + k * ns);
+  }
+  auto allreduce = [&](double* ptr, int cnt) { if (multi) commAllreduceSum(ptr, cnt); };
+  auto norms = [&](double* out3) {   // per-component 1-norms of r
+    reduceRows<3>(n, AbsRowsStrided{r.p, n, nc}, scalars.p + 8);
+    allreduce(scalars.p + 8, 3);
+    copyD2H(out3, scalars.p + 8, 3 * sizeof(double));
+  };
+  for (int k = 0; k < nc; k++)   // r = b + A x
+    parallelFor(n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, bOrig.p + (size_t)k * n, x.p + k * ns,
+                                r.p + (size_t)k * n});
+  double r0[3], rn[3];
+  norms(r0);
+  for (int k = 0; k < 3; k++) rn[k] = r0[k];
+  double den = 0;
+  for (int k = 0; k < nc; k++) den += r0[k] * r0[k];
+  history.push_back(std::sqrt(den));
+  copyD2D(rTilda.p, r.p, N * sizeof(double));
+  double* S = scalars.p;
+  int iters = 0;
+  bool haveP = false;
+  auto mag2 = [&](const double* q) { double m = 0; for (int k = 0; k < nc; k++) m += q[k] * q[k]; return m; };
+  for (int i = 0; i < nMaxIterations; i++) {
+    iters++;
+    copyD2D(S + 1, S + 0, sizeof(double));
+    reduceRows<1>((long long)N, Dot1Rows{r.p, rTilda.p}, S + 0);          // rho, summed over the components
+    allreduce(S + 0, 1);
+    if (!haveP) { copyD2D(p.p, r.p, N * sizeof(double)); haveP = true; }
+    else parallelFor((long long)N, BcgUpdateP{S, v.p, r.p, p.p});
+    for (int k = 0; k < nc; k++) {
+      precondition(p.p + (size_t)k * n, pHat.p + k * ns);
+      MultiplyRows m{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, pHat.p + k * ns, v.p + (size_t)k * n};
+      parallelFor(n, m);
+    }
+    copyD2D(S + 2, S + 0, sizeof(double));
+    reduceRows<1>((long long)N, Dot1Rows{rTilda.p, v.p}, S + 3);
+    allreduce(S + 3, 1);
+    for (int k = 0; k < nc; k++) parallelFor(n, MsaxpyScalarPtr{S + 2, S + 3, pHat.p + k * ns, x.p + k * ns});
+    parallelFor((long long)N, MsaxpyScalarPtr{S + 2, S + 3, v.p, r.p});
+    norms(rn);
+    if (mag2(rn) < absTol * absTol) break;
+    for (int k = 0; k < nc; k++) {
+      precondition(r.p + (size_t)k * n, pHat.p + k * ns);
+      MultiplyRows m{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, pHat.p + k * ns, t.p + (size_t)k * n};
+      parallelFor(n, m);
+    }
+    reduceRows<2>((long long)N, Dot2Rows{t.p, r.p}, S + 4);
+    allreduce(S + 4, 2);
+    for (int k = 0; k < nc; k++) parallelFor(n, MsaxpyScalarPtr{S + 4, S + 5, pHat.p + k * ns, x.p + k * ns});
+    parallelFor((long long)N, MsaxpyScalarPtr{S + 4, S + 5, t.p, r.p});
+    norms(rn);
+    history.push_back(std::sqrt(mag2(rn)));
+    const double num = mag2(rn);
+    if (num < absTol * absTol || (den > 0 ? num / den : num) < relTol * relTol) break;
+  }
+  totalIterations += iters;
+  for (int k = 0; k < nc; k++) {
+    parallelFor(n, PermScatterAoS{perm0.p, x.p + k * ns, nc, k, delta3});
+    if (ng) {  // ghosts of delta synced, as the reference leaves them (x->sync())
+      exchange(L0, x.p + k * ns);
+      parallelFor((long long)ng, PermScatterGhostAoS{x.p + k * ns + n, nc, k, n, delta3});
+    }
+  }
+  for (int k = 0; k < nc; k++) {
+    if (rnorm0Out) rnorm0Out[k] = r0[k];
+    if (rnormOut) rnormOut[k] = rn[k];
+  }
+  if (itersOut) *itersOut = iters;
+}
+
 // CG::solve, F/CG.cpp:24-140: conjugate gradients preconditioned by one AMG cycle from a zero guess
 // (preconditioner->smooth on (delta := z = 0, b := r)). Sign convention of the library: r = b + A x,
 // the cycle solves A z + r = 0, so x -= alpha p and r -= alpha q exactly as the reference's msaxpy calls.

@@ -100,6 +100,8 @@ struct Amg {
   void bcgstab(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0, double* rnorm,
                int* iters);
   void cg(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0, double* rnorm, int* iters);
+  void bcgstabMulti(System* sys, int nc, const double* b3, double* delta3, int nMaxIterations, double relTol,
+                    double absTol, double* rnorm0, double* rnorm, int* iters);
   void jacobiSolve(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0, double* rnorm,
                    int* iters);
 

@@ -296,3 +296,51 @@ def test_parallel_cavity_amg_convergence_history_tracks_the_golden(hostsim_lib):
         ratio = ours[1:, col] / gold[1:, col]
         assert ratio.max() < 1.6 and ratio.min() > 1 / 1.6, (col, ratio.min(), ratio.max())
         assert abs(ratio[-1] - 1.0) < 0.05
+
+
+PCAV_ILU_GOLDEN = "/root/reference/src/fvm/test/PARALLEL_CAVITY_ILU0/proc1/GOLDEN/convergence.dat"
+
+
+@pytest.mark.skipif(not os.path.exists(PCAV_ILU_GOLDEN), reason="reference tree not mounted")
+def test_parallel_cavity_ilu0_reproduces_the_golden_convergence_history(hostsim_lib):
+    """T/PARALLEL_CAVITY_ILU0 (testFlowParallel.py on cav32.cas; momentum and pressure correction solved by
+    BCGStab preconditioned with ILU0Solver, rel 1e-1 / 20 iterations; 100 SIMPLE iterations). Everything on this
+    path is deterministic arithmetic in the reference's order -- assembly, the ILU(0) factors, and a BCGStab whose
+    dot products are summed over the three velocity components exactly as MultiFieldReduction::reduceSum does --
+    so, unlike the AMG variant, the whole outer history of the golden file is reproduced: all 100 momentum (x, y)
+    and continuity norms to the golden's printed precision (5e-6; 97 of 100 within 5e-7)."""
+    import contextlib
+    import io
+    import re
+    reader = importers.FluentCase(FVM002_CAS)
+    reader.read()
+    meshes = reader.getMeshList()
+    geom = M.GeomFields("geom")
+    M.MeshMetricsCalculatorA(geom, meshes, lib=hostsim_lib).init()
+    ff = M.FlowFields("flow")
+    fm = M.FlowModelA(geom, ff, meshes, lib=hostsim_lib)
+    bc3 = fm.getBCMap()[3]
+    bc3.bcType = "NoSlipWall"
+    bc3.setVar("specifiedXVelocity", 1)
+    for vc in fm.getVCMap().values():
+        vc.setVar("density", 1.0); vc.setVar("viscosity", 0.1)
+    fo = fm.getOptions()
+    for nm in ("momentumLinearSolver", "pressureLinearSolver"):
+        s = M.BCGStab()
+        s.preconditioner = M.ILU0Solver()
+        s.relativeTolerance, s.nMaxIterations, s.verbosity = 1e-1, 20, 0
+        setattr(fo, nm, s)
+    fo.momentumTolerance = fo.continuityTolerance = 1e-5
+    fo.printNormalizedResiduals = False
+    fm.init()
+    with contextlib.redirect_stdout(io.StringIO()):
+        fm.advance(100)
+    ours = np.array([[t["momentum_norm"][0], t["momentum_norm"][1], t["continuity_norm"]] for t in fm.timings])
+    gold = np.array([[float(x) for x in re.findall(r"[-+]?\d+\.?\d*(?:e[-+]?\d+)?", l.split(":", 1)[1])]
+                     for l in open(PCAV_ILU_GOLDEN).read().splitlines()])[:, [0, 1, 3]]
+    assert ours.shape == gold.shape == (100, 3)
+    dev = np.abs(ours - gold) / np.maximum(np.abs(gold), 1e-300)
+    dev[0, 1] = 0.0                      # the y-momentum norm of iteration 0 is exactly 0 in both
+    assert ours[0, 1] == gold[0, 1] == 0.0
+    assert dev.max() < 5e-6 and (dev.max(axis=1) < 5e-7).sum() >= 90
+    assert all(t["momentum_norm"][2] == 0.0 for t in fm.timings)
