@@ -108,6 +108,21 @@ def test_flow_model_on_partitioned_meshes(world, case):
     assert res[0]["vmax"] > 0.02    # the lid actually drives a flow in the interior cells
 
 
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/fvm/test/PARALLEL_CAVITY_JACOBI/PROC4/GOLDEN/convergence.dat"),
+                    reason="reference tree not mounted")
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_partitioned_cavity_reproduces_the_reference_parallel_golden(world):
+    """T/PARALLEL_CAVITY_JACOBI: the reference's golden outer-residual history is the same file for 1, 4, 16 and
+    64 MPI ranks (Jacobi relaxation with a ghost refresh after every pass is partition-independent). FlowModelA on
+    1, 2 and 3 mesh parts of cav32.cas -- halo exchanges, all-reduced norms, shared convergence test, reference
+    pressure from the owner of cell 0 -- reproduces every number of that file to its printed precision."""
+    res = run_world(world, "cav32", "flowgold")
+    for d in res:
+        assert d["rows"] == 10 and d["y0"] == 0.0
+        assert d["golden_dev"] < 2e-6, d["golden_dev"]
+        assert world == 1 or d["collectives"] > 0
+
+
 def test_electric_model_on_partitioned_tets():
     """BASELINE configs[4] in miniature: ElectricModelA (Poisson + drift / transient charge transport) on
     an RCB-partitioned tet mesh, 2 ranks, against the single-partition run of the same model."""
