@@ -944,6 +944,36 @@ class FlowModelA:
         self._download(mesh, fl)
         return converged
 
+    def dumpContinuityMatrix(self, file_base):
+        """Impl::dumpContinuityMatrix, F/FlowModel_impl.h:1560-1622: one momentum solve, then the pressure-
+        correction system as a MatrixMarket file + right-hand side (T/FLOW_CONTINUITY_MATRIX)."""
+        o = self._options
+        mesh = self.meshes[0]
+        fl = self._flows[mesh.getID()]
+        msolver, mbcg = _solver_args(o.getMomentumLinearSolver())
+        mdev = msolver._device(fl.lib)
+        self._upload(mesh, fl)
+        fo = self._flow_opts()
+        fl.assemble_momentum(fo)
+        fl.solve_momentum(mdev, mbcg)
+        mdev.cleanup()
+        fl.assemble_continuity(fo)
+        d = fl.download_continuity()
+        n = mesh.getCells().getSelfCount()
+        row, col = mesh.cc_row, mesh.cc_col
+        lines = []
+        for i in range(n):
+            lines.append("%d %d %f" % (i + 1, i + 1, d["diag"][i]))
+            for jp in range(row[i], row[i + 1]):
+                if col[jp] < n:
+                    lines.append("%d %d %f" % (i + 1, col[jp] + 1, d["offdiag"][jp]))
+        with open(file_base + ".mat", "w") as fh:
+            fh.write("%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (n, n, len(lines)))
+            fh.write("\n".join(lines) + "\n")
+        with open(file_base + ".rhs", "w") as fh:
+            fh.write("".join("%f\n" % (-v) for v in d["b"][:n]))
+        self._download(mesh, fl)
+
     def updateTime(self):  # F/FlowModel_impl.h:351-370
         f, o = self.fields, self._options
         for mesh in self.meshes:

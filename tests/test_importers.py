@@ -344,3 +344,37 @@ def test_parallel_cavity_ilu0_reproduces_the_golden_convergence_history(hostsim_
     assert ours[0, 1] == gold[0, 1] == 0.0
     assert dev.max() < 5e-6 and (dev.max(axis=1) < 5e-7).sum() >= 90
     assert all(t["momentum_norm"][2] == 0.0 for t in fm.timings)
+
+
+FCM_GOLDEN = "/root/reference/src/fvm/test/FLOW_CONTINUITY_MATRIX/GOLDEN/"
+
+
+@pytest.mark.skipif(not os.path.exists(FCM_GOLDEN + "matrix.mat"), reason="reference tree not mounted")
+def test_flow_continuity_matrix_golden(hostsim_lib, tmp_path):
+    """T/FLOW_CONTINUITY_MATRIX: dumpContinuityMatrix on cav32.cas after one momentum solve. The pressure-correction
+    MATRIX (Rhie-Chow coefficients from the momentum diagonal, reference-cell row) is pure assembly and is written
+    byte for byte like the golden matrix.mat; the right-hand side is the mass imbalance of velocities that went
+    through one AMG cycle stopped at rel 1e-1, so it agrees with matrix.rhs only to about 1 % of its scale."""
+    reader = importers.FluentCase(FVM002_CAS)
+    reader.read()
+    meshes = reader.getMeshList()
+    geom = M.GeomFields("geom")
+    M.MeshMetricsCalculatorA(geom, meshes, lib=hostsim_lib).init()
+    ff = M.FlowFields("flow")
+    fm = M.FlowModelA(geom, ff, meshes, lib=hostsim_lib)
+    bc3 = fm.getBCMap()[3]
+    bc3.bcType = "NoSlipWall"
+    bc3.setVar("specifiedXVelocity", 1)
+    for vc in fm.getVCMap().values():
+        vc.setVar("density", 1.0); vc.setVar("viscosity", 0.1)
+    fo = fm.getOptions()
+    for nm in ("momentumLinearSolver", "pressureLinearSolver"):
+        s = M.AMG()
+        s.relativeTolerance, s.nMaxIterations, s.maxCoarseLevels, s.verbosity = 1e-1, 20, 30, 0
+        setattr(fo, nm, s)
+    fm.init()
+    base = str(tmp_path / "matrix")
+    fm.dumpContinuityMatrix(base)
+    assert open(base + ".mat", "rb").read() == open(FCM_GOLDEN + "matrix.mat", "rb").read()
+    ours, gold = np.loadtxt(base + ".rhs"), np.loadtxt(FCM_GOLDEN + "matrix.rhs")
+    assert ours.shape == gold.shape and np.abs(ours - gold).max() <= 0.02 * np.abs(gold).max()
