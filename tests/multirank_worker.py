@@ -97,6 +97,53 @@ def main():
         lib.dll.fvmgpu_hostsim_set_comm(*_keep)
         lib.comm_init(world, rank)
 
+    if solver_kind == "thermgold":
+        # T/PARALLEL_TESTS CAVITY_*_JACOBISOLVER: the golden (iteration count + last residual of a Jacobi-smoothed
+        # solve to rel 1e-5) is the same file for every rank count the reference registered (1 ... 47)
+        import contextlib
+        import io
+        from fvm_b200 import importers, models as M
+        cas, golden = {"cav32": ("cav32.cas", "QUAD_1024"), "tri894": ("tri_894.cas", "TRI_894"),
+                       "tetra8k": ("cav_tetra.cas", "TETRA_8K")}[case]
+        fc = importers.FluentCase("/root/reference/src/fvm/test/" + cas)
+        fc.read()
+        raw0 = fc.getMeshList()[0].raw
+        geo0 = G.metrics(raw0)
+        part = (P.assign_slabs(raw0.n_cells, world) if case == "cav32"
+                else P.assign_rcb(geo0["cell_centroid"][:raw0.n_cells], world))
+        loc = P.partition_mesh(raw0, geo0, part, rank)
+        mesh = M.Mesh(loc)
+        geomf = M.GeomFields("geom")
+        M.MeshMetricsCalculatorA(geomf, [mesh], lib=lib).init()
+        tf = M.ThermalFields("therm")
+        tm = M.ThermalModelA(geomf, tf, [mesh], lib=lib)
+        bcm = tm.getBCMap()
+        if 3 in bcm:
+            bcm[3].bcType = "SpecifiedTemperature"; bcm[3].setVar("specifiedTemperature", 400)
+        for gid in (4, 5, 6):
+            if gid in bcm:
+                bcm[gid].bcType = "SpecifiedTemperature"; bcm[gid].setVar("specifiedTemperature", 0)
+        for vc in tm.getVCMap().values():
+            vc.setVar("thermalConductivity", 1.0)
+        sv = M.AMG()
+        sv.smootherType, sv.maxCoarseLevels = 1, 0
+        sv.relativeTolerance, sv.nMaxIterations, sv.verbosity = 1e-5, 20000, 0
+        tm.getOptions().linearSolver = sv
+        tm.init()
+        with contextlib.redirect_stdout(io.StringIO()):
+            tm.advance(1)
+        gold = open("/root/reference/src/fvm/test/PARALLEL_TESTS/SOLVER_JACOBI/%s/proc2/GOLDEN/convergence.dat" % golden)
+        last = gold.read().splitlines()[1]
+        out = dict(rank=rank, world=world, n_self=int(loc.n_cells), peers=[int(p) for p in loc.halo["peers"]],
+                   err_diag=0.0, err_b=0.0, rel_l2=0.0, ghost_err=0.0, r0=1.0, r=0.0, iters=int(sv.lastIterations),
+                   levels=[], collectives=lib.comm_collectives(), golden_last=last,
+                   ours_last="%d: [therm.temperature : %g]" % (sv.lastIterations, sv.lastResidual))
+        with open(os.path.join(os.environ["FVM_RESULT_DIR"], "rank%d.json" % rank), "w") as fh:
+            json.dump(out, fh)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
     if solver_kind == "flowgold":
         # T/PARALLEL_CAVITY_JACOBI: cav32.cas, lid u = 1, both systems relaxed by Jacobi sweeps on the fine level only
         # (AMG with smootherType = JACOBI, maxCoarseLevels = 0, rel 1e-1 / 200). Jacobi with a ghost refresh after every

@@ -378,3 +378,52 @@ def test_flow_continuity_matrix_golden(hostsim_lib, tmp_path):
     assert open(base + ".mat", "rb").read() == open(FCM_GOLDEN + "matrix.mat", "rb").read()
     ours, gold = np.loadtxt(base + ".rhs"), np.loadtxt(FCM_GOLDEN + "matrix.rhs")
     assert ours.shape == gold.shape and np.abs(ours - gold).max() <= 0.02 * np.abs(gold).max()
+
+
+JAC_DIR = "/root/reference/src/fvm/test/PARALLEL_TESTS/SOLVER_JACOBI/"
+
+
+def _thermal_jacobi(lib, mesh):
+    """T/PARALLEL_TESTS/testThermalParallelJacobi.py: T = 400 on zone 3, 0 on zones 4-6, k = 1, AMG with the Jacobi
+    smoother and no coarse levels, rel 1e-5."""
+    import contextlib
+    import io
+    geom = M.GeomFields("geom")
+    M.MeshMetricsCalculatorA(geom, [mesh], lib=lib).init()
+    tf = M.ThermalFields("therm")
+    tm = M.ThermalModelA(geom, tf, [mesh], lib=lib)
+    bc = tm.getBCMap()
+    if 3 in bc:
+        bc[3].bcType = "SpecifiedTemperature"; bc[3].setVar("specifiedTemperature", 400)
+    for gid in (4, 5, 6):
+        if gid in bc:
+            bc[gid].bcType = "SpecifiedTemperature"; bc[gid].setVar("specifiedTemperature", 0)
+    for vc in tm.getVCMap().values():
+        vc.setVar("thermalConductivity", 1.0)
+    s = M.AMG()
+    s.smootherType, s.maxCoarseLevels = 1, 0
+    s.relativeTolerance, s.nMaxIterations, s.verbosity = 1e-5, 20000, 0
+    tm.getOptions().linearSolver = s
+    tm.init()
+    with contextlib.redirect_stdout(io.StringIO()):
+        tm.advance(1)
+    return s
+
+
+@pytest.mark.parametrize("cas,golden", [("cav32.cas", "QUAD_1024"), ("tri_894.cas", "TRI_894"),
+                                        ("cav_hexa.cas", "HEXA_10K"), ("cav_tetra.cas", "TETRA_8K")])
+def test_thermal_jacobi_goldens_of_the_reference(hostsim_lib, cas, golden):
+    """The reference's registered CAVITY_*_JACOBISOLVER tests: quads, triangles, hexahedra and tetrahedra read from
+    the reference's own case files; the golden is the first and the last line of the solver's history. Iteration
+    count and final residual (as printed, 6 digits) are reproduced exactly: 863 / 0.629004, 930 / 0.723422,
+    302 / 0.302091, 460 / 0.351129."""
+    path = "/root/reference/src/fvm/test/" + cas
+    gpath = JAC_DIR + golden + "/proc1/GOLDEN/convergence.dat"
+    if not (os.path.exists(path) and os.path.exists(gpath)):
+        pytest.skip("reference tree not mounted")
+    fc = importers.FluentCase(path)
+    fc.read()
+    s = _thermal_jacobi(hostsim_lib, fc.getMeshList()[0])
+    first, last = open(gpath).read().splitlines()[:2]
+    assert last == "%d: [therm.temperature : %g]" % (s.lastIterations, s.lastResidual)
+    assert first.startswith("0: [therm.temperature : ")

@@ -123,6 +123,19 @@ def test_partitioned_cavity_reproduces_the_reference_parallel_golden(world):
         assert world == 1 or d["collectives"] > 0
 
 
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/fvm/test/PARALLEL_TESTS/SOLVER_JACOBI/QUAD_1024/proc2/GOLDEN/convergence.dat"),
+                    reason="reference tree not mounted")
+@pytest.mark.parametrize("world,case", [(2, "cav32"), (3, "tri894"), (2, "tetra8k")])
+def test_partitioned_thermal_jacobi_reproduces_the_reference_parallel_goldens(world, case):
+    """T/PARALLEL_TESTS CAVITY_{QUAD1024,TRI894,TETRA8K}_PROCSn_JACOBISOLVER: the reference registers the same golden
+    for every rank count (2 ... 47 ranks); ThermalModelA on 2 / 3 mesh parts of the reference's own case files (slab
+    and RCB partitions) stops at the same iteration with the same printed residual."""
+    res = run_world(world, case, "thermgold")
+    for d in res:
+        assert d["ours_last"] == d["golden_last"], (d["ours_last"], d["golden_last"])
+        assert d["collectives"] > 0
+
+
 def test_electric_model_on_partitioned_tets():
     """BASELINE configs[4] in miniature: ElectricModelA (Poisson + drift / transient charge transport) on
     an RCB-partitioned tet mesh, 2 ranks, against the single-partition run of the same model."""
