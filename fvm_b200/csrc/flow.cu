@@ -1012,9 +1012,11 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
     solver->precondKind = keep;
   };
   const fvmgpu_amg_opts userOpts = solver->opts;
-  const int limit = useBcgstab ? bcgMaxIter : userOpts.nMaxIterations - 1;
-  const double rel = useBcgstab ? bcgRel : userOpts.relativeTolerance;
-  const double abs = useBcgstab ? bcgAbs : userOpts.absoluteTolerance;
+  const bool jacobi = useBcgstab == 3;   // JacobiSolver (F/JacobiSolver.cpp:46-95) with the limits passed like BCGStab's
+  if (jacobi) useBcgstab = 0;
+  const int limit = useBcgstab ? bcgMaxIter : (jacobi ? bcgMaxIter - 1 : userOpts.nMaxIterations - 1);
+  const double rel = (useBcgstab || jacobi) ? bcgRel : userOpts.relativeTolerance;
+  const double abs = (useBcgstab || jacobi) ? bcgAbs : userOpts.absoluteTolerance;
   std::vector<double> hist[3];
   for (int k = 0; k < 3; k++) hist[k].assign(1, norms[k]);
   // ---- the shared convergence test: |rNorm|_2 / |rNorm0|_2 over the vector of component 1-norms
@@ -1023,7 +1025,14 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
   for (int k = 0; k < 3; k++) den += norms[k] * norms[k];
   auto converged = [&](int i) {
     double num = 0;
-    for (int k = 0; k < 3; k++) { const double r = hist[k][(size_t)std::min<int>(i, (int)hist[k].size() - 1)]; num += r * r; }
+    double ratios = 0;   // JacobiSolver divides component by component (safeDivide, F/JacobiSolver.cpp:73)
+    for (int k = 0; k < 3; k++) {
+      const double r = hist[k][(size_t)std::min<int>(i, (int)hist[k].size() - 1)];
+      num += r * r;
+      const double q = norms[k] != 0.0 ? r / norms[k] : r;
+      ratios += q * q;
+    }
+    if (jacobi) return num < abs * abs || ratios < rel * rel;
     return num < abs * abs || (den > 0 ? num / den : num) < rel * rel;
   };
   int N = 0;
@@ -1057,11 +1066,15 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
           hist[k] = solver->history;
         } else {            // stationary iteration: one more cycle from the stored delta
           select(k);
-          solver->opts.nMaxIterations = 2; solver->opts.relativeTolerance = 0.0; solver->opts.absoluteTolerance = 0.0;
           double r0 = 0, r = 0;
           int one = 0;
-          solver->solve(s, &r0, &r, &one);
-          solver->opts = userOpts;
+          if (jacobi) {
+            solver->jacobiSolve(s, 2, 0.0, 0.0, &r0, &r, &one);
+          } else {
+            solver->opts.nMaxIterations = 2; solver->opts.relativeTolerance = 0.0; solver->opts.absoluteTolerance = 0.0;
+            solver->solve(s, &r0, &r, &one);
+            solver->opts = userOpts;
+          }
           hist[k].push_back(r);
         }
         store(k);
@@ -1118,7 +1131,9 @@ void flowSolveContinuity(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, d
   System* s = F->pp.get();
   double r0 = 0, r = 0;
   int it = 0;
-  if (useBcgstab) {
+  if (useBcgstab == 3) {
+    solver->jacobiSolve(s, bcgMaxIter, bcgRel, bcgAbs, &r0, &r, &it);
+  } else if (useBcgstab) {
     const int keep = solver->precondKind;
     solver->precondKind = useBcgstab == 2 ? 1 : 0;
     solver->bcgstab(s, bcgMaxIter, bcgRel, bcgAbs, &r0, &r, &it);

@@ -745,6 +745,10 @@ def _solver_args(solver):
             raise CException("BCGStab: no preconditioner set")
         kind = 2 if isinstance(solver.preconditioner, ILU0Solver) else 1   # fvmgpu_flow_solve_*'s bcgstab argument
         return solver.preconditioner, (solver.nMaxIterations, solver.relativeTolerance, solver.absoluteTolerance, kind)
+    if isinstance(solver, JacobiSolver):
+        return solver._amg, (solver.nMaxIterations, solver.relativeTolerance, solver.absoluteTolerance, 3)
+    if not isinstance(solver, AMG):
+        raise CException("FlowModelA: %s is not supported as a flow solver" % type(solver).__name__)
     return solver, None
 
 

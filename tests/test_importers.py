@@ -427,3 +427,62 @@ def test_thermal_jacobi_goldens_of_the_reference(hostsim_lib, cas, golden):
     first, last = open(gpath).read().splitlines()[:2]
     assert last == "%d: [therm.temperature : %g]" % (s.lastIterations, s.lastResidual)
     assert first.startswith("0: [therm.temperature : ")
+
+
+def _cavity_flow(lib, make_solver):
+    """T/PARALLEL_CAVITY_*/testFlowParallel.py on cav32.cas (lid u = 1, rho = 1, mu = 0.1)."""
+    reader = importers.FluentCase(FVM002_CAS)
+    reader.read()
+    meshes = reader.getMeshList()
+    geom = M.GeomFields("geom")
+    M.MeshMetricsCalculatorA(geom, meshes, lib=lib).init()
+    ff = M.FlowFields("flow")
+    fm = M.FlowModelA(geom, ff, meshes, lib=lib)
+    bc3 = fm.getBCMap()[3]
+    bc3.bcType = "NoSlipWall"
+    bc3.setVar("specifiedXVelocity", 1)
+    for vc in fm.getVCMap().values():
+        vc.setVar("density", 1.0); vc.setVar("viscosity", 0.1)
+    fo = fm.getOptions()
+    fo.momentumLinearSolver, fo.pressureLinearSolver = make_solver(), make_solver()
+    fo.momentumTolerance = fo.continuityTolerance = 1e-5
+    fo.printNormalizedResiduals = False
+    fm.init()
+    return fm
+
+
+def _golden_history(path):
+    import re
+    return np.array([[float(x) for x in re.findall(r"[-+]?\d+\.?\d*(?:e[-+]?\d+)?", l.split(":", 1)[1])]
+                     for l in open(path).read().splitlines()])[:, [0, 1, 3]]
+
+
+@pytest.mark.parametrize("variant", ["JACOBI", "JACOBI_1"])
+def test_parallel_cavity_jacobi_goldens(hostsim_lib, variant):
+    """T/PARALLEL_CAVITY_JACOBI (AMG with the Jacobi smoother and no coarse levels) and T/PARALLEL_CAVITY_JACOBI_1 (the
+    JacobiSolver class, whose convergence test divides component by component): rel 1e-1 / 200 sweeps for both
+    systems. Deterministic arithmetic throughout, so the golden outer-residual histories are reproduced to their
+    printed precision."""
+    import contextlib
+    import io
+    gpath = "/root/reference/src/fvm/test/PARALLEL_CAVITY_%s/PROC1/GOLDEN/convergence.dat" % variant
+    if not os.path.exists(gpath):
+        pytest.skip("reference tree not mounted")
+
+    def make():
+        if variant == "JACOBI":
+            s = M.AMG()
+            s.smootherType, s.maxCoarseLevels = 1, 0
+        else:
+            s = M.JacobiSolver()
+        s.relativeTolerance, s.nMaxIterations, s.verbosity = 1e-1, 200, 0
+        return s
+
+    gold = _golden_history(gpath)
+    fm = _cavity_flow(hostsim_lib, make)
+    with contextlib.redirect_stdout(io.StringIO()):
+        fm.advance(len(gold))
+    ours = np.array([[t["momentum_norm"][0], t["momentum_norm"][1], t["continuity_norm"]] for t in fm.timings])
+    dev = np.abs(ours - gold) / np.maximum(np.abs(gold), 1e-300)
+    dev[0, 1] = 0.0
+    assert ours[0, 1] == 0.0 and dev.max() < 1e-6
