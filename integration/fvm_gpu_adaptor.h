@@ -6,6 +6,7 @@
 //
 //   class GpuAMG     : public LinearSolver   (F/LinearSolver.h:11-31)  -- drop-in for AMG
 //   class GpuBCGStab : public LinearSolver                              -- drop-in for BCGStab
+//   GpuCG / GpuJacobiSolver / GpuILU0Solver / GpuBCGStabILU0            -- drop-ins for CG, JacobiSolver, ILU0Solver
 //   class GpuThermalLinearizer                                          -- replaces the body of
 //        ThermalModel<T>::Impl::linearize (F/ThermalModel_impl.h:236-398: GradientModel::compute,
 //        Linearizer::linearize over the discretization list and the GenericBCS loop) plus
@@ -182,6 +183,49 @@ class GpuBCGStab : public LinearSolver {
  private:
   int _totalIterations;
 };
+
+// CG (F/CG.cpp:24-140), JacobiSolver (F/JacobiSolver.cpp:46-95), ILU0Solver (F/ILU0Solver.cpp:46-93) and BCGStab with
+// the ILU0 preconditioner (T/PARALLEL_CAVITY_ILU0): the same pattern, other entry points.
+class GpuKrylovLike : public LinearSolver {
+ public:
+  enum Kind { CG_AMG, JACOBI, ILU0, BCGSTAB_ILU0 };
+  explicit GpuKrylovLike(Kind k) : preconditioner(0), _kind(k), _totalIterations(0) {}
+  GpuAMG* preconditioner;   // CG_AMG: the AMG whose cycle preconditions; the others: any GpuAMG (it owns the device system)
+  virtual MFRPtr solve(LinearSystem& ls) {
+    if (!preconditioner) throw CException("GpuKrylovLike: set `preconditioner` to a GpuAMG");
+    ScalarSystemView v = preconditioner->upload(ls);
+    double r0 = 0, r = 0;
+    int it = 0;
+    fvmgpu_solver_t h = preconditioner->handle();
+    fvmgpu_system_t sys = preconditioner->system();
+    switch (_kind) {
+      case CG_AMG: check(fvmgpu_cg_solve(h, sys, nMaxIterations, relativeTolerance, absoluteTolerance, &r0, &r, &it)); break;
+      case JACOBI: check(fvmgpu_jacobi_solve(h, sys, nMaxIterations, relativeTolerance, absoluteTolerance, &r0, &r, &it)); break;
+      case ILU0: check(fvmgpu_ilu0_solve(h, sys, nMaxIterations, relativeTolerance, absoluteTolerance, &r0, &r, &it, 0)); break;
+      case BCGSTAB_ILU0:
+        check(fvmgpu_bcgstab_ilu0_solve(h, sys, nMaxIterations, relativeTolerance, absoluteTolerance, &r0, &r, &it));
+        break;
+    }
+    _totalIterations += it;
+    preconditioner->download(ls, v);
+    if (verbosity > 0) {
+      std::cout << "0: [" << v.index.first->getName() << " : " << r0 << "]" << std::endl;
+      std::cout << it << ": [" << v.index.first->getName() << " : " << r << "]" << std::endl;
+    }
+    return GpuAMG::norm(v, r0);
+  }
+  virtual void smooth(LinearSystem&) { throw CException("GpuKrylovLike: not usable as a preconditioner"); }
+  virtual void cleanup() { if (preconditioner) preconditioner->cleanup(); }
+  int getTotalIterations() const { return _totalIterations; }
+
+ private:
+  Kind _kind;
+  int _totalIterations;
+};
+struct GpuCG : GpuKrylovLike { GpuCG() : GpuKrylovLike(CG_AMG) {} };
+struct GpuJacobiSolver : GpuKrylovLike { GpuJacobiSolver() : GpuKrylovLike(JACOBI) {} };
+struct GpuILU0Solver : GpuKrylovLike { GpuILU0Solver() : GpuKrylovLike(ILU0) {} };
+struct GpuBCGStabILU0 : GpuKrylovLike { GpuBCGStabILU0() : GpuKrylovLike(BCGSTAB_ILU0) {} };
 
 // ------------------------------------------------------------------------------------ assembly
 // Device mirror of one reference Mesh + GeomFields, created once (geometry outlives the models).
