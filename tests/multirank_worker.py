@@ -64,6 +64,15 @@ def _allgather(send, recv, nbytes):
 _keep = (EXCH(_exchange), ALLR(_allreduce), ALLG(_allgather))
 
 
+def rejoin(lib, world, rank):
+    """Join the library's communicator again after a single-partition run (hostsim: callbacks; GPU: a fresh
+    NCCL communicator bootstrapped through torch.distributed)."""
+    if os.environ.get("FVM_WORKER_GPU") == "1":
+        X.init_comm_from_torch(lib)
+    else:
+        lib.comm_init(world, rank)
+
+
 def make_case(name):
     if name == "hex_slabs":
         raw = G.hex_mesh(10, 9, 12, jitter=0.15, seed=3)
@@ -263,7 +272,7 @@ def main():
         # single-partition run of the same code BEFORE this process joins the communicator
         lib.comm_destroy()
         pot_ref, chg_ref = run(raw, lib)
-        lib.comm_init(world, rank)
+        rejoin(lib, world, rank)
         pot, chg = run(loc, lib)
         own = loc.cell_global[:loc.n_cells]
         num = float(((pot[:loc.n_cells] - pot_ref[own]) ** 2).sum()) + float(((chg[:loc.n_cells, 2] / 1e12 - chg_ref[own, 2] / 1e12) ** 2).sum())
@@ -314,7 +323,7 @@ def main():
 
         lib.comm_destroy()
         v_ref, p_ref, _ = run(raw, lib)
-        lib.comm_init(world, rank)
+        rejoin(lib, world, rank)
         v, pr, mf = run(loc, lib)
         own = loc.cell_global[:loc.n_cells]
         num = float(((v[:loc.n_cells] - v_ref[own]) ** 2).sum()) + float(((pr[:loc.n_cells] - p_ref[own]) ** 2).sum())

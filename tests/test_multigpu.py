@@ -18,7 +18,8 @@ def _n_gpus():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case,solver,merge", [("hex_slabs", "amg", 64), ("tet_rcb", "bcgstab", 200),
-                                                ("tet_rcb", "model", 200)])
+                                                ("tet_rcb", "model", 200), ("hex_slabs", "flow", 200),
+                                                ("tet_rcb", "electric", 200)])
 def test_two_gpus_match_single_partition_oracle(case, solver, merge):
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
