@@ -612,6 +612,12 @@ int fvmref_flow_set_option(void* h, const char* name, double value) {
   return 0;
   CATCH(-1)
 }
+int fvmref_flow_update_time(void* h) {   // FlowModel::updateTime, F/FlowModel_impl.h:351-370
+  TRY RefFlow* t = (RefFlow*)h;
+  t->model->updateTime();
+  return 0;
+  CATCH(-1)
+}
 int fvmref_flow_set_solver(void* h, int which, const SolverCfg* cfg) {
   TRY RefFlow* t = (RefFlow*)h;
   if (which == 0) { t->momSolver = make_solver(*cfg); t->model->getOptions().momentumLinearSolver = t->momSolver.top; }

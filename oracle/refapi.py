@@ -97,6 +97,7 @@ def lib():
         L.fvmref_flow_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.fvmref_flow_set_solver.argtypes = [C.c_void_p, C.c_int, C.POINTER(SolverCfg)]
         L.fvmref_flow_init.argtypes = [C.c_void_p]
+        L.fvmref_flow_update_time.argtypes = [C.c_void_p]
         L.fvmref_flow_field.restype = C.POINTER(C.c_double)
         L.fvmref_flow_field.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
         L.fvmref_flow_momentum_system.argtypes = [C.c_void_p, _dp, _dp, _dp]
@@ -329,6 +330,9 @@ class RefFlow:
         if not p:
             raise RuntimeError("reference: " + lib().fvmref_last_error().decode())
         return np.ctypeslib.as_array(p, shape=(n.value,))
+
+    def update_time(self):
+        _check(lib().fvmref_flow_update_time(self.h))
 
     def momentum_system(self):
         m = self.mesh
