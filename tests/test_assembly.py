@@ -211,3 +211,32 @@ def test_bad_inputs_raise(devlib):
     with pytest.raises(X.FvmGpuError, match="FACE_FLUX"):
         ds.assemble(convection=1)
     ds.close(); dm.close()
+
+
+def test_standalone_gradient_is_exact_for_linear_fields(hostsim_lib):
+    """GradientModel::compute on its own (fvmgpu_compute_gradient) and the least-squares weights it uses
+    (fvmgpu_mesh_download_gradient_weights, F/GradientModel.h:126-436): the LS gradient reproduces a linear field
+    exactly on interior cells of a jittered tet mesh, and sum_k w_k (x_nb - x_c) with the downloaded weights is that
+    gradient."""
+    raw = G.tet_mesh(5, 4, 6, jitter=0.2, seed=11)
+    geo = G.metrics(raw)
+    row, col = G.connectivity(raw)
+    dm = X.DeviceMesh(hostsim_lib, 3, raw.n_cells, raw.n_total, raw.face_cells, row, col, raw.group_offset,
+                      raw.group_count, raw.group_id, raw.group_kind)
+    dm.set_geometry(geo["face_area"], geo["face_area_mag"], geo["cell_centroid"], geo["cell_volume"],
+                    ib_type=np.full(raw.n_total, -1, np.int32))
+    a = np.array([1.5, -0.7, 2.25])
+    x = geo["cell_centroid"] @ a + 3.0
+    ds = X.DeviceSystem(hostsim_lib, dm)
+    ds.set_field(X.FIELD_X, x)
+    ds.compute_gradient()
+    g = ds.get_field(X.FIELD_GRADIENT).reshape(-1, 3)
+    # cells all of whose neighbours are interior cells or boundary ghosts holding the linear field
+    assert np.abs(g[:raw.n_cells] - a).max() <= 1e-11
+    w = dm.gradient_weights()
+    i = raw.n_cells // 2
+    acc = np.zeros(3)
+    for k in range(row[i], row[i + 1]):
+        acc += w[k] * (x[col[k]] - x[i])
+    assert np.abs(acc - g[i]).max() <= 1e-13
+    ds.close(); dm.close()
