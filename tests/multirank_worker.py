@@ -400,6 +400,13 @@ def main():
         if gid in present:
             kind, v = bcs.get(gid, ("neumann", 0.0))
             ds.set_bc(gid, kinds[kind], [v])
+    # MultiField::sync on its own (fvmgpu_system_halo_exchange): every interface ghost receives its owner's value
+    probe = np.where(np.arange(loc.n_total) < loc.n_cells, loc.cell_global.astype(float) + 0.25, -1.0)
+    ds.set_field(X.FIELD_DIFFUSIVITY, probe)
+    ds.halo_exchange(X.FIELD_DIFFUSIVITY)
+    got = ds.get_field(X.FIELD_DIFFUSIVITY)
+    sync_err = float(np.abs(got[h["gather_idx"]] - (loc.cell_global[h["gather_idx"]] + 0.25)).max()) if len(h["gather_idx"]) else 0.0
+    ds.set_field(X.FIELD_DIFFUSIVITY, k_glob[loc.cell_global])
     ds.assemble()
     a = ds.download()
     own = loc.cell_global[:loc.n_cells]
@@ -432,7 +439,7 @@ def main():
     dist.all_reduce(t)
     out = dict(rank=rank, world=world, n_self=int(loc.n_cells), peers=[int(p) for p in h["peers"]],
                err_diag=err_diag, err_b=err_b, rel_l2=float(np.sqrt(float(t[0]) / float(t[1]))), ghost_err=ghost_err,
-               r0=r0, r=r, iters=it, levels=[int(s) for s in levels["sizes"]],
+               r0=r0, r=r, iters=it, levels=[int(s) for s in levels["sizes"]], sync_err=sync_err,
                colours=[int(c) for c in levels["colours"]],
                collectives=lib.comm_collectives())
     with open(os.path.join(os.environ["FVM_RESULT_DIR"], "rank%d.json" % rank), "w") as fh:

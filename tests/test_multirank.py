@@ -46,6 +46,7 @@ def check(res):
         assert d["err_diag"] <= 1e-12 and d["err_b"] <= 1e-12, d
         assert d["rel_l2"] <= 1e-8, d
         assert d["ghost_err"] <= 1e-6, d
+        assert d.get("sync_err", 0.0) == 0.0, d
         assert d["r"] / d["r0"] < 1e-13, d
         assert d["collectives"] > 0
 
