@@ -476,3 +476,58 @@ def _alist(items):
             rest = it[1:]
             d[it[0]] = rest[0] if len(rest) == 1 else rest
     return d
+
+
+class MMReader:
+    """MatrixMarket matrix + right-hand-side pair -> one scalar linear system (I/MMReader.cpp:24-184; the input of the
+    reference's testLinearSolver, T/TESTS Fvm001). Off-diagonal entries keep their file order inside each row (that is
+    the order every row sum runs in), the diagonal is stored apart, symmetric files are expanded, and b = -rhs
+    (the library's sign convention r = b + A x). `getLS(lib)` returns a `capi.DeviceSystem` ready for any solver."""
+
+    def __init__(self, matrixFileName, rhsFileName):
+        self.matrixFileName, self.rhsFileName = matrixFileName, rhsFileName
+
+    def read(self):
+        with open(self.matrixFileName) as fh:
+            tokens = fh.read().split()
+        if tokens[0] == "%%" and tokens[1] == "MatrixMarket":
+            tokens = tokens[2:]
+        elif tokens[0] == "%%MatrixMarket":
+            tokens = tokens[1:]
+        else:
+            raise CException("not a MatrixMarket file")
+        mtype, coord, ftype, symm = tokens[:4]
+        if mtype != "matrix":
+            raise CException("not a MatrixMarket file")
+        if coord != "coordinate":
+            raise CException("not a sparse matrix")
+        if ftype != "real":
+            raise CException("not a real matrix")
+        if symm not in ("symmetric", "general"):
+            raise CException("not symmetric or general matrix")
+        n, ncol, nnz = (int(t) for t in tokens[4:7])
+        if n != ncol:
+            raise CException("not a square matrix")
+        body = tokens[7:7 + 3 * nnz]
+        rows = [[] for _ in range(n)]
+        diag = np.zeros(n)
+        for e in range(nnz):
+            i, j, c = int(body[3 * e]) - 1, int(body[3 * e + 1]) - 1, float(body[3 * e + 2])
+            if i != j:
+                rows[i].append((j, c))
+                if symm == "symmetric":
+                    rows[j].append((i, c))
+            else:
+                diag[i] = c
+        row = np.zeros(n + 1, np.int32)
+        row[1:] = np.cumsum([len(r) for r in rows])
+        col = np.array([j for r in rows for j, _ in r], np.int32)
+        off = np.array([c for r in rows for _, c in r], np.float64)
+        with open(self.rhsFileName) as fh:
+            b = -np.array(fh.read().split()[:n], dtype=np.float64)
+        return dict(n=n, row=row, col=col, diag=diag, off=off, b=b)
+
+    def getLS(self, lib):
+        from . import capi
+        d = self.read()
+        return capi.DeviceSystem(lib, raw=(d["n"], 0, d["row"], d["col"], d["diag"], d["off"], d["b"]))

@@ -486,3 +486,34 @@ def test_parallel_cavity_jacobi_goldens(hostsim_lib, variant):
     dev = np.abs(ours - gold) / np.maximum(np.abs(gold), 1e-300)
     dev[0, 1] = 0.0
     assert ours[0, 1] == 0.0 and dev.max() < 1e-6
+
+
+def test_matrix_market_reader_reproduces_the_reference_system(hostsim_lib, tmp_path):
+    """MMReader (I/MMReader.cpp) on the inputs of the reference's testLinearSolver (T/TESTS Fvm001): the same CSR
+    pattern in the same entry order, diagonal apart, b = -rhs -- compared with the system the reference itself built
+    from those files (fixture mm226.npz); a symmetric file written by the test is expanded to both triangles."""
+    from fvm_b200 import capi as X
+    mm, rhs = "/root/reference/src/fvm/test/MatrixMarket226.dat", "/root/reference/src/fvm/test/rhs226.dat"
+    if os.path.exists(mm):
+        g = load_golden("mm226.npz")
+        d = importers.MMReader(mm, rhs).read()
+        assert d["n"] == int(g["n"])
+        for k in ("row", "col", "diag", "off", "b"):
+            assert np.array_equal(d[k], g[k]), k
+        ds = importers.MMReader(mm, rhs).getLS(hostsim_lib)
+        amg = X.DeviceAMG(hostsim_lib)
+        r0, r, it = amg.solve(ds)
+        assert abs(r0 - float(g["ref_rnorm0"])) <= 1e-9 * r0 and r / r0 < 1e-8
+        amg.close(); ds.close()
+    p = tmp_path / "s.mtx"
+    p.write_text("%%MatrixMarket matrix coordinate real symmetric\n3 3 5\n1 1 4.0\n2 1 -1.0\n2 2 4.0\n3 2 -2.0\n3 3 5.0\n")
+    q = tmp_path / "s.rhs"
+    q.write_text("1\n2\n3\n")
+    d = importers.MMReader(str(p), str(q)).read()
+    assert d["row"].tolist() == [0, 1, 3, 4] and d["col"].tolist() == [1, 0, 2, 1]
+    assert d["off"].tolist() == [-1.0, -1.0, -2.0, -2.0] and d["diag"].tolist() == [4.0, 4.0, 5.0]
+    assert d["b"].tolist() == [-1.0, -2.0, -3.0]
+    bad = tmp_path / "bad.mtx"
+    bad.write_text("%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n")
+    with pytest.raises(M.CException):
+        importers.MMReader(str(bad), str(q)).read()
