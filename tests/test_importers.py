@@ -537,21 +537,28 @@ def test_fvm002_golden_is_reproduced_byte_for_byte_in_reference_order(hostsim_li
 
 
 @pytest.mark.skipif(not os.path.exists(PCAV_GOLDEN), reason="reference tree not mounted")
-def test_parallel_cavity_amg_golden_in_reference_order(hostsim_lib, reference_order):
-    """T/PARALLEL_CAVITY_AMG/proc1: with the reference's agglomeration and sweep order the AMG-based history is
-    reproduced as well -- all 100 SIMPLE iterations to the golden's printed precision."""
+@pytest.mark.parametrize("variant", ["AMG", "BCGStab"])
+def test_parallel_cavity_amg_golden_in_reference_order(hostsim_lib, reference_order, variant):
+    """T/PARALLEL_CAVITY_AMG/proc1 and T/PARALLEL_CAVITY_BCGStab/proc1 (BCGStab preconditioned by an AMG cycle, the
+    component-coupled recurrence): with the reference's agglomeration and sweep order the AMG-based histories are
+    reproduced as well -- all 100 SIMPLE iterations to the goldens' printed precision."""
     import contextlib
     import io
 
     def make():
         s = M.AMG()
         s.relativeTolerance, s.nMaxIterations, s.maxCoarseLevels, s.verbosity = 1e-1, 20, 30, 0
-        return s
+        if variant == "AMG":
+            return s
+        k = M.BCGStab()
+        k.preconditioner = s
+        k.relativeTolerance, k.nMaxIterations, k.verbosity = 1e-1, 20, 0
+        return k
 
     fm = _cavity_flow(hostsim_lib, make)
     with contextlib.redirect_stdout(io.StringIO()):
         fm.advance(100)
-    gold = _golden_history(PCAV_GOLDEN)
+    gold = _golden_history(PCAV_GOLDEN.replace("PARALLEL_CAVITY_AMG", "PARALLEL_CAVITY_" + variant))
     ours = np.array([[t["momentum_norm"][0], t["momentum_norm"][1], t["continuity_norm"]] for t in fm.timings])
     dev = np.abs(ours - gold) / np.maximum(np.abs(gold), 1e-300)
     dev[0, 1] = 0.0
