@@ -1046,12 +1046,15 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
     copyD2H(&nd, F->scal.p + 5, sizeof(double));
     coupledKrylov = nd == 0.0;
   }
+  if (useBcgstab == 4 && !coupledKrylov && den > 0 && !(den < abs * abs))
+    fail("flow: CG on the momentum system needs one diagonal for the three components (no symmetry planes)");
   if (coupledKrylov) {
     select(0);
     const int keep = solver->precondKind;
     solver->precondKind = useBcgstab == 2 ? 1 : 0;
     double r0v[3], rv[3];
-    solver->bcgstabMulti(s, 3, F->mB.p, F->mDelta.p, bcgMaxIter, bcgRel, bcgAbs, r0v, rv, &N);
+    if (useBcgstab == 4) solver->cgMulti(s, 3, F->mB.p, F->mDelta.p, bcgMaxIter, bcgRel, bcgAbs, r0v, rv, &N);
+    else solver->bcgstabMulti(s, 3, F->mB.p, F->mDelta.p, bcgMaxIter, bcgRel, bcgAbs, r0v, rv, &N);
     solver->precondKind = keep;
   } else if (den > 0 && !(den < abs * abs)) {
     while (N < limit) {
@@ -1133,6 +1136,8 @@ void flowSolveContinuity(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, d
   int it = 0;
   if (useBcgstab == 3) {
     solver->jacobiSolve(s, bcgMaxIter, bcgRel, bcgAbs, &r0, &r, &it);
+  } else if (useBcgstab == 4) {
+    solver->cg(s, bcgMaxIter, bcgRel, bcgAbs, &r0, &r, &it);
   } else if (useBcgstab) {
     const int keep = solver->precondKind;
     solver->precondKind = useBcgstab == 2 ? 1 : 0;

@@ -2259,6 +2259,7 @@ struct PermScatterGhostAoS {  // ghost slots keep their cell index: dst[nc*(n+g)
   const double* src; int nc, k, n; double* dst;
   FVM_DEV void operator()(long long g) const { dst[(size_t)nc * (n + g) + k] = src[g]; }
 };
+struct SumScalarsKernel { const double* a; int n; double* out; FVM_DEV void operator()(long long) const { double s = 0; for (int k = 0; k < n; k++) s += a[k]; out[0] = s; } };
 struct AbsRowsStrided {  // 1-norms of up to 3 component vectors stored one after the other
   const double* a; long long stride; int nc;
   FVM_DEV void operator()(long long i, double* o) const {
@@ -2406,6 +2407,84 @@ void Amg::cg(System* sys, int nMaxIterations, double relTol, double absTol, doub
   }
   if (rnorm0Out) *rnorm0Out = rNorm0;
   if (rnormOut) *rnormOut = rNorm;
+  if (itersOut) *itersOut = iters;
+}
+
+// CG on a Vector<T,NC> system with shared scalars (rho and p.q summed over the components, F/CG.cpp:72-99), the
+// conjugate-gradient counterpart of bcgstabMulti
+void Amg::cgMulti(System* sys, int nc, const double* b3, double* delta3, int nMaxIterations, double relTol,
+                  double absTol, double* rnorm0Out, double* rnormOut, int* itersOut) {
+  requireReady();
+  if (nc < 1 || nc > 3) fail("cgMulti: 1 to 3 components");
+  ensureSetup(sys);
+  history.clear();
+  Level& L0 = *levels[0];
+  const int n = L0.n;
+  const size_t ng = (size_t)L0.nGhost, ns = (size_t)n + ng, N = (size_t)nc * n;
+  DBuf<double> x(nc * ns), z(nc * ns), p(nc * ns), bOrig(N), r(N), q(N);
+  x.zero(); z.zero(); p.zero();
+  for (int k = 0; k < nc; k++) {
+    parallelFor(n, PermGatherAoS{perm0.p, b3, nc, k, bOrig.p + (size_t)k * n});
+    parallelFor(n, PermGatherAoS{perm0.p, delta3, nc, k, x.p + k * ns});
+    if (ng) exchange(L0, x.p + k * ns);
+  }
+  auto allreduce = [&](double* ptr, int cnt) { if (multi) commAllreduceSum(ptr, cnt); };
+  auto norms = [&](double* out3) {
+    reduceRows<3>(n, AbsRowsStrided{r.p, n, nc}, scalars.p + 8);
+    allreduce(scalars.p + 8, 3);
+    copyD2H(out3, scalars.p + 8, 3 * sizeof(double));
+  };
+  // dot products over all components of vectors stored with different strides
+  auto dotAll = [&](const double* a, size_t sa, const double* b, size_t sb, double* out) {
+    for (int k = 0; k < nc; k++) reduceRows<1>(n, Dot1Rows{a + k * sa, b + k * sb}, scalars.p + 12 + k);
+    parallelFor(1, SumScalarsKernel{scalars.p + 12, nc, out});
+    allreduce(out, 1);
+  };
+  for (int k = 0; k < nc; k++)
+    parallelFor(n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, bOrig.p + (size_t)k * n, x.p + k * ns,
+                                r.p + (size_t)k * n});
+  double r0[3], rn[3];
+  norms(r0);
+  for (int k = 0; k < 3; k++) rn[k] = r0[k];
+  auto mag2 = [&](const double* v) { double m = 0; for (int k = 0; k < nc; k++) m += v[k] * v[k]; return m; };
+  const double den = mag2(r0);
+  history.push_back(std::sqrt(den));
+  double* S = scalars.p;   // S[0]=rho S[1]=rhoPrev S[2]=p.q
+  int iters = 0;
+  bool haveP = false;
+  for (int i = 0; i < nMaxIterations; i++) {
+    iters++;
+    for (int k = 0; k < nc; k++) precondition(r.p + (size_t)k * n, z.p + k * ns);
+    copyD2D(S + 1, S + 0, sizeof(double));
+    dotAll(r.p, (size_t)n, z.p, ns, S + 0);
+    for (int k = 0; k < nc; k++) {
+      if (!haveP) copyD2D(p.p + k * ns, z.p + k * ns, (size_t)n * sizeof(double));
+      else parallelFor(n, ScaleAddRows{S + 0, S + 1, z.p + k * ns, p.p + k * ns});
+      if (ng) exchange(L0, p.p + k * ns);
+      MultiplyRows m{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, p.p + k * ns, q.p + (size_t)k * n};
+      parallelFor(n, m);
+    }
+    haveP = true;
+    dotAll(q.p, (size_t)n, p.p, ns, S + 2);
+    for (int k = 0; k < nc; k++) parallelFor(n, MsaxpyScalarPtr{S + 0, S + 2, p.p + k * ns, x.p + k * ns});
+    parallelFor((long long)N, MsaxpyScalarPtr{S + 0, S + 2, q.p, r.p});
+    norms(rn);
+    const double num = mag2(rn);
+    history.push_back(std::sqrt(num));
+    if (num < absTol * absTol || (den > 0 ? num / den : num) < relTol * relTol) break;
+  }
+  totalIterations += iters;
+  for (int k = 0; k < nc; k++) {
+    parallelFor(n, PermScatterAoS{perm0.p, x.p + k * ns, nc, k, delta3});
+    if (ng) {
+      exchange(L0, x.p + k * ns);
+      parallelFor((long long)ng, PermScatterGhostAoS{x.p + k * ns + n, nc, k, n, delta3});
+    }
+  }
+  for (int k = 0; k < nc; k++) {
+    if (rnorm0Out) rnorm0Out[k] = r0[k];
+    if (rnormOut) rnormOut[k] = rn[k];
+  }
   if (itersOut) *itersOut = iters;
 }
 

@@ -102,6 +102,8 @@ struct Amg {
   void cg(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0, double* rnorm, int* iters);
   void bcgstabMulti(System* sys, int nc, const double* b3, double* delta3, int nMaxIterations, double relTol,
                     double absTol, double* rnorm0, double* rnorm, int* iters);
+  void cgMulti(System* sys, int nc, const double* b3, double* delta3, int nMaxIterations, double relTol, double absTol,
+               double* rnorm0, double* rnorm, int* iters);
   void jacobiSolve(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0, double* rnorm,
                    int* iters);
 

@@ -747,6 +747,10 @@ def _solver_args(solver):
         return solver.preconditioner, (solver.nMaxIterations, solver.relativeTolerance, solver.absoluteTolerance, kind)
     if isinstance(solver, JacobiSolver):
         return solver._amg, (solver.nMaxIterations, solver.relativeTolerance, solver.absoluteTolerance, 3)
+    if isinstance(solver, CG):
+        if solver.preconditioner is None:
+            raise CException("CG: no preconditioner set")
+        return solver.preconditioner, (solver.nMaxIterations, solver.relativeTolerance, solver.absoluteTolerance, 4)
     if not isinstance(solver, AMG):
         raise CException("FlowModelA: %s is not supported as a flow solver" % type(solver).__name__)
     return solver, None

@@ -316,7 +316,8 @@ int fvmgpu_flow_assemble_momentum(fvmgpu_flow_t flow, const fvmgpu_flow_opts* op
 int fvmgpu_flow_download_momentum(fvmgpu_flow_t flow, double* diag3, double* offdiag, double* b3);
 /* momentumLinearSolver.solve + postSolve + updateSolution + momAp (:744-768). bcgstab != 0:
  * BCGStab (its nMaxIterations / tolerances given here) preconditioned by `solver` (1: one AMG cycle,
- * 2: the reference's ILU(0), see fvmgpu_bcgstab_ilu0_solve); 3: JacobiSolver with those limits.
+ * 2: the reference's ILU(0), see fvmgpu_bcgstab_ilu0_solve); 3: JacobiSolver with those limits; 4: CG
+ * preconditioned by one AMG cycle.
  * rnorm0[3] = initial residual 1-norm per velocity component, iters[3] */
 int fvmgpu_flow_solve_momentum(fvmgpu_flow_t flow, fvmgpu_solver_t solver, int bcgstab, int bcgMaxIterations,
                                double bcgRelTol, double bcgAbsTol, double* rnorm0, int* iters);

@@ -537,11 +537,12 @@ def test_fvm002_golden_is_reproduced_byte_for_byte_in_reference_order(hostsim_li
 
 
 @pytest.mark.skipif(not os.path.exists(PCAV_GOLDEN), reason="reference tree not mounted")
-@pytest.mark.parametrize("variant", ["AMG", "BCGStab"])
+@pytest.mark.parametrize("variant", ["AMG", "BCGStab", "CG"])
 def test_parallel_cavity_amg_golden_in_reference_order(hostsim_lib, reference_order, variant):
-    """T/PARALLEL_CAVITY_AMG/proc1 and T/PARALLEL_CAVITY_BCGStab/proc1 (BCGStab preconditioned by an AMG cycle, the
-    component-coupled recurrence): with the reference's agglomeration and sweep order the AMG-based histories are
-    reproduced as well -- all 100 SIMPLE iterations to the goldens' printed precision."""
+    """T/PARALLEL_CAVITY_AMG/proc1, T/PARALLEL_CAVITY_BCGStab/proc1 and T/PARALLEL_CAVITY_CG/proc1 (BCGStab / CG
+    preconditioned by an AMG cycle, the component-coupled recurrences): with the reference's agglomeration and sweep
+    order the AMG-based histories are reproduced as well -- all 100 SIMPLE iterations to the goldens' printed
+    precision."""
     import contextlib
     import io
 
@@ -550,7 +551,7 @@ def test_parallel_cavity_amg_golden_in_reference_order(hostsim_lib, reference_or
         s.relativeTolerance, s.nMaxIterations, s.maxCoarseLevels, s.verbosity = 1e-1, 20, 30, 0
         if variant == "AMG":
             return s
-        k = M.BCGStab()
+        k = M.BCGStab() if variant == "BCGStab" else M.CG()
         k.preconditioner = s
         k.relativeTolerance, k.nMaxIterations, k.verbosity = 1e-1, 20, 0
         return k
