@@ -103,6 +103,7 @@ SIGNATURES = {
                                     np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"), _ip]),
     "fvmgpu_amg_level_order": (C.c_int, [_vp, C.c_int, C.c_longlong, _ip, C.POINTER(C.c_int),
                                          np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]),
+    "fvmgpu_debug_set_aggregator": (C.c_int, [_vp, _vp]),
     "fvmgpu_amg_last_timing": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "fvmgpu_solver_history": (C.c_int, [_vp, C.c_int, _dp, C.POINTER(C.c_int)]),
     "fvmgpu_bcgstab_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
@@ -242,6 +243,11 @@ class Lib:
             out.append(dict(name=_demangle(nm), rows=int(rows[i]), launches=int(launches[i]), ms=float(ms[i]),
                             level=level))
         return out
+
+    def set_aggregator(self, fn_ptr, user=None):
+        """Verification hook (include/fvmgpu.h: fvmgpu_debug_set_aggregator): fn_ptr is the address of a C function
+        with the fvmgpu_aggregate_fn signature (or None to restore the library's own parallel pairing)."""
+        self.call("fvmgpu_debug_set_aggregator", C.c_void_p(fn_ptr) if fn_ptr else None, user)
 
     # ---- multi-GPU
     def comm_unique_id(self):

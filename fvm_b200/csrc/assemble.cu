@@ -509,6 +509,8 @@ System* systemCreate(Mesh* m) {
   }
   if (s->bcs.size() > MAX_BC_GROUPS) fail("system: more than %d face groups", MAX_BC_GROUPS);
   s->bcPerFace.resize(s->bcs.size());
+  s->version = nextVersion();
+  s->patternVersion = nextVersion();
   streamSync();
   return s.release();
 }
@@ -531,7 +533,8 @@ System* systemCreateRaw(int nSelf, int nGhost, const int* row, const int* col, c
   s->delta.alloc(nt); s->delta.zero();
   s->x.alloc(nt); s->x.zero();
   s->isBoundary.alloc(nt); s->isBoundary.zero();
-  s->version = 1;
+  s->version = nextVersion();
+  s->patternVersion = nextVersion();
   streamSync();
   return s.release();
 }
@@ -567,7 +570,8 @@ void systemSetField(System* s, int field, const double* host, long long n, bool 
   if (field == FVMGPU_FIELD_FACE_FLUX) s->hasFaceFlux = true;
   if (field == FVMGPU_FIELD_X_N1) s->hasXN1 = true;
   if (field == FVMGPU_FIELD_X_N2) s->hasXN2 = true;
-  if (field == FVMGPU_FIELD_B) s->version++;
+  // b and delta do not enter the hierarchy or the ILU factors: the stamp stays (the reference keeps its
+  // coarse levels while the matrix is unchanged, F/AMG.cpp:222-226)
 }
 
 void systemGetField(System* s, int field, double* host, long long n) {
@@ -670,7 +674,7 @@ void assemble(System* s, const fvmgpu_assemble_opts& o) {
   parallelFor(m->nTotal, AssembleRows{P});
   // LinearSystem::initSolve: delta = 0
   s->delta.zero();
-  s->version++;
+  s->version = nextVersion();
   if (o.apply_bcs) s->gradientValid = false;  // Dirichlet BCs rewrote x in the ghost cells
 }
 

@@ -392,6 +392,11 @@ int fvmgpu_amg_level_order(fvmgpu_solver_t s, int level, long long cap, int* nat
   }
   API_END
 }
+int fvmgpu_debug_set_aggregator(fvmgpu_aggregate_fn fn, void* user) {
+  API_BEGIN
+  setDebugAggregator(fn, user);
+  API_END
+}
 int fvmgpu_amg_last_timing(fvmgpu_solver_t s, double* setup_ms, double* cycles_ms) {
   API_BEGIN
   Amg* a = A(s);

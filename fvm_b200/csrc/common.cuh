@@ -89,6 +89,10 @@ struct Context {
 };
 Context& ctx();
 void requireReady();
+// Process-wide, strictly increasing stamp: every System gets a fresh one when it is created and whenever its
+// matrix (diag / off-diagonal / pattern) changes. Cached hierarchies and ILU factors are keyed on the stamp
+// alone -- an address can be handed out again by malloc / the block cache, a stamp cannot.
+unsigned long long nextVersion();
 
 inline int ceilDiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -767,7 +767,8 @@ static System* makeScalarSystem(Mesh* m, bool multi) {
   s->diag.alloc(nt); s->b.alloc(nt); s->delta.alloc(nt); s->x.alloc(nt); s->off.alloc((size_t)m->nnz);
   s->isBoundary.alloc(nt);
   s->diag.zero(); s->b.zero(); s->delta.zero(); s->x.zero(); s->off.zero(); s->isBoundary.zero();
-  s->version = 1;
+  s->version = nextVersion();
+  s->patternVersion = nextVersion();
   return s.release();
 }
 
@@ -998,7 +999,7 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
       same = nd == 0.0;
     }
     if (!same) {
-      s->version++;  // the hierarchy is rebuilt for this component's diagonal
+      s->version = nextVersion();  // the hierarchy is rebuilt for this component's diagonal
       copyD2D(F->lastDiag.p, s->diag.p, (size_t)nt * sizeof(double));
       haveHierarchy = true;
     }
@@ -1114,7 +1115,7 @@ void flowAssembleContinuity(Flow* F, const fvmgpu_flow_opts& o) {
   ContinuityRows K{P, F->scal.p, F->pressureBoundaryAnywhere ? 0 : 1, F->refCell, s->diag.p, s->off.p, s->b.p, s->isBoundary.p};
   parallelFor(m->nTotal, K);
   s->delta.zero();
-  s->version++;
+  s->version = nextVersion();
 }
 
 void flowDownloadContinuity(Flow* F, double* diag, double* off, double* b, int* isBoundary) {

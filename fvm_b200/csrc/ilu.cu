@@ -24,9 +24,8 @@ struct Ilu0 {
   DBuf<double> coef, y;
   DBuf<int> orderL, orderU;           // rows sorted by level
   std::vector<int> startL, startU;    // level boundaries in orderL / orderU
-  const int* patternOf = nullptr;     // sys->row the pattern was built for
-  const System* factoredFor = nullptr;
-  unsigned long long factoredVersion = 0;
+  unsigned long long patternVersion = 0;   // System::patternVersion the pattern analysis was done for
+  unsigned long long factoredVersion = 0;  // System::version the factors belong to (0: none)
 };
 void Ilu0Deleter::operator()(Ilu0* p) const { delete p; }
 
@@ -133,18 +132,18 @@ static void iluPattern(Ilu0& I, System* sys) {
     levelOrder(true, I.orderL, I.startL);
     levelOrder(false, I.orderU, I.startU);
   }
-  I.patternOf = sys->row;
-  I.factoredFor = nullptr;
+  I.patternVersion = sys->patternVersion;
+  I.factoredVersion = 0;
 }
 
 static void iluEnsure(Ilu0& I, System* sys) {
-  if (I.patternOf != sys->row || I.n != sys->nSelf) iluPattern(I, sys);
-  if (I.factoredFor == sys && I.factoredVersion == sys->version) return;
+  // stamps, not addresses: a destroyed system's address (host and device) is readily handed out again
+  if (I.patternVersion != sys->patternVersion || I.n != sys->nSelf) iluPattern(I, sys);
+  if (I.factoredVersion == sys->version) return;
   parallelFor(I.nnz, IluFillKernel{I.src.p, sys->diag.p, sys->off.p, I.coef.p});
   for (size_t l = 0; l + 1 < I.startL.size(); l++)
     parallelFor(I.startL[l + 1] - I.startL[l],
                 IluFactorRows{I.startL[l], I.orderL.p, I.row.p, I.col.p, I.diagIdx.p, I.coef.p});
-  I.factoredFor = sys;
   I.factoredVersion = sys->version;
 }
 

@@ -23,6 +23,11 @@ Context& ctx() {
   return c;
 }
 
+unsigned long long nextVersion() {
+  static unsigned long long counter = 0;  // one caller thread per process (include/fvmgpu.h)
+  return ++counter;
+}
+
 void requireReady() {
   if (!ctx().ready) fail("libfvmgpu: not initialised (call fvmgpu_init; a CUDA device is required, there is no CPU path)");
 }

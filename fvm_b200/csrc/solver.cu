@@ -51,12 +51,10 @@ struct FillDblKernel { double* p; double v; FVM_DEV void operator()(long long i)
 
 // ---- colouring (Jones-Plassmann with hashed priorities) on a CSR pattern
 struct ColourRoundKernel {
-  int n; const int* row; const int* col; int* colour; int* remaining; int* overflow; int degreeFirst;
+  int n; const int* row; const int* col; int* colour; int* remaining; int* overflow;
   FVM_DEV bool higher(int a, int b) const {  // priority(a) > priority(b)
-    if (degreeFirst) {
-      const int da = row[a + 1] - row[a], db = row[b + 1] - row[b];
-      if (da != db) return da > db;
-    }
+    const int da = row[a + 1] - row[a], db = row[b + 1] - row[b];
+    if (da != db) return da > db;   // rows with more neighbours first (~7 % fewer classes than hashed priorities alone)
     const unsigned ha = hash32((unsigned)a), hb = hash32((unsigned)b);
     return ha != hb ? ha > hb : a > b;
   }
@@ -112,62 +110,6 @@ struct SymEntriesKernel {  // entry k of row i -> (i, j) and (j, i); ghost / dia
     }
   }
 };
-// ---- 2-colouring of bipartite patterns by breadth-first parity (structured hex / quad meshes are
-// bipartite; Jones-Plassmann needs 6-7 colours there). The search runs as ONE cooperative kernel:
-// frontier queues (work proportional to the edges, not rows x diameter) and a grid-wide barrier per
-// BFS level, so a 256^3 mesh (diameter 768) costs ~800 barriers instead of ~800 launches over all
-// 16.8 M rows. BFS levels are unique, so the colouring is deterministic even though the order of
-// the queue entries is not. An edge inside one parity class (odd cycle) aborts the search.
-struct BfsIsolatedKernel {  // rows without neighbours are their own (trivially 2-colourable) component
-  int n; const int* row; const int* col; int* depth;
-  FVM_DEV void operator()(long long ii) const {
-    const int i = (int)ii;
-    for (int k = row[i]; k < row[i + 1]; k++) {
-      const int j = col[k];
-      if (j < n && j != i) return;
-    }
-    depth[i] = 0;
-  }
-};
-struct MinUnreachedKernel {  // flags[0] = smallest row index not reached yet
-  const int* depth; int* flags;
-  FVM_DEV void operator()(long long i) const { if (depth[i] == -1) atomicMin(&flags[0], (int)i); }
-};
-struct ParityKernel { const int* depth; int* colour; FVM_DEV void operator()(long long i) const { colour[i] = depth[i] & 1; } };
-
-// state[0], state[1]: sizes of the two queues; state[2]: odd-cycle flag; state[3]: last depth used
-// A BFS level is one dependent chain per frontier row (queue -> row range -> columns -> depth CAS ->
-// queue tail -> store), so the neighbours of a row are taken in batches of 8: all column loads, then all
-// compare-and-swaps in flight together, then ONE queue-tail atomic for the rows the batch discovered --
-// instead of a CAS + tail atomic round trip per neighbour, one after the other.
-FVM_DEV void bfsExpand(int i, int d, int n, const int* row, const int* col, int* depth, int* qout, int* cout, int* odd) {
-  const int end = row[i + 1];
-  for (int k0 = row[i]; k0 < end; k0 += 8) {
-    int js[8], olds[8];
-#pragma unroll
-    for (int t = 0; t < 8; t++) {
-      const int j = (k0 + t < end) ? col[k0 + t] : -1;
-      js[t] = (j >= 0 && j < n && j != i) ? j : -1;
-    }
-#pragma unroll
-    for (int t = 0; t < 8; t++) olds[t] = js[t] >= 0 ? atomicCAS(&depth[js[t]], -1, d + 1) : 0x7ffffffe;
-    int fresh = 0;
-    bool sameParity = false;
-#pragma unroll
-    for (int t = 0; t < 8; t++) {
-      if (js[t] < 0) continue;
-      if (olds[t] == -1) fresh++;
-      else if (((olds[t] ^ d) & 1) == 0) sameParity = true;
-    }
-    if (sameParity) *odd = 1;
-    if (fresh) {
-      int base = atomicAdd(cout, fresh);
-#pragma unroll
-      for (int t = 0; t < 8; t++)
-        if (js[t] >= 0 && olds[t] == -1) qout[base++] = js[t];
-    }
-  }
-}
 #ifndef FVMGPU_HOSTSIM
 // Grid-wide barrier for cooperative kernels: one arrival counter that only grows (zeroed by the host
 // before the launch); the CTA's thread 0 arrives and spins until the whole grid has arrived for
@@ -192,57 +134,8 @@ struct GridSync {
     __syncthreads();
   }
 };
-// state[0..2]: queue counters, rotating (round k consumes [k%3], fills [(k+1)%3], thread 0 clears [(k+2)%3]
-// for the round after); state[5], state[6]: odd-cycle flags, alternating per round; state[4]: barrier
-// counter; on exit state[7] = odd cycle seen, state[3] = last depth. What a round reads at its top (the
-// size of its queue, the previous round's flag) was final before the barrier that ended the previous
-// round, and nothing written during a round is read in the same round -- so ONE grid barrier per BFS
-// level is enough and every thread takes the same exit decision.
-__global__ void __launch_bounds__(1024) k_bfs_component(int n, const int* row, const int* col, int* depth, int* qA, int* qB,
-                                                         int* state, int d0) {
-  GridSync grid{reinterpret_cast<unsigned*>(&state[4])};
-  const long long tid = grid.tid();
-  const long long nthreads = grid.stride();
-  int d = d0;
-  int* qin = qA; int* qout = qB;
-  int odd = 0;
-  for (int k = 0;; k++) {
-    const int m = *(volatile int*)&state[k % 3];
-    odd = k > 0 ? *(volatile int*)&state[5 + ((k - 1) & 1)] : 0;
-    if (m == 0 || odd) break;
-    if (tid == 0) state[(k + 2) % 3] = 0;
-    int* cout = &state[(k + 1) % 3];
-    int* oddOut = &state[5 + (k & 1)];
-    for (long long idx = tid; idx < m; idx += nthreads) bfsExpand(qin[idx], d, n, row, col, depth, qout, cout, oddOut);
-    grid.sync();
-    int* t = qin; qin = qout; qout = t;
-    d++;
-  }
-  if (tid == 0) { state[7] = odd; state[3] = d; }
-}
 #endif
 
-// Iterated greedy (Culberson): rebuild the colouring class by class in REVERSE class order; a row takes
-// the smallest colour not held by its already re-coloured neighbours. The rows of an old class are
-// pairwise non-adjacent, so a class is one parallel launch; the number of colours never goes up and
-// usually drops by 1-3 on the coarse levels.
-struct RecolourClassKernel {
-  int n; const int* row; const int* col; int cls; const int* oldColour; int* newColour;
-  FVM_DEV void operator()(long long ii) const {
-    const int i = (int)ii;
-    if (oldColour[i] != cls) return;
-    unsigned long long used = 0ULL;
-    for (int k = row[i]; k < row[i + 1]; k++) {
-      const int j = col[k];
-      if (j >= n || j == i) continue;
-      const int cj = newColour[j];
-      if (cj >= 0) used |= 1ULL << cj;
-    }
-    int c = 0;
-    while ((used >> c) & 1ULL) c++;
-    newColour[i] = c;
-  }
-};
 // sort key of a row: 2*colour + (0 if the row has a halo column, else 1): inside a colour the rows the
 // other ranks need (and that need the other ranks) come first, so that a pass can run them apart
 // from the interior rows and overlap the halo exchange with the latter
@@ -258,7 +151,6 @@ struct IfaceKeyKernel {
     colour[i] = 2 * colour[i] + (iface ? 0 : 1);
   }
 };
-struct ClampColourKernel { int K; int* colour; FVM_DEV void operator()(long long i) const { if (colour[i] > K) colour[i] = K; } };
 struct RemapColourKernel { const int* remap; int* colour; FVM_DEV void operator()(long long i) const { colour[i] = remap[colour[i]]; } };
 struct ColourOneRows { const int* colour; FVM_DEV void operator()(long long i, double* o) const { o[0] = (double)colour[i]; } };
 struct ColourCountKernel {
@@ -332,19 +224,6 @@ struct GsRows {  // one colour: rows [rowBegin, rowBegin+count)
     x[r] = -sum / diag[r];
   }
 };
-struct GsRemainderRows {  // remainder class of the hybrid smoother: new values from the OLD x, parked in tmp
-  int rowBegin; const int* sliceOff; const int* scol; const double* sval; const double* diag; const double* b;
-  const double* x; double* tmp;
-  FVM_DEV void operator()(long long t) const {
-    const int r = rowBegin + (int)t;
-    const int s = r >> 5;
-    const int end = sliceOff[s + 1];
-    double sum = b[r];
-    for (int p = sliceOff[s] + (r & 31); p < end; p += 32) sum += sval[p] * x[scol[p]];
-    tmp[r] = -sum / diag[r];
-  }
-};
-struct CopyRangeRows { int rowBegin; const double* src; double* dst; FVM_DEV void operator()(long long t) const { dst[rowBegin + t] = src[rowBegin + t]; } };
 struct GsFirstColourZeroRows {  // first colour of a sweep on x == 0: x_i = -b_i/a_ii, no matrix read
   int rowBegin; const double* diag; const double* b; double* x;
   FVM_DEV void operator()(long long t) const {
@@ -488,7 +367,7 @@ struct StrongestKernel {  // per row: the largest weight among eligible neighbou
 // boundary layers in-plane): every coarse level of a hex / quad mesh is again a structured grid, i.e.
 // bipartite -> 2 colours instead of 7-10, and the cycle count drops by a third (hex 32^3: 76 -> 48).
 // On unstructured numberings it is a consistent symmetric choice among the strong connections.
-// FVMGPU_PAIR_STRONGEST_FIRST=1 restores weight-first ordering (w0 carries the weight then).
+// (w0 carries the weight for the role-based rounds below, which rank by weight first.)
 struct EdgeKey {
   float w0, w; int d; int odd; unsigned h;
   FVM_DEV bool betterThan(const EdgeKey& o) const {
@@ -734,7 +613,7 @@ struct ComposeGhostKernel {  // o[g] = b[a[g] - nMid]  (a: x index in the middle
 };
 struct IotaDblKernel { double* p; FVM_DEV void operator()(long long i) const { p[i] = (double)i; } };
 
-// ---- 2-colouring by tree parity (the default; the BFS below is kept for comparison, FVMGPU_BFS_COLOURING=1)
+// ---- 2-colouring by tree parity
 // A bipartite graph has exactly one proper 2-colouring per component (up to the swap), and the depth
 // parity in ANY spanning tree gives it. So: every row links to its smallest-index neighbour below itself
 // (a forest, links strictly decrease), pointer jumping turns link[i] = 2*ancestor + parity-of-the-path
@@ -834,15 +713,21 @@ static bool twoColouringByTreeParity(int n, const int* row, const int* col, DBuf
   return false;
 }
 
-// ================================================================= reference-order verification mode
-// FVMGPU_REFERENCE_ORDER=1 (a parity tool, not a fast path): the hierarchy is built by the reference's SEQUENTIAL
-// greedy agglomeration (CRMatrix::createCoarsening, F/CRMatrix.h:468-586, run on the host over the level's rows
-// in natural order) and the "colours" of a level are the dependency levels of its natural numbering
-// (level(i) = 1 + max level of the neighbours below i). Adjacent rows never share a level, ascending levels are a
-// valid schedule of the sequential forward sweep and descending levels of the reverse sweep, and every row sums
-// its entries in stored order -- so the multicolour machinery then performs EXACTLY the reference's sequential
-// Gauss-Seidel, in parallel inside a wavefront. With it the AMG histories of the reference's registered goldens
-// (testLinearSolver.out, AMG_MERGING_THERMAL) are reproduced digit for digit. Single rank only.
+// ================================================================= external-aggregation verification mode
+// fvmgpu_debug_set_aggregator(fn) (a parity tool, not a fast path; include/fvmgpu.h): while a callback is
+// registered, every level's aggregates come from the CALLER -- the level's matrix is handed over as a CSR in the
+// level's natural numbering and the callback returns one coarse index per row -- and the "colours" of a level are
+// the dependency levels of its natural numbering (level(i) = 1 + max level of the neighbours below i). Adjacent
+// rows never share a level, ascending levels are a valid schedule of a sequential forward sweep and descending
+// levels of the reverse sweep, and every row sums its entries in stored order -- so the multicolour machinery then
+// performs EXACTLY a sequential Gauss-Seidel, in parallel inside a wavefront. The tests register a CPU restatement
+// of the reference's sequential greedy agglomeration (CRMatrix::createCoarsening, F/CRMatrix.h:468-586) that lives
+// with the test infrastructure; with it this library's own solver reproduces the AMG histories of the reference's
+// registered goldens (testLinearSolver.out, AMG_MERGING_THERMAL, ...) digit for digit. The library itself contains
+// no agglomeration but its own parallel one. Single rank only.
+static fvmgpu_aggregate_fn g_aggregator = nullptr;
+static void* g_aggregatorUser = nullptr;
+void setDebugAggregator(fvmgpu_aggregate_fn fn, void* user) { g_aggregator = fn; g_aggregatorUser = user; }
 static bool g_referenceOrder = false;
 
 static int wavefrontColouring(int n, const int* row, const int* col, DBuf<int>& colour, std::vector<int>& counts) {
@@ -876,87 +761,9 @@ static int wavefrontColouring(int n, const int* row, const int* col, DBuf<int>& 
 
 // ================================================================= level construction
 // Colour a CSR pattern; returns number of colours, fills colour[] (device)
-static bool tryTwoColouring(int n, const int* row, const int* col, DBuf<int>& colour) {
-  DBuf<int> depth(n), qA(n), qB(n), state(8), flags(1);
-  depth.fillBytes(0xff);
-  parallelFor(n, BfsIsolatedKernel{n, row, col, depth.p});
-  const int big = 0x7fffffff;
-  int d0 = 0;
-  for (int component = 0; component < 32; component++) {
-    int hf = big;
-    copyH2D(flags.p, &hf, sizeof(int));
-    parallelFor(n, MinUnreachedKernel{depth.p, flags.p});
-    flags.download(&hf, 1);
-    if (hf == big) {  // everything reached
-      colour.alloc(n);
-      parallelFor(n, ParityKernel{depth.p, colour.p});
-      return true;
-    }
-    int seed = hf;
-    if (component == 0 && n > 4096) {
-      // The search costs one barrier + one dependent gather chain per BFS level, i.e. it scales with
-      // the eccentricity of the seed. The lowest row index is a corner of a structured mesh; the row in
-      // the middle of an (assumed cubic) natural numbering is near its centre and halves the depth.
-      // Any unreached row is a valid seed, so a wrong guess costs nothing.
-      const double c = std::cbrt((double)n);
-      long long cand = (long long)n / 2 + (long long)(c * c / 2) + (long long)(c / 2);
-      if (cand >= n) cand = n - 1;
-      int dc = 0;
-      copyD2H(&dc, depth.p + cand, sizeof(int));
-      if (dc == -1) seed = (int)cand;
-    }
-    int hs[8] = {1, 0, 0, d0, 0, 0, 0, 0};
-    copyH2D(state.p, hs, sizeof(hs));
-    copyH2D(qA.p, &seed, sizeof(int));
-    copyH2D(depth.p + seed, &d0, sizeof(int));
-#ifdef FVMGPU_HOSTSIM
-    {
-      int d = d0;
-      int* qin = qA.p; int* qout = qB.p;
-      int* cin = &state.p[0]; int* cout = &state.p[1];
-      while (*cin > 0 && !state.p[2]) {
-        const int m = *cin;
-        for (int idx = 0; idx < m; idx++) bfsExpand(qin[idx], d, n, row, col, depth.p, qout, cout, &state.p[2]);
-        *cin = 0; state.p[3] = d + 1;
-        std::swap(qin, qout); std::swap(cin, cout);
-        d++;
-      }
-      state.p[7] = state.p[2];
-      ctx().launches++;
-    }
-#else
-    {
-      // one 1024-thread CTA per SM: the arrival-counter barrier costs ~10 ns per arriving CTA, and a BFS
-      // level of a 256^3 mesh (<= 50 k frontier rows) never needs more threads than that
-      // (FVMGPU_BFS_CTAS_PER_SM=k launches k 256-thread CTAs per SM instead, for comparison)
-      static int maxBlocks = 0, threads = 1024;
-      if (!maxBlocks) {
-        int perSm = 0, want = 0;
-        if (const char* e = getenv("FVMGPU_BFS_CTAS_PER_SM")) want = atoi(e);
-        if (want > 0) threads = 256;
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_bfs_component, threads, 0));
-        if (perSm < 1) fail("amg: k_bfs_component cannot be made resident");
-        maxBlocks = ctx().smCount * (want > 0 ? (want < perSm ? want : perSm) : 1);
-      }
-      int nn = n, dd = d0;
-      int* depthP = depth.p; int* a = qA.p; int* b = qB.p; int* st = state.p;
-      void* args[] = {&nn, (void*)&row, (void*)&col, &depthP, &a, &b, &st, &dd};
-      ProfileScope prof("N6fvmgpu15k_bfs_componentE", n);
-      CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_bfs_component, dim3(maxBlocks), dim3(threads), args, 0, ctx().stream));
-      ctx().launches++;
-    }
-#endif
-    state.download(hs, 8);
-    if (hs[7]) return false;       // odd cycle: not bipartite
-    d0 = (hs[3] + 2) & ~1;         // next component restarts from an even depth
-  }
-  return false;                    // many components: leave it to the general colouring
-}
-
 static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, std::vector<int>& counts) {
   if (g_referenceOrder) return wavefrontColouring(n, row, col, colour, counts);
-  static const bool useBfs = getenv("FVMGPU_BFS_COLOURING") && atoi(getenv("FVMGPU_BFS_COLOURING")) != 0;
-  if (useBfs ? tryTwoColouring(n, row, col, colour) : twoColouringByTreeParity(n, row, col, colour)) {
+  if (twoColouringByTreeParity(n, row, col, colour)) {
     // class sizes: a sum of the 0/1 colours (exact in a double) instead of n atomics on two counters
     DBuf<double> ones(1);
     reduceRows<1>(n, ColourOneRows{colour.p}, ones.p);
@@ -993,15 +800,11 @@ static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, s
     }
   }
   int rounds = 0;
-  // priorities: rows with more neighbours first, a hash among equals (largest-degree-first needs ~7 %
-  // fewer classes than purely hashed priorities on tet / jittered-hex coarse levels, same cycle counts;
-  // FVMGPU_COLOUR_DEGREE_FIRST=0 for the latter)
-  const int degreeFirst = (getenv("FVMGPU_COLOUR_DEGREE_FIRST") && atoi(getenv("FVMGPU_COLOUR_DEGREE_FIRST")) == 0) ? 0 : 1;
   for (;;) {
     flags.zero();
     for (int k = 0; k < 4; k++) {
       if (k) devMemset(flags.p, 0, sizeof(int));
-      parallelFor(n, ColourRoundKernel{n, row, col, colour.p, flags.p, flags.p + 1, degreeFirst});
+      parallelFor(n, ColourRoundKernel{n, row, col, colour.p, flags.p, flags.p + 1});
       rounds++;
     }
     int h[2];
@@ -1011,25 +814,11 @@ static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, s
     if (rounds > 4096) fail("amg: colouring did not terminate");
   }
   DBuf<int> cnt(64);
-  std::vector<int> h;
-  int nc = 64;
-  // off by default: on the meshes tried it saves 7-9 % of the colour passes but the re-ordered
-  // Gauss-Seidel needed up to 10 % more cycles (hex 40^3: 84 -> 93), a net loss
-  const bool recolour = getenv("FVMGPU_RECOLOUR") && atoi(getenv("FVMGPU_RECOLOUR")) != 0;
-  for (int sweep = 0; sweep < 4; sweep++) {
-    cnt.zero();
-    parallelFor(n, ColourCountKernel{colour.p, cnt.p});
-    h = cnt.toHost();
-    int now = 0;
-    for (int c = 0; c < 64; c++) if (h[c] > 0) now = c + 1;
-    const bool improved = now < nc;
-    nc = now;
-    if (!recolour || sweep == 3 || (sweep > 0 && !improved) || nc <= 2) break;
-    DBuf<int> next(n);
-    next.fillBytes(0xff);
-    for (int c = nc - 1; c >= 0; c--) parallelFor(n, RecolourClassKernel{n, row, col, c, colour.p, next.p});
-    colour = std::move(next);
-  }
+  cnt.zero();
+  parallelFor(n, ColourCountKernel{colour.p, cnt.p});
+  std::vector<int> h = cnt.toHost();
+  int nc = 0;
+  for (int c = 0; c < 64; c++) if (h[c] > 0) nc = c + 1;
   counts.assign(h.begin(), h.begin() + nc);
   return nc;
 }
@@ -1043,22 +832,6 @@ static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, c
   std::vector<int> counts;
   DBuf<int> colour;
   L.nColours = colourCsr(n, row, col, colour, counts);
-  L.hybridLast = false;
-  {
-    // Hybrid smoother (opt-in, FVMGPU_HYBRID_COLOURS=K): keep the K largest-priority classes exact and
-    // merge all later (small) classes into one remainder class that is relaxed Jacobi-style among
-    // itself -- the late Jones-Plassmann classes hold a few per cent of the rows but each costs a
-    // full latency-bound pass.
-    int K = 0;
-    if (const char* e = getenv("FVMGPU_HYBRID_COLOURS")) K = atoi(e);
-    if (K >= 2 && L.nColours > K + 1) {
-      parallelFor(n, ClampColourKernel{K, colour.p});
-      for (int c = K + 1; c < L.nColours; c++) counts[K] += counts[c];
-      counts.resize(K + 1);
-      L.nColours = K + 1;
-      L.hybridLast = true;
-    }
-  }
   L.colourStart.assign(L.nColours + 1, 0);
   for (int c = 0; c < L.nColours; c++) L.colourStart[c + 1] = L.colourStart[c] + counts[c];
   L.ifaceCount.assign(L.nColours, 0);
@@ -1116,10 +889,9 @@ static bool aggregate(Level& F, const int* excluded, double threshold, DBuf<int>
   root.fillBytes(0xff);
   parallelFor(n, StrongestKernel{n, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, excluded, strongest.p});
   const int kRounds = 6;
-  const int strongestFirst = (getenv("FVMGPU_PAIR_STRONGEST_FIRST") && atoi(getenv("FVMGPU_PAIR_STRONGEST_FIRST"))) ? 1 : 0;
   for (int r = 0; r < kRounds; r++) {
     parallelFor(n, ProposeKernel{n, F.sliceOff.p, F.scol.p, F.sval.p, F.diag.p, excluded, strongest.p, threshold,
-                                 root.p, F.nat.p, strongestFirst, propose.p});
+                                 root.p, F.nat.p, 0, propose.p});
     parallelFor(n, HandshakeKernel{propose.p, F.nat.p, root.p});
   }
   {  // directed strength: many rows left without a mutual partner -> role-based matching rounds
@@ -1146,10 +918,11 @@ static bool aggregate(Level& F, const int* excluded, double threshold, DBuf<int>
   return nc > 0 && nc < n;
 }
 
-// (1') reference-order mode: CRMatrix::createCoarsening itself (F/CRMatrix.h:468-586), on the host, over the rows in
-//      NATURAL order; groupSize is the reference's coarseGroupSize (no composed pairing passes here).
-static bool aggregateSequential(Level& F, const int* excluded_d, int groupSize, double threshold, DBuf<int>& ciNat,
-                                int& nc) {
+// (1') external-aggregation mode: the level's matrix as a CSR in NATURAL numbering (entries keep their stored
+//      order) goes to the registered callback, which fills one coarse index per natural row (-1: not coarsened)
+//      and returns the number of aggregates.
+static bool aggregateExternal(Level& F, const int* excluded_d, int groupSize, double threshold, DBuf<int>& ciNat,
+                              int& nc) {
   const int n = F.n;
   nc = 0;
   if (n <= 1) return false;
@@ -1159,10 +932,8 @@ static bool aggregateSequential(Level& F, const int* excluded_d, int groupSize, 
   if (excluded_d) copyD2H(exclL.data(), excluded_d, (size_t)n * sizeof(int));
   std::vector<int> inv((size_t)n);
   for (int r = 0; r < n; r++) inv[(size_t)nat[(size_t)r]] = r;
-  // natural-order CSR (entries keep their stored order)
-  std::vector<int> row((size_t)n + 1, 0), col;
+  std::vector<int> row((size_t)n + 1, 0), col, isB((size_t)n, 0);
   std::vector<double> off, diag((size_t)n);
-  std::vector<char> isB((size_t)n, 0);
   for (int a = 0; a < n; a++) {
     const int r = inv[(size_t)a], sl = r >> 5;
     diag[(size_t)a] = diagL[(size_t)r];
@@ -1175,45 +946,17 @@ static bool aggregateSequential(Level& F, const int* excluded_d, int groupSize, 
     }
     row[(size_t)a + 1] = (int)col.size();
   }
-  std::vector<int> coarseIndex((size_t)n, -1), coarseCount((size_t)n, 0);
-  int nCoarseRows = 0;
-  for (int nr = 0; nr < n; nr++) {
-    if (coarseIndex[(size_t)nr] != -1 || isB[(size_t)nr]) continue;
-    int current = nr, colMaxGrouped = -1, colMaxUngrouped = -1, nGrouped;
-    coarseIndex[(size_t)current] = nCoarseRows;
-    for (nGrouped = 1; nGrouped < groupSize; nGrouped++) {
-      double maxWeightUngrouped = 0, maxWeightGrouped = 0;
-      colMaxGrouped = -1; colMaxUngrouped = -1;
-      for (int nb = row[(size_t)current]; nb < row[(size_t)current + 1]; nb++) {
-        const int c = col[(size_t)nb];
-        if (isB[(size_t)c]) continue;
-        const double d0 = std::fabs(diag[(size_t)nr]), d1 = std::fabs(diag[(size_t)c]);
-        const double w = std::fabs(std::fabs(off[(size_t)nb]) / std::max(d0, d1));
-        if (coarseIndex[(size_t)c] == -1) {
-          if (colMaxUngrouped == -1 || w > maxWeightUngrouped) { colMaxUngrouped = c; maxWeightUngrouped = w; }
-        } else if (coarseIndex[(size_t)c] != coarseIndex[(size_t)nr]) {
-          if (colMaxGrouped == -1 || w > maxWeightGrouped) { colMaxGrouped = c; maxWeightGrouped = w; }
-        }
-      }
-      if (colMaxUngrouped != -1 && (colMaxGrouped == -1 || maxWeightUngrouped > threshold * maxWeightGrouped)) {
-        coarseIndex[(size_t)colMaxUngrouped] = coarseIndex[(size_t)current];
-        coarseCount[(size_t)coarseIndex[(size_t)current]]++;
-        current = colMaxUngrouped;
-      } else {
-        break;
-      }
-    }
-    if (nGrouped > 1 || colMaxGrouped == -1 || coarseCount[(size_t)coarseIndex[(size_t)colMaxGrouped]] > groupSize + 2) {
-      coarseCount[(size_t)coarseIndex[(size_t)nr]]++;
-      nCoarseRows++;
-    } else {
-      coarseIndex[(size_t)nr] = coarseIndex[(size_t)colMaxGrouped];
-      coarseCount[(size_t)coarseIndex[(size_t)colMaxGrouped]]++;
-    }
-  }
-  nc = nCoarseRows;
+  if (col.empty()) { col.push_back(0); off.push_back(0.0); }
+  std::vector<int> coarseIndex((size_t)n, -1);
+  nc = g_aggregator(g_aggregatorUser, n, row.data(), col.data(), diag.data(), off.data(), isB.data(), groupSize, threshold,
+                    coarseIndex.data());
+  if (nc < 0) fail("amg: the registered aggregation callback failed (%d)", nc);
   std::vector<int> ciLevel((size_t)n);
-  for (int r = 0; r < n; r++) ciLevel[(size_t)r] = coarseIndex[(size_t)nat[(size_t)r]];
+  for (int r = 0; r < n; r++) {
+    const int c = coarseIndex[(size_t)nat[(size_t)r]];
+    if (c < -1 || c >= nc) fail("amg: aggregation callback returned coarse index %d of %d", c, nc);
+    ciLevel[(size_t)r] = c;
+  }
   ciNat.upload(ciLevel.data(), ciLevel.size());
   return nc > 0 && nc < n;
 }
@@ -1322,7 +1065,7 @@ static std::unique_ptr<Level> coarsenPass(Level& F, const int* excluded, double 
   DBuf<int> ciNat, crow, ccol, perm;
   DBuf<double> cval, cdiag;
   int nc = 0;
-  bool ok = g_referenceOrder ? aggregateSequential(F, excluded, groupSize, threshold, ciNat, nc)
+  bool ok = g_referenceOrder ? aggregateExternal(F, excluded, groupSize, threshold, ciNat, nc)
                              : aggregate(F, excluded, threshold, ciNat, nc);
   if (multi) ok = commAll(ok);
   if (!ok) return nullptr;
@@ -1383,7 +1126,7 @@ void Amg::setup(System* sys) {
   // one GPU: ghost columns carry delta = 0 and are dropped. Several ranks: the interface ghost
   // columns stay and their x slots are filled by the halo exchange.
   multi = commActive() && sys->mesh && !sys->noHalo;
-  g_referenceOrder = !multi && getenv("FVMGPU_REFERENCE_ORDER") && atoi(getenv("FVMGPU_REFERENCE_ORDER")) != 0;
+  g_referenceOrder = !multi && g_aggregator != nullptr;
   levels.emplace_back(new Level);
   Level& L0 = *levels[0];
   DBuf<int> ghostIsHalo;
@@ -1465,6 +1208,9 @@ void Amg::setup(System* sys) {
   streamSync();
   builtFor = sys;
   builtVersion = sys->version;
+  builtMaxCoarseLevels = opts.maxCoarseLevels;
+  builtGroupSize = opts.coarseGroupSize;
+  builtThreshold = opts.weightRatioThreshold;
 }
 
 // ================================================================= merged (replicated) coarse level
@@ -1847,8 +1593,6 @@ void Amg::buildTail() {
     if (coopOk) start = cstart; else tailIsCoop = false;
   }
   if (nl - start < 2) return;  // nothing worth fusing
-  for (int l = start; l < nl; l++)
-    if (levels[l]->hybridLast) return;  // the fused kernels implement the exact multicolour sweep only
   std::vector<TailLevel> h;
   tailColourStarts.clear();
   for (int l = start; l < nl; l++) {
@@ -1920,10 +1664,6 @@ void Amg::sweeps(int nSweeps, int lvl) {
         auto rowsOf = [&](int begin, int count) {
           if (count <= 0) return;
           if (L.xZero) parallelFor(count, GsFirstColourZeroRows{begin, L.diag.p, L.b.p, L.x.p});
-          else if (L.hybridLast && c == L.nColours - 1) {
-            parallelFor(count, GsRemainderRows{begin, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p});
-            parallelFor(count, CopyRangeRows{begin, L.r.p, L.x.p});
-          }
           else parallelFor(count, GsRows{begin, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p});
         };
         // Ghost values: refreshed after each half-sweep (forward / reverse), i.e. neighbours' rows
@@ -2032,7 +1772,10 @@ void Amg::storeDelta(double* delta_d) {
 }
 
 void Amg::ensureSetup(System* sys) {
-  if (builtFor != sys || builtVersion != sys->version || levels.empty()) setup(sys);
+  const bool sameStructure = builtMaxCoarseLevels == opts.maxCoarseLevels && builtGroupSize == opts.coarseGroupSize &&
+                             builtThreshold == opts.weightRatioThreshold;
+  if (builtVersion != sys->version || !sameStructure || levels.empty()) setup(sys);
+  builtFor = sys;
   if (!scalars.p) scalars.alloc(16);
 }
 
@@ -2051,6 +1794,18 @@ void Amg::dropGraphs() {
 // kind 1: preconditioner   (x = 0, cycle; b already loaded)
 void Amg::cycleGraphed(int kind) {
   Level& L0 = *levels[0];
+  // The rows of the colour relaxed last satisfy their equations up to rounding, so the convergence test may skip
+  // them -- but their true residual is the rounding residue (~eps * sum |a_ij x_j|), not 0: near machine precision
+  // (and in the reference-order verification mode) the full residual is computed, as the reference does.
+  static const bool fullResidualEnv = getenv("FVMGPU_FULL_RESIDUAL") && atoi(getenv("FVMGPU_FULL_RESIDUAL")) != 0;
+  const bool fullResidual = fullResidualEnv || g_referenceOrder || opts.relativeTolerance < 1e-10;
+  {  // the captured graphs bake these in: re-capture when one of them changed since the capture
+    const int key[5] = {opts.nPreSweeps, opts.nPostSweeps, opts.cycleType, opts.smootherType, fullResidual ? 1 : 0};
+    if (std::memcmp(key, graphOpts, sizeof(key)) != 0) {
+      dropGraphs();
+      std::memcpy(graphOpts, key, sizeof(key));
+    }
+  }
   auto body = [&]() {
     if (kind == 1) { L0.x.zero(); L0.xZero = true; L0.rValid = false; }
     cycle(opts.cycleType, 0);
@@ -2058,9 +1813,8 @@ void Amg::cycleGraphed(int kind) {
       LevelTag tag(tagBase);
       const ResidualRows R{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, L0.b.p, L0.x.p, L0.r.p};
       // the cycle ends with a post-sweep on level 0 whose last pass relaxes colour 0 = rows [0, colourStart[1])
-      static const bool fullResidual = getenv("FVMGPU_FULL_RESIDUAL") && atoi(getenv("FVMGPU_FULL_RESIDUAL")) != 0;
       const bool lastColourExact = !fullResidual && opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL &&
-                                   opts.nPostSweeps >= 1 && !L0.hybridLast && L0.nColours >= 2;
+                                   opts.nPostSweeps >= 1 && L0.nColours >= 2;
       if (lastColourExact) {
         const int z0 = multi ? L0.ifaceCount[0] : 0, z1 = L0.colourStart[1];
         if (z1 > z0) devMemset(L0.r.p + z0, 0, (size_t)(z1 - z0) * sizeof(double));

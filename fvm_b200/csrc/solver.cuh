@@ -21,7 +21,6 @@ struct Level {
   // link to the next coarser level (in ITS numbering)
   DBuf<int> ci;              // n: coarse row of each fine row, -1 = not coarsened
   DBuf<int> memOff, mem;     // coarse row -> its fine rows (ascending)
-  bool hybridLast = false;   // the last colour class is a Jacobi-relaxed remainder (hybrid smoother)
   bool xZero = false;        // x is known to be identically zero
   bool rValid = false;       // r holds b + A x for the current x
   // multi-GPU: x and r carry nGhost extra slots (columns >= n of the matrix) filled by the halo
@@ -49,8 +48,13 @@ struct Amg {
   std::vector<std::unique_ptr<Level>> levels;
   DBuf<int> perm0;           // system (natural) row -> level-0 row
   DBuf<double> scalars;      // device scalars for dots / norms
-  System* builtFor = nullptr;
-  unsigned long long builtVersion = 0;
+  System* builtFor = nullptr;          // the system of the last setup (used by the ILU preconditioner path)
+  unsigned long long builtVersion = 0; // its System::version stamp: THE identity of the hierarchy (stamps are unique)
+  // structural options the hierarchy was built with (a change rebuilds it) and the cycle options the captured
+  // graphs bake in (a change re-captures them)
+  int builtMaxCoarseLevels = -1, builtGroupSize = -1;
+  double builtThreshold = -1;
+  int graphOpts[5] = {-1, -1, -1, -1, -1};  // nPre, nPost, cycleType, smootherType, full-residual decision
   std::vector<double> history;
   long long totalIterations = 0;
   double lastSetupMs = 0, lastCyclesMs = 0;  // host wall clock of the last solve(): hierarchy build / cycle loop
@@ -125,6 +129,8 @@ struct Amg {
   void cycleGraphed(int kind);
   ~Amg() { dropGraphs(); }
 };
+
+void setDebugAggregator(fvmgpu_aggregate_fn fn, void* user);  // solver.cu
 
 // mesh.cu / assemble.cu entry points used by capi.cu
 Mesh* meshCreate(int dim, int nSelf, int nTotal, int nFaces, const int* faceCells, const int* ccRow,

@@ -76,7 +76,8 @@ struct System {
   std::vector<DBuf<double>> bcPerFace;  // owning storage of per-face values
   DBuf<BcEntry> bcsDev;
   bool bcsDirty = true;
-  unsigned long long version = 0;  // bumped by every assemble (AMG rebuilds its hierarchy)
+  unsigned long long version = 0;  // nextVersion() stamp of the matrix values: renewed by every assemble / matrix change
+  unsigned long long patternVersion = 0;  // stamp of the CSR pattern (set once at creation)
   bool noHalo = false;             // replicated (merged coarse) system: solved without communication
 };
 

@@ -202,6 +202,18 @@ int fvmgpu_amg_levels(fvmgpu_solver_t s, int cap, int* nLevels, long long* sizes
  * colour class. Rows of one class are relaxed concurrently, so no stored a_ij may join two of them. */
 int fvmgpu_amg_level_order(fvmgpu_solver_t s, int level, long long cap, int* nat, int* nColours,
                            long long* colourStart);
+/* Verification hook (tests; not a fast path). While a callback is registered, every AMG hierarchy of this process
+ * takes its aggregates from the CALLER instead of the library's parallel pairing: per level the callback receives
+ * the level matrix as a CSR in natural row numbering (diag separate, entries in stored order, isBoundary[i] != 0:
+ * row not to be coarsened), fills coarseIndex[0..nRows-1] (-1 = not coarsened) and returns the number of aggregates
+ * (< 0: error). Levels built this way are smoothed in natural row order (dependency wavefronts), i.e. exactly a
+ * sequential forward / reverse Gauss-Seidel. tests/ register the oracle's restatement of the reference's sequential
+ * agglomeration (CRMatrix::createCoarsening, F/CRMatrix.h:468-586) to reproduce the reference's AMG goldens digit
+ * for digit with this library's kernels. fn = NULL restores the default. Single rank only. */
+typedef int (*fvmgpu_aggregate_fn)(void* user, int nRows, const int* row, const int* col, const double* diag,
+                                   const double* offdiag, const int* isBoundary, int groupSize,
+                                   double weightRatioThreshold, int* coarseIndex);
+int fvmgpu_debug_set_aggregator(fvmgpu_aggregate_fn fn, void* user);
 /* host wall clock of the last fvmgpu_amg_solve, split into the hierarchy build (0 when the hierarchy
  * was reused) and the cycle loop, in milliseconds */
 int fvmgpu_amg_last_timing(fvmgpu_solver_t s, double* setup_ms, double* cycles_ms);

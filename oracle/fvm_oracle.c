@@ -580,6 +580,19 @@ static void precondition(fvmo_hier* H, const double* rhs, double* out) {
   memcpy(out, L0->x, sizeof(double) * (size_t)L0->nSelf);
 }
 
+/* CRMatrix::createCoarsening alone (F/CRMatrix.h:468-586) on a square CSR without ghost rows; signature of
+ * fvmgpu_aggregate_fn (include/fvmgpu.h) so that the tests can hand it to the library's verification hook */
+int fvmo_create_coarsening(void* user, int nRows, const int* row, const int* col, const double* diag,
+                           const double* off, const int* isBoundary, int groupSize, double thr, int* coarseIndex) {
+  (void)user;
+  fvmo_level L;
+  memset(&L, 0, sizeof(L));
+  L.nSelf = nRows; L.nTotal = nRows;
+  L.row = (int*)row; L.col = (int*)col; L.diag = (double*)diag; L.off = (double*)off;
+  L.isBoundary = (int*)isBoundary;
+  return create_coarsening(&L, groupSize, thr, coarseIndex);
+}
+
 int fvmo_solve(int nSelf, int nGhost, const int* row, const int* col, const double* diag, const double* off,
                const double* b, const int* isBoundary, const fvmo_amg_opts* o, int useBcgstab, double* x,
                double* history, int histCap, int* nHist, int* levelSizes) {

@@ -1,3 +1,4 @@
+import contextlib
 import os
 import sys
 
@@ -51,6 +52,38 @@ def ref():
     if not refapi.available():
         pytest.skip("oracle/_ref/libfvmref.so not built")
     return refapi
+
+
+def oracle_aggregator():
+    """Address of the oracle's restatement of the reference's sequential agglomeration (oracle/fvm_oracle.c:
+    fvmo_create_coarsening, signature fvmgpu_aggregate_fn) for the library's verification hook."""
+    import ctypes as C
+    from oracle import port
+    return C.cast(port.lib().fvmo_create_coarsening, C.c_void_p).value
+
+
+@contextlib.contextmanager
+def reference_order_mode(lib):
+    """Reference-order verification mode of `lib` (include/fvmgpu.h: fvmgpu_debug_set_aggregator): aggregates from the
+    oracle's sequential agglomeration, smoothing in natural row order."""
+    lib.set_aggregator(oracle_aggregator())
+    try:
+        yield
+    finally:
+        lib.set_aggregator(None)
+
+
+@pytest.fixture
+def reference_order(hostsim_lib):
+    with reference_order_mode(hostsim_lib):
+        yield
+
+
+@pytest.fixture
+def reference_order_dev(devlib):
+    """the same for tests parametrised over the device library and the host simulator"""
+    with reference_order_mode(devlib):
+        yield
 
 
 def load_golden(name):

@@ -519,17 +519,10 @@ def test_matrix_market_reader_reproduces_the_reference_system(hostsim_lib, tmp_p
         importers.MMReader(str(bad), str(q)).read()
 
 
-@pytest.fixture
-def reference_order():
-    os.environ["FVMGPU_REFERENCE_ORDER"] = "1"
-    yield
-    os.environ.pop("FVMGPU_REFERENCE_ORDER", None)
-
-
 @pytest.mark.skipif(not os.path.exists(FVM002_GOLDEN), reason="reference tree not mounted")
 def test_fvm002_golden_is_reproduced_byte_for_byte_in_reference_order(hostsim_lib, tmp_path, reference_order):
     """T/TESTS Fvm002 exactly as registered (AMG inner solves stopped at rel 1e-1, 10 SIMPLE iterations) with the
-    library in reference-order mode (the reference's sequential agglomeration and sweep order, FVMGPU_REFERENCE_ORDER=1):
+    library in reference-order mode (the reference's sequential agglomeration and sweep order, fvmgpu_debug_set_aggregator):
     the exported file IS cav32-prism.dat -- all 8893 lines, byte for byte."""
     out = str(tmp_path / "cav32.dat")
     _fvm002(hostsim_lib, 1e-1, 20, out)

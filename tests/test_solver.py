@@ -315,3 +315,60 @@ def test_cg_on_the_symmetric_thermal_system(devlib):
     ds.post_solve_update()
     assert rel_l2(ds.get_field(X.FIELD_X), g["ref_x"]) <= SOL_TOL
     amg.close(); ds.close(); dm.close()
+
+
+def test_cycle_options_changed_between_solves_take_effect(devlib):
+    """The captured cycle graphs bake in the sweep counts, the cycle type and the smoother: changing one of them on a
+    solver that already solved this system (same matrix stamp) must re-capture, not replay the old graph. The
+    histories of a V/GS solve and of a W/Jacobi solve on one solver object must equal those of fresh solvers."""
+    g = load_golden("mm226.npz")
+
+    def history(amg, ds, **kw):
+        o = devlib.default_amg_opts()
+        o.relativeTolerance, o.nMaxIterations = 1e-8, 500
+        for k, v in kw.items():
+            setattr(o, k, v)
+        amg.set_opts(o)
+        ds.fill_field(X.FIELD_DELTA, 0.0)
+        amg.solve(ds)
+        return amg.history()
+
+    ds = mm226_system(devlib, g)
+    amg = X.DeviceAMG(devlib)
+    h_v = history(amg, ds)
+    h_w = history(amg, ds, cycleType=X.CYCLE_W, smootherType=X.SMOOTHER_JACOBI, nPreSweeps=1)
+    h_v2 = history(amg, ds)
+    amg.close()
+    fresh = X.DeviceAMG(devlib)
+    h_w_fresh = history(fresh, ds, cycleType=X.CYCLE_W, smootherType=X.SMOOTHER_JACOBI, nPreSweeps=1)
+    fresh.close(); ds.close()
+    assert len(h_w) != len(h_v) or not np.array_equal(h_w, h_v)     # the options do change the iteration
+    assert np.array_equal(h_w, h_w_fresh) and np.array_equal(h_v, h_v2)
+
+
+def test_recreated_system_never_reuses_cached_factors_or_hierarchy(devlib):
+    """Hierarchies and ILU(0) factors are keyed on a process-wide matrix stamp, not on addresses: a system destroyed
+    and re-created (malloc and the device block cache hand the same addresses back) with ANOTHER matrix must be
+    factorised / coarsened afresh -- the reference-side adaptor re-creates its raw system every outer iteration."""
+    g = load_golden("cav32.npz")
+    n, nt = int(g["n_self"]), int(g["n_total"])
+    amg = X.DeviceAMG(devlib)
+    sols = []
+    for scale in (1.0, 0.5):   # weaker coupling the second time: another matrix on the same pattern
+        ds = X.DeviceSystem(devlib, raw=(n, nt - n, g["cc_row"], g["cc_col"], g["diag"], g["off"] * scale, g["b"]))
+        r0, r, it = amg.bcgstab_ilu0(ds, 500, 1e-12, 1e-50)   # applies the cached ILU(0) factors
+        assert r / r0 < 1e-12, (scale, it, r / r0)
+        x_ilu = ds.get_field(X.FIELD_DELTA).copy()
+        ds.fill_field(X.FIELD_DELTA, 0.0)
+        o = devlib.default_amg_opts()
+        o.relativeTolerance, o.nMaxIterations = 1e-12, 2000
+        amg.set_opts(o)
+        r0, r, it2 = amg.solve(ds)
+        assert r / r0 < 1e-12
+        sols.append((x_ilu[:n], ds.get_field(X.FIELD_DELTA)[:n].copy(), it))
+        ds.close()
+    amg.close()
+    for x_ilu, x_amg, _ in sols:
+        assert rel_l2(x_ilu, x_amg) < 1e-8
+    assert rel_l2(sols[0][1], sols[1][1]) > 1e-3      # the two matrices really differ
+    assert sols[1][2] < sols[0][2]                    # and stale factors would not have converged this fast
