@@ -22,8 +22,15 @@ roofline  dominant kernel = the level-0 multicolour Gauss-Seidel pass (GsRows); 
 cpu_baseline / --impl reference: the reference's own C++ (oracle/_ref, compiled in place) on the
         box's host cores on a bounded sample of the same workload (smaller mesh, same BCs/solver).
 
-N>1 (torchrun): every rank solves its own equal-size mesh replica set ... see DESIGN.md §5:
-        weak scaling, value = sum over ranks of cells / max over ranks of time.
+parity  printed with every line, for every N: (1) the converged field of the timed workload against the exact
+        discrete solution of this workload (uniform hexes, T fixed on z = 0 / top: linear in z), relative L2 over
+        all ranks; (2) a 64^3 jittered-hex problem with random conductivity solved by ALL ranks of this run as one
+        partitioned problem (same code path: halo exchange, distributed hierarchy) against the reference's own
+        C++ (oracle/_ref, rank 0, single partition): assembled diag / b of every rank's rows (bar 1e-12) and the
+        converged temperature, both solvers at rel 1e-13 (bar 1e-8 relative L2).
+
+N>1 (torchrun): ONE problem, z-slab partition, one part per GPU: weak scaling, 256^3 cells per
+        GPU (8 GPUs = the 512^3 mesh), value = all cells / max over ranks of the time.
 """
 import argparse
 import json
@@ -64,6 +71,8 @@ def parse():
     p.add_argument("--ref-n", type=int, default=0,
                    help="cells per side of the CPU sample mesh (default: 128 for --impl reference, 96 for the "
                         "cpu_baseline leg of the GPU arm)")
+    p.add_argument("--parity-size", type=int, default=64,
+                   help="cells per side of the partitioned oracle-parity problem every run solves (0: skip)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-profile", action="store_true")
     p.add_argument("--_worker", action="store_true", help=argparse.SUPPRESS)
@@ -167,7 +176,7 @@ def build_case(n, lib, rank=0, world=1):
     model.getOptions().linearSolver = solver
     model.getOptions()["initialTemperature"] = T_INIT
     model.init()
-    return raw, meshes[0], fields, model, solver
+    return raw, meshes[0], fields, model, solver, geom
 
 
 def device_step(lib, model, mesh, ls, solver):
@@ -212,7 +221,7 @@ def run_ours(args):
         capi.init_comm_from_torch(lib)   # the library's own NCCL communicator (halo exchange, all-reduce)
     n = args.n or 256
     t0 = time.time()
-    raw, mesh, fields, model, solver = build_case(n, lib, rank, world)
+    raw, mesh, fields, model, solver, geom = build_case(n, lib, rank, world)
     ls = model._systems[mesh.getID()]
     setup_s = time.time() - t0
     ncells = raw.n_cells
@@ -274,6 +283,10 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     x = fields.temperature[cells]
+    # ---- parity (collective: all ranks)
+    zc = np.asarray(geom.coordinate[cells])[:, 2]
+    lz = global_dims(n, world)[2] / n if MESH == "hex" else 1.0
+    parity = parity_block(lib, rank, world, np.asarray(x), zc, lz, ncells, getattr(args, "parity_size", 64))
     # ---- profiled step for the roofline of the dominant kernel
     roof = None
     prof_table = None
@@ -332,6 +345,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int((h1[1] - h0[1]) / ne2e), "d2h_bytes_per_step": int((h1[2] - h0[2]) / ne2e),
                 "seconds_per_step": e2e_s},
         "solution_check": {"min": float(x.min()), "max": float(x.max()), "mean": float(x[:ncells].mean())},
+        "parity": parity,
         "clocks": clocks, "mesh_setup_s": setup_s,
     }
     if world > 1:
@@ -344,6 +358,131 @@ def run_ours(args):
     if cpu:
         out["cpu_baseline"] = cpu
     print(json.dumps(out))
+
+
+def parity_block(lib, rank, world, x, zc, lz, n_own, n):
+    """The `parity` object of the JSON line (see the module docstring). Collective: every rank calls it."""
+    import torch
+    import torch.distributed as dist
+    from fvm_b200 import capi as X, meshgen as G, partition as P
+
+    def allsum(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return [float(v) for v in t.cpu()]
+
+    out = {}
+    # (1) the timed workload against its exact discrete solution (the face-centred two-point flux is exact for a
+    #     field that is linear in z on uniform hexes, so the linear profile IS the discrete solution)
+    if MESH == "hex":
+        exact = T_COLD + (T_HOT - T_COLD) * zc[:n_own] / lz
+        num, den = allsum([((x[:n_own] - exact) ** 2).sum(), (exact ** 2).sum()])
+        out["workload_vs_exact_solution_rel_l2"] = float(np.sqrt(num / den))
+        out["workload_solver_rel_tol"] = REL_TOL
+    if n <= 0:
+        return out
+    # (2) partitioned n^3 problem of this run's ranks against the reference on rank 0
+    raw = G.hex_mesh(n, n, n, jitter=0.15, seed=1)
+    geo = G.metrics(raw)
+    k_glob = np.exp(0.5 * np.random.default_rng(11).normal(size=raw.n_total))
+    bcs = {5: ("dirichlet", T_COLD), 6: ("dirichlet", T_HOT), 1: ("neumann", 5.0)}
+    ref_x = np.zeros(raw.n_total)
+    ref_diag = np.zeros(raw.n_total)
+    ref_b = np.zeros(raw.n_total)
+    kind = "none"
+    ref_cycles = -1
+    if rank == 0:
+        from oracle import refapi
+        if refapi.available():
+            kind = "reference (oracle/_ref)"
+            rm = refapi.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes,
+                                         raw.face_node_count, raw.face_group_size)
+            t = refapi.RefThermal(rm)
+            t.set_bc(5, "SpecifiedTemperature", specifiedTemperature=T_COLD)
+            t.set_bc(6, "SpecifiedTemperature", specifiedTemperature=T_HOT)
+            t.set_bc(1, "SpecifiedHeatFlux", specifiedHeatFlux=5.0)
+            t.set_solver(refapi.solver_cfg(relativeTolerance=1e-13, nMaxIterations=5000, verbosity=0))
+            t.init()
+            t.field("conductivity")[:] = k_glob
+            a = t.assemble(1)
+            t.field("temperature")[:] = T_INIT
+            r = t.advance_timed()
+            ref_cycles = int(r["cycles"])
+            ref_x[:] = t.field("temperature")
+            ref_diag[:], ref_b[:] = a["diag"], a["b"]
+            t.close()
+        else:
+            from oracle import port
+            kind = "port (oracle/fvm_oracle.c)"
+            conn = dict(zip(("cc_row", "cc_col"), G.connectivity(raw)))
+            conn.update(face_cells=raw.face_cells, group_offset=raw.group_offset, group_count=raw.group_count,
+                        group_id=raw.group_id, group_kind=raw.group_kind)
+            g2 = dict(geo)
+            g2["ib_type"] = np.full(raw.n_total, -1, np.int32)
+            rr = port.thermal_reference(raw, conn, g2, k_glob, bcs, x0=T_INIT, tol=1e-13)
+            ref_x[:], ref_diag[:], ref_b[:] = rr["x"], rr["diag"], rr["b"]
+    if world > 1:
+        pack = torch.from_numpy(np.concatenate([ref_x, ref_diag, ref_b])).cuda()
+        dist.broadcast(pack, 0)
+        pack = pack.cpu().numpy()
+        nt = raw.n_total
+        ref_x, ref_diag, ref_b = pack[:nt], pack[nt:2 * nt], pack[2 * nt:]
+        loc = P.partition_mesh(raw, geo, P.assign_slabs(raw.n_cells, world), rank)
+        cell_global, ge = loc.cell_global, loc.geometry
+    else:
+        loc = raw
+        cell_global, ge = np.arange(raw.n_total), geo
+    row, col = G.connectivity(loc)
+    dm = X.DeviceMesh(lib, loc.dim, loc.n_cells, loc.n_total, loc.face_cells, row, col, loc.group_offset,
+                      loc.group_count, loc.group_id, loc.group_kind)
+    dm.set_geometry(ge["face_area"], ge["face_area_mag"], ge["cell_centroid"], ge["cell_volume"],
+                    face_centroid=ge["face_centroid"], ib_type=np.full(loc.n_total, -1, np.int32))
+    if world > 1:
+        h = loc.halo
+        dm.set_halo(h["peers"], h["scatter_off"], h["scatter_idx"], h["gather_off"], h["gather_idx"])
+    ds = X.DeviceSystem(lib, dm)
+    ds.fill_field(X.FIELD_X, T_INIT)
+    ds.set_field(X.FIELD_DIFFUSIVITY, k_glob[cell_global])
+    kinds = {"dirichlet": X.BC_DIRICHLET, "neumann": X.BC_NEUMANN}
+    for gid in sorted(set(int(i) for i in loc.group_id)):
+        if 1 <= gid <= 6:
+            knd, v = bcs.get(gid, ("neumann", 0.0))
+            ds.set_bc(gid, kinds[knd], [v])
+    ds.assemble()
+    a = ds.download()
+    own = cell_global[:loc.n_cells]
+    ed = float(np.abs(a["diag"][:loc.n_cells] - ref_diag[own]).max())
+    eb = float(np.abs(a["b"][:loc.n_cells] - ref_b[own]).max())
+    o = lib.default_amg_opts()
+    o.relativeTolerance, o.nMaxIterations = 1e-13, 5000
+    amg = X.DeviceAMG(lib, o)
+    if KRYLOV:
+        r0, r, it = amg.bcgstab(ds, 500, 1e-13, 1e-50)
+    else:
+        r0, r, it = amg.solve(ds)
+    ds.post_solve_update()
+    xs = ds.get_field(X.FIELD_X)
+    num, den = allsum([((xs[:loc.n_cells] - ref_x[own]) ** 2).sum(), (ref_x[own] ** 2).sum()])
+    if world > 1:
+        t = torch.tensor([ed, eb], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ed, eb = float(t[0]), float(t[1])
+    amg.close(); ds.close(); dm.close()
+    sd, sb = float(np.abs(ref_diag).max()), float(np.abs(ref_b).max())
+    out["oracle_check"] = {
+        "oracle": kind, "mesh": "%d^3 jittered hexes, random conductivity, %d part(s)" % (n, world),
+        "assembly_max_rel_diff": {"diag": ed / max(sd, 1e-300), "b": eb / max(sb, 1e-300), "bar": 1e-12},
+        "solution_rel_l2": float(np.sqrt(num / max(den, 1e-300))), "solution_bar": 1e-8,
+        "solver_rel_tol_both": 1e-13, "cycles": int(it), "reference_cycles": ref_cycles}
+    if kind == "none":
+        out["oracle_check"] = {"oracle": "unavailable (oracle/_ref and the C port are missing)"}
+    else:
+        oc = out["oracle_check"]
+        oc["pass"] = bool(oc["assembly_max_rel_diff"]["diag"] <= 1e-12 and oc["assembly_max_rel_diff"]["b"] <= 1e-12
+                          and oc["solution_rel_l2"] <= 1e-8)
+    return out
 
 
 def hbm_peak():

@@ -21,6 +21,7 @@ HOSTSIM_LIB = os.path.join(HOSTSIM_DIR, "libfvmgpu_hostsim.so")
 SOURCES = [
     ("runtime.cu", []),
     ("comm.cu", []),
+    ("peer.cu", []),
     ("mesh.cu", ["-fmad=false"]),
     ("assemble.cu", ["-fmad=false"]),
     ("solver.cu", []),

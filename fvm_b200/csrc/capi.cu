@@ -66,9 +66,6 @@ int fvmgpu_init(int device) {
   CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   c.smCount = prop.multiProcessorCount;
   CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-  CUDA_CHECK(cudaStreamCreateWithFlags(&c.commStream, cudaStreamNonBlocking));
-  CUDA_CHECK(cudaEventCreateWithFlags(&c.evFork, cudaEventDisableTiming));
-  CUDA_CHECK(cudaEventCreateWithFlags(&c.evJoin, cudaEventDisableTiming));
   {
     cudaMemPool_t pool;
     CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -102,8 +99,6 @@ int fvmgpu_shutdown(void) {
   for (int i = 0; i < 16; i++) { cudaEventDestroy(c.timerStart[i]); cudaEventDestroy(c.timerStop[i]); }
   cudaStreamDestroy(c.stream);
   c.stream = nullptr;
-  if (c.commStream) { cudaStreamDestroy(c.commStream); c.commStream = nullptr; }
-  if (c.evFork) { cudaEventDestroy(c.evFork); cudaEventDestroy(c.evJoin); c.evFork = c.evJoin = nullptr; }
 #endif
   c.ready = false;
   API_END
@@ -574,6 +569,7 @@ int fvmgpu_comm_init(int nranks, int rank, const void* uniqueId128) {
   commInitNccl(nranks, rank, uniqueId128);
   ctx().nranks = nranks;
   ctx().rank = rank;
+  peerInit();   // NVLink peer-memory transport on top (collective); stays inactive where it cannot be set up
   API_END
 }
 int fvmgpu_comm_destroy(void) {

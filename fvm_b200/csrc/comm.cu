@@ -48,6 +48,7 @@ void Halo::build(const std::vector<HaloMsg>& m, const std::vector<int>& scatter,
   recvBuf.alloc((size_t)nRecv + 1);
   widthCap = 1;
   detectContiguous(gather);
+  peerPlanBuild(peer, msgs, 1);   // NVLink peer stores when the transport is up (else the plan stays invalid: NCCL)
 }
 
 void Halo::buildDev(const std::vector<HaloMsg>& m, DBuf<int>&& scatterDev, int nSendEntries, const std::vector<int>& gather) {
@@ -60,10 +61,17 @@ void Halo::buildDev(const std::vector<HaloMsg>& m, DBuf<int>&& scatterDev, int n
   recvBuf.alloc((size_t)nRecv + 1);
   widthCap = 1;
   detectContiguous(gather);
+  peerPlanBuild(peer, msgs, 1);
 }
 
 void Halo::exchange(double* x, int width) {
   if (!commActive() || msgs.empty()) return;
+  if (peer.valid()) {
+    // gather + store into the neighbours' memory + flag + wait + unpack: ONE kernel, no host-side collective call
+    if (width > peer.width && !peerPlanBuild(peer, msgs, width)) fail("halo exchange: no room in the peer windows for width %d (FVMGPU_PEER_WINDOW_MB)", width);
+    peerExchange(peer, scatterIdx.p, gatherIdx.p, gatherBase, x, x, width);
+    return;
+  }
   if (width > widthCap) {
     sendBuf.alloc((size_t)nSend * width + 1);
     recvBuf.alloc((size_t)nRecv * width + 1);
@@ -76,6 +84,15 @@ void Halo::exchange(double* x, int width) {
   }
   commExchange(msgs, sendBuf.p, recvBuf.p, width);
   if (nRecv) parallelFor((long long)nRecv * width, HaloUnpackKernel{gatherIdx.p, recvBuf.p, x, width});
+}
+
+void Halo::exchangeBegin(double* x) {
+  if (!commActive() || msgs.empty()) return;
+  peerExchangeBegin(peer, scatterIdx.p, x, 1);
+}
+void Halo::exchangeEnd(double* x) {
+  if (!commActive() || msgs.empty()) return;
+  peerExchangeEnd(peer, gatherIdx.p, gatherBase, x, 1);
 }
 
 #ifndef FVMGPU_HOSTSIM
@@ -138,6 +155,7 @@ void commInitNccl(int nranks, int rank, const void* uniqueId128) {
   }
 }
 void commDestroy() {
+  peerShutdown();
   if (ctx().ncclComm) { nccl().CommDestroy(ctx().ncclComm); ctx().ncclComm = nullptr; }
 }
 
@@ -158,6 +176,7 @@ void commExchange(const std::vector<HaloMsg>& msgs, const double* send_d, double
 }
 void commAllreduceSum(double* data_d, int cnt) {
   if (!commActive()) return;
+  if (peerAllreduceSum(data_d, cnt)) return;
   ncclCheck(nccl().AllReduce(data_d, data_d, (size_t)cnt, kNcclDouble, kNcclSum, ctx().ncclComm, ctx().stream),
             "ncclAllReduce");
   ctx().collectives++;

@@ -72,8 +72,6 @@ struct Context {
   int smCount = 148;
 #ifndef FVMGPU_HOSTSIM
   cudaStream_t stream = nullptr;  // compute stream: every kernel of the library runs here
-  cudaStream_t commStream = nullptr;  // halo exchanges overlapped with interior rows run here
-  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   cudaEvent_t timerStart[16] = {};
   cudaEvent_t timerStop[16] = {};
 #endif

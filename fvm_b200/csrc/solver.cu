@@ -1111,6 +1111,7 @@ void Amg::cleanup() {
   dropGraphs();
   tailStart = -1;
   nested.reset(); mergedSys.reset(); mergedLevel = -1; nestedLoaded = false;
+  mergePlan.release();
   levels.clear();
   builtFor = nullptr;
   builtVersion = 0;
@@ -1122,6 +1123,7 @@ void Amg::setup(System* sys) {
   tailStart = -1;
   levels.clear();
   nested.reset(); mergedSys.reset(); mergedLevel = -1; nestedLoaded = false;
+  mergePlan.release();
   const int n = sys->nSelf;
   // one GPU: ghost columns carry delta = 0 and are dropped. Several ranks: the interface ghost
   // columns stay and their x slots are filled by the halo exchange.
@@ -1320,6 +1322,7 @@ void Amg::buildMerged() {
   nested->setup(mergedSys.get());
   mergeSend.alloc((size_t)maxLocal); mergeSend.zero();
   mergeB.alloc((size_t)N); mergeX.alloc((size_t)N);
+  peerGatherPlan(mergePlan, maxLocal);   // built here: the first all-gather may run inside a graph capture
   nestedLoaded = false;
 }
 
@@ -1328,7 +1331,8 @@ void Amg::cycleMerged(int cycleType, int lvl) {
   LevelTag tag(tagBase + lvl);
   if (C.xZero || !nestedLoaded) {
     copyD2D(mergeSend.p, C.b.p, (size_t)C.n * sizeof(double));
-    commAllgather(mergeSend.p, mergeB.p, (size_t)mergeMaxLocal * sizeof(double));
+    if (mergePlan.valid()) peerAllgather(mergePlan, mergeSend.p, mergeB.p, mergeMaxLocal);
+    else commAllgather(mergeSend.p, mergeB.p, (size_t)mergeMaxLocal * sizeof(double));
     nested->loadSystem(mergedSys.get(), mergeB.p, nullptr);
     nestedLoaded = true;
   }
@@ -1340,33 +1344,28 @@ void Amg::cycleMerged(int cycleType, int lvl) {
 }
 
 void Amg::exchange(Level& L, double* x) {
+  joinExchange();
   if (multi) L.halo.exchange(x, 1);
 }
 
-// Overlapped exchange: the pack kernel and the NCCL calls are issued on the communication stream,
-// ordered after everything issued so far on the compute stream; joinExchange() makes the compute
-// stream wait for it. Both work inside a stream capture (fork / join of the graph).
+// Overlapped exchange (NVLink peer transport only): Begin gathers the interface values, stores them into the
+// neighbours' memory and flags them -- without waiting; the rows of the next pass that read no ghost slot run
+// meanwhile; End (joinExchange) waits for the neighbours' flags, which have long arrived by then, and unpacks.
+// One stream, no fork / join: the transport latency and the skew between the GPUs hide behind the interior rows.
+bool Amg::overlapOn(const Level& L) const {
+  return multi && overlapExchange && L.halo.canSplit() && L.n >= overlapMinRows && !exchangePerColour;
+}
 void Amg::forkExchange(Level& L, double* x) {
-#ifndef FVMGPU_HOSTSIM
-  Context& c = ctx();
-  CUDA_CHECK(cudaEventRecord(c.evFork, c.stream));
-  CUDA_CHECK(cudaStreamWaitEvent(c.commStream, c.evFork, 0));
-  cudaStream_t compute = c.stream;
-  c.stream = c.commStream;
-  try { L.halo.exchange(x, 1); } catch (...) { c.stream = compute; throw; }
-  c.stream = compute;
-  CUDA_CHECK(cudaEventRecord(c.evJoin, c.commStream));
-  exchangePending = true;
-#else
-  L.halo.exchange(x, 1);
-#endif
+  joinExchange();
+  L.halo.exchangeBegin(x);
+  pendingHalo = &L.halo;
+  pendingX = x;
 }
 void Amg::joinExchange() {
-#ifndef FVMGPU_HOSTSIM
-  if (!exchangePending) return;
-  CUDA_CHECK(cudaStreamWaitEvent(ctx().stream, ctx().evJoin, 0));
-  exchangePending = false;
-#endif
+  if (!pendingHalo) return;
+  Halo* h = pendingHalo;
+  pendingHalo = nullptr;
+  h->exchangeEnd(pendingX);
 }
 
 // ================================================================= coarse levels without launches
@@ -1648,7 +1647,7 @@ void Amg::runTail() {
 }
 
 // ================================================================= cycle
-void Amg::sweeps(int nSweeps, int lvl) {
+void Amg::sweeps(int nSweeps, int lvl, bool ghostsReadAfter) {
   Level& L = *levels[lvl];
   LevelTag tag(tagBase + lvl);
   // A colour pass only reads the OTHER colours, so repeating the pass that was just done changes
@@ -1670,8 +1669,11 @@ void Amg::sweeps(int nSweeps, int lvl) {
         // are lagged by at most one half-sweep -- the reference lags them by a whole sweep
         // (forwardGS+reverseGS, then x.sync(), F/MultiFieldMatrix.cpp:125-165). Per-colour exchange
         // (exact multicolour GS across ranks) is available with FVMGPU_EXCHANGE_PER_COLOUR=1.
-        const bool exchangeNow = multi && (exchangePerColour || pass == L.nColours - 1 || pass == 2 * L.nColours - 1);
-        if (multi && overlapExchange && L.n >= overlapMinRows) {
+        bool exchangeNow = multi && (exchangePerColour || pass == L.nColours - 1 || pass == 2 * L.nColours - 1);
+        // the very last refresh is for whoever reads this level's ghost slots next; on the way up of a V-cycle
+        // nobody does (a coarse level restarts from x = 0, ghosts included, in the next cycle)
+        if (exchangeNow && !ghostsReadAfter && s == nSweeps - 1 && pass == 2 * L.nColours - 1) exchangeNow = false;
+        if (overlapOn(L)) {
           // interior rows first (they read no ghost slot), then wait for the exchange started by the
           // previous half-sweep, then the interface rows; the exchange this pass starts runs on the
           // communication stream underneath the NEXT pass's interior rows
@@ -1690,10 +1692,11 @@ void Amg::sweeps(int nSweeps, int lvl) {
       joinExchange();
     } else {
       // two Jacobi passes per sweep (F/AMG.cpp:59-63), ping-pong through r
+      joinExchange();
       parallelFor(L.n, JacobiRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p});
       exchange(L, L.r.p);
       parallelFor(L.n, JacobiRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.r.p, L.x.p});
-      exchange(L, L.x.p);
+      if (ghostsReadAfter || s < nSweeps - 1) exchange(L, L.x.p);
       L.xZero = false;
     }
     L.rValid = false;
@@ -1722,7 +1725,7 @@ void Amg::cycle(int cycleType, int lvl) {
   Level& L = *levels[lvl];
   if (lvl == tailStart && cycleType == FVMGPU_CYCLE_V && L.xZero) { runTail(); return; }
   if (lvl == mergedLevel) { cycleMerged(cycleType, lvl); return; }
-  sweeps(opts.nPreSweeps, lvl);
+  sweeps(opts.nPreSweeps, lvl, true);
   if (lvl + 1 < (int)levels.size()) {
     Level& C = *levels[lvl + 1];
     const double* src;
@@ -1739,11 +1742,14 @@ void Amg::cycle(int cycleType, int lvl) {
     if (cycleType == FVMGPU_CYCLE_W) cycle(FVMGPU_CYCLE_W, lvl + 1);
     else if (cycleType == FVMGPU_CYCLE_F) cycle(FVMGPU_CYCLE_V, lvl + 1);
     { LevelTag tag(tagBase + lvl); parallelFor(L.n, CorrectRows{L.ci.p, C.x.p, L.x.p}); }
-    exchange(L, L.x.p);
+    // the corrected values travel under the interior rows of the first post-sweep pass
+    if (overlapOn(L) && opts.nPostSweeps > 0 && opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL) forkExchange(L, L.x.p);
+    else exchange(L, L.x.p);
     L.xZero = false;
     L.rValid = false;
   }
-  sweeps(opts.nPostSweeps, lvl);
+  sweeps(opts.nPostSweeps, lvl, lvl == 0 || cycleType != FVMGPU_CYCLE_V);
+  joinExchange();
 }
 
 void Amg::loadSystem(System* sys, const double* b_d, const double* x_d) {
@@ -1881,6 +1887,7 @@ void Amg::solve(System* sys, double* rnorm0Out, double* rnormOut, int* itersOut)
   totalIterations += iters;
   storeDelta(sys->delta.p);
   streamSync();
+  if (multi) peerCheck();
   const auto t2 = std::chrono::steady_clock::now();
   lastSetupMs = std::chrono::duration<double, std::milli>(t1 - t0).count();
   lastCyclesMs = std::chrono::duration<double, std::milli>(t2 - t1).count();

@@ -79,21 +79,21 @@ struct Amg {
   // F/LinearSystemMerger.cpp: gather coarse levels instead of exchanging halos of tiny levels)
   bool multi = false;
   int tagBase = 0;                 // profiler level tags of a nested hierarchy continue after the merged level
-  // Overlap (FVMGPU_OVERLAP=1, off by default): run the exchange on the communication stream under the
-  // next pass's interior rows (rows are ordered interface-first inside every colour for this).
-  // Measured on 2 B200s at 256^3 per GPU: 4.82 ms per cycle without, 5.18 ms with overlap on the
-  // levels >= 2 M rows, 6.60 ms with overlap on every level -- an exchange is ~1 MB over NVLink
-  // (~10 us) and costs less than the second launch per colour plus the graph fork/join that hiding it
-  // needs. Kept for slower interconnects / larger interfaces.
-  bool overlapExchange = false;
-  int overlapMinRows = 2000000;
-  bool exchangePending = false;
+  // Overlap (NVLink peer transport; FVMGPU_OVERLAP=0 switches it off): the halo exchange of a pass is started
+  // after its interface rows and finished before the interface rows of the next pass, with the interior rows
+  // in between (rows are ordered interface-first inside every colour for this); levels below overlapMinRows
+  // rows exchange in one piece (a pass there is shorter than the two extra launches).
+  bool overlapExchange = true;
+  int overlapMinRows = 1000000;
+  Halo* pendingHalo = nullptr;     // exchange begun, not yet finished
+  double* pendingX = nullptr;
   bool exchangePerColour = false;  // true: halo exchange after every colour pass; false: after every half-sweep
   int mergedLevel = -1;            // index of the distributed level that is solved replicated
   int mergeMaxLocal = 0;           // rows per rank block in the merged numbering (padded)
   std::unique_ptr<System> mergedSys;
   std::unique_ptr<Amg> nested;
   DBuf<double> mergeSend, mergeB, mergeX;
+  PeerPlan mergePlan;              // all-gather of the merged level's right-hand side over NVLink peer stores
   bool nestedLoaded = false;
 
   void setup(System* sys);   // AMG::createCoarseLevels
@@ -111,7 +111,7 @@ struct Amg {
   void jacobiSolve(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0, double* rnorm,
                    int* iters);
 
-  void sweeps(int nSweeps, int lvl);
+  void sweeps(int nSweeps, int lvl, bool ghostsReadAfter);
   void residual(int lvl);
   double residualNorm(int lvl);
   void cycle(int cycleType, int lvl);
@@ -121,6 +121,7 @@ struct Amg {
   void buildMerged();
   void cycleMerged(int cycleType, int lvl);
   void exchange(Level& L, double* x);
+  bool overlapOn(const Level& L) const;
   void forkExchange(Level& L, double* x);
   void joinExchange();
   void buildTail();

@@ -16,7 +16,8 @@ def test_bench_json_line_has_the_contract_keys(hostsim_lib, monkeypatch, mesh):
     monkeypatch.setattr(capi, "default_lib", lambda: hostsim_lib)
     monkeypatch.setattr(bench, "MESH", mesh)
     monkeypatch.setattr(bench, "KRYLOV", False)
-    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, n=6, no_profile=False, no_cpu_baseline=True, ref_n=0)
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, n=6, no_profile=False, no_cpu_baseline=True, ref_n=0,
+                                 parity_size=8)
     buf = io.StringIO()
     with redirect_stdout(buf):
         bench.run_ours(args)
@@ -34,3 +35,8 @@ def test_bench_json_line_has_the_contract_keys(hostsim_lib, monkeypatch, mesh):
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert d["gpu_launches"] > 0 and d["amg_cycles"] > 0 and len(d["step_ms"]) == 2
     assert 0 < d["solve_hbm"]["bytes_per_cycle"]
+    # parity block: this run's own small problem against the oracle (assembly 1e-12, solution 1e-8)
+    oc = d["parity"]["oracle_check"]
+    assert oc["pass"] and oc["assembly_max_rel_diff"]["diag"] <= 1e-12 and oc["solution_rel_l2"] <= 1e-8, oc
+    if mesh == "hex":
+        assert d["parity"]["workload_vs_exact_solution_rel_l2"] < 1e-6
