@@ -268,9 +268,13 @@ __global__ void __launch_bounds__(256) k_peer_exchange(const PeerMsg* msgs, int 
       }
     }
   }
-  __threadfence_system();
+  // ONE system-scope fence per CTA, by the thread that then counts the CTA in: the barrier orders every thread's
+  // stores before it (a fence in every thread throttles the NVLink stores to a third: tools/ipc_probe.cu)
   __syncthreads();
-  if (threadIdx.x == 0) sLast = atomicAdd(&counters[0], 1u) == gridDim.x - 1 ? 1 : 0;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    sLast = atomicAdd(&counters[0], 1u) == gridDim.x - 1 ? 1 : 0;
+  }
   __syncthreads();
   if (sLast) {
     __threadfence_system();
@@ -328,9 +332,13 @@ __global__ void __launch_bounds__(256) k_peer_push(const PeerMsg* msgs, int nMsg
       }
     }
   }
-  __threadfence_system();
+  // ONE system-scope fence per CTA, by the thread that then counts the CTA in: the barrier orders every thread's
+  // stores before it (a fence in every thread throttles the NVLink stores to a third: tools/ipc_probe.cu)
   __syncthreads();
-  if (threadIdx.x == 0) sLast = atomicAdd(&counters[0], 1u) == gridDim.x - 1 ? 1 : 0;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    sLast = atomicAdd(&counters[0], 1u) == gridDim.x - 1 ? 1 : 0;
+  }
   __syncthreads();
   if (sLast) {
     __threadfence_system();

@@ -284,19 +284,26 @@ struct MultiplyRows {  // y = A x   (CRMatrix::multiply, F/CRMatrix.h:200-216)
   }
 };
 struct InjectRows {  // coarse b[I] = sum of fine src over the aggregate (ascending fine row); coarse x = 0
-  const int* memOff; const int* mem; const double* src; double* bC; double* xC;
+  const int* memOff; const int* mem; const double* src; double* bC; double* xC;  // xC == nullptr: see Amg::cycle
   FVM_DEV void operator()(long long I) const {
     double s = 0.0;
     for (int p = memOff[I]; p < memOff[I + 1]; p++) s += src[mem[p]];
     bC[I] = s;
-    xC[I] = 0.0;
+    if (xC) xC[I] = 0.0;
   }
 };
-struct CorrectRows {  // fine x[i] += coarse x[ci[i]]
-  const int* ci; const double* xC; double* x;
-  FVM_DEV void operator()(long long i) const {
+// fine x[i] += coarse x[ci[i]] (Array::correct, F/Array.h:450-467) over the rows outside [skipFrom, skipTo): the
+// interior rows of the colour the first post-sweep pass relaxes are overwritten by that pass without being read
+// (a Gauss-Seidel row never reads its own old value), so correcting them is dead work -- half of the level on a
+// 2-coloured hierarchy. fineIsZero: the fine x is identically zero by construction (nPreSweeps = 0 on a coarse
+// level) and was never written: assign instead of add.
+struct CorrectRows {
+  int skipFrom, skipTo; int fineIsZero; const int* ci; const double* xC; double* x;
+  FVM_DEV void operator()(long long t) const {
+    const long long i = t < skipFrom ? t : t + (skipTo - skipFrom);
     const int c = ci[i];
-    if (c >= 0) x[i] += xC[c];
+    const double d = c >= 0 ? xC[c] : 0.0;
+    x[i] = fineIsZero ? d : x[i] + d;
   }
 };
 
@@ -1734,14 +1741,27 @@ void Amg::cycle(int cycleType, int lvl) {
       if (!L.rValid) residual(lvl);
       src = L.r.p;
     }
-    { LevelTag tag(tagBase + lvl); parallelFor(C.n, InjectRows{L.memOff.p, L.mem.p, src, C.b.p, C.x.p}); }
+    // The coarse level starts from x = 0. With Gauss-Seidel on <= 2 colours nobody reads a coarse x value before it
+    // has been written (the first pass on x == 0 reads no x at all, the second only rows of the first colour, and
+    // the prolongation below assigns), so the zeros are not even stored; otherwise they are.
+    const bool gs = opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL;
+    const bool lazyZero = gs && C.nColours <= 2 && cycleType == FVMGPU_CYCLE_V && opts.nPreSweeps == 0 &&
+                          opts.nPostSweeps >= 1 && lvl + 1 != tailStart;   // (the fused tail kernels add into x)
+    { LevelTag tag(tagBase + lvl); parallelFor(C.n, InjectRows{L.memOff.p, L.mem.p, src, C.b.p, lazyZero ? nullptr : C.x.p}); }
     if (C.nGhost) devMemset(C.x.p + C.n, 0, (size_t)C.nGhost * sizeof(double));
     C.xZero = true;
     C.rValid = false;
     cycle(cycleType, lvl + 1);
     if (cycleType == FVMGPU_CYCLE_W) cycle(FVMGPU_CYCLE_W, lvl + 1);
     else if (cycleType == FVMGPU_CYCLE_F) cycle(FVMGPU_CYCLE_V, lvl + 1);
-    { LevelTag tag(tagBase + lvl); parallelFor(L.n, CorrectRows{L.ci.p, C.x.p, L.x.p}); }
+    {
+      LevelTag tag(tagBase + lvl);
+      // rows [z0, z1): interior rows of colour 0 = what the first post-sweep pass overwrites unread
+      int z0 = 0, z1 = 0;
+      if (gs && opts.nPostSweeps >= 1) { z0 = multi ? L.ifaceCount[0] : 0; z1 = L.colourStart[1]; }
+      if (z1 < z0) z1 = z0;
+      parallelFor(L.n - (z1 - z0), CorrectRows{z0, z1, L.xZero ? 1 : 0, L.ci.p, C.x.p, L.x.p});
+    }
     // the corrected values travel under the interior rows of the first post-sweep pass
     if (overlapOn(L) && opts.nPostSweeps > 0 && opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL) forkExchange(L, L.x.p);
     else exchange(L, L.x.p);

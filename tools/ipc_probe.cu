@@ -60,6 +60,32 @@ __global__ void pushExchange(const double* src, double* peerDst, long long n, un
   __syncthreads();
 }
 
+// push-only variants (no wait): bytes per store instruction and stores in flight per thread
+__global__ void pushV1(const double* src, double* dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+  __threadfence_system();
+}
+__global__ void pushV2(const double2* src, double2* dst, long long n2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n2) dst[i] = src[i];
+  __threadfence_system();
+}
+__global__ void pushV2x4(const double2* src, double2* dst, long long n2) {   // 4 x 16 B per thread, grid-stride
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double2 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) if (i + k * stride < n2) v[k] = src[i + k * stride];
+#pragma unroll
+  for (int k = 0; k < 4; k++) if (i + k * stride < n2) dst[i + k * stride] = v[k];
+  __threadfence_system();
+}
+__global__ void pushNoFence(const double* src, double* dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
 #define STAGE(msg) fprintf(stderr, "[%d] %s\n", me, msg)
 int main() {
   setvbuf(stdout, nullptr, _IONBF, 0);
@@ -124,7 +150,7 @@ int main() {
   if (me == 0) printf("ipc_probe: flag round trip %.2f us (one way ~%.2f us)\n", ms * 1e3 / iters, ms * 1e3 / iters / 2);
   // (2) push + signal + wait, one kernel per exchange, back to back
   unsigned long long epoch = 0;
-  for (long long n : {1024LL, 16384LL, 131072LL, 1048576LL, 4194304LL}) {
+  for (long long n : {1024LL, 16384LL, 131072LL, 262144LL}) {   // <= 1024 CTAs: all resident (the kernel spins)
     const int reps = 200;
     for (int w = 0; w < 5; w++) {
       epoch++;
@@ -144,6 +170,30 @@ int main() {
              ms * 1e3 / reps, n * 8.0 / (ms * 1e-3 / reps) / 1e9);
   }
   { int to = 0; CK(cudaMemcpyFromSymbol(&to, g_timeouts, 4)); fprintf(stderr, "[%d] total timeouts=%d\n", me, to); }
+  // (3) push-only kernels (rank 0 pushes, rank 1 idles): store width / stores in flight / fence, and the copy engine
+  if (write(wr, &c, 1) != 1 || read(rd, &c, 1) != 1) return 1;
+  if (me == 0) {
+    for (long long n : {131072LL, 262144LL, 1048576LL, 4194304LL}) {
+      const int reps = 100;
+      auto timeIt = [&](const char* name, auto launch) {
+        for (int w = 0; w < 3; w++) launch();
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(a));
+        for (int r = 0; r < reps; r++) launch();
+        CK(cudaEventRecord(b));
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventElapsedTime(&ms, a, b));
+        printf("ipc_probe: %-22s %8lld doubles: %7.2f us  %6.1f GB/s\n", name, n, ms * 1e3 / reps, n * 8.0 / (ms * 1e-3 / reps) / 1e9);
+      };
+      timeIt("8 B/thread + fence", [&] { pushV1<<<(unsigned)((n + 255) / 256), 256>>>(src, peerData, n); });
+      timeIt("8 B/thread no fence", [&] { pushNoFence<<<(unsigned)((n + 255) / 256), 256>>>(src, peerData, n); });
+      timeIt("16 B/thread + fence", [&] { pushV2<<<(unsigned)((n / 2 + 255) / 256), 256>>>((const double2*)src, (double2*)peerData, n / 2); });
+      timeIt("4x16 B/thread + fence", [&] { pushV2x4<<<(unsigned)((n / 8 + 255) / 256), 256>>>((const double2*)src, (double2*)peerData, n / 2); });
+      timeIt("8 B/thread, local dst", [&] { pushV1<<<(unsigned)((n + 255) / 256), 256>>>(src, myData, n); });
+      timeIt("cudaMemcpyAsync D2D", [&] { cudaMemcpyAsync(peerData, src, n * 8, cudaMemcpyDeviceToDevice, 0); });
+    }
+  }
+  if (write(wr, &c, 1) != 1 || read(rd, &c, 1) != 1) return 1;
   // check the data arrived
   double hv = 0;
   CK(cudaMemcpy(&hv, myData + 5, 8, cudaMemcpyDeviceToHost));
