@@ -64,6 +64,25 @@ void Halo::buildDev(const std::vector<HaloMsg>& m, DBuf<int>&& scatterDev, int n
   peerPlanBuild(peer, msgs, 1);
 }
 
+struct HaloIotaKernel { int base; int* p; FVM_DEV void operator()(long long i) const { p[i] = base + (int)i; } };
+void Halo::buildDevContiguous(const std::vector<HaloMsg>& m, DBuf<int>&& scatterDev, int nSendEntries, int base, int nRecvEntries) {
+  msgs = m;
+  nSend = nSendEntries;
+  nRecv = nRecvEntries;
+  scatterIdx = std::move(scatterDev);
+  gatherIdx.alloc((size_t)nRecv + 1);
+  if (nRecv) parallelFor(nRecv, HaloIotaKernel{base, gatherIdx.p});
+  sendBuf.alloc((size_t)nSend + 1);
+  recvBuf.alloc((size_t)nRecv + 1);
+  widthCap = 1;
+  gatherBase = -1;
+  int expect = 0;
+  bool inOrder = true;
+  for (const HaloMsg& hm : msgs) { if (hm.recvOff != expect) inOrder = false; expect += hm.recvCnt; }
+  if (inOrder && nRecv > 0) gatherBase = base;
+  peerPlanBuild(peer, msgs, 1);
+}
+
 void Halo::exchange(double* x, int width) {
   if (!commActive() || msgs.empty()) return;
   if (peer.valid()) {
@@ -224,6 +243,17 @@ void commAllgather(const void* send_d, void* recv_d, size_t bytesPerRank) {
   ctx().collectives++;
 }
 #endif
+
+std::vector<double> commGatherHost(const double* vals, int cnt) {
+  const int nr = ctx().nranks;
+  std::vector<double> out((size_t)nr * cnt);
+  if (!commActive()) { for (int k = 0; k < cnt; k++) out[(size_t)k] = vals[k]; return out; }
+  DBuf<double> d((size_t)cnt), all((size_t)nr * cnt);
+  copyH2D(d.p, vals, sizeof(double) * (size_t)cnt);
+  commAllgather(d.p, all.p, sizeof(double) * (size_t)cnt);
+  copyD2H(out.data(), all.p, sizeof(double) * out.size());
+  return out;
+}
 
 double commSumHost(double v) {
   if (!commActive()) return v;

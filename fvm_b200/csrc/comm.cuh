@@ -30,6 +30,7 @@ void commExchange(const std::vector<HaloMsg>& msgs, const double* send_d, double
 void commAllreduceSum(double* data_d, int n);                       // in place
 void commAllgather(const void* send_d, void* recv_d, size_t bytesPerRank);
 double commSumHost(double v);                                       // host scalar convenience (synchronises)
+std::vector<double> commGatherHost(const double* vals, int cnt);    // every rank's cnt values, rank-major (one all-gather)
 double commMaxHost(double v);
 inline bool commAll(bool ok) { return !commActive() ? ok : commSumHost(ok ? 1.0 : 0.0) > ctx().nranks - 0.5; }
 inline bool commAny(bool ok) { return !commActive() ? ok : commSumHost(ok ? 1.0 : 0.0) > 0.5; }
@@ -87,6 +88,8 @@ struct Halo {
   void build(const std::vector<HaloMsg>& m, const std::vector<int>& scatter, const std::vector<int>& gather);
   // same with the scatter list already on the device
   void buildDev(const std::vector<HaloMsg>& m, DBuf<int>&& scatterDev, int nSendEntries, const std::vector<int>& gather);
+  // ghost slots gatherBase .. gatherBase + nRecvEntries - 1 in message order (every coarse AMG level): nothing comes from the host
+  void buildDevContiguous(const std::vector<HaloMsg>& m, DBuf<int>&& scatterDev, int nSendEntries, int base, int nRecvEntries);
   // x is `width` doubles per entry (AoS); ghost slots of x are overwritten with the peers' values
   void exchange(double* x, int width = 1);
   // split form (peer transport only, see peerExchangeBegin / End)

@@ -153,10 +153,33 @@ struct IfaceKeyKernel {
 };
 struct RemapColourKernel { const int* remap; int* colour; FVM_DEV void operator()(long long i) const { colour[i] = remap[colour[i]]; } };
 struct ColourOneRows { const int* colour; FVM_DEV void operator()(long long i, double* o) const { o[0] = (double)colour[i]; } };
-struct ColourCountKernel {
-  const int* colour; int* counts;
-  FVM_DEV void operator()(long long i) const { atomicAdd(&counts[colour[i]], 1); }
-};
+// class sizes: keys in [0, 128). One shared-memory histogram per CTA, then <= 128 global atomics per CTA (16.8 M
+// rows hammering 4 global counters cost 1.4 ms per level-0 call; this is ~0.1 ms)
+#ifndef FVMGPU_HOSTSIM
+__global__ void __launch_bounds__(256) k_histogram128(long long n, const int* key, int* counts) {
+  __shared__ int h[128];
+  if (threadIdx.x < 128) h[threadIdx.x] = 0;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&h[key[i] & 127], 1);
+  __syncthreads();
+  if (threadIdx.x < 128 && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], h[threadIdx.x]);
+}
+#endif
+static void histogram128(long long n, const int* key, int* counts /* 128, zeroed by the caller */) {
+  if (n <= 0) return;
+#ifdef FVMGPU_HOSTSIM
+  for (long long i = 0; i < n; i++) counts[key[i] & 127]++;
+  ctx().launches++;
+#else
+  ProfileScope prof("N6fvmgpu14k_histogram128E", n);
+  long long g = (n + 256 * 8 - 1) / (256 * 8);
+  if (g > 148 * 8) g = 148 * 8;
+  k_histogram128<<<(int)g, 256, 0, ctx().stream>>>(n, key, counts);
+  ctx().launches++;
+  CUDA_CHECK(cudaGetLastError());
+#endif
+}
 
 // ---- CSR -> SELL-32 with renumbering
 struct RowLenKernel {  // per NEW row
@@ -820,9 +843,9 @@ static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, s
     if (h[0] == 0) break;
     if (rounds > 4096) fail("amg: colouring did not terminate");
   }
-  DBuf<int> cnt(64);
+  DBuf<int> cnt(128);
   cnt.zero();
-  parallelFor(n, ColourCountKernel{colour.p, cnt.p});
+  histogram128(n, colour.p, cnt.p);
   std::vector<int> h = cnt.toHost();
   int nc = 0;
   for (int c = 0; c < 64; c++) if (h[c] > 0) nc = c + 1;
@@ -847,7 +870,7 @@ static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, c
     parallelFor(n, IfaceKeyKernel{n, row, col, ghostIsHalo, colour.p});
     DBuf<int> cnt2(2 * 64);
     cnt2.zero();
-    parallelFor(n, ColourCountKernel{colour.p, cnt2.p});
+    histogram128(n, colour.p, cnt2.p);
     std::vector<int> h2 = cnt2.toHost();
     for (int c = 0; c < L.nColours; c++) L.ifaceCount[c] = h2[2 * c];
     keyRange = 2 * L.nColours + 1;
@@ -976,43 +999,69 @@ static bool aggregateExternal(Level& F, const int* excluded_d, int groupSize, do
 //     F/MultiFieldMatrix.cpp:475-624). Fills F.ghostCoarse (fine ghost slot -> coarse x index).
 struct CoarseHaloInfo {
   std::vector<HaloMsg> msgs;
-  std::vector<int> scatterNat;  // natural coarse ids to send, concatenated per peer
-  int nGhost = 0;
+  DBuf<int> scatterNat;   // device: natural coarse ids to send, concatenated per peer
+  int nSend = 0, nGhost = 0;
 };
-static void coarseHalo(Level& F, const DBuf<int>& ciNat, int nc, CoarseHaloInfo& H) {
-  H.msgs.clear(); H.scatterNat.clear(); H.nGhost = 0;
-  std::vector<int> ghostCoarse((size_t)F.nGhost, -1);
+// The distinct ids of a message in ascending order WITHOUT sorting: mark[id] = 1, exclusive scan of the marks ->
+// pos[id] = rank of id among the marked ones. Everything stays on the device (round 1 sorted on the host: 70 ms of
+// the 8-GPU hierarchy build); only the two counts per message come back.
+struct MarkIdsKernel {
+  const double* ids; int* mark;
+  FVM_DEV void operator()(long long k) const { const int id = (int)ids[k]; if (id >= 0) mark[id] = 1; }
+};
+struct CompactMarkedKernel {
+  const int* mark; const int* pos; int base; int* out;
+  FVM_DEV void operator()(long long id) const { if (mark[id]) out[base + pos[id]] = (int)id; }
+};
+struct GhostSlotKernel {
+  const double* ids; const int* pos; const int* gatherIdx; int n; int base; int* ghostCoarse;
+  FVM_DEV void operator()(long long k) const {
+    const int id = (int)ids[k];
+    if (id >= 0) ghostCoarse[gatherIdx[k] - n] = base + pos[id];
+  }
+};
+// ncAll[r]: number of aggregates of rank r (bounds the ids a neighbour sends)
+static void coarseHalo(Level& F, const DBuf<int>& ciNat, int nc, const std::vector<int>& ncAll, CoarseHaloInfo& H) {
+  H.msgs.clear(); H.nSend = 0; H.nGhost = 0;
   const int ns = F.halo.nSend, nr = F.halo.nRecv;
+  F.ghostCoarse.alloc((size_t)(F.nGhost > 0 ? F.nGhost : 1));
+  F.ghostCoarse.fillBytes(0xff);
   DBuf<double> send((size_t)ns + 1), recv((size_t)nr + 1);
   if (ns) parallelFor(ns, GatherIntAsDoubleKernel{F.halo.scatterIdx.p, ciNat.p, send.p});
   commExchange(F.halo.msgs, send.p, recv.p, 1);
-  std::vector<double> hs((size_t)ns + 1), hr((size_t)nr + 1);
-  send.download(hs.data(), (size_t)ns + 1);
-  recv.download(hr.data(), (size_t)nr + 1);
+  int maxIds = nc;
+  for (const HaloMsg& m : F.halo.msgs) maxIds = std::max(maxIds, ncAll[(size_t)m.rank]);
+  DBuf<int> mark((size_t)maxIds + 1), pos((size_t)maxIds + 2);
+  H.scatterNat.alloc((size_t)ns + 1);   // distinct ids per message <= entries per message
   int sOff = 0, gOff = 0;
   for (const HaloMsg& m : F.halo.msgs) {
-    std::vector<int> us, ur;
-    for (int k = 0; k < m.sendCnt; k++) { const int id = (int)hs[(size_t)m.sendOff + k]; if (id >= 0) us.push_back(id); }
-    for (int k = 0; k < m.recvCnt; k++) { const int id = (int)hr[(size_t)m.recvOff + k]; if (id >= 0) ur.push_back(id); }
-    std::sort(us.begin(), us.end()); us.erase(std::unique(us.begin(), us.end()), us.end());
-    std::sort(ur.begin(), ur.end()); ur.erase(std::unique(ur.begin(), ur.end()), ur.end());
-    for (int k = 0; k < m.recvCnt; k++) {
-      const int id = (int)hr[(size_t)m.recvOff + k];
-      if (id < 0) continue;
-      const int slot = (int)(std::lower_bound(ur.begin(), ur.end(), id) - ur.begin());
-      ghostCoarse[(size_t)F.gatherHost[(size_t)m.recvOff + k] - F.n] = nc + gOff + slot;
+    int nus = 0, nur = 0;
+    if (m.sendCnt) {   // what I send: my own aggregate ids
+      mark.zero();
+      parallelFor(m.sendCnt, MarkIdsKernel{send.p + m.sendOff, mark.p});
+      exclusiveScan(mark.p, pos.p, nc);
+      nus = pos.hostAt((size_t)nc);
+      parallelFor(nc, CompactMarkedKernel{mark.p, pos.p, sOff, H.scatterNat.p});
+    }
+    if (m.recvCnt) {   // what I receive: the neighbour's aggregate ids, ordered exactly as the neighbour's own list
+      const int pnc = ncAll[(size_t)m.rank];
+      mark.zero();
+      parallelFor(m.recvCnt, MarkIdsKernel{recv.p + m.recvOff, mark.p});
+      exclusiveScan(mark.p, pos.p, pnc);
+      nur = pos.hostAt((size_t)pnc);
+      parallelFor(m.recvCnt, GhostSlotKernel{recv.p + m.recvOff, pos.p, F.halo.gatherIdx.p + m.recvOff, F.n, nc + gOff,
+                                             F.ghostCoarse.p});
     }
     HaloMsg cm;
     cm.rank = m.rank;
-    cm.sendOff = sOff; cm.sendCnt = (int)us.size();
-    cm.recvOff = gOff; cm.recvCnt = (int)ur.size();
+    cm.sendOff = sOff; cm.sendCnt = nus;
+    cm.recvOff = gOff; cm.recvCnt = nur;
     H.msgs.push_back(cm);
-    H.scatterNat.insert(H.scatterNat.end(), us.begin(), us.end());
-    sOff += (int)us.size();
-    gOff += (int)ur.size();
+    sOff += nus;
+    gOff += nur;
   }
+  H.nSend = sOff;
   H.nGhost = gOff;
-  F.ghostCoarse.upload(ghostCoarse.data(), ghostCoarse.size());
 }
 
 // (3) Galerkin by summation through ciNat (and F.ghostCoarse for ghost columns): coarse CSR in the
@@ -1059,7 +1108,7 @@ static void galerkin(Level& F, const DBuf<int>& ciNat, int nc, DBuf<int>& crow, 
 // Every rank must issue the same number of colour passes (each is followed by a halo exchange):
 // ranks with fewer colours run empty passes for the missing ones.
 static void agreeColours(Level& L) {
-  const int ncg = (int)commMaxHost((double)L.nColours);
+  const int ncg = (int)commMaxHost((double)L.nColours);   // one all-gather of a scalar
   while ((int)L.colourStart.size() < ncg + 1) L.colourStart.push_back(L.n);
   while ((int)L.ifaceCount.size() < ncg) L.ifaceCount.push_back(0);
   L.nColours = ncg;
@@ -1074,23 +1123,29 @@ static std::unique_ptr<Level> coarsenPass(Level& F, const int* excluded, double 
   int nc = 0;
   bool ok = g_referenceOrder ? aggregateExternal(F, excluded, groupSize, threshold, ciNat, nc)
                              : aggregate(F, excluded, threshold, ciNat, nc);
-  if (multi) ok = commAll(ok);
+  std::vector<int> ncAll;
+  if (multi) {   // one all-gather settles: does every rank go on, how many rows has everybody (coarse halo bounds, merge decision)
+    const double mine[2] = {ok ? 1.0 : 0.0, (double)nc};
+    const std::vector<double> all = commGatherHost(mine, 2);
+    ncAll.resize((size_t)ctx().nranks);
+    for (int r = 0; r < ctx().nranks; r++) { ok = ok && all[(size_t)2 * r] > 0.5; ncAll[(size_t)r] = (int)all[(size_t)2 * r + 1]; }
+  }
   if (!ok) return nullptr;
   CoarseHaloInfo H;
   F.ghostCoarse.release();
-  if (multi) coarseHalo(F, ciNat, nc, H);
+  if (multi) coarseHalo(F, ciNat, nc, ncAll, H);
   galerkin(F, ciNat, nc, crow, ccol, cval, cdiag);
   std::unique_ptr<Level> C(new Level);
   buildLevelFromCsr(*C, nc, crow.p, ccol.p, cval.p, cdiag.p, !multi, perm, H.nGhost, multi, nullptr);
   if (multi) {
-    const int ns = (int)H.scatterNat.size();
-    DBuf<int> natDev, scatterDev((size_t)ns + 1);
-    natDev.upload(H.scatterNat.data(), H.scatterNat.size());
-    if (ns) parallelFor(ns, GatherIntKernel{natDev.p, perm.p, scatterDev.p});
-    C->gatherHost.resize((size_t)H.nGhost);
-    for (int g = 0; g < H.nGhost; g++) C->gatherHost[(size_t)g] = nc + g;
-    C->halo.buildDev(H.msgs, std::move(scatterDev), ns, C->gatherHost);
+    const int ns = H.nSend;
+    DBuf<int> scatterDev((size_t)ns + 1);
+    if (ns) parallelFor(ns, GatherIntKernel{H.scatterNat.p, perm.p, scatterDev.p});
+    C->halo.buildDevContiguous(H.msgs, std::move(scatterDev), ns, nc, H.nGhost);   // ghost slots: nc .. nc + nGhost - 1
     agreeColours(*C);
+    C->globalRows = 0;
+    C->anyTiny = false;
+    for (int r : ncAll) { C->globalRows += r; C->anyTiny = C->anyTiny || r <= 3; }
   }
   parallelFor(F.n, RemapCiKernel{perm.p, ciNat.p});  // natural coarse id -> C's row numbering
   ci = std::move(ciNat);
@@ -1156,8 +1211,7 @@ void Amg::setup(System* sys) {
     const int ns = m->halo.nSend;
     DBuf<int> scatterDev((size_t)ns + 1);
     if (ns) parallelFor(ns, GatherIntKernel{m->halo.scatterIdx.p, perm0.p, scatterDev.p});
-    L0.gatherHost = m->haloGatherHost;  // ghost columns keep their cell index (>= n)
-    L0.halo.buildDev(m->halo.msgs, std::move(scatterDev), ns, L0.gatherHost);
+    L0.halo.buildDev(m->halo.msgs, std::move(scatterDev), ns, m->haloGatherHost);  // ghost columns keep their cell index (>= n)
     agreeColours(L0);
     // the captured cycle contains the NCCL send/recv, all-reduce and all-gather calls (NCCL >= 2.9
     // supports stream capture); measured on 2 B200s: 7.5 -> 5.35 ms per cycle
@@ -1185,8 +1239,7 @@ void Amg::setup(System* sys) {
     if (!C) break;
     // coarseGroupSize > 2: pair again and compose the maps, dropping the intermediate level
     for (int pass = 1; pass < passesPerLevel; pass++) {
-      bool more = C->n > 3;
-      if (multi) more = commAll(more);
+      bool more = multi ? !C->anyTiny : C->n > 3;
       if (!more) break;
       DBuf<int> ci2;
       std::unique_ptr<Level> C2 = coarsenPass(*C, nullptr, opts.weightRatioThreshold, multi, ci2);
@@ -1207,8 +1260,7 @@ void Amg::setup(System* sys) {
     // reference (parallel build, F/AMG.cpp:171-180): push the level, then stop once it has <= 3 rows
     levels.push_back(std::move(C));
     if (multi) {
-      const double globalRows = commSumHost((double)cn);
-      if (globalRows <= (double)mergeRows || commAny(cn <= 3)) { buildMerged(); break; }
+      if (levels.back()->globalRows <= (double)mergeRows || levels.back()->anyTiny) { buildMerged(); break; }
     } else if (cn <= 3) {
       break;
     }
@@ -1228,104 +1280,121 @@ void Amg::setup(System* sys) {
 // the owner's global id, and every rank builds the same single-GPU hierarchy below it. During a
 // cycle the level's right-hand side is all-gathered, the replicated hierarchy runs one cycle on
 // every rank (bit-identical: same input, deterministic kernels) and each rank keeps its block.
+// device-side construction (round 1 pulled the level to the host, rebuilt the CSR there and staged five
+// all-gathers through host memory):
+struct MergeRowLenKernel {   // true entries of a SELL row (padding has column == row)
+  int n; const int* sliceOff; const int* scol; int* len;
+  FVM_DEV void operator()(long long rr) const {
+    const int r = (int)rr;
+    int c = 0;
+    if (r < n) {
+      const int s = r >> 5;
+      for (int p = sliceOff[s] + (r & 31); p < sliceOff[s + 1]; p += 32) if (scol[p] != r) c++;
+    }
+    len[r] = c;
+  }
+};
+struct MergeBlockFillKernel {   // my padded block: entries packed row after row, columns as GLOBAL ids
+  int n, me, maxLocal; const int* sliceOff; const int* scol; const double* sval; const double* diag; const int* nat;
+  const int* off; const int* slotPeer; const double* ownerRow; int* bCol; double* bVal; double* bDiag; int* bNat;
+  FVM_DEV void operator()(long long rr) const {
+    const int r = (int)rr;
+    if (r >= n) { bDiag[r] = -1.0; bNat[r] = r; return; }   // padding row: inert, its own natural slot
+    bDiag[r] = diag[r];
+    bNat[r] = nat[r];
+    int q = off[r];
+    const int s = r >> 5;
+    for (int p = sliceOff[s] + (r & 31); p < sliceOff[s + 1]; p += 32) {
+      const int j = scol[p];
+      if (j == r) continue;
+      bCol[q] = j < n ? me * maxLocal + j : slotPeer[j - n] * maxLocal + (int)ownerRow[j];
+      bVal[q] = sval[p];
+      q++;
+    }
+  }
+};
+struct MergeAssembleKernel {   // global row g of the merged CSR from the gathered blocks
+  int maxLocal; long long maxStored; const int* row; const int* gCol; const double* gVal; const double* gDiag;
+  const int* gNat; const int* rowsOfRank; int* col; double* val; double* diag; int* isBoundary; int* hint;
+  FVM_DEV void operator()(long long gg) const {
+    const int g = (int)gg, r = g / maxLocal, i = g - r * maxLocal;
+    diag[g] = gDiag[g];
+    isBoundary[g] = i >= rowsOfRank[r] ? 1 : 0;   // padding row: x = -b/diag = 0, never coarsened
+    hint[g] = r * maxLocal + gNat[g];
+    const int beg = row[g], len = row[g + 1] - beg;
+    const long long src = (long long)r * maxStored + (beg - row[r * maxLocal]);
+    for (int k = 0; k < len; k++) { col[beg + k] = gCol[src + k]; val[beg + k] = gVal[src + k]; }
+  }
+};
+
 void Amg::buildMerged() {
   mergedLevel = (int)levels.size() - 1;
   Level& C = *levels[mergedLevel];
   const int nr = ctx().nranks, me = ctx().rank;
-  // row counts / nnz of every rank
-  DBuf<double> cntSend(2), cntAll((size_t)2 * nr);
-  double hc[2] = {(double)C.n, (double)C.nnzStored};
-  copyH2D(cntSend.p, hc, sizeof(hc));
-  commAllgather(cntSend.p, cntAll.p, sizeof(hc));
-  std::vector<double> allCnt = cntAll.toHost();
+  // row counts / stored entries of every rank
+  const double hc[2] = {(double)C.n, (double)C.nnzStored};
+  const std::vector<double> allCnt = commGatherHost(hc, 2);
   int maxLocal = 1; long long maxStored = 1;
+  std::vector<int> rowsOfRank((size_t)nr);
   for (int r = 0; r < nr; r++) {
-    maxLocal = std::max(maxLocal, (int)allCnt[(size_t)2 * r]);
+    rowsOfRank[(size_t)r] = (int)allCnt[(size_t)2 * r];
+    maxLocal = std::max(maxLocal, rowsOfRank[(size_t)r]);
     maxStored = std::max(maxStored, (long long)allCnt[(size_t)2 * r + 1]);
   }
   mergeMaxLocal = maxLocal;
-  // owner's row index of every ghost slot
+  // owner's row index of every ghost slot, and the rank that owns it
   DBuf<double> idx((size_t)C.n + C.nGhost + 1);
   parallelFor(C.n + C.nGhost, IotaDblKernel{idx.p});
   C.halo.exchange(idx.p, 1);
-  std::vector<double> hIdx = idx.toHost();
-  std::vector<int> slotPeer((size_t)C.nGhost, -1);
+  std::vector<int> slotPeerH((size_t)C.nGhost + 1, -1);
   for (const HaloMsg& m : C.halo.msgs)
-    for (int k = 0; k < m.recvCnt; k++) slotPeer[(size_t)m.recvOff + k] = m.rank;
-  // local SELL -> padded CSR block with global column ids
-  std::vector<int> sliceOff = C.sliceOff.toHost(), scol = C.scol.toHost();
-  std::vector<double> sval = C.sval.toHost(), diag = C.diag.toHost();
-  const size_t maxNnz = (size_t)maxStored;
-  std::vector<int> bLen((size_t)maxLocal, 0), bCol(maxNnz, 0);
-  std::vector<double> bVal(maxNnz, 0.0), bDiag((size_t)maxLocal, -1.0);
-  size_t q = 0;
-  for (int r = 0; r < C.n; r++) {
-    const int s = r >> 5;
-    int len = 0;
-    for (int p = sliceOff[(size_t)s] + (r & 31); p < sliceOff[(size_t)s + 1]; p += 32) {
-      const int j = scol[(size_t)p];
-      if (j == r) continue;  // padding
-      int gid;
-      if (j < C.n) gid = me * maxLocal + j;
-      else gid = slotPeer[(size_t)j - C.n] * maxLocal + (int)hIdx[(size_t)j];
-      bCol[q] = gid; bVal[q] = sval[(size_t)p]; q++; len++;
-    }
-    bLen[(size_t)r] = len;
-    bDiag[(size_t)r] = diag[(size_t)r];
-  }
-  auto gatherVec = [&](const void* h, size_t bytes, std::vector<char>& out) {
-    DBuf<char> sd(bytes), rd(bytes * nr);
-    copyH2D(sd.p, h, bytes);
-    commAllgather(sd.p, rd.p, bytes);
-    out.resize(bytes * nr);
-    copyD2H(out.data(), rd.p, bytes * nr);
-  };
-  std::vector<char> gLen, gCol, gVal, gDiag, gNat;
-  {
-    // natural index of every row of this rank's level (padding rows: their own slot)
-    std::vector<int> natLocal = C.nat.toHost();
-    natLocal.resize((size_t)maxLocal);
-    for (int i = C.n; i < maxLocal; i++) natLocal[(size_t)i] = i;
-    gatherVec(natLocal.data(), (size_t)maxLocal * sizeof(int), gNat);
-  }
-  gatherVec(bLen.data(), (size_t)maxLocal * sizeof(int), gLen);
-  gatherVec(bCol.data(), maxNnz * sizeof(int), gCol);
-  gatherVec(bVal.data(), maxNnz * sizeof(double), gVal);
-  gatherVec(bDiag.data(), (size_t)maxLocal * sizeof(double), gDiag);
+    for (int k = 0; k < m.recvCnt; k++) slotPeerH[(size_t)m.recvOff + k] = m.rank;
+  DBuf<int> slotPeer;
+  slotPeer.upload(slotPeerH.data(), slotPeerH.size());
+  // my block
+  DBuf<int> bLen((size_t)maxLocal + 1), bOff((size_t)maxLocal + 2), bCol((size_t)maxStored), bNat((size_t)maxLocal);
+  DBuf<double> bVal((size_t)maxStored), bDiag((size_t)maxLocal);
+  bCol.zero(); bVal.zero();
+  parallelFor(maxLocal, MergeRowLenKernel{C.n, C.sliceOff.p, C.scol.p, bLen.p});
+  exclusiveScan(bLen.p, bOff.p, maxLocal);
+  parallelFor(maxLocal, MergeBlockFillKernel{C.n, me, maxLocal, C.sliceOff.p, C.scol.p, C.sval.p, C.diag.p, C.nat.p, bOff.p,
+                                             slotPeer.p, idx.p, bCol.p, bVal.p, bDiag.p, bNat.p});
+  // gathered blocks (device to device)
   const int N = nr * maxLocal;
-  std::vector<int> row((size_t)N + 1, 0), col, isB((size_t)N, 0);
-  std::vector<double> val, dg((size_t)N), bz((size_t)N, 0.0);
-  for (int r = 0; r < nr; r++) {
-    const int* len = reinterpret_cast<const int*>(gLen.data()) + (size_t)r * maxLocal;
-    const int* cc = reinterpret_cast<const int*>(gCol.data()) + (size_t)r * maxNnz;
-    const double* vv = reinterpret_cast<const double*>(gVal.data()) + (size_t)r * maxNnz;
-    const double* dd = reinterpret_cast<const double*>(gDiag.data()) + (size_t)r * maxLocal;
-    const int rows = (int)allCnt[(size_t)2 * r];
-    size_t pos = 0;
-    for (int i = 0; i < maxLocal; i++) {
-      const size_t g = (size_t)r * maxLocal + i;
-      dg[g] = dd[i];
-      if (i >= rows) isB[g] = 1;  // padding row: inert (x = -b/diag = 0), never coarsened
-      for (int k = 0; k < len[i]; k++) { col.push_back(cc[pos]); val.push_back(vv[pos]); pos++; }
-      row[g + 1] = (int)col.size();
-    }
-  }
-  if (col.empty()) { col.push_back(0); val.push_back(0.0); }
-  mergedSys.reset(systemCreateRaw(N, 0, row.data(), col.data(), dg.data(), val.data(), bz.data()));
-  mergedSys->isBoundary.upload(isB.data(), isB.size());
-  mergedSys->noHalo = true;
+  DBuf<int> gLen((size_t)N + 1), gCol((size_t)nr * maxStored), gNat((size_t)N);
+  DBuf<double> gVal((size_t)nr * maxStored), gDiag((size_t)N);
+  commAllgather(bLen.p, gLen.p, (size_t)maxLocal * sizeof(int));
+  commAllgather(bNat.p, gNat.p, (size_t)maxLocal * sizeof(int));
+  commAllgather(bDiag.p, gDiag.p, (size_t)maxLocal * sizeof(double));
+  commAllgather(bCol.p, gCol.p, (size_t)maxStored * sizeof(int));
+  commAllgather(bVal.p, gVal.p, (size_t)maxStored * sizeof(double));
+  // merged system, assembled where it will live
+  mergedSys.reset(new System);
+  System& M = *mergedSys;
+  M.nSelf = N; M.nTotal = N;
+  M.rawRow.alloc((size_t)N + 1);
+  exclusiveScan(gLen.p, M.rawRow.p, N);
+  const int nnz = M.rawRow.hostAt((size_t)N);
+  M.nnz = nnz;
+  M.rawCol.alloc((size_t)(nnz > 0 ? nnz : 1));
+  M.off.alloc((size_t)(nnz > 0 ? nnz : 1));
+  M.diag.alloc((size_t)N); M.b.alloc((size_t)N); M.delta.alloc((size_t)N); M.x.alloc((size_t)N); M.isBoundary.alloc((size_t)N);
+  M.b.zero(); M.delta.zero(); M.x.zero();
+  M.row = M.rawRow.p; M.col = M.rawCol.p;
+  DBuf<int> rowsDev;
+  rowsDev.upload(rowsOfRank.data(), rowsOfRank.size());
   nested.reset(new Amg);
   nested->opts = opts;
   nested->tagBase = tagBase + mergedLevel;
-  {
-    // the merged rows are the ranks' level rows in THEIR (colour-sorted) order; the pairing preference
-    // of the nested hierarchy needs the rank-major NATURAL order, in which index distance means something
-    std::vector<int> hint((size_t)N);
-    const int* gn = reinterpret_cast<const int*>(gNat.data());
-    for (int r = 0; r < nr; r++)
-      for (int i = 0; i < maxLocal; i++) hint[(size_t)r * maxLocal + i] = r * maxLocal + gn[(size_t)r * maxLocal + i];
-    nested->natHint.upload(hint.data(), hint.size());
-  }
+  // the merged rows are the ranks' level rows in THEIR (colour-sorted) order; the pairing preference of the nested
+  // hierarchy needs the rank-major NATURAL order, in which index distance means something (natHint)
+  nested->natHint.alloc((size_t)N);
+  parallelFor(N, MergeAssembleKernel{maxLocal, maxStored, M.rawRow.p, gCol.p, gVal.p, gDiag.p, gNat.p, rowsDev.p, M.rawCol.p,
+                                     M.off.p, M.diag.p, M.isBoundary.p, nested->natHint.p});
+  M.version = nextVersion();
+  M.patternVersion = nextVersion();
+  M.noHalo = true;
+  streamSync();
   nested->setup(mergedSys.get());
   mergeSend.alloc((size_t)maxLocal); mergeSend.zero();
   mergeB.alloc((size_t)N); mergeX.alloc((size_t)N);

@@ -28,7 +28,8 @@ struct Level {
   // sweep, F/MultiFieldMatrix.cpp:164,216,397)
   int nGhost = 0;
   Halo halo;
-  std::vector<int> gatherHost;   // host copy of halo.gatherIdx (x indices >= n)
+  double globalRows = 0;         // rows of this level summed over the ranks; anyTiny: some rank has <= 3
+  bool anyTiny = false;
   DBuf<int> ghostCoarse;         // per ghost slot: x index in the NEXT level (>= its n), -1 = none
 };
 
