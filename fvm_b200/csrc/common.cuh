@@ -194,9 +194,11 @@ void parallelFor(long long n, const F& f) {
 // Stage 1: per-CTA sums in a fixed tree order -> scratch; stage 2: one CTA adds the partials in
 // index order. Result lands in out_d[0..NV-1] (device). No atomics: bit-reproducible run to run.
 constexpr int kReduceBlock = 256;
-// many more CTAs than can be resident (148 SMs x 6-8 CTAs): a 1.3-wave grid left half the machine idle in
-// the tail (ncu: 53 % warps active, 4.3 TB/s on the fused residual + norm); 48 waves hide it
-constexpr int kMaxReduceBlocks = 148 * 48;
+// One row per thread up to 9.7 M rows (a level-0 colour class of the 256^3 mesh is 8.4 M): a row of the fused
+// residual + norm is a chain of dependent gathers, and a thread that walks several rows one after the other keeps
+// fewer of them in flight than the one-row-per-thread smoother does (0.66 vs 0.89 of the HBM roof with 4.6 rows per
+// thread). Earlier history: a 1.3-wave grid left half the machine idle in the tail (4.3 TB/s).
+constexpr int kMaxReduceBlocks = 148 * 256;
 #ifdef FVMGPU_HOSTSIM
 template <int NV, class F>
 void reduceRows(long long n, const F& f, double* out_d) {
@@ -242,15 +244,21 @@ __global__ void __launch_bounds__(kReduceBlock) k_reduce1(long long n, const F f
   }
 }
 template <int NV>
-__global__ void k_reduce2(int nBlocks, const double* partial, double* out) {
-  // one warp per value; lanes stride over the partials, then a fixed shuffle tree
-  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (k >= NV) return;
+__global__ void __launch_bounds__(256) k_reduce2(int nBlocks, const double* partial, double* out) {
+  // one CTA per value; threads stride over the partials, then fixed shuffle / shared-memory trees
+  __shared__ double sm[8];
+  const int k = blockIdx.x, lane = threadIdx.x & 31;
   double v = 0.0;
-  for (int b = lane; b < nBlocks; b += 32) v += partial[(size_t)b * NV + k];
+  for (int b = threadIdx.x; b < nBlocks; b += 256) v += partial[(size_t)b * NV + k];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (lane == 0) out[k] = v;
+  if (lane == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; w++) s += sm[w];
+    out[k] = s;
+  }
 }
 template <int NV, class F>
 void reduceRows(long long n, const F& f, double* out_d) {
@@ -259,7 +267,7 @@ void reduceRows(long long n, const F& f, double* out_d) {
   if (nb < 1) nb = 1;
   ProfileScope prof(typeid(F).name(), n);
   k_reduce1<NV, F><<<nb, kReduceBlock, 0, ctx().stream>>>(n, f, ctx().reduceScratch);
-  k_reduce2<NV><<<1, 32 * NV, 0, ctx().stream>>>(nb, ctx().reduceScratch, out_d);
+  k_reduce2<NV><<<NV, 256, 0, ctx().stream>>>(nb, ctx().reduceScratch, out_d);
   ctx().launches += 2;
   CUDA_CHECK(cudaGetLastError());
 }

@@ -307,12 +307,49 @@ struct MultiplyRows {  // y = A x   (CRMatrix::multiply, F/CRMatrix.h:200-216)
   }
 };
 struct InjectRows {  // coarse b[I] = sum of fine src over the aggregate (ascending fine row); coarse x = 0
-  const int* memOff; const int* mem; const double* src; double* bC; double* xC;  // xC == nullptr: see Amg::cycle
-  FVM_DEV void operator()(long long I) const {
-    double s = 0.0;
-    for (int p = memOff[I]; p < memOff[I + 1]; p++) s += src[mem[p]];
-    bC[I] = s;
-    if (xC) xC[I] = 0.0;
+  // Aggregates are visited in their NATURAL order (the order of their fine rows), cpos maps to the coarse row: the
+  // members of consecutive aggregates are then consecutive fine rows (coalesced gathers) and the results go to a
+  // few contiguous streams, one per coarse colour. Visiting them in coarse-row order read every 32 B sector of r
+  // twice on a structured hierarchy (the two coarse colours interleave along the fine rows).
+  // A thread takes kInjectUnroll aggregates (t, t + T, t + 2T, ...: every access stays coalesced across the warp) and
+  // issues their loads level by level -- offsets, member rows, residuals -- so that four chains of dependent loads
+  // are in flight per thread instead of one (the kernel is bound by that latency, not by bytes: 3.5 TB/s before).
+  // Rows in [zeroFrom, zeroTo) are known to hold an exact zero residual (the colour relaxed last, see
+  // ResidualRowsFrom) and are not read.
+  static constexpr int kInjectUnroll = 4;
+  int nc; long long T; int zeroFrom, zeroTo;
+  const int* memOff; const int* mem; const int* cpos; const double* src; double* bC; double* xC;  // xC == nullptr: see Amg::cycle
+  FVM_DEV double at(int m) const { return (m >= zeroFrom && m < zeroTo) ? 0.0 : src[m]; }
+  FVM_DEV void operator()(long long t) const {
+    int b[kInjectUnroll], e[kInjectUnroll], m0[kInjectUnroll], m1[kInjectUnroll];
+    double s[kInjectUnroll];
+#pragma unroll
+    for (int k = 0; k < kInjectUnroll; k++) {
+      const long long I = t + k * T;
+      b[k] = e[k] = 0;
+      if (I < nc) { b[k] = memOff[I]; e[k] = memOff[I + 1]; }
+    }
+#pragma unroll
+    for (int k = 0; k < kInjectUnroll; k++) {
+      m0[k] = e[k] > b[k] ? mem[b[k]] : -1;
+      m1[k] = e[k] > b[k] + 1 ? mem[b[k] + 1] : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < kInjectUnroll; k++) {   // ascending member order, starting from 0.0 like the plain loop
+      s[k] = 0.0;
+      if (m0[k] >= 0) s[k] += at(m0[k]);
+      if (m1[k] >= 0) s[k] += at(m1[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kInjectUnroll; k++) {
+      for (int p = b[k] + 2; p < e[k]; p++) s[k] += at(mem[p]);
+      const long long I = t + k * T;
+      if (I < nc) {
+        const int r = cpos[I];
+        bC[r] = s[k];
+        if (xC) xC[r] = 0.0;
+      }
+    }
   }
 };
 // fine x[i] += coarse x[ci[i]] (Array::correct, F/Array.h:450-467) over the rows outside [skipFrom, skipTo): the
@@ -1153,13 +1190,20 @@ static std::unique_ptr<Level> coarsenPass(Level& F, const int* excluded, double 
   return C;
 }
 
-static void buildMembers(Level& F, int nc) {
-  // F.ci is in the coarse level's FINAL numbering; sort fine rows by it
-  const int n = F.n;
+struct NatKeyKernel {  // key = natural id of the row's aggregate (nc for rows that are not coarsened), value = row
+  const int* ci; const int* cnat; int nc; int* key; int* val;
+  FVM_DEV void operator()(long long i) const { const int c = ci[i]; key[i] = c >= 0 ? cnat[c] : nc; val[i] = (int)i; }
+};
+static void buildMembers(Level& F, Level& C) {
+  // F.ci is in the coarse level's FINAL numbering; the member lists are kept in the aggregates' NATURAL order
+  // (C.nat: coarse row -> natural id), rows ascending inside an aggregate; F.cpos: natural id -> coarse row
+  const int n = F.n, nc = C.n;
   DBuf<int> key(n);
   F.mem.alloc(n);
   F.memOff.alloc(nc + 2);
-  parallelFor(n, SortKeyKernel{F.ci.p, nc, key.p, F.mem.p});
+  F.cpos.alloc(nc + 1);
+  parallelFor(nc, InvPermKernel{C.nat.p, F.cpos.p});
+  parallelFor(n, NatKeyKernel{F.ci.p, C.nat.p, nc, key.p, F.mem.p});
   int bits = 1;
   while ((1LL << bits) < (long long)nc + 1) bits++;
   sortPairs(key.p, F.mem.p, n, bits);
@@ -1255,7 +1299,7 @@ void Amg::setup(System* sys) {
       C = std::move(C2);
     }
     F.ci = std::move(ci);
-    buildMembers(F, C->n);
+    buildMembers(F, *C);
     const int cn = C->n;
     // reference (parallel build, F/AMG.cpp:171-180): push the level, then stop once it has <= 3 rows
     levels.push_back(std::move(C));
@@ -1459,7 +1503,7 @@ struct TailLevel {
   const int* colourStart;  // device, nColours+1
   const int* sliceOff; const int* scol; const double* sval; const double* diag;
   double* b; double* x; double* r;
-  const int* ci; const int* memOff; const int* mem;  // links to the next level (null on the last)
+  const int* ci; const int* memOff; const int* mem; const int* cpos;  // links to the next level (null on the last)
 };
 constexpr int kTailThreads = 512;  // default CTA size of the fused kernels (127 registers, no spills);
                                    // a 1024-thread variant (64 registers, spills) exists for comparison: FVMGPU_FUSED_THREADS=1024
@@ -1505,8 +1549,35 @@ __device__ __forceinline__ void prefetchRow(const TailLevel& L, int c, long long
     if (p < P.end) { P.col[k] = L.scol[p]; P.val[k] = L.sval[p]; }
   }
 }
+// The same row sum with the PROLONGATION applied on the fly (first forward half-sweep after the coarse correction has
+// come back): a column at or behind `from` -- a row of a colour this half-sweep has not relaxed yet -- reads
+// x + xc[ci], every other column reads the value the half-sweep has already stored. After the half-sweep every row
+// has been overwritten, so the corrected values never need to be stored at all: the separate prolongation pass (one
+// barrier phase and one dependent-load chain per level, in a regime where that is all a phase costs) disappears.
+// Same additions in the same order as "x += xc[ci], barrier, sweep": bit-identical.
+__device__ __forceinline__ double tailRowAccCorr(const TailLevel& L, int r, double init, int from, const double* xc,
+                                                bool fineZero) {
+  const int s = r >> 5;
+  const int end = L.sliceOff[s + 1];
+  double sum = init;
+  for (int p = L.sliceOff[s] + (r & 31); p < end; p += 32) {
+    const int j = L.scol[p];
+    double xv;
+    if (j >= from) {
+      const int cj = L.ci[j];
+      xv = fineZero ? 0.0 : L.x[j];   // fineZero: x is identically zero before the correction (nPreSweeps = 0)
+      if (cj >= 0) xv += xc[cj];
+    } else {
+      xv = L.x[j];
+    }
+    sum += L.sval[p] * xv;
+  }
+  return sum;
+}
+// xc != nullptr: the level's x still lacks the coarse correction xc[ci] (see tailRowAccCorr)
 template <class S>
-__device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& xZero, S& sy) {
+__device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& xZero, S& sy, const double* xc = nullptr,
+                           bool fineZero = false) {
   int lastColour = -1;
   const long long t0 = sy.tid(), st = sy.stride();
   if (smoother == FVMGPU_SMOOTHER_GAUSS_SEIDEL) {
@@ -1520,7 +1591,10 @@ __device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& 
       if (c == lastColour) continue;
       const int r1 = L.colourStart[c + 1];
       long long r = L.colourStart[c] + t0;
-      if (r < r1) {
+      const bool corr = xc != nullptr && q < L.nColours;   // first forward half-sweep: prolongation on the fly
+      if (corr) {
+        for (; r < r1; r += st) L.x[r] = -tailRowAccCorr(L, (int)r, L.b[r], r1, xc, fineZero) / L.diag[r];
+      } else if (r < r1) {
         // first row of the pass: use the prefetched pieces when they belong to it
         double sum, d;
         if (P.r == r) {
@@ -1582,8 +1656,9 @@ __device__ void stretchDown(const TailLevel* lv, int l0, int l1, int nPre, int s
     for (long long I = t0; I < C.n; I += st) {
       double s = 0.0;
       for (int p = L.memOff[I]; p < L.memOff[I + 1]; p++) s += src[L.mem[p]];
-      C.b[I] = s;
-      C.x[I] = 0.0;
+      const int rc = L.cpos[I];
+      C.b[rc] = s;
+      C.x[rc] = 0.0;
     }
     sy.sync();
   }
@@ -1597,18 +1672,21 @@ __device__ void stretchBottom(const TailLevel* lv, int l, int nPre, int nPost, i
 }
 // levels l1-1 down to l0: prolongation of the next level's correction, then post-sweeps
 template <class S>
-__device__ void stretchUp(const TailLevel* lv, int l0, int l1, int nPost, int smoother, S& sy) {
+__device__ void stretchUp(const TailLevel* lv, int l0, int l1, int nPost, int smoother, bool fineZero, S& sy) {
   const long long t0 = sy.tid(), st = sy.stride();
   for (int l = l1 - 1; l >= l0; l--) {
     const TailLevel L = lv[l];
     const TailLevel C = lv[l + 1];
-    for (long long i = t0; i < L.n; i += st) {
-      const int c = L.ci[i];
-      if (c >= 0) L.x[i] += C.x[c];
+    const bool onTheFly = smoother == FVMGPU_SMOOTHER_GAUSS_SEIDEL && nPost >= 1;
+    if (!onTheFly) {
+      for (long long i = t0; i < L.n; i += st) {
+        const int c = L.ci[i];
+        if (c >= 0) L.x[i] += C.x[c];
+      }
+      sy.sync();
     }
-    sy.sync();
     bool xZero = false;
-    tailSweeps(L, nPost, smoother, xZero, sy);
+    tailSweeps(L, nPost, smoother, xZero, sy, onTheFly ? C.x : nullptr, fineZero);
   }
 }
 // on entry: level 0 of the stretch has b set and x == 0
@@ -1618,7 +1696,7 @@ __global__ void __launch_bounds__(THREADS) k_tail_vcycle(const TailLevel* lv, in
   CtaSync sy;
   stretchDown(lv, 0, nLevels - 1, nPre, smoother, sy);
   stretchBottom(lv, nLevels - 1, nPre, nPost, smoother, sy);
-  stretchUp(lv, 0, nLevels - 1, nPost, smoother, sy);
+  stretchUp(lv, 0, nLevels - 1, nPost, smoother, nPre == 0, sy);
 }
 // levels [0, nGrid) by the whole grid, levels [nGrid, nLevels) by CTA 0 alone (they have <= kTailRows
 // rows: one CTA is enough and its barrier is __syncthreads())
@@ -1631,10 +1709,10 @@ __global__ void __launch_bounds__(THREADS) k_coop_vcycle(const TailLevel* lv, in
     CtaSync cs;
     stretchDown(lv, nGrid, nLevels - 1, nPre, smoother, cs);
     stretchBottom(lv, nLevels - 1, nPre, nPost, smoother, cs);
-    stretchUp(lv, nGrid, nLevels - 1, nPost, smoother, cs);
+    stretchUp(lv, nGrid, nLevels - 1, nPost, smoother, nPre == 0, cs);
   }
   gs.sync();
-  stretchUp(lv, 0, nGrid, nPost, smoother, gs);
+  stretchUp(lv, 0, nGrid, nPost, smoother, nPre == 0, gs);
 }
 #endif
 
@@ -1681,7 +1759,7 @@ void Amg::buildTail() {
     t.n = L.n; t.nColours = L.nColours; t.colourStart = tailColourStarts[l - start].p;
     t.sliceOff = L.sliceOff.p; t.scol = L.scol.p; t.sval = L.sval.p; t.diag = L.diag.p;
     t.b = L.b.p; t.x = L.x.p; t.r = L.r.p;
-    t.ci = L.ci.p; t.memOff = L.memOff.p; t.mem = L.mem.p;
+    t.ci = L.ci.p; t.memOff = L.memOff.p; t.mem = L.mem.p; t.cpos = L.cpos.p;
     h.push_back(t);
   }
   tailLevels.alloc(h.size() * sizeof(TailLevel));
@@ -1784,6 +1862,7 @@ void Amg::residual(int lvl) {
   LevelTag tag(tagBase + lvl);
   parallelFor(L.n, ResidualRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p});
   L.rValid = true;
+  L.rZeroFrom = L.rZeroTo = 0;
 }
 
 double Amg::residualNorm(int lvl) {
@@ -1792,6 +1871,7 @@ double Amg::residualNorm(int lvl) {
   reduceRows<1>(L.n, ResidualRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p}, scalars.p);
   if (multi) commAllreduceSum(scalars.p, 1);  // MultiFieldReduction::reduceSum
   L.rValid = true;
+  L.rZeroFrom = L.rZeroTo = 0;
   double v;
   copyD2H(&v, scalars.p, sizeof(double));
   return v;
@@ -1816,7 +1896,14 @@ void Amg::cycle(int cycleType, int lvl) {
     const bool gs = opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL;
     const bool lazyZero = gs && C.nColours <= 2 && cycleType == FVMGPU_CYCLE_V && opts.nPreSweeps == 0 &&
                           opts.nPostSweeps >= 1 && lvl + 1 != tailStart;   // (the fused tail kernels add into x)
-    { LevelTag tag(tagBase + lvl); parallelFor(C.n, InjectRows{L.memOff.p, L.mem.p, src, C.b.p, lazyZero ? nullptr : C.x.p}); }
+    {
+      LevelTag tag(tagBase + lvl);
+      const long long T = (C.n + InjectRows::kInjectUnroll - 1) / InjectRows::kInjectUnroll;
+      // level 0 after the residual pass of the solve loop: r is an exact zero on [rZeroFrom, rZeroTo) and not stored there
+      const bool zr = src == L.r.p && L.rZeroTo > L.rZeroFrom;
+      parallelFor(T, InjectRows{C.n, T, zr ? L.rZeroFrom : 0, zr ? L.rZeroTo : 0, L.memOff.p, L.mem.p, L.cpos.p, src, C.b.p,
+                                lazyZero ? nullptr : C.x.p});
+    }
     if (C.nGhost) devMemset(C.x.p + C.n, 0, (size_t)C.nGhost * sizeof(double));
     C.xZero = true;
     C.rValid = false;
@@ -1901,6 +1988,8 @@ void Amg::cycleGraphed(int kind) {
       std::memcpy(graphOpts, key, sizeof(key));
     }
   }
+  const bool lastColourExactNow = !fullResidual && opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL &&
+                                  opts.nPostSweeps >= 1 && L0.nColours >= 2;
   auto body = [&]() {
     if (kind == 1) { L0.x.zero(); L0.xZero = true; L0.rValid = false; }
     cycle(opts.cycleType, 0);
@@ -1908,20 +1997,27 @@ void Amg::cycleGraphed(int kind) {
       LevelTag tag(tagBase);
       const ResidualRows R{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, L0.b.p, L0.x.p, L0.r.p};
       // the cycle ends with a post-sweep on level 0 whose last pass relaxes colour 0 = rows [0, colourStart[1])
-      const bool lastColourExact = !fullResidual && opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL &&
-                                   opts.nPostSweeps >= 1 && L0.nColours >= 2;
+      const bool lastColourExact = lastColourExactNow;
       if (lastColourExact) {
+        // r on [z0, z1) is an exact zero: not stored, the restriction that reads r knows the range (Level::rZeroFrom)
         const int z0 = multi ? L0.ifaceCount[0] : 0, z1 = L0.colourStart[1];
-        if (z1 > z0) devMemset(L0.r.p + z0, 0, (size_t)(z1 - z0) * sizeof(double));
         reduceRows<1>(L0.n - (z1 - z0), ResidualRowsFrom{z0, z1, R}, scalars.p);
-      } else
-      reduceRows<1>(L0.n, R, scalars.p);
+        L0.rZeroFrom = z0; L0.rZeroTo = z1 > z0 ? z1 : z0;
+      } else {
+        reduceRows<1>(L0.n, R, scalars.p);
+        L0.rZeroFrom = L0.rZeroTo = 0;
+      }
       if (multi) commAllreduceSum(scalars.p, 1);
       L0.rValid = true;
     }
   };
 #ifndef FVMGPU_HOSTSIM
-  if (!ctx().profiling && useGraphs) {
+  // A graph bakes in what the body does with the state it finds. The first cycle of a solve finds a FULL residual
+  // (residualNorm), every later one the residual of the previous cycle with its unstored zero range: the first cycle
+  // therefore runs eagerly and the graph is captured / replayed in the steady state only.
+  const bool steady = kind != 0 || !lastColourExactNow || (L0.rValid && L0.rZeroTo > L0.rZeroFrom) ||
+                      (multi ? L0.colourStart[1] <= L0.ifaceCount[0] : L0.colourStart[1] <= 0);
+  if (!ctx().profiling && useGraphs && steady) {
     if (!graphExec[kind]) {
       // flags at the start of the body must be what they are at the start of EVERY replay
       const bool xz = L0.xZero, rv = L0.rValid;

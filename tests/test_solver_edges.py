@@ -224,10 +224,13 @@ def test_jacobi_solver_is_bit_identical_to_the_reference_class(devlib):
                      R.solver_cfg(kind=5, nMaxIterations=20000, verbosity=1, relativeTolerance=1e-12))
     last = ref["text"].splitlines()[-1]
     assert it == int(last.split(":")[0]) == 1265
-    assert "%g" % r == last.split(":")[-1].strip(" ]")
+    ref_r = float(last.split(":")[-1].strip(" ]"))
     if "hostsim" in devlib.path:
+        assert "%g" % r == "%g" % ref_r
         assert np.array_equal(ds.get_field(X.FIELD_DELTA), ref["x"])
-    else:   # the device's row sums contract a*x+s into FMAs: same iterates to rounding, not to the bit
+    else:   # the device's row sums contract a*x+s into FMAs: same iterates to rounding, not to the bit -- and the
+        # last residual (1e-12 of the first) is itself made of rounding errors: same size, not the same digits
+        assert abs(r - ref_r) <= 1e-3 * ref_r
         assert np.abs(ds.get_field(X.FIELD_DELTA) - ref["x"]).max() <= 1e-12 * np.abs(ref["x"]).max()
     amg.close(); ds.close()
 
