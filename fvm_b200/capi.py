@@ -104,6 +104,8 @@ SIGNATURES = {
     "fvmgpu_amg_level_order": (C.c_int, [_vp, C.c_int, C.c_longlong, _ip, C.POINTER(C.c_int),
                                          np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")]),
     "fvmgpu_debug_set_aggregator": (C.c_int, [_vp, _vp]),
+    "fvmgpu_debug_tail_trace": (C.c_int, [C.c_int, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS"),
+                                          _ip, C.POINTER(C.c_int)]),
     "fvmgpu_amg_last_timing": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "fvmgpu_solver_history": (C.c_int, [_vp, C.c_int, _dp, C.POINTER(C.c_int)]),
     "fvmgpu_bcgstab_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
@@ -243,6 +245,14 @@ class Lib:
             out.append(dict(name=_demangle(nm), rows=int(rows[i]), launches=int(launches[i]), ms=float(ms[i]),
                             level=level))
         return out
+
+    def tail_trace(self, cap=8192):
+        """(times_ns, tags) of the last fused coarse-level kernel launch (needs FVMGPU_TAIL_TRACE=1)."""
+        t = np.zeros(cap, np.uint64)
+        g = np.zeros(cap, np.int32)
+        n = C.c_int(0)
+        self.call("fvmgpu_debug_tail_trace", cap, t, g, C.byref(n))
+        return t[:n.value].copy(), g[:n.value].copy()
 
     def set_aggregator(self, fn_ptr, user=None):
         """Verification hook (include/fvmgpu.h: fvmgpu_debug_set_aggregator): fn_ptr is the address of a C function

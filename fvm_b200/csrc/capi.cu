@@ -387,6 +387,12 @@ int fvmgpu_amg_level_order(fvmgpu_solver_t s, int level, long long cap, int* nat
   }
   API_END
 }
+int fvmgpu_debug_tail_trace(int cap, unsigned long long* times_ns, int* tags, int* n) {
+  API_BEGIN
+  const int k = tailTraceRead(cap, times_ns, tags);
+  if (n) *n = k;
+  API_END
+}
 int fvmgpu_debug_set_aggregator(fvmgpu_aggregate_fn fn, void* user) {
   API_BEGIN
   setDebugAggregator(fn, user);

@@ -115,11 +115,27 @@ struct SymEntriesKernel {  // entry k of row i -> (i, j) and (j, i); ghost / dia
 // before the launch); the CTA's thread 0 arrives and spins until the whole grid has arrived for
 // this generation. Cheaper than cooperative_groups' grid.sync() (~1.5 us vs ~3.5 us measured per
 // barrier step here); all CTAs are co-resident by construction (cooperative launch).
+// Phase trace of the fused V-cycle kernels (FVMGPU_TAIL_TRACE=1, a measurement aid): thread 0 of CTA 0 stamps the
+// global timer after every barrier together with a tag (level << 8 | kind); read with fvmgpu_debug_tail_trace.
+constexpr unsigned kTraceCap = 8192;
+__device__ unsigned long long* g_traceBuf = nullptr;   // 2 * kTraceCap: (time, tag) pairs
+__device__ unsigned g_traceCount = 0;
+__device__ __forceinline__ void traceStamp(int tag) {
+  if (g_traceBuf && blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned k = g_traceCount++;
+    if (k < kTraceCap) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      g_traceBuf[2 * k] = t;
+      g_traceBuf[2 * k + 1] = (unsigned long long)tag;
+    }
+  }
+}
 struct GridSync {
   unsigned* bar;
   __device__ __forceinline__ long long tid() const { return (long long)blockIdx.x * blockDim.x + threadIdx.x; }
   __device__ __forceinline__ long long stride() const { return (long long)gridDim.x * blockDim.x; }
-  __device__ __forceinline__ void sync() {
+  __device__ __forceinline__ void sync(int tag = 0) {
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
@@ -132,6 +148,7 @@ struct GridSync {
       __threadfence();  // as cooperative_groups does after its spin: nothing read after the barrier may be stale
     }
     __syncthreads();
+    traceStamp(tag);
   }
 };
 #endif
@@ -1505,13 +1522,12 @@ struct TailLevel {
   double* b; double* x; double* r;
   const int* ci; const int* memOff; const int* mem; const int* cpos;  // links to the next level (null on the last)
 };
-constexpr int kTailThreads = 512;  // default CTA size of the fused kernels (127 registers, no spills);
-                                   // a 1024-thread variant (64 registers, spills) exists for comparison: FVMGPU_FUSED_THREADS=1024
+constexpr int kTailThreads = 512;  // CTA size of the fused kernels (127 registers, no spills; 1024 threads = 64 registers spilled and lost)
 
 struct CtaSync {   // one CTA
   __device__ __forceinline__ long long tid() const { return threadIdx.x; }
   __device__ __forceinline__ long long stride() const { return blockDim.x; }
-  __device__ __forceinline__ void sync() const { __syncthreads(); }
+  __device__ __forceinline__ void sync(int tag = 0) const { __syncthreads(); traceStamp(tag); }
 };
 // init + sum_j a_rj x_j accumulated in entry order, exactly like GsRows / JacobiRows / ResidualRows
 __device__ __forceinline__ double tailRowAcc(const TailLevel& L, int r, const double* x, double init) {
@@ -1549,35 +1565,8 @@ __device__ __forceinline__ void prefetchRow(const TailLevel& L, int c, long long
     if (p < P.end) { P.col[k] = L.scol[p]; P.val[k] = L.sval[p]; }
   }
 }
-// The same row sum with the PROLONGATION applied on the fly (first forward half-sweep after the coarse correction has
-// come back): a column at or behind `from` -- a row of a colour this half-sweep has not relaxed yet -- reads
-// x + xc[ci], every other column reads the value the half-sweep has already stored. After the half-sweep every row
-// has been overwritten, so the corrected values never need to be stored at all: the separate prolongation pass (one
-// barrier phase and one dependent-load chain per level, in a regime where that is all a phase costs) disappears.
-// Same additions in the same order as "x += xc[ci], barrier, sweep": bit-identical.
-__device__ __forceinline__ double tailRowAccCorr(const TailLevel& L, int r, double init, int from, const double* xc,
-                                                bool fineZero) {
-  const int s = r >> 5;
-  const int end = L.sliceOff[s + 1];
-  double sum = init;
-  for (int p = L.sliceOff[s] + (r & 31); p < end; p += 32) {
-    const int j = L.scol[p];
-    double xv;
-    if (j >= from) {
-      const int cj = L.ci[j];
-      xv = fineZero ? 0.0 : L.x[j];   // fineZero: x is identically zero before the correction (nPreSweeps = 0)
-      if (cj >= 0) xv += xc[cj];
-    } else {
-      xv = L.x[j];
-    }
-    sum += L.sval[p] * xv;
-  }
-  return sum;
-}
-// xc != nullptr: the level's x still lacks the coarse correction xc[ci] (see tailRowAccCorr)
 template <class S>
-__device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& xZero, S& sy, const double* xc = nullptr,
-                           bool fineZero = false) {
+__device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& xZero, S& sy, int lt) {
   int lastColour = -1;
   const long long t0 = sy.tid(), st = sy.stride();
   if (smoother == FVMGPU_SMOOTHER_GAUSS_SEIDEL) {
@@ -1591,10 +1580,7 @@ __device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& 
       if (c == lastColour) continue;
       const int r1 = L.colourStart[c + 1];
       long long r = L.colourStart[c] + t0;
-      const bool corr = xc != nullptr && q < L.nColours;   // first forward half-sweep: prolongation on the fly
-      if (corr) {
-        for (; r < r1; r += st) L.x[r] = -tailRowAccCorr(L, (int)r, L.b[r], r1, xc, fineZero) / L.diag[r];
-      } else if (r < r1) {
+      if (r < r1) {
         // first row of the pass: use the prefetched pieces when they belong to it
         double sum, d;
         if (P.r == r) {
@@ -1622,7 +1608,7 @@ __device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& 
       int cn = -1;
       for (int q2 = q + 1; q2 < nPass; q2++) { const int c2 = colourOf(q2); if (c2 != c) { cn = c2; break; } }
       prefetchRow(L, cn, t0, P);
-      sy.sync();
+      sy.sync(lt | 0x10 | (c & 15));
     }
   } else {
     for (int sw = 0; sw < nSweeps; sw++) {
@@ -1630,7 +1616,7 @@ __device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& 
         const double* xo = half ? L.r : L.x;
         double* xn = half ? L.x : L.r;
         for (long long r = t0; r < L.n; r += st) xn[r] = -tailRowAcc(L, (int)r, xo, L.b[r]) / L.diag[r];
-        sy.sync();
+        sy.sync(lt | 0x20);
       }
       xZero = false;
     }
@@ -1644,13 +1630,13 @@ __device__ void stretchDown(const TailLevel* lv, int l0, int l1, int nPre, int s
     const TailLevel L = lv[l];
     const TailLevel C = lv[l + 1];
     bool xZero = true;
-    tailSweeps(L, nPre, smoother, xZero, sy);
+    tailSweeps(L, nPre, smoother, xZero, sy, l << 8);
     const double* src = L.b;
     if (!xZero) {  // r = b + A x
       for (long long r = t0; r < L.n; r += st) {
         L.r[r] = tailRowAcc(L, (int)r, L.x, L.b[r] + L.diag[r] * L.x[r]);
       }
-      sy.sync();
+      sy.sync((l << 8) | 2);
       src = L.r;
     }
     for (long long I = t0; I < C.n; I += st) {
@@ -1660,33 +1646,34 @@ __device__ void stretchDown(const TailLevel* lv, int l0, int l1, int nPre, int s
       C.b[rc] = s;
       C.x[rc] = 0.0;
     }
-    sy.sync();
+    sy.sync((l << 8) | 1);
   }
 }
 template <class S>
 __device__ void stretchBottom(const TailLevel* lv, int l, int nPre, int nPost, int smoother, S& sy) {
   const TailLevel L = lv[l];
   bool xZero = true;
-  tailSweeps(L, nPre, smoother, xZero, sy);
-  tailSweeps(L, nPost, smoother, xZero, sy);  // coarsest level: pre + post sweeps
+  tailSweeps(L, nPre, smoother, xZero, sy, l << 8);
+  tailSweeps(L, nPost, smoother, xZero, sy, l << 8);  // coarsest level: pre + post sweeps
 }
 // levels l1-1 down to l0: prolongation of the next level's correction, then post-sweeps
 template <class S>
-__device__ void stretchUp(const TailLevel* lv, int l0, int l1, int nPost, int smoother, bool fineZero, S& sy) {
+__device__ void stretchUp(const TailLevel* lv, int l0, int l1, int nPost, int smoother, S& sy) {
   const long long t0 = sy.tid(), st = sy.stride();
   for (int l = l1 - 1; l >= l0; l--) {
     const TailLevel L = lv[l];
     const TailLevel C = lv[l + 1];
-    const bool onTheFly = smoother == FVMGPU_SMOOTHER_GAUSS_SEIDEL && nPost >= 1;
-    if (!onTheFly) {
-      for (long long i = t0; i < L.n; i += st) {
-        const int c = L.ci[i];
-        if (c >= 0) L.x[i] += C.x[c];
-      }
-      sy.sync();
+    // (Applying the prolongation on the fly inside the first pass -- x_j + xc[ci[j]] per matrix entry, no separate
+    // phase -- was measured with the phase trace: the pass then costs 7-9 us instead of 0.8 us even on a level of 8
+    // rows, because its three dependent gathers per entry miss to DRAM one after the other, while this streaming
+    // phase costs 2 us and leaves the pass its prefetched operands.)
+    for (long long i = t0; i < L.n; i += st) {
+      const int c = L.ci[i];
+      if (c >= 0) L.x[i] += C.x[c];
     }
+    sy.sync((l << 8) | 3);
     bool xZero = false;
-    tailSweeps(L, nPost, smoother, xZero, sy, onTheFly ? C.x : nullptr, fineZero);
+    tailSweeps(L, nPost, smoother, xZero, sy, l << 8);
   }
 }
 // on entry: level 0 of the stretch has b set and x == 0
@@ -1696,7 +1683,7 @@ __global__ void __launch_bounds__(THREADS) k_tail_vcycle(const TailLevel* lv, in
   CtaSync sy;
   stretchDown(lv, 0, nLevels - 1, nPre, smoother, sy);
   stretchBottom(lv, nLevels - 1, nPre, nPost, smoother, sy);
-  stretchUp(lv, 0, nLevels - 1, nPost, smoother, nPre == 0, sy);
+  stretchUp(lv, 0, nLevels - 1, nPost, smoother, sy);
 }
 // levels [0, nGrid) by the whole grid, levels [nGrid, nLevels) by CTA 0 alone (they have <= kTailRows
 // rows: one CTA is enough and its barrier is __syncthreads())
@@ -1709,19 +1696,13 @@ __global__ void __launch_bounds__(THREADS) k_coop_vcycle(const TailLevel* lv, in
     CtaSync cs;
     stretchDown(lv, nGrid, nLevels - 1, nPre, smoother, cs);
     stretchBottom(lv, nLevels - 1, nPre, nPost, smoother, cs);
-    stretchUp(lv, nGrid, nLevels - 1, nPost, smoother, nPre == 0, cs);
+    stretchUp(lv, nGrid, nLevels - 1, nPost, smoother, cs);
   }
-  gs.sync();
-  stretchUp(lv, 0, nGrid, nPost, smoother, nPre == 0, gs);
+  gs.sync(0xff00);
+  stretchUp(lv, 0, nGrid, nPost, smoother, gs);
 }
 #endif
 
-#ifndef FVMGPU_HOSTSIM
-static int fusedThreads() {
-  const char* e = getenv("FVMGPU_FUSED_THREADS");
-  return (e && atoi(e) == 1024) ? 1024 : kTailThreads;
-}
-#endif
 
 void Amg::buildTail() {
   tailStart = -1;
@@ -1774,25 +1755,59 @@ void Amg::buildTail() {
 #endif
 }
 
+#ifndef FVMGPU_HOSTSIM
+static DBuf<unsigned long long>& traceStore() { static DBuf<unsigned long long> t; return t; }
+static bool tailTraceOn() {
+  static const bool on = getenv("FVMGPU_TAIL_TRACE") && atoi(getenv("FVMGPU_TAIL_TRACE")) != 0;
+  return on;
+}
+#endif
+// phase trace of the LAST fused V-cycle kernel launch (FVMGPU_TAIL_TRACE=1): (time in ns, tag) pairs
+int tailTraceRead(int cap, unsigned long long* times, int* tags) {
+#ifndef FVMGPU_HOSTSIM
+  if (!tailTraceOn() || !traceStore().p) return 0;
+  streamSync();
+  unsigned n = 0;
+  CUDA_CHECK(cudaMemcpyFromSymbol(&n, g_traceCount, sizeof(unsigned)));
+  if (n > kTraceCap) n = kTraceCap;
+  std::vector<unsigned long long> h = traceStore().toHost();
+  int k = 0;
+  for (; k < (int)n && k < cap; k++) { times[k] = h[(size_t)2 * k]; tags[k] = (int)h[(size_t)2 * k + 1]; }
+  return k;
+#else
+  (void)cap; (void)times; (void)tags;
+  return 0;
+#endif
+}
+
 void Amg::runTail() {
 #ifndef FVMGPU_HOSTSIM
   const TailLevel* lv = reinterpret_cast<const TailLevel*>(tailLevels.p);
   int cnt = tailCount, nPre = opts.nPreSweeps, nPost = opts.nPostSweeps, sm = opts.smootherType;
+  if (tailTraceOn()) {   // (not inside a graph capture: the trace mode is used with eager launches / profiling runs)
+    if (!traceStore().p) {
+      traceStore().alloc(2 * kTraceCap);
+      unsigned long long* p = traceStore().p;
+      CUDA_CHECK(cudaMemcpyToSymbolAsync(g_traceBuf, &p, sizeof(p), 0, cudaMemcpyHostToDevice, ctx().stream));
+    }
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(ctx().stream, &cs);
+    if (cs == cudaStreamCaptureStatusNone) {
+      const unsigned zero = 0;
+      CUDA_CHECK(cudaMemcpyToSymbolAsync(g_traceCount, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, ctx().stream));
+    }
+  }
   if (tailIsCoop) {
     ProfileScope prof("N6fvmgpu13k_coop_vcycleE", levels[tailStart]->n);
     int nGrid = tailGridLevels;
     unsigned* bar = coopBarrier.p;
     devMemset(bar, 0, sizeof(unsigned));
     void* args[] = {(void*)&lv, &cnt, &nGrid, &nPre, &nPost, &sm, &bar};
-    if (fusedThreads() == 1024)
-      CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coop_vcycle<1024>, dim3(ctx().smCount), dim3(1024), args, 0, ctx().stream));
-    else
-      CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coop_vcycle<kTailThreads>, dim3(ctx().smCount), dim3(kTailThreads), args, 0,
-                                             ctx().stream));
+    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coop_vcycle<kTailThreads>, dim3(ctx().smCount), dim3(kTailThreads), args, 0,
+                                           ctx().stream));
   } else {
     ProfileScope prof("N6fvmgpu13k_tail_vcycleE", levels[tailStart]->n);
-    if (fusedThreads() == 1024) k_tail_vcycle<1024><<<1, 1024, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
-    else k_tail_vcycle<kTailThreads><<<1, kTailThreads, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
+    k_tail_vcycle<kTailThreads><<<1, kTailThreads, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
     CUDA_CHECK(cudaGetLastError());
   }
   ctx().launches++;

@@ -135,6 +135,7 @@ struct Amg {
 };
 
 void setDebugAggregator(fvmgpu_aggregate_fn fn, void* user);  // solver.cu
+int tailTraceRead(int cap, unsigned long long* times, int* tags);
 
 // mesh.cu / assemble.cu entry points used by capi.cu
 Mesh* meshCreate(int dim, int nSelf, int nTotal, int nFaces, const int* faceCells, const int* ccRow,

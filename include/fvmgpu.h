@@ -214,6 +214,11 @@ typedef int (*fvmgpu_aggregate_fn)(void* user, int nRows, const int* row, const 
                                    const double* offdiag, const int* isBoundary, int groupSize,
                                    double weightRatioThreshold, int* coarseIndex);
 int fvmgpu_debug_set_aggregator(fvmgpu_aggregate_fn fn, void* user);
+/* Measurement aid: with FVMGPU_TAIL_TRACE=1 in the environment the fused coarse-level V-cycle kernel stamps the GPU's
+ * global timer after each of its barrier phases; this returns the stamps of its LAST launch (ns) with their tags
+ * (level within the fused stretch << 8 | phase kind: 1 restriction, 2 residual, 3 prolongation, 0x10 | colour a
+ * Gauss-Seidel pass, 0x20 a Jacobi pass). *n = entries written. */
+int fvmgpu_debug_tail_trace(int cap, unsigned long long* times_ns, int* tags, int* n);
 /* host wall clock of the last fvmgpu_amg_solve, split into the hierarchy build (0 when the hierarchy
  * was reused) and the cycle loop, in milliseconds */
 int fvmgpu_amg_last_timing(fvmgpu_solver_t s, double* setup_ms, double* cycles_ms);

@@ -260,7 +260,7 @@ def test_hierarchy_is_rebuilt_when_the_matrix_changes(devlib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["coop512", "coop1024", "tail_only"])
+@pytest.mark.parametrize("variant", ["coop", "tail_only"])
 def test_fused_vcycle_kernels_are_bit_identical_to_per_level_launches(gpu_lib, variant):
     """k_coop_vcycle (cooperative grid, levels <= 1.2 M rows) and k_tail_vcycle (one CTA, levels <= 4096
     rows) run the same operations in the same order as the per-level launches they replace."""
@@ -273,10 +273,10 @@ def test_fused_vcycle_kernels_are_bit_identical_to_per_level_launches(gpu_lib, v
                       raw.group_count, raw.group_id, raw.group_kind)
     dm.set_geometry(geo["face_area"], geo["face_area_mag"], geo["cell_centroid"], geo["cell_volume"],
                     ib_type=np.full(raw.n_total, -1, np.int32))
-    env = {"coop512": {}, "coop1024": {"FVMGPU_FUSED_THREADS": "1024"}, "tail_only": {"FVMGPU_COOP_ROWS": "0"}}[variant]
+    env = {"coop": {}, "tail_only": {"FVMGPU_COOP_ROWS": "0"}}[variant]
     out = []
     for fused in (True, False):
-        for k in ("FVMGPU_NO_FUSED", "FVMGPU_FUSED_THREADS", "FVMGPU_COOP_ROWS"):
+        for k in ("FVMGPU_NO_FUSED", "FVMGPU_COOP_ROWS"):
             os.environ.pop(k, None)
         if fused:
             os.environ.update(env)
@@ -295,7 +295,7 @@ def test_fused_vcycle_kernels_are_bit_identical_to_per_level_launches(gpu_lib, v
         r0, r, it = amg.solve(ds)
         out.append((ds.get_field(X.FIELD_DELTA), r, amg.history()))
         amg.close(); ds.close()
-    for k in ("FVMGPU_NO_FUSED", "FVMGPU_FUSED_THREADS", "FVMGPU_COOP_ROWS"):
+    for k in ("FVMGPU_NO_FUSED", "FVMGPU_COOP_ROWS"):
         os.environ.pop(k, None)
     assert np.array_equal(out[0][0], out[1][0]) and out[0][1] == out[1][1]
     assert np.array_equal(out[0][2], out[1][2])
