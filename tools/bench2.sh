@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage: tools/bench2.sh NGPU TAG [ENV=VAL ...] -- runs bench.py on NGPU GPUs with extra environment, prints a summary
 N=$1; TAG=$2; shift 2
-env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps ${STEPS:-2} --warmup 1 --no-cpu-baseline > gpurun_out/r2_bench_${N}gpu_$TAG.json 2> gpurun_out/r2_bench_${N}gpu_$TAG.err || tail -5 gpurun_out/r2_bench_${N}gpu_$TAG.err
+env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps ${STEPS:-2} --warmup 1 --no-cpu-baseline $EXTRA > gpurun_out/r2_bench_${N}gpu_$TAG.json 2> gpurun_out/r2_bench_${N}gpu_$TAG.err || tail -5 gpurun_out/r2_bench_${N}gpu_$TAG.err
 python - <<PY
 import json
 try:
