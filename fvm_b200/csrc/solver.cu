@@ -414,6 +414,62 @@ struct BcgUpdateP {  // p = (p - omega v) * beta + r,  beta = (rho/rhoPrev) * (a
   }
 };
 struct CopyKernel { const double* a; double* b; FVM_DEV void operator()(long long i) const { b[i] = a[i]; } };
+// ---- BiCGStab with every scalar on the device (Amg::bcgstab). Scalar slots of one iteration:
+//   S[0] rho of the previous iteration   S[2] / S[3] alpha = rho / (rTilda . v)   S[4] / S[5] omega = t.r / t.t
+//   S[6] |r|_1 after the alpha step      S[8] rho = r . rTilda of this iteration   S[9] |r|_1 after the omega step
+//   S[10] r . rTilda after the omega step (the next iteration's rho)
+struct BcgDirection {  // p = (p - omega v) * beta + r, beta = (rho / rhoPrev) * (alpha / omega)   (F/BCGStab.cpp:74-80)
+  const double* S; const double* v; const double* r; double* p;
+  FVM_DEV void operator()(long long i) const {
+    const double alpha = S[2] / S[3], omega = S[4] / S[5];
+    const double beta = (S[8] / S[0]) * (alpha / omega);
+    double t = p[i];
+    t -= omega * v[i];
+    t *= beta;
+    t += r[i];
+    p[i] = t;
+  }
+};
+struct MultiplyDotRows {  // y = A x fused with the dot products the recurrence needs of it
+  MultiplyRows M; const double* w;  // out[0] = y . w, out[1] = y . y
+  FVM_DEV void operator()(long long i, double* o) const {
+    const int s = (int)i >> 5;
+    const int end = M.sliceOff[s + 1];
+    double v = M.diag[i] * M.x[i];
+    for (int p = M.sliceOff[s] + ((int)i & 31); p < end; p += 32) v += M.sval[p] * M.x[M.scol[p]];
+    M.y[i] = v;
+    o[0] = v * w[i];
+    o[1] = v * v;
+  }
+};
+struct BcgAlphaStep {  // x -= alpha pHat ; r -= alpha v ; |r|_1      alpha = S[8] / S[3]   (:97-101)
+  const double* S; const double* pHat; const double* v; double* x; double* r;
+  FVM_DEV void operator()(long long i, double* o) const {
+    const double alpha = S[8] / S[3];
+    x[i] -= alpha * pHat[i];
+    const double q = r[i] - alpha * v[i];
+    r[i] = q;
+    o[0] = fabs(q);
+  }
+};
+struct BcgOmegaStep {  // x -= omega sHat ; r -= omega t ; |r|_1 ; r . rTilda     omega = S[4] / S[5]   (:126-131)
+  const double* S; double absTol; const double* sHat; const double* t; const double* rTilda; double* x; double* r;
+  FVM_DEV void operator()(long long i, double* o) const {
+    double q = r[i];
+    if (!(S[6] < absTol)) {   // the reference leaves the loop after the alpha step in that case: nothing moves any more
+      const double omega = S[4] / S[5];
+      x[i] -= omega * sHat[i];
+      q -= omega * t[i];
+      r[i] = q;
+    }
+    o[0] = fabs(q);
+    o[1] = q * rTilda[i];
+  }
+};
+struct BcgRotate {  // end of an iteration: rho -> rhoPrev and the alpha numerator, the new rho in
+  double* S;
+  FVM_DEV void operator()(long long) const { S[2] = S[8]; S[0] = S[8]; S[8] = S[10]; }
+};
 
 // ================================================================= aggregation
 // weight of entry (i,j): |a_ij| / max(|a_ii|,|a_jj|)            F/CRMatrix.h:520-528
@@ -1236,6 +1292,7 @@ void Amg::cleanup() {
   nested.reset(); mergedSys.reset(); mergedLevel = -1; nestedLoaded = false;
   mergePlan.release();
   levels.clear();
+  krylov = KrylovVectors();
   builtFor = nullptr;
   builtVersion = 0;
 }
@@ -1985,6 +2042,42 @@ void Amg::dropGraphs() {
     if (graphExec[k]) { cudaGraphExecDestroy((cudaGraphExec_t)graphExec[k]); graphExec[k] = nullptr; }
   }
 #endif
+  dropIterationGraph();
+}
+void Amg::dropIterationGraph() {
+#ifndef FVMGPU_HOSTSIM
+  if (iterGraph) { cudaGraphExecDestroy((cudaGraphExec_t)iterGraph); iterGraph = nullptr; }
+#endif
+}
+// One Krylov iteration as a captured graph: the body issues the same launches with the same arguments every time
+// (all scalars are device resident), so it is captured at its first run and replayed afterwards.
+void Amg::runIterationGraph(const std::function<void()>& body, double absTol) {
+#ifndef FVMGPU_HOSTSIM
+  if (!ctx().profiling && useGraphs) {
+    const int key[5] = {opts.nPreSweeps, opts.nPostSweeps, opts.cycleType, opts.smootherType, precondKind};
+    if (iterGraph && (std::memcmp(key, iterGraphKey, sizeof(key)) != 0 || iterGraphAbsTol != absTol)) dropIterationGraph();
+    if (!iterGraph) {
+      cudaGraph_t g = nullptr;
+      const long long launchesBefore = ctx().launches;
+      CUDA_CHECK(cudaStreamBeginCapture(ctx().stream, cudaStreamCaptureModeThreadLocal));
+      try { body(); } catch (...) { cudaGraph_t dead = nullptr; cudaStreamEndCapture(ctx().stream, &dead); if (dead) cudaGraphDestroy(dead); throw; }
+      CUDA_CHECK(cudaStreamEndCapture(ctx().stream, &g));
+      iterGraphLaunches = ctx().launches - launchesBefore;
+      ctx().launches = launchesBefore;
+      cudaGraphExec_t ge = nullptr;
+      CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      iterGraph = ge;
+      std::memcpy(iterGraphKey, key, sizeof(key));
+      iterGraphAbsTol = absTol;
+    }
+    CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)iterGraph, ctx().stream));
+    ctx().launches += iterGraphLaunches;
+    return;
+  }
+#endif
+  (void)absTol;
+  body();
 }
 
 // kind 0: solve loop body  (cycle on the current x, then r = b + A x and |r|_1 -> scalars[0])
@@ -2129,8 +2222,26 @@ void Amg::precondition(const double* rhsPerm, double* outPerm) {
   copyD2D(outPerm, L0.x.p, ((size_t)L0.n + L0.nGhost) * sizeof(double));
 }
 
-// BCGStab::solve, F/BCGStab.cpp:26-170 (all vectors in level-0 numbering; vectors that are
-// multiplied by A carry the level's ghost slots, dots are all-reduced across ranks)
+// One preconditioner application WITHOUT copies: level 0's right-hand side pointer is swapped for `rhs` while the
+// cycle is issued (eagerly or into a stream capture), the result stays in level 0's x (ghost slots refreshed).
+void Amg::cycleOn(double* rhs) {
+  Level& L0 = *levels[0];
+  std::swap(L0.b.p, rhs);
+  try {
+    // with nPreSweeps = 0 and a Gauss-Seidel post-sweep every x value is assigned before it is read (CorrectRows)
+    const bool assigned = opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL && opts.nPreSweeps == 0 &&
+                          opts.nPostSweeps >= 1 && opts.cycleType == FVMGPU_CYCLE_V && levels.size() > 1;
+    if (!assigned) L0.x.zero();
+    L0.xZero = true; L0.rValid = false;
+    cycle(opts.cycleType, 0);
+  } catch (...) { std::swap(L0.b.p, rhs); throw; }
+  std::swap(L0.b.p, rhs);
+}
+
+// BCGStab::solve, F/BCGStab.cpp:26-170. All vectors in level-0 numbering and kept with the solver between calls;
+// every scalar of the recurrence stays on the device, the dot products ride on the kernels that produce their
+// operands, and a whole iteration -- two preconditioner cycles, two SpMVs, the vector updates, the all-reduces --
+// is ONE captured graph: per iteration the host launches it and reads two norms.
 void Amg::bcgstab(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0Out,
                   double* rnormOut, int* itersOut) {
   requireReady();
@@ -2139,63 +2250,76 @@ void Amg::bcgstab(System* sys, int nMaxIterations, double relTol, double absTol,
   Level& L0 = *levels[0];
   const int n = L0.n;
   const size_t ng = (size_t)L0.nGhost;
-  DBuf<double> x(n + ng), bOrig(n), r(n), rTilda(n), p(n), pHat(n + ng), v(n), t(n);
-  parallelFor(n, PermGatherKernel{perm0.p, sys->b.p, bOrig.p});
-  parallelFor(n, PermGatherKernel{perm0.p, sys->delta.p, x.p});
-  if (ng) {
-    copyD2D(x.p + n, sys->delta.p + n, ng * sizeof(double));
-    exchange(L0, x.p);
+  KrylovVectors& K = krylov;
+  if (K.n != n || K.ng != ng) {
+    K.x.alloc(n + ng); K.bOrig.alloc(n); K.r.alloc(n); K.rTilda.alloc(n); K.p.alloc(n); K.v.alloc(n); K.t.alloc(n);
+    K.hat.alloc(n + ng);
+    K.n = n; K.ng = ng;
+    dropIterationGraph();
   }
-  auto A = [&](const double* xin) {
-    return MultiplyRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, xin, nullptr};
-  };
+  parallelFor(n, PermGatherKernel{perm0.p, sys->b.p, K.bOrig.p});
+  parallelFor(n, PermGatherKernel{perm0.p, sys->delta.p, K.x.p});
+  if (ng) {
+    copyD2D(K.x.p + n, sys->delta.p + n, ng * sizeof(double));
+    exchange(L0, K.x.p);
+  }
   auto allreduce = [&](double* ptr, int cnt) { if (multi) commAllreduceSum(ptr, cnt); };
-  // r = b + A x ; rNorm0
-  reduceRows<1>(n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, bOrig.p, x.p, r.p}, scalars.p + 8);
-  allreduce(scalars.p + 8, 1);
+  double* S = scalars.p;
+  // r = b + A x ; rNorm0 ; rTilda = r ; rho = r . rTilda
+  reduceRows<1>(n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, K.bOrig.p, K.x.p, K.r.p}, S + 12);
+  allreduce(S + 12, 1);
+  copyD2D(K.rTilda.p, K.r.p, (size_t)n * sizeof(double));
+  reduceRows<1>(n, Dot1Rows{K.r.p, K.rTilda.p}, S + 8);
+  allreduce(S + 8, 1);
   double rNorm0;
-  copyD2H(&rNorm0, scalars.p + 8, sizeof(double));
+  copyD2H(&rNorm0, S + 12, sizeof(double));
   history.push_back(rNorm0);
-  copyD2D(rTilda.p, r.p, (size_t)n * sizeof(double));
-  double* S = scalars.p;  // S[0]=rho S[1]=rhoPrev S[2]=alphaNum(rho) S[3]=alphaDen(rtv) S[4]=tdotr S[5]=tdott
+  // first direction = r: p = v = 0 and neutral scalars make BcgDirection produce exactly r
+  K.p.zero(); K.v.zero();
+  { const double one[6] = {1, 1, 1, 1, 1, 1}; copyH2D(S, one, sizeof(one)); }
+  const bool ilu = precondKind == 1;
+  if (ilu) {   // everything that allocates or synchronises happens before an iteration can be captured
+    iluFor(sys);
+    const size_t nt = (size_t)sys->nTotal;
+    if (natIn.n < nt) { natIn.alloc(nt); natOut.alloc(nt); natIn.zero(); natOut.zero(); }
+  }
+  auto iteration = [&]() {
+    parallelFor(n, BcgDirection{S, K.v.p, K.r.p, K.p.p});
+    const double* hat;                                                 // pHat = M(p), ghost slots in step
+    if (ilu) { precondition(K.p.p, K.hat.p); hat = K.hat.p; } else { cycleOn(K.p.p); hat = L0.x.p; }
+    reduceRows<2>(n, MultiplyDotRows{MultiplyRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, hat, K.v.p}, K.rTilda.p}, S + 3);
+    // (slot 3 = rTilda . v, slot 4 is overwritten below)
+    allreduce(S + 3, 1);
+    reduceRows<1>(n, BcgAlphaStep{S, hat, K.v.p, K.x.p, K.r.p}, S + 6);
+    allreduce(S + 6, 1);
+    if (ilu) { precondition(K.r.p, K.hat.p); hat = K.hat.p; } else { cycleOn(K.r.p); hat = L0.x.p; }   // sHat = M(r)
+    reduceRows<2>(n, MultiplyDotRows{MultiplyRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, hat, K.t.p}, K.r.p}, S + 4);
+    allreduce(S + 4, 2);                                               // (t . r, t . t)
+    reduceRows<2>(n, BcgOmegaStep{S, absTol, hat, K.t.p, K.rTilda.p, K.x.p, K.r.p}, S + 9);
+    allreduce(S + 9, 2);                                               // (|r|_1, r . rTilda)
+    parallelFor(1, BcgRotate{S});
+  };
   double rNorm = rNorm0;
   int iters = 0;
-  bool haveP = false;
   for (int i = 0; i < nMaxIterations; i++) {
     iters++;
-    copyD2D(S + 1, S + 0, sizeof(double));                       // rhoPrev = rho
-    reduceRows<1>(n, Dot1Rows{r.p, rTilda.p}, S + 0);            // rho = r . rTilda
-    allreduce(S + 0, 1);
-    if (!haveP) { copyD2D(p.p, r.p, (size_t)n * sizeof(double)); haveP = true; }
-    else parallelFor(n, BcgUpdateP{S, v.p, r.p, p.p});
-    precondition(p.p, pHat.p);                                   // pHat = M(p), ghosts synced
-    { MultiplyRows m = A(pHat.p); m.y = v.p; parallelFor(n, m); }  // v = A pHat
-    copyD2D(S + 2, S + 0, sizeof(double));                       // alpha = rho / (rTilda . v)
-    reduceRows<1>(n, Dot1Rows{rTilda.p, v.p}, S + 3);
-    allreduce(S + 3, 1);
-    parallelFor(n, MsaxpyScalarPtr{S + 2, S + 3, pHat.p, x.p});  // x -= alpha pHat
-    reduceRows<1>(n, MsaxpyScalarPtr{S + 2, S + 3, v.p, r.p}, S + 6);  // r -= alpha v ; |r|_1
-    allreduce(S + 6, 1);
-    copyD2H(&rNorm, S + 6, sizeof(double));
-    if (rNorm < absTol) break;
-    precondition(r.p, pHat.p);                                   // sHat = M(r)
-    { MultiplyRows m = A(pHat.p); m.y = t.p; parallelFor(n, m); }  // t = A sHat
-    reduceRows<2>(n, Dot2Rows{t.p, r.p}, S + 4);                 // (t.r, t.t)
-    allreduce(S + 4, 2);
-    parallelFor(n, MsaxpyScalarPtr{S + 4, S + 5, pHat.p, x.p});  // x -= omega sHat
-    reduceRows<1>(n, MsaxpyScalarPtr{S + 4, S + 5, t.p, r.p}, S + 6);  // r -= omega t ; |r|_1
-    allreduce(S + 6, 1);
-    copyD2H(&rNorm, S + 6, sizeof(double));
+    runIterationGraph(iteration, absTol);
+    double h[4];   // S[6] .. S[9]
+    copyD2H(h, S + 6, sizeof(h));
+    if (h[0] < absTol) { rNorm = h[0]; break; }                        // left after the alpha step (:103-106)
+    rNorm = h[3];
     history.push_back(rNorm);
     if (rNorm < absTol || rNorm / rNorm0 < relTol) break;
   }
   totalIterations += iters;
-  parallelFor(n, PermScatterKernel{perm0.p, x.p, sys->delta.p});
+  parallelFor(n, PermScatterKernel{perm0.p, K.x.p, sys->delta.p});
   if (ng) {  // leave the ghosts of delta synced
-    copyD2D(L0.x.p, x.p, (size_t)n * sizeof(double));
+    copyD2D(L0.x.p, K.x.p, (size_t)n * sizeof(double));
     exchange(L0, L0.x.p);
     copyD2D(sys->delta.p + n, L0.x.p + n, ng * sizeof(double));
   }
+  streamSync();
+  if (multi) peerCheck();
   if (rnorm0Out) *rnorm0Out = rNorm0;
   if (rnormOut) *rnormOut = rNorm;
   if (itersOut) *itersOut = iters;

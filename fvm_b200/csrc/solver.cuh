@@ -2,6 +2,8 @@
 #pragma once
 #include "structs.cuh"
 
+#include <functional>
+
 namespace fvmgpu {
 
 struct Level {
@@ -76,6 +78,18 @@ struct Amg {
   DBuf<int> natHint;
   void* graphExec[2] = {nullptr, nullptr};
   long long graphLaunches[2] = {0, 0};
+  // Krylov work vectors (level-0 numbering), kept between solves, and the captured graph of one BiCGStab iteration
+  struct KrylovVectors {
+    int n = -1; size_t ng = 0;
+    DBuf<double> x, bOrig, r, rTilda, p, v, t, hat;
+  } krylov;
+  void* iterGraph = nullptr;
+  long long iterGraphLaunches = 0;
+  double iterGraphAbsTol = 0;
+  int iterGraphKey[5] = {-1, -1, -1, -1, -1};   // nPre, nPost, cycleType, smootherType, precondKind
+  void cycleOn(double* rhs);
+  void runIterationGraph(const std::function<void()>& body, double absTol);
+  void dropIterationGraph();
 
   // multi-GPU: below `mergeRows` global rows the level is all-gathered and the rest of the cycle runs
   // replicated on every rank with the single-GPU code (the reference's LinearSystemMerger idea,
