@@ -62,6 +62,9 @@ def parse():
     # `python -m torch.distributed.run ... bench.py --n 128` as an ambiguous --nnodes/--nproc-per-node)
     p.add_argument("--size", dest="n", type=int, default=0,
                    help="cells per side of the per-GPU hex block (default 256: 256^3 cells per GPU)")
+    p.add_argument("--workload", choices=("thermal", "cavity", "electric-tet"), default="thermal",
+                   help="thermal: the headline (BASELINE configs[1] / [3]); cavity: configs[2], FlowModel SIMPLE on a 2048^2 quad "
+                        "mesh; electric-tet: configs[4], ElectricModel on a tet box partitioned over the GPUs (bench_workloads.py)")
     p.add_argument("--mesh", choices=("hex", "tet"), default="hex",
                    help="tet: the same box cut into 6 jittered tetrahedra per hex (unstructured numbering of the "
                         "coarse levels; single GPU; not the headline workload)")
@@ -138,6 +141,7 @@ def global_dims(n, world):
 
 KRYLOV = False
 MESH = "hex"
+WORKLOAD = "thermal"
 
 
 def build_case(n, lib, rank=0, world=1):
@@ -565,6 +569,15 @@ def _ref_worker(n, steps):
     """One single-rank run of the reference C++ (oracle/_ref) or, if absent, of the C port."""
     from fvm_b200 import meshgen as G
     from oracle import refapi
+    if WORKLOAD == "cavity":
+        import bench_workloads as W
+        dt, ref = W._cavity_reference(n, 0.01, max(steps, 1), tight=False)
+        return dict(kind="reference", cells=ref["n_cells"], runs=[dict(seconds=dt, cycles=-1)] * max(steps, 1))
+    if WORKLOAD == "electric-tet":
+        import bench_workloads as W
+        rraw = G.tet_mesh(n, n, n, lx=W.E_BOX, ly=W.E_BOX, lz=W.E_BOX)
+        dt, _ = W._electric_reference(rraw, max(steps, 1), 1e-8, iters=100, kind=1)
+        return dict(kind="reference", cells=rraw.n_cells, runs=[dict(seconds=dt, cycles=-1)] * max(steps, 1))
     raw = G.hex_mesh(n, n, n)
     out = []
     if refapi.available():
@@ -601,7 +614,7 @@ def _ref_worker(n, steps):
 def cpu_sample(n, threads, steps):
     """`threads` independent single-rank processes of the reference, each on its own n^3 mesh."""
     cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--_worker", "--ref-n", str(n),
-           "--steps", str(steps)] + (["--krylov"] if KRYLOV else [])
+           "--steps", str(steps), "--workload", WORKLOAD] + (["--krylov"] if KRYLOV else [])
     env = dict(os.environ)
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
@@ -632,7 +645,7 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     # bounded sample: the reference needs O(n) more cycles per doubling of the mesh (165 at 64^3, ~330 at
     # 128^3, ~700 at 256^3), so the sample is taken as large as a few minutes allow (128^3, <= 2 steps)
-    n = args.ref_n or 128
+    n = args.ref_n or {"thermal": 128, "cavity": 512, "electric-tet": 32}[WORKLOAD]
     for _ in range(min(args.warmup, 1)):
         cpu_sample(min(n, 32), threads, 1)
     steps = max(1, min(args.steps, 2))
@@ -640,9 +653,13 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": cpu["seconds_per_step"] * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "3D steady thermal diffusion on a structured hex mesh, k=1, T=400/300 on z=1/z=0, "
-                                  "AMG (V-cycle, GS, nPre 0 / nPost 1, group 2) to rel 1e-8, one outer iteration "
-                                  "per step; CPU arm: bounded sample " + cpu["sample"]},
+           "config": {"workload": {"thermal": "3D steady thermal diffusion on a structured hex mesh, k=1, T=400/300 on z=1/z=0, "
+                                              "AMG (V-cycle, GS, nPre 0 / nPost 1, group 2) to rel 1e-8, one outer iteration per step",
+                                   "cavity": "lid-driven cavity, FlowModel SIMPLE with the reference's default solvers, one SIMPLE "
+                                             "iteration per step",
+                                   "electric-tet": "ElectricModel electrostatics + drift / transient charge transport on jittered "
+                                                   "tets, BCGStab + AMG to rel 1e-8, one time step per step"}[WORKLOAD]
+                                  + "; CPU arm: bounded sample " + cpu["sample"]},
            "cpu_baseline": cpu, "gpu_launches": 0,
            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -652,9 +669,15 @@ if __name__ == "__main__":
     a = parse()
     KRYLOV = bool(a.krylov)
     MESH = a.mesh
+    WORKLOAD = a.workload
     if a._worker:
         print(json.dumps(_ref_worker(a.ref_n, a.steps)))
     elif a.impl == "reference":
         run_reference(a)
-    else:
+    elif a.workload == "thermal":
         run_ours(a)
+    else:
+        # the workload module imports THIS module by name: make `bench` resolve to the running script
+        sys.modules.setdefault("bench", sys.modules["__main__"])
+        import bench_workloads
+        {"cavity": bench_workloads.run_cavity, "electric-tet": bench_workloads.run_electric}[a.workload](a)

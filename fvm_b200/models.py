@@ -1116,6 +1116,7 @@ class ElectricModelA:
         self._options, self._constants = ElectricModelOptions(), ElectricModelConstants()
         self._pot, self._chg = {}, {}
         self._niters = 0
+        self._timing, self.timings = {}, []
         self._initialElectroStaticsNorm = None
         self._initialChargeTransportNorm = None
         for mesh in self.meshes:  # Impl ctor, F/ElectricModel_impl.h:71-110
@@ -1225,12 +1226,15 @@ class ElectricModelA:
                 ls.set_bc(fg.id, capi.BC_CONVECTIVE, [coeff, float(bc["specifiedPotential"])])
             else:
                 raise CException(bc.bcType + " not implemented for ElectricModel")
+        ls.lib.timer_start(1)
         ls.assemble(diffusion=1, convection=0, source=1, time_order=0, dt=0.0, underrelax=0.0, apply_bcs=1,
                     eliminate_boundary=1)
         solver = o.getElectroStaticsLinearSolver()
         rnorm = solver.solve(ls)
         solver.cleanup()
         ls.post_solve_update()
+        self._timing["electrostatics_ms"] = self._timing.get("electrostatics_ms", 0.0) + ls.lib.timer_stop(1)
+        self._timing["electrostatics_iterations"] = int(getattr(solver, "lastIterations", 0))
         f.potential[cells][:] = ls.get_field(capi.FIELD_X)
         bflux = ls.get_field(capi.FIELD_BFLUX)
         for fg in mesh.getBoundaryFaceGroups():
@@ -1269,12 +1273,14 @@ class ElectricModelA:
                 ls.set_field(capi.FIELD_X_N1, np.ascontiguousarray(f.chargeN1[cells][:, k]))
                 if order > 1:
                     ls.set_field(capi.FIELD_X_N2, np.ascontiguousarray(f.chargeN2[cells][:, k]))
+            ls.lib.timer_start(1)
             ls.assemble(diffusion=0, convection=1 if (o.drift_enable and k == n_trap) else 0, source=0,
                         time_order=order, dt=float(o["timeStep"]), underrelax=0.0, apply_bcs=1 if bcs_on else 0,
                         eliminate_boundary=1)
             norms[k] = solver.solve(ls)
             solver.cleanup()
             ls.post_solve_update()
+            self._timing["charge_ms"] = self._timing.get("charge_ms", 0.0) + ls.lib.timer_stop(1)
             f.charge[cells][:, k] = ls.get_field(capi.FIELD_X)
         return norms
 
@@ -1286,6 +1292,8 @@ class ElectricModelA:
             raise CException("ElectricModelA: one mesh per model in this release")
         mesh = self.meshes[0]
         flag1 = False
+        self._timing = {}          # device time (CUDA events) of assembly + solve + update per equation, this call
+        self.timings.append(self._timing)
         if o.electrostatics_enable:
             for _ in range(niter):
                 e = self._solve_electrostatics(mesh)

@@ -240,6 +240,74 @@ def hex_slab(nx, ny, nz, rank, nparts, lx=1.0, ly=1.0, lz=1.0, lib=None):
     return m
 
 
+def block_dims(nparts):
+    """(px, py, pz) with px * py * pz = nparts: prime factors dealt out to z, y, x in turn, largest first
+    (8 -> 2 x 2 x 2, 4 -> 1 x 2 x 2, 2 -> 1 x 1 x 2) -- what coordinate bisection gives on a uniform box."""
+    dims = [1, 1, 1]
+    f, n, fac = 2, int(nparts), []
+    while n > 1:
+        while n % f == 0:
+            fac.append(f); n //= f
+        f += 1
+    for k, q in enumerate(sorted(fac, reverse=True)):
+        dims[2 - k % 3] *= q
+    return tuple(dims)
+
+
+def assign_blocks(nx, ny, nz, nparts, cells_per_hex=1):
+    """Cell -> part for a lattice mesh of meshgen (hex_mesh: 1 cell per hex, tet_mesh: 6): part = block of the hex."""
+    px, py, pz = block_dims(nparts)
+    xb, yb, zb = [(np.arange(q + 1, dtype=np.int64) * n) // q for q, n in ((px, nx), (py, ny), (pz, nz))]
+    K, J, I = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    b = (np.searchsorted(xb, I.ravel(), side="right") - 1) + px * ((np.searchsorted(yb, J.ravel(), side="right") - 1)
+                                                                  + py * (np.searchsorted(zb, K.ravel(), side="right") - 1))
+    return np.repeat(b.astype(np.int32), cells_per_hex)
+
+
+def tet_block(nx, ny, nz, rank, nparts, lx=1.0, ly=1.0, lz=1.0, jitter=0.2, seed=42):
+    """Local mesh of block `rank` of meshgen.tet_mesh(nx, ny, nz, ...) cut into block_dims(nparts) blocks, built
+    from the block and one layer of hexes around it only -- never the global mesh (a 50 M-tet box is 8 x 6.3 M).
+    Identical (arrays, numbering, halo maps, geometry) to partition_mesh(tet_mesh(...), metrics, assign_blocks(...,
+    6), rank): global cell ids are lattice functions (6 * hex + tet), interior faces of the generator are ordered
+    by their (lower, higher) cell id, and a sub-box keeps that order -- so both sides of an interface list its
+    faces in the same order without ever seeing each other's mesh."""
+    px, py, pz = block_dims(nparts)
+    bx, by, bz = rank % px, (rank // px) % py, rank // (px * py)
+    xb, yb, zb = [(np.arange(q + 1, dtype=np.int64) * n) // q for q, n in ((px, nx), (py, ny), (pz, nz))]
+    lo = [max(int(xb[bx]) - 1, 0), max(int(yb[by]) - 1, 0), max(int(zb[bz]) - 1, 0)]
+    hi = [min(int(xb[bx + 1]) + 1, nx), min(int(yb[by + 1]) + 1, ny), min(int(zb[bz + 1]) + 1, nz)]
+    ex, ey, ez = hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]
+    hx, hy, hz = lx / nx, ly / ny, lz / nz
+    ext = meshgen.tet_mesh(ex, ey, ez, lx=ex * hx, ly=ey * hy, lz=ez * hz, jitter=0.0)
+    # node coordinates of the GLOBAL mesh (same linspace values, same jitter stream)
+    xs, ys, zs = np.linspace(0.0, lx, nx + 1), np.linspace(0.0, ly, ny + 1), np.linspace(0.0, lz, nz + 1)
+    KK, JJ, II = np.meshgrid(np.arange(ez + 1) + lo[2], np.arange(ey + 1) + lo[1], np.arange(ex + 1) + lo[0], indexing="ij")
+    II, JJ, KK = II.ravel(), JJ.ravel(), KK.ravel()
+    nodes = np.stack([xs[II], ys[JJ], zs[KK]], axis=1)
+    if jitter > 0:
+        rng = np.random.default_rng(seed)
+        d = rng.uniform(-jitter, jitter, size=((nx + 1) * (ny + 1) * (nz + 1), 3)) * [hx, hy, hz]
+        inner = (II > 0) & (II < nx) & (JJ > 0) & (JJ < ny) & (KK > 0) & (KK < nz)
+        gnode = II + (nx + 1) * (JJ + (ny + 1) * KK)
+        nodes[inner] += d[gnode[inner]]
+        del d
+    ext.nodes = nodes
+    # owner of every cell of the sub-box, global cell ids
+    K, J, I = np.meshgrid(np.arange(ez) + lo[2], np.arange(ey) + lo[1], np.arange(ex) + lo[0], indexing="ij")
+    I, J, K = I.ravel(), J.ravel(), K.ravel()
+    owner = ((np.searchsorted(xb, I, side="right") - 1) + px * ((np.searchsorted(yb, J, side="right") - 1)
+                                                                + py * (np.searchsorted(zb, K, side="right") - 1)))
+    part = np.repeat(owner.astype(np.int32), 6)
+    gid = np.repeat(6 * (I + nx * (J + ny * K.astype(np.int64))), 6) + np.tile(np.arange(6), len(I))
+    geo = meshgen.metrics(ext)
+    loc = partition_mesh(ext, geo, part, rank)
+    cg = loc.cell_global
+    loc.cell_global = np.where(cg < ext.n_cells, gid[np.minimum(cg, ext.n_cells - 1)], -1).astype(np.int64)
+    loc.nparts = int(nparts)
+    loc.nodes_ext = None
+    return loc
+
+
 class MeshPartitioner:
     """Mirror of `fvmparallel.MeshPartitioner(meshes, npart, etype)` (P/MeshPartitioner.i:12-27):
     `partition(); mesh(); meshList()` return THIS rank's meshes. The cell assignment is RCB (or

@@ -40,3 +40,32 @@ def test_bench_json_line_has_the_contract_keys(hostsim_lib, monkeypatch, mesh):
     assert oc["pass"] and oc["assembly_max_rel_diff"]["diag"] <= 1e-12 and oc["solution_rel_l2"] <= 1e-8, oc
     if mesh == "hex":
         assert d["parity"]["workload_vs_exact_solution_rel_l2"] < 1e-6
+
+
+@pytest.mark.parametrize("workload", ["cavity", "electric-tet"])
+def test_secondary_workloads_print_the_same_contract(hostsim_lib, monkeypatch, workload):
+    """BASELINE configs[2] (cavity, FlowModel SIMPLE) and configs[4] (ElectricModel on tets) through bench.py's workload
+    runners at toy size in the host simulator: contract keys, cpu_baseline from the reference's own model, and the
+    parity block green against oracle/_ref."""
+    import bench
+    import bench_workloads as W
+    from fvm_b200 import capi
+    from oracle import refapi
+    if not refapi.available():
+        pytest.skip("oracle/_ref not built")
+    monkeypatch.setattr(capi, "default_lib", lambda: hostsim_lib)
+    monkeypatch.setattr(bench, "WORKLOAD", workload)
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, n=20 if workload == "cavity" else 5, no_profile=False,
+                                 no_cpu_baseline=False, ref_n=12 if workload == "cavity" else 4,
+                                 parity_size=12 if workload == "cavity" else 4)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        (W.run_cavity if workload == "cavity" else W.run_electric)(args)
+    d = json.loads([l for l in buf.getvalue().splitlines() if l.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "parity", "cpu_baseline"):
+        assert k in d, k
+    assert d["metric"] == "fp64_cell_updates_per_s" and d["dtype"] == "f64" and d["gpu_launches"] > 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] > 0
+    assert d["parity"]["oracle_check"]["pass"], d["parity"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0

@@ -73,3 +73,30 @@ def test_mesh_partitioner_api():
     mp.partition()
     m = mp.meshList()[0]
     assert m.rank == 1 and m.n_cells == 24 and list(m.halo["peers"]) == [0]
+
+
+@pytest.mark.parametrize("dims,nparts", [((6, 5, 7), 8), ((5, 4, 6), 2), ((7, 5, 6), 3)])
+def test_tet_block_equals_the_partition_of_the_global_mesh(dims, nparts):
+    """partition.tet_block builds one block of the jittered tet box from the block and a layer of hexes around it;
+    it must be THE part `partition_mesh` cuts out of the global mesh -- same numbering, same halo maps (both sides
+    of an interface list its faces in the same order), bit-identical geometry."""
+    from fvm_b200 import meshgen as G, partition as P
+    nx, ny, nz = dims
+    raw = G.tet_mesh(nx, ny, nz, lx=1.3, ly=0.9, lz=1.1)
+    geo = G.metrics(raw)
+    part = P.assign_blocks(nx, ny, nz, nparts, 6)
+    assert sorted(set(part.tolist())) == list(range(nparts))
+    for r in range(nparts):
+        a = P.partition_mesh(raw, geo, part, r)
+        b = P.tet_block(nx, ny, nz, r, nparts, lx=1.3, ly=0.9, lz=1.1)
+        assert (a.n_cells, a.n_total, a.n_faces) == (b.n_cells, b.n_total, b.n_faces)
+        assert np.array_equal(a.face_cells, b.face_cells)
+        for k in ("group_id", "group_count", "group_kind", "group_offset"):
+            assert np.array_equal(a[k], b[k]), k
+        for k in a.halo:
+            assert np.array_equal(a.halo[k], b.halo[k]), k
+        for k in a.geometry:
+            assert np.array_equal(a.geometry[k], b.geometry[k]), k
+        assert np.array_equal(a.cell_global[:a.n_cells], b.cell_global[:b.n_cells])
+        gi = a.halo["gather_idx"]
+        assert np.array_equal(a.cell_global[gi], b.cell_global[gi])
