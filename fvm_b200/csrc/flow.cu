@@ -954,9 +954,10 @@ void flowDownloadMomentum(Flow* F, double* diag3, double* off, double* b3) {
 // LinearSolver::solve on the momentum system + postSolve + updateSolution + momAp (F/FlowModel_impl.h:744-768).
 // useBcgstab: BCGStab preconditioned by `solver` with its own iteration limit / tolerances.
 //
-// The reference solves ONE system whose unknowns are Vector<T,3>. Every reduction (norms, BCGStab's dot
-// products) is a Vector of per-component sums (F/Vector.h:189-199), so the three components run independent
-// recurrences -- but the convergence test is shared: `normRatio < relativeTolerance` compares the MAGNITUDE of
+// The reference solves ONE system whose unknowns are Vector<T,3>. Norms are Vectors of per-component sums
+// (F/Vector.h:189-199) while BCGStab's / CG's dot products are additionally summed over the components (reduceSum,
+// F/MultiFieldReduction.cpp:165-185: shared alpha / beta / omega, see Amg::bcgstabMulti). The stationary AMG cycles
+// act on every component separately -- but the convergence test is shared: `normRatio < relativeTolerance` compares the MAGNITUDE of
 // the vector of component ratios (Vector::operator<, F/Vector.h:169-172; zero components divide safely and
 // count 0). All components therefore take the same number of cycles / iterations N, the first one at which
 // |(r_x, r_y, r_z)|_2 < tol * |(r0_x, r0_y, r0_z)|_2 (r_k = 1-norm of component k's residual). Here the components
@@ -1038,14 +1039,18 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
   };
   int N = 0;
   bool coupledKrylov = false;
-  if (useBcgstab && den > 0 && !(den < abs * abs)) {
-    // the reference's BCGStab shares its scalars between the components (Amg::bcgstabMulti); that needs one
-    // diagonal for all three (always the case without symmetry planes)
+  // one diagonal for all three components (always the case without symmetry planes)? Then the system is ONE matrix
+  // with Vector<T,3> unknowns: the reference's BCGStab shares its scalars between the components
+  // (Amg::bcgstabMulti), and the AMG cycles run once for all components (Amg::solveMulti)
+  bool oneDiagonal = false;
+  const bool wantMultiRhs = !useBcgstab && !jacobi && solver->multiRhsSupported();
+  if ((useBcgstab || wantMultiRhs) && den > 0 && !(den < abs * abs)) {
     reduceRows<1>(m->nSelf, DiagTensorDiffRows{F->mDiag.p}, F->scal.p + 5);
     if (F->multi) commAllreduceSum(F->scal.p + 5, 1);
     double nd;
     copyD2H(&nd, F->scal.p + 5, sizeof(double));
-    coupledKrylov = nd == 0.0;
+    oneDiagonal = nd == 0.0;
+    coupledKrylov = useBcgstab && oneDiagonal;
   }
   if (useBcgstab == 4 && !coupledKrylov && den > 0 && !(den < abs * abs))
     fail("flow: CG on the momentum system needs one diagonal for the three components (no symmetry planes)");
@@ -1057,6 +1062,12 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
     if (useBcgstab == 4) solver->cgMulti(s, 3, F->mB.p, F->mDelta.p, bcgMaxIter, bcgRel, bcgAbs, r0v, rv, &N);
     else solver->bcgstabMulti(s, 3, F->mB.p, F->mDelta.p, bcgMaxIter, bcgRel, bcgAbs, r0v, rv, &N);
     solver->precondKind = keep;
+  } else if (wantMultiRhs && oneDiagonal && !F->multi) {
+    // every matrix entry is read once per pass for all components; a 2-D flow carries two of them
+    select(0);
+    const int nc = (m->dim == 2 && !(norms[2] > 0.0)) ? 2 : 3;
+    double r0v[3] = {0, 0, 0}, rv[3] = {0, 0, 0};
+    solver->solveMulti(s, nc, F->mB.p, F->mDelta.p, 3, limit + 1, rel, abs, r0v, rv, &N);
   } else if (den > 0 && !(den < abs * abs)) {
     while (N < limit) {
       N++;
@@ -1088,7 +1099,7 @@ void flowSolveMomentum(Flow* F, Amg* solver, int useBcgstab, int bcgMaxIter, dou
   }
   for (int k = 0; k < 3; k++) {
     if (rnorm0) rnorm0[k] = norms[k];
-    if (iters) iters[k] = (norms[k] > 0.0 || coupledKrylov) ? N : 0;
+    if (iters) iters[k] = (norms[k] > 0.0 || coupledKrylov) ? N : 0;   // (a zero component stays zero whichever path ran)
   }
   parallelFor(3LL * nt, AddRows{F->mDelta.p, F->V.p});   // ls.updateSolution: x += delta
   parallelFor(nt - m->nSelf, MomentumGhostRows{m->nSelf, m->row.p, m->col.p, s->isBoundary.p, F->mDiag.p, F->mOff.p,

@@ -964,11 +964,37 @@ static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, s
 }
 
 // Build level L from a CSR system in "natural" numbering; returns perm (natural -> level numbering).
+// `cache` (level 0 only): everything below that depends on the PATTERN alone -- colouring, row order, SELL slice
+// layout and column indices -- is kept with the solver and reused while the system's pattern stamp is the same: the
+// models re-assemble on one mesh every outer iteration, only the coefficients change.
 static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, const double* val,
                               const double* diag, bool dropGhost, DBuf<int>& perm, int nGhost = 0,
-                              bool splitIface = false, const int* ghostIsHalo = nullptr) {
+                              bool splitIface = false, const int* ghostIsHalo = nullptr, PatternCache* cache = nullptr,
+                              unsigned long long patternStamp = 0) {
   L.n = n;
   L.nGhost = dropGhost ? 0 : nGhost;
+  if (cache && cache->stamp == patternStamp && patternStamp != 0 && cache->n == n && cache->dropGhost == dropGhost &&
+      cache->splitIface == splitIface) {
+    L.nColours = cache->nColours;
+    L.colourStart = cache->colourStart;
+    L.ifaceCount = cache->ifaceCount;
+    L.nSlices = cache->nSlices;
+    L.nnzStored = cache->nnzStored;
+    L.nnzTrue = cache->nnzTrue;
+    perm.alloc(n); L.nat.alloc(n); L.sliceOff.alloc(L.nSlices + 1);
+    copyD2D(perm.p, cache->perm.p, (size_t)n * sizeof(int));
+    copyD2D(L.nat.p, cache->nat.p, (size_t)n * sizeof(int));
+    copyD2D(L.sliceOff.p, cache->sliceOff.p, ((size_t)L.nSlices + 1) * sizeof(int));
+    const long long total = L.nnzStored;
+    L.scol.alloc(total > 0 ? total : 1);
+    L.sval.alloc(total > 0 ? total : 1);
+    L.diag.alloc(n); L.b.alloc(n); L.x.alloc((size_t)n + L.nGhost); L.r.alloc((size_t)n + L.nGhost);
+    L.b.zero(); L.x.zero(); L.r.zero();
+    parallelFor(n, SellFillKernel{n, L.nat.p, perm.p, row, col, val, diag, dropGhost ? 1 : 0, L.sliceOff.p, L.scol.p,
+                                  L.sval.p, L.diag.p});
+    streamSync();
+    return;
+  }
   std::vector<int> counts;
   DBuf<int> colour;
   L.nColours = colourCsr(n, row, col, colour, counts);
@@ -1014,6 +1040,15 @@ static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, c
   DBuf<int> lenScan(n + 1);
   exclusiveScan(len.p, lenScan.p, n);
   L.nnzTrue = lenScan.hostAt(n);
+  if (cache && patternStamp != 0) {
+    cache->stamp = patternStamp; cache->n = n; cache->dropGhost = dropGhost; cache->splitIface = splitIface;
+    cache->nColours = L.nColours; cache->colourStart = L.colourStart; cache->ifaceCount = L.ifaceCount;
+    cache->nSlices = L.nSlices; cache->nnzStored = L.nnzStored; cache->nnzTrue = L.nnzTrue;
+    cache->perm.alloc(n); cache->nat.alloc(n); cache->sliceOff.alloc(L.nSlices + 1);
+    copyD2D(cache->perm.p, perm.p, (size_t)n * sizeof(int));
+    copyD2D(cache->nat.p, L.nat.p, (size_t)n * sizeof(int));
+    copyD2D(cache->sliceOff.p, L.sliceOff.p, ((size_t)L.nSlices + 1) * sizeof(int));
+  }
   streamSync();
 }
 
@@ -1292,6 +1327,7 @@ void Amg::cleanup() {
   nested.reset(); mergedSys.reset(); mergedLevel = -1; nestedLoaded = false;
   mergePlan.release();
   levels.clear();
+  multiNc = 0;
   krylov = KrylovVectors();
   builtFor = nullptr;
   builtVersion = 0;
@@ -1302,6 +1338,7 @@ void Amg::setup(System* sys) {
   dropGraphs();
   tailStart = -1;
   levels.clear();
+  multiNc = 0;
   nested.reset(); mergedSys.reset(); mergedLevel = -1; nestedLoaded = false;
   mergePlan.release();
   const int n = sys->nSelf;
@@ -1317,8 +1354,10 @@ void Amg::setup(System* sys) {
     for (int g : sys->mesh->haloGatherHost) mask[(size_t)g - n] = 1;
     ghostIsHalo.upload(mask.data(), mask.size());
   }
+  // (reference-order mode colours by wavefronts: no caching there; nested hierarchies are rebuilt with their system)
+  PatternCache* cache = (g_referenceOrder || natHint.p) ? nullptr : &cache0;
   buildLevelFromCsr(L0, n, sys->row, sys->col, sys->off.p, sys->diag.p, !multi, perm0, sys->nTotal - n, multi,
-                    ghostIsHalo.p);
+                    ghostIsHalo.p, cache, sys->patternVersion);
   if (natHint.p) {
     DBuf<int> natural(n);
     parallelFor(n, ComposeKernel{L0.nat.p, natHint.p, natural.p});
@@ -1571,14 +1610,46 @@ void Amg::joinExchange() {
 //   k_tail_vcycle   levels with <= kTailRows rows in ONE CTA, __syncthreads() barriers
 //   k_coop_vcycle   levels with <= coopRows rows in one COOPERATIVE grid (one CTA per SM),
 //                   grid.sync() barriers; it hands its last levels to the same code path
+// ---- values a row carries: one double (CRMatrix<T,T,T>) or NC of them sharing one matrix (the momentum system
+// CRMatrix<DiagonalTensor<T,3>,T,Vector<T,3>> with equal diagonal components, F/FlowModel_impl.h:536: scalar
+// off-diagonal, Vector unknowns -- every kernel below reads a matrix entry ONCE for all components)
+template <int NC>
+struct VecN { double v[NC]; };
+template <> struct alignas(16) VecN<2> { double v[2]; };
+FVM_DEV void vset0(double& a) { a = 0.0; }
+FVM_DEV void vaxpy(double& s, double a, double x) { s += a * x; }          // s += a x
+FVM_DEV void vadd(double& s, double x) { s += x; }
+FVM_DEV double vnegdiv(double s, double d) { return -s / d; }
+FVM_DEV double vabs1(double s, int) { return fabs(s); }
+template <int NC> FVM_DEV void vset0(VecN<NC>& a) {
+#pragma unroll
+  for (int k = 0; k < NC; k++) a.v[k] = 0.0;
+}
+template <int NC> FVM_DEV void vaxpy(VecN<NC>& s, double a, const VecN<NC>& x) {
+#pragma unroll
+  for (int k = 0; k < NC; k++) s.v[k] += a * x.v[k];
+}
+template <int NC> FVM_DEV void vadd(VecN<NC>& s, const VecN<NC>& x) {
+#pragma unroll
+  for (int k = 0; k < NC; k++) s.v[k] += x.v[k];
+}
+template <int NC> FVM_DEV VecN<NC> vnegdiv(const VecN<NC>& s, double d) {
+  VecN<NC> o;
+#pragma unroll
+  for (int k = 0; k < NC; k++) o.v[k] = -s.v[k] / d;
+  return o;
+}
+
 #ifndef FVMGPU_HOSTSIM
-struct TailLevel {
+template <class V>
+struct TailLevelT {
   int n, nColours;
   const int* colourStart;  // device, nColours+1
   const int* sliceOff; const int* scol; const double* sval; const double* diag;
-  double* b; double* x; double* r;
+  V* b; V* x; V* r;
   const int* ci; const int* memOff; const int* mem; const int* cpos;  // links to the next level (null on the last)
 };
+typedef TailLevelT<double> TailLevel;
 constexpr int kTailThreads = 512;  // CTA size of the fused kernels (127 registers, no spills; 1024 threads = 64 registers spilled and lost)
 
 struct CtaSync {   // one CTA
@@ -1587,25 +1658,28 @@ struct CtaSync {   // one CTA
   __device__ __forceinline__ void sync(int tag = 0) const { __syncthreads(); traceStamp(tag); }
 };
 // init + sum_j a_rj x_j accumulated in entry order, exactly like GsRows / JacobiRows / ResidualRows
-__device__ __forceinline__ double tailRowAcc(const TailLevel& L, int r, const double* x, double init) {
+template <class V>
+__device__ __forceinline__ V tailRowAcc(const TailLevelT<V>& L, int r, const V* x, V init) {
   const int s = r >> 5;
   const int end = L.sliceOff[s + 1];
-  double sum = init;
-  for (int p = L.sliceOff[s] + (r & 31); p < end; p += 32) sum += L.sval[p] * x[L.scol[p]];
+  V sum = init;
+  for (int p = L.sliceOff[s] + (r & 31); p < end; p += 32) vaxpy(sum, L.sval[p], x[L.scol[p]]);
   return sum;
 }
 // Everything a colour pass needs of its FIRST row except the x values: loaded BEFORE the barrier that
 // ends the previous pass (the matrix, b and diag do not change during a cycle), so that after the
 // barrier only the x gathers are left on the critical path (one dependent load instead of three).
 constexpr int kPrefetch = 6;
+template <class V>
 struct RowPrefetch {
   long long r;       // row, -1 = none
   int beg, end;      // SELL element range of the row (stride 32)
-  double b, d;
+  V b; double d;
   int col[kPrefetch];
   double val[kPrefetch];
 };
-__device__ __forceinline__ void prefetchRow(const TailLevel& L, int c, long long t0, RowPrefetch& P) {
+template <class V>
+__device__ __forceinline__ void prefetchRow(const TailLevelT<V>& L, int c, long long t0, RowPrefetch<V>& P) {
   P.r = -1;
   if (c < 0) return;
   const long long r = L.colourStart[c] + t0;
@@ -1622,15 +1696,15 @@ __device__ __forceinline__ void prefetchRow(const TailLevel& L, int c, long long
     if (p < P.end) { P.col[k] = L.scol[p]; P.val[k] = L.sval[p]; }
   }
 }
-template <class S>
-__device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& xZero, S& sy, int lt) {
+template <class V, class S>
+__device__ void tailSweeps(const TailLevelT<V>& L, int nSweeps, int smoother, bool& xZero, S& sy, int lt) {
   int lastColour = -1;
   const long long t0 = sy.tid(), st = sy.stride();
   if (smoother == FVMGPU_SMOOTHER_GAUSS_SEIDEL) {
     // the colour sequence of all sweeps (a pass that would repeat the previous colour is skipped)
     const int nPass = 2 * L.nColours * nSweeps;
     auto colourOf = [&](int q) { const int pass = q % (2 * L.nColours); return pass < L.nColours ? pass : 2 * L.nColours - 1 - pass; };
-    RowPrefetch P;
+    RowPrefetch<V> P;
     P.r = -1;
     for (int q = 0; q < nPass; q++) {
       const int c = colourOf(q);
@@ -1639,24 +1713,24 @@ __device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& 
       long long r = L.colourStart[c] + t0;
       if (r < r1) {
         // first row of the pass: use the prefetched pieces when they belong to it
-        double sum, d;
+        V sum; double d;
         if (P.r == r) {
           sum = P.b; d = P.d;
           if (!xZero) {
 #pragma unroll
             for (int k = 0; k < kPrefetch; k++)
-              if (P.beg + 32 * k < P.end) sum += P.val[k] * L.x[P.col[k]];
-            for (int p = P.beg + 32 * kPrefetch; p < P.end; p += 32) sum += L.sval[p] * L.x[L.scol[p]];
+              if (P.beg + 32 * k < P.end) vaxpy(sum, P.val[k], L.x[P.col[k]]);
+            for (int p = P.beg + 32 * kPrefetch; p < P.end; p += 32) vaxpy(sum, L.sval[p], L.x[L.scol[p]]);
           }
         } else {
           sum = L.b[r]; d = L.diag[r];
           if (!xZero) sum = tailRowAcc(L, (int)r, L.x, sum);
         }
-        L.x[r] = -sum / d;
+        L.x[r] = vnegdiv(sum, d);
         for (r += st; r < r1; r += st) {
-          double s2 = L.b[r];
+          V s2 = L.b[r];
           if (!xZero) s2 = tailRowAcc(L, (int)r, L.x, s2);
-          L.x[r] = -s2 / L.diag[r];
+          L.x[r] = vnegdiv(s2, L.diag[r]);
         }
       }
       xZero = false;
@@ -1670,9 +1744,9 @@ __device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& 
   } else {
     for (int sw = 0; sw < nSweeps; sw++) {
       for (int half = 0; half < 2; half++) {
-        const double* xo = half ? L.r : L.x;
-        double* xn = half ? L.x : L.r;
-        for (long long r = t0; r < L.n; r += st) xn[r] = -tailRowAcc(L, (int)r, xo, L.b[r]) / L.diag[r];
+        const V* xo = half ? L.r : L.x;
+        V* xn = half ? L.x : L.r;
+        for (long long r = t0; r < L.n; r += st) xn[r] = vnegdiv(tailRowAcc(L, (int)r, xo, L.b[r]), L.diag[r]);
         sy.sync(lt | 0x20);
       }
       xZero = false;
@@ -1680,53 +1754,56 @@ __device__ void tailSweeps(const TailLevel& L, int nSweeps, int smoother, bool& 
   }
 }
 // levels [l0, l1): pre-sweeps, then restriction of the residual into the next level (which gets x = 0)
-template <class S>
-__device__ void stretchDown(const TailLevel* lv, int l0, int l1, int nPre, int smoother, S& sy) {
+template <class V, class S>
+__device__ void stretchDown(const TailLevelT<V>* lv, int l0, int l1, int nPre, int smoother, S& sy) {
   const long long t0 = sy.tid(), st = sy.stride();
   for (int l = l0; l < l1; l++) {
-    const TailLevel L = lv[l];
-    const TailLevel C = lv[l + 1];
+    const TailLevelT<V> L = lv[l];
+    const TailLevelT<V> C = lv[l + 1];
     bool xZero = true;
     tailSweeps(L, nPre, smoother, xZero, sy, l << 8);
-    const double* src = L.b;
+    const V* src = L.b;
     if (!xZero) {  // r = b + A x
       for (long long r = t0; r < L.n; r += st) {
-        L.r[r] = tailRowAcc(L, (int)r, L.x, L.b[r] + L.diag[r] * L.x[r]);
+        V init = L.b[r];
+        vaxpy(init, L.diag[r], L.x[r]);
+        L.r[r] = tailRowAcc(L, (int)r, L.x, init);
       }
       sy.sync((l << 8) | 2);
       src = L.r;
     }
     for (long long I = t0; I < C.n; I += st) {
-      double s = 0.0;
-      for (int p = L.memOff[I]; p < L.memOff[I + 1]; p++) s += src[L.mem[p]];
+      V s;
+      vset0(s);
+      for (int p = L.memOff[I]; p < L.memOff[I + 1]; p++) vadd(s, src[L.mem[p]]);
       const int rc = L.cpos[I];
       C.b[rc] = s;
-      C.x[rc] = 0.0;
+      vset0(C.x[rc]);
     }
     sy.sync((l << 8) | 1);
   }
 }
-template <class S>
-__device__ void stretchBottom(const TailLevel* lv, int l, int nPre, int nPost, int smoother, S& sy) {
-  const TailLevel L = lv[l];
+template <class V, class S>
+__device__ void stretchBottom(const TailLevelT<V>* lv, int l, int nPre, int nPost, int smoother, S& sy) {
+  const TailLevelT<V> L = lv[l];
   bool xZero = true;
   tailSweeps(L, nPre, smoother, xZero, sy, l << 8);
   tailSweeps(L, nPost, smoother, xZero, sy, l << 8);  // coarsest level: pre + post sweeps
 }
 // levels l1-1 down to l0: prolongation of the next level's correction, then post-sweeps
-template <class S>
-__device__ void stretchUp(const TailLevel* lv, int l0, int l1, int nPost, int smoother, S& sy) {
+template <class V, class S>
+__device__ void stretchUp(const TailLevelT<V>* lv, int l0, int l1, int nPost, int smoother, S& sy) {
   const long long t0 = sy.tid(), st = sy.stride();
   for (int l = l1 - 1; l >= l0; l--) {
-    const TailLevel L = lv[l];
-    const TailLevel C = lv[l + 1];
+    const TailLevelT<V> L = lv[l];
+    const TailLevelT<V> C = lv[l + 1];
     // (Applying the prolongation on the fly inside the first pass -- x_j + xc[ci[j]] per matrix entry, no separate
     // phase -- was measured with the phase trace: the pass then costs 7-9 us instead of 0.8 us even on a level of 8
     // rows, because its three dependent gathers per entry miss to DRAM one after the other, while this streaming
     // phase costs 2 us and leaves the pass its prefetched operands.)
     for (long long i = t0; i < L.n; i += st) {
       const int c = L.ci[i];
-      if (c >= 0) L.x[i] += C.x[c];
+      if (c >= 0) vadd(L.x[i], C.x[c]);
     }
     sy.sync((l << 8) | 3);
     bool xZero = false;
@@ -1734,8 +1811,8 @@ __device__ void stretchUp(const TailLevel* lv, int l0, int l1, int nPost, int sm
   }
 }
 // on entry: level 0 of the stretch has b set and x == 0
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_tail_vcycle(const TailLevel* lv, int nLevels, int nPre, int nPost,
+template <class V, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_tail_vcycle(const TailLevelT<V>* lv, int nLevels, int nPre, int nPost,
                                                            int smoother) {
   CtaSync sy;
   stretchDown(lv, 0, nLevels - 1, nPre, smoother, sy);
@@ -1744,8 +1821,8 @@ __global__ void __launch_bounds__(THREADS) k_tail_vcycle(const TailLevel* lv, in
 }
 // levels [0, nGrid) by the whole grid, levels [nGrid, nLevels) by CTA 0 alone (they have <= kTailRows
 // rows: one CTA is enough and its barrier is __syncthreads())
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_coop_vcycle(const TailLevel* lv, int nLevels, int nGrid, int nPre,
+template <class V, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_coop_vcycle(const TailLevelT<V>* lv, int nLevels, int nGrid, int nPre,
                                                            int nPost, int smoother, unsigned* bar) {
   GridSync gs{bar};
   stretchDown(lv, 0, nGrid, nPre, smoother, gs);   // ends with a grid barrier after filling level nGrid's b
@@ -1759,7 +1836,6 @@ __global__ void __launch_bounds__(THREADS) k_coop_vcycle(const TailLevel* lv, in
   stretchUp(lv, 0, nGrid, nPost, smoother, gs);
 }
 #endif
-
 
 void Amg::buildTail() {
   tailStart = -1;
@@ -1778,7 +1854,7 @@ void Amg::buildTail() {
     if (coopOk < 0) {
       int perSm = 0, dev = ctx().device, attr = 0;
       cudaDeviceGetAttribute(&attr, cudaDevAttrCooperativeLaunch, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_coop_vcycle<kTailThreads>, kTailThreads, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_coop_vcycle<double, kTailThreads>, kTailThreads, 0);
       coopOk = (attr && perSm >= 1) ? 1 : 0;
     }
     if (coopOk) start = cstart; else tailIsCoop = false;
@@ -1860,11 +1936,11 @@ void Amg::runTail() {
     unsigned* bar = coopBarrier.p;
     devMemset(bar, 0, sizeof(unsigned));
     void* args[] = {(void*)&lv, &cnt, &nGrid, &nPre, &nPost, &sm, &bar};
-    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coop_vcycle<kTailThreads>, dim3(ctx().smCount), dim3(kTailThreads), args, 0,
+    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coop_vcycle<double, kTailThreads>, dim3(ctx().smCount), dim3(kTailThreads), args, 0,
                                            ctx().stream));
   } else {
     ProfileScope prof("N6fvmgpu13k_tail_vcycleE", levels[tailStart]->n);
-    k_tail_vcycle<kTailThreads><<<1, kTailThreads, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
+    k_tail_vcycle<double, kTailThreads><<<1, kTailThreads, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
     CUDA_CHECK(cudaGetLastError());
   }
   ctx().launches++;
@@ -2043,6 +2119,8 @@ void Amg::dropGraphs() {
   }
 #endif
   dropIterationGraph();
+  dropMultiGraph();
+  graphWarmM = false;
 }
 void Amg::dropIterationGraph() {
 #ifndef FVMGPU_HOSTSIM
@@ -2606,6 +2684,325 @@ void Amg::jacobiSolve(System* sys, int nMaxIterations, double relTol, double abs
   if (rnorm0Out) *rnorm0Out = rNorm0;
   if (rnormOut) *rnormOut = rNorm;
   if (itersOut) *itersOut = iters;
+}
+
+// ================================================================= several right-hand sides on one matrix
+// CRMatrix<DiagonalTensor<T,3>, T, Vector<T,3>> (the momentum system, F/FlowModel_impl.h:536, F/CRMatrix.h:303-346
+// instantiated with Vector unknowns): scalar off-diagonal, and -- without symmetry planes -- one diagonal value for
+// the three components. Round 1 solved it as three scalar systems, i.e. read the matrix three times per pass. Here
+// the unknown of a row is a VecN<NC>: every kernel of the cycle reads a matrix entry once for all components
+// (hex: 36 NC + 72 bytes per row instead of 108 NC), and the latency-bound coarse levels run once, not NC times.
+// Same hierarchy, same operations per component in the same order as the scalar kernels. Single GPU, V-cycle,
+// Gauss-Seidel; anything else falls back to the component-by-component path (csrc/flow.cu).
+namespace {
+template <int NC>
+struct GsRowsN {
+  int rowBegin; const int* sliceOff; const int* scol; const double* sval; const double* diag; const VecN<NC>* b; VecN<NC>* x;
+  FVM_DEV void operator()(long long t) const {
+    const int r = rowBegin + (int)t, s = r >> 5;
+    const int end = sliceOff[s + 1];
+    VecN<NC> sum = b[r];
+    for (int p = sliceOff[s] + (r & 31); p < end; p += 32) vaxpy(sum, sval[p], x[scol[p]]);
+    x[r] = vnegdiv(sum, diag[r]);
+  }
+};
+template <int NC>
+struct GsFirstColourZeroRowsN {
+  int rowBegin; const double* diag; const VecN<NC>* b; VecN<NC>* x;
+  FVM_DEV void operator()(long long t) const { const int r = rowBegin + (int)t; x[r] = vnegdiv(b[r], diag[r]); }
+};
+template <int NC>
+struct ResidualRowsN {  // r = b + A x outside [skipFrom, skipTo), fused with the per-component 1-norms
+  int skipFrom, skipTo; const int* sliceOff; const int* scol; const double* sval; const double* diag; const VecN<NC>* b;
+  const VecN<NC>* x; VecN<NC>* r;
+  FVM_DEV VecN<NC> compute(int i) const {
+    const int s = i >> 5;
+    const int end = sliceOff[s + 1];
+    VecN<NC> v = b[i];
+    vaxpy(v, diag[i], x[i]);
+    for (int p = sliceOff[s] + (i & 31); p < end; p += 32) vaxpy(v, sval[p], x[scol[p]]);
+    return v;
+  }
+  FVM_DEV void operator()(long long t) const {
+    const int i = (int)t < skipFrom ? (int)t : (int)t + (skipTo - skipFrom);
+    r[i] = compute(i);
+  }
+  FVM_DEV void operator()(long long t, double* out) const {
+    const int i = (int)t < skipFrom ? (int)t : (int)t + (skipTo - skipFrom);
+    const VecN<NC> v = compute(i);
+    r[i] = v;
+#pragma unroll
+    for (int k = 0; k < NC; k++) out[k] = fabs(v.v[k]);
+  }
+};
+template <int NC>
+struct InjectRowsN {
+  const int* memOff; const int* mem; const int* cpos; const VecN<NC>* src; VecN<NC>* bC; VecN<NC>* xC;
+  FVM_DEV void operator()(long long I) const {
+    VecN<NC> s;
+    vset0(s);
+    for (int p = memOff[I]; p < memOff[I + 1]; p++) vadd(s, src[mem[p]]);
+    const int r = cpos[I];
+    bC[r] = s;
+    if (xC) vset0(xC[r]);
+  }
+};
+template <int NC>
+struct CorrectRowsN {
+  int skipFrom, skipTo; int fineIsZero; const int* ci; const VecN<NC>* xC; VecN<NC>* x;
+  FVM_DEV void operator()(long long t) const {
+    const long long i = t < skipFrom ? t : t + (skipTo - skipFrom);
+    const int c = ci[i];
+    VecN<NC> d;
+    if (fineIsZero) vset0(d); else d = x[i];
+    if (c >= 0) vadd(d, xC[c]);
+    x[i] = d;
+  }
+};
+template <int NC>
+struct LoadAoSN {   // dst[perm[i]][k] = src[stride * i + k]
+  const int* perm; const double* src; int stride; VecN<NC>* dst;
+  FVM_DEV void operator()(long long i) const {
+    VecN<NC> v;
+#pragma unroll
+    for (int k = 0; k < NC; k++) v.v[k] = src[(size_t)stride * i + k];
+    dst[perm[i]] = v;
+  }
+};
+template <int NC>
+struct StoreAoSN {  // dst[stride * i + k] = src[perm[i]][k]
+  const int* perm; const VecN<NC>* src; int stride; double* dst;
+  FVM_DEV void operator()(long long i) const {
+    const VecN<NC> v = src[perm[i]];
+#pragma unroll
+    for (int k = 0; k < NC; k++) dst[(size_t)stride * i + k] = v.v[k];
+  }
+};
+
+template <int NC> VecN<NC>* vb(Level& L) { return reinterpret_cast<VecN<NC>*>(L.mb.p); }
+template <int NC> VecN<NC>* vx(Level& L) { return reinterpret_cast<VecN<NC>*>(L.mx.p); }
+template <int NC> VecN<NC>* vr(Level& L) { return reinterpret_cast<VecN<NC>*>(L.mr.p); }
+
+template <int NC>
+void sweepsN(Amg& A, int nSweeps, int lvl) {
+  Level& L = *A.levels[lvl];
+  LevelTag tag(A.tagBase + lvl);
+  int lastColour = -1;
+  for (int s = 0; s < nSweeps; s++) {
+    for (int pass = 0; pass < 2 * L.nColours; pass++) {
+      const int c = pass < L.nColours ? pass : 2 * L.nColours - 1 - pass;
+      if (c == lastColour) continue;
+      const int r0 = L.colourStart[c], cnt = L.colourStart[c + 1] - r0;
+      if (cnt > 0) {
+        if (L.xZero) parallelFor(cnt, GsFirstColourZeroRowsN<NC>{r0, L.diag.p, vb<NC>(L), vx<NC>(L)});
+        else parallelFor(cnt, GsRowsN<NC>{r0, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, vb<NC>(L), vx<NC>(L)});
+      }
+      L.xZero = false;
+      lastColour = c;
+    }
+    L.rValid = false;
+  }
+}
+
+template <int NC>
+void runTailN(Amg& A) {
+#ifndef FVMGPU_HOSTSIM
+  typedef VecN<NC> V;
+  const TailLevelT<V>* lv = reinterpret_cast<const TailLevelT<V>*>(A.tailLevelsM.p);
+  int cnt = A.tailCount, nPre = A.opts.nPreSweeps, nPost = A.opts.nPostSweeps, sm = A.opts.smootherType;
+  if (A.tailIsCoop) {
+    ProfileScope prof("N6fvmgpu14k_coop_vcycleNE", A.levels[A.tailStart]->n);
+    int nGrid = A.tailGridLevels;
+    unsigned* bar = A.coopBarrier.p;
+    devMemset(bar, 0, sizeof(unsigned));
+    void* args[] = {(void*)&lv, &cnt, &nGrid, &nPre, &nPost, &sm, &bar};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coop_vcycle<V, kTailThreads>, dim3(ctx().smCount), dim3(kTailThreads), args, 0,
+                                           ctx().stream));
+  } else {
+    ProfileScope prof("N6fvmgpu14k_tail_vcycleNE", A.levels[A.tailStart]->n);
+    k_tail_vcycle<V, kTailThreads><<<1, kTailThreads, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  ctx().launches++;
+  for (int l = A.tailStart; l < (int)A.levels.size(); l++) { A.levels[l]->xZero = false; A.levels[l]->rValid = false; }
+#else
+  (void)A;
+#endif
+}
+
+template <int NC>
+void cycleN(Amg& A, int lvl) {   // V-cycle (AMG::cycle, F/AMG.cpp:70-147) on the NC-wide vectors
+  Level& L = *A.levels[lvl];
+  if (lvl == A.tailStart && L.xZero) { runTailN<NC>(A); return; }
+  sweepsN<NC>(A, A.opts.nPreSweeps, lvl);
+  if (lvl + 1 < (int)A.levels.size()) {
+    Level& C = *A.levels[lvl + 1];
+    const VecN<NC>* src;
+    if (L.xZero) src = vb<NC>(L);
+    else {
+      if (!L.rValid) {
+        LevelTag tag(A.tagBase + lvl);
+        parallelFor(L.n, ResidualRowsN<NC>{0, 0, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, vb<NC>(L), vx<NC>(L), vr<NC>(L)});
+        L.rValid = true;
+      }
+      src = vr<NC>(L);
+    }
+    // (lazy zero of the coarse x and the skipped rows of the prolongation: see Amg::cycle)
+    const bool lazyZero = C.nColours <= 2 && A.opts.nPreSweeps == 0 && A.opts.nPostSweeps >= 1 && lvl + 1 != A.tailStart;
+    { LevelTag tag(A.tagBase + lvl); parallelFor(C.n, InjectRowsN<NC>{L.memOff.p, L.mem.p, L.cpos.p, src, vb<NC>(C), lazyZero ? nullptr : vx<NC>(C)}); }
+    C.xZero = true;
+    C.rValid = false;
+    cycleN<NC>(A, lvl + 1);
+    {
+      LevelTag tag(A.tagBase + lvl);
+      int z0 = 0, z1 = 0;
+      if (A.opts.nPostSweeps >= 1) z1 = L.colourStart[1];
+      parallelFor(L.n - (z1 - z0), CorrectRowsN<NC>{z0, z1, L.xZero ? 1 : 0, L.ci.p, vx<NC>(C), vx<NC>(L)});
+    }
+    L.xZero = false;
+    L.rValid = false;
+  }
+  sweepsN<NC>(A, A.opts.nPostSweeps, lvl);
+}
+
+template <int NC>
+void solveN(Amg& A, System* sys, const double* b3, double* delta3, int stride, int maxCycles, double relTol, double absTol,
+            double* rnorm0Out, double* rnormOut, int* itersOut) {
+  typedef VecN<NC> V;
+  A.ensureSetup(sys);
+  // NC-wide vectors of every level (+ the level table of the fused kernels), kept with the hierarchy
+  if (A.multiNc != NC) {
+    for (auto& lp : A.levels) {
+      Level& L = *lp;
+      L.mb.alloc((size_t)NC * L.n); L.mx.alloc((size_t)NC * L.n); L.mr.alloc((size_t)NC * L.n);
+      L.mb.zero(); L.mx.zero(); L.mr.zero();
+    }
+    A.dropMultiGraph();
+#ifndef FVMGPU_HOSTSIM
+    if (A.tailStart >= 0) {
+      std::vector<TailLevelT<V>> h;
+      for (int l = A.tailStart; l < (int)A.levels.size(); l++) {
+        Level& L = *A.levels[l];
+        TailLevelT<V> t;
+        t.n = L.n; t.nColours = L.nColours; t.colourStart = A.tailColourStarts[(size_t)(l - A.tailStart)].p;
+        t.sliceOff = L.sliceOff.p; t.scol = L.scol.p; t.sval = L.sval.p; t.diag = L.diag.p;
+        t.b = vb<NC>(L); t.x = vx<NC>(L); t.r = vr<NC>(L);
+        t.ci = L.ci.p; t.memOff = L.memOff.p; t.mem = L.mem.p; t.cpos = L.cpos.p;
+        h.push_back(t);
+      }
+      A.tailLevelsM.alloc(h.size() * sizeof(TailLevelT<V>));
+      copyH2D(A.tailLevelsM.p, h.data(), h.size() * sizeof(TailLevelT<V>));
+    }
+#endif
+    A.multiNc = NC;
+  }
+  A.history.clear();
+  Level& L0 = *A.levels[0];
+  parallelFor(L0.n, LoadAoSN<NC>{A.perm0.p, b3, stride, vb<NC>(L0)});
+  parallelFor(L0.n, LoadAoSN<NC>{A.perm0.p, delta3, stride, vx<NC>(L0)});
+  L0.xZero = false;
+  L0.rValid = false;
+  double* S = A.scalars.p;
+  auto residualNorms = [&](bool skipExact) {
+    LevelTag tag(A.tagBase);
+    int z0 = 0, z1 = 0;
+    if (skipExact && A.opts.nPostSweeps >= 1 && L0.nColours >= 2 && !(A.opts.relativeTolerance < 1e-10)) {
+      z1 = L0.colourStart[1];   // rows relaxed last: exact zero residual (see ResidualRowsFrom)
+      if (z1 > z0) devMemset(vr<NC>(L0) + z0, 0, (size_t)(z1 - z0) * sizeof(V));
+    }
+    reduceRows<NC>(L0.n - (z1 - z0), ResidualRowsN<NC>{z0, z1, L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, vb<NC>(L0),
+                                                      vx<NC>(L0), vr<NC>(L0)}, S);
+    L0.rValid = true;
+  };
+  residualNorms(false);
+  double n0[3] = {0, 0, 0}, nn[3] = {0, 0, 0};
+  copyD2H(n0, S, NC * sizeof(double));
+  for (int k = 0; k < 3; k++) nn[k] = n0[k];
+  auto mag2 = [&](const double* q) { double m = 0; for (int k = 0; k < NC; k++) m += q[k] * q[k]; return m; };
+  const double den = mag2(n0);
+  A.history.push_back(std::sqrt(den));
+  int iters = 0;
+  if (den > 0 && !(den < absTol * absTol)) {
+    auto body = [&]() { cycleN<NC>(A, 0); residualNorms(true); };
+    for (int i = 1; i < maxCycles; i++) {
+      A.runMultiGraph(body, NC);
+      iters++;
+      copyD2H(nn, S, NC * sizeof(double));
+      const double num = mag2(nn);
+      A.history.push_back(std::sqrt(num));
+      // shared test: magnitude of the vector of component norms (normalize + Vector::operator<, F/AMG.cpp:256-272)
+      if (num < absTol * absTol || num / den < relTol * relTol) break;
+    }
+  }
+  A.totalIterations += iters;
+  parallelFor(L0.n, StoreAoSN<NC>{A.perm0.p, vx<NC>(L0), stride, delta3});
+  for (int k = 0; k < NC; k++) {
+    if (rnorm0Out) rnorm0Out[k] = n0[k];
+    if (rnormOut) rnormOut[k] = nn[k];
+  }
+  if (itersOut) *itersOut = iters;
+}
+}  // namespace
+
+void Amg::dropMultiGraph() {
+#ifndef FVMGPU_HOSTSIM
+  if (graphExecM) { cudaGraphExecDestroy((cudaGraphExec_t)graphExecM); graphExecM = nullptr; }
+#endif
+}
+// (cycle + residual norms) of the NC-wide solve as a captured graph, like cycleGraphed(0)
+void Amg::runMultiGraph(const std::function<void()>& body, int nc) {
+#ifndef FVMGPU_HOSTSIM
+  if (!ctx().profiling && useGraphs) {
+    const int key[6] = {opts.nPreSweeps, opts.nPostSweeps, opts.cycleType, opts.smootherType, nc,
+                        opts.relativeTolerance < 1e-10 ? 1 : 0};
+    if (graphExecM && std::memcmp(key, graphKeyM, sizeof(key)) != 0) dropMultiGraph();
+    Level& L0 = *levels[0];
+    // (captured from the second cycle on: the first one finds level 0 in its just-loaded state, see cycleGraphed)
+    if (!graphExecM && graphWarmM) {
+      const bool xz = L0.xZero, rv = L0.rValid;
+      cudaGraph_t g = nullptr;
+      const long long launchesBefore = ctx().launches;
+      CUDA_CHECK(cudaStreamBeginCapture(ctx().stream, cudaStreamCaptureModeThreadLocal));
+      try { body(); } catch (...) { cudaGraph_t dead = nullptr; cudaStreamEndCapture(ctx().stream, &dead); if (dead) cudaGraphDestroy(dead); throw; }
+      CUDA_CHECK(cudaStreamEndCapture(ctx().stream, &g));
+      graphLaunchesM = ctx().launches - launchesBefore;
+      ctx().launches = launchesBefore;
+      cudaGraphExec_t ge = nullptr;
+      CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
+      cudaGraphDestroy(g);
+      graphExecM = ge;
+      std::memcpy(graphKeyM, key, sizeof(key));
+      L0.xZero = xz; L0.rValid = rv;
+    }
+    if (graphExecM) {
+      CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)graphExecM, ctx().stream));
+      ctx().launches += graphLaunchesM;
+      L0.xZero = false; L0.rValid = true;
+      for (size_t l = 1; l < levels.size(); l++) { levels[l]->xZero = false; levels[l]->rValid = false; }
+      return;
+    }
+    graphWarmM = true;
+  }
+#endif
+  (void)nc;
+  body();
+}
+
+bool Amg::multiRhsSupported() const {
+  return !multi && opts.cycleType == FVMGPU_CYCLE_V && opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL && !g_referenceOrder;
+}
+
+// AMG::solve for a system with Vector<T,nc> unknowns sharing one scalar matrix: b3 / delta3 hold `stride` doubles
+// per row (AoS, natural numbering), the first nc of them are solved for. Convergence: the reference's shared test on
+// the magnitude of the vector of component 1-norms. iters = cycles run.
+void Amg::solveMulti(System* sys, int nc, const double* b3, double* delta3, int stride, int maxCycles, double relTol,
+                     double absTol, double* rnorm0Out, double* rnormOut, int* itersOut) {
+  requireReady();
+  if (!scalars.p) scalars.alloc(16);
+  multi = commActive() && sys->mesh && !sys->noHalo;
+  if (nc == 2) solveN<2>(*this, sys, b3, delta3, stride, maxCycles, relTol, absTol, rnorm0Out, rnormOut, itersOut);
+  else if (nc == 3) solveN<3>(*this, sys, b3, delta3, stride, maxCycles, relTol, absTol, rnorm0Out, rnormOut, itersOut);
+  else fail("solveMulti: 2 or 3 components");
 }
 
 }  // namespace fvmgpu

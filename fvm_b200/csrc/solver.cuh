@@ -15,6 +15,7 @@ struct Level {
   DBuf<int> scol;
   DBuf<double> sval;
   DBuf<double> diag, b, x, r;
+  DBuf<double> mb, mx, mr;   // the same three vectors with NC values per row (Amg::solveMulti)
   DBuf<int> nat;             // level row -> index in the level's natural (pre-colouring) numbering
   // colouring: rows [colourStart[c], colourStart[c+1]) have colour c
   int nColours = 0;
@@ -37,6 +38,16 @@ struct Level {
   DBuf<int> ghostCoarse;         // per ghost slot: x index in the NEXT level (>= its n), -1 = none
 };
 
+// pattern-only part of level 0 (see buildLevelFromCsr)
+struct PatternCache {
+  unsigned long long stamp = 0;
+  int n = 0; bool dropGhost = false, splitIface = false;
+  int nColours = 0, nSlices = 0;
+  long long nnzStored = 0, nnzTrue = 0;
+  std::vector<int> colourStart, ifaceCount;
+  DBuf<int> perm, nat, sliceOff;
+};
+
 struct Ilu0;
 struct Ilu0Deleter { void operator()(Ilu0* p) const; };
 
@@ -52,6 +63,7 @@ struct Amg {
   DBuf<double> natIn, natOut;
   std::vector<std::unique_ptr<Level>> levels;
   DBuf<int> perm0;           // system (natural) row -> level-0 row
+  PatternCache cache0;       // survives cleanup(): the next outer iteration assembles on the same pattern
   DBuf<double> scalars;      // device scalars for dots / norms
   System* builtFor = nullptr;          // the system of the last setup (used by the ILU preconditioner path)
   unsigned long long builtVersion = 0; // its System::version stamp: THE identity of the hierarchy (stamps are unique)
@@ -87,6 +99,18 @@ struct Amg {
   long long iterGraphLaunches = 0;
   double iterGraphAbsTol = 0;
   int iterGraphKey[5] = {-1, -1, -1, -1, -1};   // nPre, nPost, cycleType, smootherType, precondKind
+  // several right-hand sides on one matrix (the momentum system): see the end of solver.cu
+  int multiNc = 0;
+  DBuf<char> tailLevelsM;
+  void* graphExecM = nullptr;
+  long long graphLaunchesM = 0;
+  int graphKeyM[6] = {-1, -1, -1, -1, -1, -1};
+  bool graphWarmM = false;
+  bool multiRhsSupported() const;
+  void solveMulti(System* sys, int nc, const double* b3, double* delta3, int stride, int maxCycles, double relTol, double absTol,
+                  double* rnorm0, double* rnorm, int* iters);
+  void runMultiGraph(const std::function<void()>& body, int nc);
+  void dropMultiGraph();
   void cycleOn(double* rhs);
   void runIterationGraph(const std::function<void()>& body, double absTol);
   void dropIterationGraph();

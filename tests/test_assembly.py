@@ -90,11 +90,13 @@ CASES = {
 
 
 @pytest.mark.parametrize("case", sorted(CASES))
-@pytest.mark.parametrize("convecting", [False, True])
+@pytest.mark.parametrize("convecting", [False, True, "central"])
 def test_live_reference_random_fields(devlib, ref, case, convecting):
     """Seeded random x / conductivity / source (and a random convecting face flux, which turns the
     Dirichlet groups into the reference's per-face Dirichlet-or-extrapolation switch) on meshes with
-    corner cells, a single cell, ragged strips; compared with the reference on identical arrays."""
+    corner cells, a single cell, ragged strips; compared with the reference on identical arrays.
+    "central": ConvectionDiscretization's useCentralDifference branch (F/ConvectionDiscretization.h:119-164,
+    including its x[c0] + x[c0] face value) instead of the upwind one."""
     m = CASES[case]()
     rm = ref.RefMesh.from_raw(m.dim, m.n_cells, m.nodes, m.face_cells, m.face_nodes, m.face_node_count,
                               m.face_group_size)
@@ -118,6 +120,8 @@ def test_live_reference_random_fields(devlib, ref, case, convecting):
                 "Mixed": ["convectiveCoefficient", "surfaceEmissivity", "farFieldTemperature"]}[typ]
         t.set_bc(gid, typ, **{kk: vals[kk] for kk in keep})
     t.set_solver(ref.solver_cfg(verbosity=0))
+    if convecting == "central":
+        t.set_option("useCentralDifference", 1)
     t.init()
     t.field("conductivity")[:] = k
     t.field("source")[:] = src
@@ -138,7 +142,7 @@ def test_live_reference_random_fields(devlib, ref, case, convecting):
         t.field("temperature")[:] = x0
         a = t.assemble(stage)
         ds.set_field(X.FIELD_X, x0)
-        ds.assemble(convection=1 if convecting else 0, eliminate_boundary=stage)
+        ds.assemble(convection={False: 0, True: 1, "central": 2}[convecting], eliminate_boundary=stage)
         d = ds.download()
         check_system(d, a["diag"], a["offdiag"], a["b"])
         assert np.array_equal(d["is_boundary"], a["is_boundary"])
