@@ -17,9 +17,9 @@ class FvmGpuError(RuntimeError):
 
 
 # enums of fvmgpu.h
-GROUP_INTERIOR, GROUP_BOUNDARY, GROUP_INTERFACE, GROUP_SYMMETRY = 0, 1, 2, 3
+GROUP_INTERIOR, GROUP_BOUNDARY, GROUP_INTERFACE, GROUP_SYMMETRY, GROUP_DIELECTRIC_INTERFACE = 0, 1, 2, 3, 4
 (BC_DIRICHLET, BC_NEUMANN, BC_EXTRAPOLATION, BC_CONVECTIVE, BC_RADIATIVE, BC_MIXED, BC_INTERFACE,
- BC_DIRICHLET_OR_OUTFLOW) = range(8)
+ BC_DIRICHLET_OR_OUTFLOW, BC_DIELECTRIC_INTERFACE) = range(9)
 (FIELD_X, FIELD_DIFFUSIVITY, FIELD_SOURCE, FIELD_FACE_FLUX, FIELD_X_N1, FIELD_X_N2, FIELD_DENSITY,
  FIELD_CONT_RESID, FIELD_GRADIENT, FIELD_BFLUX, FIELD_DELTA, FIELD_B) = range(12)
 CYCLE_V, CYCLE_W, CYCLE_F = 0, 1, 2
@@ -29,7 +29,7 @@ SMOOTHER_GAUSS_SEIDEL, SMOOTHER_JACOBI = 0, 1
 class AssembleOpts(C.Structure):
     _fields_ = [("diffusion", C.c_int), ("convection", C.c_int), ("source", C.c_int),
                 ("time_order", C.c_int), ("dt", C.c_double), ("underrelax", C.c_double),
-                ("apply_bcs", C.c_int), ("eliminate_boundary", C.c_int)]
+                ("apply_bcs", C.c_int), ("eliminate_boundary", C.c_int), ("interface_thickness", C.c_double)]
 
 
 class AmgOpts(C.Structure):
@@ -513,9 +513,9 @@ class DeviceSystem:
         self.lib.call("fvmgpu_compute_gradient", self.h)
 
     def assemble(self, diffusion=1, convection=0, source=1, time_order=0, dt=0.0, underrelax=0.0,
-                 apply_bcs=1, eliminate_boundary=1):
+                 apply_bcs=1, eliminate_boundary=1, interface_thickness=0.0):
         o = AssembleOpts(diffusion, convection, source, time_order, dt, underrelax, apply_bcs,
-                         eliminate_boundary)
+                         eliminate_boundary, interface_thickness)
         self.lib.call("fvmgpu_assemble", self.h, C.byref(o))
 
     def download(self):

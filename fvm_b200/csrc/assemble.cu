@@ -93,6 +93,12 @@ struct GradientRows {
     state[i] = s;
     return;
   }
+  if (kind == FVMGPU_GROUP_DIELECTRIC_INTERFACE) {
+    // no copy from the neighbour (F/GradientModel.h:538-539) and GradientMatrix::getGradient only fills the interior
+    // rows (F/GradientMatrix.h:55-76): the reference leaves the gradient of these ghost cells unset -- here it is 0
+    state[i] = make_double4(0.0, 0.0, 0.0, xi);
+    return;
+  }
   rowGradient(c0, x[c0], row, col, x, w, nnz, g0, g1, g2);
   if (kind == FVMGPU_GROUP_SYMMETRY) {  // reflectGradient, F/GradientModel.h:21-28
     const double4 fg = faceGeom[f];
@@ -129,7 +135,7 @@ FVM_DEV double harmonicAverage(double x0, double x1) {
 }
 
 // F/DiffusionDiscretization.h:165-209 for one face with cells (c0,c1)
-FVM_DEV void diffusionFace(const double4 fg, const CellV& a0, const CellV& a1,
+FVM_DEV void diffusionFaceRegular(const double4 fg, const CellV& a0, const CellV& a1,
                                               double& diffCoeff, double& dFlux) {
   const double vol0 = a0.g.w, vol1 = a1.g.w;
   const double ds0 = a1.g.x - a0.g.x, ds1 = a1.g.y - a0.g.y, ds2 = a1.g.z - a0.g.z;
@@ -151,6 +157,32 @@ FVM_DEV void diffusionFace(const double4 fg, const CellV& a0, const CellV& a1,
   dFlux = diffCoeff * (a1.s.w - a0.s.w) + sec;
 }
 
+// The "dielectric interface" branch of the same loop (F/DiffusionDiscretization.h:97-151): on the faces of a group of
+// that type the two cells are separated by a thin layer of the given thickness -- the metric is
+// sign(A . ds) |A| / (|ds| + thickness / 2), the face diffusivity always the harmonic mean, no secondary-gradient term.
+FVM_DEV void diffusionFaceDielectric(const double4 fg, const CellV& a0, const CellV& a1, double thickness,
+                                     double& diffCoeff, double& dFlux) {
+  const double ds0 = a1.g.x - a0.g.x, ds1 = a1.g.y - a0.g.y, ds2 = a1.g.z - a0.g.z;
+  double m2 = 0.0;   // mag(ds) = sqrt(dot(ds, ds)), F/Vector.h
+  m2 += ds0 * ds0; m2 += ds1 * ds1; m2 += ds2 * ds2;
+  const double dsMag = sqrt(m2);
+  const double fd = harmonicAverage(a0.k, a1.k);
+  double sign = 1.0;
+  double ad = 0.0;
+  ad += fg.x * ds0; ad += fg.y * ds1; ad += fg.z * ds2;
+  if (ad < 0.0) sign *= -1.0;
+  const double diffMetric = sign * fg.w / (dsMag + 0.5 * thickness);
+  diffCoeff = fd * diffMetric;
+  dFlux = diffCoeff * (a1.s.w - a0.s.w);
+}
+FVM_DEV void diffusionFace(const AsmParams& P, int f, const double4 fg, const CellV& a0, const CellV& a1,
+                           double& diffCoeff, double& dFlux) {
+  if (f >= P.nInteriorFaces && P.bcs[P.faceGroupOf[f - P.nInteriorFaces]].groupKind == FVMGPU_GROUP_DIELECTRIC_INTERFACE)
+    diffusionFaceDielectric(fg, a0, a1, P.o.interface_thickness, diffCoeff, dFlux);
+  else
+    diffusionFaceRegular(fg, a0, a1, diffCoeff, dFlux);
+}
+
 // Values of the (single-face) ghost row c1 and of the interior coefficient toward it, as the
 // reference leaves them after the discretization list and before the BC loop.
 struct GhostRow {
@@ -163,7 +195,7 @@ FVM_DEV GhostRow ghostRowBeforeBC(const AsmParams& P, int f, const double4 fg,
   g.r1 = 0.0; g.diag1 = 0.0; g.c10 = 0.0;
   if (P.o.diffusion) {
     double dc, df;
-    diffusionFace(fg, a0, a1, dc, df);
+    diffusionFace(P, f, fg, a0, a1, dc, df);
     g.r1 -= df;
     g.c10 += dc;
     g.diag1 -= dc;
@@ -224,6 +256,17 @@ FVM_DEV BcOut bcOnGhost(int kind, const double* p, double bValue, double areaMag
       const double h = bValue, Xinf = p[1];
       const double fluxInterior = -g.r1;
       const double fluxBoundary = -h * (x1 - Xinf) * areaMag;
+      g.r1 = fluxBoundary - fluxInterior;
+      g.diag1 -= h * areaMag;
+      o.marks = true;
+      o.flux = fluxBoundary; o.rflux = 0.0; o.cL = 0.0; o.cR = -h * areaMag;
+    } break;
+    case FVMGPU_BC_DIELECTRIC_INTERFACE: {  // applyDielectricInterfaceBC :367-400  p0 = Xinf, p1 = hCoeff, p2 = source
+      const double Xinf = bValue, h = p[1], source = p[2];
+      const double fluxInterior = -g.r1;
+      double fluxSource = source * areaMag;
+      fluxSource /= 2.0;   // (the reference halves it in 2-D and in 3-D alike)
+      const double fluxBoundary = -h * (x1 - Xinf) * areaMag + fluxSource;
       g.r1 = fluxBoundary - fluxInterior;
       g.diag1 -= h * areaMag;
       o.marks = true;
@@ -290,8 +333,8 @@ struct AssembleRows {
       const CellV ot = loadCell(P, P.col[k]);
       const double4 fg = P.faceGeom[f];
       double dc, df;
-      if (side == 0) { diffusionFace(fg, me, ot, dc, df); r += df; }
-      else { diffusionFace(fg, ot, me, dc, df); r -= df; }
+      if (side == 0) { diffusionFace(P, f, fg, me, ot, dc, df); r += df; }
+      else { diffusionFace(P, f, fg, ot, me, dc, df); r -= df; }
       offk += dc;
       diag -= dc;
     }
@@ -355,7 +398,7 @@ struct AssembleRows {
         if (kind == FVMGPU_BC_INTERFACE) {
           const CellV a0 = loadCell(P, c0);
           const double4 fg = P.faceGeom[f];
-          if (P.o.diffusion) { double dc, df; diffusionFace(fg, a0, me, dc, df); c01 += dc; }
+          if (P.o.diffusion) { double dc, df; diffusionFace(P, f, fg, a0, me, dc, df); c01 += dc; }
           if (P.o.convection && !(P.faceFlux[f] > 0.0)) c01 -= P.faceFlux[f];
         }
         const BcOut o = bcOnGhost(kind, bc.p, bValue, P.faceGeom[f].w, x0, me.s.w, c01, g);

@@ -289,7 +289,7 @@ int fvmgpu_system_get_field(fvmgpu_system_t sys, int field, double* host, long l
 int fvmgpu_system_set_bc(fvmgpu_system_t sys, int groupId, int bcKind, const double* p, int np,
                          const double* perFace) {
   API_BEGIN
-  if (bcKind < 0 || bcKind > FVMGPU_BC_DIRICHLET_OR_OUTFLOW) fail("set_bc: unknown BC kind %d", bcKind);
+  if (bcKind < 0 || bcKind > FVMGPU_BC_DIELECTRIC_INTERFACE) fail("set_bc: unknown BC kind %d", bcKind);
   systemSetBc(S(sys), groupId, bcKind, p, np, perFace);
   API_END
 }
@@ -368,7 +368,10 @@ int fvmgpu_amg_levels(fvmgpu_solver_t s, int cap, int* nLevels, long long* sizes
   if (nLevels) *nLevels = nl;
   for (int l = 0; l < nl && l < cap; l++) {
     if (sizes) sizes[l] = all[l]->n;
-    if (nnzs) nnzs[l] = all[l]->nnzTrue;
+    if (nnzs) {
+      if (all[l]->nnzTrue < 0 && all[l]->nnzDev.p) all[l]->nnzTrue = (long long)all[l]->nnzDev.hostAt(0);
+      nnzs[l] = all[l]->nnzTrue;
+    }
     if (colours) colours[l] = all[l]->nColours;
   }
   API_END

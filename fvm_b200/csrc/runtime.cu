@@ -182,7 +182,7 @@ void exclusiveScan(const int* in_d, int* out_d, long long n) {
   cubTemp().ensure(bytes);
   CUDA_CHECK(cub::DeviceScan::ExclusiveSum(cubTemp().p, bytes, tmp.p, out_d, (int)(n + 1), ctx().stream));
   ctx().launches += 2;
-  streamSync();  // tmp freed on return
+  // (no synchronisation: tmp goes back to the stream-ordered pool / block cache, whose reuse is ordered on this stream)
 }
 
 void sortPairs(int* keys_d, int* vals_d, long long n, int bits) {
@@ -196,7 +196,6 @@ void sortPairs(int* keys_d, int* vals_d, long long n, int bits) {
   copyD2D(keys_d, k2.p, (size_t)n * sizeof(int));
   copyD2D(vals_d, v2.p, (size_t)n * sizeof(int));
   ctx().launches += 4;
-  streamSync();
 }
 
 // ---- profiler

@@ -169,6 +169,7 @@ struct IfaceKeyKernel {
   }
 };
 struct RemapColourKernel { const int* remap; int* colour; FVM_DEV void operator()(long long i) const { colour[i] = remap[colour[i]]; } };
+struct IntAsDoubleRows { const int* a; FVM_DEV void operator()(long long i, double* o) const { o[0] = (double)a[i]; } };
 struct ColourOneRows { const int* colour; FVM_DEV void operator()(long long i, double* o) const { o[0] = (double)colour[i]; } };
 // class sizes: keys in [0, 128). One shared-memory histogram per CTA, then <= 128 global atomics per CTA (16.8 M
 // rows hammering 4 global counters cost 1.4 ms per level-0 call; this is ~0.1 ms)
@@ -832,11 +833,13 @@ static bool twoColouringByTreeParity(int n, const int* row, const int* col, DBuf
   int h[2];
   for (int round = 0; round < 64; round++) {
     for (int jump = 0;; jump++) {
+      // three jumps per look at the flag: a jump on converged links changes nothing, a host round trip per jump
+      // costs more than two idle passes
       flags.zero();
-      parallelFor(n, TreeJumpKernel{link.p, flags.p});
+      for (int k = 0; k < 3; k++) parallelFor(n, TreeJumpKernel{link.p, flags.p});
       flags.download(h, 1);
       if (!h[0]) break;
-      if (jump > 64) return false;
+      if (jump > 32) return false;
     }
     flags.zero();
     parallelFor(n, TreeHookKernel{n, row, col, link.p, hook.p, flags.p});
@@ -981,6 +984,7 @@ static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, c
     L.nSlices = cache->nSlices;
     L.nnzStored = cache->nnzStored;
     L.nnzTrue = cache->nnzTrue;
+    if (L.nnzTrue < 0) { L.nnzDev.alloc(1); copyD2D(L.nnzDev.p, cache->nnzDev.p, sizeof(double)); }
     perm.alloc(n); L.nat.alloc(n); L.sliceOff.alloc(L.nSlices + 1);
     copyD2D(perm.p, cache->perm.p, (size_t)n * sizeof(int));
     copyD2D(L.nat.p, cache->nat.p, (size_t)n * sizeof(int));
@@ -1036,14 +1040,15 @@ static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, c
   L.b.zero(); L.x.zero(); L.r.zero();
   parallelFor(n, SellFillKernel{n, invp.p, perm.p, row, col, val, diag, dropGhost ? 1 : 0, L.sliceOff.p, L.scol.p,
                                 L.sval.p, L.diag.p});
-  // true nnz (for the report)
-  DBuf<int> lenScan(n + 1);
-  exclusiveScan(len.p, lenScan.p, n);
-  L.nnzTrue = lenScan.hostAt(n);
+  // true nnz (for the report): summed on the device, fetched only when somebody asks (fvmgpu_amg_levels)
+  L.nnzDev.alloc(1);
+  reduceRows<1>(n, IntAsDoubleRows{len.p}, L.nnzDev.p);
+  L.nnzTrue = -1;
   if (cache && patternStamp != 0) {
     cache->stamp = patternStamp; cache->n = n; cache->dropGhost = dropGhost; cache->splitIface = splitIface;
     cache->nColours = L.nColours; cache->colourStart = L.colourStart; cache->ifaceCount = L.ifaceCount;
     cache->nSlices = L.nSlices; cache->nnzStored = L.nnzStored; cache->nnzTrue = L.nnzTrue;
+    cache->nnzDev.alloc(1); copyD2D(cache->nnzDev.p, L.nnzDev.p, sizeof(double));
     cache->perm.alloc(n); cache->nat.alloc(n); cache->sliceOff.alloc(L.nSlices + 1);
     copyD2D(cache->perm.p, perm.p, (size_t)n * sizeof(int));
     copyD2D(cache->nat.p, L.nat.p, (size_t)n * sizeof(int));

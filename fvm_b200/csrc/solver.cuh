@@ -9,7 +9,8 @@ namespace fvmgpu {
 struct Level {
   int n = 0;                 // solved rows of this level
   long long nnzStored = 0;   // SELL elements incl. padding
-  long long nnzTrue = 0;     // off-diagonal entries
+  long long nnzTrue = 0;     // off-diagonal entries (-1: still on the device in nnzDev)
+  DBuf<double> nnzDev;
   int nSlices = 0;
   DBuf<int> sliceOff;        // nSlices+1 element offsets into scol/sval (multiples of 32)
   DBuf<int> scol;
@@ -46,6 +47,7 @@ struct PatternCache {
   long long nnzStored = 0, nnzTrue = 0;
   std::vector<int> colourStart, ifaceCount;
   DBuf<int> perm, nat, sliceOff;
+  DBuf<double> nnzDev;
 };
 
 struct Ilu0;

@@ -92,7 +92,8 @@ class Mesh:
         kinds = []
         for g in self._groups:
             kinds.append({"interior": capi.GROUP_INTERIOR, "interface": capi.GROUP_INTERFACE,
-                          "symmetry": capi.GROUP_SYMMETRY}.get(g.groupType, capi.GROUP_BOUNDARY))
+                          "symmetry": capi.GROUP_SYMMETRY,
+                          "dielectric interface": capi.GROUP_DIELECTRIC_INTERFACE}.get(g.groupType, capi.GROUP_BOUNDARY))
         return np.array(kinds, np.int32)
 
 
@@ -1200,7 +1201,9 @@ class ElectricModelA:
             f.chargeN1[cells][:] = f.charge[cells]
 
     # ---- electrostatics
-    def _solve_electrostatics(self, mesh):
+    def _assemble_electrostatics(self, mesh):
+        """initElectroStaticsLinearization + linearizeElectroStatics + initSolve (F/ElectricModel_impl.h:552-767);
+        returns the system and the ids of the symmetry groups"""
         f, o, c = self.fields, self._options, self._constants
         ls = self._pot[mesh.getID()]
         cells = mesh.getCells()
@@ -1221,14 +1224,24 @@ class ElectricModelA:
             elif bc.bcType == "Symmetry":
                 ls.set_bc(fg.id, capi.BC_NEUMANN, [0.0])
                 sym.append(fg.id)
-            elif bc.bcType == "SpecialDielectricBoundary":  # applyDielectricInterfaceBC with src = 0, :734-745
+            elif bc.bcType == "SpecialDielectricBoundary":  # applyDielectricInterfaceBC (src = 0 in the model), :734-745
                 coeff = float(c["dielectric_constant"]) * E0_SI / float(c["dielectric_thickness"])
-                ls.set_bc(fg.id, capi.BC_CONVECTIVE, [coeff, float(bc["specifiedPotential"])])
+                v = bc["specifiedPotential"]
+                if isinstance(v, np.ndarray):
+                    ls.set_bc(fg.id, capi.BC_DIELECTRIC_INTERFACE, [0.0, coeff, 0.0], per_face=v)
+                else:
+                    ls.set_bc(fg.id, capi.BC_DIELECTRIC_INTERFACE, [float(v), coeff, 0.0])
             else:
                 raise CException(bc.bcType + " not implemented for ElectricModel")
         ls.lib.timer_start(1)
         ls.assemble(diffusion=1, convection=0, source=1, time_order=0, dt=0.0, underrelax=0.0, apply_bcs=1,
-                    eliminate_boundary=1)
+                    eliminate_boundary=1, interface_thickness=float(c["dielectric_thickness"]))
+        return ls, sym
+
+    def _solve_electrostatics(self, mesh):
+        f, o, c = self.fields, self._options, self._constants
+        cells = mesh.getCells()
+        ls, sym = self._assemble_electrostatics(mesh)
         solver = o.getElectroStaticsLinearSolver()
         rnorm = solver.solve(ls)
         solver.cleanup()

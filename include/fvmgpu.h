@@ -30,7 +30,13 @@ enum {
   FVMGPU_GROUP_INTERIOR = 0,
   FVMGPU_GROUP_BOUNDARY = 1,  /* "wall", "velocity-inlet", "pressure-outlet", ...           */
   FVMGPU_GROUP_INTERFACE = 2, /* partition interface (F/Mesh.cpp:267-274)                    */
-  FVMGPU_GROUP_SYMMETRY = 3   /* boundary whose ghost gradient is reflected (F/GradientModel.h:536-549) */
+  FVMGPU_GROUP_SYMMETRY = 3,  /* boundary whose ghost gradient is reflected (F/GradientModel.h:536-549) */
+  /* "dielectric interface": the ghost cells of the group stand for cells behind a thin dielectric layer. Their
+   * centroid / volume are the CALLER's (F/MeshMetricsCalculator_impl.h:208-209,445-446 skips the group; so
+   * fvmgpu_mesh_compute_geometry rejects it: use fvmgpu_mesh_set_geometry), no gradient is copied into them
+   * (F/GradientModel.h:538-539), and the diffusion coefficient of their faces is the thin-layer one
+   * (F/DiffusionDiscretization.h:97-151, fvmgpu_assemble_opts::interface_thickness) */
+  FVMGPU_GROUP_DIELECTRIC_INTERFACE = 4
 };
 
 /* ---- boundary-condition kinds = GenericBCS::apply*BC (F/GenericBCS.h) ---- */
@@ -44,7 +50,11 @@ enum {
   FVMGPU_BC_INTERFACE = 6,     /* applyInterfaceBC     :325-356                                   */
   /* ThermalModel "SpecifiedTemperature" with a convecting flux present: per face
    * extrapolation where flux>0 else Dirichlet (F/ThermalModel_impl.h:313-331); p[0] = value */
-  FVMGPU_BC_DIRICHLET_OR_OUTFLOW = 7
+  FVMGPU_BC_DIRICHLET_OR_OUTFLOW = 7,
+  /* applyDielectricInterfaceBC :367-407: flux = -h (x - Xinf) |A| + source |A| / 2;
+   * p[0] = Xinf (per-face values override it: FloatValEvaluator bT[f], F/ElectricModel_impl.h:734-745),
+   * p[1] = h = dielectric_constant / dielectric_thickness, p[2] = source */
+  FVMGPU_BC_DIELECTRIC_INTERFACE = 8
 };
 
 /* ---- named per-system device fields ---- */
@@ -78,6 +88,8 @@ typedef struct {
   int apply_bcs;        /* run the per-group GenericBCS table set by fvmgpu_system_set_bc           */
   int eliminate_boundary; /* LinearSystem::initSolve -> CRMatrix::eliminateBoundaryEquations
                              F/LinearSystem.cpp:39-64, F/CRMatrix.h:899-944,1064-1085               */
+  double interface_thickness; /* DiffusionDiscretization::_thickness (0 in ThermalModel, dielectric_thickness in
+                             ElectricModel, F/ElectricModel_impl.h:563): only read on FVMGPU_GROUP_DIELECTRIC_INTERFACE faces */
 } fvmgpu_assemble_opts;
 
 /* ---- solver options = public tunables of AMG (F/AMG.h:74-81, defaults F/AMG.cpp:14-22)

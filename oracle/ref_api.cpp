@@ -273,6 +273,53 @@ void* fvmref_mesh_from_raw_sym(int dim, int nCells, int nNodes, const double* no
   CATCH(nullptr)
 }
 
+// same with group types given by code: 3 = "symmetry", 4 = "dielectric interface" (a group whose ghost cells stand for
+// cells behind a thin dielectric layer: MeshMetricsCalculator leaves their centroid / volume alone,
+// F/MeshMetricsCalculator_impl.h:208-209,445-446; DiffusionDiscretization takes its thin-layer branch on its faces,
+// F/DiffusionDiscretization.h:97-151). Nothing in the reference tree creates such a group; a script would.
+void* fvmref_mesh_from_raw_typed(int dim, int nCells, int nNodes, const double* nodes, int nFaces,
+                                 const int* faceCells, const int* faceNodes, const int* faceNodeCount,
+                                 int nGroups, const int* faceGroupSize, int nTyped, const int* groupIds, const int* codes) {
+  TRY RefMesh* rm = new RefMesh;
+  Vec3Array coords(nNodes);
+  for (int i = 0; i < nNodes; i++)
+    for (int k = 0; k < 3; k++) coords[i][k] = nodes[3 * i + k];
+  IArray fc(2 * nFaces), fnc(nFaces), fgs(nGroups);
+  long nfn = 0;
+  for (int f = 0; f < nFaces; f++) {
+    fc[2 * f] = faceCells[2 * f];
+    fc[2 * f + 1] = faceCells[2 * f + 1];
+    fnc[f] = faceNodeCount[f];
+    nfn += faceNodeCount[f];
+  }
+  IArray fn((int)nfn);
+  for (long i = 0; i < nfn; i++) fn[(int)i] = faceNodes[i];
+  for (int g = 0; g < nGroups; g++) fgs[g] = faceGroupSize[g];
+  std::shared_ptr<Mesh> mesh(new Mesh(dim, nCells, coords, fc, fn, fnc, fgs));
+  for (const FaceGroupPtr fg : mesh->getBoundaryFaceGroups())
+    for (int k = 0; k < nTyped; k++)
+      if (fg->id == groupIds[k]) fg->groupType = codes[k] == 3 ? "symmetry" : (codes[k] == 4 ? "dielectric interface" : "wall");
+  rm->owned.push_back(mesh);
+  rm->meshes.push_back(mesh.get());
+  finish_mesh(rm);
+  return rm;
+  CATCH(nullptr)
+}
+// overwrite centroid / volume of cells [first, first + count) in the reference's GeomFields (ghost cells of a
+// "dielectric interface" group have no metrics of their own)
+int fvmref_mesh_set_cell_geometry(void* h, int first, int count, const double* centroid, const double* volume) {
+  TRY RefMesh* rm = (RefMesh*)h;
+  const StorageSite& cells = rm->mesh().getCells();
+  Vec3Array& cx = dynamic_cast<Vec3Array&>(rm->geom->coordinate[cells]);
+  DArray& cv = dynamic_cast<DArray&>(rm->geom->volume[cells]);
+  for (int c = 0; c < count; c++) {
+    for (int k = 0; k < 3; k++) cx[first + c][k] = centroid[3 * c + k];
+    cv[first + c] = volume[c];
+  }
+  return 0;
+  CATCH(-1)
+}
+
 void fvmref_mesh_free(void* h) { delete (RefMesh*)h; }
 
 // out[0..7] = dim, nCellsSelf, nCellsTotal, nFaces, nnz(cellCells), nFaceGroups(all), nNodes, meshId
@@ -317,7 +364,8 @@ int fvmref_mesh_connectivity(void* h, int* faceCells, int* ccRow, int* ccCol, in
     groupOffset[g] = fg->site.getOffset();
     groupCount[g] = fg->site.getCount();
     groupId[g] = fg->id;
-    groupKind[g] = fg->groupType == "interior" ? 0 : (fg->groupType == "interface" ? 2 : (fg->groupType == "symmetry" ? 3 : 1));
+    groupKind[g] = fg->groupType == "interior" ? 0 : (fg->groupType == "interface" ? 2 : (fg->groupType == "symmetry" ? 3 :
+                   (fg->groupType == "dielectric interface" ? 4 : 1)));
     g++;
   }
   return 0;

@@ -62,6 +62,11 @@ def lib():
         L.fvmref_mesh_from_raw.restype = C.c_void_p
         L.fvmref_mesh_from_raw.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_int, _ip, _ip, _ip,
                                            C.c_int, _ip]
+        L.fvmref_mesh_from_raw_typed.restype = C.c_void_p
+        L.fvmref_mesh_from_raw_typed.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_int, _ip, _ip, _ip,
+                                                 C.c_int, _ip, C.c_int, _ip, _ip]
+        L.fvmref_mesh_set_cell_geometry.restype = C.c_int
+        L.fvmref_mesh_set_cell_geometry.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, _dp]
         L.fvmref_mesh_from_raw_sym.restype = C.c_void_p
         L.fvmref_mesh_from_raw_sym.argtypes = [C.c_int, C.c_int, C.c_int, _dp, C.c_int, _ip, _ip, _ip,
                                                C.c_int, _ip, C.c_int, _ip]
@@ -146,7 +151,17 @@ class RefMesh:
 
     @classmethod
     def from_raw(cls, dim, n_cells, nodes, face_cells, face_nodes, face_node_count, face_group_size,
-                 symmetry_groups=()):
+                 symmetry_groups=(), dielectric_groups=()):
+        if len(dielectric_groups):
+            nodes = np.ascontiguousarray(nodes, np.float64).reshape(-1, 3)
+            fc = np.ascontiguousarray(face_cells, np.int32).reshape(-1)
+            fn = np.ascontiguousarray(face_nodes, np.int32).reshape(-1)
+            fnc = np.ascontiguousarray(face_node_count, np.int32)
+            fgs = np.ascontiguousarray(face_group_size, np.int32)
+            ids = np.ascontiguousarray(list(symmetry_groups) + list(dielectric_groups), np.int32)
+            codes = np.ascontiguousarray([3] * len(symmetry_groups) + [4] * len(dielectric_groups), np.int32)
+            return cls(lib().fvmref_mesh_from_raw_typed(dim, n_cells, len(nodes), nodes, len(fnc), fc, fn, fnc,
+                                                        len(fgs), fgs, len(ids), ids, codes))
         if len(symmetry_groups):
             nodes = np.ascontiguousarray(nodes, np.float64).reshape(-1, 3)
             fc = np.ascontiguousarray(face_cells, np.int32).reshape(-1)
@@ -193,6 +208,13 @@ class RefMesh:
                               face_centroid=fx.reshape(-1, 3), cell_centroid=cx.reshape(-1, 3),
                               cell_volume=cv, ib_type=ib)
         return self._geom
+
+    def set_cell_geometry(self, first, centroid, volume):
+        """overwrite centroid / volume of `len(volume)` cells from `first` on in the reference's GeomFields"""
+        c = np.ascontiguousarray(centroid, np.float64).reshape(-1)
+        v = np.ascontiguousarray(volume, np.float64)
+        _check(lib().fvmref_mesh_set_cell_geometry(self.h, int(first), len(v), c, v))
+        self._geom = None
 
     def close(self):
         if self.h:

@@ -83,3 +83,98 @@ def test_unsupported_source_models_are_rejected(devlib):
     em.getOptions().tunneling_enable = True
     with pytest.raises(M.CException):
         em.init()
+
+
+def test_dielectric_interface_group_and_boundary_match_the_reference(devlib, ref):
+    """The two pieces of ElectricModel's electrostatics that need a thin dielectric layer, against the reference run
+    in place (oracle/_ref): a face group typed "dielectric interface" (F/DiffusionDiscretization.h:97-151: metric
+    sign |A| / (|ds| + thickness / 2), harmonic-mean permittivity, no secondary gradient; its ghost cells keep the
+    caller's centroid / volume, F/MeshMetricsCalculator_impl.h:208-209,445-446) and the SpecialDielectricBoundary
+    condition with per-face potentials (applyDielectricInterfaceBC, F/GenericBCS.h:367-407). Assembled potential system
+    (1e-12 relative) and the solved potential / electric field (1e-10)."""
+    raw = G.hex_mesh(6, 5, 4, lx=1e-6, ly=1e-6, lz=0.8e-6, jitter=0.15, seed=5)
+    rm = ref.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes, raw.face_node_count,
+                              raw.face_group_size, symmetry_groups=(1,), dielectric_groups=(6,))
+    conn, geo = rm.connectivity(), rm.geometry()
+    assert list(conn["group_kind"]) == [0, 3, 1, 1, 1, 1, 4]
+    # the ghost cells of the dielectric-interface group: a cell centre 0.3 h behind the face, the neighbour's volume
+    o6, c6 = int(conn["group_offset"][6]), int(conn["group_count"][6])
+    fc = conn["face_cells"][o6:o6 + c6]
+    ghosts = fc[:, 1]
+    assert (np.diff(ghosts) == 1).all()
+    en = geo["face_area"][o6:o6 + c6] / geo["face_area_mag"][o6:o6 + c6, None]
+    cen = geo["face_centroid"][o6:o6 + c6] + 0.3 * 0.2e-6 * en
+    vol = geo["cell_volume"][fc[:, 0]]
+    rm.set_cell_geometry(int(ghosts[0]), cen, vol)
+    geo = rm.geometry()
+    assert np.array_equal(geo["cell_centroid"][ghosts], cen)
+    tight = dict(relativeTolerance=1e-13, nMaxIterations=2000, verbosity=0)
+
+    def reference_model():
+        e = ref.RefElectric(rm)
+        e.set_bc(1, "Symmetry")
+        e.set_bc(2, "SpecifiedPotentialFlux", specifiedPotentialFlux=2e-3)
+        e.set_bc(3, "SpecialDielectricBoundary", specifiedPotential=20.0)
+        e.set_bc(4, "SpecifiedPotentialFlux", specifiedPotentialFlux=0.0)
+        e.set_bc(5, "SpecifiedPotential", specifiedPotential=0.0)
+        e.set_bc(6, "SpecifiedPotential", specifiedPotential=100.0)
+        e.set_option("initialTotalCharge", 1e18)
+        e.set_option("chargetransport_enable", 0)
+        e.set_constant("dielectric_thickness", 1.5e-7)
+        e.set_solver(0, ref.solver_cfg(**tight))
+        e.set_solver(1, ref.solver_cfg(**tight))
+        e.init()
+        return e
+
+    e = reference_model()
+    sys_ref = e.potential_system()     # (assembling moves the Dirichlet values into the ghost cells: a model of its own)
+    e.close()
+    e = reference_model()
+    e.advance(2)
+    pot_ref, ef_ref = e.field("potential").copy(), e.field("electric_field").reshape(-1, 3).copy()
+    e.close()
+
+    m = G.RawMesh()
+    m.dim, m.n_cells, m.n_total, m.n_faces = 3, rm.n_self, rm.n_total, rm.n_faces
+    m.nodes, m.face_cells = raw.nodes, conn["face_cells"]
+    m.face_nodes, m.face_node_count, m.face_group_size = raw.face_nodes, raw.face_node_count, raw.face_group_size
+    m.group_offset, m.group_count, m.group_id, m.group_kind = (conn["group_offset"], conn["group_count"], conn["group_id"],
+                                                               conn["group_kind"])
+    m.geometry = dict(face_area=geo["face_area"], face_area_mag=geo["face_area_mag"], face_centroid=geo["face_centroid"],
+                      cell_centroid=geo["cell_centroid"], cell_volume=geo["cell_volume"])
+    types = ["interior", "symmetry", "wall", "wall", "wall", "wall", "dielectric interface"]
+    mesh = M.Mesh(m, group_types=types)
+    geom = M.GeomFields("geom")
+    M.MeshMetricsCalculatorA(geom, [mesh], lib=devlib).init()
+    ef = M.ElectricFields("elec")
+    em = M.ElectricModelA(geom, ef, [mesh], lib=devlib)
+    bc = em.getBCMap()
+    bc[1].bcType = "Symmetry"
+    bc[2].bcType = "SpecifiedPotentialFlux"; bc[2]["specifiedPotentialFlux"] = 2e-3
+    bc[3].bcType = "SpecialDielectricBoundary"; bc[3]["specifiedPotential"] = 20.0
+    bc[4].bcType = "SpecifiedPotentialFlux"; bc[4]["specifiedPotentialFlux"] = 0.0
+    bc[5].bcType = "SpecifiedPotential"; bc[5]["specifiedPotential"] = 0.0
+    bc[6].bcType = "SpecifiedPotential"; bc[6]["specifiedPotential"] = 100.0
+    o = em.getOptions()
+    o["initialTotalCharge"] = 1e18
+    o.chargetransport_enable = False
+    em.getConstants()["dielectric_thickness"] = 1.5e-7
+    for nm in ("electrostaticsLinearSolver", "chargetransportLinearSolver"):
+        s = M.AMG()
+        s.relativeTolerance, s.nMaxIterations, s.verbosity = 1e-13, 2000, 0
+        setattr(o, nm, s)
+    em.init()
+    cells = mesh.getCells()
+    with contextlib.redirect_stdout(io.StringIO()):
+        em.advance(2)   # the second iteration sees the gradients (non-orthogonal corrections) of the first
+    assert rel(ef.potential[cells], pot_ref) <= 1e-10
+    keep = np.ones(rm.n_total, bool)
+    keep[ghosts] = False      # (the reference leaves the gradient of the dielectric-interface ghost cells unset)
+    assert rel(np.asarray(ef.electric_field[cells])[keep], ef_ref[keep]) <= 1e-10
+    # the assembled system itself: re-assemble from the initial state
+    em.init()
+    ls, _ = em._assemble_electrostatics(mesh)
+    ls.lib.timer_stop(1)
+    d = ls.download()
+    for k, kk in (("diag", "diag"), ("offdiag", "offdiag"), ("b", "b")):
+        assert rel(d[k], sys_ref[kk]) <= 1e-12, k
