@@ -6,7 +6,11 @@
 //     `options.linearSolver = new GpuAMG` (the drop-in): same script, solver swapped -- and then
 //     with GpuBCGStab;
 //  3. re-does the reference's linearize + initSolve on the GPU with GpuScalarLinearizer and
-//     compares CRMatrix diag / offdiag / b entry by entry with the reference's own assembly.
+//     compares CRMatrix diag / offdiag / b entry by entry with the reference's own assembly;
+//  4. runs one whole outer iteration device-resident (GpuScalarLinearizer::iterateOnDevice: the matrix never
+//     leaves the GPU) against ThermalModel::advance(1) of the reference;
+//  5. runs a lid-driven cavity with GpuFlowModel (FlowModel::advance on the device, boundary conditions /
+//     material / options read from the reference's own FlowModel object) against the reference FlowModel.
 // Prints one line per check and exits non-zero on failure.
 #include <cmath>
 #include <cstdio>
@@ -25,10 +29,14 @@
 #include "ThermalFields.h"
 #include "ThermalModel.h"
 #include "ThermalModel_impl.h"
+#include "FlowFields.h"
+#include "FlowModel.h"
+#include "FlowModel_impl.h"
 #undef private
 #include "BCGStab.h"
 #include "fvm_gpu_adaptor.h"
 
+template class FlowModel<double>;
 using namespace fvmgpu_adaptor;
 typedef Vector<double, 3> Vec3;
 
@@ -166,6 +174,85 @@ int main(int argc, char** argv) {
       const bool ok = worst <= 1e-12 * scale && worstB <= 1e-12 * scaleB;
       printf("GpuScalarLinearizer vs reference linearize+initSolve: max |dA| = %.3e (scale %.3e), max |db| = %.3e (scale %.3e) %s\n",
              worst, scale, worstB, scaleB, ok ? "OK" : "FAIL");
+      failures += !ok;
+    }
+    // ---- 4. one outer iteration with the system resident on the device
+    {
+      ThermalFields tfRef("therm"), tfGpu("therm");
+      ThermalModel<double> tmRef(geom, tfRef, meshes), tmGpu(geom, tfGpu, meshes);
+      setBCs(tmRef);
+      setBCs(tmGpu);
+      AMG cpu;
+      cpu.relativeTolerance = 1e-13; cpu.nMaxIterations = 5000; cpu.verbosity = 0;
+      tmRef.getOptions().linearSolver = &cpu;
+      tmRef.init();
+      tmGpu.init();
+      std::stringstream sink;
+      std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+      tmRef.advance(1);
+      std::cout.rdbuf(old);
+      GpuMesh gm(*mesh, geom);
+      GpuScalarLinearizer lin(gm);
+      GpuAMG gpu;
+      gpu.relativeTolerance = 1e-13; gpu.nMaxIterations = 5000; gpu.verbosity = 0;
+      std::vector<GpuBC> bcs;
+      GpuBC b4 = {4, FVMGPU_BC_DIRICHLET, {400, 0, 0, 0}}, b3 = {3, FVMGPU_BC_DIRICHLET, {300, 0, 0, 0}},
+            b1 = {1, FVMGPU_BC_NEUMANN, {12.0, 0, 0, 0}}, b2 = {2, FVMGPU_BC_NEUMANN, {0, 0, 0, 0}};
+      bcs.push_back(b4); bcs.push_back(b3); bcs.push_back(b1); bcs.push_back(b2);
+      fvmgpu_assemble_opts o = {1, 0, 1, 0, 0.0, 0.0, 1, 1};
+      int its = 0;
+      const double r0 = lin.iterateOnDevice(gpu, tfGpu.temperature, tfGpu.conductivity, tfGpu.source, bcs, o, 0, &its);
+      const double e = relL2(dynamic_cast<const Array<double>&>(tfGpu.temperature[cells]),
+                             dynamic_cast<const Array<double>&>(tfRef.temperature[cells]));
+      printf("device-resident outer iteration (linearize -> GpuAMG -> postSolve/update, %d cycles, r0 = %.6g) vs "
+             "ThermalModel.advance(1): rel L2 = %.3e %s\n", its, r0, e, e <= 1e-8 ? "OK" : "FAIL");
+      failures += !(e <= 1e-8);
+    }
+
+    // ---- 5. FlowModel::advance on the device, driven by the reference's own FlowModel object
+    {
+      FlowFields ffRef("flow"), ffGpu("flow");
+      FlowModel<double> fmRef(geom, ffRef, meshes), fmGpu(geom, ffGpu, meshes);
+      FlowModel<double>* both[2] = {&fmRef, &fmGpu};
+      AMG ms, ps;
+      for (int k = 0; k < 2; k++) {
+        FlowModel<double>& fm = *both[k];
+        fm.getBCMap()[4]->find("specifiedXVelocity")->second.constant = 1.0;   // the lid
+        fm.getVCMap()[mesh->getID()]->find("viscosity")->second.constant = 0.1;
+        fm.getOptions().momentumTolerance = 1e-30;
+        fm.getOptions().continuityTolerance = 1e-30;
+      }
+      ms.relativeTolerance = ps.relativeTolerance = 1e-13;
+      ms.nMaxIterations = ps.nMaxIterations = 3000;
+      ms.verbosity = ps.verbosity = 0;
+      fmRef.getOptions().momentumLinearSolver = &ms;
+      fmRef.getOptions().pressureLinearSolver = &ps;
+      std::stringstream sink;
+      std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+      fmRef.init();
+      fmGpu.init();
+      fmRef.advance(3);
+      GpuMesh gm(*mesh, geom);
+      GpuFlowModel g(gm, fmGpu, ffGpu);
+      g.momentumSolver.relativeTolerance = g.pressureSolver.relativeTolerance = 1e-13;
+      g.momentumSolver.nMaxIterations = g.pressureSolver.nMaxIterations = 3000;
+      g.init();
+      g.advance(3);
+      std::cout.rdbuf(old);
+      const Array<Vec3>& vr = dynamic_cast<const Array<Vec3>&>(ffRef.velocity[cells]);
+      const Array<Vec3>& vg = dynamic_cast<const Array<Vec3>&>(ffGpu.velocity[cells]);
+      double num = 0, den = 0;
+      for (int i = 0; i < cells.getSelfCount(); i++)
+        for (int k = 0; k < 3; k++) { num += (vg[i][k] - vr[i][k]) * (vg[i][k] - vr[i][k]); den += vr[i][k] * vr[i][k]; }
+      const double ev = std::sqrt(num / den);
+      const Array<double>& pr = dynamic_cast<const Array<double>&>(ffRef.pressure[cells]);
+      const Array<double>& pg = dynamic_cast<const Array<double>&>(ffGpu.pressure[cells]);
+      num = den = 0;
+      for (int i = 0; i < cells.getSelfCount(); i++) { num += (pg[i] - pr[i]) * (pg[i] - pr[i]); den += pr[i] * pr[i]; }
+      const double ep = std::sqrt(num / den);
+      const bool ok = ev <= 1e-8 && ep <= 1e-8;
+      printf("GpuFlowModel.advance(3) vs reference FlowModel.advance(3) on the lid-driven cavity: velocity rel L2 = %.3e, "
+             "pressure rel L2 = %.3e %s\n", ev, ep, ok ? "OK" : "FAIL");
       failures += !ok;
     }
   } catch (std::exception& e) {

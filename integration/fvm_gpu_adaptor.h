@@ -7,17 +7,26 @@
 //   class GpuAMG     : public LinearSolver   (F/LinearSolver.h:11-31)  -- drop-in for AMG
 //   class GpuBCGStab : public LinearSolver                              -- drop-in for BCGStab
 //   GpuCG / GpuJacobiSolver / GpuILU0Solver / GpuBCGStabILU0            -- drop-ins for CG, JacobiSolver, ILU0Solver
-//   class GpuThermalLinearizer                                          -- replaces the body of
+//   class GpuScalarLinearizer                                           -- replaces the body of
 //        ThermalModel<T>::Impl::linearize (F/ThermalModel_impl.h:236-398: GradientModel::compute,
 //        Linearizer::linearize over the discretization list and the GenericBCS loop) plus
 //        LinearSystem::initSolve's boundary elimination, writing into the reference's own
-//        CRMatrix<T,T,T> / MultiField arrays.
+//        CRMatrix<T,T,T> / MultiField arrays; `iterateOnDevice` is the whole outer iteration
+//        (linearize -> solve -> postSolve -> updateSolution, F/ThermalModel_impl.h:424-456) with the matrix
+//        never leaving the device: only the fields go up and the new field comes down.
+//   class GpuFlowModel                                                  -- FlowModel<T>::advance
+//        (F/FlowModel_impl.h:730-770, 1410-1471: solveMomentum, solveContinuity, residual bookkeeping) on the
+//        device, driven by the reference's own FlowModel object for boundary conditions, material and options,
+//        reading and writing the reference's FlowFields arrays.
 //
 // Scripts select it exactly like any other solver:  tmodel.getOptions().linearSolver = GpuAMG()
 // Errors from the C ABI are rethrown as CException (F/CException.h:16-21).
 #ifndef FVM_GPU_ADAPTOR_H_
 #define FVM_GPU_ADAPTOR_H_
 
+#include <algorithm>
+#include <cmath>
+#include <iostream>
 #include <map>
 #include <string>
 #include <vector>
@@ -25,6 +34,8 @@
 #include "AMG.h"
 #include "CException.h"
 #include "CRMatrix.h"
+#include "FlowFields.h"
+#include "FlowModel.h"
 #include "GeomFields.h"
 #include "LinearSolver.h"
 #include "LinearSystem.h"
@@ -108,6 +119,29 @@ class GpuAMG : public LinearSolver {
   int getTotalIterations() const { return _totalIterations; }
   fvmgpu_solver_t handle() { return _solver; }
   fvmgpu_system_t system() { return _system; }
+
+  // AMG::solve on a system that already lives on the device (assembled there by GpuScalarLinearizer): nothing is
+  // copied; delta stays in the system's FVMGPU_FIELD_DELTA. Returns the initial residual norm.
+  double solveOnDevice(fvmgpu_system_t sys, int* iterations = 0) {
+    syncOptions();
+    double r0 = 0, r = 0;
+    int it = 0;
+    check(fvmgpu_amg_solve(_solver, sys, &r0, &r, &it));
+    _totalIterations += it;
+    if (iterations) *iterations = it;
+    return r0;
+  }
+  void syncOptions() {
+    ensureInit();
+    fvmgpu_amg_opts o;
+    o.nMaxIterations = nMaxIterations; o.verbosity = verbosity;
+    o.relativeTolerance = relativeTolerance; o.absoluteTolerance = absoluteTolerance;
+    o.maxCoarseLevels = maxCoarseLevels; o.nPreSweeps = nPreSweeps; o.nPostSweeps = nPostSweeps;
+    o.coarseGroupSize = coarseGroupSize; o.weightRatioThreshold = weightRatioThreshold;
+    o.cycleType = (int)cycleType; o.smootherType = (int)smootherType;
+    if (!_solver) check(fvmgpu_amg_create(&_solver, &o));
+    else check(fvmgpu_amg_set_opts(_solver, &o));
+  }
 
   ScalarSystemView upload(LinearSystem& ls) {
     ensureInit();
@@ -301,9 +335,174 @@ class GpuScalarLinearizer {
   }
   fvmgpu_system_t handle() { return _sys; }
 
+  // One outer iteration with the linear system resident on the device from assembly to update
+  // (XModel::Impl::advance's loop body, F/ThermalModel_impl.h:428-449): fields up, linearize + initSolve,
+  // solver.solve, postSolve + updateSolution, the new field (and the boundary fluxes, over all faces) down.
+  // Returns the initial residual 1-norm (what LinearSolver::solve returns).
+  double iterateOnDevice(GpuAMG& solver, Field& varField, const Field& diffusivity, const Field& source,
+                         const std::vector<GpuBC>& bcs, const fvmgpu_assemble_opts& opts, double* boundaryFlux = 0,
+                         int* iterations = 0) {
+    const StorageSite& cells = _gm.mesh().getCells();
+    DArray& x = dynamic_cast<DArray&>(varField[cells]);
+    const long long nt = cells.getCount();
+    check(fvmgpu_system_set_field(_sys, FVMGPU_FIELD_X, (const double*)x.getData(), nt));
+    check(fvmgpu_system_set_field(_sys, FVMGPU_FIELD_DIFFUSIVITY, (const double*)diffusivity[cells].getData(), nt));
+    check(fvmgpu_system_set_field(_sys, FVMGPU_FIELD_SOURCE, (const double*)source[cells].getData(), nt));
+    for (size_t i = 0; i < bcs.size(); i++) check(fvmgpu_system_set_bc(_sys, bcs[i].groupId, bcs[i].kind, bcs[i].p, 4, 0));
+    check(fvmgpu_assemble(_sys, &opts));
+    const double r0 = solver.solveOnDevice(_sys, iterations);
+    check(fvmgpu_amg_cleanup(solver.handle()));
+    check(fvmgpu_post_solve_update(_sys));
+    check(fvmgpu_system_get_field(_sys, FVMGPU_FIELD_X, (double*)x.getData(), nt));
+    if (boundaryFlux)
+      check(fvmgpu_system_get_field(_sys, FVMGPU_FIELD_BFLUX, boundaryFlux, _gm.mesh().getFaces().getCount()));
+    return r0;
+  }
+
  private:
   const GpuMesh& _gm;
   fvmgpu_system_t _sys;
+};
+
+// ------------------------------------------------------------------------------------ FlowModel
+// FlowModel<double>::advance on the device. The reference FlowModel object stays the owner of the boundary-condition
+// map, the material map and the options (scripts keep writing fmodel.getBCMap()[id].bcType = ... as before) and of
+// the FlowFields arrays; its init() has been called. Solvers: GpuAMG objects (AMG cycles, the reference default) --
+// set `momentumSolver` / `pressureSolver` or leave the defaults of FlowModelOptions (rel 1e-1, 20 iterations).
+class GpuFlowModel {
+ public:
+  GpuFlowModel(const GpuMesh& gm, FlowModel<double>& model, FlowFields& fields)
+      : _gm(gm), _model(model), _f(fields), _flow(0), _niters(0), _haveInitial(false) {
+    check(fvmgpu_flow_create(&_flow, gm.handle()));
+    momentumSolver.relativeTolerance = 1e-1; momentumSolver.nMaxIterations = 20; momentumSolver.verbosity = 0;
+    pressureSolver.relativeTolerance = 1e-1; pressureSolver.nMaxIterations = 20; pressureSolver.verbosity = 0;
+    for (int k = 0; k < 3; k++) _mNorm0[k] = 0;
+    _cNorm0 = 0;
+  }
+  ~GpuFlowModel() { if (_flow) fvmgpu_flow_destroy(_flow); }
+  GpuAMG momentumSolver, pressureSolver;
+
+  // after FlowModel::init(): fields and boundary conditions to the device, default face mass fluxes and continuity
+  // residual computed there (F/FlowModel_impl.h:222-340) and mirrored back
+  void init() {
+    upload(false);
+    check(fvmgpu_flow_init(_flow));
+    const StorageSite& cells = _gm.mesh().getCells();
+    const StorageSite& faces = _gm.mesh().getFaces();
+    get(FVMGPU_FLOW_MASS_FLUX, _f.massFlux[faces], faces.getCount());
+    get(FVMGPU_FLOW_CONT_RESID, _f.continuityResidual[cells], cells.getCount());
+    _niters = 0;
+    _haveInitial = false;
+  }
+
+  // FlowModel::advance (F/FlowModel_impl.h:1433-1471): true when both normalised residuals are below the tolerances
+  bool advance(int niter) {
+    FlowModelOptions<double>& o = _model.getOptions();
+    fvmgpu_flow_opts fo;
+    fo.momentumURF = o["momentumURF"]; fo.pressureURF = o["pressureURF"];
+    fo.transient = o.transient ? 1 : 0; fo.time_order = o.timeDiscretizationOrder; fo.dt = o["timeStep"];
+    fo.correctVelocity = o.correctVelocity ? 1 : 0;
+    fo.operatingPressure = o["operatingPressure"]; fo.operatingTemperature = o["operatingTemperature"];
+    fo.molecularWeight = o["molecularWeight"]; fo.incompressible = o.incompressible ? 1 : 0;
+    momentumSolver.syncOptions();
+    pressureSolver.syncOptions();
+    upload(true);
+    bool converged = false;
+    for (int n = 0; n < niter; n++) {
+      double mNorm[3] = {0, 0, 0}, cNorm = 0;
+      int mIts[3] = {0, 0, 0}, cIts = 0;
+      check(fvmgpu_flow_assemble_momentum(_flow, &fo));                                        // solveMomentum :730-770
+      check(fvmgpu_flow_solve_momentum(_flow, momentumSolver.handle(), 0, 0, 0.0, 0.0, mNorm, mIts));
+      check(fvmgpu_amg_cleanup(momentumSolver.handle()));
+      check(fvmgpu_flow_assemble_continuity(_flow, &fo));                                      // solveContinuity :1410-1430
+      check(fvmgpu_flow_solve_continuity(_flow, pressureSolver.handle(), 0, 0, 0.0, 0.0, &fo, &cNorm, &cIts));
+      check(fvmgpu_amg_cleanup(pressureSolver.handle()));
+      if (!_haveInitial) {
+        for (int k = 0; k < 3; k++) _mNorm0[k] = mNorm[k];
+        _cNorm0 = cNorm;
+        _haveInitial = true;
+      }
+      if (_niters < 5) {   // setMax, :1441-1445
+        for (int k = 0; k < 3; k++) _mNorm0[k] = std::max(_mNorm0[k], mNorm[k]);
+        _cNorm0 = std::max(_cNorm0, cNorm);
+      }
+      double mr[3], cr = _cNorm0 > 0 ? cNorm / _cNorm0 : 0.0, mag = 0;
+      for (int k = 0; k < 3; k++) { mr[k] = _mNorm0[k] > 0 ? mNorm[k] / _mNorm0[k] : 0.0; mag += mr[k] * mr[k]; }
+      lastMomentumNorm[0] = mNorm[0]; lastMomentumNorm[1] = mNorm[1]; lastMomentumNorm[2] = mNorm[2];
+      lastContinuityNorm = cNorm;
+      if (o.printNormalizedResiduals)
+        std::cout << _niters << ": [" << _f.velocity.getName() << " : [" << mr[0] << " " << mr[1] << " " << mr[2] << "]];["
+                  << _f.pressure.getName() << " : " << cr << "]" << std::endl;
+      else
+        std::cout << _niters << ": [" << _f.velocity.getName() << " : [" << mNorm[0] << " " << mNorm[1] << " " << mNorm[2]
+                  << "]];[" << _f.pressure.getName() << " : " << cNorm << "]" << std::endl;
+      _niters++;
+      // Vector::operator< compares magnitudes (F/Vector.h:169-172)
+      if (std::sqrt(mag) < o.momentumTolerance && cr < o.continuityTolerance) { converged = true; break; }
+    }
+    download();
+    return converged;
+  }
+  double lastMomentumNorm[3], lastContinuityNorm;
+  fvmgpu_flow_t handle() { return _flow; }
+
+ private:
+  void set(int field, const ArrayBase& a, long long n) { check(fvmgpu_flow_set_field(_flow, field, (const double*)a.getData(), n)); }
+  void get(int field, ArrayBase& a, long long n) { check(fvmgpu_flow_get_field(_flow, field, (double*)a.getData(), n)); }
+  void upload(bool withFlux) {
+    const Mesh& mesh = _gm.mesh();
+    const StorageSite& cells = mesh.getCells();
+    const StorageSite& faces = mesh.getFaces();
+    const long long nt = cells.getCount(), nf = faces.getCount();
+    set(FVMGPU_FLOW_VELOCITY, _f.velocity[cells], 3 * nt);
+    set(FVMGPU_FLOW_PRESSURE, _f.pressure[cells], nt);
+    set(FVMGPU_FLOW_FACE_PRESSURE, _f.pressure[faces], nf);
+    set(FVMGPU_FLOW_DENSITY, _f.density[cells], nt);
+    set(FVMGPU_FLOW_VISCOSITY, _f.viscosity[cells], nt);
+    if (withFlux) {
+      set(FVMGPU_FLOW_MASS_FLUX, _f.massFlux[faces], nf);
+      set(FVMGPU_FLOW_CONT_RESID, _f.continuityResidual[cells], nt);
+    }
+    FlowModelOptions<double>& o = _model.getOptions();
+    if (o.transient) {
+      set(FVMGPU_FLOW_VELOCITY_N1, _f.velocityN1[cells], 3 * nt);
+      if (o.timeDiscretizationOrder > 1) set(FVMGPU_FLOW_VELOCITY_N2, _f.velocityN2[cells], 3 * nt);
+    }
+    foreach (const FaceGroupPtr fgPtr, mesh.getBoundaryFaceGroups()) {
+      const FaceGroup& fg = *fgPtr;
+      FlowBC<double>& bc = *_model.getBCMap()[fg.id];
+      double p[5] = {bc["specifiedXVelocity"], bc["specifiedYVelocity"], bc["specifiedZVelocity"], bc["specifiedPressure"],
+                     bc["accomodationCoefficient"]};
+      int kind;
+      if (bc.bcType == "NoSlipWall") kind = FVMGPU_FLOWBC_NOSLIP_WALL;
+      else if (bc.bcType == "SlipJump") { kind = FVMGPU_FLOWBC_SLIP_JUMP; p[3] = 0.0; }
+      else if (bc.bcType == "Symmetry") kind = FVMGPU_FLOWBC_SYMMETRY;
+      else if (bc.bcType == "VelocityBoundary") kind = FVMGPU_FLOWBC_VELOCITY;
+      else if (bc.bcType == "PressureBoundary") kind = FVMGPU_FLOWBC_PRESSURE;
+      else throw CException(bc.bcType + " not implemented for FlowModel");
+      check(fvmgpu_flow_set_bc(_flow, fg.id, kind, p, 5));
+    }
+  }
+  void download() {
+    const StorageSite& cells = _gm.mesh().getCells();
+    const StorageSite& faces = _gm.mesh().getFaces();
+    const long long nt = cells.getCount(), nf = faces.getCount();
+    get(FVMGPU_FLOW_VELOCITY, _f.velocity[cells], 3 * nt);
+    get(FVMGPU_FLOW_PRESSURE, _f.pressure[cells], nt);
+    get(FVMGPU_FLOW_FACE_PRESSURE, _f.pressure[faces], nf);
+    get(FVMGPU_FLOW_MASS_FLUX, _f.massFlux[faces], nf);
+    get(FVMGPU_FLOW_CONT_RESID, _f.continuityResidual[cells], nt);
+    get(FVMGPU_FLOW_PRESSURE_GRADIENT, _f.pressureGradient[cells], 3 * nt);
+    get(FVMGPU_FLOW_VELOCITY_GRADIENT, _f.velocityGradient[cells], 9 * nt);
+  }
+  GpuFlowModel(const GpuFlowModel&);
+  const GpuMesh& _gm;
+  FlowModel<double>& _model;
+  FlowFields& _f;
+  fvmgpu_flow_t _flow;
+  int _niters;
+  bool _haveInitial;
+  double _mNorm0[3], _cNorm0;
 };
 
 }  // namespace fvmgpu_adaptor

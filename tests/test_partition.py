@@ -100,3 +100,44 @@ def test_tet_block_equals_the_partition_of_the_global_mesh(dims, nparts):
         assert np.array_equal(a.cell_global[:a.n_cells], b.cell_global[:b.n_cells])
         gi = a.halo["gather_idx"]
         assert np.array_equal(a.cell_global[gi], b.cell_global[gi])
+
+
+def test_partition_replays_the_reference_parthmesh_golden():
+    """The reference partitioner's registered golden for cav32.cas on 4 ranks (T/PARALLEL_TESTS/TESTS:24,
+    PARTHMESH/QUAD_1024/proc4/GOLDEN; fixture extracted by tests/golden/make_parthmesh_golden.py): its ParMETIS cell
+    assignment is REPLAYED (ParMETIS is a missing blob of the reference tree) and partition_mesh must rebuild the
+    reference's per-rank meshes: same cell counts (256 interior + 32 boundary ghosts + 32 interface ghosts), same
+    neighbour ranks, the SAME ghost-cell (gather) lists entry for entry, and the interface faces in the same order.
+    The own-cell (scatter) lists agree entry for entry except where they name one of the first 32 interior cells of a
+    part: the golden was written by a partitioner revision that numbers those two cell rows in face-encounter order
+    (0, 1, 3, 5, ... / 2, 4, 6, ...), whereas the reference source as shipped numbers all interior cells by ascending
+    global id (preserve_cell_order, P/MeshPartitioner.cpp:1606-1635, 1706-1712) -- which is what is built here."""
+    from conftest import load_golden
+    g, h = load_golden("cav32.npz"), load_golden("parthmesh_quad1024_proc4.npz")
+    raw = G.RawMesh()
+    raw.dim, raw.n_cells, raw.n_total = 2, int(g["n_self"]), int(g["n_total"])
+    raw.face_cells = g["face_cells"]
+    raw.n_faces = len(raw.face_cells)
+    raw.group_offset, raw.group_count, raw.group_id, raw.group_kind = (g["group_offset"], g["group_count"],
+                                                                       g["group_id"], g["group_kind"])
+    raw.face_group_size = g["group_count"]
+    geo = dict(face_area=g["face_area"], face_area_mag=g["face_area_mag"], face_centroid=g["face_centroid"],
+               cell_centroid=g["cell_centroid"], cell_volume=g["cell_volume"])
+    part = h["cell_parts"][:raw.n_cells]
+    assert np.bincount(part).tolist() == [256, 256, 256, 256]
+    agree = total = 0
+    for r in range(int(h["nparts"])):
+        loc = P.partition_mesh(raw, geo, part, r)
+        H = h["halo%d" % r]
+        assert loc.n_total == int(h["nodes_cells%d" % r][1]) and loc.n_cells == 256
+        assert loc.halo["peers"].tolist() == sorted(set(H[:, 0].tolist()))
+        for k, p in enumerate(loc.halo["peers"]):
+            go, so = loc.halo["gather_off"], loc.halo["scatter_off"]
+            gi = loc.halo["gather_idx"][go[k]:go[k + 1]]
+            si = loc.halo["scatter_idx"][so[k]:so[k + 1]]
+            Hp = H[H[:, 0] == p]
+            assert np.array_equal(Hp[:, 1] - 1, gi)                 # ghost cells: identical
+            same = (Hp[:, 2] - 1) == si
+            assert np.all(same | (si < 32))                         # own cells: identical beyond the first two rows
+            agree += int(same.sum()); total += len(si)
+    assert agree >= 0.75 * total
