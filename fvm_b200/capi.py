@@ -21,7 +21,7 @@ GROUP_INTERIOR, GROUP_BOUNDARY, GROUP_INTERFACE, GROUP_SYMMETRY, GROUP_DIELECTRI
 (BC_DIRICHLET, BC_NEUMANN, BC_EXTRAPOLATION, BC_CONVECTIVE, BC_RADIATIVE, BC_MIXED, BC_INTERFACE,
  BC_DIRICHLET_OR_OUTFLOW, BC_DIELECTRIC_INTERFACE) = range(9)
 (FIELD_X, FIELD_DIFFUSIVITY, FIELD_SOURCE, FIELD_FACE_FLUX, FIELD_X_N1, FIELD_X_N2, FIELD_DENSITY,
- FIELD_CONT_RESID, FIELD_GRADIENT, FIELD_BFLUX, FIELD_DELTA, FIELD_B) = range(12)
+ FIELD_CONT_RESID, FIELD_GRADIENT, FIELD_BFLUX, FIELD_DELTA, FIELD_B, FIELD_BFLUX_BOUNDARY) = range(13)
 CYCLE_V, CYCLE_W, CYCLE_F = 0, 1, 2
 SMOOTHER_GAUSS_SEIDEL, SMOOTHER_JACOBI = 0, 1
 
@@ -68,6 +68,8 @@ SIGNATURES = {
     "fvmgpu_timer_stop": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "fvmgpu_counters": (C.c_int, [C.POINTER(C.c_longlong)] * 3),
     "fvmgpu_flush_l2": (C.c_int, []),
+    "fvmgpu_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_ulonglong]),
+    "fvmgpu_host_free": (C.c_int, [C.c_void_p]),
     "fvmgpu_profile_begin": (C.c_int, []),
     "fvmgpu_profile_end": (C.c_int, [C.c_int, C.c_char_p, C.c_int,
                                      np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS"),
@@ -221,6 +223,24 @@ class Lib:
 
     def flush_l2(self):
         self.call("fvmgpu_flush_l2")
+
+    def pinned_empty(self, shape, dtype=np.float64):
+        """numpy array in page-locked host memory (fvmgpu_host_alloc), freed with the array: field arrays allocated
+        this way go to and from the device at PCIe speed."""
+        import weakref
+        shape = (int(shape),) if np.isscalar(shape) else tuple(int(s) for s in shape)
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p(0)
+        self.call("fvmgpu_host_alloc", C.byref(p), max(nbytes, 1))
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        weakref.finalize(buf, self.dll.fvmgpu_host_free, p)
+        return arr
+
+    def pinned_full(self, shape, value, dtype=np.float64):
+        a = self.pinned_empty(shape, dtype)
+        a[...] = value
+        return a
 
     def profile_begin(self):
         self.call("fvmgpu_profile_begin")
@@ -416,6 +436,7 @@ class DeviceMesh:
         self.dim, self.n_self, self.n_total = int(dim), int(n_self), int(n_total)
         fc = _i32(face_cells).reshape(-1)
         self.n_faces = len(fc) // 2
+        self.n_interior_faces = int(group_count[0])
         self.nnz = int(cc_row[-1])
         self.group_offset = _i32(group_offset)
         self.group_count = _i32(group_count)
@@ -493,16 +514,25 @@ class DeviceSystem:
     def fill_field(self, field, value):
         self.lib.call("fvmgpu_system_fill_field", self.h, field, float(value))
 
-    def get_field(self, field):
+    def get_field(self, field, out=None):
+        """`out`: a C-contiguous float64 array of the right size to receive the values in place (no temporary)"""
         if field == FIELD_GRADIENT:
             n = 3 * self.n_total
         elif field in (FIELD_FACE_FLUX, FIELD_BFLUX):
             n = self.mesh.n_faces
+        elif field == FIELD_BFLUX_BOUNDARY:
+            n = self.mesh.n_faces - self.mesh.n_interior_faces
         else:
             n = self.n_total
-        out = np.zeros(n)
-        self.lib.call("fvmgpu_system_get_field", self.h, field, out, n)
-        return out.reshape(-1, 3) if field == FIELD_GRADIENT else out
+        if out is None or out.dtype != np.float64 or not out.flags.c_contiguous or out.size != n:
+            res = np.empty(n)
+            self.lib.call("fvmgpu_system_get_field", self.h, field, res, n)
+            if out is not None:
+                out.reshape(-1)[:] = res
+                return out
+            return res.reshape(-1, 3) if field == FIELD_GRADIENT else res
+        self.lib.call("fvmgpu_system_get_field", self.h, field, out.reshape(-1), n)
+        return out
 
     def set_bc(self, group_id, kind, params=(), per_face=None):
         p = _f64(list(params) + [0.0] * (4 - len(params)))

@@ -626,6 +626,13 @@ void systemGetField(System* s, int field, double* host, long long n) {
     tmp.download(host, tmp.n);
     return;
   }
+  if (field == FVMGPU_FIELD_BFLUX_BOUNDARY) {
+    if (!s->mesh) fail("get_field: raw systems have no boundary flux");
+    const size_t nb = (size_t)(s->mesh->nFaces - s->mesh->nInteriorFaces);
+    if ((size_t)n != nb) fail("get_field: boundary flux (boundary faces) expects %zu values", nb);
+    s->bflux.download(host, nb);
+    return;
+  }
   if (field == FVMGPU_FIELD_BFLUX) {
     if (!s->mesh) fail("get_field: raw systems have no boundary flux");
     // laid out over ALL faces like the reference's per-group heatFlux arrays concatenated;

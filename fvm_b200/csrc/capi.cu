@@ -158,6 +158,26 @@ int fvmgpu_counters(long long* kernel_launches, long long* h2d_bytes, long long*
   if (d2h_bytes) *d2h_bytes = ctx().d2h;
   return 0;
 }
+int fvmgpu_host_alloc(void** out, unsigned long long bytes) {
+  API_BEGIN
+  if (!out) fail("host_alloc: null output");
+#ifdef FVMGPU_HOSTSIM
+  *out = std::malloc(bytes ? bytes : 1);
+#else
+  requireReady();
+  CUDA_CHECK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+#endif
+  API_END
+}
+int fvmgpu_host_free(void* p) {
+  API_BEGIN
+#ifdef FVMGPU_HOSTSIM
+  std::free(p);
+#else
+  if (p) CUDA_CHECK(cudaFreeHost(p));
+#endif
+  API_END
+}
 int fvmgpu_flush_l2(void) {
   API_BEGIN
   requireReady();

@@ -513,13 +513,18 @@ class ThermalModelA:
             cells, faces = mesh.getCells(), mesh.getFaces()
             n = cells.getCount()
             vc = self._vcMap[mesh.getID()]
-            f.temperature[cells] = np.full(n, float(o["initialTemperature"]))
+            if mesh.device is None:
+                raise CException("ThermalModel.init: mesh metrics not initialised (MeshMetricsCalculatorA.init)")
+            hostlib = self.lib or mesh.device.lib
+            # the fields that travel every advance() live in page-locked memory (the reference's Array<T> storage
+            # allocated with fvmgpu_host_alloc): scripts see ordinary numpy arrays
+            f.temperature[cells] = hostlib.pinned_full(n, float(o["initialTemperature"]))
             if o.transient:
                 f.temperatureN1[cells] = f.temperature[cells].copy()
                 if o.timeDiscretizationOrder > 1:
                     f.temperatureN2[cells] = f.temperature[cells].copy()
-            f.conductivity[cells] = np.full(n, float(vc["thermalConductivity"]))
-            f.source[cells] = np.zeros(n)
+            f.conductivity[cells] = hostlib.pinned_full(n, float(vc["thermalConductivity"]))
+            f.source[cells] = hostlib.pinned_full(n, 0.0)
             f.specificHeat[cells] = np.full(n, float(vc["density"]) * float(vc["specificHeat"]))
             f.temperatureGradient[cells] = np.zeros((n, 3))
             f.convectionFlux[faces] = np.zeros(faces.getCount())
@@ -540,7 +545,7 @@ class ThermalModelA:
         ls.set_field(capi.FIELD_DIFFUSIVITY, f.conductivity[cells])
         ls.set_field(capi.FIELD_SOURCE, f.source[cells])
         flux = f.convectionFlux[faces]
-        self._convecting = bool(np.any(flux != 0.0))
+        self._convecting = bool(flux.any())   # (no temporary: the face array of a 256^3 mesh has 50 M entries)
         if self._convecting:
             ls.set_field(capi.FIELD_FACE_FLUX, flux)
         if o.transient:
@@ -582,10 +587,11 @@ class ThermalModelA:
     def _download(self, mesh, ls):
         f = self.fields
         cells = mesh.getCells()
-        f.temperature[cells][:] = ls.get_field(capi.FIELD_X)
-        bflux = ls.get_field(capi.FIELD_BFLUX)
+        ls.get_field(capi.FIELD_X, out=f.temperature[cells])          # straight into the field array
+        bflux = ls.get_field(capi.FIELD_BFLUX_BOUNDARY)               # boundary faces only
+        ni = mesh.getFaces().getCount() - len(bflux)
         for fg in mesh.getBoundaryFaceGroups():
-            o = fg.site.getOffset()
+            o = fg.site.getOffset() - ni
             f.heatFlux[fg.site][:] = bflux[o:o + fg.site.getCount()]
 
     def _assemble(self, ls):

@@ -71,7 +71,8 @@ enum {
   FVMGPU_FIELD_BFLUX = 9,      /* nFaces: boundary flux unknowns (heatFlux, ls.getX()[fIndex]) -- output*/
   FVMGPU_FIELD_DELTA = 10,     /* nCellsTotal  (ls.getDelta())                                        */
   FVMGPU_FIELD_B = 11,         /* nCellsTotal  (ls.getB())                                            */
-  FVMGPU_FIELD_COUNT = 12
+  FVMGPU_FIELD_BFLUX_BOUNDARY = 12, /* nFaces - nInteriorFaces: FIELD_BFLUX without the interior faces' zeros -- output */
+  FVMGPU_FIELD_COUNT = 13
 };
 
 /* ---- assembly options: which Discretization objects of the list are present
@@ -126,6 +127,10 @@ int fvmgpu_timer_stop(int slot, double* ms);/* records, synchronizes the stop ev
 /* counts of kernels the library launched / bytes copied since init (gpu_launches claim) */
 int fvmgpu_counters(long long* kernel_launches, long long* h2d_bytes, long long* d2h_bytes);
 int fvmgpu_flush_l2(void);                  /* writes a 256 MiB scratch buffer (> 126 MB L2) */
+/* page-locked host memory for the caller's field arrays (the reference's Array<T> storage, F/Array.h:22-54, would be
+ * allocated with this instead of new[]): copies to and from it run at PCIe speed and need no staging */
+int fvmgpu_host_alloc(void** out, unsigned long long bytes);
+int fvmgpu_host_free(void* p);
 /* per-launch profiler: between begin and end every kernel launch is bracketed by CUDA events on
  * the compute stream; end returns one record per (kernel class, rows): names[i*nameStride..] is
  * the (mangled) functor name, rows[i] the logical threads, launches[i], ms[i] the summed duration */
