@@ -211,6 +211,13 @@ int main(int argc, char** argv) {
 
     // ---- 5. FlowModel::advance on the device, driven by the reference's own FlowModel object
     {
+      // single-rank identity local <-> global cell maps: the -DFVM_PARALLEL build of FlowModel reads them in
+      // setDirichlet (F/FlowModel_impl.h:931-968); MeshPartitioner fills them even for one part, the raw Mesh ctor not
+      if (!mesh->getLocalToGlobalPtr()) {
+        mesh->createLocalGlobalArray();
+        Array<int>& l2g = mesh->getLocalToGlobal();
+        for (int i = 0; i < cells.getCount(); i++) { l2g[i] = i; mesh->getGlobalToLocal()[i] = i; }
+      }
       FlowFields ffRef("flow"), ffGpu("flow");
       FlowModel<double> fmRef(geom, ffRef, meshes), fmGpu(geom, ffGpu, meshes);
       FlowModel<double>* both[2] = {&fmRef, &fmGpu};

@@ -492,8 +492,9 @@ class GpuFlowModel {
     get(FVMGPU_FLOW_FACE_PRESSURE, _f.pressure[faces], nf);
     get(FVMGPU_FLOW_MASS_FLUX, _f.massFlux[faces], nf);
     get(FVMGPU_FLOW_CONT_RESID, _f.continuityResidual[cells], nt);
-    get(FVMGPU_FLOW_PRESSURE_GRADIENT, _f.pressureGradient[cells], 3 * nt);
-    get(FVMGPU_FLOW_VELOCITY_GRADIENT, _f.velocityGradient[cells], 9 * nt);
+    // (the gradient fields get their arrays from the reference's GradientModel on first use: mirrored when present)
+    if (_f.pressureGradient.hasArray(cells)) get(FVMGPU_FLOW_PRESSURE_GRADIENT, _f.pressureGradient[cells], 3 * nt);
+    if (_f.velocityGradient.hasArray(cells)) get(FVMGPU_FLOW_VELOCITY_GRADIENT, _f.velocityGradient[cells], 9 * nt);
   }
   GpuFlowModel(const GpuFlowModel&);
   const GpuMesh& _gm;

@@ -22,3 +22,20 @@ def test_reference_thermal_model_with_gpu_solver_and_linearizer(n):
     print(r.stdout, r.stderr)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "adaptor_test: OK" in r.stdout
+
+
+def test_adaptor_glue_against_the_host_simulator():
+    """The same binary linked with the TEST-ONLY host simulator of the library (oracle/Makefile adaptor_hostsim): the
+    reference-side glue -- GpuAMG / GpuBCGStab as LinearSolvers of the reference's ThermalModel, GpuScalarLinearizer,
+    the device-resident outer iteration and GpuFlowModel driven by the reference's own FlowModel object -- runs on the
+    GPU-less box against the reference classes compiled in place."""
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("reference tree not mounted")
+    from fvm_b200 import build
+    build.build_hostsim()
+    mk = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "adaptor_hostsim"], capture_output=True, text=True)
+    assert mk.returncode == 0, mk.stdout + mk.stderr
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "adaptor_test_hostsim"), "16"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "adaptor_test: OK" in r.stdout, r.stdout + r.stderr
+    assert r.stdout.count(" OK") >= 6
