@@ -65,6 +65,9 @@ def parse():
     p.add_argument("--workload", choices=("thermal", "cavity", "electric-tet"), default="thermal",
                    help="thermal: the headline (BASELINE configs[1] / [3]); cavity: configs[2], FlowModel SIMPLE on a 2048^2 quad "
                         "mesh; electric-tet: configs[4], ElectricModel on a tet box partitioned over the GPUs (bench_workloads.py)")
+    p.add_argument("--global-size", type=int, default=0,
+                   help="STRONG scaling: one fixed G^3 hex box (e.g. 512: BASELINE configs[3]) cut into z-slabs over the GPUs "
+                        "instead of --size cells per side per GPU; the line then says scaling = strong")
     p.add_argument("--mesh", choices=("hex", "tet"), default="hex",
                    help="tet: the same box cut into 6 jittered tetrahedra per hex (unstructured numbering of the "
                         "coarse levels; single GPU; not the headline workload)")
@@ -125,9 +128,15 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- workload
+GLOBAL_SIZE = 0
+
+
 def global_dims(n, world):
     """Weak scaling: n^3 cells per GPU; the box doubles along x, then y, then z with the GPU count
-    (8 GPUs at n = 256: the 512^3 mesh of BASELINE.json configs[3]); z-slab partition."""
+    (8 GPUs at n = 256: the 512^3 mesh of BASELINE.json configs[3]); z-slab partition.
+    --global-size G: the box is G^3 whatever the GPU count (strong scaling)."""
+    if GLOBAL_SIZE:
+        return [GLOBAL_SIZE, GLOBAL_SIZE, GLOBAL_SIZE]
     dims = [n, n, n]
     k, axis = world, 0
     while k > 1:
@@ -154,10 +163,12 @@ def build_case(n, lib, rank=0, world=1):
             raise SystemExit("--mesh tet runs on one GPU (use tests/test_multigpu.py for partitioned tets)")
         raw = G.tet_mesh(n, n, n)
     elif world == 1:
-        raw = G.hex_mesh(n, n, n)
+        g = GLOBAL_SIZE or n
+        raw = G.hex_mesh(g, g, g)
     else:
         nx, ny, nz = global_dims(n, world)
-        raw = P.hex_slab(nx, ny, nz, rank, world, nx / n, ny / n, nz / n, lib=lib)
+        unit = GLOBAL_SIZE or n
+        raw = P.hex_slab(nx, ny, nz, rank, world, nx / unit, ny / unit, nz / unit, lib=lib)
     meshes = [M.Mesh(raw)]
     geom = M.GeomFields("geom")
     M.MeshMetricsCalculatorA(geom, meshes, lib=lib).init()
@@ -289,7 +300,7 @@ def run_ours(args):
     x = fields.temperature[cells]
     # ---- parity (collective: all ranks)
     zc = np.asarray(geom.coordinate[cells])[:, 2]
-    lz = global_dims(n, world)[2] / n if MESH == "hex" else 1.0
+    lz = global_dims(n, world)[2] / (GLOBAL_SIZE or n) if MESH == "hex" else 1.0
     parity = parity_block(lib, rank, world, np.asarray(x), zc, lz, ncells, getattr(args, "parity_size", 64))
     # ---- profiled step for the roofline of the dominant kernel
     roof = None
@@ -325,7 +336,8 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": ncells * world * args.steps / max(total_ms * 1e-3, 1e-12), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if GLOBAL_SIZE else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
         "config": {"workload": ("3D steady thermal diffusion, %s " + mesh_desc + " (%d cells, %d per GPU), k=1, "
                                 "T=400/300 on z=top/z=0, %sAMG (V-cycle, multicolour GS, nPre 0 / nPost 1, group 2) "
                                 "to rel 1e-8, one outer iteration per step")
@@ -333,8 +345,9 @@ def run_ours(args):
                                   "BCGStab preconditioned by one cycle of " if KRYLOV else ""),
                    "cells_per_gpu": ncells, "l2": "inputs (>= 1.8 GB of matrix per pass) exceed the 126 MB L2; "
                                                   "L2 flushed between warm-up steps",
-                   "parallelism": ("z-slab domain decomposition, one part per GPU, NCCL halo exchange per colour "
-                                   "pass + all-reduced norms, coarse levels merged and solved replicated")
+                   "parallelism": ("z-slab domain decomposition, one part per GPU; halo values stored straight into the "
+                                   "neighbour's memory over NVLink (device-initiated, one flag per exchange) after every "
+                                   "half-sweep, norms all-reduced the same way, coarse levels merged and solved replicated")
                    if world > 1 else "single"},
         "time_to_converge_s": ms_per_step * 1e-3, "step_ms": [round(s_["total_ms"], 3) for s_ in steps],
         "solve_split_ms": {"hierarchy_setup": [round(s_["setup_ms"], 2) for s_ in steps],
@@ -670,6 +683,7 @@ if __name__ == "__main__":
     KRYLOV = bool(a.krylov)
     MESH = a.mesh
     WORKLOAD = a.workload
+    GLOBAL_SIZE = a.global_size
     if a._worker:
         print(json.dumps(_ref_worker(a.ref_n, a.steps)))
     elif a.impl == "reference":

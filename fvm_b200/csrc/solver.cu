@@ -1850,7 +1850,9 @@ void Amg::buildTail() {
   int coopRows = 1200000;
   if (const char* e = getenv("FVMGPU_COOP_ROWS")) coopRows = atoi(e);
   int start = nl;
-  while (start > 1 && levels[start - 1]->n <= kTailRows) start--;
+  int tailRows = kTailRows;   // rows a level may have to be worked by ONE CTA (FVMGPU_TAIL_ROWS: measurement knob)
+  if (const char* e = getenv("FVMGPU_TAIL_ROWS")) tailRows = atoi(e);
+  while (start > 1 && levels[start - 1]->n <= tailRows) start--;
   int cstart = start;
   while (cstart > 1 && levels[cstart - 1]->n <= coopRows) cstart--;
   tailIsCoop = cstart < start;   // some levels are too large for one CTA: use the cooperative grid for the stretch
@@ -1887,7 +1889,7 @@ void Amg::buildTail() {
   tailCount = nl - start;
   tailGridLevels = 0;
   if (tailIsCoop) {
-    while (tailGridLevels < tailCount - 1 && levels[start + tailGridLevels]->n > kTailRows) tailGridLevels++;
+    while (tailGridLevels < tailCount - 1 && levels[start + tailGridLevels]->n > tailRows) tailGridLevels++;
     if (!coopBarrier.p) coopBarrier.alloc(4);
   }
 #endif

@@ -35,7 +35,9 @@ def main():
         ds.set_bc(g, X.BC_NEUMANN, [0.0])
     ds.assemble()
     o = lib.default_amg_opts()
-    o.maxCoarseLevels, o.nMaxIterations, o.relativeTolerance = 0, 6, 1e-30
+    # optional second argument: number of coarse levels to keep (1: the level-0 restriction / prolongation kernels
+    # InjectRows / CorrectRows appear as well)
+    o.maxCoarseLevels, o.nMaxIterations, o.relativeTolerance = (int(sys.argv[2]) if len(sys.argv) > 2 else 0), 6, 1e-30
     amg = X.DeviceAMG(lib, o)
     r0, r, it = amg.solve(ds)
     print("level-0 only: %d sweeps, residual %g -> %g, colours %s" % (it, r0, r, amg.levels()["colours"]))
