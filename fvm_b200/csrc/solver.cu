@@ -2996,6 +2996,7 @@ void Amg::runMultiGraph(const std::function<void()>& body, int nc) {
 }
 
 bool Amg::multiRhsSupported() const {
+  if (const char* e = getenv("FVMGPU_MULTI_RHS")) { if (atoi(e) == 0) return false; }   // A/B switch: component by component
   return !multi && opts.cycleType == FVMGPU_CYCLE_V && opts.smootherType == FVMGPU_SMOOTHER_GAUSS_SEIDEL && !g_referenceOrder;
 }
 
