@@ -283,8 +283,9 @@ int fvmgpu_electric_drift_flux(fvmgpu_system_t potential, fvmgpu_system_t charge
 
 /* ---- FlowModel (SIMPLE): momentum + pressure-correction hot path (F/FlowModel_impl.h:522-1471,
  *      F/FlowModelInterior.h, F/FlowModelVelocityBC.h, F/MomentumPressureGradientDiscretization.h).
- *      Boundary types: NoSlipWall, Symmetry, VelocityBoundary, PressureBoundary (SlipJump is not
- *      built). One GPU per model in this release. Vector cell fields are AoS (Vector<T,3>,
+ *      Boundary types: NoSlipWall, Symmetry, VelocityBoundary, PressureBoundary, SlipJump. On several
+ *      ranks (fvmgpu_comm_init) every rank holds the model of its mesh part and makes the same sequence
+ *      of calls. Vector cell fields are AoS (Vector<T,3>,
  *      F/Vector.h:229; Gradient<Vector<T,3>> = 9 doubles [direction][component], F/Gradient.h:199). ---- */
 typedef struct fvmgpu_flow_s* fvmgpu_flow_t;  /* FlowFields of one mesh + the two linear systems */
 enum {
@@ -366,10 +367,16 @@ int fvmgpu_flow_solve_continuity(fvmgpu_flow_t flow, fvmgpu_solver_t solver, int
 /* ---- multi-GPU (one process per GPU, one mesh part per GPU; NCCL resolved at run time with dlopen)
  * The reference's MPI layer maps as follows (all stream ordered, no host staging):
  *   MultiField::sync / Field::syncLocal  (Isend/Irecv of packed ghosts, F/MultiField.cpp:488-551,
- *       F/Field.cpp:333-394)                    -> pack kernel + grouped ncclSend/ncclRecv + unpack kernel
- *   MultiFieldReduction::reduceSum (Allreduce SUM, F/MultiFieldReduction.cpp:213-225) -> ncclAllReduce
+ *       F/Field.cpp:333-394)    -> ONE kernel that gathers the interface rows, stores them into the neighbour's
+ *                                  memory over NVLink (CUDA IPC peer mapping), raises a flag there, waits for the
+ *                                  neighbour's flag and scatters what arrived into the ghost cells (csrc/peer.cuh)
+ *   MultiFieldReduction::reduceSum (Allreduce SUM, F/MultiFieldReduction.cpp:213-225)
+ *                               -> every rank stores its partial sums into all peers and adds them in rank order
  *   LinearSystemMerger (coarse levels gathered below a size threshold, F/LinearSystemMerger.cpp)
- *                                               -> coarse level all-gathered and solved replicated
+ *                               -> coarse level all-gathered (peer stores) and solved replicated
+ * The peer-memory transport needs all ranks on one node with peer access (NVLink / NVSwitch); otherwise, or with
+ * FVMGPU_PEER=0, the same steps run as pack kernel + grouped ncclSend/ncclRecv + unpack kernel / ncclAllReduce /
+ * ncclAllGather. NCCL is also what carries the IPC handles at set-up.
  * After fvmgpu_comm_init with nranks > 1, every rank must make the same sequence of solver /
  * assembly calls on meshes that carry halo maps (fvmgpu_mesh_set_halo). */
 int fvmgpu_comm_unique_id(void* out128);                               /* ncclGetUniqueId      */
