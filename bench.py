@@ -567,7 +567,7 @@ def roofline(recs, step):
             "share_of_step": ms / step["total_ms"]}
     # DRAM traffic of that kernel from the committed `ncu --set full` capture (per launch), when the
     # capture was taken on this workload size
-    tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
     if os.path.exists(tpath):
         t = json.load(open(tpath))
         g = t.get("GsRows_level0", {})

@@ -116,8 +116,9 @@ def _cavity_model(lib, n, mu):
     return raw, mesh, ff, fm
 
 
-def _cavity_reference(n, mu, iters, tight):
-    """oracle/_ref: the reference's FlowModel<double> on the same cavity. Returns (seconds per iteration, fields)."""
+def _cavity_reference(n, mu, iters, tight, pressure_kind=0):
+    """oracle/_ref: the reference's FlowModel<double> on the same cavity. Returns (seconds per iteration, fields).
+    pressure_kind: refapi solver kind of the pressure-correction solver when tight (0 = AMG, 1 = BCGStab + AMG)."""
     from fvm_b200 import meshgen as G
     from oracle import refapi as R
     raw = G.quad_mesh(n, n)
@@ -134,7 +135,7 @@ def _cavity_reference(n, mu, iters, tight):
     if tight:
         cfg = dict(relativeTolerance=1e-13, nMaxIterations=3000, verbosity=0)
         f.set_solver(0, R.solver_cfg(**cfg))
-        f.set_solver(1, R.solver_cfg(**cfg))
+        f.set_solver(1, R.solver_cfg(kind=pressure_kind, **cfg))
     f.init()
     t0 = time.perf_counter()
     f.advance(iters)

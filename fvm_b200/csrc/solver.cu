@@ -131,7 +131,9 @@ __device__ __forceinline__ void traceStamp(int tag) {
     }
   }
 }
-struct GridSync {
+template <int UU>
+struct GridSyncT {
+  static constexpr int U = UU;   // rows a thread works together (tailRowBatch)
   unsigned* bar;
   __device__ __forceinline__ long long tid() const { return (long long)blockIdx.x * blockDim.x + threadIdx.x; }
   __device__ __forceinline__ long long stride() const { return (long long)gridDim.x * blockDim.x; }
@@ -1657,7 +1659,9 @@ struct TailLevelT {
 typedef TailLevelT<double> TailLevel;
 constexpr int kTailThreads = 512;  // CTA size of the fused kernels (127 registers, no spills; 1024 threads = 64 registers spilled and lost)
 
-struct CtaSync {   // one CTA
+template <int UU>
+struct CtaSyncT {   // one CTA
+  static constexpr int U = UU;
   __device__ __forceinline__ long long tid() const { return threadIdx.x; }
   __device__ __forceinline__ long long stride() const { return blockDim.x; }
   __device__ __forceinline__ void sync(int tag = 0) const { __syncthreads(); traceStamp(tag); }
@@ -1670,6 +1674,70 @@ __device__ __forceinline__ V tailRowAcc(const TailLevelT<V>& L, int r, const V* 
   V sum = init;
   for (int p = L.sliceOff[s] + (r & 31); p < end; p += 32) vaxpy(sum, L.sval[p], x[L.scol[p]]);
   return sum;
+}
+// U rows of one thread (r, r + st, ...) worked TOGETHER: a thread of the fused kernels owns several rows of a pass, and
+// one row after the other leaves the whole load latency of each (slice offsets -> entries -> x gathers) exposed --
+// the 1 M-row level ran at 2.5 TB/s. Here the loads of U independent rows are in flight at once; every row still
+// accumulates its own entries in entry order (bit-identical to the one-row loop).
+// MODE 0: x_r = -(b_r + sum_j a_rj x_j) / d_r     MODE 1: r_r = b_r + d_r x_r + sum_j a_rj x_j
+template <class V, class S> struct TailBatch {   // Vector<T,3> rows: one at a time (two spill 320 bytes)
+  static constexpr int U = sizeof(V) == sizeof(double) ? S::U : (sizeof(V) <= 2 * sizeof(double) && S::U >= 2 ? 2 : 1);
+};
+template <int MODE, int U, class V>
+__device__ __forceinline__ void tailRowBatch(const TailLevelT<V>& L, long long r, long long st, long long r1, bool xZero) {
+  int p[U], e[U];
+  V sum[U];
+  double d[U];
+  bool any = false;
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const long long row = r + u * st;
+    p[u] = 0; e[u] = 0; d[u] = 1.0;
+    vset0(sum[u]);
+    if (row < r1) {
+      const int s = (int)(row >> 5);
+      p[u] = L.sliceOff[s] + (int)(row & 31);
+      e[u] = L.sliceOff[s + 1];
+      sum[u] = L.b[row];
+      d[u] = L.diag[row];
+    }
+  }
+  if (MODE == 1) {
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (r + u * st < r1) vaxpy(sum[u], d[u], L.x[r + u * st]);
+  }
+  if (MODE == 1 || !xZero) {
+#pragma unroll
+    for (int u = 0; u < U; u++) any |= p[u] < e[u];
+    while (any) {
+      int col[U];
+      double val[U];
+      V xv[U];
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (p[u] < e[u]) { col[u] = L.scol[p[u]]; val[u] = L.sval[p[u]]; }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (p[u] < e[u]) xv[u] = L.x[col[u]];
+      any = false;
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (p[u] < e[u]) {
+          vaxpy(sum[u], val[u], xv[u]);
+          p[u] += 32;
+          any |= p[u] < e[u];
+        }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const long long row = r + u * st;
+    if (row < r1) {
+      if (MODE == 0) L.x[row] = vnegdiv(sum[u], d[u]);
+      else L.r[row] = sum[u];
+    }
+  }
 }
 // Everything a colour pass needs of its FIRST row except the x values: loaded BEFORE the barrier that
 // ends the previous pass (the matrix, b and diag do not change during a cycle), so that after the
@@ -1732,11 +1800,7 @@ __device__ void tailSweeps(const TailLevelT<V>& L, int nSweeps, int smoother, bo
           if (!xZero) sum = tailRowAcc(L, (int)r, L.x, sum);
         }
         L.x[r] = vnegdiv(sum, d);
-        for (r += st; r < r1; r += st) {
-          V s2 = L.b[r];
-          if (!xZero) s2 = tailRowAcc(L, (int)r, L.x, s2);
-          L.x[r] = vnegdiv(s2, L.diag[r]);
-        }
+        for (r += st; r < r1; r += TailBatch<V, S>::U * st) tailRowBatch<0, TailBatch<V, S>::U>(L, r, st, r1, xZero);
       }
       xZero = false;
       lastColour = c;
@@ -1769,21 +1833,40 @@ __device__ void stretchDown(const TailLevelT<V>* lv, int l0, int l1, int nPre, i
     tailSweeps(L, nPre, smoother, xZero, sy, l << 8);
     const V* src = L.b;
     if (!xZero) {  // r = b + A x
-      for (long long r = t0; r < L.n; r += st) {
-        V init = L.b[r];
-        vaxpy(init, L.diag[r], L.x[r]);
-        L.r[r] = tailRowAcc(L, (int)r, L.x, init);
-      }
+      for (long long r = t0; r < L.n; r += TailBatch<V, S>::U * st) tailRowBatch<1, TailBatch<V, S>::U>(L, r, st, L.n, false);
       sy.sync((l << 8) | 2);
       src = L.r;
     }
-    for (long long I = t0; I < C.n; I += st) {
-      V s;
-      vset0(s);
-      for (int p = L.memOff[I]; p < L.memOff[I + 1]; p++) vadd(s, src[L.mem[p]]);
-      const int rc = L.cpos[I];
-      C.b[rc] = s;
-      vset0(C.x[rc]);
+    constexpr int U = TailBatch<V, S>::U;   // U aggregates of a thread together (see tailRowBatch)
+    for (long long I = t0; I < C.n; I += U * st) {
+      int m0[U], m1[U], rc[U];
+      V s[U];
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const long long Iu = I + u * st;
+        m0[u] = 0; m1[u] = 0; rc[u] = -1;
+        vset0(s[u]);
+        if (Iu < C.n) { m0[u] = L.memOff[Iu]; m1[u] = L.memOff[Iu + 1]; rc[u] = L.cpos[Iu]; }
+        any |= m0[u] < m1[u];
+      }
+      while (any) {
+        int idx[U];
+        V v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (m0[u] < m1[u]) idx[u] = L.mem[m0[u]];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (m0[u] < m1[u]) v[u] = src[idx[u]];
+        any = false;
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (m0[u] < m1[u]) { vadd(s[u], v[u]); m0[u]++; any |= m0[u] < m1[u]; }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (rc[u] >= 0) { C.b[rc[u]] = s[u]; vset0(C.x[rc[u]]); }
     }
     sy.sync((l << 8) | 1);
   }
@@ -1806,9 +1889,18 @@ __device__ void stretchUp(const TailLevelT<V>* lv, int l0, int l1, int nPost, in
     // phase -- was measured with the phase trace: the pass then costs 7-9 us instead of 0.8 us even on a level of 8
     // rows, because its three dependent gathers per entry miss to DRAM one after the other, while this streaming
     // phase costs 2 us and leaves the pass its prefetched operands.)
-    for (long long i = t0; i < L.n; i += st) {
-      const int c = L.ci[i];
-      if (c >= 0) vadd(L.x[i], C.x[c]);
+    constexpr int U = TailBatch<V, S>::U;
+    for (long long i = t0; i < L.n; i += U * st) {
+      int c[U];
+      V xc[U], xf[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) c[u] = i + u * st < L.n ? L.ci[i + u * st] : -1;
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (c[u] >= 0) { xc[u] = C.x[c[u]]; xf[u] = L.x[i + u * st]; }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        if (c[u] >= 0) { vadd(xf[u], xc[u]); L.x[i + u * st] = xf[u]; }
     }
     sy.sync((l << 8) | 3);
     bool xZero = false;
@@ -1816,23 +1908,23 @@ __device__ void stretchUp(const TailLevelT<V>* lv, int l0, int l1, int nPost, in
   }
 }
 // on entry: level 0 of the stretch has b set and x == 0
-template <class V, int THREADS>
+template <class V, int THREADS, int U>
 __global__ void __launch_bounds__(THREADS) k_tail_vcycle(const TailLevelT<V>* lv, int nLevels, int nPre, int nPost,
                                                            int smoother) {
-  CtaSync sy;
+  CtaSyncT<U> sy;
   stretchDown(lv, 0, nLevels - 1, nPre, smoother, sy);
   stretchBottom(lv, nLevels - 1, nPre, nPost, smoother, sy);
   stretchUp(lv, 0, nLevels - 1, nPost, smoother, sy);
 }
 // levels [0, nGrid) by the whole grid, levels [nGrid, nLevels) by CTA 0 alone (they have <= kTailRows
 // rows: one CTA is enough and its barrier is __syncthreads())
-template <class V, int THREADS>
+template <class V, int THREADS, int U>
 __global__ void __launch_bounds__(THREADS) k_coop_vcycle(const TailLevelT<V>* lv, int nLevels, int nGrid, int nPre,
                                                            int nPost, int smoother, unsigned* bar) {
-  GridSync gs{bar};
+  GridSyncT<U> gs{bar};
   stretchDown(lv, 0, nGrid, nPre, smoother, gs);   // ends with a grid barrier after filling level nGrid's b
   if (blockIdx.x == 0) {
-    CtaSync cs;
+    CtaSyncT<U> cs;
     stretchDown(lv, nGrid, nLevels - 1, nPre, smoother, cs);
     stretchBottom(lv, nLevels - 1, nPre, nPost, smoother, cs);
     stretchUp(lv, nGrid, nLevels - 1, nPost, smoother, cs);
@@ -1841,6 +1933,16 @@ __global__ void __launch_bounds__(THREADS) k_coop_vcycle(const TailLevelT<V>* lv
   stretchUp(lv, 0, nGrid, nPost, smoother, gs);
 }
 #endif
+
+// rows of one thread worked together in the fused kernels (tailRowBatch); FVMGPU_TAIL_BATCH = 1 | 2 | 4: measurement knob
+static int tailBatchWidth() {
+  static int u = 0;
+  if (!u) {
+    u = 2;
+    if (const char* e = getenv("FVMGPU_TAIL_BATCH")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) u = v; }
+  }
+  return u;
+}
 
 void Amg::buildTail() {
   tailStart = -1;
@@ -1861,7 +1963,7 @@ void Amg::buildTail() {
     if (coopOk < 0) {
       int perSm = 0, dev = ctx().device, attr = 0;
       cudaDeviceGetAttribute(&attr, cudaDevAttrCooperativeLaunch, dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_coop_vcycle<double, kTailThreads>, kTailThreads, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_coop_vcycle<double, kTailThreads, 4>, kTailThreads, 0);
       coopOk = (attr && perSm >= 1) ? 1 : 0;
     }
     if (coopOk) start = cstart; else tailIsCoop = false;
@@ -1943,11 +2045,17 @@ void Amg::runTail() {
     unsigned* bar = coopBarrier.p;
     devMemset(bar, 0, sizeof(unsigned));
     void* args[] = {(void*)&lv, &cnt, &nGrid, &nPre, &nPost, &sm, &bar};
-    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coop_vcycle<double, kTailThreads>, dim3(ctx().smCount), dim3(kTailThreads), args, 0,
-                                           ctx().stream));
+    const int U = tailBatchWidth();
+    const void* fn = U == 1 ? (const void*)k_coop_vcycle<double, kTailThreads, 1>
+                   : U == 2 ? (const void*)k_coop_vcycle<double, kTailThreads, 2>
+                            : (const void*)k_coop_vcycle<double, kTailThreads, 4>;
+    CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(ctx().smCount), dim3(kTailThreads), args, 0, ctx().stream));
   } else {
     ProfileScope prof("N6fvmgpu13k_tail_vcycleE", levels[tailStart]->n);
-    k_tail_vcycle<double, kTailThreads><<<1, kTailThreads, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
+    const int U = tailBatchWidth();
+    if (U == 1) k_tail_vcycle<double, kTailThreads, 1><<<1, kTailThreads, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
+    else if (U == 2) k_tail_vcycle<double, kTailThreads, 2><<<1, kTailThreads, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
+    else k_tail_vcycle<double, kTailThreads, 4><<<1, kTailThreads, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
     CUDA_CHECK(cudaGetLastError());
   }
   ctx().launches++;
@@ -2823,11 +2931,11 @@ void runTailN(Amg& A) {
     unsigned* bar = A.coopBarrier.p;
     devMemset(bar, 0, sizeof(unsigned));
     void* args[] = {(void*)&lv, &cnt, &nGrid, &nPre, &nPost, &sm, &bar};
-    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coop_vcycle<V, kTailThreads>, dim3(ctx().smCount), dim3(kTailThreads), args, 0,
+    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coop_vcycle<V, kTailThreads, 2>, dim3(ctx().smCount), dim3(kTailThreads), args, 0,
                                            ctx().stream));
   } else {
     ProfileScope prof("N6fvmgpu14k_tail_vcycleNE", A.levels[A.tailStart]->n);
-    k_tail_vcycle<V, kTailThreads><<<1, kTailThreads, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
+    k_tail_vcycle<V, kTailThreads, 2><<<1, kTailThreads, 0, ctx().stream>>>(lv, cnt, nPre, nPost, sm);
     CUDA_CHECK(cudaGetLastError());
   }
   ctx().launches++;

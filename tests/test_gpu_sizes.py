@@ -34,17 +34,21 @@ def test_thermal_hex_above_the_cooperative_row_limit(lib_and_gpu, ref, monkeypat
 
 
 def test_cavity_128_three_simple_iterations(lib_and_gpu, ref):
-    """128^2 lid-driven cavity, 3 SIMPLE iterations with converged inner solves on both sides (multi-RHS momentum
-    cycles, pressure correction with the reference cell pinned)."""
+    """128^2 lid-driven cavity, 3 SIMPLE iterations with converged inner solves on both sides: momentum by AMG
+    (the multi-RHS cycles), pressure correction (reference cell pinned) by BCGStab + AMG -- plain V(0,1) cycles
+    contract this system by only 0.995 per cycle at 128^2, on either side, and do not reach 1e-13."""
     from fvm_b200 import models as M
     lib, gpu = lib_and_gpu
     n, mu = (128 if gpu else 16), 0.01
-    _, r = W._cavity_reference(n, mu, 3, tight=True)
+    _, r = W._cavity_reference(n, mu, 3, tight=True, pressure_kind=1)
     _, mesh, ff, fm = W._cavity_model(lib, n, mu)
-    for nm in ("momentumLinearSolver", "pressureLinearSolver"):
-        s = M.AMG()
+    o = fm.getOptions()
+    o.momentumLinearSolver = M.AMG()
+    o.pressureLinearSolver = M.BCGStab()
+    o.pressureLinearSolver.preconditioner = M.AMG()
+    o.pressureLinearSolver.preconditioner.verbosity = 0
+    for s in (o.momentumLinearSolver, o.pressureLinearSolver):
         s.relativeTolerance, s.nMaxIterations, s.verbosity = 1e-13, 3000, 0
-        setattr(fm.getOptions(), nm, s)
     with contextlib.redirect_stdout(io.StringIO()):
         fm.advance(3)
     cells, nn = mesh.getCells(), r["n_cells"]
