@@ -1609,13 +1609,14 @@ void Amg::joinExchange() {
 }
 
 // ================================================================= coarse levels without launches
-// Below ~1 M rows a colour pass is latency-bound: the dependent loads of one row (slice offset ->
+// Below a few 100 K rows a colour pass is latency-bound: the dependent loads of one row (slice offset ->
 // column/value -> x -> divide) take longer than the pass has work for, and every launch boundary
 // adds its own gap. Two kernels run whole stretches of the V-cycle (restrict down, smooth, prolong
 // up) with a barrier where the launch boundaries would be -- the same operations in the same order
 // as the per-level launches, so the results are bit-identical to them:
 //   k_tail_vcycle   levels with <= kTailRows rows in ONE CTA, __syncthreads() barriers
-//   k_coop_vcycle   levels with <= coopRows rows in one COOPERATIVE grid (one CTA per SM),
+//   k_coop_vcycle   levels below a row limit that grows with their colour count (Amg::buildTail: 139 K rows for 2
+//                   classes, 331 K for 8) in one COOPERATIVE grid (one CTA per SM),
 //                   grid.sync() barriers; it hands its last levels to the same code path
 // ---- values a row carries: one double (CRMatrix<T,T,T>) or NC of them sharing one matrix (the momentum system
 // CRMatrix<DiagonalTensor<T,3>,T,Vector<T,3>> with equal diagonal components, F/FlowModel_impl.h:536: scalar
@@ -1949,14 +1950,20 @@ void Amg::buildTail() {
   if (const char* e = getenv("FVMGPU_NO_FUSED")) { if (atoi(e)) return; }
 #ifndef FVMGPU_HOSTSIM
   const int nl = (int)levels.size();
-  int coopRows = 1200000;
-  if (const char* e = getenv("FVMGPU_COOP_ROWS")) coopRows = atoi(e);
+  // Largest level the cooperative kernel takes. Its 512 threads per SM stream a large level at less than half the
+  // bandwidth of the per-level kernels, but a pass costs it one grid barrier (~3 us) instead of a launch gap (~4-5 us
+  // between tiny kernels): the more colour classes (= passes) a level has, the larger the level that still pays.
+  // Measured at 256^3 hexes (2 classes): limit 150 K rows 517 ms/step, 300 K 521, 1.2 M 540; on 96^3 x 6 tets (6-10
+  // classes): 75 K 1028, 150 K 996, 300 K 983, 600 K 991, 1.2 M 1014.   FVMGPU_COOP_ROWS fixes the limit.
+  int coopRowsFixed = -1;
+  if (const char* e = getenv("FVMGPU_COOP_ROWS")) coopRowsFixed = atoi(e);
+  auto coopLimit = [&](const Level& L) { return coopRowsFixed >= 0 ? coopRowsFixed : 75000 + 32000 * std::min(L.nColours, 8); };
   int start = nl;
   int tailRows = kTailRows;   // rows a level may have to be worked by ONE CTA (FVMGPU_TAIL_ROWS: measurement knob)
   if (const char* e = getenv("FVMGPU_TAIL_ROWS")) tailRows = atoi(e);
   while (start > 1 && levels[start - 1]->n <= tailRows) start--;
   int cstart = start;
-  while (cstart > 1 && levels[cstart - 1]->n <= coopRows) cstart--;
+  while (cstart > 1 && levels[cstart - 1]->n <= coopLimit(*levels[cstart - 1])) cstart--;
   tailIsCoop = cstart < start;   // some levels are too large for one CTA: use the cooperative grid for the stretch
   if (tailIsCoop) {
     static int coopOk = -1;

@@ -82,7 +82,7 @@ struct Amg {
   int tailStart = -1, tailCount = 0;
   int tailGridLevels = 0;    // leading levels of the stretch worked by the whole grid; the rest by CTA 0
   DBuf<unsigned> coopBarrier;
-  bool tailIsCoop = false;   // the stretch runs in the cooperative grid kernel (levels up to ~1.2 M rows)
+  bool tailIsCoop = false;   // the stretch runs in the cooperative grid kernel (levels up to 139 K - 331 K rows, see Amg::buildTail)
   DBuf<char> tailLevels;
   std::vector<DBuf<int>> tailColourStarts;
   // captured (cycle [+ residual norm]) graphs

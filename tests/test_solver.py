@@ -262,7 +262,7 @@ def test_hierarchy_is_rebuilt_when_the_matrix_changes(devlib):
 @pytest.mark.gpu
 @pytest.mark.parametrize("variant", ["coop", "tail_only"])
 def test_fused_vcycle_kernels_are_bit_identical_to_per_level_launches(gpu_lib, variant):
-    """k_coop_vcycle (cooperative grid, levels <= 1.2 M rows) and k_tail_vcycle (one CTA, levels <= 4096
+    """k_coop_vcycle (cooperative grid, levels up to 139 K - 331 K rows depending on their colour count) and k_tail_vcycle (one CTA, levels <= 4096
     rows) run the same operations in the same order as the per-level launches they replace."""
     import os
     from fvm_b200 import meshgen as G

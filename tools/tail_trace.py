@@ -29,7 +29,9 @@ def main():
     lib.profile_end(cap=8192)
     t, g = lib.tail_trace()
     sizes = st["levels"]["sizes"]
-    first = next(i for i, s in enumerate(sizes) if s <= int(os.environ.get("FVMGPU_COOP_ROWS", "1200000")) and i > 0)
+    cols = st["levels"]["colours"]
+    fixed = os.environ.get("FVMGPU_COOP_ROWS")
+    first = next(i for i, s in enumerate(sizes) if i > 0 and s <= (int(fixed) if fixed else 75000 + 32000 * min(cols[i], 8)))
     print("levels", sizes, "fused stretch starts at level", first, "stamps", len(t))
     if len(t) < 2:
         return
