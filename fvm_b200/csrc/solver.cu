@@ -224,22 +224,80 @@ struct SliceWidthKernel {
 struct SellFillKernel {
   int n; const int* invp; const int* perm; const int* row; const int* col; const double* val;
   const double* diagOld; int dropGhost; const int* sliceOff; int* scol; double* sval; double* diagNew;
+  int sortCols;   // entries of a row in ascending (level) column order: what the compressed columns want (SellCols).
+                  // Off in the reference-order verification mode, where a row accumulates in the reference's CSR order.
+  static constexpr int kSortCap = 16;   // rows up to this length are sorted in thread-local storage
   FVM_DEV void operator()(long long rr) const {
     const int r = (int)rr, old = invp[r];
     const int s = r >> 5, lane = r & 31;
-    int p = sliceOff[s] + lane;
+    const int p0 = sliceOff[s] + lane;
+    int p = p0;
     const int end = sliceOff[s + 1];
-    for (int k = row[old]; k < row[old + 1]; k++) {
-      const int c = col[k];
-      if (dropGhost && c >= n) continue;
-      scol[p] = c < n ? perm[c] : c;  // ghost columns keep their index (>= n)
-      sval[p] = val[k];
-      p += 32;
+    const int k0 = row[old], k1 = row[old + 1];
+    if (sortCols && k1 - k0 <= kSortCap) {
+      int cs[kSortCap];
+      double vs[kSortCap];
+      int m = 0;
+      for (int k = k0; k < k1; k++) {
+        const int c = col[k];
+        if (dropGhost && c >= n) continue;
+        const int cn = c < n ? perm[c] : c;  // ghost columns keep their index (>= n)
+        const double v = val[k];
+        int q = m;
+        while (q > 0 && cs[q - 1] > cn) { cs[q] = cs[q - 1]; vs[q] = vs[q - 1]; q--; }
+        cs[q] = cn; vs[q] = v;
+        m++;
+      }
+      for (int q = 0; q < m; q++, p += 32) { scol[p] = cs[q]; sval[p] = vs[q]; }
+    } else {
+      for (int k = k0; k < k1; k++) {
+        const int c = col[k];
+        if (dropGhost && c >= n) continue;
+        const int cn = c < n ? perm[c] : c;
+        const double v = val[k];
+        int q = p;
+        if (sortCols) {   // long row: insertion into the sorted prefix in place
+          while (q > p0 && scol[q - 32] > cn) { scol[q] = scol[q - 32]; sval[q] = sval[q - 32]; q -= 32; }
+        }
+        scol[q] = cn;
+        sval[q] = v;
+        p += 32;
+      }
     }
     for (; p < end; p += 32) { scol[p] = r; sval[p] = 0.0; }
     diagNew[r] = diagOld[old];
   }
 };
+// Compressed columns of one slice (SellCols): base = smallest REAL column among the 32 k-th entries. Padding entries
+// (value 0.0, column = own row in the plain array -- a real off-diagonal entry never names its own row, and the
+// aggregation kernels recognise padding by that) point at the base in the compressed copy: 0.0 * x[base] instead of
+// 0.0 * x[row], the same (signed) zero contribution for any finite x. kCompressLanes threads per slice take the entry
+// positions k = t, t + kCompressLanes, ...; `mode` starts at 1 and any position that does not fit clears it.
+constexpr int kCompressLanes = 8;
+struct CompressColsKernel {
+  int n; const int* sliceOff; const int* scol; unsigned short* c16; int* base; unsigned char* mode;
+  FVM_DEV void operator()(long long tt) const {
+    const int s = (int)(tt / kCompressLanes), off = sliceOff[s], w = (sliceOff[s + 1] - off) >> 5, r0 = s * 32;
+    const int lanes = n - r0 < 32 ? n - r0 : 32;
+    for (int k = (int)(tt % kCompressLanes); k < w; k += kCompressLanes) {
+      const int q = off + 32 * k;
+      int mn = 0x7fffffff, mx = -1;
+      for (int l = 0; l < lanes; l++) {
+        const int c = scol[q + l];
+        if (c != r0 + l) { mn = c < mn ? c : mn; mx = c > mx ? c : mx; }
+      }
+      if (mx < 0) { mn = r0; mx = r0; }          // nothing but padding at this position
+      base[q >> 5] = mn;
+      const bool fits = mx - mn <= 65535;
+      if (!fits) mode[s] = 0;
+      for (int l = 0; l < 32; l++) {
+        const int c = l < lanes ? scol[q + l] : r0 + l;
+        c16[q + l] = (fits && c != r0 + l) ? (unsigned short)(c - mn) : (unsigned short)0;
+      }
+    }
+  }
+};
+struct CountModeRows { const unsigned char* mode; FVM_DEV void operator()(long long i, double* o) const { o[0] = (double)mode[i]; } };
 struct PermGatherKernel {  // dst[perm[i]] = src[i]
   const int* perm; const double* src; double* dst;
   FVM_DEV void operator()(long long i) const { dst[perm[i]] = src[i]; }
@@ -256,14 +314,18 @@ struct PermIntKernel {  // excl[perm[i]] = src[i]
 
 // ---- smoothers / residual on SELL
 struct GsRows {  // one colour: rows [rowBegin, rowBegin+count)
-  int rowBegin; const int* sliceOff; const int* scol; const double* sval; const double* diag; const double* b;
+  int rowBegin; const int* sliceOff; SellCols cols; const double* sval; const double* diag; const double* b;
   double* x;
   FVM_DEV void operator()(long long t) const {
     const int r = rowBegin + (int)t;
     const int s = r >> 5;
     const int end = sliceOff[s + 1];
     double sum = b[r];
-    for (int p = sliceOff[s] + (r & 31); p < end; p += 32) sum += sval[p] * x[scol[p]];
+    if (cols.compressed(s)) {
+      for (int p = sliceOff[s] + (r & 31); p < end; p += 32) sum += sval[p] * x[cols.base[p >> 5] + (int)cols.c16[p]];
+    } else {
+      for (int p = sliceOff[s] + (r & 31); p < end; p += 32) sum += sval[p] * x[cols.scol[p]];
+    }
     x[r] = -sum / diag[r];
   }
 };
@@ -286,13 +348,17 @@ struct JacobiRows {
   }
 };
 struct ResidualRows {  // r = b + A x
-  const int* sliceOff; const int* scol; const double* sval; const double* diag; const double* b;
+  const int* sliceOff; SellCols cols; const double* sval; const double* diag; const double* b;
   const double* x; double* r;
   FVM_DEV double compute(int i) const {
     const int s = i >> 5;
     const int end = sliceOff[s + 1];
     double v = b[i] + diag[i] * x[i];
-    for (int p = sliceOff[s] + (i & 31); p < end; p += 32) v += sval[p] * x[scol[p]];
+    if (cols.compressed(s)) {
+      for (int p = sliceOff[s] + (i & 31); p < end; p += 32) v += sval[p] * x[cols.base[p >> 5] + (int)cols.c16[p]];
+    } else {
+      for (int p = sliceOff[s] + (i & 31); p < end; p += 32) v += sval[p] * x[cols.scol[p]];
+    }
     return v;
   }
   FVM_DEV void operator()(long long i) const { r[i] = compute((int)i); }
@@ -317,12 +383,16 @@ struct ResidualRowsFrom {  // logical row t -> t below skipFrom, t + (skipTo - s
   }
 };
 struct MultiplyRows {  // y = A x   (CRMatrix::multiply, F/CRMatrix.h:200-216)
-  const int* sliceOff; const int* scol; const double* sval; const double* diag; const double* x; double* y;
+  const int* sliceOff; SellCols cols; const double* sval; const double* diag; const double* x; double* y;
   FVM_DEV void operator()(long long ii) const {
     const int i = (int)ii, s = i >> 5;
     const int end = sliceOff[s + 1];
     double v = diag[i] * x[i];
-    for (int p = sliceOff[s] + (i & 31); p < end; p += 32) v += sval[p] * x[scol[p]];
+    if (cols.compressed(s)) {
+      for (int p = sliceOff[s] + (i & 31); p < end; p += 32) v += sval[p] * x[cols.base[p >> 5] + (int)cols.c16[p]];
+    } else {
+      for (int p = sliceOff[s] + (i & 31); p < end; p += 32) v += sval[p] * x[cols.scol[p]];
+    }
     y[i] = v;
   }
 };
@@ -439,7 +509,11 @@ struct MultiplyDotRows {  // y = A x fused with the dot products the recurrence 
     const int s = (int)i >> 5;
     const int end = M.sliceOff[s + 1];
     double v = M.diag[i] * M.x[i];
-    for (int p = M.sliceOff[s] + ((int)i & 31); p < end; p += 32) v += M.sval[p] * M.x[M.scol[p]];
+    if (M.cols.compressed(s)) {
+      for (int p = M.sliceOff[s] + ((int)i & 31); p < end; p += 32) v += M.sval[p] * M.x[M.cols.base[p >> 5] + (int)M.cols.c16[p]];
+    } else {
+      for (int p = M.sliceOff[s] + ((int)i & 31); p < end; p += 32) v += M.sval[p] * M.x[M.cols.scol[p]];
+    }
     M.y[i] = v;
     o[0] = v * w[i];
     o[1] = v * v;
@@ -874,6 +948,12 @@ static fvmgpu_aggregate_fn g_aggregator = nullptr;
 static void* g_aggregatorUser = nullptr;
 void setDebugAggregator(fvmgpu_aggregate_fn fn, void* user) { g_aggregator = fn; g_aggregatorUser = user; }
 static bool g_referenceOrder = false;
+// rows keep the entry order of the caller's CSR (no column sort, no compressed columns): the reference-order mode and
+// the single-level stationary solvers (JacobiSolver: iterates bit-compatible with the reference's, which sums a row in
+// CSR order)
+static bool g_keepEntryOrder = false;
+// the hierarchy being built is expected to run enough cycles for the 16-bit column copy to pay (Amg::setup)
+static bool g_compressWanted = false;
 
 static int wavefrontColouring(int n, const int* row, const int* col, DBuf<int>& colour, std::vector<int>& counts) {
   std::vector<int> hrow((size_t)n + 1), hcol, lvl((size_t)n, 0);
@@ -968,6 +1048,29 @@ static int colourCsr(int n, const int* row, const int* col, DBuf<int>& colour, s
   return nc;
 }
 
+// 16-bit column copy of a level (SellCols) for the row kernels of the large levels: built where a row pass is bound
+// by memory traffic (the fused coarse-level kernels read the plain columns). FVMGPU_COL16=0: measurement switch.
+constexpr int kCompressMinCycles = 64;
+constexpr int kCompressMinRows = 512;   // smaller levels live in the fused kernels (plain columns)
+static void compressColumns(Level& L) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("FVMGPU_COL16"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  L.scol16.release(); L.colBase.release(); L.sliceMode.release();
+  if (!on || !g_compressWanted || g_keepEntryOrder || L.n < kCompressMinRows || L.nnzStored <= 0) return;
+  L.scol16.alloc((size_t)L.nnzStored);
+  L.colBase.alloc((size_t)(L.nnzStored >> 5) + 1);
+  L.sliceMode.alloc((size_t)L.nSlices);
+  L.sliceMode.fillBytes(1);
+  parallelFor((long long)L.nSlices * kCompressLanes,
+              CompressColsKernel{L.n, L.sliceOff.p, L.scol.p, L.scol16.p, L.colBase.p, L.sliceMode.p});
+  static const bool report = getenv("FVMGPU_COL16_REPORT") && atoi(getenv("FVMGPU_COL16_REPORT")) != 0;
+  if (report) {   // how many slices of the level took the 16-bit form
+    DBuf<double> cnt(1);
+    reduceRows<1>(L.nSlices, CountModeRows{L.sliceMode.p}, cnt.p);
+    fprintf(stderr, "[fvmgpu] level of %d rows: %.0f of %d slices with 16-bit columns\n", L.n, cnt.hostAt(0), L.nSlices);
+  }
+}
+
 // Build level L from a CSR system in "natural" numbering; returns perm (natural -> level numbering).
 // `cache` (level 0 only): everything below that depends on the PATTERN alone -- colouring, row order, SELL slice
 // layout and column indices -- is kept with the solver and reused while the system's pattern stamp is the same: the
@@ -997,7 +1100,8 @@ static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, c
     L.diag.alloc(n); L.b.alloc(n); L.x.alloc((size_t)n + L.nGhost); L.r.alloc((size_t)n + L.nGhost);
     L.b.zero(); L.x.zero(); L.r.zero();
     parallelFor(n, SellFillKernel{n, L.nat.p, perm.p, row, col, val, diag, dropGhost ? 1 : 0, L.sliceOff.p, L.scol.p,
-                                  L.sval.p, L.diag.p});
+                                  L.sval.p, L.diag.p, g_keepEntryOrder ? 0 : 1});
+    compressColumns(L);
     streamSync();
     return;
   }
@@ -1041,7 +1145,8 @@ static void buildLevelFromCsr(Level& L, int n, const int* row, const int* col, c
   L.diag.alloc(n); L.b.alloc(n); L.x.alloc((size_t)n + L.nGhost); L.r.alloc((size_t)n + L.nGhost);
   L.b.zero(); L.x.zero(); L.r.zero();
   parallelFor(n, SellFillKernel{n, invp.p, perm.p, row, col, val, diag, dropGhost ? 1 : 0, L.sliceOff.p, L.scol.p,
-                                L.sval.p, L.diag.p});
+                                L.sval.p, L.diag.p, g_keepEntryOrder ? 0 : 1});
+  compressColumns(L);
   // true nnz (for the report): summed on the device, fetched only when somebody asks (fvmgpu_amg_levels)
   L.nnzDev.alloc(1);
   reduceRows<1>(n, IntAsDoubleRows{len.p}, L.nnzDev.p);
@@ -1353,6 +1458,12 @@ void Amg::setup(System* sys) {
   // columns stay and their x slots are filled by the halo exchange.
   multi = commActive() && sys->mesh && !sys->noHalo;
   g_referenceOrder = !multi && g_aggregator != nullptr;
+  g_keepEntryOrder = g_referenceOrder || opts.maxCoarseLevels == 0;
+  // Building the compressed columns costs about as much as three cycles save: worth it for a solve of many cycles
+  // (the thermal workload: ~290), not for the 2 - 20 cycles of a SIMPLE inner solve. Guide: the cycles the previous
+  // solve on this solver took (the models solve a similar system every outer iteration); before the first one, the
+  // caller's iteration limit.
+  g_compressWanted = (lastSolveCycles >= 0 ? lastSolveCycles : cycleBudget) >= kCompressMinCycles;
   levels.emplace_back(new Level);
   Level& L0 = *levels[0];
   DBuf<int> ghostIsHalo;
@@ -1549,6 +1660,8 @@ void Amg::buildMerged() {
   rowsDev.upload(rowsOfRank.data(), rowsOfRank.size());
   nested.reset(new Amg);
   nested->opts = opts;
+  nested->cycleBudget = cycleBudget;
+  nested->lastSolveCycles = lastSolveCycles;
   nested->tagBase = tagBase + mergedLevel;
   // the merged rows are the ranks' level rows in THEIR (colour-sorted) order; the pairing preference of the nested
   // hierarchy needs the rank-major NATURAL order, in which index distance means something (natHint)
@@ -2087,7 +2200,7 @@ void Amg::sweeps(int nSweeps, int lvl, bool ghostsReadAfter) {
         auto rowsOf = [&](int begin, int count) {
           if (count <= 0) return;
           if (L.xZero) parallelFor(count, GsFirstColourZeroRows{begin, L.diag.p, L.b.p, L.x.p});
-          else parallelFor(count, GsRows{begin, L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p});
+          else parallelFor(count, GsRows{begin, L.sliceOff.p, L.cols(), L.sval.p, L.diag.p, L.b.p, L.x.p});
         };
         // Ghost values: refreshed after each half-sweep (forward / reverse), i.e. neighbours' rows
         // are lagged by at most one half-sweep -- the reference lags them by a whole sweep
@@ -2130,7 +2243,7 @@ void Amg::sweeps(int nSweeps, int lvl, bool ghostsReadAfter) {
 void Amg::residual(int lvl) {
   Level& L = *levels[lvl];
   LevelTag tag(tagBase + lvl);
-  parallelFor(L.n, ResidualRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p});
+  parallelFor(L.n, ResidualRows{L.sliceOff.p, L.cols(), L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p});
   L.rValid = true;
   L.rZeroFrom = L.rZeroTo = 0;
 }
@@ -2138,7 +2251,7 @@ void Amg::residual(int lvl) {
 double Amg::residualNorm(int lvl) {
   Level& L = *levels[lvl];
   LevelTag tag(tagBase + lvl);
-  reduceRows<1>(L.n, ResidualRows{L.sliceOff.p, L.scol.p, L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p}, scalars.p);
+  reduceRows<1>(L.n, ResidualRows{L.sliceOff.p, L.cols(), L.sval.p, L.diag.p, L.b.p, L.x.p, L.r.p}, scalars.p);
   if (multi) commAllreduceSum(scalars.p, 1);  // MultiFieldReduction::reduceSum
   L.rValid = true;
   L.rZeroFrom = L.rZeroTo = 0;
@@ -2303,7 +2416,7 @@ void Amg::cycleGraphed(int kind) {
     cycle(opts.cycleType, 0);
     if (kind == 0) {
       LevelTag tag(tagBase);
-      const ResidualRows R{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, L0.b.p, L0.x.p, L0.r.p};
+      const ResidualRows R{L0.sliceOff.p, L0.cols(), L0.sval.p, L0.diag.p, L0.b.p, L0.x.p, L0.r.p};
       // the cycle ends with a post-sweep on level 0 whose last pass relaxes colour 0 = rows [0, colourStart[1])
       const bool lastColourExact = lastColourExactNow;
       if (lastColourExact) {
@@ -2358,6 +2471,7 @@ void Amg::cycleGraphed(int kind) {
 void Amg::solve(System* sys, double* rnorm0Out, double* rnormOut, int* itersOut) {
   requireReady();
   const auto t0 = std::chrono::steady_clock::now();
+  cycleBudget = opts.nMaxIterations;
   ensureSetup(sys);
   streamSync();
   const auto t1 = std::chrono::steady_clock::now();
@@ -2378,6 +2492,7 @@ void Amg::solve(System* sys, double* rnorm0Out, double* rnormOut, int* itersOut)
     }
   }
   totalIterations += iters;
+  lastSolveCycles = iters;
   storeDelta(sys->delta.p);
   streamSync();
   if (multi) peerCheck();
@@ -2392,6 +2507,7 @@ void Amg::solve(System* sys, double* rnorm0Out, double* rnormOut, int* itersOut)
 // AMG::smooth, F/AMG.cpp:285-298: one cycle on (b, delta) of the system
 void Amg::smooth(System* sys) {
   requireReady();
+  cycleBudget = 1;
   ensureSetup(sys);
   loadSystem(sys, sys->b.p, sys->delta.p);
   levels[0]->xZero = false;
@@ -2445,6 +2561,7 @@ void Amg::cycleOn(double* rhs) {
 void Amg::bcgstab(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0Out,
                   double* rnormOut, int* itersOut) {
   requireReady();
+  cycleBudget = 2 * nMaxIterations;   // two preconditioner cycles and two products with the matrix per iteration
   ensureSetup(sys);
   history.clear();
   Level& L0 = *levels[0];
@@ -2466,7 +2583,7 @@ void Amg::bcgstab(System* sys, int nMaxIterations, double relTol, double absTol,
   auto allreduce = [&](double* ptr, int cnt) { if (multi) commAllreduceSum(ptr, cnt); };
   double* S = scalars.p;
   // r = b + A x ; rNorm0 ; rTilda = r ; rho = r . rTilda
-  reduceRows<1>(n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, K.bOrig.p, K.x.p, K.r.p}, S + 12);
+  reduceRows<1>(n, ResidualRows{L0.sliceOff.p, L0.cols(), L0.sval.p, L0.diag.p, K.bOrig.p, K.x.p, K.r.p}, S + 12);
   allreduce(S + 12, 1);
   copyD2D(K.rTilda.p, K.r.p, (size_t)n * sizeof(double));
   reduceRows<1>(n, Dot1Rows{K.r.p, K.rTilda.p}, S + 8);
@@ -2487,13 +2604,13 @@ void Amg::bcgstab(System* sys, int nMaxIterations, double relTol, double absTol,
     parallelFor(n, BcgDirection{S, K.v.p, K.r.p, K.p.p});
     const double* hat;                                                 // pHat = M(p), ghost slots in step
     if (ilu) { precondition(K.p.p, K.hat.p); hat = K.hat.p; } else { cycleOn(K.p.p); hat = L0.x.p; }
-    reduceRows<2>(n, MultiplyDotRows{MultiplyRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, hat, K.v.p}, K.rTilda.p}, S + 3);
+    reduceRows<2>(n, MultiplyDotRows{MultiplyRows{L0.sliceOff.p, L0.cols(), L0.sval.p, L0.diag.p, hat, K.v.p}, K.rTilda.p}, S + 3);
     // (slot 3 = rTilda . v, slot 4 is overwritten below)
     allreduce(S + 3, 1);
     reduceRows<1>(n, BcgAlphaStep{S, hat, K.v.p, K.x.p, K.r.p}, S + 6);
     allreduce(S + 6, 1);
     if (ilu) { precondition(K.r.p, K.hat.p); hat = K.hat.p; } else { cycleOn(K.r.p); hat = L0.x.p; }   // sHat = M(r)
-    reduceRows<2>(n, MultiplyDotRows{MultiplyRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, hat, K.t.p}, K.r.p}, S + 4);
+    reduceRows<2>(n, MultiplyDotRows{MultiplyRows{L0.sliceOff.p, L0.cols(), L0.sval.p, L0.diag.p, hat, K.t.p}, K.r.p}, S + 4);
     allreduce(S + 4, 2);                                               // (t . r, t . t)
     reduceRows<2>(n, BcgOmegaStep{S, absTol, hat, K.t.p, K.rTilda.p, K.x.p, K.r.p}, S + 9);
     allreduce(S + 9, 2);                                               // (|r|_1, r . rTilda)
@@ -2512,6 +2629,7 @@ void Amg::bcgstab(System* sys, int nMaxIterations, double relTol, double absTol,
     if (rNorm < absTol || rNorm / rNorm0 < relTol) break;
   }
   totalIterations += iters;
+  lastSolveCycles = 2 * iters;
   parallelFor(n, PermScatterKernel{perm0.p, K.x.p, sys->delta.p});
   if (ng) {  // leave the ghosts of delta synced
     copyD2D(L0.x.p, K.x.p, (size_t)n * sizeof(double));
@@ -2555,6 +2673,7 @@ void Amg::bcgstabMulti(System* sys, int nc, const double* b3, double* delta3, in
                        double absTol, double* rnorm0Out, double* rnormOut, int* itersOut) {
   requireReady();
   if (nc < 1 || nc > 3) fail("bcgstabMulti: 1 to 3 components");
+  cycleBudget = 2 * nMaxIterations;
   ensureSetup(sys);
   history.clear();
   Level& L0 = *levels[0];
@@ -2574,7 +2693,7 @@ void Amg::bcgstabMulti(System* sys, int nc, const double* b3, double* delta3, in
     copyD2H(out3, scalars.p + 8, 3 * sizeof(double));
   };
   for (int k = 0; k < nc; k++)   // r = b + A x
-    parallelFor(n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, bOrig.p + (size_t)k * n, x.p + k * ns,
+    parallelFor(n, ResidualRows{L0.sliceOff.p, L0.cols(), L0.sval.p, L0.diag.p, bOrig.p + (size_t)k * n, x.p + k * ns,
                                 r.p + (size_t)k * n});
   double r0[3], rn[3];
   norms(r0);
@@ -2596,7 +2715,7 @@ void Amg::bcgstabMulti(System* sys, int nc, const double* b3, double* delta3, in
     else parallelFor((long long)N, BcgUpdateP{S, v.p, r.p, p.p});
     for (int k = 0; k < nc; k++) {
       precondition(p.p + (size_t)k * n, pHat.p + k * ns);
-      MultiplyRows m{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, pHat.p + k * ns, v.p + (size_t)k * n};
+      MultiplyRows m{L0.sliceOff.p, L0.cols(), L0.sval.p, L0.diag.p, pHat.p + k * ns, v.p + (size_t)k * n};
       parallelFor(n, m);
     }
     copyD2D(S + 2, S + 0, sizeof(double));
@@ -2608,7 +2727,7 @@ void Amg::bcgstabMulti(System* sys, int nc, const double* b3, double* delta3, in
     if (mag2(rn) < absTol * absTol) break;
     for (int k = 0; k < nc; k++) {
       precondition(r.p + (size_t)k * n, pHat.p + k * ns);
-      MultiplyRows m{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, pHat.p + k * ns, t.p + (size_t)k * n};
+      MultiplyRows m{L0.sliceOff.p, L0.cols(), L0.sval.p, L0.diag.p, pHat.p + k * ns, t.p + (size_t)k * n};
       parallelFor(n, m);
     }
     reduceRows<2>((long long)N, Dot2Rows{t.p, r.p}, S + 4);
@@ -2621,6 +2740,7 @@ void Amg::bcgstabMulti(System* sys, int nc, const double* b3, double* delta3, in
     if (num < absTol * absTol || (den > 0 ? num / den : num) < relTol * relTol) break;
   }
   totalIterations += iters;
+  lastSolveCycles = 2 * iters;
   for (int k = 0; k < nc; k++) {
     parallelFor(n, PermScatterAoS{perm0.p, x.p + k * ns, nc, k, delta3});
     if (ng) {  // ghosts of delta synced, as the reference leaves them (x->sync())
@@ -2645,6 +2765,7 @@ struct ScaleAddRows {  // p = p * (num/den) + z
 void Amg::cg(System* sys, int nMaxIterations, double relTol, double absTol, double* rnorm0Out, double* rnormOut,
              int* itersOut) {
   requireReady();
+  cycleBudget = nMaxIterations;
   ensureSetup(sys);
   history.clear();
   Level& L0 = *levels[0];
@@ -2656,7 +2777,7 @@ void Amg::cg(System* sys, int nMaxIterations, double relTol, double absTol, doub
   if (ng) { copyD2D(x.p + n, sys->delta.p + n, ng * sizeof(double)); exchange(L0, x.p); }
   auto allreduce = [&](double* ptr, int cnt) { if (multi) commAllreduceSum(ptr, cnt); };
   double* S = scalars.p;  // S[0]=rho S[1]=rhoPrev S[2]=p.q S[6]=|r|_1
-  reduceRows<1>(n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, bOrig.p, x.p, r.p}, S + 6);
+  reduceRows<1>(n, ResidualRows{L0.sliceOff.p, L0.cols(), L0.sval.p, L0.diag.p, bOrig.p, x.p, r.p}, S + 6);
   allreduce(S + 6, 1);
   double rNorm0;
   copyD2H(&rNorm0, S + 6, sizeof(double));
@@ -2673,7 +2794,7 @@ void Amg::cg(System* sys, int nMaxIterations, double relTol, double absTol, doub
     if (!haveP) { copyD2D(p.p, z.p, (size_t)n * sizeof(double)); haveP = true; }
     else parallelFor(n, ScaleAddRows{S + 0, S + 1, z.p, p.p});  // p = p * (rho/rhoPrev) + z
     if (ng) exchange(L0, p.p);
-    { MultiplyRows m{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, p.p, q.p}; parallelFor(n, m); }  // q = A p
+    { MultiplyRows m{L0.sliceOff.p, L0.cols(), L0.sval.p, L0.diag.p, p.p, q.p}; parallelFor(n, m); }  // q = A p
     reduceRows<1>(n, Dot1Rows{p.p, q.p}, S + 2);
     allreduce(S + 2, 1);
     parallelFor(n, MsaxpyScalarPtr{S + 0, S + 2, p.p, x.p});    // x -= alpha p, alpha = rho / p.q
@@ -2684,6 +2805,7 @@ void Amg::cg(System* sys, int nMaxIterations, double relTol, double absTol, doub
     if (rNorm < absTol || rNorm / rNorm0 < relTol) break;
   }
   totalIterations += iters;
+  lastSolveCycles = iters;
   parallelFor(n, PermScatterKernel{perm0.p, x.p, sys->delta.p});
   if (ng) {
     copyD2D(L0.x.p, x.p, (size_t)n * sizeof(double));
@@ -2701,6 +2823,7 @@ void Amg::cgMulti(System* sys, int nc, const double* b3, double* delta3, int nMa
                   double absTol, double* rnorm0Out, double* rnormOut, int* itersOut) {
   requireReady();
   if (nc < 1 || nc > 3) fail("cgMulti: 1 to 3 components");
+  cycleBudget = nMaxIterations;
   ensureSetup(sys);
   history.clear();
   Level& L0 = *levels[0];
@@ -2726,7 +2849,7 @@ void Amg::cgMulti(System* sys, int nc, const double* b3, double* delta3, int nMa
     allreduce(out, 1);
   };
   for (int k = 0; k < nc; k++)
-    parallelFor(n, ResidualRows{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, bOrig.p + (size_t)k * n, x.p + k * ns,
+    parallelFor(n, ResidualRows{L0.sliceOff.p, L0.cols(), L0.sval.p, L0.diag.p, bOrig.p + (size_t)k * n, x.p + k * ns,
                                 r.p + (size_t)k * n});
   double r0[3], rn[3];
   norms(r0);
@@ -2746,7 +2869,7 @@ void Amg::cgMulti(System* sys, int nc, const double* b3, double* delta3, int nMa
       if (!haveP) copyD2D(p.p + k * ns, z.p + k * ns, (size_t)n * sizeof(double));
       else parallelFor(n, ScaleAddRows{S + 0, S + 1, z.p + k * ns, p.p + k * ns});
       if (ng) exchange(L0, p.p + k * ns);
-      MultiplyRows m{L0.sliceOff.p, L0.scol.p, L0.sval.p, L0.diag.p, p.p + k * ns, q.p + (size_t)k * n};
+      MultiplyRows m{L0.sliceOff.p, L0.cols(), L0.sval.p, L0.diag.p, p.p + k * ns, q.p + (size_t)k * n};
       parallelFor(n, m);
     }
     haveP = true;
@@ -2759,6 +2882,7 @@ void Amg::cgMulti(System* sys, int nc, const double* b3, double* delta3, int nMa
     if (num < absTol * absTol || (den > 0 ? num / den : num) < relTol * relTol) break;
   }
   totalIterations += iters;
+  lastSolveCycles = iters;
   for (int k = 0; k < nc; k++) {
     parallelFor(n, PermScatterAoS{perm0.p, x.p + k * ns, nc, k, delta3});
     if (ng) {
@@ -2991,6 +3115,7 @@ template <int NC>
 void solveN(Amg& A, System* sys, const double* b3, double* delta3, int stride, int maxCycles, double relTol, double absTol,
             double* rnorm0Out, double* rnormOut, int* itersOut) {
   typedef VecN<NC> V;
+  A.cycleBudget = maxCycles;
   A.ensureSetup(sys);
   // NC-wide vectors of every level (+ the level table of the fused kernels), kept with the hierarchy
   if (A.multiNc != NC) {
@@ -3057,6 +3182,7 @@ void solveN(Amg& A, System* sys, const double* b3, double* delta3, int stride, i
     }
   }
   A.totalIterations += iters;
+  A.lastSolveCycles = iters;
   parallelFor(L0.n, StoreAoSN<NC>{A.perm0.p, vx<NC>(L0), stride, delta3});
   for (int k = 0; k < NC; k++) {
     if (rnorm0Out) rnorm0Out[k] = n0[k];

@@ -6,6 +6,19 @@
 
 namespace fvmgpu {
 
+// Column indices of a SELL-32 level as the hot row kernels read them. On top of the plain 32-bit array the level
+// keeps a COMPRESSED copy: one base per (slice, entry position) and a 16-bit offset per element -- in a slice of 32
+// neighbouring rows the k-th columns lie close together (rows store their entries in ascending column order; the
+// colour ordering keeps mesh neighbours of neighbouring rows next to each other), so 2 bytes instead of 4 per stored
+// entry cross the memory bus (12 -> 10 B per entry, ~11 % of a row pass on hexes). A slice whose k-th columns
+// spread over more than 65535 rows (unstructured numbering, interface rows with halo columns) is marked in `mode`
+// and read from the plain array.
+struct SellCols {
+  const int* scol; const unsigned short* c16; const int* base; const unsigned char* mode;   // mode == nullptr: plain only
+  FVM_DEV bool compressed(int slice) const { return mode != nullptr && mode[slice] != 0; }
+  FVM_DEV int at(int p, bool cmp) const { return cmp ? base[p >> 5] + (int)c16[p] : scol[p]; }
+};
+
 struct Level {
   int n = 0;                 // solved rows of this level
   long long nnzStored = 0;   // SELL elements incl. padding
@@ -14,6 +27,10 @@ struct Level {
   int nSlices = 0;
   DBuf<int> sliceOff;        // nSlices+1 element offsets into scol/sval (multiples of 32)
   DBuf<int> scol;
+  DBuf<unsigned short> scol16;   // compressed copy of scol (see SellCols); empty when not built
+  DBuf<int> colBase;             // nnzStored / 32 bases
+  DBuf<unsigned char> sliceMode; // per slice: 1 = read the compressed copy
+  SellCols cols() const { return SellCols{scol.p, scol16.p, colBase.p, scol16.p ? sliceMode.p : nullptr}; }
   DBuf<double> sval;
   DBuf<double> diag, b, x, r;
   DBuf<double> mb, mx, mr;   // the same three vectors with NC values per row (Amg::solveMulti)
@@ -65,6 +82,8 @@ struct Amg {
   DBuf<double> natIn, natOut;
   std::vector<std::unique_ptr<Level>> levels;
   DBuf<int> perm0;           // system (natural) row -> level-0 row
+  int cycleBudget = 1 << 30;   // upper bound of the cycles the coming solve may run (set by the solve entry points)
+  int lastSolveCycles = -1;    // cycles the previous solve took; survives cleanup() like cache0
   PatternCache cache0;       // survives cleanup(): the next outer iteration assembles on the same pattern
   DBuf<double> scalars;      // device scalars for dots / norms
   System* builtFor = nullptr;          // the system of the last setup (used by the ILU preconditioner path)

@@ -154,8 +154,15 @@ static RefSolver make_solver(const SolverCfg& c) {
 struct CoutCapture {
   std::ostringstream os;
   std::streambuf* old;
-  CoutCapture() : old(std::cout.rdbuf(os.rdbuf())) {}
-  ~CoutCapture() { std::cout.rdbuf(old); }
+  // the reference's Vector<T,N> printer leaves std::cout in scientific notation for the rest of the process
+  // (F/Vector.h:66): every capture starts from the default formatting, as a fresh reference process would
+  std::ios_base::fmtflags flags;
+  std::streamsize prec;
+  CoutCapture() : old(std::cout.rdbuf(os.rdbuf())), flags(std::cout.flags()), prec(std::cout.precision()) {
+    std::cout.unsetf(std::ios_base::floatfield);
+    std::cout.precision(6);
+  }
+  ~CoutCapture() { std::cout.rdbuf(old); std::cout.flags(flags); std::cout.precision(prec); }
 };
 
 static void copy_text(const std::string& s, char* out, int cap) {
