@@ -512,15 +512,17 @@ def hbm_peak():
 def cycle_hbm(step, cycles_ms):
     """Whole-solve HBM fraction of ONE GPU: algorithmic bytes of a V(0,1) cycle with
     multicolour Gauss-Seidel summed over this rank's levels, times the cycles, over the wall time of the
-    cycle loop. Row pass = 36 B per row + 12 B per stored off-diagonal entry; a sweep with k
+    cycle loop. Row pass = 36 B per row + 12 B per stored off-diagonal entry (10.125 B where the level
+    stores 16-bit column offsets: the bytes of the format actually read, so that the fraction stays a utilisation); a sweep with k
     colour classes visits (2k-1)/k of the rows (forward + reverse, repeated class skipped); the level-0
     residual skips the class relaxed last; restriction and prolongation move 32 B and 28 B per fine row."""
     lv = step["levels"]
     sizes, nnzs, cols = lv["sizes"], lv["nnz"], lv["colours"]
+    cbytes = lv.get("col_bytes") or [4.0] * len(sizes)     # column-index bytes per entry as stored (4, or 2.125 compressed)
     total = 0.0
     for l, (n, nnz, k) in enumerate(zip(sizes, nnzs, cols)):
         k = max(int(k), 1)
-        row_pass = 36.0 * n + 12.0 * nnz
+        row_pass = 36.0 * n + (8.0 + cbytes[l]) * nnz
         total += row_pass * (2 * k - 1) / k                    # post-sweep
         if l == 0:
             total += row_pass * (k - 1) / k + 8.0 * n          # residual + 1-norm (last class skipped), r written
@@ -556,13 +558,14 @@ def roofline(recs, step):
     ms = sum(r["ms"] for r in picked)
     if not launches:
         return None, table
-    per_row = 36.0 + 12.0 * nnz0 / n0
+    col_bytes0 = (step["levels"].get("col_bytes") or [4.0])[0]
+    per_row = 36.0 + (8.0 + col_bytes0) * nnz0 / n0
     total_bytes = sum(r["launches"] * r["rows"] * per_row for r in picked)
     achieved = total_bytes / (ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None, "kernel": "k_rows<GsRows> at AMG level 0 (one colour of the multicolour Gauss-Seidel sweep)",
             "peak_source": src, "bytes_per_launch": total_bytes / launches,
-            "bytes_per_row": per_row, "rows_per_launch": sum(r["launches"] * r["rows"] for r in picked) / launches,
+            "bytes_per_row": per_row, "column_index_bytes_per_entry": col_bytes0, "rows_per_launch": sum(r["launches"] * r["rows"] for r in picked) / launches,
             "mean_launch_ms": ms / launches, "launches": launches,
             "share_of_step": ms / step["total_ms"]}
     # DRAM traffic of that kernel from the committed `ncu --set full` capture (per launch), when the

@@ -108,6 +108,7 @@ SIGNATURES = {
     "fvmgpu_debug_set_aggregator": (C.c_int, [_vp, _vp]),
     "fvmgpu_debug_tail_trace": (C.c_int, [C.c_int, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS"),
                                           _ip, C.POINTER(C.c_int)]),
+    "fvmgpu_amg_level_col_bytes": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     "fvmgpu_amg_last_timing": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "fvmgpu_solver_history": (C.c_int, [_vp, C.c_int, _dp, C.POINTER(C.c_int)]),
     "fvmgpu_bcgstab_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
@@ -644,7 +645,9 @@ class DeviceAMG:
         cols = np.zeros(64, np.int32)
         self.lib.call("fvmgpu_amg_levels", self.h, 64, C.byref(n), sizes, nnzs, cols)
         k = n.value
-        return dict(sizes=sizes[:k].tolist(), nnz=nnzs[:k].tolist(), colours=cols[:k].tolist())
+        cb = np.zeros(64)
+        self.lib.call("fvmgpu_amg_level_col_bytes", self.h, 64, cb.ctypes.data_as(C.POINTER(C.c_double)))
+        return dict(sizes=sizes[:k].tolist(), nnz=nnzs[:k].tolist(), colours=cols[:k].tolist(), col_bytes=cb[:k].tolist())
 
     def level_order(self, level=0):
         """(nat, colourStart): nat[r] = source row of level-row r; colour class c = level-rows

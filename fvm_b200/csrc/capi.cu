@@ -396,6 +396,23 @@ int fvmgpu_amg_levels(fvmgpu_solver_t s, int cap, int* nLevels, long long* sizes
   }
   API_END
 }
+int fvmgpu_amg_level_col_bytes(fvmgpu_solver_t s, int cap, double* colBytes) {
+  API_BEGIN
+  Amg* a = A(s);
+  std::vector<Level*> all;
+  for (auto& l : a->levels) all.push_back(l.get());
+  if (a->nested) for (auto& l : a->nested->levels) all.push_back(l.get());
+  for (int l = 0; l < (int)all.size() && l < cap; l++) {
+    Level& L = *all[l];
+    double frac = 0.0;
+    if (L.scol16.p && L.nSlices > 0) {
+      if (L.compressedSlices < 0 && L.modeCount.p) L.compressedSlices = (long long)L.modeCount.hostAt(0);
+      frac = (double)L.compressedSlices / (double)L.nSlices;
+    }
+    colBytes[l] = 4.0 - frac * (4.0 - 2.125);
+  }
+  API_END
+}
 int fvmgpu_amg_level_order(fvmgpu_solver_t s, int level, long long cap, int* nat, int* nColours,
                            long long* colourStart) {
   API_BEGIN

@@ -1055,7 +1055,8 @@ constexpr int kCompressMinRows = 512;   // smaller levels live in the fused kern
 static void compressColumns(Level& L) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("FVMGPU_COL16"); on = (e && atoi(e) == 0) ? 0 : 1; }
-  L.scol16.release(); L.colBase.release(); L.sliceMode.release();
+  L.scol16.release(); L.colBase.release(); L.sliceMode.release(); L.modeCount.release();
+  L.compressedSlices = -1;
   if (!on || !g_compressWanted || g_keepEntryOrder || L.n < kCompressMinRows || L.nnzStored <= 0) return;
   L.scol16.alloc((size_t)L.nnzStored);
   L.colBase.alloc((size_t)(L.nnzStored >> 5) + 1);
@@ -1063,12 +1064,9 @@ static void compressColumns(Level& L) {
   L.sliceMode.fillBytes(1);
   parallelFor((long long)L.nSlices * kCompressLanes,
               CompressColsKernel{L.n, L.sliceOff.p, L.scol.p, L.scol16.p, L.colBase.p, L.sliceMode.p});
-  static const bool report = getenv("FVMGPU_COL16_REPORT") && atoi(getenv("FVMGPU_COL16_REPORT")) != 0;
-  if (report) {   // how many slices of the level took the 16-bit form
-    DBuf<double> cnt(1);
-    reduceRows<1>(L.nSlices, CountModeRows{L.sliceMode.p}, cnt.p);
-    fprintf(stderr, "[fvmgpu] level of %d rows: %.0f of %d slices with 16-bit columns\n", L.n, cnt.hostAt(0), L.nSlices);
-  }
+  L.modeCount.alloc(1);
+  L.compressedSlices = -1;
+  reduceRows<1>(L.nSlices, CountModeRows{L.sliceMode.p}, L.modeCount.p);
 }
 
 // Build level L from a CSR system in "natural" numbering; returns perm (natural -> level numbering).

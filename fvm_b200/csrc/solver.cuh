@@ -30,6 +30,8 @@ struct Level {
   DBuf<unsigned short> scol16;   // compressed copy of scol (see SellCols); empty when not built
   DBuf<int> colBase;             // nnzStored / 32 bases
   DBuf<unsigned char> sliceMode; // per slice: 1 = read the compressed copy
+  DBuf<double> modeCount;        // number of such slices (device; fetched when somebody asks)
+  long long compressedSlices = -1;
   SellCols cols() const { return SellCols{scol.p, scol16.p, colBase.p, scol16.p ? sliceMode.p : nullptr}; }
   DBuf<double> sval;
   DBuf<double> diag, b, x, r;

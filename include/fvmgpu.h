@@ -214,6 +214,10 @@ int fvmgpu_amg_destroy(fvmgpu_solver_t s);
 /* hierarchy report: sizes[l] rows and nnzs[l] off-diagonal entries per level (level 0 = finest) */
 int fvmgpu_amg_levels(fvmgpu_solver_t s, int cap, int* nLevels, long long* sizes, long long* nnzs,
                       int* colours);
+/* storage report: colBytes[l] = bytes of column index the level's row kernels read per stored entry -- 4 for plain
+ * int32 columns, 2.125 where the 16-bit offsets (one int32 base per 32 entries) are in use, in between when only
+ * some 32-row slices of the level qualify. bench.py's byte model of a row pass uses it. */
+int fvmgpu_amg_level_col_bytes(fvmgpu_solver_t s, int cap, double* colBytes);
 /* smoother ordering of one level (inspection / tests): nat[r] = row of level-row r in the numbering the
  * level was built from (level 0: the system's rows), colourStart[0..nColours] = first level-row of each
  * colour class. Rows of one class are relaxed concurrently, so no stored a_ij may join two of them. */
