@@ -37,10 +37,13 @@ def main():
     o = lib.default_amg_opts()
     # optional second argument: number of coarse levels to keep (1: the level-0 restriction / prolongation kernels
     # InjectRows / CorrectRows appear as well)
-    o.maxCoarseLevels, o.nMaxIterations, o.relativeTolerance = (int(sys.argv[2]) if len(sys.argv) > 2 else 0), 6, 1e-30
+    # (with coarse levels the iteration limit is >= 64, so that the 16-bit column copy is built as in a long solve)
+    coarse = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    o.maxCoarseLevels, o.nMaxIterations, o.relativeTolerance = coarse, (70 if coarse else 6), 1e-30
     amg = X.DeviceAMG(lib, o)
     r0, r, it = amg.solve(ds)
-    print("level-0 only: %d sweeps, residual %g -> %g, colours %s" % (it, r0, r, amg.levels()["colours"]))
+    lv = amg.levels()
+    print("%d cycles, residual %g -> %g, colours %s, column bytes per entry %s" % (it, r0, r, lv["colours"], lv["col_bytes"]))
 
 
 if __name__ == "__main__":
