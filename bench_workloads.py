@@ -280,7 +280,9 @@ def _electric_setup(em, M, tol, iters):
         setattr(o, nm, s)
 
 
-def _electric_model(lib, raw, tol=1e-8, iters=100):
+def _electric_model(lib, raw, tol=1e-8, iters=100, uniform_field=False):
+    """uniform_field: no space charge and the potential initialised with its exact (linear) solution, so that the
+    electron velocity is the same in every cell (see the parity note in run_electric)."""
     from fvm_b200 import models as M
     mesh = M.Mesh(raw)
     geom = M.GeomFields("geom")
@@ -290,6 +292,9 @@ def _electric_model(lib, raw, tol=1e-8, iters=100):
     _electric_setup(em, M, tol, iters)
     em.init()
     cells = mesh.getCells()
+    if uniform_field:
+        ef.total_charge[cells][:] = 0.0
+        ef.potential[cells][:] = 100.0 * np.asarray(geom.coordinate[cells])[:, 2] / E_BOX
     gids = raw.cell_global if "cell_global" in raw else np.arange(raw.n_total)
     own = np.arange(raw.n_total) < raw.n_cells
     ef.charge[cells][:, 2] = np.where(own, 1e15 * (1 + np.maximum(gids, 0) % 7), 0.0)
@@ -297,7 +302,7 @@ def _electric_model(lib, raw, tol=1e-8, iters=100):
     return mesh, ef, em
 
 
-def _electric_reference(raw, steps, tol, iters=2000, kind=1):
+def _electric_reference(raw, steps, tol, iters=2000, kind=1, uniform_field=False):
     """oracle/_ref: the reference's ElectricModel<double> on the same (single-partition) mesh."""
     from oracle import refapi as R
     rm = R.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes, raw.face_node_count,
@@ -317,6 +322,10 @@ def _electric_reference(raw, steps, tol, iters=2000, kind=1):
     e.set_solver(0, R.solver_cfg(**cfg))
     e.set_solver(1, R.solver_cfg(**cfg))
     e.init()
+    if uniform_field:
+        from fvm_b200 import meshgen as G
+        e.field("total_charge")[:] = 0.0
+        e.field("potential")[:] = 100.0 * G.metrics(raw)["cell_centroid"][:, 2] / E_BOX
     e.field("charge").reshape(-1, 3)[:raw.n_cells, 2] = 1e15 * (1 + np.arange(raw.n_cells) % 7)
     e.field("chargeN1").reshape(-1, 3)[:] = e.field("charge").reshape(-1, 3)
     t0 = time.perf_counter()
@@ -375,43 +384,57 @@ def run_electric(args):
     step_ms = [t.get("electrostatics_ms", 0.0) + t.get("charge_ms", 0.0) for t in tm]
     total_ms = _allmax(sum(step_ms), world)
     e2e_s = _allmax(float(np.mean(e2e_t)), world)
-    # parity: the same model on a small box, THIS run's ranks as one partitioned problem, against the reference
+    # parity: the same model on a small box, THIS run's ranks as one partitioned problem, against the reference.
+    # The reference's updateConvectionFlux gives boundary face k of a non-symmetry group the velocity of cell c0 of face
+    # k of the whole mesh (F/ElectricModel_impl.h:1070-1088; reproduced in csrc/electric.cu): the charge then depends on
+    # the face numbering, hence on the partition, in the reference as here. On several ranks the charge is therefore
+    # compared in a second run whose field is uniform (potential started from its exact linear solution, no space
+    # charge: every cell has the same velocity); the potential is compared in the workload's own configuration.
     parity = {"oracle_check": {"oracle": "unavailable"}}
     if args.parity_size > 0:
         pn = max(4, min(args.parity_size, 16))
         praw = G.tet_mesh(pn, pn, pn, lx=E_BOX, ly=E_BOX, lz=E_BOX)
         nt = praw.n_total
-        ref_pot, ref_chg = np.zeros(nt), np.zeros(nt)
-        have = 0
+        cases = [False] if world == 1 else [False, True]      # uniform_field of _electric_model
+        ref_pack = np.zeros(2 * nt * len(cases) + 1)
         if rank == 0 and refapi.available():
-            _, ref = _electric_reference(praw, 2, 1e-13, kind=0)
-            ref_pot[:], ref_chg[:] = ref["potential"], ref["charge"][:, 2]
-            have = 1
+            for i, uf in enumerate(cases):
+                _, ref = _electric_reference(praw, 2, 1e-13, kind=0, uniform_field=uf)
+                ref_pack[2 * nt * i:2 * nt * i + nt] = ref["potential"]
+                ref_pack[2 * nt * i + nt:2 * nt * (i + 1)] = ref["charge"][:, 2]
+            ref_pack[-1] = 1
         if world > 1:
-            pack = torch.from_numpy(np.concatenate([ref_pot, ref_chg, [have]])).cuda()
+            pack = torch.from_numpy(ref_pack).cuda()
             dist.broadcast(pack, 0)
-            pack = pack.cpu().numpy()
-            ref_pot, ref_chg, have = pack[:nt], pack[nt:2 * nt], int(pack[-1])
+            ref_pack = pack.cpu().numpy()
             ploc = P.tet_block(pn, pn, pn, rank, world, lx=E_BOX, ly=E_BOX, lz=E_BOX)
         else:
             ploc = praw
-        if have:
-            m2, f2, e2 = _electric_model(lib, ploc, tol=1e-13, iters=500)
-            for _ in range(2):
-                with _quiet():
-                    e2.advance(1)
-                e2.updateTime()
-            c2 = m2.getCells()
+        if int(ref_pack[-1]):
             own = (ploc.cell_global if "cell_global" in ploc else np.arange(ploc.n_total))[:ploc.n_cells]
-            pot = np.asarray(f2.potential[c2])[:ploc.n_cells]
-            chg = np.asarray(f2.charge[c2])[:ploc.n_cells, 2]
-            s = _allsum([((pot - ref_pot[own]) ** 2).sum(), (ref_pot[own] ** 2).sum(),
-                         ((chg - ref_chg[own]) ** 2).sum(), (ref_chg[own] ** 2).sum()], world)
-            ep, ec = float(np.sqrt(s[0] / s[1])), float(np.sqrt(s[2] / s[3]))
-            parity = {"oracle_check": {"oracle": "reference (oracle/_ref ElectricModel<double>, single partition)",
-                                       "case": "%d^3 x 6 jittered tets in %d part(s), 2 time steps, solvers to rel 1e-13" % (pn, world),
-                                       "potential_rel_l2": ep, "charge_rel_l2": ec, "bar": 1e-8,
-                                       "pass": bool(ep <= 1e-8 and ec <= 1e-8)}}
+            errs = []
+            for i, uf in enumerate(cases):
+                ref_pot, ref_chg = ref_pack[2 * nt * i:2 * nt * i + nt], ref_pack[2 * nt * i + nt:2 * nt * (i + 1)]
+                m2, f2, e2 = _electric_model(lib, ploc, tol=1e-13, iters=500, uniform_field=uf)
+                for _ in range(2):
+                    with _quiet():
+                        e2.advance(1)
+                    e2.updateTime()
+                c2 = m2.getCells()
+                pot = np.asarray(f2.potential[c2])[:ploc.n_cells]
+                chg = np.asarray(f2.charge[c2])[:ploc.n_cells, 2]
+                s = _allsum([((pot - ref_pot[own]) ** 2).sum(), (ref_pot[own] ** 2).sum(),
+                             ((chg - ref_chg[own]) ** 2).sum(), (ref_chg[own] ** 2).sum()], world)
+                errs.append((float(np.sqrt(s[0] / s[1])), float(np.sqrt(s[2] / s[3]))))
+            ep, ec = errs[0][0], errs[-1][1]
+            oc = {"oracle": "reference (oracle/_ref ElectricModel<double>, single partition)",
+                  "case": "%d^3 x 6 jittered tets in %d part(s), 2 time steps, solvers to rel 1e-13" % (pn, world),
+                  "potential_rel_l2": ep, "charge_rel_l2": ec, "bar": 1e-8, "pass": bool(ep <= 1e-8 and ec <= 1e-8)}
+            if world > 1:
+                oc["charge_case"] = ("uniform field (linear initial potential, no space charge): the reference's boundary "
+                                     "drift flux depends on the face numbering, F/ElectricModel_impl.h:1070-1088")
+                oc["charge_rel_l2_workload_configuration"] = errs[0][1]
+            parity = {"oracle_check": oc}
     roof = table = None
     if not args.no_profile:
         lib.profile_begin()

@@ -43,6 +43,7 @@ struct ElectronVelocityRows {  // F/ElectricModel_impl.h:1037-1045
 // velocity of cell c0 of face k of the whole mesh (an interior face), not of its own neighbour cell.
 struct DriftFluxFaces {  // F/ElectricModel_impl.h:1064-1088
   int nInteriorFaces; const int* faceCells; const int* faceGroupOf; const int* groupIsSymmetry; const int* groupOffset;
+  const int* groupKind;
   const double4* faceGeom; const double* vel; double* flux;
   FVM_DEV double vdotA(int c, const double4 fg) const {
     double s = 0.0;
@@ -53,7 +54,9 @@ struct DriftFluxFaces {  // F/ElectricModel_impl.h:1064-1088
     const int f = (int)ff;
     const int c0 = faceCells[2 * f], c1 = faceCells[2 * f + 1];
     const double4 fg = faceGeom[f];
-    if (f >= nInteriorFaces) {
+    // the reference's first loop runs over ALL faces, its second one over the BOUNDARY groups only: a partition
+    // interface face keeps the two-sided average (c1 = the ghost cell holding the owner's velocity)
+    if (f >= nInteriorFaces && groupKind[faceGroupOf[f - nInteriorFaces]] != FVMGPU_GROUP_INTERFACE) {
       const int g = faceGroupOf[f - nInteriorFaces];
       const int cq = faceCells[2 * (f - groupOffset[g])];  // see NB above
       flux[f] = groupIsSymmetry[g] ? 0.0 : vdotA(cq, fg);
@@ -94,7 +97,7 @@ void electricDriftFlux(System* potential, System* charge, double mobility, doubl
   isSymDev.upload(isSym.data(), isSym.size());
   gOffDev.upload(gOff.data(), gOff.size());
   if (charge->faceFlux.n < (size_t)m->nFaces) charge->faceFlux.alloc((size_t)m->nFaces);
-  parallelFor(m->nFaces, DriftFluxFaces{m->nInteriorFaces, m->faceCells.p, m->faceGroupOf.p, isSymDev.p, gOffDev.p, m->faceGeom.p,
+  parallelFor(m->nFaces, DriftFluxFaces{m->nInteriorFaces, m->faceCells.p, m->faceGroupOf.p, isSymDev.p, gOffDev.p, m->groupKindDev.p, m->faceGeom.p,
                                         potential->aux3b.p, charge->faceFlux.p});
   charge->hasFaceFlux = true;
   if (vel_host) potential->aux3b.download(vel_host, 3 * nt);

@@ -106,6 +106,67 @@ def main():
         lib.dll.fvmgpu_hostsim_set_comm(*_keep)
         lib.comm_init(world, rank)
 
+    if solver_kind == "electric_bench":
+        # bench.py --workload electric-tet in miniature: the bench's own model set-up (Symmetry walls, BCGStab + AMG
+        # for both systems, its charge initial condition) on the block partition it uses (partition.tet_block),
+        # against the single-partition run of the same code.
+        # The reference's updateConvectionFlux gives boundary face k of a non-symmetry group the velocity of cell c0 of
+        # face k OF THE WHOLE MESH (F/ElectricModel_impl.h:1070-1088, reproduced): its result depends on the face
+        # numbering, i.e. on the partition -- in the reference as here. The partitioned run can therefore be compared
+        # with the single-partition one (i) in the potential, always, (ii) in the charge when the field is uniform (the
+        # velocity is then the same in every cell): potential initialised with the exact linear profile and no
+        # space charge. With the non-uniform field the interface fluxes are checked against their definition instead.
+        import contextlib
+        import io
+        import bench_workloads as W
+        pn = int(case)
+        kw = dict(lx=W.E_BOX, ly=W.E_BOX, lz=W.E_BOX)
+        graw = G.tet_mesh(pn, pn, pn, **kw)
+
+        def run(mesh_raw, uniform_field):
+            m2, f2, e2 = W._electric_model(lib, mesh_raw, tol=1e-13, iters=500, uniform_field=uniform_field)
+            for _ in range(2):
+                with contextlib.redirect_stdout(io.StringIO()):
+                    e2.advance(1)
+                e2.updateTime()
+            c2 = m2.getCells()
+            run.model = (m2, f2, e2)
+            return np.asarray(f2.potential[c2]).copy(), np.asarray(f2.charge[c2])[:, 2].copy()
+
+        lib.comm_destroy()
+        ref = {u: run(graw, u) for u in (False, True)}
+        rejoin(lib, world, rank)
+        ploc = P.tet_block(pn, pn, pn, rank, world, **kw) if world > 1 else graw
+        own = (ploc.cell_global if "cell_global" in ploc else np.arange(ploc.n_total))[:ploc.n_cells]
+        nv = ploc.n_cells
+        pot, _ = run(ploc, False)
+        # interface faces: flux = 0.5 (v_own + v_ghost) . A with the owner's velocity in the ghost cell
+        m2, f2, e2 = run.model
+        vel = np.asarray(f2.electron_velocity[m2.getCells()])
+        flux = np.asarray(f2.convectionFlux[m2.getFaces()])
+        area = np.asarray(e2.geom.area[m2.getFaces()])
+        fc = np.asarray(ploc.face_cells).reshape(-1, 2)
+        iface_err, n_iface = 0.0, 0
+        for gi in range(len(ploc.group_id)):
+            if int(ploc.group_kind[gi]) != X.GROUP_INTERFACE:
+                continue
+            o, c = int(ploc.group_offset[gi]), int(ploc.group_count[gi])
+            want = 0.5 * (np.einsum("ij,ij->i", vel[fc[o:o + c, 0]], area[o:o + c]) +
+                          np.einsum("ij,ij->i", vel[fc[o:o + c, 1]], area[o:o + c]))
+            iface_err = max(iface_err, float(np.abs(flux[o:o + c] - want).max() / np.abs(want).max()))
+            n_iface += c
+        _, chg = run(ploc, True)
+        t = torch.tensor([((pot[:nv] - ref[False][0][own]) ** 2).sum(), (ref[False][0][own] ** 2).sum(),
+                          ((chg[:nv] - ref[True][1][own]) ** 2).sum(), (ref[True][1][own] ** 2).sum()])
+        dist.all_reduce(t)
+        out = dict(rank=rank, world=world, n_self=int(nv), pot_rel_l2=float(torch.sqrt(t[0] / t[1])),
+                   chg_rel_l2=float(torch.sqrt(t[2] / t[3])), iface_flux_err=iface_err, n_iface=n_iface)
+        with open(os.path.join(os.environ["FVM_RESULT_DIR"], "rank%d.json" % rank), "w") as fh:
+            json.dump(out, fh)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
     if solver_kind == "thermgold":
         # T/PARALLEL_TESTS CAVITY_*_JACOBISOLVER: the golden (iteration count + last residual of a Jacobi-smoothed
         # solve to rel 1e-5) is the same file for every rank count the reference registered (1 ... 47)

@@ -142,3 +142,17 @@ def test_electric_model_on_partitioned_tets():
     an RCB-partitioned tet mesh, 2 ranks, against the single-partition run of the same model."""
     res = run_world(2, "tet_rcb", "electric", 200)
     check(res)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_electric_bench_configuration_on_block_partitions(world):
+    """bench.py --workload electric-tet's parity problem (its model set-up on partition.tet_block parts) against the
+    single-partition run: potential in the workload's configuration, charge with a uniform field (the reference's
+    boundary drift flux depends on the face numbering, see the worker), partition-interface fluxes = the two-sided
+    average of the owner's and the ghost's velocity."""
+    res = run_world(world, "8", "electric_bench")
+    for d in res:
+        assert d["pot_rel_l2"] <= 1e-8 and d["chg_rel_l2"] <= 1e-8, d
+        assert d["iface_flux_err"] <= 1e-12, d
+    assert sum(d["n_iface"] for d in res) > 0
+
