@@ -1501,7 +1501,7 @@ void Amg::setup(System* sys) {
   while ((1 << passesPerLevel) < opts.coarseGroupSize) passesPerLevel++;
   if (opts.coarseGroupSize <= 1) passesPerLevel = 0;
   if (g_referenceOrder && passesPerLevel > 1) passesPerLevel = 1;   // the sequential sweep groups coarseGroupSize rows itself
-  int mergeRows = 262144;
+  int mergeRows = 524288;   // 8 B200s, 512^3: 65536 1185 ms/step, 262144 1160, 524288 1146, 1048576 1150, 2100000 1257
   if (const char* e = getenv("FVMGPU_MERGE_ROWS")) mergeRows = atoi(e);
 
   for (int lvl = 0; lvl < opts.maxCoarseLevels && passesPerLevel > 0; lvl++) {
