@@ -577,6 +577,8 @@ def roofline(recs, step):
         if t.get("workload_cells") == n0 and g.get("rows_per_launch") == int(round(roof["rows_per_launch"])):
             roof["traffic"] = g["dram_bytes_read"] + g["dram_bytes_write"]
             roof["traffic_source"] = t["source"]
+        elif t.get("workload_cells") == n0 and t.get("note"):
+            roof["traffic_note"] = t["note"]
     return roof, table
 
 
