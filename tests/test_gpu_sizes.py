@@ -1,6 +1,6 @@
-"""Parity at sizes where the production code path differs from the one the small fixtures reach: level 0 above the
-cooperative kernel's row limit (per-level launches + CUDA graph + fused coarse stretch in ONE cycle), hierarchies of
-15+ levels, several CTAs per colour class. The checker is the reference's own C++ (oracle/_ref, prebuilt, travels to
+"""Parity at sizes where the production code path differs from the one the small fixtures reach: several levels above
+the cooperative kernel's row limit (per-level launches with 16-bit column offsets + CUDA graph + fused coarse stretch in
+ONE cycle), hierarchies of 15+ levels, several CTAs per colour class. The checker is the reference's own C++ (oracle/_ref, prebuilt, travels to
 the GPU box) run on the same mesh: assembly 1e-12, converged fields 1e-8 (north_star).
 The same code runs in the host simulator at toy sizes (-m "not gpu") so that the test bodies themselves stay green."""
 import contextlib
@@ -19,8 +19,8 @@ def lib_and_gpu(devlib, request):
 
 
 def test_thermal_hex_above_the_cooperative_row_limit(lib_and_gpu, ref, monkeypatch):
-    """112^3 jittered hexes (1.4 M rows: level 0 runs as per-level launches, levels 1.. in k_coop_vcycle /
-    k_tail_vcycle), random conductivity, flux + Dirichlet boundaries: bench.py's own parity block."""
+    """112^3 jittered hexes (1.4 M rows: levels 0-3 run as per-level launches, the levels from 88 K rows down in
+    k_coop_vcycle / k_tail_vcycle), random conductivity, flux + Dirichlet boundaries: bench.py's own parity block."""
     lib, gpu = lib_and_gpu
     n = 112 if gpu else 10
     monkeypatch.setattr(bench, "MESH", "tet")      # skip the exact-solution check of the bench workload (no workload here)
