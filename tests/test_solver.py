@@ -396,3 +396,40 @@ def test_compressed_columns_give_the_same_iterates(devlib):
     assert [b for b, n in zip(cb1, sz) if n >= 512] == [2.125] * sum(1 for n in sz if n >= 512) and cb1[0] == 2.125
     assert np.array_equal(h0, h1) and np.array_equal(d0, d1)
     ds.close(); dm.close()
+
+
+def test_compressed_columns_fall_back_slice_by_slice_on_a_scrambled_numbering(devlib):
+    """A 300 x 300 five-point system (90 000 rows) whose upper 80 % of the rows are renumbered at random: in the
+    scrambled part the k-th columns of a 32-row slice lie up to 70 000 rows apart, so those slices keep the int32
+    columns while the rest use the 16-bit copy (column bytes per entry strictly between 2.125 and 4). Mixed slices
+    must still give the plain-column iterates bit for bit."""
+    import scipy.sparse as sp
+    nx = 300
+    n = nx * nx
+    idx = np.arange(n).reshape(nx, nx)
+    pairs = np.concatenate([np.stack([idx[:, :-1].ravel(), idx[:, 1:].ravel()], 1),
+                            np.stack([idx[:-1, :].ravel(), idx[1:, :].ravel()], 1)])
+    rng = np.random.default_rng(12)
+    perm = np.arange(n)
+    perm[n // 5:] = n // 5 + rng.permutation(n - n // 5)
+    i, j = perm[pairs[:, 0]], perm[pairs[:, 1]]
+    w = rng.uniform(0.5, 2.0, len(i))
+    A = sp.coo_matrix((np.concatenate([w, w]), (np.concatenate([i, j]), np.concatenate([j, i]))), shape=(n, n)).tocsr()
+    A.sort_indices()
+    diag = -(np.asarray(A.sum(axis=1)).ravel() + 1e-3)          # rows sum to a small negative number: M-matrix
+    b = rng.normal(size=n)
+    out = []
+    for limit in (60, 70):
+        ds = X.DeviceSystem(devlib, raw=(n, 0, A.indptr.astype(np.int32), A.indices.astype(np.int32), diag,
+                                         A.data.copy(), b))
+        o = devlib.default_amg_opts()
+        o.nMaxIterations, o.relativeTolerance = limit, 1e-30
+        amg = X.DeviceAMG(devlib, o)
+        r0, r, it = amg.solve(ds)
+        # the residual history of the first 40 cycles is the fingerprint of the iterates (the two runs stop at
+        # different cycle counts)
+        out.append((amg.history()[:40], amg.levels()["col_bytes"]))
+        amg.close(); ds.close()
+    assert all(c == 4.0 for c in out[0][1])
+    assert 2.125 < out[1][1][0] < 4.0, out[1][1]
+    assert len(out[0][0]) == 40 and np.array_equal(out[0][0], out[1][0])
