@@ -1,13 +1,15 @@
 // fvm_b200 / libfvmgpu -- inter-rank communication of the hot path (one process per GPU).
 //
 // What the reference does with MPI                         here
-//   MultiField::sync / Field::syncLocal                     Halo::exchange: pack kernel -> grouped
-//     Isend/Irecv of packed ghost values + Waitall            ncclSend/ncclRecv over NVLink -> unpack
-//     (F/MultiField.cpp:488-551, F/Field.cpp:333-394)         kernel, all stream ordered
-//   MultiFieldReduction::reduceSum  Allreduce(SUM)          commAllreduceSum (ncclAllReduce, 1-8 doubles)
+//   MultiField::sync / Field::syncLocal                     Halo::exchange: ONE kernel stores the interface values
+//     Isend/Irecv of packed ghost values + Waitall            into the neighbour's memory over NVLink, flags, waits
+//     (F/MultiField.cpp:488-551, F/Field.cpp:333-394)         and unpacks (peer.cuh); all stream ordered
+//   MultiFieldReduction::reduceSum  Allreduce(SUM)          commAllreduceSum (peer stores, summed in rank order)
 //     (F/MultiFieldReduction.cpp:213-225)
-//   LinearSystemMerger Gatherv/Scatterv of coarse levels    commAllgather (ncclAllGather, equal-size
-//     (F/LinearSystemMerger.cpp:720-819)                      padded blocks)
+//   LinearSystemMerger Gatherv/Scatterv of coarse levels    commAllgather / peerAllgather (equal-size padded blocks)
+//     (F/LinearSystemMerger.cpp:720-819)
+// Without peer access between the ranks (or with FVMGPU_PEER=0) the same three steps run as pack kernel + grouped
+// ncclSend/ncclRecv + unpack kernel, ncclAllReduce and ncclAllGather; NCCL also carries the set-up.
 //
 // NCCL is resolved with dlopen (no link-time dependency). The FVMGPU_HOSTSIM test build replaces
 // the transport by callbacks the test harness registers (tests drive them with torch.distributed

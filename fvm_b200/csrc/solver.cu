@@ -1486,8 +1486,9 @@ void Amg::setup(System* sys) {
     if (ns) parallelFor(ns, GatherIntKernel{m->halo.scatterIdx.p, perm0.p, scatterDev.p});
     L0.halo.buildDev(m->halo.msgs, std::move(scatterDev), ns, m->haloGatherHost);  // ghost columns keep their cell index (>= n)
     agreeColours(L0);
-    // the captured cycle contains the NCCL send/recv, all-reduce and all-gather calls (NCCL >= 2.9
-    // supports stream capture); measured on 2 B200s: 7.5 -> 5.35 ms per cycle
+    // the captured cycle contains the exchange / all-reduce / all-gather kernels of the peer transport (their
+    // sequence numbers live in device memory, so a graph replays) -- or, on the fallback, the NCCL calls (NCCL >= 2.9
+    // supports stream capture); round 1, 2 B200s: 7.5 -> 5.35 ms per cycle
     if (const char* e = getenv("FVMGPU_MULTI_GRAPHS")) useGraphs = atoi(e) != 0;
     if (const char* e = getenv("FVMGPU_EXCHANGE_PER_COLOUR")) exchangePerColour = atoi(e) != 0;
     if (const char* e = getenv("FVMGPU_OVERLAP")) overlapExchange = atoi(e) != 0;
