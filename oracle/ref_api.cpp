@@ -344,6 +344,31 @@ int fvmref_mesh_sizes(void* h, int* out) {
   CATCH(-1)
 }
 
+// Mesh::getCellNodes (F/Mesh.cpp:425-451: cellFaces x faceNodes, then Cell<T>::orderCellFacesAndNodes, F/Cell.cpp:96-200):
+// row[nCells+1] / col of the SELF cells. Pass col == NULL to get the row offsets only (col length = row[nCells]).
+int fvmref_mesh_cell_nodes(void* h, int* row, int* col) {
+  TRY Mesh& mesh = ((RefMesh*)h)->mesh();
+  const CRConnectivity& cn = mesh.getCellNodes();
+  const int n = mesh.getCells().getSelfCount();
+  row[0] = 0;
+  for (int c = 0; c < n; c++) row[c + 1] = row[c] + cn.getCount(c);
+  if (col)
+    for (int c = 0; c < n; c++)
+      for (int k = 0; k < cn.getCount(c); k++) col[row[c] + k] = cn(c, k);
+  return 0;
+  CATCH(-1)
+}
+
+// Mesh::getNodeCoordinates(): xyz[3 * nNodes] in the mesh's own node numbering
+int fvmref_mesh_node_coordinates(void* h, double* xyz) {
+  TRY Mesh& mesh = ((RefMesh*)h)->mesh();
+  const Array<Vector<double, 3>>& x = mesh.getNodeCoordinates();
+  for (int i = 0; i < x.getLength(); i++)
+    for (int d = 0; d < 3; d++) xyz[3 * i + d] = x[i][d];
+  return 0;
+  CATCH(-1)
+}
+
 // groupKind: 0 interior, 1 boundary, 2 interface.  pairToCol: F/CRConnectivity.cpp:729-792.
 int fvmref_mesh_connectivity(void* h, int* faceCells, int* ccRow, int* ccCol, int* pairToCol,
                              int* groupOffset, int* groupCount, int* groupId, int* groupKind) {

@@ -73,6 +73,8 @@ def lib():
         L.fvmref_mesh_free.argtypes = [C.c_void_p]
         L.fvmref_mesh_sizes.argtypes = [C.c_void_p, _ip]
         L.fvmref_mesh_connectivity.argtypes = [C.c_void_p] + [_ip] * 8
+        L.fvmref_mesh_cell_nodes.argtypes = [C.c_void_p, _ip, C.c_void_p]
+        L.fvmref_mesh_node_coordinates.argtypes = [C.c_void_p, _dp]
         L.fvmref_mesh_geometry.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _ip]
         L.fvmref_thermal_create.restype = C.c_void_p
         L.fvmref_thermal_create.argtypes = [C.c_void_p]
@@ -194,6 +196,19 @@ class RefMesh:
                               pair_to_col=p2c.reshape(-1, 2), group_offset=go, group_count=gc,
                               group_id=gi, group_kind=gk)
         return self._conn
+
+    def cell_nodes(self):
+        """Mesh::getCellNodes() of the self cells as (row, col): the reference's canonical node order per cell type."""
+        row = np.zeros(self.n_self + 1, np.int32)
+        _check(lib().fvmref_mesh_cell_nodes(self.h, row, None))
+        col = np.zeros(int(row[-1]), np.int32)
+        _check(lib().fvmref_mesh_cell_nodes(self.h, row, col.ctypes.data_as(C.c_void_p)))
+        return row, col
+
+    def node_coordinates(self):
+        xyz = np.zeros(3 * self.n_nodes)
+        _check(lib().fvmref_mesh_node_coordinates(self.h, xyz))
+        return xyz.reshape(-1, 3)
 
     def geometry(self):
         if self._geom is None:
