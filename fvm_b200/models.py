@@ -669,6 +669,253 @@ class ThermalModelA:
             f.temperatureN1[cells][:] = f.temperature[cells]
 
 
+# ----------------------------------------------------------------------------- SpeciesModel
+class SpeciesBC(FloatVarDict):
+    """F/SpeciesBC.h:8-19"""
+
+    def __init__(self):
+        super().__init__()
+        self.defineVar("specifiedMassFraction", 0.0)
+        self.defineVar("specifiedMassFlux", 0.0)
+        self.bcType = ""
+
+
+class SpeciesVC(FloatVarDict):
+    """F/SpeciesBC.h:21-30"""
+
+    def __init__(self):
+        super().__init__()
+        self.defineVar("massDiffusivity", 1e-9)
+        self.defineVar("initialMassFraction", 1.0)
+        self.vcType = ""
+
+
+class SpeciesModelOptions(FloatVarDict):
+    """F/SpeciesBC.h:32-74"""
+
+    def __init__(self):
+        super().__init__()
+        for name, v in (("A_coeff", 1.0), ("B_coeff", 0.0), ("ButlerVolmerRRConstant", 5.0e-7),
+                        ("ButlerVolmerAnodeShellMeshID", -1), ("ButlerVolmerCathodeShellMeshID", -1),
+                        ("timeStep", 0.1), ("interfaceUnderRelax", 1.0)):
+            self.defineVar(name, v)
+        self.relativeTolerance = 1e-8
+        self.absoluteTolerance = 1e-16
+        self.linearSolver = None
+        self.useCentralDifference = False
+        self.transient = False
+        self.ButlerVolmer = False
+        self.timeDiscretizationOrder = 1
+
+    def getLinearSolver(self):
+        if self.linearSolver is None:  # F/SpeciesBC.h:61-72
+            ls = AMG()
+            ls.relativeTolerance = 1e-1
+            ls.nMaxIterations = 20
+            ls.verbosity = 0
+            self.linearSolver = ls
+        return self.linearSolver
+
+
+class SpeciesFields:
+    """F/SpeciesFields.h:11-30 (one set per species)"""
+
+    def __init__(self, base_name):
+        for n in ("massFraction", "massFlux", "diffusivity", "source", "convectionFlux", "massFractionN1",
+                  "massFractionN2", "zero", "one", "elecPotential", "massFractionElectricModel"):
+            setattr(self, n, Field(base_name + "." + n))
+
+
+class SpeciesModelA:
+    """SpeciesModel<double> (F/SpeciesModel.h:17-55, Impl in F/SpeciesModel_impl.h): nSpecies scalar transport
+    equations (diffusion + convection + source [+ time derivative]), one after the other per outer iteration -- the
+    same device path as ThermalModelA (gradient, fused assembly with BCs and boundary elimination, linear solve,
+    postSolve / updateSolution), one LinearSystem per species. The shell-mesh couplings of the reference (interface
+    jump, Butler-Volmer: F/SpeciesModel_impl.h:493-540) belong to its battery models and are rejected."""
+
+    def __init__(self, geom_fields, meshes, nSpecies, lib=None):
+        self.geom, self.meshes, self.lib, self._nSpecies = geom_fields, list(meshes), lib, int(nSpecies)
+        self._options = SpeciesModelOptions()
+        self._fields = [SpeciesFields("species") for _ in range(self._nSpecies)]
+        self._bcMaps = [dict() for _ in range(self._nSpecies)]
+        self._vcMaps = [dict() for _ in range(self._nSpecies)]
+        self._initialNorm = [None] * self._nSpecies
+        self._currentResidual = [None] * self._nSpecies
+        self._niters = 0
+        self._systems = {}
+        self.timings = []
+        for m in range(self._nSpecies):  # F/SpeciesModel_impl.h:55-95
+            for mesh in self.meshes:
+                vc = SpeciesVC()
+                vc.vcType = "flow"
+                self._vcMaps[m][mesh.getID()] = vc
+                for fg in mesh.getBoundaryFaceGroups():
+                    bc = SpeciesBC()
+                    self._bcMaps[m][fg.id] = bc
+                    if fg.groupType in ("wall", "symmetry"):
+                        bc.bcType = "SpecifiedMassFlux"
+                    elif fg.groupType in ("velocity-inlet", "pressure-outlet"):
+                        bc.bcType = "SpecifiedMassFraction"
+                    else:
+                        raise CException("SpeciesModel: unknown face group type " + fg.groupType)
+
+    def getSpeciesFields(self, speciesId):
+        return self._fields[speciesId]
+
+    def getBCMap(self, speciesId):
+        return self._bcMaps[speciesId]
+
+    def getVCMap(self, speciesId):
+        return self._vcMaps[speciesId]
+
+    def getBC(self, gid, speciesId):
+        return self._bcMaps[speciesId][gid]
+
+    def getOptions(self):
+        return self._options
+
+    def init(self):  # F/SpeciesModel_impl.h:97-330
+        o = self._options
+        if o.ButlerVolmer:
+            raise CException("SpeciesModelA: the Butler-Volmer shell coupling is not built")
+        for m in range(self._nSpecies):
+            f = self._fields[m]
+            for mesh in self.meshes:
+                if mesh.device is None:
+                    raise CException("SpeciesModel.init: mesh metrics not initialised (MeshMetricsCalculatorA.init)")
+                cells, faces = mesh.getCells(), mesh.getFaces()
+                n = cells.getCount()
+                vc = self._vcMaps[m][mesh.getID()]
+                f.massFraction[cells] = np.full(n, float(vc["initialMassFraction"]))
+                if o.transient:
+                    f.massFractionN1[cells] = f.massFraction[cells].copy()
+                    if o.timeDiscretizationOrder > 1:
+                        f.massFractionN2[cells] = f.massFraction[cells].copy()
+                f.diffusivity[cells] = np.full(n, float(vc["massDiffusivity"]))
+                f.source[cells] = np.zeros(n)
+                f.zero[cells] = np.zeros(n)
+                f.one[cells] = np.ones(n)
+                f.convectionFlux[faces] = np.zeros(faces.getCount())
+                for fg in mesh.getBoundaryFaceGroups():
+                    f.massFlux[fg.site] = np.zeros(fg.site.getCount())
+                lib = self.lib or mesh.device.lib
+                self._systems[(m, mesh.getID())] = LinearSystem(lib, mesh=mesh.device, field_name=f.massFraction.name)
+        self._niters = 0
+        self._initialNorm = [None] * self._nSpecies
+        self._currentResidual = [None] * self._nSpecies
+
+    def _upload(self, m, mesh, ls):
+        f, o = self._fields[m], self._options
+        cells, faces = mesh.getCells(), mesh.getFaces()
+        ls.set_field(capi.FIELD_X, f.massFraction[cells])
+        ls.set_field(capi.FIELD_DIFFUSIVITY, f.diffusivity[cells])
+        ls.set_field(capi.FIELD_SOURCE, f.source[cells])
+        flux = f.convectionFlux[faces]
+        convecting = bool(flux.any())
+        if convecting:
+            ls.set_field(capi.FIELD_FACE_FLUX, flux)
+        if o.transient:
+            ls.set_field(capi.FIELD_X_N1, f.massFractionN1[cells])
+            ls.set_field(capi.FIELD_DENSITY, f.one[cells])
+            if o.timeDiscretizationOrder > 1:
+                ls.set_field(capi.FIELD_X_N2, f.massFractionN2[cells])
+        for fg in mesh.getBoundaryFaceGroups():   # F/SpeciesModel_impl.h:549-606
+            bc = self._bcMaps[m].get(fg.id)
+            if bc is None:
+                raise CException("SpeciesModel: Error in BC Map")
+            if bc.bcType == "SpecifiedMassFraction":
+                # the model always holds a convection flux: per face extrapolation where it leaves, else Dirichlet
+                v = bc["specifiedMassFraction"]
+                kind = capi.BC_DIRICHLET_OR_OUTFLOW if convecting else capi.BC_DIRICHLET
+                if isinstance(v, np.ndarray):
+                    ls.set_bc(fg.id, kind, [0.0], per_face=v)
+                else:
+                    ls.set_bc(fg.id, kind, [float(v)])
+            elif bc.bcType == "SpecifiedMassFlux":
+                ls.set_bc(fg.id, capi.BC_NEUMANN, [float(bc["specifiedMassFlux"])])
+            elif bc.bcType == "Symmetry":
+                ls.set_bc(fg.id, capi.BC_NEUMANN, [0.0])
+            else:
+                raise CException(bc.bcType + " not implemented for SpeciesModel")
+        return convecting
+
+    def advance(self, niter):
+        """Impl::advance, F/SpeciesModel_impl.h:671-713: every outer iteration solves the species one after the other;
+        the loop ends when all of them meet the tolerance."""
+        o = self._options
+        solver = o.getLinearSolver()
+        if len(self.meshes) != 1:
+            raise CException("SpeciesModelA: one mesh per model in this release")
+        mesh = self.meshes[0]
+        cells = mesh.getCells()
+        for _ in range(niter):
+            all_converged = True
+            for m in range(self._nSpecies):
+                f = self._fields[m]
+                ls = self._systems[(m, mesh.getID())]
+                convecting = self._upload(m, mesh, ls)
+                ls.lib.timer_start(1)
+                ls.assemble(diffusion=1, convection=(2 if o.useCentralDifference else 1) if convecting else 0, source=1,
+                            time_order=(o.timeDiscretizationOrder if o.transient else 0),
+                            dt=float(o["timeStep"]) if o.transient else 0.0, underrelax=0.0, apply_bcs=1,
+                            eliminate_boundary=1)
+                rnorm = solver.solve(ls)
+                if self._initialNorm[m] is None:
+                    self._initialNorm[m] = rnorm
+                ratio = rnorm / self._initialNorm[m] if self._initialNorm[m] != 0 else 0.0
+                print("Species Number: %d" % m)
+                print("%d: [%s : %g]" % (self._niters, f.massFraction.name, rnorm))
+                solver.cleanup()
+                ls.post_solve_update()
+                self.timings.append({"species": m, "ms": ls.lib.timer_stop(1), "rnorm": rnorm,
+                                     "linear_iterations": getattr(solver, "lastIterations", 0)})
+                f.massFraction[cells][:] = ls.get_field(capi.FIELD_X)
+                bflux = ls.get_field(capi.FIELD_BFLUX)
+                for fg in mesh.getBoundaryFaceGroups():
+                    off = fg.site.getOffset()
+                    f.massFlux[fg.site][:] = bflux[off:off + fg.site.getCount()]
+                self._niters += 1
+                self._currentResidual[m] = rnorm
+                if not (rnorm < o.absoluteTolerance or ratio < o.relativeTolerance):
+                    all_converged = False
+            if all_converged:
+                break
+
+    def updateTime(self):  # F/SpeciesModel_impl.h:341-368
+        o = self._options
+        for f in self._fields:
+            for mesh in self.meshes:
+                cells = mesh.getCells()
+                if o.timeDiscretizationOrder > 1:
+                    f.massFractionN2[cells][:] = f.massFractionN1[cells]
+                f.massFractionN1[cells][:] = f.massFraction[cells]
+
+    def getMassFluxIntegral(self, mesh, faceGroupId, m):  # F/SpeciesModel_impl.h:614-652
+        for fg in mesh.getBoundaryFaceGroups():
+            if fg.id == faceGroupId:
+                return float(np.sum(self._fields[m].massFlux[fg.site]))
+        raise CException("getMassFluxIntegral: invalid faceGroupID")
+
+    def getAverageMassFraction(self, mesh, m):  # :654-668
+        cells = mesh.getCells()
+        n = cells.getSelfCount()
+        vol = np.asarray(self.geom.volume[cells])[:n]
+        return float(np.sum(np.asarray(self._fields[m].massFraction[cells])[:n] * vol) / np.sum(vol))
+
+    def getMassFractionResidual(self, speciesId):  # :739-748
+        return self._currentResidual[speciesId]
+
+    def printBCs(self):  # :715-737
+        for m in range(self._nSpecies):
+            print("Species Number :%d" % m)
+            for gid in sorted(self._bcMaps[m]):
+                bc = self._bcMaps[m][gid]
+                print("Face Group %d:" % gid)
+                print("    bc type " + bc.bcType)
+                for k in sorted(bc):
+                    print("   %s %g" % (k, bc[k]))
+
+
 # ----------------------------------------------------------------------------- FlowModel (SIMPLE)
 class FlowBC(FloatVarDict):
     """F/FlowBC.h:9-21"""

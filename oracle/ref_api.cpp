@@ -55,6 +55,9 @@
 #include "ElectricFields.h"
 #include "ElectricModel.h"
 #include "ElectricModel_impl.h"
+#include "SpeciesFields.h"
+#include "SpeciesModel.h"
+#include "SpeciesModel_impl.h"
 #undef private
 #undef protected
 
@@ -62,6 +65,7 @@ template class MeshMetricsCalculator<double>;
 template class ThermalModel<double>;
 template class FlowModel<double>;
 template class ElectricModel<double>;
+template class SpeciesModel<double>;
 
 typedef Vector<double, 3> Vec3;
 typedef Array<Vec3> Vec3Array;
@@ -171,6 +175,12 @@ static void copy_text(const std::string& s, char* out, int cap) {
   std::memcpy(out, s.data(), n);
   out[n] = 0;
 }
+
+struct RefSpecies {
+  RefMesh* m;
+  std::shared_ptr<SpeciesModel<double>> model;
+  RefSolver solver;
+};
 
 struct RefThermal {
   RefMesh* m;
@@ -429,6 +439,112 @@ int fvmref_mesh_geometry(void* h, double* faceArea, double* faceAreaMag, double*
     cellVolume[c] = cv[c];
     if (ibType) ibType[c] = ib[c];
   }
+  return 0;
+  CATCH(-1)
+}
+
+// ---------------------------------------------------------------- SpeciesModel (F/SpeciesModel.h:17-55)
+
+void* fvmref_species_create(void* h, int nSpecies) {
+  TRY RefMesh* rm = (RefMesh*)h;
+  RefSpecies* t = new RefSpecies;
+  t->m = rm;
+  t->model.reset(new SpeciesModel<double>(*rm->geom, rm->meshes, nSpecies));
+  return t;
+  CATCH(nullptr)
+}
+void fvmref_species_free(void* h) { delete (RefSpecies*)h; }
+int fvmref_species_set_bc(void* h, int species, int id, const char* bcType, const char* var, double value) {
+  TRY RefSpecies* t = (RefSpecies*)h;
+  auto& bcMap = t->model->getBCMap(species);
+  if (bcMap.find(id) == bcMap.end()) throw CException("no such boundary id");
+  SpeciesBC<double>& bc = *bcMap[id];
+  if (bcType && bcType[0]) bc.bcType = bcType;
+  if (var && var[0]) {
+    auto pos = bc.find(var);
+    if (pos == bc.end()) throw CException(std::string("unknown bc var ") + var);
+    pos->second.constant = value;
+  }
+  return 0;
+  CATCH(-1)
+}
+int fvmref_species_set_vc(void* h, int species, const char* var, double value) {
+  TRY RefSpecies* t = (RefSpecies*)h;
+  for (auto& kv : t->model->getVCMap(species)) {
+    auto pos = kv.second->find(var);
+    if (pos == kv.second->end()) throw CException(std::string("unknown vc var ") + var);
+    pos->second.constant = value;
+  }
+  return 0;
+  CATCH(-1)
+}
+int fvmref_species_set_option(void* h, const char* name, double value) {
+  TRY RefSpecies* t = (RefSpecies*)h;
+  SpeciesModelOptions<double>& o = t->model->getOptions();
+  std::string n(name);
+  if (n == "relativeTolerance") o.relativeTolerance = value;
+  else if (n == "absoluteTolerance") o.absoluteTolerance = value;
+  else if (n == "transient") o.transient = value != 0;
+  else if (n == "timeDiscretizationOrder") o.timeDiscretizationOrder = (int)value;
+  else if (n == "useCentralDifference") o.useCentralDifference = value != 0;
+  else {
+    auto pos = o.find(n);
+    if (pos == o.end()) throw CException("unknown option " + n);
+    pos->second.constant = value;
+  }
+  return 0;
+  CATCH(-1)
+}
+int fvmref_species_set_solver(void* h, const SolverCfg* cfg) {
+  TRY RefSpecies* t = (RefSpecies*)h;
+  t->solver = make_solver(*cfg);
+  t->model->getOptions().linearSolver = t->solver.top;
+  return 0;
+  CATCH(-1)
+}
+int fvmref_species_init(void* h) {
+  TRY((RefSpecies*)h)->model->init();
+  return 0;
+  CATCH(-1)
+}
+// name: massFraction, diffusivity, source, massFractionN1, massFractionN2 (cells), convectionFlux (all faces)
+double* fvmref_species_field(void* h, int species, const char* name, int* len) {
+  TRY RefSpecies* t = (RefSpecies*)h;
+  Mesh& mesh = t->m->mesh();
+  const StorageSite& cells = mesh.getCells();
+  std::string n(name);
+  SpeciesFields& sf = t->model->getSpeciesFields(species);
+  ArrayBase* a = nullptr;
+  if (n == "massFraction") a = &sf.massFraction[cells];
+  else if (n == "diffusivity") a = &sf.diffusivity[cells];
+  else if (n == "source") a = &sf.source[cells];
+  else if (n == "massFractionN1") a = &sf.massFractionN1[cells];
+  else if (n == "massFractionN2") a = &sf.massFractionN2[cells];
+  else if (n == "convectionFlux") a = &sf.convectionFlux[mesh.getFaces()];
+  else throw CException("unknown field " + n);
+  if (len) *len = a->getDataSize() / (int)sizeof(double);
+  return (double*)a->getData();
+  CATCH(nullptr)
+}
+int fvmref_species_advance(void* h, int niter, char* text, int textCap) {
+  TRY RefSpecies* t = (RefSpecies*)h;
+  CoutCapture cap;
+  t->model->advance(niter);
+  copy_text(cap.os.str(), text, textCap);
+  return 0;
+  CATCH(-1)
+}
+int fvmref_species_update_time(void* h) {
+  TRY((RefSpecies*)h)->model->updateTime();
+  return 0;
+  CATCH(-1)
+}
+// getMassFluxIntegral / getAverageMassFraction / getMassFractionResidual: what = 0 / 1 / 2 (arg = face group id for 0)
+int fvmref_species_query(void* h, int species, int what, int arg, double* out) {
+  TRY RefSpecies* t = (RefSpecies*)h;
+  if (what == 0) *out = t->model->getMassFluxIntegral(t->m->mesh(), arg, species);
+  else if (what == 1) *out = t->model->getAverageMassFraction(t->m->mesh(), species);
+  else *out = t->model->getMassFractionResidual(species);
   return 0;
   CATCH(-1)
 }

@@ -1,0 +1,118 @@
+"""SpeciesModel (another consumer of the same scalar path): nSpecies transport equations -- diffusion,
+upwind convection with the per-face outflow rule on SpecifiedMassFraction boundaries, source, second-order time
+derivative -- against the reference's own SpeciesModel<double> run in place (oracle/_ref)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from fvm_b200 import meshgen as G, models as M
+
+SOL_TOL = 1e-9     # north_star: 1e-8; observed 1e-12
+
+
+def _setup_ref(ref, raw, transient):
+    rm = ref.RefMesh.from_raw(raw.dim, raw.n_cells, raw.nodes, raw.face_cells, raw.face_nodes, raw.face_node_count,
+                              raw.face_group_size)
+    s = ref.RefSpecies(rm, 2)
+    for m, (lo, hi) in enumerate(((0.2, 0.9), (1.0, 0.0))):
+        for g in (2, 3, 4):
+            s.set_bc(m, g, "Symmetry")
+        s.set_bc(m, 1, "SpecifiedMassFlux", specifiedMassFlux=0.3 * (m + 1))
+        s.set_bc(m, 5, "SpecifiedMassFraction", specifiedMassFraction=lo)
+        s.set_bc(m, 6, "SpecifiedMassFraction", specifiedMassFraction=hi)
+        s.set_vc(m, "massDiffusivity", 0.7 + m)
+        s.set_vc(m, "initialMassFraction", 0.5)
+    if transient:
+        s.set_option("transient", 1)
+        s.set_option("timeDiscretizationOrder", 2)
+        s.set_option("timeStep", 0.05)
+    s.set_solver(ref.solver_cfg(relativeTolerance=1e-13, nMaxIterations=3000, verbosity=0))
+    s.init()
+    return rm, s
+
+
+def _setup_ours(lib, raw, transient):
+    mesh = M.Mesh(raw)
+    geom = M.GeomFields("geom")
+    M.MeshMetricsCalculatorA(geom, [mesh], lib=lib).init()
+    sm = M.SpeciesModelA(geom, [mesh], 2, lib=lib)
+    for m, (lo, hi) in enumerate(((0.2, 0.9), (1.0, 0.0))):
+        bcs = sm.getBCMap(m)
+        for g in (2, 3, 4):
+            bcs[g].bcType = "Symmetry"
+        bcs[1].bcType = "SpecifiedMassFlux"; bcs[1]["specifiedMassFlux"] = 0.3 * (m + 1)
+        bcs[5].bcType = "SpecifiedMassFraction"; bcs[5]["specifiedMassFraction"] = lo
+        bcs[6].bcType = "SpecifiedMassFraction"; bcs[6]["specifiedMassFraction"] = hi
+        vc = sm.getVCMap(m)[mesh.getID()]
+        vc["massDiffusivity"] = 0.7 + m
+        vc["initialMassFraction"] = 0.5
+    o = sm.getOptions()
+    if transient:
+        o.transient, o.timeDiscretizationOrder = True, 2
+        o["timeStep"] = 0.05
+    s = M.AMG()
+    s.relativeTolerance, s.nMaxIterations, s.verbosity = 1e-13, 3000, 0
+    o.linearSolver = s
+    sm.init()
+    return mesh, sm
+
+
+@pytest.mark.parametrize("mesh_kind,transient", [("hex", False), ("hex", True), ("tet", True)])
+def test_species_model_matches_the_reference(devlib, ref, mesh_kind, transient):
+    raw = G.hex_mesh(7, 6, 8, jitter=0.15, seed=5) if mesh_kind == "hex" else G.tet_mesh(4, 5, 4)
+    rm, rs = _setup_ref(ref, raw, transient)
+    mesh, sm = _setup_ours(devlib, raw, transient)
+    # a convecting flux (uniform velocity through the mesh: leaves through some boundary faces, enters through others)
+    # for species 1 only; species 0 diffuses
+    area = rm.geometry()["face_area"]
+    flux = area @ np.array([0.4, -0.2, 0.9])
+    rs.field(1, "convectionFlux")[:] = flux
+    sm.getSpeciesFields(1).convectionFlux[mesh.getFaces()][:] = flux
+    # a source for species 0
+    src = np.linspace(0.0, 2.0, raw.n_total)
+    rs.field(0, "source")[:] = src
+    sm.getSpeciesFields(0).source[mesh.getCells()][:] = src
+    texts = []
+    for step in range(3 if transient else 1):
+        rs.advance(2)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            sm.advance(2)
+        texts.append(buf.getvalue())
+        if transient:
+            rs.update_time()
+            sm.updateTime()
+    n = raw.n_cells
+    for m in range(2):
+        got = np.asarray(sm.getSpeciesFields(m).massFraction[mesh.getCells()])
+        want = rs.field(m, "massFraction")
+        assert np.abs(got[:n] - want[:n]).max() <= SOL_TOL * np.abs(want[:n]).max(), (m, mesh_kind, transient)
+        assert np.abs(got[n:] - want[n:]).max() <= 1e-8 * np.abs(want).max()      # ghost values (Dirichlet / extrapolated)
+        assert abs(sm.getAverageMassFraction(mesh, m) - rs.average_mass_fraction(m)) <= 1e-9
+        for gid in (1, 5, 6):
+            a, b = sm.getMassFluxIntegral(mesh, gid, m), rs.mass_flux_integral(m, gid)
+            assert abs(a - b) <= 1e-8 * max(1.0, abs(b)), (m, gid, a, b)
+    lines = texts[0].splitlines()
+    assert lines[0] == "Species Number: 0" and lines[1].startswith("0: [species.massFraction : ")
+    assert lines[2] == "Species Number: 1" and lines[3].startswith("1: [species.massFraction : ")
+    with pytest.raises(M.CException):
+        sm.getMassFluxIntegral(mesh, 99, 0)
+    rs.close()
+
+
+def test_species_model_rejects_what_is_not_built(hostsim_lib):
+    raw = G.hex_mesh(3, 3, 3)
+    mesh = M.Mesh(raw)
+    geom = M.GeomFields("geom")
+    M.MeshMetricsCalculatorA(geom, [mesh], lib=hostsim_lib).init()
+    sm = M.SpeciesModelA(geom, [mesh], 1, lib=hostsim_lib)
+    sm.getOptions().ButlerVolmer = True
+    with pytest.raises(M.CException):
+        sm.init()
+    sm.getOptions().ButlerVolmer = False
+    sm.init()
+    sm.getBCMap(0)[1].bcType = "Convective"
+    with pytest.raises(M.CException):
+        sm.advance(1)
