@@ -916,6 +916,227 @@ class SpeciesModelA:
                     print("   %s %g" % (k, bc[k]))
 
 
+# ----------------------------------------------------------------------------- VacancyModel
+class VacancyBC(FloatVarDict):
+    """F/VacancyBC.h:8-20"""
+
+    def __init__(self):
+        super().__init__()
+        self.defineVar("specifiedConcentration", 300.0)
+        self.defineVar("specifiedVacaFlux", 0.0)
+        self.defineVar("convectiveCoefficient", 0.0)
+        self.defineVar("farFieldConcentration", 300.0)
+        self.bcType = ""
+
+
+class VacancyVC(FloatVarDict):
+    """F/VacancyBC.h:22-34"""
+
+    def __init__(self):
+        super().__init__()
+        self.defineVar("vacancyDiffusioncoefficient", 1.0)
+        self.defineVar("density", 1.0)
+        self.defineVar("specificVaca", 1.0)
+        self.vcType = ""
+
+
+class VacancyModelOptions(FloatVarDict):
+    """F/VacancyBC.h:36-73"""
+
+    def __init__(self):
+        super().__init__()
+        self.defineVar("initialConcentration", 300.0)
+        self.defineVar("timeStep", 1e-7)
+        self.relativeTolerance = 1e-8
+        self.absoluteTolerance = 1e-16
+        self.linearSolver = None
+        self.useCentralDifference = False
+        self.transient = False
+        self.timeDiscretizationOrder = 1
+
+    def getLinearSolver(self):
+        if self.linearSolver is None:
+            ls = AMG()
+            ls.relativeTolerance = 1e-1
+            ls.nMaxIterations = 20
+            ls.verbosity = 0
+            self.linearSolver = ls
+        return self.linearSolver
+
+
+class VacancyFields:
+    """F/VacancyFields.h:11-30 (names as F/VacancyFields.cpp:7-21 spells them)"""
+
+    def __init__(self, base_name):
+        for n in ("concentration", "concentrationN1", "concentrationN2", "vacaFlux", "concentrationGradient",
+                  "concentrationGradientVector", "diffusioncoefficient", "source", "convectionFlux", "specificVaca"):
+            setattr(self, n, Field(base_name + "." + n))
+        for n in ("plasticStrain", "zero", "one"):
+            setattr(self, n, Field(base_name + n))
+
+
+class VacancyModelA:
+    """VacancyModel<double> (F/VacancyModel.h:18-55, Impl in F/VacancyModel_impl.h): the vacancy-concentration
+    transport equation -- diffusion + convection + source [+ rho * specificVaca time derivative] with
+    SpecifiedConcentration (per-face outflow rule) / SpecifiedVacaFlux / Symmetry / Convective boundaries -- on the
+    scalar device path. computePlasticStrainRate (the gradient of the concentration gradient, a coupling to the
+    structure models, :619-662) and the immersed-boundary hooks are not built."""
+
+    def __init__(self, geom_fields, vacancy_fields, meshes, lib=None):
+        self.geom, self.fields, self.meshes, self.lib = geom_fields, vacancy_fields, list(meshes), lib
+        self._bcMap, self._vcMap = {}, {}
+        self._options = VacancyModelOptions()
+        self._initialNorm = None
+        self._niters = 0
+        self._systems = {}
+        self.timings = []
+        for mesh in self.meshes:  # F/VacancyModel_impl.h:57-86
+            vc = VacancyVC()
+            vc.vcType = "flow"
+            self._vcMap[mesh.getID()] = vc
+            for fg in mesh.getBoundaryFaceGroups():
+                bc = VacancyBC()
+                self._bcMap[fg.id] = bc
+                if fg.groupType in ("wall", "symmetry"):
+                    bc.bcType = "SpecifiedVacaFlux"
+                elif fg.groupType in ("velocity-inlet", "pressure-outlet"):
+                    bc.bcType = "SpecifiedConcentration"
+                else:
+                    raise CException("VacancyModel: unknown face group type " + fg.groupType)
+
+    def getBCMap(self):
+        return self._bcMap
+
+    def getVCMap(self):
+        return self._vcMap
+
+    def getBC(self, gid):
+        return self._bcMap[gid]
+
+    def getOptions(self):
+        return self._options
+
+    def init(self):  # F/VacancyModel_impl.h:88-186
+        f, o = self.fields, self._options
+        for mesh in self.meshes:
+            if mesh.device is None:
+                raise CException("VacancyModel.init: mesh metrics not initialised (MeshMetricsCalculatorA.init)")
+            cells, faces = mesh.getCells(), mesh.getFaces()
+            n = cells.getCount()
+            vc = self._vcMap[mesh.getID()]
+            f.concentration[cells] = np.full(n, float(o["initialConcentration"]))
+            if o.transient:
+                f.concentrationN1[cells] = f.concentration[cells].copy()
+                if o.timeDiscretizationOrder > 1:
+                    f.concentrationN2[cells] = f.concentration[cells].copy()
+            f.diffusioncoefficient[cells] = np.full(n, float(vc["vacancyDiffusioncoefficient"]))
+            f.source[cells] = np.zeros(n)
+            f.zero[cells] = np.zeros(n)
+            f.one[cells] = np.ones(n)
+            f.specificVaca[cells] = np.full(n, float(vc["density"]) * float(vc["specificVaca"]))
+            f.concentrationGradient[cells] = np.zeros((n, 3))
+            f.concentrationGradientVector[cells] = np.zeros((n, 3))
+            f.plasticStrain[cells] = np.zeros((n, 3, 3))
+            f.convectionFlux[faces] = np.zeros(faces.getCount())
+            for fg in mesh.getBoundaryFaceGroups():
+                f.vacaFlux[fg.site] = np.zeros(fg.site.getCount())
+            lib = self.lib or mesh.device.lib
+            self._systems[mesh.getID()] = LinearSystem(lib, mesh=mesh.device, field_name=f.concentration.name)
+        self._niters = 0
+        self._initialNorm = None
+
+    def _upload(self, mesh, ls):
+        f, o = self.fields, self._options
+        cells, faces = mesh.getCells(), mesh.getFaces()
+        ls.set_field(capi.FIELD_X, f.concentration[cells])
+        ls.set_field(capi.FIELD_DIFFUSIVITY, f.diffusioncoefficient[cells])
+        ls.set_field(capi.FIELD_SOURCE, f.source[cells])
+        flux = f.convectionFlux[faces]
+        convecting = bool(flux.any())
+        if convecting:
+            ls.set_field(capi.FIELD_FACE_FLUX, flux)
+        if o.transient:
+            ls.set_field(capi.FIELD_X_N1, f.concentrationN1[cells])
+            ls.set_field(capi.FIELD_DENSITY, f.specificVaca[cells])
+            if o.timeDiscretizationOrder > 1:
+                ls.set_field(capi.FIELD_X_N2, f.concentrationN2[cells])
+
+        def scalar_or_faces(v):
+            return (0.0, v) if isinstance(v, np.ndarray) else (float(v), None)
+
+        for fg in mesh.getBoundaryFaceGroups():   # F/VacancyModel_impl.h:316-381
+            bc = self._bcMap[fg.id]
+            if bc.bcType == "SpecifiedConcentration":
+                v, pf = scalar_or_faces(bc["specifiedConcentration"])
+                ls.set_bc(fg.id, capi.BC_DIRICHLET_OR_OUTFLOW if convecting else capi.BC_DIRICHLET, [v], per_face=pf)
+            elif bc.bcType == "SpecifiedVacaFlux":
+                v, pf = scalar_or_faces(bc["specifiedVacaFlux"])
+                ls.set_bc(fg.id, capi.BC_NEUMANN, [v], per_face=pf)
+            elif bc.bcType == "Symmetry":
+                ls.set_bc(fg.id, capi.BC_NEUMANN, [0.0])
+            elif bc.bcType == "Convective":
+                ls.set_bc(fg.id, capi.BC_CONVECTIVE, [float(bc["convectiveCoefficient"]), float(bc["farFieldConcentration"])])
+            else:
+                raise CException(bc.bcType + " not implemented for VacancyModel")
+        return convecting
+
+    def advance(self, niter):
+        """Impl::advance, F/VacancyModel_impl.h:424-456"""
+        o = self._options
+        solver = o.getLinearSolver()
+        for mesh in self.meshes:
+            ls = self._systems[mesh.getID()]
+            cells = mesh.getCells()
+            convecting = self._upload(mesh, ls)
+            for _ in range(niter):
+                ls.lib.timer_start(1)
+                ls.assemble(diffusion=1, convection=(2 if o.useCentralDifference else 1) if convecting else 0, source=1,
+                            time_order=(o.timeDiscretizationOrder if o.transient else 0),
+                            dt=float(o["timeStep"]) if o.transient else 0.0, underrelax=0.0, apply_bcs=1,
+                            eliminate_boundary=1)
+                rnorm = solver.solve(ls)
+                if self._initialNorm is None:
+                    self._initialNorm = rnorm
+                ratio = rnorm / self._initialNorm if self._initialNorm != 0 else 0.0
+                print("%d: [%s : %g]" % (self._niters, self.fields.concentration.name, rnorm))
+                solver.cleanup()
+                ls.post_solve_update()
+                self.timings.append({"ms": ls.lib.timer_stop(1), "rnorm": rnorm})
+                self._niters += 1
+                if rnorm < o.absoluteTolerance or ratio < o.relativeTolerance:
+                    break
+            self.fields.concentration[cells][:] = ls.get_field(capi.FIELD_X)
+            bflux = ls.get_field(capi.FIELD_BFLUX)
+            for fg in mesh.getBoundaryFaceGroups():
+                off = fg.site.getOffset()
+                self.fields.vacaFlux[fg.site][:] = bflux[off:off + fg.site.getCount()]
+
+    def updateTime(self):  # F/VacancyModel_impl.h:472-494
+        f, o = self.fields, self._options
+        for mesh in self.meshes:
+            cells = mesh.getCells()
+            if o.timeDiscretizationOrder > 1:
+                f.concentrationN2[cells][:] = f.concentrationN1[cells]
+            f.concentrationN1[cells][:] = f.concentration[cells]
+
+    def getVacaFluxIntegral(self, mesh, faceGroupId):  # :400-421
+        for fg in mesh.getBoundaryFaceGroups():
+            if fg.id == faceGroupId:
+                return float(np.sum(self.fields.vacaFlux[fg.site]))
+        raise CException("getVacaFluxIntegral: invalid faceGroupID")
+
+    def computePlasticStrainRate(self):
+        raise CException("VacancyModelA: computePlasticStrainRate is not built")
+
+    def printBCs(self):  # :458-470
+        for gid in sorted(self._bcMap):
+            bc = self._bcMap[gid]
+            print("Face Group %d:" % gid)
+            print("    bc type " + bc.bcType)
+            for k in sorted(bc):
+                print("   %s %g" % (k, bc[k]))
+
+
 # ----------------------------------------------------------------------------- FlowModel (SIMPLE)
 class FlowBC(FloatVarDict):
     """F/FlowBC.h:9-21"""

@@ -55,6 +55,9 @@
 #include "ElectricFields.h"
 #include "ElectricModel.h"
 #include "ElectricModel_impl.h"
+#include "VacancyFields.h"
+#include "VacancyModel.h"
+#include "VacancyModel_impl.h"
 #include "SpeciesFields.h"
 #include "SpeciesModel.h"
 #include "SpeciesModel_impl.h"
@@ -66,6 +69,7 @@ template class ThermalModel<double>;
 template class FlowModel<double>;
 template class ElectricModel<double>;
 template class SpeciesModel<double>;
+template class VacancyModel<double>;
 
 typedef Vector<double, 3> Vec3;
 typedef Array<Vec3> Vec3Array;
@@ -175,6 +179,13 @@ static void copy_text(const std::string& s, char* out, int cap) {
   std::memcpy(out, s.data(), n);
   out[n] = 0;
 }
+
+struct RefVacancy {
+  RefMesh* m;
+  std::shared_ptr<VacancyFields> fields;
+  std::shared_ptr<VacancyModel<double>> model;
+  RefSolver solver;
+};
 
 struct RefSpecies {
   RefMesh* m;
@@ -439,6 +450,112 @@ int fvmref_mesh_geometry(void* h, double* faceArea, double* faceAreaMag, double*
     cellVolume[c] = cv[c];
     if (ibType) ibType[c] = ib[c];
   }
+  return 0;
+  CATCH(-1)
+}
+
+// ---------------------------------------------------------------- VacancyModel (F/VacancyModel.h:18-55)
+
+void* fvmref_vacancy_create(void* h) {
+  TRY RefMesh* rm = (RefMesh*)h;
+  RefVacancy* t = new RefVacancy;
+  t->m = rm;
+  t->fields.reset(new VacancyFields("vacancy"));
+  t->model.reset(new VacancyModel<double>(*rm->geom, *t->fields, rm->meshes));
+  return t;
+  CATCH(nullptr)
+}
+void fvmref_vacancy_free(void* h) { delete (RefVacancy*)h; }
+int fvmref_vacancy_set_bc(void* h, int id, const char* bcType, const char* var, double value) {
+  TRY RefVacancy* t = (RefVacancy*)h;
+  auto& bcMap = t->model->getBCMap();
+  if (bcMap.find(id) == bcMap.end()) throw CException("no such boundary id");
+  VacancyBC<double>& bc = *bcMap[id];
+  if (bcType && bcType[0]) bc.bcType = bcType;
+  if (var && var[0]) {
+    auto pos = bc.find(var);
+    if (pos == bc.end()) throw CException(std::string("unknown bc var ") + var);
+    pos->second.constant = value;
+  }
+  return 0;
+  CATCH(-1)
+}
+int fvmref_vacancy_set_vc(void* h, const char* var, double value) {
+  TRY RefVacancy* t = (RefVacancy*)h;
+  for (auto& kv : t->model->getVCMap()) {
+    auto pos = kv.second->find(var);
+    if (pos == kv.second->end()) throw CException(std::string("unknown vc var ") + var);
+    pos->second.constant = value;
+  }
+  return 0;
+  CATCH(-1)
+}
+int fvmref_vacancy_set_option(void* h, const char* name, double value) {
+  TRY RefVacancy* t = (RefVacancy*)h;
+  VacancyModelOptions<double>& o = t->model->getOptions();
+  std::string n(name);
+  if (n == "relativeTolerance") o.relativeTolerance = value;
+  else if (n == "absoluteTolerance") o.absoluteTolerance = value;
+  else if (n == "transient") o.transient = value != 0;
+  else if (n == "timeDiscretizationOrder") o.timeDiscretizationOrder = (int)value;
+  else if (n == "useCentralDifference") o.useCentralDifference = value != 0;
+  else {
+    auto pos = o.find(n);
+    if (pos == o.end()) throw CException("unknown option " + n);
+    pos->second.constant = value;
+  }
+  return 0;
+  CATCH(-1)
+}
+int fvmref_vacancy_set_solver(void* h, const SolverCfg* cfg) {
+  TRY RefVacancy* t = (RefVacancy*)h;
+  t->solver = make_solver(*cfg);
+  t->model->getOptions().linearSolver = t->solver.top;
+  return 0;
+  CATCH(-1)
+}
+int fvmref_vacancy_init(void* h) {
+  TRY((RefVacancy*)h)->model->init();
+  return 0;
+  CATCH(-1)
+}
+// name: concentration, diffusioncoefficient, source, specificVaca, concentrationN1, concentrationN2 (cells),
+//       convectionFlux (all faces)
+double* fvmref_vacancy_field(void* h, const char* name, int* len) {
+  TRY RefVacancy* t = (RefVacancy*)h;
+  Mesh& mesh = t->m->mesh();
+  const StorageSite& cells = mesh.getCells();
+  std::string n(name);
+  VacancyFields& vf = *t->fields;
+  ArrayBase* a = nullptr;
+  if (n == "concentration") a = &vf.concentration[cells];
+  else if (n == "diffusioncoefficient") a = &vf.diffusioncoefficient[cells];
+  else if (n == "source") a = &vf.source[cells];
+  else if (n == "specificVaca") a = &vf.specificVaca[cells];
+  else if (n == "concentrationN1") a = &vf.concentrationN1[cells];
+  else if (n == "concentrationN2") a = &vf.concentrationN2[cells];
+  else if (n == "convectionFlux") a = &vf.convectionFlux[mesh.getFaces()];
+  else throw CException("unknown field " + n);
+  if (len) *len = a->getDataSize() / (int)sizeof(double);
+  return (double*)a->getData();
+  CATCH(nullptr)
+}
+int fvmref_vacancy_advance(void* h, int niter, char* text, int textCap) {
+  TRY RefVacancy* t = (RefVacancy*)h;
+  CoutCapture cap;
+  t->model->advance(niter);
+  copy_text(cap.os.str(), text, textCap);
+  return 0;
+  CATCH(-1)
+}
+int fvmref_vacancy_update_time(void* h) {
+  TRY((RefVacancy*)h)->model->updateTime();
+  return 0;
+  CATCH(-1)
+}
+int fvmref_vacancy_flux_integral(void* h, int groupId, double* out) {
+  TRY RefVacancy* t = (RefVacancy*)h;
+  *out = t->model->getVacaFluxIntegral(t->m->mesh(), groupId);
   return 0;
   CATCH(-1)
 }

@@ -76,6 +76,19 @@ def lib():
         L.fvmref_mesh_cell_nodes.argtypes = [C.c_void_p, _ip, C.c_void_p]
         L.fvmref_mesh_node_coordinates.argtypes = [C.c_void_p, _dp]
         L.fvmref_mesh_geometry.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _ip]
+        L.fvmref_vacancy_create.restype = C.c_void_p
+        L.fvmref_vacancy_create.argtypes = [C.c_void_p]
+        L.fvmref_vacancy_free.argtypes = [C.c_void_p]
+        L.fvmref_vacancy_set_bc.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_double]
+        L.fvmref_vacancy_set_vc.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.fvmref_vacancy_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.fvmref_vacancy_set_solver.argtypes = [C.c_void_p, C.POINTER(SolverCfg)]
+        L.fvmref_vacancy_init.argtypes = [C.c_void_p]
+        L.fvmref_vacancy_field.restype = C.POINTER(C.c_double)
+        L.fvmref_vacancy_field.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
+        L.fvmref_vacancy_advance.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+        L.fvmref_vacancy_update_time.argtypes = [C.c_void_p]
+        L.fvmref_vacancy_flux_integral.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         L.fvmref_species_create.restype = C.c_void_p
         L.fvmref_species_create.argtypes = [C.c_void_p, C.c_int]
         L.fvmref_species_free.argtypes = [C.c_void_p]
@@ -317,6 +330,59 @@ class RefThermal:
     def close(self):
         if self.h:
             lib().fvmref_thermal_free(self.h)
+            self.h = None
+
+
+class RefVacancy:
+    """The reference `VacancyModel<double>` on a RefMesh (F/VacancyModel.h:18-55)."""
+
+    def __init__(self, mesh):
+        self.mesh = mesh
+        self.h = lib().fvmref_vacancy_create(mesh.h)
+        if not self.h:
+            raise RuntimeError("reference: " + lib().fvmref_last_error().decode())
+
+    def set_bc(self, gid, bc_type="", **vars_):
+        _check(lib().fvmref_vacancy_set_bc(self.h, gid, bc_type.encode(), b"", 0.0))
+        for k, v in vars_.items():
+            _check(lib().fvmref_vacancy_set_bc(self.h, gid, b"", k.encode(), float(v)))
+
+    def set_vc(self, name, value):
+        _check(lib().fvmref_vacancy_set_vc(self.h, name.encode(), float(value)))
+
+    def set_option(self, name, value):
+        _check(lib().fvmref_vacancy_set_option(self.h, name.encode(), float(value)))
+
+    def set_solver(self, cfg):
+        self._cfg = cfg
+        _check(lib().fvmref_vacancy_set_solver(self.h, C.byref(cfg)))
+
+    def init(self):
+        _check(lib().fvmref_vacancy_init(self.h))
+
+    def field(self, name):
+        n = C.c_int(0)
+        p = lib().fvmref_vacancy_field(self.h, name.encode(), C.byref(n))
+        if not p:
+            raise RuntimeError("reference: " + lib().fvmref_last_error().decode())
+        return np.ctypeslib.as_array(p, shape=(n.value,))
+
+    def advance(self, niter=1):
+        buf = C.create_string_buffer(1 << 16)
+        _check(lib().fvmref_vacancy_advance(self.h, niter, buf, len(buf)))
+        return buf.value.decode()
+
+    def update_time(self):
+        _check(lib().fvmref_vacancy_update_time(self.h))
+
+    def flux_integral(self, gid):
+        out = C.c_double(0)
+        _check(lib().fvmref_vacancy_flux_integral(self.h, gid, C.byref(out)))
+        return out.value
+
+    def close(self):
+        if self.h:
+            lib().fvmref_vacancy_free(self.h)
             self.h = None
 
 
