@@ -403,6 +403,66 @@ def main():
         dist.destroy_process_group()
         return
 
+    if solver_kind == "species":
+        # SpeciesModelA (two species: one diffusing with a source, one convected) with BDF2 on this rank's mesh part,
+        # three time steps; checked against the single-partition run of the same code, which tests/test_species.py
+        # pins to the reference's SpeciesModel
+        import contextlib
+        import io
+        from fvm_b200 import models as M
+
+        def run(mesh_raw, geo_raw):
+            mesh = M.Mesh(mesh_raw)
+            geomf = M.GeomFields("geom")
+            M.MeshMetricsCalculatorA(geomf, [mesh], lib=lib).init()
+            sm = M.SpeciesModelA(geomf, [mesh], 2, lib=lib)
+            for m in range(2):
+                bcm = sm.getBCMap(m)
+                for gid, bc in bcm.items():
+                    bc.bcType = "Symmetry"
+                if 5 in bcm:
+                    bcm[5].bcType = "SpecifiedMassFraction"; bcm[5]["specifiedMassFraction"] = 0.1 + m
+                if 6 in bcm:
+                    bcm[6].bcType = "SpecifiedMassFraction"; bcm[6]["specifiedMassFraction"] = 0.9 - 0.5 * m
+                if 1 in bcm:
+                    bcm[1].bcType = "SpecifiedMassFlux"; bcm[1]["specifiedMassFlux"] = 0.2
+                sm.getVCMap(m)[mesh.getID()]["massDiffusivity"] = 0.6 + m
+                sm.getVCMap(m)[mesh.getID()]["initialMassFraction"] = 0.5
+            o = sm.getOptions()
+            o.transient, o.timeDiscretizationOrder = True, 2
+            o["timeStep"] = 0.05
+            sv = M.AMG()
+            sv.relativeTolerance, sv.nMaxIterations, sv.verbosity = 1e-13, 3000, 0
+            o.linearSolver = sv
+            sm.init()
+            gids = mesh_raw.cell_global if "cell_global" in mesh_raw else np.arange(mesh_raw.n_total)
+            area = np.asarray(geomf.area[mesh.getFaces()])
+            sm.getSpeciesFields(1).convectionFlux[mesh.getFaces()][:] = area @ np.array([0.3, -0.2, 0.7])
+            sm.getSpeciesFields(0).source[mesh.getCells()][:] = np.where(gids >= 0, 1.0 + (np.maximum(gids, 0) % 5), 0.0)
+            for _ in range(3):
+                with contextlib.redirect_stdout(io.StringIO()):
+                    sm.advance(2)
+                sm.updateTime()
+            return [np.asarray(sm.getSpeciesFields(m).massFraction[mesh.getCells()]).copy() for m in range(2)]
+
+        lib.comm_destroy()
+        ref_x = run(raw, geo)
+        rejoin(lib, world, rank)
+        x = run(loc, loc.geometry)
+        own = loc.cell_global[:loc.n_cells]
+        num = sum(float(((x[m][:loc.n_cells] - ref_x[m][own]) ** 2).sum()) for m in range(2))
+        den = sum(float((ref_x[m][own] ** 2).sum()) for m in range(2))
+        t = torch.tensor([num, den])
+        dist.all_reduce(t)
+        out = dict(rank=rank, world=world, n_self=int(loc.n_cells), peers=[int(p) for p in loc.halo["peers"]],
+                   err_diag=0.0, err_b=0.0, rel_l2=float(np.sqrt(float(t[0]) / float(t[1]))), ghost_err=0.0,
+                   r0=1.0, r=0.0, iters=0, levels=[], collectives=lib.comm_collectives())
+        with open(os.path.join(os.environ["FVM_RESULT_DIR"], "rank%d.json" % rank), "w") as fh:
+            json.dump(out, fh)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
     if solver_kind == "model":
         # the public (reference-mirroring) Python API on this rank's mesh: same script as single rank
         import contextlib

@@ -156,3 +156,12 @@ def test_electric_bench_configuration_on_block_partitions(world):
         assert d["iface_flux_err"] <= 1e-12, d
     assert sum(d["n_iface"] for d in res) > 0
 
+
+
+
+@pytest.mark.parametrize("world,case", [(2, "tet_rcb"), (3, "hex_slabs")])
+def test_species_model_on_partitioned_meshes(world, case):
+    """SpeciesModelA on mesh parts: two species, convection + source + BDF2, three time steps, against
+    the single-partition run of the same model (which tests/test_species.py pins to the reference's SpeciesModel)."""
+    res = run_world(world, case, "species", 200)
+    check(res)
