@@ -275,7 +275,25 @@ class FluentCase:
         fc = np.array([[g2l[int(self._fc[f, 0])], g2l[int(self._fc[f, 1])]] for f in face_list], np.int32)
         counts = np.array([len(self._fn[f]) for f in face_list], np.int32)
         fnodes = np.concatenate([self._fn[f] for f in face_list]).astype(np.int32)
-        raw = meshgen._finish(self._dim, n_mesh_cells, self._coords, fc, fnodes, counts, sizes)
+        # Nodes of the mesh in the reference's order (I/FluentReader.cpp:841-856: cellNodes = cellFaces x faceNodes of the
+        # whole file, localized over the zone's cells): numbered as the zone's cells meet them, cell after cell, a cell's
+        # nodes in the order of its faces (file order) and of their stored node lists. Nodes no cell of the zone uses
+        # are dropped. (No kernel depends on it; the Tecplot dumps of the reference's test scripts do.)
+        faces_of = [[] for _ in range(cend + 1)]
+        for f in range(self._num_faces):
+            for c in self._fc[f]:
+                if cbeg <= c <= cend:
+                    faces_of[int(c)].append(f)
+        new_id = np.full(len(self._coords), -1, np.int64)
+        order = []
+        for c in range(cbeg, cend + 1):
+            for f in faces_of[c]:
+                for v in self._fn[f]:
+                    if new_id[v] < 0:
+                        new_id[v] = len(order)
+                        order.append(int(v))
+        fnodes = new_id[fnodes].astype(np.int32)
+        raw = meshgen._finish(self._dim, n_mesh_cells, self._coords[np.asarray(order, np.int64)], fc, fnodes, counts, sizes)
         raw.group_id = np.array(ids, np.int32)
         raw.group_types = types
         raw.group_kind = np.array([0] + [3 if t == "symmetry" else 1 for t in types[1:]], np.int32)

@@ -27,12 +27,11 @@ def test_cell_nodes_follow_the_reference_element_order(ref, name):
     assert len(set(np.diff(r))) == 1 and np.diff(r)[0] == {"quad": 4, "hex": 8, "tet": 4}[name]
 
 
-@pytest.mark.parametrize("cas", ["cav32.cas", "tri_894.cas", "cav_tetra.cas"])
+@pytest.mark.parametrize("cas", ["cav32.cas", "tri_894.cas", "cav_tetra.cas", "cav_hexa.cas"])
 def test_cell_nodes_of_the_reference_case_files(ref, cas):
-    """quadrilaterals, triangles and tetrahedra of the reference's own case files. The reference's reader renumbers the
-    nodes of a cell zone in the order its cells meet them (I/FluentReader.cpp:841-856), fvm_b200.importers keeps the
-    file's numbering (no kernel depends on it): the two connectivities are compared through the node COORDINATES, which
-    both read from the same file."""
+    """quadrilaterals, triangles and tetrahedra of the reference's own case files: fvm_b200.importers numbers the nodes
+    of the cell zone in the order its cells meet them, as the reference's reader does (I/FluentReader.cpp:841-856), so
+    node coordinates and cell -> node lists are identical arrays."""
     path = os.path.join(REF_TEST, cas)
     if not os.path.exists(path):
         pytest.skip("reference tree not present")
@@ -42,8 +41,8 @@ def test_cell_nodes_of_the_reference_case_files(ref, cas):
     rm = ref.RefMesh.from_cas(path)
     rr, rc = rm.cell_nodes()
     r, c = E.cell_nodes(raw)
-    assert np.array_equal(r, rr)
-    assert np.array_equal(np.asarray(raw.nodes).reshape(-1, 3)[c], rm.node_coordinates()[rc])
+    assert np.array_equal(r, rr) and np.array_equal(c, rc)
+    assert np.array_equal(np.asarray(raw.nodes).reshape(-1, 3), rm.node_coordinates())
 
 
 def test_tecplot_file_layout(hostsim_lib, tmp_path):
